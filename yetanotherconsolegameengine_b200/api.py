@@ -1,0 +1,463 @@
+"""ctypes bindings for the product libraries.
+
+* ``libycge.so``       — the C ABI of ``include/ycge.h`` (CUDA, sm_100a).  No CPU path: every call fails loudly
+                         (``YcgeError``) when no CUDA device is usable.
+* ``libycge_host.so``  — the C++ mirror of the reference's C# host side (scene factories of ``BuildSceneTable()``,
+                         ``MeshLoader``, ``Framebuffer``/``Chexel``, ``IConsoleRenderer``, ``ANSITerminalRenderer``).
+
+The Python classes below mirror the reference-facing names (``RaytraceEntity.IConsoleRenderer``: SetCamera / SetFov /
+TryFlipAndBlit / Resize, ConsoleGame/RaytraceEntity.cs:12-18) so that the parity tests read like calls into the
+reference.  Nothing in this module imports or calls the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libycge.so")
+HOST_LIB_PATH = os.path.join(_PKG_DIR, "libycge_host.so")
+
+
+class YcgeError(RuntimeError):
+    """Raised for any negative ycge_status (the reference throws InvalidOperationException / ArgumentException)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"ycge error {code}: {message}")
+        self.code = code
+
+
+# ---------------------------------------------------------------------------------------------- ABI structs (ycge.h)
+class Material(C.Structure):
+    _fields_ = [("albedo", C.c_float * 3), ("reflectivity", C.c_float), ("emission", C.c_float * 3), ("transparency", C.c_float),
+                ("transmission", C.c_float * 3), ("ior", C.c_float), ("specular", C.c_float), ("tex_id", C.c_int32),
+                ("tex_weight", C.c_float), ("uv_scale", C.c_float)]
+
+
+class Object(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("mat_a", C.c_int32), ("mat_b", C.c_int32), ("checker_scale", C.c_float), ("override_sr", C.c_int32),
+                ("specular", C.c_float), ("reflectivity", C.c_float), ("ref_id", C.c_int32), ("p", C.c_float * 12)]
+
+
+class Light(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("color", C.c_float * 3), ("intensity", C.c_float)]
+
+
+class Bvh(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("root", C.c_int32), ("n_leaf_refs", C.c_int32)] + \
+               [(n, C.POINTER(C.c_float)) for n in ("min_x", "min_y", "min_z", "max_x", "max_y", "max_z")] + \
+               [(n, C.POINTER(C.c_int32)) for n in ("left", "right", "start", "count", "leaf_index")]
+
+
+class Scene(C.Structure):
+    _fields_ = [("bg_top", C.c_float * 3), ("bg_bottom", C.c_float * 3), ("ambient_color", C.c_float * 3), ("ambient_intensity", C.c_float),
+                ("is_volume_scene", C.c_int32), ("n_lights", C.c_int32), ("lights", C.POINTER(Light)), ("n_materials", C.c_int32),
+                ("materials", C.POINTER(Material)), ("n_objects", C.c_int32), ("objects", C.POINTER(Object)), ("bvh", C.POINTER(Bvh))]
+
+
+class MeshSoa(C.Structure):
+    _fields_ = [("n_tris", C.c_int32)] + \
+               [(n, C.POINTER(C.c_float)) for n in ("ax", "ay", "az", "e1x", "e1y", "e1z", "e2x", "e2y", "e2z", "nx", "ny", "nz")] + \
+               [("material", Material), ("bvh", C.POINTER(Bvh))]
+
+
+class Volume(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("min_corner", C.c_float * 3), ("voxel_size", C.c_float * 3),
+                ("mat", C.POINTER(C.c_int32)), ("meta", C.POINTER(C.c_int32)), ("wireframe", C.c_int32), ("wire_width_frac", C.c_float),
+                ("wire_max_distance", C.c_float), ("palette_n_ids", C.c_int32), ("palette_meta_levels", C.c_int32),
+                ("palette", C.POINTER(C.c_int32)), ("palette_default", C.c_int32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("diffuse_bounces", C.c_int32), ("max_mirror_bounces", C.c_int32), ("max_refractions", C.c_int32), ("atrous_iterations", C.c_int32),
+                ("mirror_threshold", C.c_float), ("eps", C.c_float), ("taa_alpha", C.c_float), ("motion_trans_reset", C.c_float),
+                ("motion_rot_reset", C.c_float), ("diffuse_sigma_deg", C.c_float), ("luminance_pad", C.c_float),
+                ("c_phi", C.c_float), ("n_phi", C.c_float), ("z_phi", C.c_float), ("a_phi", C.c_float),
+                ("tone_exposure", C.c_float), ("tone_gamma", C.c_float), ("ae_key", C.c_float), ("ae_speed", C.c_float), ("ae_min", C.c_float),
+                ("ae_max", C.c_float), ("saturation", C.c_float), ("vibrance", C.c_float), ("auto_exposure", C.c_int32), ("seed_salt", C.c_uint64)]
+
+
+class Config(C.Structure):
+    _fields_ = [("fb_w", C.c_int32), ("fb_h", C.c_int32), ("ss", C.c_int32), ("device", C.c_int32), ("tile_row0", C.c_int32),
+                ("tile_rows", C.c_int32), ("params", Params)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("rays", C.c_uint64), ("top_nodes_popped", C.c_uint64), ("mesh_nodes_popped", C.c_uint64),
+                ("leaf_refs", C.c_uint64), ("tris_tested", C.c_uint64), ("prims_tested", C.c_uint64), ("dda_cells", C.c_uint64),
+                ("ms_trace", C.c_float), ("ms_taa", C.c_float), ("ms_atrous", C.c_float), ("ms_exposure", C.c_float), ("ms_cells", C.c_float),
+                ("ms_total", C.c_float), ("ae_exposure", C.c_float), ("log_sum", C.c_float), ("log_cnt", C.c_int32), ("kernel_launches", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+CELL_DTYPE = np.dtype([("glyph", "<u2"), ("fg16", "u1"), ("bg16", "u1"), ("fg_ansi", "u1"), ("bg_ansi", "u1"), ("attr", "<u2"),
+                       ("fg", "<f4", (3,)), ("bg", "<f4", (3,))])
+assert CELL_DTYPE.itemsize == 32
+
+DBG_RAYS, DBG_HDR, DBG_ALBEDO_SKY, DBG_NORMAL_DEPTH, DBG_TAA, DBG_DENOISED, DBG_PRIM_ID, DBG_LOG_SAMPLES = range(8)
+PTR_CELLS, PTR_LOG_SAMPLES = 0, 1
+
+# every symbol include/ycge.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
+    "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
+    "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
+    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_frame_begin", "ycge_frame_finish", "ycge_device_ptr",
+    "ycge_set_stream", "ycge_debug_read", "ycge_get_stats", "ycge_get_frame_counter", "ycge_rng_kat",
+]
+
+_lib = None
+_host = None
+
+
+def load_lib() -> C.CDLL:
+    """Load libycge.so.  Raises (never falls back) if the extension was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback for the ray tracing path)")
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        vp = C.c_void_p
+        lib.ycge_last_error.restype = C.c_char_p
+        lib.ycge_last_error.argtypes = [vp]
+        lib.ycge_default_params.argtypes = [C.POINTER(Params)]
+        lib.ycge_default_params.restype = None
+        lib.ycge_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        lib.ycge_destroy.argtypes = [vp]
+        lib.ycge_destroy.restype = None
+        lib.ycge_resize.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+        lib.ycge_mesh_upload_soa.argtypes = [vp, C.c_int32, vp]
+        lib.ycge_mesh_upload_triangles.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+        lib.ycge_volume_upload.argtypes = [vp, C.c_int32, vp]
+        lib.ycge_scene_upload.argtypes = [vp, vp]
+        lib.ycge_lights_update.argtypes = [vp, C.c_int32, vp]
+        lib.ycge_globals_update.argtypes = [vp, vp, vp, vp, C.c_float]
+        lib.ycge_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
+        lib.ycge_set_fov.argtypes = [vp, C.c_float]
+        lib.ycge_reset_history.argtypes = [vp]
+        lib.ycge_render_frame.argtypes = [vp, vp, C.c_int32]
+        lib.ycge_render_frame_stats.argtypes = [vp, vp, C.c_int32]
+        lib.ycge_render_frames_async.argtypes = [vp, C.c_int32]
+        lib.ycge_wait.argtypes = [vp]
+        lib.ycge_read_cells.argtypes = [vp, vp, C.c_int32]
+        lib.ycge_frame_begin.argtypes = [vp]
+        lib.ycge_frame_finish.argtypes = [vp]
+        lib.ycge_device_ptr.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        lib.ycge_set_stream.argtypes = [vp, vp]
+        lib.ycge_debug_read.argtypes = [vp, C.c_int32, vp, C.c_size_t]
+        lib.ycge_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        lib.ycge_get_frame_counter.argtypes = [vp, C.POINTER(C.c_int64)]
+        lib.ycge_rng_kat.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp]
+        _lib = lib
+    return _lib
+
+
+def load_host() -> C.CDLL:
+    global _host
+    if _host is None:
+        load_lib()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise ImportError(f"{HOST_LIB_PATH} is missing: run __graft_entry__.build()")
+        h = C.CDLL(HOST_LIB_PATH)
+        vp = C.c_void_p
+        h.ycgeh_last_error.restype = C.c_char_p
+        h.ycgeh_set_asset_dir.argtypes = [C.c_char_p]
+        h.ycgeh_set_asset_dir.restype = None
+        h.ycgeh_scene_create.argtypes = [C.c_char_p]
+        h.ycgeh_scene_create.restype = vp
+        h.ycgeh_scene_from_triangles.argtypes = [C.c_char_p, C.c_int, vp, C.c_int, vp]
+        h.ycgeh_scene_from_triangles.restype = vp
+        h.ycgeh_scene_destroy.argtypes = [vp]
+        h.ycgeh_scene_destroy.restype = None
+        h.ycgeh_scene_flat.argtypes = [vp]
+        h.ycgeh_scene_flat.restype = C.POINTER(Scene)
+        h.ycgeh_scene_n_meshes.argtypes = [vp]
+        h.ycgeh_scene_mesh.argtypes = [vp, C.c_int]
+        h.ycgeh_scene_mesh.restype = C.POINTER(MeshSoa)
+        h.ycgeh_scene_n_volumes.argtypes = [vp]
+        h.ycgeh_scene_volume.argtypes = [vp, C.c_int]
+        h.ycgeh_scene_volume.restype = C.POINTER(Volume)
+        h.ycgeh_scene_mesh_triangles.argtypes = [vp, C.c_int]
+        h.ycgeh_scene_mesh_triangles.restype = C.POINTER(C.c_float)
+        h.ycgeh_scene_camera.argtypes = [vp, vp, vp, vp, vp]
+        h.ycgeh_scene_camera.restype = None
+        h.ycgeh_scene_name.argtypes = [vp]
+        h.ycgeh_scene_name.restype = C.c_char_p
+        h.ycgeh_scene_counts.argtypes = [vp, vp, vp, vp, vp, vp]
+        h.ycgeh_scene_bvh.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(Bvh)), C.POINTER(C.c_uint64)]
+        h.ycgeh_renderer_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        h.ycgeh_renderer_create.restype = vp
+        h.ycgeh_renderer_destroy.argtypes = [vp]
+        h.ycgeh_renderer_destroy.restype = None
+        h.ycgeh_renderer_ctx.argtypes = [vp]
+        h.ycgeh_renderer_ctx.restype = vp
+        h.ycgeh_renderer_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
+        h.ycgeh_renderer_set_fov.argtypes = [vp, C.c_float]
+        h.ycgeh_renderer_resize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        h.ycgeh_renderer_render_cells.argtypes = [vp, vp]
+        h.ycgeh_renderer_blit_ansi.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint8))]
+        h.ycgeh_renderer_blit_ansi.restype = C.c_int64
+        h.ycgeh_renderer_charinfo.argtypes = [vp, vp]
+        h.ycgeh_ansi_from_cells.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64]
+        h.ycgeh_ansi_from_cells.restype = C.c_int64
+        h.ycgeh_synthetic_height.argtypes = [C.c_int, C.c_int, C.c_int]
+        h.ycgeh_synthetic_height.restype = C.c_float
+        _host = h
+    return _host
+
+
+def default_params() -> Params:
+    p = Params()
+    load_lib().ycge_default_params(C.byref(p))
+    return p
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+# ---------------------------------------------------------------------------------------------- host-side scene
+BENCH_POSE = ((0.0, 0.9, -1.4), float(np.float32(np.pi)), -0.15)  # default mesh poses look away from the mesh
+
+
+class HostScene:
+    """A scene built by the host mirror (the reference's BuildSceneTable() factories), flattened for the C ABI."""
+
+    def __init__(self, name: str, asset_dir: Optional[str] = None):
+        self._h = load_host()
+        if asset_dir is None:
+            asset_dir = os.environ.get("YCGE_ASSETS", os.path.join(os.path.dirname(_PKG_DIR), "assets"))
+        self._h.ycgeh_set_asset_dir(asset_dir.encode())
+        self.handle = self._h.ycgeh_scene_create(name.encode())
+        if not self.handle:
+            raise ValueError(self._h.ycgeh_last_error().decode())
+        self.name = self._h.ycgeh_scene_name(self.handle).decode()
+
+    @classmethod
+    def from_triangles(cls, name: str, verts: np.ndarray, faces: np.ndarray) -> "HostScene":
+        self = cls.__new__(cls)
+        self._h = load_host()
+        v = np.ascontiguousarray(verts, np.float32)
+        f = np.ascontiguousarray(faces, np.int32)
+        self.handle = self._h.ycgeh_scene_from_triangles(name.encode(), len(v), _ptr(v), len(f), _ptr(f))
+        if not self.handle:
+            raise ValueError(self._h.ycgeh_last_error().decode())
+        self.name = name
+        return self
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._h.ycgeh_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def flat(self):
+        return self._h.ycgeh_scene_flat(self.handle)
+
+    @property
+    def n_meshes(self) -> int:
+        return self._h.ycgeh_scene_n_meshes(self.handle)
+
+    @property
+    def n_volumes(self) -> int:
+        return self._h.ycgeh_scene_n_volumes(self.handle)
+
+    def mesh(self, i):
+        return self._h.ycgeh_scene_mesh(self.handle, i)
+
+    def mesh_triangles(self, i) -> np.ndarray:
+        n = self.mesh(i).contents.n_tris
+        p = self._h.ycgeh_scene_mesh_triangles(self.handle, i)
+        return np.ctypeslib.as_array(p, shape=(n, 9)).copy()
+
+    def volume(self, i):
+        return self._h.ycgeh_scene_volume(self.handle, i)
+
+    def default_camera(self):
+        pos = (C.c_float * 3)()
+        yaw, pitch, fov = C.c_float(), C.c_float(), C.c_float()
+        self._h.ycgeh_scene_camera(self.handle, pos, C.byref(yaw), C.byref(pitch), C.byref(fov))
+        return (pos[0], pos[1], pos[2]), yaw.value, pitch.value, fov.value
+
+    def counts(self):
+        no, nl, nm = C.c_int(), C.c_int(), C.c_int()
+        nt, nv = C.c_int64(), C.c_int64()
+        self._h.ycgeh_scene_counts(self.handle, C.byref(no), C.byref(nl), C.byref(nm), C.byref(nt), C.byref(nv))
+        return dict(objects=no.value, lights=nl.value, materials=nm.value, triangles=nt.value, voxels=nv.value)
+
+    def bvh_arrays(self, which: int = -1):
+        """The host-built tree (top level: which=-1, else mesh index) as numpy arrays."""
+        pb = C.POINTER(Bvh)()
+        sf = C.c_uint64()
+        if self._h.ycgeh_scene_bvh(self.handle, which, C.byref(pb), C.byref(sf)) != 0:
+            raise IndexError(which)
+        b = pb.contents
+        n = b.n_nodes
+        boxes = np.stack([np.ctypeslib.as_array(getattr(b, k), shape=(n,)) for k in ("min_x", "min_y", "min_z", "max_x", "max_y", "max_z")], 1).copy() if n else np.zeros((0, 6), np.float32)
+        lrsc = np.stack([np.ctypeslib.as_array(getattr(b, k), shape=(n,)) for k in ("left", "right", "start", "count")], 1).copy() if n else np.zeros((0, 4), np.int32)
+        leaf = np.ctypeslib.as_array(b.leaf_index, shape=(b.n_leaf_refs,)).copy() if b.n_leaf_refs else np.zeros((0,), np.int32)
+        return dict(root=b.root, boxes=boxes, lrsc=lrsc, leaf=leaf, sort_fallbacks=sf.value)
+
+
+# ---------------------------------------------------------------------------------------------- the drop-in renderer
+class CudaRaytraceRenderer:
+    """Mirror of RaytraceRenderer's public surface (RaytraceRenderer.cs:74,110,140,150,157) behind IConsoleRenderer,
+    producing frames through libycge.so.  ``tile_row0/tile_rows`` select a row tile for one-process-per-GPU sharding."""
+
+    def __init__(self, scene: HostScene, fb_w: int, fb_h: int, super_sample: int = 1, device: int = 0, tile_row0: int = 0, tile_rows: int = 0):
+        self._h = load_host()
+        self._lib = load_lib()
+        self.scene = scene
+        self.fb_w, self.fb_h, self.ss = fb_w, fb_h, max(1, super_sample)
+        self.tile_row0 = tile_row0
+        self.tile_rows = tile_rows if tile_rows > 0 else fb_h - tile_row0
+        self.handle = self._h.ycgeh_renderer_create(scene.handle, fb_w, fb_h, self.ss, device, tile_row0, tile_rows)
+        if not self.handle:
+            raise YcgeError(-2, self._h.ycgeh_last_error().decode())
+        self.ctx = C.c_void_p(self._h.ycgeh_renderer_ctx(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._h.ycgeh_renderer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- IConsoleRenderer --
+    def SetCamera(self, pos, yaw: float, pitch: float):
+        p = (C.c_float * 3)(*pos)
+        if self._h.ycgeh_renderer_set_camera(self.handle, p, yaw, pitch) != 0:
+            raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+
+    def SetFov(self, fov_deg: float):
+        if self._h.ycgeh_renderer_set_fov(self.handle, fov_deg) != 0:
+            raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+
+    def Resize(self, fb_w: int, fb_h: int, super_sample: int):
+        if self._h.ycgeh_renderer_resize(self.handle, fb_w, fb_h, super_sample) != 0:
+            raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+        self.fb_w, self.fb_h, self.ss = fb_w, fb_h, max(1, super_sample)
+        self.tile_row0, self.tile_rows = 0, fb_h
+
+    def TryFlipAndBlit(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Synchronous frame: returns the (tile_rows, fb_w) cell array (the Framebuffer's Chexels)."""
+        if out is None:
+            out = np.empty((self.tile_rows, self.fb_w), CELL_DTYPE)
+        if self._h.ycgeh_renderer_render_cells(self.handle, _ptr(out)) != 0:
+            raise YcgeError(-2, self._h.ycgeh_last_error().decode())
+        return out
+
+    def blit_ansi(self) -> bytes:
+        """TryFlipAndBlit into the host Framebuffer, then ANSITerminalRenderer.Render's byte stream."""
+        p = C.POINTER(C.c_uint8)()
+        n = self._h.ycgeh_renderer_blit_ansi(self.handle, C.byref(p))
+        if n < 0:
+            raise YcgeError(-2, self._h.ycgeh_last_error().decode())
+        return C.string_at(p, n)
+
+    # -- C-ABI passthroughs used by tests / bench --
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise YcgeError(rc, (self._lib.ycge_last_error(self.ctx) or b"").decode())
+
+    def reset_history(self):
+        self._ck(self._lib.ycge_reset_history(self.ctx))
+
+    def render_frame_stats(self) -> np.ndarray:
+        out = np.empty((self.tile_rows, self.fb_w), CELL_DTYPE)
+        self._ck(self._lib.ycge_render_frame_stats(self.ctx, _ptr(out), 0))
+        return out
+
+    def render_frames_async(self, n: int):
+        self._ck(self._lib.ycge_render_frames_async(self.ctx, n))
+
+    def wait(self):
+        self._ck(self._lib.ycge_wait(self.ctx))
+
+    def read_cells(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.tile_rows, self.fb_w), CELL_DTYPE)
+        self._ck(self._lib.ycge_read_cells(self.ctx, _ptr(out), 0))
+        return out
+
+    def frame_begin(self):
+        self._ck(self._lib.ycge_frame_begin(self.ctx))
+
+    def frame_finish(self):
+        self._ck(self._lib.ycge_frame_finish(self.ctx))
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._lib.ycge_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+
+    def device_ptr(self, kind: int):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.ycge_device_ptr(self.ctx, kind, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self._lib.ycge_get_stats(self.ctx, C.byref(s)))
+        return s.as_dict()
+
+    @property
+    def hi_w(self):
+        return self.fb_w * self.ss
+
+    @property
+    def hi_h(self):
+        return self.fb_h * 2 * self.ss
+
+    def debug_read(self, kind: int) -> np.ndarray:
+        n = self.hi_w * self.hi_h
+        if kind == DBG_RAYS:
+            a = np.empty((self.hi_h, self.hi_w, 6), np.float32)
+        elif kind == DBG_PRIM_ID:
+            a = np.empty((self.hi_h, self.hi_w, 2), np.int32)
+        elif kind == DBG_LOG_SAMPLES:
+            step = max(2, self.ss * 2)
+            a = np.empty(((self.hi_h + step - 1) // step, (self.hi_w + step - 1) // step), np.float32)
+        else:
+            a = np.empty((self.hi_h, self.hi_w, 4), np.float32)
+        rc = self._lib.ycge_debug_read(self.ctx, kind, _ptr(a), a.nbytes)
+        if rc != 0 and kind == DBG_RAYS:  # first call only arms the tap
+            return None
+        self._ck(rc)
+        return a
+
+    def rng_kat(self, which: int, xs, ys, frames, n_draws: int):
+        x = np.ascontiguousarray(xs, np.int32)
+        y = np.ascontiguousarray(ys, np.int32)
+        f = np.ascontiguousarray(frames, np.int64)
+        bits = np.empty((len(x), n_draws), np.uint32)
+        seeds = np.empty(len(x), np.uint64)
+        self._ck(self._lib.ycge_rng_kat(self.ctx, which, len(x), _ptr(x), _ptr(y), _ptr(f), n_draws, _ptr(bits), _ptr(seeds)))
+        return bits, seeds
+
+
+def ansi_from_cells(cells: np.ndarray) -> bytes:
+    """ANSITerminalRenderer.Render's byte stream (ANSITerminalRenderer.cs:86-153) for a cell array (host-side C++)."""
+    h = load_host()
+    cells = np.ascontiguousarray(cells)
+    fb_h, fb_w = cells.shape
+    cap = 64 + fb_w * fb_h * 32
+    buf = np.empty(cap, np.uint8)
+    n = h.ycgeh_ansi_from_cells(_ptr(cells), fb_w, fb_h, _ptr(buf), cap)
+    if n < 0:
+        raise YcgeError(-1, "ANSI buffer too small")
+    return buf[:n].tobytes()

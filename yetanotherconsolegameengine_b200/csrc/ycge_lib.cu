@@ -1,0 +1,922 @@
+// ycge_lib.cu — the C ABI of include/ycge.h: context, scene flattening into HBM, per-frame launch sequence.
+// Product code: no CPU fallback.  Every entry point fails loudly (negative status + message) when CUDA is not usable.
+#include "post.cuh"
+#include "bvh_build.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace ycge;
+
+namespace {
+
+thread_local std::string tl_error;
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t s) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        e = cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(s);
+    }
+};
+
+struct MeshStore {
+    DevBuf<PairNode> nodes;
+    DevBuf<DevTri> tris;
+    DevBuf<int> tri_id;
+    TreeRoot root;
+    ycge_material material;
+    int n_tris = 0;
+};
+struct VolumeStore {
+    DevBuf<uint8_t> vox;
+    DevBuf<int> raw_mat, raw_meta; // kept until the scene (and so the material indices) is known
+    std::vector<int> palette;
+    int n_ids = 0, levels = 1, def = 0;
+    bool packed = false;
+    DevVolume dv;
+};
+
+} // namespace
+
+struct ycge_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    ycge_params P;
+    int fbW = 0, fbH = 0, ss = 1, W = 0, H = 0;
+    int tile_row0 = 0, tile_rows = 0;
+    bool sharded = false;
+
+    // image planes
+    DevBuf<float4> cur, gnd0, gnd1, gas0, gas1, hist, sa, sb;
+    DevBuf<int2> prim;
+    DevBuf<float> rays_dbg;
+    DevBuf<float> logs;
+    DevBuf<int> progress;
+    DevBuf<ExposureState> expo;
+    DevBuf<ycge_cell> cells;
+    DevBuf<TraceCounters> counters;
+    int sw = 0, sh = 0;
+    const float4 *denoised = nullptr;
+
+    // scene
+    std::map<int, std::unique_ptr<MeshStore>> meshes;
+    std::map<int, std::unique_ptr<VolumeStore>> volumes;
+    DevBuf<PairNode> s_nodes;
+    DevBuf<int> s_leaf;
+    DevBuf<DevObject> s_objects;
+    DevBuf<float4> s_materials;
+    DevBuf<DevMesh> s_meshes;
+    DevBuf<DevVolume> s_volumes;
+    DevBuf<DevLight> s_lights;
+    DevScene ds;
+    bool have_scene = false;
+
+    // renderer state (RaytraceRenderer.cs:24-29,69; TemporalAA.cs:12-16; ToneMapper.cs:13)
+    long long frame_counter = 0;
+    float cam[3] = {0.0f, 1.0f, 0.0f};
+    float yaw = 0.0f, pitch = 0.0f, fov = 45.0f;
+    float last_cam[3] = {NAN, NAN, NAN}, last_yaw = NAN, last_pitch = NAN;
+    bool taa_valid = false, force_reset = false;
+    float snap_cam[3] = {0, 0, 0}, snap_yaw = 0, snap_pitch = 0; // snapshot of the frame in flight
+    bool frame_open = false;
+    bool want_stats = false;
+    bool debug_rays = false;
+    float ansi_th[5] = {0, 0, 0, 0, 0};
+    int inplace_rows_per_launch = 0;
+
+    // timing
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int launches_last = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(ycge_ctx *ctx, int code, const std::string &msg) {
+    tl_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, YCGE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+// ---- reference SoA tree -> pair nodes (device_types.h) ------------------------------------------------------
+struct TreeView {
+    int n_nodes, root, n_leaf;
+    const float *min_x, *min_y, *min_z, *max_x, *max_y, *max_z;
+    const int32_t *left, *right, *start, *count, *leaf;
+};
+TreeView view_of(const FlatTree &t) {
+    return TreeView{t.n_nodes(), t.root, (int)t.leaf_index.size(), t.min_x.data(), t.min_y.data(), t.min_z.data(), t.max_x.data(), t.max_y.data(), t.max_z.data(),
+                    t.left.data(), t.right.data(), t.start.data(), t.count.data(), t.leaf_index.data()};
+}
+TreeView view_of(const ycge_bvh &b) {
+    return TreeView{b.n_nodes, b.root, b.n_leaf_refs, b.min_x, b.min_y, b.min_z, b.max_x, b.max_y, b.max_z, b.left, b.right, b.start, b.count, b.leaf_index};
+}
+int flatten(ycge_ctx *ctx, const TreeView &t, std::vector<PairNode> &out, TreeRoot &root) {
+    out.clear();
+    memset(&root, 0, sizeof root);
+    root.ref = YCGE_REF_NONE;
+    if (t.root < 0 || t.n_nodes == 0) return 0;
+    std::vector<int> pair_of(t.n_nodes, -1);
+    int n_pairs = 0;
+    for (int i = 0; i < t.n_nodes; i++) if (t.count[i] <= 0) pair_of[i] = n_pairs++;
+    auto ref_of = [&](int i, int &ref) -> bool {
+        if (i < 0) { ref = YCGE_REF_NONE; return true; }
+        if (i >= t.n_nodes) return false;
+        if (t.count[i] > 0) {
+            if (t.count[i] > YCGE_LEAF_MAX_COUNT || t.start[i] < 0 || t.start[i] >= YCGE_LEAF_MAX_START || t.start[i] + t.count[i] > t.n_leaf) return false;
+            ref = ~(((t.count[i] - 1) << 26) | t.start[i]);
+        } else ref = pair_of[i];
+        return true;
+    };
+    out.resize(n_pairs);
+    for (int i = 0; i < t.n_nodes; i++) {
+        if (t.count[i] > 0) continue;
+        int l = t.left[i], r = t.right[i], lref, rref;
+        if (!ref_of(l, lref) || !ref_of(r, rref)) return fail(ctx, YCGE_ERR_LIMIT, "BVH node out of range or leaf larger than 32 primitives");
+        float lb[6] = {0, 0, 0, 0, 0, 0}, rb[6] = {0, 0, 0, 0, 0, 0};
+        if (l >= 0) { lb[0] = t.min_x[l]; lb[1] = t.min_y[l]; lb[2] = t.min_z[l]; lb[3] = t.max_x[l]; lb[4] = t.max_y[l]; lb[5] = t.max_z[l]; }
+        if (r >= 0) { rb[0] = t.min_x[r]; rb[1] = t.min_y[r]; rb[2] = t.min_z[r]; rb[3] = t.max_x[r]; rb[4] = t.max_y[r]; rb[5] = t.max_z[r]; }
+        PairNode pn;
+        pn.q0 = make_float4(lb[0], lb[1], lb[2], lb[3]);
+        pn.q1 = make_float4(lb[4], lb[5], rb[0], rb[1]);
+        pn.q2 = make_float4(rb[2], rb[3], rb[4], rb[5]);
+        int zero = 0;
+        float lf, rf, zf;
+        memcpy(&lf, &lref, 4); memcpy(&rf, &rref, 4); memcpy(&zf, &zero, 4);
+        pn.q3 = make_float4(lf, rf, zf, zf);
+        out[pair_of[i]] = pn;
+    }
+    int rr;
+    if (!ref_of(t.root, rr)) return fail(ctx, YCGE_ERR_LIMIT, "BVH root out of range");
+    root.ref = rr;
+    root.lo[0] = t.min_x[t.root]; root.lo[1] = t.min_y[t.root]; root.lo[2] = t.min_z[t.root];
+    root.hi[0] = t.max_x[t.root]; root.hi[1] = t.max_y[t.root]; root.hi[2] = t.max_z[t.root];
+    return 0;
+}
+
+// ---- ANSI thresholds: smallest binary32 c in [0,1] with LinearToSrgb8((double)c) >= bound --------------------
+int linear_to_srgb8(double c) { // ANSITerminalRenderer.cs:298-307
+    if (c < 0.0) c = 0.0;
+    if (c > 1.0) c = 1.0;
+    double s = c <= 0.0031308 ? 12.92 * c : 1.055 * std::pow(c, 1.0 / 2.4) - 0.055;
+    int v = (int)std::nearbyint(s * 255.0);
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+float ansi_threshold(int bound) {
+    uint32_t lo = 0, hi = 0x3F800000u; // f(lo) < bound <= f(hi)
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        float c;
+        memcpy(&c, &mid, 4);
+        if (linear_to_srgb8((double)c) >= bound) hi = mid; else lo = mid;
+    }
+    float c;
+    memcpy(&c, &hi, 4);
+    return c;
+}
+
+int alloc_planes(ycge_ctx *c) {
+    size_t n = (size_t)c->W * c->H;
+    CK(c, c->cur.alloc(n)); CK(c, c->gnd0.alloc(n)); CK(c, c->gnd1.alloc(n)); CK(c, c->gas0.alloc(n)); CK(c, c->gas1.alloc(n));
+    CK(c, c->hist.alloc(n)); CK(c, c->sa.alloc(n)); CK(c, c->sb.alloc(n)); CK(c, c->prim.alloc(n));
+    int step = std::max(2, c->ss * 2);
+    c->sw = (c->W + step - 1) / step;
+    c->sh = (c->H + step - 1) / step;
+    CK(c, c->logs.alloc((size_t)c->sw * c->sh));
+    CK(c, c->progress.alloc((size_t)c->H * 8));
+    CK(c, c->cells.alloc((size_t)c->fbW * c->tile_rows));
+    CK(c, cudaMemsetAsync(c->cur.p, 0, n * sizeof(float4), c->stream));
+    CK(c, cudaMemsetAsync(c->hist.p, 0, n * sizeof(float4), c->stream));
+    CK(c, cudaMemsetAsync(c->sa.p, 0, n * sizeof(float4), c->stream));
+    CK(c, cudaMemsetAsync(c->sb.p, 0, n * sizeof(float4), c->stream));
+    CK(c, cudaMemsetAsync(c->gnd0.p, 0, n * sizeof(float4), c->stream)); CK(c, cudaMemsetAsync(c->gnd1.p, 0, n * sizeof(float4), c->stream));
+    CK(c, cudaMemsetAsync(c->gas0.p, 0, n * sizeof(float4), c->stream)); CK(c, cudaMemsetAsync(c->gas1.p, 0, n * sizeof(float4), c->stream));
+    CK(c, cudaMemsetAsync(c->logs.p, 0, c->logs.n * sizeof(float), c->stream));
+    CK(c, cudaMemsetAsync(c->cells.p, 0, c->cells.n * sizeof(ycge_cell), c->stream));
+    c->taa_valid = false;
+    c->denoised = nullptr;
+    return 0;
+}
+
+int set_geometry(ycge_ctx *c, int fb_w, int fb_h, int ss, int tile_row0, int tile_rows) {
+    if (fb_w <= 0 || fb_h <= 0) return fail(c, YCGE_ERR_INVALID, "framebuffer size must be positive");
+    c->fbW = fb_w; c->fbH = fb_h; c->ss = ss < 1 ? 1 : ss;
+    c->W = c->fbW * c->ss; c->H = c->fbH * 2 * c->ss;
+    if (tile_row0 < 0 || tile_row0 >= fb_h) return fail(c, YCGE_ERR_INVALID, "tile_row0 out of range");
+    if (tile_rows <= 0) tile_rows = fb_h - tile_row0;
+    if (tile_row0 + tile_rows > fb_h) return fail(c, YCGE_ERR_INVALID, "tile exceeds framebuffer");
+    c->tile_row0 = tile_row0; c->tile_rows = tile_rows;
+    c->sharded = !(tile_row0 == 0 && tile_rows == fb_h);
+    return alloc_planes(c);
+}
+
+void normalize3(float v[3]) { // Vec3.Normalized
+    float l2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    if (l2 <= 0.0f) return;
+    float inv = 1.0f / std::sqrt(l2);
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+}
+void cross3h(const float a[3], const float b[3], float o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+float fracf_h(float v) { return v - std::floor(v); }
+
+bool should_reset_history(const ycge_ctx *c) { // TemporalAA.cs:58-67
+    float dx = c->snap_cam[0] - c->last_cam[0], dy = c->snap_cam[1] - c->last_cam[1], dz = c->snap_cam[2] - c->last_cam[2];
+    float trans = (dx != dx) ? 0.0f : std::sqrt(dx * dx + dy * dy + dz * dz);
+    float dyaw = (c->last_yaw != c->last_yaw) ? 0.0f : std::fabs(c->snap_yaw - c->last_yaw);
+    float dpitch = (c->last_pitch != c->last_pitch) ? 0.0f : std::fabs(c->snap_pitch - c->last_pitch);
+    float tr = c->P.motion_trans_reset > 0.0f ? c->P.motion_trans_reset : 0.0f;
+    float rr = c->P.motion_rot_reset > 0.0f ? c->P.motion_rot_reset : 0.0f;
+    return trans > tr || dyaw > rr || dpitch > rr;
+}
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- the per-frame launch sequence ----------------------------------------------------------------------------
+int frame_begin_impl(ycge_ctx *c) {
+    if (!c->have_scene) return fail(c, YCGE_ERR_NO_SCENE, "Scene BVH not built; call ycge_scene_upload() after populating the scene");
+    if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_begin called twice without ycge_frame_finish");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int W = c->W, H = c->H, ss = c->ss;
+    // camera snapshot (:161-169) and history decision (:171)
+    memcpy(c->snap_cam, c->cam, sizeof c->cam); c->snap_yaw = c->yaw; c->snap_pitch = c->pitch;
+    bool reset = should_reset_history(c) || c->force_reset || !c->taa_valid;
+    c->force_reset = false;
+    long long frame = ++c->frame_counter;                                   // :175
+    int frameIdx = (int)(frame & 0x7fffffff);                              // :177
+    FrameConsts fc;
+    fc.jitter_rot_x = fracf_h((float)(frameIdx + 1) * 0.61803398875f);     // :178
+    fc.jitter_rot_y = fracf_h((float)(frameIdx + 1) * 0.38196601125f);     // :179
+    fc.rot0 = fracf_h((float)(frameIdx + 1) * 0.7548776662466927f);        // RaytraceSampler.cs:32
+    fc.rot1 = fracf_h((float)(frameIdx + 1) * 0.5698402909980532f);
+    float aspect = (float)W / (float)H;                                     // :159
+    float fovRad = c->fov * (3.14159274f / 180.0f);                          // :428
+    fc.half_h = ycge_tanf(0.5f * fovRad);
+    fc.half_w = fc.half_h * aspect;
+    float cp = ycge_cosf(c->snap_pitch);                                     // :413-417
+    float fwd[3] = {ycge_sinf(c->snap_yaw) * cp, ycge_sinf(c->snap_pitch), -ycge_cosf(c->snap_yaw) * cp};
+    normalize3(fwd);
+    float worldUp[3] = {0.0f, 1.0f, 0.0f}, right[3], up[3];
+    cross3h(fwd, worldUp, right); normalize3(right);
+    cross3h(right, fwd, up); normalize3(up);
+    for (int k = 0; k < 3; k++) { fc.cam[k] = c->snap_cam[k]; fc.fwd[k] = fwd[k]; fc.right[k] = right[k]; fc.up[k] = up[k]; }
+    fc.frame = frame; fc.W = W; fc.H = H;
+
+    // row ranges: the tile plus the halo each later pass needs (DESIGN.md "Multi-GPU")
+    const int K = std::max(1, c->P.atrous_iterations);
+    const int ty0 = c->tile_row0 * 2 * ss, ty1 = (c->tile_row0 + c->tile_rows) * 2 * ss;
+    std::vector<int> halo_after(K + 1, 0); // halo_after[k] = rows still needed around the tile after pass k-1 (k=0: TAA output)
+    for (int k = K - 1; k >= 0; k--) halo_after[k] = halo_after[k + 1] + 2 * (1 << k);
+    auto range = [&](int halo, int &a, int &b) { a = std::max(0, ty0 - halo); b = std::min(H, ty1 + halo); };
+
+    const int parity = (int)(frame & 1);
+    ImagePlanes img;
+    img.cur = c->cur.p; img.gnd[0] = c->gnd0.p; img.gnd[1] = c->gnd1.p; img.gas[0] = c->gas0.p; img.gas[1] = c->gas1.p;
+    img.hist = c->hist.p; img.sa = c->sa.p; img.sb = c->sb.p; img.prim = c->prim.p; img.rays = c->debug_rays ? c->rays_dbg.p : nullptr;
+
+    int launches = 0;
+    CK(c, cudaEventRecord(c->ev[0], s));
+    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), s));
+    { // K1
+        int a, b; range(halo_after[0] + 1, a, b);
+        fc.y0 = a; fc.y1 = b;
+        TraceParams tp;
+        tp.diffuse_bounces = c->P.diffuse_bounces; tp.max_mirror_bounces = c->P.max_mirror_bounces; tp.max_refractions = c->P.max_refractions;
+        tp.mirror_threshold = c->P.mirror_threshold; tp.eps = c->P.eps; tp.sigma_rad = c->P.diffuse_sigma_deg * (3.14159274f / 180.0f); // :460
+        tp.seed_salt = c->P.seed_salt;
+        dim3 grid(div_up(W, 16), div_up(b - a, 8));
+        if (c->want_stats) trace_kernel<true><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p);
+        else trace_kernel<false><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p);
+        launches++;
+    }
+    CK(c, cudaEventRecord(c->ev[1], s));
+    { // K2
+        int a, b; range(halo_after[0], a, b);
+        TaaArgs t;
+        t.cur = c->cur.p; t.gnd_now = img.gnd[parity]; t.gnd_prev = img.gnd[parity ^ 1]; t.gas_now = img.gas[parity]; t.gas_prev = img.gas[parity ^ 1];
+        t.hist = c->hist.p; t.W = W; t.H = H; t.y0 = a; t.y1 = b; t.reset = reset ? 1 : 0;
+        float al = c->P.taa_alpha; al = al < 0.0f ? 0.0f : (al > 1.0f ? 1.0f : al); // :305
+        t.alpha = al; t.pad = c->P.luminance_pad;
+        taa_kernel<<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(t);
+        launches++;
+        c->taa_valid = true;
+    }
+    CK(c, cudaEventRecord(c->ev[2], s));
+    { // K3: the reference's ping-pong including its in-place iteration (:648-719)
+        // logical buffers of the reference: 0 = src (TAA history), 1 = scratchA, 2 = scratchB
+        float4 *phys[3] = {c->hist.p, c->sa.p, c->sb.p};
+        int cur_id = 0, dst_id = 1;
+        float dc = std::max(1e-6f, c->P.c_phi), dn = std::max(1e-6f, c->P.n_phi), dz = std::max(1e-6f, c->P.z_phi), da = std::max(1e-6f, c->P.a_phi);
+        for (int it = 0; it < K; it++) {
+            int a, b; range(halo_after[it + 1], a, b);
+            int step = 1 << it;
+            if (cur_id == dst_id) {
+                // in-place pass on scratch X: OLD = X, NEW = the other scratch (dead at this point), which then becomes X
+                int X = cur_id, Y = (X == 1) ? 2 : 1;
+                int C = std::max(1, std::min(step, 8));
+                AtrousInplaceArgs ia;
+                ia.old_ = phys[X]; ia.new_ = phys[Y]; ia.gnd = img.gnd[parity]; ia.gas = img.gas[parity]; ia.progress = c->progress.p;
+                ia.W = W; ia.H = H; ia.step = step; ia.C = C; ia.dc = dc; ia.dn = dn; ia.dz = dz; ia.da = da;
+                // rows above `a` (a sharded tile's upper halo, filled by the previous rank) already hold NEW values
+                if (a > 0) CK(c, cudaMemsetAsync(c->progress.p, 0x7f, (size_t)a * C * sizeof(int), s));
+                CK(c, cudaMemsetAsync(c->progress.p + (size_t)a * C, 0, (size_t)(H - a) * C * sizeof(int), s));
+                if (c->inplace_rows_per_launch <= 0) {
+                    int per_sm = 0;
+                    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_inplace_kernel, 256, 0));
+                    cudaDeviceProp prop;
+                    CK(c, cudaGetDeviceProperties(&prop, c->device));
+                    c->inplace_rows_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
+                }
+                for (int r0 = a; r0 < b; r0 += c->inplace_rows_per_launch) {
+                    ia.y0 = r0; ia.y1 = std::min(b, r0 + c->inplace_rows_per_launch);
+                    atrous_inplace_kernel<<<ia.y1 - ia.y0, C * 32, 0, s>>>(ia);
+                    launches++;
+                }
+                std::swap(phys[X], phys[Y]);
+            } else {
+                AtrousArgs aa;
+                aa.src = phys[cur_id]; aa.gnd = img.gnd[parity]; aa.gas = img.gas[parity]; aa.dst = phys[dst_id];
+                aa.W = W; aa.H = H; aa.y0 = a; aa.y1 = b; aa.step = step; aa.dc = dc; aa.dn = dn; aa.dz = dz; aa.da = da;
+                atrous_kernel<<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
+                launches++;
+            }
+            int tmp = cur_id; // var tmp = cur; cur = dst; dst = (tmp == scratchA) ? scratchB : scratchA;   :718
+            cur_id = dst_id;
+            dst_id = (tmp == 1) ? 2 : 1;
+        }
+        c->denoised = phys[cur_id];
+    }
+    CK(c, cudaEventRecord(c->ev[3], s));
+    { // K4a
+        int step = std::max(2, ss * 2); // :226; sample row k is pixel row k*step = top row of cell row k
+        int srow0 = div_up(ty0, step), srow1 = std::min(c->sh, div_up(ty1, step));
+        if (c->sharded) CK(c, cudaMemsetAsync(c->logs.p, 0, c->logs.n * sizeof(float), s));
+        const float4 *gas = (frame & 1) ? c->gas1.p : c->gas0.p;
+        if (srow1 > srow0) {
+            exposure_log_kernel<<<dim3(div_up(c->sw, 128), srow1 - srow0), 128, 0, s>>>(c->denoised, gas, c->logs.p, W, c->sw, step, srow0, srow1);
+            launches++;
+        }
+    }
+    CK(c, cudaEventRecord(c->ev[4], s));
+    CK(c, cudaGetLastError());
+    c->launches_last = launches;
+    c->frame_open = true;
+    return 0;
+}
+
+int frame_finish_impl(ycge_ctx *c) {
+    if (!c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish without ycge_frame_begin");
+    cudaStream_t s = c->stream;
+    ExposureParams ep;
+    ep.tone_exposure = c->P.tone_exposure; ep.ae_key = c->P.ae_key; ep.ae_speed = c->P.ae_speed; ep.ae_min = c->P.ae_min; ep.ae_max = c->P.ae_max;
+    ep.auto_exposure = c->P.auto_exposure;
+    exposure_finish_kernel<<<1, 1024, 0, s>>>(c->logs.p, c->sw * c->sh, ep, c->expo.p);
+    CK(c, cudaEventRecord(c->ev[5], s));
+    CellArgs ca;
+    ca.den = c->denoised; ca.expo = c->expo.p; ca.cells = c->cells.p; ca.W = c->W; ca.fbW = c->fbW; ca.ss = c->ss;
+    ca.cy0 = c->tile_row0; ca.cy1 = c->tile_row0 + c->tile_rows;
+    ca.gamma = c->P.tone_gamma; ca.saturation = c->P.saturation; ca.vibrance = c->P.vibrance;
+    for (int k = 0; k < 5; k++) ca.th[k] = c->ansi_th[k];
+    cells_kernel<<<dim3(div_up(c->fbW, 128), c->tile_rows), 128, 0, s>>>(ca);
+    CK(c, cudaEventRecord(c->ev[6], s));
+    CK(c, cudaGetLastError());
+    c->launches_last += 2;
+    // taa.CommitCamera (:266, TemporalAA.cs:69-76)
+    memcpy(c->last_cam, c->snap_cam, sizeof c->last_cam); c->last_yaw = c->snap_yaw; c->last_pitch = c->snap_pitch;
+    c->frame_open = false;
+    return 0;
+}
+
+int read_cells_impl(ycge_ctx *c, ycge_cell *out, int stride) {
+    if (!out) return fail(c, YCGE_ERR_INVALID, "out is NULL");
+    if (stride <= 0) stride = c->fbW;
+    if (stride < c->fbW) return fail(c, YCGE_ERR_INVALID, "stride smaller than fb_w");
+    CK(c, cudaMemcpy2DAsync(out, (size_t)stride * sizeof(ycge_cell), c->cells.p, (size_t)c->fbW * sizeof(ycge_cell), (size_t)c->fbW * sizeof(ycge_cell),
+                            (size_t)c->tile_rows, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+} // namespace
+
+// =============================================================================================== exported C ABI
+extern "C" {
+
+YCGE_API void ycge_default_params(ycge_params *p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->diffuse_bounces = 1; p->max_mirror_bounces = 2; p->max_refractions = 2; p->atrous_iterations = 3;
+    p->mirror_threshold = 0.9f; p->eps = 1e-4f; p->taa_alpha = 0.01f; p->motion_trans_reset = 0.0025f; p->motion_rot_reset = 0.0025f;
+    p->diffuse_sigma_deg = 25.0f; p->luminance_pad = 0.10f; p->c_phi = 3.0f; p->n_phi = 0.35f; p->z_phi = 2.0f; p->a_phi = 0.20f;
+    p->tone_exposure = 1.0f; p->tone_gamma = 2.2f; p->ae_key = 0.18f; p->ae_speed = 0.2f; p->ae_min = 0.10f; p->ae_max = 1.50f;
+    p->saturation = 2.0f; p->vibrance = 0.0f; p->auto_exposure = 1; p->seed_salt = 0x9E3779B97F4A7C15ULL;
+}
+
+YCGE_API const char *ycge_last_error(ycge_ctx *ctx) { return ctx ? ctx->err.c_str() : tl_error.c_str(); }
+
+YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, YCGE_ERR_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, YCGE_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, YCGE_ERR_INVALID, "device ordinal out of range");
+    std::unique_ptr<ycge_ctx> c(new ycge_ctx());
+    c->device = cfg->device;
+    c->P = cfg->params;
+    if (c->P.atrous_iterations > 8) return fail(nullptr, YCGE_ERR_INVALID, "atrous_iterations > 8 not supported");
+    CK(nullptr, cudaSetDevice(c->device));
+    CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (auto &ev : c->ev) CK(nullptr, cudaEventCreate(&ev));
+    CK(nullptr, c->expo.alloc(1));
+    ExposureState es;
+    es.ae_exposure = 1.0f; es.effective = 1.0f; es.log_sum = 0.0f; es.cnt = 0; // ToneMapper.cs:13,17
+    CK(nullptr, cudaMemcpyAsync(c->expo.p, &es, sizeof es, cudaMemcpyHostToDevice, c->stream));
+    CK(nullptr, c->counters.alloc(1));
+    CK(nullptr, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), c->stream));
+    static const int bounds[5] = {48, 114, 154, 194, 234}; // ANSITerminalRenderer.cs:288-296
+    for (int k = 0; k < 5; k++) c->ansi_th[k] = ansi_threshold(bounds[k]);
+    int rc = set_geometry(c.get(), cfg->fb_w, cfg->fb_h, cfg->ss, cfg->tile_row0, cfg->tile_rows);
+    if (rc != 0) { tl_error = c->err; return rc; }
+    CK(nullptr, cudaStreamSynchronize(c->stream));
+    memset(&c->ds, 0, sizeof c->ds);
+    *out = c.release();
+    return 0;
+}
+
+YCGE_API void ycge_destroy(ycge_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+YCGE_API int ycge_resize(ycge_ctx *c, int32_t fb_w, int32_t fb_h, int32_t ss) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    int row0 = c->sharded ? c->tile_row0 : 0, rows = c->sharded ? c->tile_rows : 0;
+    if (c->sharded && row0 + rows > fb_h) return fail(c, YCGE_ERR_INVALID, "tile exceeds resized framebuffer");
+    int rc = set_geometry(c, fb_w, fb_h, ss, row0, rows);
+    if (rc) return rc;
+    if (c->debug_rays) CK(c, c->rays_dbg.alloc((size_t)c->W * c->H * 6));
+    // TemporalAA.Resize (TemporalAA.cs:33-45): the camera memory is cleared; frame counter and exposure survive (:110-138)
+    c->last_cam[0] = c->last_cam[1] = c->last_cam[2] = NAN; c->last_yaw = NAN; c->last_pitch = NAN;
+    return 0;
+}
+
+YCGE_API int ycge_set_stream(ycge_ctx *c, void *cuda_stream) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+// ---- meshes ------------------------------------------------------------------------------------------------
+static int store_mesh(ycge_ctx *c, int id, int n, const float *soa12 /* n x (A,e1,e2,n) */, const TreeView &tv, const ycge_material &mat) {
+    std::vector<PairNode> pairs;
+    TreeRoot root;
+    int rc = flatten(c, tv, pairs, root);
+    if (rc) return rc;
+    std::vector<DevTri> tris(tv.n_leaf);
+    std::vector<int> ids(tv.n_leaf);
+    for (int s = 0; s < tv.n_leaf; s++) {
+        int t = tv.leaf[s];
+        if (t < 0 || t >= n) return fail(c, YCGE_ERR_INVALID, "leafTriIndex out of range");
+        const float *q = soa12 + 12 * (size_t)t;
+        tris[s].t0 = make_float4(q[0], q[1], q[2], q[3]);
+        tris[s].t1 = make_float4(q[4], q[5], q[6], q[7]);
+        tris[s].t2 = make_float4(q[8], q[9], q[10], q[11]);
+        ids[s] = t;
+    }
+    std::unique_ptr<MeshStore> m(new MeshStore());
+    CK(c, m->nodes.upload(pairs, c->stream));
+    CK(c, m->tris.upload(tris, c->stream));
+    CK(c, m->tri_id.upload(ids, c->stream));
+    m->root = root; m->material = mat; m->n_tris = n;
+    c->meshes[id] = std::move(m);
+    c->have_scene = false; // object table must be rebuilt
+    return 0;
+}
+
+YCGE_API int ycge_mesh_upload_soa(ycge_ctx *c, int32_t id, const ycge_mesh_soa *mesh) {
+    if (!c || !mesh || !mesh->bvh) return fail(c, YCGE_ERR_INVALID, "ctx/mesh/mesh->bvh is NULL");
+    CK(c, cudaSetDevice(c->device));
+    int n = mesh->n_tris;
+    std::vector<float> soa((size_t)n * 12);
+    for (int i = 0; i < n; i++) {
+        float *d = &soa[(size_t)i * 12];
+        d[0] = mesh->ax[i]; d[1] = mesh->ay[i]; d[2] = mesh->az[i]; d[3] = mesh->e1x[i]; d[4] = mesh->e1y[i]; d[5] = mesh->e1z[i];
+        d[6] = mesh->e2x[i]; d[7] = mesh->e2y[i]; d[8] = mesh->e2z[i]; d[9] = mesh->nx[i]; d[10] = mesh->ny[i]; d[11] = mesh->nz[i];
+    }
+    return store_mesh(c, id, n, soa.data(), view_of(*mesh->bvh), mesh->material);
+}
+
+YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *c, int32_t id, int32_t n, const float *abc, const ycge_material *material) {
+    if (!c || !abc || !material || n < 0) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    std::vector<float> soa((size_t)n * 12);
+    std::vector<BuildItem> items((size_t)n);
+    for (int i = 0; i < n; i++) { // MeshBVH.cs:83-97
+        const float *t = abc + 9 * (size_t)i;
+        items[i] = triangle_item(i, t);
+        float *d = &soa[(size_t)i * 12];
+        d[0] = t[0]; d[1] = t[1]; d[2] = t[2];
+        float lx = t[3] - t[0], ly = t[4] - t[1], lz = t[5] - t[2];
+        float mx = t[6] - t[0], my = t[7] - t[1], mz = t[8] - t[2];
+        d[3] = lx; d[4] = ly; d[5] = lz; d[6] = mx; d[7] = my; d[8] = mz;
+        float nnx = ly * mz - lz * my, nny = lz * mx - lx * mz, nnz = lx * my - ly * mx;
+        float invLen = 1.0f / detail::net_max(1e-20f, std::sqrt(nnx * nnx + nny * nny + nnz * nnz));
+        d[9] = nnx * invLen; d[10] = nny * invLen; d[11] = nnz * invLen;
+    }
+    FlatTree tree;
+    build_reference_tree(items, 8, true, tree);
+    return store_mesh(c, id, n, soa.data(), view_of(tree), *material);
+}
+
+// ---- volumes -----------------------------------------------------------------------------------------------
+YCGE_API int ycge_volume_upload(ycge_ctx *c, int32_t id, const ycge_volume *v) {
+    if (!c || !v || !v->mat || !v->meta || !v->palette) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if (v->nx <= 0 || v->ny <= 0 || v->nz <= 0) return fail(c, YCGE_ERR_UNBOUNDED, "empty VolumeGrid has no bounds");
+    CK(c, cudaSetDevice(c->device));
+    std::unique_ptr<VolumeStore> vs(new VolumeStore());
+    DevVolume &d = vs->dv;
+    memset(&d, 0, sizeof d);
+    d.nx = v->nx; d.ny = v->ny; d.nz = v->nz;
+    d.nbx = (v->nx + 7) >> 3; d.nby = (v->ny + 7) >> 3; d.nbz = (v->nz + 7) >> 3;
+    size_t cap = (size_t)d.nbx * d.nby * d.nbz * 512;
+    if (cap > (size_t)0x7fffffff) return fail(c, YCGE_ERR_LIMIT, "VolumeGrid larger than 2^31 voxels (the reference indexes with int)");
+    for (int k = 0; k < 3; k++) { d.min_corner[k] = v->min_corner[k]; d.voxel_size[k] = v->voxel_size[k]; }
+    d.wireframe = v->wireframe; d.wire_width_frac = v->wire_width_frac; d.wire_max_distance = v->wire_max_distance;
+    CK(c, vs->vox.alloc(cap));
+    CK(c, vs->raw_mat.alloc(cap));
+    CK(c, vs->raw_meta.alloc(cap));
+    CK(c, cudaMemcpyAsync(vs->raw_mat.p, v->mat, cap * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(vs->raw_meta.p, v->meta, cap * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    vs->n_ids = v->palette_n_ids; vs->levels = v->palette_meta_levels < 1 ? 1 : v->palette_meta_levels; vs->def = v->palette_default;
+    vs->palette.assign(v->palette, v->palette + (size_t)vs->n_ids * vs->levels);
+    for (int mi : vs->palette) if (mi < 0 || mi >= 255) return fail(c, YCGE_ERR_LIMIT, "voxel palette material index must be in [0,254]");
+    if (vs->def < 0 || vs->def >= 255) return fail(c, YCGE_ERR_LIMIT, "voxel palette default material index must be in [0,254]");
+    // materialLookup(id, meta) resolved now: one byte per voxel
+    DevBuf<int> pal;
+    CK(c, pal.upload(vs->palette, c->stream));
+    voxel_pack_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(vs->raw_mat.p, vs->raw_meta.p, vs->vox.p, cap, pal.p, vs->n_ids, vs->levels, vs->def);
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));
+    vs->raw_mat.release(); vs->raw_meta.release();
+    vs->packed = true;
+    d.vox = vs->vox.p;
+    c->volumes[id] = std::move(vs);
+    c->have_scene = false;
+    return 0;
+}
+
+// ---- scene -------------------------------------------------------------------------------------------------
+static bool object_bounds(ycge_ctx *c, const ycge_object &o, Aabb &box, float cen[3]) {
+    const float *p = o.p;
+    const float E = 1e-4f;
+    switch (o.kind) {
+        case YCGE_SPHERE: case YCGE_DISK: { // BoundedObjects.cs:20-29, Surfaces.cs:96-105
+            float R = o.kind == YCGE_SPHERE ? p[3] : p[6];
+            for (int k = 0; k < 3; k++) { box.lo[k] = p[k] - R; box.hi[k] = p[k] + R; }
+            break; }
+        case YCGE_PLANE: // Surfaces.cs:30-36: +-1e6 box, centroid exactly 0
+            for (int k = 0; k < 3; k++) { box.lo[k] = -1e6f; box.hi[k] = 1e6f; cen[k] = 0.0f; }
+            return true;
+        case YCGE_XYRECT: box.lo[0] = p[0]; box.lo[1] = p[2]; box.lo[2] = p[4] - E; box.hi[0] = p[1]; box.hi[1] = p[3]; box.hi[2] = p[4] + E; break;
+        case YCGE_XZRECT: box.lo[0] = p[0]; box.lo[1] = p[4] - E; box.lo[2] = p[2]; box.hi[0] = p[1]; box.hi[1] = p[4] + E; box.hi[2] = p[3]; break;
+        case YCGE_YZRECT: box.lo[0] = p[4] - E; box.lo[1] = p[0]; box.lo[2] = p[2]; box.hi[0] = p[4] + E; box.hi[1] = p[1]; box.hi[2] = p[3]; break;
+        case YCGE_BOX: for (int k = 0; k < 3; k++) { box.lo[k] = p[k]; box.hi[k] = p[3 + k]; } break;
+        case YCGE_CYLINDER_Y: box.lo[0] = p[0] - p[3]; box.lo[1] = p[4]; box.lo[2] = p[2] - p[3]; box.hi[0] = p[0] + p[3]; box.hi[1] = p[5]; box.hi[2] = p[2] + p[3]; break;
+        case YCGE_TRIANGLE: { BuildItem it = triangle_item(0, p); box = it.box; break; } // Triangle.cs:54-66 (same rule as MeshBVH)
+        case YCGE_MESH: {
+            auto it = c->meshes.find(o.ref_id);
+            if (it == c->meshes.end() || it->second->root.ref == YCGE_REF_NONE) return false;
+            for (int k = 0; k < 3; k++) { box.lo[k] = it->second->root.lo[k]; box.hi[k] = it->second->root.hi[k]; }
+            break; }
+        case YCGE_VOLUME: { // VolumeGrid.cs:386-403
+            auto it = c->volumes.find(o.ref_id);
+            if (it == c->volumes.end()) return false;
+            const DevVolume &d = it->second->dv;
+            box.lo[0] = d.min_corner[0]; box.lo[1] = d.min_corner[1]; box.lo[2] = d.min_corner[2];
+            box.hi[0] = d.min_corner[0] + d.nx * d.voxel_size[0]; box.hi[1] = d.min_corner[1] + d.ny * d.voxel_size[1]; box.hi[2] = d.min_corner[2] + d.nz * d.voxel_size[2];
+            break; }
+        default: return false;
+    }
+    for (int k = 0; k < 3; k++) cen[k] = 0.5f * (box.lo[k] + box.hi[k]);
+    return true;
+}
+
+YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) {
+    if (!c || !s) return fail(c, YCGE_ERR_INVALID, "ctx/scene is NULL");
+    if (s->n_objects < 0 || s->n_lights < 0 || s->n_materials < 0) return fail(c, YCGE_ERR_INVALID, "negative count");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->have_scene = false;
+    // materials: the scene's table, then one entry per uploaded mesh
+    std::vector<float4> mats;
+    auto push_mat = [&](const ycge_material &m) {
+        mats.push_back(make_float4(m.albedo[0], m.albedo[1], m.albedo[2], m.reflectivity));
+        mats.push_back(make_float4(m.emission[0], m.emission[1], m.emission[2], m.transparency));
+        mats.push_back(make_float4(m.transmission[0], m.transmission[1], m.transmission[2], m.ior));
+        int tex = m.tex_id; float texf; memcpy(&texf, &tex, 4);
+        mats.push_back(make_float4(m.specular, texf, m.tex_weight, m.uv_scale));
+    };
+    for (int i = 0; i < s->n_materials; i++) push_mat(s->materials[i]);
+    std::map<int, int> mesh_slot, vol_slot;
+    std::vector<DevMesh> dmeshes;
+    std::vector<DevVolume> dvols;
+    std::vector<DevObject> dobjs((size_t)s->n_objects);
+    std::vector<BuildItem> items;
+    for (int i = 0; i < s->n_objects; i++) {
+        const ycge_object &o = s->objects[i];
+        DevObject d;
+        memset(&d, 0, sizeof d);
+        d.kind = o.kind; d.mat_a = o.mat_a; d.mat_b = o.mat_b; d.override_sr = o.override_sr;
+        d.checker_scale = o.checker_scale; d.specular = o.specular; d.reflectivity = o.reflectivity; d.ref = -1;
+        memcpy(d.p, o.p, sizeof d.p);
+        const float *p = o.p;
+        bool needs_mat = true;
+        switch (o.kind) {
+            case YCGE_PLANE: d.d[0] = p[3] * p[0] + p[4] * p[1] + p[5] * p[2]; break;                     // Surfaces.cs:26
+            case YCGE_DISK: d.d[0] = p[3] * p[0] + p[4] * p[1] + p[5] * p[2]; d.d[1] = p[6] * p[6]; break;  // Surfaces.cs:92-93 (Normal.Dot(Center))
+            case YCGE_CYLINDER_Y: d.d[0] = p[3] * p[3]; break;                                           // BoundedObjects.cs:136
+            case YCGE_TRIANGLE: { // Triangle.cs:36-44
+                float e1x = p[3] - p[0], e1y = p[4] - p[1], e1z = p[5] - p[2], e2x = p[6] - p[0], e2y = p[7] - p[1], e2z = p[8] - p[2];
+                float nnx = e1y * e2z - e1z * e2y, nny = e1z * e2x - e1x * e2z, nnz = e1x * e2y - e1y * e2x;
+                float invLen = 1.0f / detail::net_max(1e-20f, std::sqrt(nnx * nnx + nny * nny + nnz * nnz));
+                d.d[0] = e1x; d.d[1] = e1y; d.d[2] = e1z; d.d[3] = e2x; d.d[4] = e2y; d.d[5] = e2z;
+                d.d[6] = nnx * invLen; d.d[7] = nny * invLen; d.d[8] = nnz * invLen;
+                break; }
+            case YCGE_MESH: {
+                auto it = c->meshes.find(o.ref_id);
+                if (it == c->meshes.end()) return fail(c, YCGE_ERR_INVALID, "object references a mesh id that was not uploaded");
+                if (!mesh_slot.count(o.ref_id)) {
+                    MeshStore &m = *it->second;
+                    DevMesh dm;
+                    dm.nodes = m.nodes.p; dm.tris = m.tris.p; dm.tri_id = m.tri_id.p; dm.root = m.root; dm.n_tris = m.n_tris;
+                    dm.material = (int)(mats.size() / 4);
+                    push_mat(m.material);
+                    mesh_slot[o.ref_id] = (int)dmeshes.size();
+                    dmeshes.push_back(dm);
+                }
+                d.ref = mesh_slot[o.ref_id];
+                needs_mat = false;
+                break; }
+            case YCGE_VOLUME: {
+                auto it = c->volumes.find(o.ref_id);
+                if (it == c->volumes.end()) return fail(c, YCGE_ERR_INVALID, "object references a volume id that was not uploaded");
+                if (!vol_slot.count(o.ref_id)) { vol_slot[o.ref_id] = (int)dvols.size(); dvols.push_back(it->second->dv); }
+                d.ref = vol_slot[o.ref_id];
+                for (int mi : it->second->palette) if (mi >= s->n_materials) return fail(c, YCGE_ERR_INVALID, "voxel palette references a material outside the scene table");
+                needs_mat = false;
+                break; }
+            default: break;
+        }
+        if (o.kind < 0 || o.kind > YCGE_VOLUME) return fail(c, YCGE_ERR_INVALID, "unknown object kind");
+        if (needs_mat && (o.mat_a < 0 || o.mat_a >= s->n_materials || o.mat_b < 0 || o.mat_b >= s->n_materials))
+            return fail(c, YCGE_ERR_INVALID, "object material index out of range");
+        dobjs[i] = d;
+        if (!s->bvh) {
+            BuildItem it;
+            it.index = i;
+            if (!object_bounds(c, o, it.box, it.c)) return fail(c, YCGE_ERR_UNBOUNDED, "Unbounded Hittable");
+            items.push_back(it);
+        }
+    }
+    std::vector<PairNode> pairs;
+    std::vector<int> leaf;
+    TreeRoot root;
+    if (s->bvh) {
+        TreeView tv = view_of(*s->bvh);
+        int rc = flatten(c, tv, pairs, root);
+        if (rc) return rc;
+        leaf.assign(tv.leaf, tv.leaf + tv.n_leaf);
+    } else { // new BVH(Objects)  BVH.cs:29-97
+        FlatTree tree;
+        build_reference_tree(items, 4, false, tree);
+        int rc = flatten(c, view_of(tree), pairs, root);
+        if (rc) return rc;
+        leaf = tree.leaf_index;
+    }
+    for (int v : leaf) if (v < 0 || v >= s->n_objects) return fail(c, YCGE_ERR_INVALID, "leafObjIndex out of range");
+    std::vector<DevLight> lights((size_t)s->n_lights);
+    for (int i = 0; i < s->n_lights; i++) {
+        for (int k = 0; k < 3; k++) { lights[i].pos[k] = s->lights[i].pos[k]; lights[i].color[k] = s->lights[i].color[k]; }
+        lights[i].intensity = s->lights[i].intensity; lights[i].pad = 0.0f;
+    }
+    CK(c, c->s_nodes.upload(pairs, c->stream));
+    CK(c, c->s_leaf.upload(leaf, c->stream));
+    CK(c, c->s_objects.upload(dobjs, c->stream));
+    CK(c, c->s_materials.upload(mats, c->stream));
+    CK(c, c->s_meshes.upload(dmeshes, c->stream));
+    CK(c, c->s_volumes.upload(dvols, c->stream));
+    CK(c, c->s_lights.upload(lights, c->stream));
+    DevScene &ds = c->ds;
+    memset(&ds, 0, sizeof ds);
+    ds.nodes = c->s_nodes.p; ds.leaf_obj = c->s_leaf.p; ds.objects = c->s_objects.p; ds.materials = c->s_materials.p;
+    ds.meshes = c->s_meshes.p; ds.volumes = c->s_volumes.p; ds.lights = c->s_lights.p; ds.root = root;
+    ds.n_lights = s->n_lights; ds.is_volume_scene = s->is_volume_scene;
+    for (int k = 0; k < 3; k++) { ds.bg_top[k] = s->bg_top[k]; ds.bg_bottom[k] = s->bg_bottom[k]; ds.ambient[k] = s->ambient_color[k]; }
+    ds.ambient_intensity = s->ambient_intensity;
+    c->have_scene = true;
+    return 0;
+}
+
+YCGE_API int ycge_lights_update(ycge_ctx *c, int32_t n, const ycge_light *l) {
+    if (!c || n < 0 || (n > 0 && !l)) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    std::vector<DevLight> lights((size_t)n);
+    for (int i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) { lights[i].pos[k] = l[i].pos[k]; lights[i].color[k] = l[i].color[k]; }
+        lights[i].intensity = l[i].intensity; lights[i].pad = 0.0f;
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    if ((size_t)n > c->s_lights.n) CK(c, c->s_lights.alloc((size_t)n));
+    if (n) CK(c, cudaMemcpyAsync(c->s_lights.p, lights.data(), (size_t)n * sizeof(DevLight), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->ds.lights = c->s_lights.p; c->ds.n_lights = n;
+    return 0;
+}
+
+YCGE_API int ycge_globals_update(ycge_ctx *c, const float bg_top[3], const float bg_bottom[3], const float ambient_color[3], float ambient_intensity) {
+    if (!c || !bg_top || !bg_bottom || !ambient_color) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    for (int k = 0; k < 3; k++) { c->ds.bg_top[k] = bg_top[k]; c->ds.bg_bottom[k] = bg_bottom[k]; c->ds.ambient[k] = ambient_color[k]; }
+    c->ds.ambient_intensity = ambient_intensity;
+    return 0;
+}
+
+// ---- per frame ---------------------------------------------------------------------------------------------
+YCGE_API int ycge_set_camera(ycge_ctx *c, const float pos[3], float yaw, float pitch) {
+    if (!c || !pos) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    c->cam[0] = pos[0]; c->cam[1] = pos[1]; c->cam[2] = pos[2]; c->yaw = yaw; c->pitch = pitch;
+    return 0;
+}
+YCGE_API int ycge_set_fov(ycge_ctx *c, float fov_deg) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); c->fov = fov_deg; return 0; }
+YCGE_API int ycge_reset_history(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); c->force_reset = true; return 0; }
+
+YCGE_API int ycge_frame_begin(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); return frame_begin_impl(c); }
+YCGE_API int ycge_frame_finish(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); return frame_finish_impl(c); }
+
+YCGE_API int ycge_render_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    int rc = frame_begin_impl(c);
+    if (rc) return rc;
+    rc = frame_finish_impl(c);
+    if (rc) return rc;
+    return read_cells_impl(c, out, stride_cells);
+}
+YCGE_API int ycge_render_frame_stats(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    c->want_stats = true;
+    int rc = ycge_render_frame(c, out, stride_cells);
+    c->want_stats = false;
+    return rc;
+}
+YCGE_API int ycge_render_frames_async(ycge_ctx *c, int32_t n) {
+    if (!c || n < 0) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    for (int i = 0; i < n; i++) {
+        int rc = frame_begin_impl(c);
+        if (rc) return rc;
+        rc = frame_finish_impl(c);
+        if (rc) return rc;
+    }
+    return 0;
+}
+YCGE_API int ycge_wait(ycge_ctx *c) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+YCGE_API int ycge_read_cells(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    return read_cells_impl(c, out, stride_cells);
+}
+YCGE_API int ycge_device_ptr(ycge_ctx *c, int32_t kind, void **ptr, size_t *bytes) {
+    if (!c || !ptr || !bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if (kind == YCGE_PTR_CELLS) { *ptr = c->cells.p; *bytes = c->cells.n * sizeof(ycge_cell); return 0; }
+    if (kind == YCGE_PTR_LOG_SAMPLES) { *ptr = c->logs.p; *bytes = c->logs.n * sizeof(float); return 0; }
+    return fail(c, YCGE_ERR_INVALID, "unknown pointer kind");
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------
+YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes) {
+    if (!c || !dst) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    size_t n = (size_t)c->W * c->H;
+    const void *src = nullptr;
+    size_t need = 0;
+    int parity = (int)(c->frame_counter & 1);
+    switch (kind) {
+        case YCGE_DBG_RAYS:
+            if (!c->debug_rays) { // enable the tap; the next frame fills it
+                CK(c, c->rays_dbg.alloc(n * 6));
+                c->debug_rays = true;
+                return fail(c, YCGE_ERR_INVALID, "ray tap enabled now; render a frame and read again");
+            }
+            src = c->rays_dbg.p; need = n * 24; break;
+        case YCGE_DBG_HDR: src = c->cur.p; need = n * 16; break;
+        case YCGE_DBG_ALBEDO_SKY: src = parity ? c->gas1.p : c->gas0.p; need = n * 16; break;
+        case YCGE_DBG_NORMAL_DEPTH: src = parity ? c->gnd1.p : c->gnd0.p; need = n * 16; break;
+        case YCGE_DBG_TAA: src = c->hist.p; need = n * 16; break;
+        case YCGE_DBG_DENOISED: src = c->denoised; need = n * 16; break;
+        case YCGE_DBG_PRIM_ID: src = c->prim.p; need = n * 8; break;
+        case YCGE_DBG_LOG_SAMPLES: src = c->logs.p; need = c->logs.n * 4; break;
+        default: return fail(c, YCGE_ERR_INVALID, "unknown debug kind");
+    }
+    if (!src) return fail(c, YCGE_ERR_INVALID, "no frame rendered yet");
+    if (bytes < need) return fail(c, YCGE_ERR_INVALID, "destination too small");
+    CK(c, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
+    if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    TraceCounters tc;
+    CK(c, cudaMemcpy(&tc, c->counters.p, sizeof tc, cudaMemcpyDeviceToHost));
+    ExposureState es;
+    CK(c, cudaMemcpy(&es, c->expo.p, sizeof es, cudaMemcpyDeviceToHost));
+    out->frames = (uint64_t)c->frame_counter; out->rays = tc.rays;
+    out->top_nodes_popped = tc.top_nodes; out->mesh_nodes_popped = tc.mesh_nodes; out->leaf_refs = tc.leaf_refs;
+    out->tris_tested = tc.tris; out->prims_tested = tc.prims; out->dda_cells = tc.dda;
+    if (tc.stack_overflow) return fail(c, YCGE_ERR_LIMIT, "traversal stack overflow (tree deeper than the device stack)");
+    if (c->frame_counter > 0) {
+        float ms[6];
+        for (int k = 0; k < 6; k++) if (cudaEventElapsedTime(&ms[k], c->ev[k], c->ev[k + 1]) != cudaSuccess) ms[k] = 0.0f;
+        out->ms_trace = ms[0]; out->ms_taa = ms[1]; out->ms_atrous = ms[2]; out->ms_exposure = ms[3] + ms[4]; out->ms_cells = ms[5];
+        float tot = 0.0f;
+        if (cudaEventElapsedTime(&tot, c->ev[0], c->ev[6]) == cudaSuccess) out->ms_total = tot;
+    }
+    out->ae_exposure = es.ae_exposure; out->log_sum = es.log_sum; out->log_cnt = es.cnt;
+    out->kernel_launches = c->launches_last;
+    return 0;
+}
+
+YCGE_API int ycge_get_frame_counter(ycge_ctx *c, int64_t *frame) {
+    if (!c || !frame) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    *frame = c->frame_counter;
+    return 0;
+}
+
+YCGE_API int ycge_rng_kat(ycge_ctx *c, int32_t which, int32_t n, const int32_t *x, const int32_t *y, const int64_t *frame, int32_t n_draws,
+                          uint32_t *out_bits, uint64_t *out_seed) {
+    if (!c || n <= 0 || n_draws <= 0 || !x || !y || !frame || !out_bits || !out_seed) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    DevBuf<int> dx, dy;
+    DevBuf<long long> df;
+    DevBuf<unsigned int> db;
+    DevBuf<unsigned long long> dsd;
+    CK(c, dx.alloc(n)); CK(c, dy.alloc(n)); CK(c, df.alloc(n)); CK(c, db.alloc((size_t)n * n_draws)); CK(c, dsd.alloc(n));
+    CK(c, cudaMemcpy(dx.p, x, n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(dy.p, y, n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(df.p, frame, n * sizeof(long long), cudaMemcpyHostToDevice));
+    rng_kat_kernel<<<div_up(n, 128), 128, 0, c->stream>>>(which, n, dx.p, dy.p, df.p, n_draws, db.p, dsd.p, c->P.seed_salt);
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(out_bits, db.p, (size_t)n * n_draws * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(out_seed, dsd.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,1012 @@
+// ycge_host.cpp — implementation of the C++ host mirror (see ycge_host.hpp) + a small C API for Python (ctypes).
+#include "ycge_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <set>
+#include <sstream>
+#include <unordered_map>
+#include <unordered_set>
+
+namespace ycge_host {
+
+using ycge::detail::net_max;
+using ycge::detail::net_min;
+static const float kInf = std::numeric_limits<float>::infinity();
+
+Vec3 Vec3::Normalized() const { // Vec3.cs:98-107
+    float lenSq = X * X + Y * Y + Z * Z;
+    if (lenSq <= 0.0f) return *this;
+    float invLen = 1.0f / std::sqrt(lenSq);
+    return Vec3(X * invLen, Y * invLen, Z * invLen);
+}
+
+ycge_material Material::ToAbi() const {
+    ycge_material m;
+    m.albedo[0] = Albedo.X; m.albedo[1] = Albedo.Y; m.albedo[2] = Albedo.Z; m.reflectivity = (float)Reflectivity;
+    m.emission[0] = Emission.X; m.emission[1] = Emission.Y; m.emission[2] = Emission.Z; m.transparency = (float)Transparency;
+    m.transmission[0] = TransmissionColor.X; m.transmission[1] = TransmissionColor.Y; m.transmission[2] = TransmissionColor.Z; m.ior = (float)IndexOfRefraction;
+    m.specular = (float)Specular; m.tex_id = DiffuseTexture; m.tex_weight = (float)TextureWeight; m.uv_scale = (float)UVScale;
+    return m;
+}
+
+MaterialFunc Solid(Vec3 albedo) { MaterialFunc f; f.a = f.b = Material(albedo, 0.0, 0.0, Vec3()); return f; }                  // Scenes.cs:408-411
+MaterialFunc Emissive(Vec3 emission) { MaterialFunc f; f.a = f.b = Material(Vec3(0.0, 0.0, 0.0), 0.0, 0.0, emission); return f; } // :413-416
+MaterialFunc Checker(Vec3 a, Vec3 b, float scale) {                                                                             // :418-428
+    MaterialFunc f; f.a = Material(a, 0.0, 0.0, Vec3()); f.b = Material(b, 0.0, 0.0, Vec3()); f.scale = scale; return f;
+}
+MaterialFunc Constant(const Material &m) { MaterialFunc f; f.a = f.b = m; return f; }
+
+static void center_of(float minX, float minY, float minZ, float maxX, float maxY, float maxZ, float &cx, float &cy, float &cz) {
+    cx = 0.5f * (minX + maxX); cy = 0.5f * (minY + maxY); cz = 0.5f * (minZ + maxZ);
+}
+
+// ---- SceneExport ------------------------------------------------------------------------------------------------
+int SceneExport::AddMaterial(const Material &m) {
+    ycge_material a = m.ToAbi();
+    for (size_t i = 0; i < materials.size(); i++) if (memcmp(&materials[i], &a, sizeof a) == 0) return (int)i;
+    materials.push_back(a);
+    return (int)materials.size() - 1;
+}
+void SceneExport::AddFunc(ycge_object &o, const MaterialFunc &f, float specular, float reflectivity) {
+    o.mat_a = AddMaterial(f.a);
+    o.mat_b = f.scale != 0.0f ? AddMaterial(f.b) : o.mat_a;
+    o.checker_scale = f.scale;
+    o.override_sr = 1; o.specular = specular; o.reflectivity = reflectivity;
+}
+static ycge_object blank_object(int kind) {
+    ycge_object o;
+    memset(&o, 0, sizeof o);
+    o.kind = kind; o.ref_id = -1;
+    return o;
+}
+
+// ---- primitives -------------------------------------------------------------------------------------------------
+bool Sphere::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const {
+    minX = Center.X - Radius; minY = Center.Y - Radius; minZ = Center.Z - Radius; maxX = Center.X + Radius; maxY = Center.Y + Radius; maxZ = Center.Z + Radius;
+    center_of(minX, minY, minZ, maxX, maxY, maxZ, cx, cy, cz);
+    return true;
+}
+void Sphere::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_SPHERE);
+    o.mat_a = o.mat_b = out.AddMaterial(Mat);
+    o.p[0] = Center.X; o.p[1] = Center.Y; o.p[2] = Center.Z; o.p[3] = Radius;
+    out.objects.push_back(o);
+}
+bool Plane::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const {
+    float B = 1e6f; // Surfaces.cs:30-36
+    minX = -B; minY = -B; minZ = -B; maxX = B; maxY = B; maxZ = B; cx = 0.0f; cy = 0.0f; cz = 0.0f;
+    return true;
+}
+void Plane::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_PLANE);
+    out.AddFunc(o, MatFunc, Specular, Reflectivity);
+    o.p[0] = Point.X; o.p[1] = Point.Y; o.p[2] = Point.Z; o.p[3] = Normal.X; o.p[4] = Normal.Y; o.p[5] = Normal.Z;
+    out.objects.push_back(o);
+}
+bool Disk::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const {
+    minX = Center.X - Radius; minY = Center.Y - Radius; minZ = Center.Z - Radius; maxX = Center.X + Radius; maxY = Center.Y + Radius; maxZ = Center.Z + Radius;
+    center_of(minX, minY, minZ, maxX, maxY, maxZ, cx, cy, cz);
+    return true;
+}
+void Disk::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_DISK);
+    out.AddFunc(o, MatFunc, Specular, Reflectivity);
+    o.p[0] = Center.X; o.p[1] = Center.Y; o.p[2] = Center.Z; o.p[3] = Normal.X; o.p[4] = Normal.Y; o.p[5] = Normal.Z; o.p[6] = Radius;
+    out.objects.push_back(o);
+}
+bool AxisRect::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const {
+    const float Eps = 1e-4f;
+    if (Kind == YCGE_XYRECT) { minX = A0; minY = B0; minZ = K - Eps; maxX = A1; maxY = B1; maxZ = K + Eps; }
+    else if (Kind == YCGE_XZRECT) { minX = A0; minY = K - Eps; minZ = B0; maxX = A1; maxY = K + Eps; maxZ = B1; }
+    else { minX = K - Eps; minY = A0; minZ = B0; maxX = K + Eps; maxY = A1; maxZ = B1; }
+    center_of(minX, minY, minZ, maxX, maxY, maxZ, cx, cy, cz);
+    return true;
+}
+void AxisRect::Export(SceneExport &out) const {
+    ycge_object o = blank_object(Kind);
+    out.AddFunc(o, MatFunc, Specular, Reflectivity);
+    o.p[0] = A0; o.p[1] = A1; o.p[2] = B0; o.p[3] = B1; o.p[4] = K;
+    out.objects.push_back(o);
+}
+bool Box::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const {
+    minX = Min.X; minY = Min.Y; minZ = Min.Z; maxX = Max.X; maxY = Max.Y; maxZ = Max.Z;
+    center_of(minX, minY, minZ, maxX, maxY, maxZ, cx, cy, cz);
+    return true;
+}
+void Box::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_BOX);
+    out.AddFunc(o, MatFunc, Specular, Reflectivity);
+    o.p[0] = Min.X; o.p[1] = Min.Y; o.p[2] = Min.Z; o.p[3] = Max.X; o.p[4] = Max.Y; o.p[5] = Max.Z;
+    out.objects.push_back(o);
+}
+CylinderY::CylinderY(Vec3 c, float r, float yMin, float yMax, bool capped, Material m)
+    : Center(c), Radius(r), YMin(net_min(yMin, yMax)), YMax(net_max(yMin, yMax)), Capped(capped), Mat(m) {}
+bool CylinderY::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const {
+    minX = Center.X - Radius; minY = YMin; minZ = Center.Z - Radius; maxX = Center.X + Radius; maxY = YMax; maxZ = Center.Z + Radius;
+    center_of(minX, minY, minZ, maxX, maxY, maxZ, cx, cy, cz);
+    return true;
+}
+void CylinderY::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_CYLINDER_Y);
+    o.mat_a = o.mat_b = out.AddMaterial(Mat);
+    o.p[0] = Center.X; o.p[1] = Center.Y; o.p[2] = Center.Z; o.p[3] = Radius; o.p[4] = YMin; o.p[5] = YMax; o.p[6] = Capped ? 1.0f : 0.0f;
+    out.objects.push_back(o);
+}
+bool Triangle::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const {
+    float abc[9] = {A.X, A.Y, A.Z, B.X, B.Y, B.Z, C.X, C.Y, C.Z};
+    ycge::BuildItem it = ycge::triangle_item(0, abc); // Triangle.cs:54-66
+    minX = it.box.lo[0]; minY = it.box.lo[1]; minZ = it.box.lo[2]; maxX = it.box.hi[0]; maxY = it.box.hi[1]; maxZ = it.box.hi[2];
+    cx = it.c[0]; cy = it.c[1]; cz = it.c[2];
+    return true;
+}
+void Triangle::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_TRIANGLE);
+    o.mat_a = o.mat_b = out.AddMaterial(Mat);
+    o.p[0] = A.X; o.p[1] = A.Y; o.p[2] = A.Z; o.p[3] = B.X; o.p[4] = B.Y; o.p[5] = B.Z; o.p[6] = C.X; o.p[7] = C.Y; o.p[8] = C.Z;
+    out.objects.push_back(o);
+}
+
+// ---- MeshBVH / Mesh ---------------------------------------------------------------------------------------------
+int MeshBVH::counter = 0;
+MeshBVH::MeshBVH(const std::vector<Triangle> &tris) { // MeshBVH.cs:41-130
+    counter = counter + (int)tris.size();
+    size_t n = tris.size();
+    ax.resize(n); ay.resize(n); az.resize(n); e1x.resize(n); e1y.resize(n); e1z.resize(n);
+    e2x.resize(n); e2y.resize(n); e2z.resize(n); nx.resize(n); ny.resize(n); nz.resize(n);
+    std::vector<ycge::BuildItem> items(n);
+    for (size_t i = 0; i < n; i++) {
+        const Triangle &t = tris[i];
+        float abc[9] = {t.A.X, t.A.Y, t.A.Z, t.B.X, t.B.Y, t.B.Z, t.C.X, t.C.Y, t.C.Z};
+        items[i] = ycge::triangle_item((int)i, abc);
+        this->abc.insert(this->abc.end(), abc, abc + 9);
+        ax[i] = t.A.X; ay[i] = t.A.Y; az[i] = t.A.Z;
+        float lx = t.B.X - t.A.X, ly = t.B.Y - t.A.Y, lz = t.B.Z - t.A.Z;
+        float mx = t.C.X - t.A.X, my = t.C.Y - t.A.Y, mz = t.C.Z - t.A.Z;
+        e1x[i] = lx; e1y[i] = ly; e1z[i] = lz; e2x[i] = mx; e2y[i] = my; e2z[i] = mz;
+        float nnx = ly * mz - lz * my, nny = lz * mx - lx * mz, nnz = lx * my - ly * mx;
+        float invLen = 1.0f / net_max(1e-20f, std::sqrt(nnx * nnx + nny * nny + nnz * nnz));
+        nx[i] = nnx * invLen; ny[i] = nny * invLen; nz[i] = nnz * invLen;
+    }
+    if (n) triMat = tris[0].Mat; // MeshLoader gives every triangle the same defaultMaterial (MeshLoader.cs:82)
+    ycge::build_reference_tree(items, 8, true, tree);
+}
+bool Mesh::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const { // MeshBVH.cs:585-603
+    const ycge::FlatTree &t = bvh->tree;
+    if (t.root < 0) { minX = minY = minZ = maxX = maxY = maxZ = cx = cy = cz = 0.0f; return false; }
+    minX = t.min_x[t.root]; minY = t.min_y[t.root]; minZ = t.min_z[t.root]; maxX = t.max_x[t.root]; maxY = t.max_y[t.root]; maxZ = t.max_z[t.root];
+    center_of(minX, minY, minZ, maxX, maxY, maxZ, cx, cy, cz);
+    return true;
+}
+void Mesh::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_MESH);
+    o.ref_id = (int)out.meshes.size();
+    out.meshes.push_back(bvh);
+    out.objects.push_back(o);
+}
+
+// ---- MeshLoader -------------------------------------------------------------------------------------------------
+static int ParseIndex(const std::string &token, int count) { // MeshLoader.cs:99-105
+    if (token.empty()) return 0;
+    int idx = std::atoi(token.c_str());
+    if (idx > 0) return idx - 1;
+    return count + idx;
+}
+ObjData MeshLoader::ParseObj(const std::string &path) { // MeshLoader.cs:23-56
+    std::ifstream f(path);
+    if (!f.good()) throw std::runtime_error("OBJ not found: " + path);
+    ObjData d;
+    std::string line;
+    std::vector<std::string> tok;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty() || line[0] == '#') continue;
+        tok.clear();
+        std::istringstream ss(line);
+        std::string t;
+        while (ss >> t) tok.push_back(t);
+        if (tok.empty()) continue;
+        if (tok[0] == "v" && tok.size() >= 4) {
+            d.positions.push_back(Vec3(std::strtof(tok[1].c_str(), nullptr), std::strtof(tok[2].c_str(), nullptr), std::strtof(tok[3].c_str(), nullptr)));
+        } else if (tok[0] == "f" && tok.size() >= 4) {
+            int faceVerts = (int)tok.size() - 1;
+            std::vector<int> vIdx(faceVerts);
+            for (int i = 0; i < faceVerts; i++) {
+                std::string part = tok[i + 1].substr(0, tok[i + 1].find('/'));
+                vIdx[i] = ParseIndex(part, (int)d.positions.size());
+            }
+            for (int i = 2; i < faceVerts; i++) { d.faces.push_back(vIdx[0]); d.faces.push_back(vIdx[i - 1]); d.faces.push_back(vIdx[i]); }
+        }
+    }
+    if (d.positions.empty() || d.faces.empty()) throw std::runtime_error("OBJ had no triangles.");
+    return d;
+}
+void MeshLoader::NormalizeAllUsedVertices(std::vector<Vec3> &pos, const std::vector<int> &faces, float targetSize) { // MeshLoader.cs:107-148
+    std::vector<char> used(pos.size(), 0);
+    for (int v : faces) used[v] = 1;
+    float minX = kInf, minY = kInf, minZ = kInf, maxX = -kInf, maxY = -kInf, maxZ = -kInf;
+    for (size_t vi = 0; vi < pos.size(); vi++) { // min/max are order-independent (HashSet enumeration order does not matter)
+        if (!used[vi]) continue;
+        const Vec3 &p = pos[vi];
+        if (p.X < minX) minX = p.X; if (p.Y < minY) minY = p.Y; if (p.Z < minZ) minZ = p.Z;
+        if (p.X > maxX) maxX = p.X; if (p.Y > maxY) maxY = p.Y; if (p.Z > maxZ) maxZ = p.Z;
+    }
+    if (std::isinf(minX) || std::isinf(minY) || std::isinf(minZ) || std::isinf(maxX) || std::isinf(maxY) || std::isinf(maxZ)) return;
+    float cx = (minX + maxX) * 0.5f, cy = (minY + maxY) * 0.5f, cz = (minZ + maxZ) * 0.5f;
+    float rx = maxX - minX, ry = maxY - minY, rz = maxZ - minZ;
+    float maxExtent = rx; if (ry > maxExtent) maxExtent = ry; if (rz > maxExtent) maxExtent = rz;
+    if (maxExtent <= 0.0f) maxExtent = 1.0f;
+    float s = targetSize / maxExtent;
+    for (size_t i = 0; i < pos.size(); i++) pos[i] = Vec3((pos[i].X - cx) * s, (pos[i].Y - cy) * s, (pos[i].Z - cz) * s);
+}
+std::shared_ptr<Mesh> MeshLoader::FromData(ObjData d, Material defaultMaterial, float scale, Vec3 t, bool normalize, float targetSize) { // MeshLoader.cs:58-97
+    if (d.positions.empty() || d.faces.empty()) throw std::runtime_error("OBJ had no triangles.");
+    std::vector<Vec3> &pos = d.positions;
+    if (normalize) NormalizeAllUsedVertices(pos, d.faces, targetSize);
+    if (scale != 1.0f || t.X != 0.0f || t.Y != 0.0f || t.Z != 0.0f)
+        for (size_t i = 0; i < pos.size(); i++) pos[i] = Vec3(pos[i].X * scale + t.X, pos[i].Y * scale + t.Y, pos[i].Z * scale + t.Z);
+    float minX = kInf, minY = kInf, minZ = kInf, maxX = -kInf, maxY = -kInf, maxZ = -kInf;
+    std::vector<Triangle> tris;
+    tris.reserve(d.faces.size() / 3);
+    for (size_t i = 0; i + 2 < d.faces.size(); i += 3) {
+        Vec3 a = pos[d.faces[i]], b = pos[d.faces[i + 1]], c = pos[d.faces[i + 2]];
+        tris.emplace_back(a, b, c, defaultMaterial);
+        for (const Vec3 *p : {&a, &b, &c}) {
+            if (p->X < minX) minX = p->X; if (p->Y < minY) minY = p->Y; if (p->Z < minZ) minZ = p->Z;
+            if (p->X > maxX) maxX = p->X; if (p->Y > maxY) maxY = p->Y; if (p->Z > maxZ) maxZ = p->Z;
+        }
+    }
+    return std::make_shared<Mesh>(tris, Vec3(minX, minY, minZ), Vec3(maxX, maxY, maxZ));
+}
+std::shared_ptr<Mesh> MeshLoader::FromObj(const std::string &path, Material m, float scale, Vec3 translate, bool normalize, float targetSize) {
+    if (path.empty()) throw std::invalid_argument("path");
+    return FromData(ParseObj(path), m, scale, translate, normalize, targetSize);
+}
+// MeshScenes.TryReadObjBoundsNormalized (MeshScenes.cs:186-331): bounds of the largest connected component, centred on
+// the area-unweighted triangle-centroid mean, scaled to unit max extent. Only min.Y is consumed (AddMeshAutoGround).
+bool MeshLoader::BoundsNormalizedLargestComponent(const ObjData &d, Vec3 &mn, Vec3 &mx) {
+    int vCount = (int)d.positions.size(), fCount = (int)d.faces.size() / 3;
+    if (vCount == 0 || fCount == 0) return false;
+    std::vector<int> parent(vCount), rank(vCount, 0);
+    for (int i = 0; i < vCount; i++) parent[i] = i;
+    auto Find = [&](int x) { while (x != parent[x]) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    auto Union = [&](int x, int y) {
+        int rx = Find(x), ry = Find(y);
+        if (rx == ry) return;
+        if (rank[rx] < rank[ry]) parent[rx] = ry; else if (rank[rx] > rank[ry]) parent[ry] = rx; else { parent[ry] = rx; rank[rx]++; }
+    };
+    for (int i = 0; i < fCount; i++) { Union(d.faces[3 * i], d.faces[3 * i + 1]); Union(d.faces[3 * i + 1], d.faces[3 * i + 2]); }
+    // Dictionary<int,List<int>> enumerates in insertion order (no removals): first component reaching the max count wins
+    std::vector<int> order;
+    std::unordered_map<int, std::vector<int>> comp;
+    for (int i = 0; i < fCount; i++) {
+        int r = Find(d.faces[3 * i]);
+        auto it = comp.find(r);
+        if (it == comp.end()) { order.push_back(r); comp[r].push_back(i); } else it->second.push_back(i);
+    }
+    int bestRoot = -1, bestCount = -1;
+    for (int r : order) { int cnt = (int)comp[r].size(); if (cnt > bestCount) { bestCount = cnt; bestRoot = r; } }
+    if (bestRoot == -1) return false;
+    const std::vector<int> &fi = comp[bestRoot];
+    std::vector<char> used(vCount, 0);
+    for (int f : fi) { used[d.faces[3 * f]] = 1; used[d.faces[3 * f + 1]] = 1; used[d.faces[3 * f + 2]] = 1; }
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    for (int f : fi) { // float accumulation in kept-face order (:291-301)
+        const Vec3 &A = d.positions[d.faces[3 * f]], &B = d.positions[d.faces[3 * f + 1]], &C = d.positions[d.faces[3 * f + 2]];
+        cx += (A.X + B.X + C.X) * (1.0f / 3.0f); cy += (A.Y + B.Y + C.Y) * (1.0f / 3.0f); cz += (A.Z + B.Z + C.Z) * (1.0f / 3.0f);
+    }
+    int triCount = (int)fi.size();
+    float invT = 1.0f / triCount;
+    cx *= invT; cy *= invT; cz *= invT;
+    float rMinX = kInf, rMinY = kInf, rMinZ = kInf, rMaxX = -kInf, rMaxY = -kInf, rMaxZ = -kInf;
+    for (int v = 0; v < vCount; v++) {
+        if (!used[v]) continue;
+        float x = d.positions[v].X - cx, y = d.positions[v].Y - cy, z = d.positions[v].Z - cz;
+        if (x < rMinX) rMinX = x; if (y < rMinY) rMinY = y; if (z < rMinZ) rMinZ = z;
+        if (x > rMaxX) rMaxX = x; if (y > rMaxY) rMaxY = y; if (z > rMaxZ) rMaxZ = z;
+    }
+    float rx = rMaxX - rMinX, ry = rMaxY - rMinY, rz = rMaxZ - rMinZ;
+    float maxExtent = rx; if (ry > maxExtent) maxExtent = ry; if (rz > maxExtent) maxExtent = rz;
+    if (maxExtent <= 0.0f) maxExtent = 1.0f;
+    float s = 1.0f / maxExtent;
+    mn = Vec3(rMinX * s, rMinY * s, rMinZ * s);
+    mx = Vec3(rMaxX * s, rMaxY * s, rMaxZ * s);
+    return true;
+}
+
+// ---- VolumeGrid -------------------------------------------------------------------------------------------------
+int VolumeGrid::Morton3_3bits(int x, int y, int z) { // VolumeGrid.cs:246-252
+    return ((x & 1) << 0) | ((y & 1) << 1) | ((z & 1) << 2) | ((x & 2) << 2) | ((y & 2) << 3) | ((z & 2) << 4) | ((x & 4) << 4) | ((y & 4) << 5) | ((z & 4) << 6);
+}
+int VolumeGrid::IndexOf(int ix, int iy, int iz) const { // VolumeGrid.cs:235-242
+    int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
+    int brickLinear = ((bz * nby) + by) * nbx + bx;
+    return brickLinear * 512 + Morton3_3bits(ix & 7, iy & 7, iz & 7);
+}
+VolumeGrid::VolumeGrid(int nx_, int ny_, int nz_, const std::function<void(int, int, int, int &, int &)> &cells, Vec3 minCorner_, Vec3 voxelSize_,
+                       std::shared_ptr<VoxelPalette> lookup, bool enableWireframe, float wireWidthFraction, float wireMaxDistance_)
+    : nx(nx_), ny(ny_), nz(nz_), minCorner(minCorner_), palette(lookup), wireframe(enableWireframe) {
+    nbx = (nx + 7) >> 3; nby = (ny + 7) >> 3; nbz = (nz + 7) >> 3;
+    size_t capacity = (size_t)nbx * nby * nbz * 512;
+    mat.assign(capacity, 0); meta.assign(capacity, 0);
+    voxelSize = Vec3(net_max(1e-6f, voxelSize_.X), net_max(1e-6f, voxelSize_.Y), net_max(1e-6f, voxelSize_.Z));
+    if (wireWidthFraction < 0.0f) wireWidthFraction = 0.0f; if (wireWidthFraction > 0.5f) wireWidthFraction = 0.5f;
+    wireWidthFrac = wireWidthFraction;
+    if (wireMaxDistance_ < 0.0f) wireMaxDistance_ = 0.0f;
+    wireMaxDistance = wireMaxDistance_;
+    for (int iz = 0; iz < nz; iz++) for (int iy = 0; iy < ny; iy++) for (int ix = 0; ix < nx; ix++) {
+        int m = 0, e = 0;
+        cells(ix, iy, iz, m, e);
+        int idx = IndexOf(ix, iy, iz);
+        mat[idx] = m; meta[idx] = e;
+    }
+}
+bool VolumeGrid::AnySolid() const { for (int v : mat) if (v > 0) return true; return false; }
+bool VolumeGrid::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const { // :386-403
+    if (nx <= 0 || ny <= 0 || nz <= 0) { minX = minY = minZ = maxX = maxY = maxZ = cx = cy = cz = 0.0f; return false; }
+    minX = minCorner.X; minY = minCorner.Y; minZ = minCorner.Z;
+    maxX = minCorner.X + nx * voxelSize.X; maxY = minCorner.Y + ny * voxelSize.Y; maxZ = minCorner.Z + nz * voxelSize.Z;
+    center_of(minX, minY, minZ, maxX, maxY, maxZ, cx, cy, cz);
+    return true;
+}
+void VolumeGrid::Export(SceneExport &out) const {
+    ycge_object o = blank_object(YCGE_VOLUME);
+    o.ref_id = (int)out.volumes.size();
+    out.volumes.push_back(this);
+    std::vector<int32_t> table(palette->table.size());
+    std::vector<int> slot(palette->materials.size());
+    for (size_t i = 0; i < palette->materials.size(); i++) slot[i] = out.AddMaterial(palette->materials[i]);
+    for (size_t i = 0; i < table.size(); i++) table[i] = slot[palette->table[i]];
+    table.push_back(slot[palette->def]); // last entry: default
+    out.volume_palettes.push_back(table);
+    out.objects.push_back(o);
+}
+
+// ---- BVH --------------------------------------------------------------------------------------------------------
+BVH::BVH(const std::vector<std::shared_ptr<Hittable>> &objects) { // BVH.cs:29-97
+    std::vector<ycge::BuildItem> items;
+    for (size_t i = 0; i < objects.size(); i++) {
+        ycge::BuildItem it;
+        it.index = (int)i;
+        if (!objects[i]->TryGetBounds(it.box.lo[0], it.box.lo[1], it.box.lo[2], it.box.hi[0], it.box.hi[1], it.box.hi[2], it.c[0], it.c[1], it.c[2]))
+            throw std::runtime_error("Unbounded Hittable");
+        items.push_back(it);
+    }
+    ycge::build_reference_tree(items, 4, false, tree);
+}
+
+// ---- scene factories: Scenes/Scenes.cs --------------------------------------------------------------------------
+namespace Scenes {
+std::shared_ptr<Scene> BuildTestScene() { // :11-35
+    auto s = std::make_shared<Scene>(); s->Name = "test";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.01f);
+    Material red(Vec3(1.0, 0.0, 0.0), 0.15, 0.0, Vec3()), green(Vec3(0.0, 1.0, 0.0), 0.15, 0.0, Vec3()), blue(Vec3(0.0, 0.0, 1.0), 0.15, 0.0, Vec3());
+    Material mirror(Vec3(0.98, 0.98, 0.98), 0.0, 0.9, Vec3());
+    float r = 0.9f;
+    s->Add(std::make_shared<Sphere>(Vec3(-1.2, (double)r, -2.2), r, red));
+    s->Add(std::make_shared<Sphere>(Vec3(1.2, (double)r, -2.2), r, green));
+    s->Add(std::make_shared<Sphere>(Vec3(-1.2, (double)r, -3.6), r, blue));
+    s->Add(std::make_shared<Sphere>(Vec3(1.2, (double)r, -3.6), r, mirror));
+    s->Lights.push_back(PointLight(Vec3(0.0, 3.2, -2.9), Vec3(1.0, 1.0, 1.0), 140.0f));
+    s->Lights.push_back(PointLight(Vec3(-2.2, 2.0, -2.4), Vec3(1.0, 1.0, 1.0), 60.0f));
+    s->BackgroundTop = Vec3(0.05, 0.05, 0.05); s->BackgroundBottom = Vec3(0.05, 0.05, 0.05);
+    s->Update(0.0f);
+    return s;
+}
+std::shared_ptr<Scene> BuildCornellBox() { // :269-309
+    auto s = std::make_shared<Scene>(); s->Name = "cornell";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.00f);
+    MaterialFunc white = Solid(Vec3(0.82, 0.82, 0.82)), red = Solid(Vec3(0.80, 0.10, 0.10)), green = Solid(Vec3(0.10, 0.80, 0.10)), lightEmit = Emissive(Vec3(0.6, 0.6, 0.6));
+    float xL = -3.0f, xR = 3.0f, yB = 0.0f, yT = 5.0f, zF = 0.0f, zB = -5.0f;
+    s->Add(YZRect(yB, yT, zB, zF, xL, red, 0.0f, 0.0f));
+    s->Add(YZRect(yB, yT, zB, zF, xR, green, 0.0f, 0.0f));
+    s->Add(XZRect(xL, xR, zB, zF, yB, white, 0.0f, 0.0f));
+    s->Add(XZRect(xL, xR, zB, zF, yT, white, 0.0f, 0.0f));
+    s->Add(XYRect(xL, xR, yB, yT, zB, white, 0.0f, 0.0f));
+    float lx0 = -0.9f, lx1 = 0.9f, lz0 = -3.2f, lz1 = -2.2f, ly = yT - 0.01f;
+    s->Add(XZRect(lx0, lx1, lz0, lz1, ly, lightEmit, 0.0f, 0.0f));
+    s->Add(std::make_shared<Box>(Vec3(-2.2, 0.0, -4.0), Vec3(-0.8, 1.0, -2.8), white, 0.0f, 0.0f));
+    s->Add(std::make_shared<Box>(Vec3(0.6, 0.0, -3.3), Vec3(2.0, 1.8, -2.1), white, 0.0f, 0.0f));
+    s->Lights.push_back(PointLight(Vec3(0.0, 4.6, -2.7), Vec3(1.0, 1.0, 1.0), 20.0f));
+    s->BackgroundTop = Vec3(0.0, 0.0, 0.0); s->BackgroundBottom = Vec3(0.0, 0.0, 0.0);
+    s->Update(0.0f);
+    return s;
+}
+std::shared_ptr<Scene> BuildMirrorSpheresOnChecker() { // :311-335
+    auto s = std::make_shared<Scene>(); s->Name = "mirror_spheres";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.01f);
+    MaterialFunc floor = Checker(Vec3(0.8, 0.8, 0.8), Vec3(0.15, 0.15, 0.15), 0.6f);
+    s->Add(XZRect(-8.0f, 8.0f, -8.0f, 4.0f, 0.0f, floor, 0.1f, 0.0f));
+    Material gold(Vec3(1.0, 0.85, 0.57), 0.25, 0.1, Vec3()), glassy(Vec3(0.9, 0.95, 1.0), 0.0, 0.6, Vec3()), mirror(Vec3(0.98, 0.98, 0.98), 0.0, 0.85, Vec3());
+    s->Add(std::make_shared<Sphere>(Vec3(-1.2, 1.0, -2.0), 1.0f, gold));
+    s->Add(std::make_shared<Sphere>(Vec3(1.3, 1.0, -2.6), 1.0f, glassy));
+    s->Add(std::make_shared<Sphere>(Vec3(0.0, 0.5, -4.2), 0.5f, mirror));
+    s->Lights.push_back(PointLight(Vec3(-2.5, 3.5, -1.5), Vec3(1.0, 0.95, 0.9), 90.0f));
+    s->Lights.push_back(PointLight(Vec3(2.0, 2.8, -3.8), Vec3(0.9, 0.95, 1.0), 70.0f));
+    s->BackgroundTop = Vec3(0.55, 0.75, 1.0); s->BackgroundBottom = Vec3(0.95, 0.98, 1.0);
+    s->Update(0.0f);
+    return s;
+}
+std::shared_ptr<Scene> BuildCylindersDisksAndTriangles() { // :359-383
+    auto s = std::make_shared<Scene>(); s->Name = "cylinders_disks_triangles";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.01f);
+    MaterialFunc floor = Checker(Vec3(0.75, 0.75, 0.75), Vec3(0.2, 0.2, 0.2), 0.8f);
+    s->Add(std::make_shared<Plane>(Vec3(0.0, 0.0, 0.0), Vec3(0.0, 1.0, 0.0), floor, 0.05f, 0.0f));
+    Material matteBlue(Vec3(0.2, 0.35, 0.9), 0.1, 0.0, Vec3()), matteRed(Vec3(0.9, 0.25, 0.25), 0.1, 0.0, Vec3());
+    s->Add(std::make_shared<CylinderY>(Vec3(-1.2, 0.0, -3.0), 0.6f, 0.0f, 1.6f, true, matteBlue));
+    s->Add(std::make_shared<Disk>(Vec3(1.6, 0.01, -2.2), Vec3(0.0, 1.0, 0.0), 0.9f, Solid(Vec3(0.8, 0.8, 0.1)), 0.0f, 0.0f));
+    s->Add(std::make_shared<Triangle>(Vec3(0.2, 0.0, -3.6), Vec3(1.3, 1.4, -3.0), Vec3(-0.7, 0.7, -2.8), matteRed));
+    s->Lights.push_back(PointLight(Vec3(-2.2, 3.2, -2.0), Vec3(1.0, 0.95, 0.9), 70.0f));
+    s->Lights.push_back(PointLight(Vec3(2.4, 2.2, -4.4), Vec3(0.9, 0.95, 1.0), 60.0f));
+    s->BackgroundTop = Vec3(0.58, 0.78, 1.0); s->BackgroundBottom = Vec3(0.95, 0.98, 1.0);
+    s->Update(0.0f);
+    return s;
+}
+std::shared_ptr<Scene> BuildBoxesShowcase() { // :385-406
+    auto s = std::make_shared<Scene>(); s->Name = "boxes";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.01f);
+    MaterialFunc floor = Checker(Vec3(0.85, 0.85, 0.85), Vec3(0.15, 0.15, 0.15), 0.7f);
+    s->Add(std::make_shared<Plane>(Vec3(0.0, 0.0, 0.0), Vec3(0.0, 1.0, 0.0), floor, 0.05f, 0.0f));
+    MaterialFunc white = Solid(Vec3(0.86, 0.86, 0.86));
+    s->Add(std::make_shared<Box>(Vec3(-2.2, 0.0, -3.6), Vec3(-1.0, 1.2, -2.4), white, 0.1f, 0.0f));
+    s->Add(std::make_shared<Box>(Vec3(-0.6, 0.0, -4.2), Vec3(0.6, 0.6, -3.0), white, 0.1f, 0.4f));
+    s->Add(std::make_shared<Box>(Vec3(1.0, 0.0, -3.0), Vec3(2.4, 2.0, -1.8), white, 0.0f, 0.0f));
+    s->Lights.push_back(PointLight(Vec3(-2.0, 3.0, -2.0), Vec3(1.0, 0.95, 0.9), 70.0f));
+    s->Lights.push_back(PointLight(Vec3(2.0, 2.5, -4.2), Vec3(0.9, 0.95, 1.0), 50.0f));
+    s->BackgroundTop = Vec3(0.6, 0.8, 1.0); s->BackgroundBottom = Vec3(0.95, 0.98, 1.0);
+    s->Update(0.0f);
+    return s;
+}
+std::shared_ptr<Scene> BuildVolumeGridTestScene() { // :36-161
+    auto s = std::make_shared<Scene>(); s->Name = "volume_grid_test";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.01f);
+    const int nx = 16, ny = 8, nz = 16;
+    std::vector<int> cm((size_t)nx * ny * nz, 0), ce((size_t)nx * ny * nz, 0);
+    auto at = [&](int x, int y, int z) { return ((size_t)x * ny + y) * nz + z; };
+    for (int x = 0; x < nx; x++) for (int z = 0; z < nz; z++) cm[at(x, 0, z)] = 1;
+    for (int y = 1; y <= 3; y++) {
+        for (int x = 0; x < nx; x++) { cm[at(x, y, 0)] = 1; cm[at(x, y, nz - 1)] = 1; }
+        for (int z = 0; z < nz; z++) { cm[at(0, y, z)] = 1; cm[at(nx - 1, y, z)] = 1; }
+    }
+    auto Pillar = [&](int cx, int cz, int height, int m) { for (int y = 1; y <= height && y < ny; y++) { cm[at(cx, y, cz)] = m; ce[at(cx, y, cz)] = 0; } };
+    Pillar(4, 4, 4, 2); Pillar(11, 4, 3, 3); Pillar(4, 11, 5, 4); Pillar(11, 11, 4, 5);
+    for (int x = 6; x <= 9; x++) for (int z = 6; z <= 9; z++) { bool check = ((x + z) & 1) == 0; cm[at(x, 1, z)] = check ? 1 : 4; ce[at(x, 1, z)] = 0; }
+    cm[at(2, 1, 2)] = 2; ce[at(2, 1, 2)] = 101; cm[at(13, 1, 2)] = 3; ce[at(13, 1, 2)] = 102;
+    cm[at(2, 1, 13)] = 4; ce[at(2, 1, 13)] = 103; cm[at(13, 1, 13)] = 5; ce[at(13, 1, 13)] = 104;
+    auto pal = std::make_shared<VoxelPalette>(); // materialLookup :107-118: switch on id, meta ignored
+    pal->n_ids = 6; pal->meta_levels = 1;
+    pal->materials = {Material(Vec3(0.7, 0.7, 0.7), 0.0, 0.0, Vec3()), Material(Vec3(0.82, 0.82, 0.85), 0.0, 0.0, Vec3()), Material(Vec3(0.95, 0.15, 0.15), 0.05, 0.0, Vec3()),
+                      Material(Vec3(0.15, 0.95, 0.20), 0.05, 0.0, Vec3()), Material(Vec3(0.15, 0.25, 0.95), 0.05, 0.0, Vec3()), Material(Vec3(0.98, 0.98, 0.98), 0.0, 0.9, Vec3())};
+    pal->table = {0, 1, 2, 3, 4, 5}; pal->def = 0;
+    s->Add(std::make_shared<VolumeGrid>(nx, ny, nz, [&](int x, int y, int z, int &m, int &e) { m = cm[at(x, y, z)]; e = ce[at(x, y, z)]; },
+                                        Vec3(-4.0, 0.0, -6.0), Vec3(0.5, 0.5, 0.5), pal));
+    Material pedestalMat(Vec3(0.85, 0.85, 0.85), 0.0, 0.0, Vec3()), red(Vec3(0.95, 0.15, 0.15), 0.05, 0.0, Vec3()), green(Vec3(0.15, 0.95, 0.20), 0.05, 0.0, Vec3());
+    Material blue(Vec3(0.15, 0.25, 0.95), 0.05, 0.0, Vec3()), mirror(Vec3(0.98, 0.98, 0.98), 0.0, 0.9, Vec3());
+    Material clear(Vec3(1.0, 1.0, 1.0), 0.0, 0.02, Vec3(), 1.0, 1.5, Vec3(1.0, 1.0, 1.0));
+    float pedR = 0.25f, pedH = 1.2f, sphR = 0.35f;
+    Vec3 centerXZ(0.0, 0.0, -2.0), posL(-1.6, 0.0, -2.0), posR(1.6, 0.0, -2.0), posF(0.0, 0.0, -0.8), posB(0.0, 0.0, -3.2);
+    for (Vec3 p : {posL, posR, posF, posB}) s->Add(std::make_shared<CylinderY>(p, pedR, 0.0f, pedH, true, pedestalMat));
+    Vec3 up(0.0, (double)(pedH + sphR), 0.0);
+    s->Add(std::make_shared<Sphere>(posL + up, sphR, mirror));
+    s->Add(std::make_shared<Sphere>(posR + up, sphR, red));
+    s->Add(std::make_shared<Sphere>(posF + up, sphR, blue));
+    s->Add(std::make_shared<Sphere>(posB + up, sphR, green));
+    float clearR = 0.5f;
+    s->Add(std::make_shared<Sphere>(Vec3(centerXZ.X, centerXZ.Y + 2, centerXZ.Z), clearR, clear));
+    s->Lights.push_back(PointLight(Vec3(0.0, 5.0, -3.0), Vec3(1.0, 1.0, 1.0), 220.0f));
+    s->Lights.push_back(PointLight(Vec3(-2.5, 3.0, -1.8), Vec3(1.0, 0.95, 0.9), 90.0f));
+    s->BackgroundTop = Vec3(0.02, 0.02, 0.02); s->BackgroundBottom = Vec3(0.02, 0.02, 0.02);
+    s->Update(0.0f);
+    return s;
+}
+} // namespace Scenes
+
+// ---- Scenes/MeshScenes.cs ---------------------------------------------------------------------------------------
+namespace MeshScenes {
+std::string AssetDir = "assets";
+static Vec3 ScaleC(Vec3 v, float k) { if (k < 0.0f) k = 0.0f; if (k > 1.0f) k = 1.0f; return Vec3(v.X * k, v.Y * k, v.Z * k); } // MeshSwatches.Scale :47-53
+static std::shared_ptr<Scene> NewBaseScene() { // :160-171
+    MeshBVH::counter = 0;
+    auto s = std::make_shared<Scene>();
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.15f);
+    s->Objects.push_back(std::make_shared<Plane>(Vec3(0.0, 0.0, 0.0), Vec3(0.0, 1.0, 0.0), Solid(Vec3(1.0f, 1.0f, 1.0f)), 0.01f, 0.00f));
+    s->Lights.push_back(PointLight(Vec3(0.0, 30.6, -4.2), Vec3(1.0, 0.95, 0.88), 110.0f));
+    s->Lights.push_back(PointLight(Vec3(0.0, 30.0, 4.2), Vec3(0.85, 0.90, 1.0), 85.0f));
+    s->BackgroundTop = Vec3(0.0, 0.0, 0.0); s->BackgroundBottom = Vec3(0.0, 0.0, 0.0);
+    return s;
+}
+static void AddMeshAutoGround(Scene &s, const ObjData &obj, Material mat, float scale, Vec3 targetPos) { // :173-184
+    Vec3 mnN, mxN;
+    if (!MeshLoader::BoundsNormalizedLargestComponent(obj, mnN, mxN)) throw std::runtime_error("OBJ not found or empty");
+    float minYNormalized = mnN.Y;
+    float yTranslate = targetPos.Y - minYNormalized * scale + 0.01f;
+    Vec3 translate(targetPos.X, yTranslate, targetPos.Z);
+    s.Objects.push_back(MeshLoader::FromData(obj, mat, scale, translate, true, 1.0f));
+}
+std::shared_ptr<Scene> BuildMeshScene(const ObjData &mesh, Material mat, const std::string &name, Vec3 targetPos) {
+    auto s = NewBaseScene(); s->Name = name;
+    AddMeshAutoGround(*s, mesh, mat, 1.0f, targetPos);
+    s->RebuildBVH();
+    return s;
+}
+std::shared_ptr<Scene> BuildCowScene() { // :108-115; Gold = Scale(Yellow, 0.90)
+    return BuildMeshScene(MeshLoader::ParseObj(AssetDir + "/cow.obj"), Material(ScaleC(Vec3(1.0f, 1.0f, 0.0f), 0.90f), 0.08, 0.00, Vec3()), "cow");
+}
+std::shared_ptr<Scene> BuildBunnyScene() { // :117-124; Emerald = Scale(Green, 0.85)
+    return BuildMeshScene(MeshLoader::ParseObj(AssetDir + "/stanford-bunny.obj"), Material(ScaleC(Vec3(0.0f, 1.0f, 0.0f), 0.85f), 0.12, 0.00, Vec3()), "bunny");
+}
+std::shared_ptr<Scene> BuildTeapotScene() { // :126-133; Ruby = Scale(Red, 0.92)
+    return BuildMeshScene(MeshLoader::ParseObj(AssetDir + "/teapot.obj"), Material(ScaleC(Vec3(1.0f, 0.0f, 0.0f), 0.92f), 0.30, 0.06, Vec3()), "teapot");
+}
+ObjData ProceduralKnot(int segU, int segV) {
+    // "dragon-standin": a (2,3) torus knot tube with scale-like bumps. Deterministic double-precision construction;
+    // it is scene *input* (both the oracle and the GPU consume the same vertices), so libm here is harmless.
+    ObjData d;
+    d.positions.reserve((size_t)segU * segV);
+    const double PI = 3.14159265358979323846;
+    auto curve = [&](double u, double o[3]) {
+        double r = 2.0 + std::cos(3.0 * u);
+        o[0] = r * std::cos(2.0 * u); o[1] = std::sin(3.0 * u); o[2] = r * std::sin(2.0 * u);
+    };
+    for (int i = 0; i < segU; i++) {
+        double u = 2.0 * PI * i / segU, c0[3], c1[3], c2[3];
+        curve(u, c0); curve(u + 1e-4, c1); curve(u - 1e-4, c2);
+        double T[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+        double tl = std::sqrt(T[0] * T[0] + T[1] * T[1] + T[2] * T[2]);
+        for (double &v : T) v /= tl;
+        double A[3] = {c1[0] + c2[0] - 2 * c0[0], c1[1] + c2[1] - 2 * c0[1], c1[2] + c2[2] - 2 * c0[2]}; // curvature direction
+        double ad = A[0] * T[0] + A[1] * T[1] + A[2] * T[2];
+        double N[3] = {A[0] - ad * T[0], A[1] - ad * T[1], A[2] - ad * T[2]};
+        double nl = std::sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+        for (double &v : N) v /= nl;
+        double B[3] = {T[1] * N[2] - T[2] * N[1], T[2] * N[0] - T[0] * N[2], T[0] * N[1] - T[1] * N[0]};
+        for (int j = 0; j < segV; j++) {
+            double v = 2.0 * PI * j / segV;
+            double rad = 0.42 * (1.0 + 0.18 * std::sin(40.0 * u) * std::sin(6.0 * v) + 0.10 * std::cos(9.0 * u + 2.0 * v));
+            double cx = std::cos(v) * rad, sx = std::sin(v) * rad;
+            d.positions.push_back(Vec3(c0[0] + cx * N[0] + sx * B[0], c0[1] + cx * N[1] + sx * B[1], c0[2] + cx * N[2] + sx * B[2]));
+        }
+    }
+    d.faces.reserve((size_t)segU * segV * 6);
+    for (int i = 0; i < segU; i++) for (int j = 0; j < segV; j++) {
+        int i1 = (i + 1) % segU, j1 = (j + 1) % segV;
+        int a = i * segV + j, b = i1 * segV + j, c = i1 * segV + j1, e = i * segV + j1;
+        d.faces.push_back(a); d.faces.push_back(b); d.faces.push_back(c);
+        d.faces.push_back(a); d.faces.push_back(c); d.faces.push_back(e);
+    }
+    return d;
+}
+std::shared_ptr<Scene> BuildDragonScene() { // :135-143; Sapphire = Scale(Blue, 0.85); Mirror(tint, 0.70) -> shades as diffuse (0.70 < 0.9)
+    Material dragonMat(ScaleC(Vec3(0.0f, 0.0f, 1.0f), 0.85f), 0.0, 0.70, Vec3());
+    std::shared_ptr<Scene> s;
+    std::ifstream probe(AssetDir + "/xyzrgb_dragon.obj");
+    if (probe.good()) s = BuildMeshScene(MeshLoader::ParseObj(AssetDir + "/xyzrgb_dragon.obj"), dragonMat, "dragon");
+    else s = BuildMeshScene(ProceduralKnot(1400, 100), dragonMat, "dragon-standin");
+    s->DefaultCameraPos = Vec3(0.0f, 10.0f, 0.0f);
+    return s;
+}
+} // namespace MeshScenes
+
+// ---- synthetic voxel world with the structure BuildMinecraftLike produces ---------------------------------------
+namespace VolumeScenes {
+static uint32_t hash2(int x, int z) {
+    uint32_t h = 2166136261u;
+    h = (h ^ (uint32_t)x) * 16777619u; h = (h ^ (uint32_t)z) * 16777619u;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
+    return h;
+}
+static float lattice(int x, int z) { return (float)(hash2(x, z) & 0xFFFFFF) * (1.0f / 16777215.0f); }
+static float value_noise(float x, float z) {
+    float fx = std::floor(x), fz = std::floor(z);
+    int ix = (int)fx, iz = (int)fz;
+    float tx = x - fx, tz = z - fz;
+    tx = tx * tx * (3.0f - 2.0f * tx); tz = tz * tz * (3.0f - 2.0f * tz);
+    float a = lattice(ix, iz), b = lattice(ix + 1, iz), c = lattice(ix, iz + 1), d = lattice(ix + 1, iz + 1);
+    return (a + (b - a) * tx) + ((c + (d - c) * tx) - (a + (b - a) * tx)) * tz;
+}
+float SyntheticHeight(int x, int z, int worldHeight) {
+    float n = 0.65f * value_noise(x * (1.0f / 96.0f), z * (1.0f / 96.0f)) + 0.25f * value_noise(x * (1.0f / 24.0f) + 17.0f, z * (1.0f / 24.0f) - 9.0f) +
+              0.10f * value_noise(x * (1.0f / 6.0f) - 3.0f, z * (1.0f / 6.0f) + 41.0f);
+    float h = 0.25f * worldHeight + 0.1875f * worldHeight * n; // 64 + 48*n for a 256-high world
+    return h;
+}
+static std::shared_ptr<VoxelPalette> WorldPalette() { // Scenes/VoxelMaterialPalette.cs:10-98
+    static const float P16[16][3] = {{0, 0, 0}, {0, 0, .5f}, {0, .5f, 0}, {0, .5f, .5f}, {.5f, 0, 0}, {.5f, 0, .5f}, {.5f, .5f, 0}, {.75f, .75f, .75f},
+                                     {.5f, .5f, .5f}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {1, 0, 0}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1}};
+    auto pal = std::make_shared<VoxelPalette>();
+    for (int i = 0; i < 16; i++) pal->materials.push_back(Material(Vec3(P16[i][0], P16[i][1], P16[i][2]), 0.05, 0.00, Vec3(0.0, 0.0, 0.0)));
+    pal->n_ids = 12; pal->meta_levels = 3;
+    static const int tbl[12][3] = {{0, 0, 0}, {8, 7, 15}, {6, 6, 6}, {10, 10, 10}, {9, 9, 9}, {14, 14, 14}, {6, 6, 6}, {2, 2, 2}, {15, 15, 15}, {0, 7, 14}, {10, 10, 10}, {12, 12, 12}};
+    for (int id = 0; id < 12; id++) for (int m = 0; m < 3; m++) pal->table.push_back(tbl[id][m]);
+    pal->def = 8; // Normalize(default) -> (Stone, 0) -> PalMat(8)
+    return pal;
+}
+std::shared_ptr<Scene> BuildSyntheticWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds) {
+    auto s = std::make_shared<Scene>(); s->Name = "voxel_world_synthetic"; s->IsVolumeScene = true;
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.0f);
+    auto pal = WorldPalette();
+    const int seaLevel = worldHeight / 4 + 2;
+    int chunksX = worldSize / chunkSize, chunksY = worldHeight / chunkSize, chunksZ = worldSize / chunkSize;
+    Vec3 worldMin((float)(-worldSize / 2), 0.0f, (float)(-worldSize / 2)); // VolumeScenes.cs:588
+    std::vector<int> hmap((size_t)worldSize * worldSize);
+    for (int z = 0; z < worldSize; z++) for (int x = 0; x < worldSize; x++) hmap[(size_t)z * worldSize + x] = (int)SyntheticHeight(x, z, worldHeight);
+    for (int cz = 0; cz < chunksZ; cz++) for (int cy = 0; cy < chunksY; cy++) for (int cx = 0; cx < chunksX; cx++) {
+        int baseX = cx * chunkSize, baseY = cy * chunkSize, baseZ = cz * chunkSize;
+        auto cell = [&](int ix, int iy, int iz, int &m, int &e) {
+            int wx = baseX + ix, wy = baseY + iy, wz = baseZ + iz;
+            int h = hmap[(size_t)wz * worldSize + wx];
+            e = 0;
+            if (wy > h) { m = (wy <= seaLevel) ? 4 : 0; return; }              // water fills up to sea level
+            if (wy == h) { m = h <= seaLevel + 1 ? 5 : (h > (int)(0.40f * worldHeight) ? 8 : 3); return; } // sand / snow / grass
+            if (wy >= h - 3) { m = 2; return; }                                // dirt
+            m = 1; e = (int)(hash2(wx * 7 + wy, wz * 13 - wy) % 3u);          // stone, strata meta 0..2
+        };
+        // all-air chunks are skipped (WorldManager.cs:720,759)
+        bool any = false;
+        for (int iz = 0; iz < chunkSize && !any; iz++) for (int ix = 0; ix < chunkSize && !any; ix++) {
+            int h = std::max(hmap[(size_t)(baseZ + iz) * worldSize + baseX + ix], seaLevel);
+            if (h >= baseY) any = true;
+        }
+        if (!any) continue;
+        Vec3 minCorner(worldMin.X + baseX * 1.0f, worldMin.Y + baseY * 1.0f, worldMin.Z + baseZ * 1.0f); // WorldManager.cs:764-768
+        s->Add(std::make_shared<VolumeGrid>(chunkSize, chunkSize, chunkSize, cell, minCorner, Vec3(1.0f, 1.0f, 1.0f), pal));
+    }
+    // DayNightEntity.Update at time = daySeconds (Scenes/DayNightCycle.cs:41-91), cycle 120 s, radius 2000
+    {
+        const float cycleSeconds = 120.0f, sunRadius = 2000.0f, PI = 3.14159274f;
+        float t01 = std::fmod(daySeconds, cycleSeconds) / cycleSeconds;
+        float theta = (t01 * 2.0f * PI) - PI * 0.5f;
+        float sx = std::cos(theta), sy = std::sin(theta), sz = 0.25f;
+        float norm = std::sqrt(sx * sx + sy * sy + sz * sz);
+        sx /= norm; sy /= norm; sz /= norm;
+        Vec3 sunPos((double)(sx * sunRadius), std::max(50.0, (double)(sy * sunRadius)), (double)(sz * sunRadius));
+        Vec3 moonPos((double)-sunPos.X, std::max(50.0, (double)-sunPos.Y), (double)-sunPos.Z);
+        float sunN = std::max(0.0f, sy), moonN = std::max(0.0f, -sy);
+        float sunI = sunN * sunN, moonI = std::sqrt(moonN) * 0.10f;
+        s->Lights.push_back(PointLight(sunPos, Vec3(1.00, 0.96, 0.88), 300000.0f * sunI));
+        s->Lights.push_back(PointLight(moonPos, Vec3(0.65, 0.70, 0.90), 8000.0f * moonI));
+        float skyBlend = sunI * 1.5f; skyBlend = skyBlend < 0.0f ? 0.0f : (skyBlend > 1.0f ? 1.0f : skyBlend);
+        auto lerp = [&](Vec3 a, Vec3 b, float t) { return a * (1.0f - t) + b * t; };
+        s->BackgroundTop = lerp(Vec3(0.02, 0.03, 0.06), Vec3(0.30, 0.55, 0.95), skyBlend);
+        s->BackgroundBottom = lerp(Vec3(0.00, 0.00, 0.00), Vec3(0.80, 0.90, 1.00), skyBlend);
+    }
+    int hc = hmap[(size_t)(worldSize / 2) * worldSize + worldSize / 2];
+    s->DefaultCameraPos = Vec3(0.0f, (float)std::max(hc, seaLevel) + 1.0f + 1.8f, 0.0f);
+    s->DefaultYaw = 0.6f; s->DefaultPitch = -0.25f;
+    s->ResetCamera();
+    s->RebuildBVH();
+    return s;
+}
+} // namespace VolumeScenes
+
+std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
+    if (name == "test") return Scenes::BuildTestScene();
+    if (name == "cornell") return Scenes::BuildCornellBox();
+    if (name == "mirror_spheres") return Scenes::BuildMirrorSpheresOnChecker();
+    if (name == "cylinders_disks_triangles") return Scenes::BuildCylindersDisksAndTriangles();
+    if (name == "boxes") return Scenes::BuildBoxesShowcase();
+    if (name == "volume_grid_test") return Scenes::BuildVolumeGridTestScene();
+    if (name == "cow") return MeshScenes::BuildCowScene();
+    if (name == "bunny") return MeshScenes::BuildBunnyScene();
+    if (name == "teapot") return MeshScenes::BuildTeapotScene();
+    if (name == "dragon") return MeshScenes::BuildDragonScene();
+    if (name.rfind("knot:", 0) == 0) { // knot:<segU>x<segV> — procedural mesh of a chosen size (tests)
+        int su = 0, sv = 0;
+        if (sscanf(name.c_str() + 5, "%dx%d", &su, &sv) != 2 || su < 3 || sv < 3) throw std::invalid_argument("knot:<segU>x<segV>");
+        return MeshScenes::BuildMeshScene(MeshScenes::ProceduralKnot(su, sv), Material(Vec3(0.0f, 0.0f, 0.85f), 0.0, 0.70, Vec3()), name);
+    }
+    if (name.rfind("voxel_world:", 0) == 0) { // voxel_world:<size>x<height>
+        int ws = 0, wh = 0;
+        if (sscanf(name.c_str() + 12, "%dx%d", &ws, &wh) != 2 || ws % 32 || wh % 32) throw std::invalid_argument("voxel_world:<size>x<height>, multiples of 32");
+        return VolumeScenes::BuildSyntheticWorld(ws, wh, 32, 45.0f);
+    }
+    if (name == "voxel_world") return VolumeScenes::BuildSyntheticWorld(1024, 256, 32, 45.0f);
+    throw std::invalid_argument("unknown scene: " + name);
+}
+
+// ---- Framebuffer ------------------------------------------------------------------------------------------------
+Framebuffer::Framebuffer(int width, int height) : Width(width), Height(height), chexels((size_t)width * height) {
+    Chexel blank; // new Chexel(' ', ConsoleColor.Black, ConsoleColor.White)  Framebuffer.cs:24-27
+    blank.Char = u' ';
+    blank.ForegroundColor.color_16 = 0; blank.ForegroundColor.color_f32 = Vec3(0.0f, 0.0f, 0.0f); blank.ForegroundColor.ansi_256 = 16;
+    blank.BackgroundColor.color_16 = 15; blank.BackgroundColor.color_f32 = Vec3(1.0f, 1.0f, 1.0f); blank.BackgroundColor.ansi_256 = 231;
+    std::fill(chexels.begin(), chexels.end(), blank);
+}
+
+// ---- flattening a Scene into the C ABI structs ------------------------------------------------------------------
+struct FlatScene {
+    SceneExport ex;
+    ycge_scene scene;
+    ycge_bvh top;
+    std::vector<ycge_bvh> mesh_bvh;
+    std::vector<ycge_mesh_soa> mesh_soa;
+    std::vector<ycge_volume> vols;
+    std::shared_ptr<Scene> keep;
+};
+static ycge_bvh bvh_view(const ycge::FlatTree &t) {
+    ycge_bvh b;
+    b.n_nodes = t.n_nodes(); b.root = t.root; b.n_leaf_refs = (int)t.leaf_index.size();
+    b.min_x = t.min_x.data(); b.min_y = t.min_y.data(); b.min_z = t.min_z.data(); b.max_x = t.max_x.data(); b.max_y = t.max_y.data(); b.max_z = t.max_z.data();
+    b.left = t.left.data(); b.right = t.right.data(); b.start = t.start.data(); b.count = t.count.data(); b.leaf_index = t.leaf_index.data();
+    return b;
+}
+static std::unique_ptr<FlatScene> Flatten(std::shared_ptr<Scene> sp) {
+    Scene &s = *sp;
+    if (!s.bvh) s.RebuildBVH();
+    std::unique_ptr<FlatScene> f(new FlatScene());
+    f->keep = sp;
+    for (auto &o : s.Objects) o->Export(f->ex);
+    for (auto &l : s.Lights) {
+        ycge_light L;
+        L.pos[0] = l.Position.X; L.pos[1] = l.Position.Y; L.pos[2] = l.Position.Z; L.color[0] = l.Color.X; L.color[1] = l.Color.Y; L.color[2] = l.Color.Z; L.intensity = l.Intensity;
+        f->ex.lights.push_back(L);
+    }
+    f->top = bvh_view(s.bvh->tree);
+    ycge_scene &sc = f->scene;
+    memset(&sc, 0, sizeof sc);
+    sc.bg_top[0] = s.BackgroundTop.X; sc.bg_top[1] = s.BackgroundTop.Y; sc.bg_top[2] = s.BackgroundTop.Z;
+    sc.bg_bottom[0] = s.BackgroundBottom.X; sc.bg_bottom[1] = s.BackgroundBottom.Y; sc.bg_bottom[2] = s.BackgroundBottom.Z;
+    sc.ambient_color[0] = s.Ambient.Color.X; sc.ambient_color[1] = s.Ambient.Color.Y; sc.ambient_color[2] = s.Ambient.Color.Z;
+    sc.ambient_intensity = s.Ambient.Intensity;
+    sc.is_volume_scene = s.IsVolumeScene ? 1 : 0;
+    sc.n_lights = (int)f->ex.lights.size(); sc.lights = f->ex.lights.data();
+    sc.n_materials = (int)f->ex.materials.size(); sc.materials = f->ex.materials.data();
+    sc.n_objects = (int)f->ex.objects.size(); sc.objects = f->ex.objects.data();
+    sc.bvh = &f->top;
+    f->mesh_bvh.resize(f->ex.meshes.size()); f->mesh_soa.resize(f->ex.meshes.size());
+    for (size_t i = 0; i < f->ex.meshes.size(); i++) {
+        const MeshBVH &m = *f->ex.meshes[i];
+        f->mesh_bvh[i] = bvh_view(m.tree);
+        ycge_mesh_soa &ms = f->mesh_soa[i];
+        ms.n_tris = m.TriangleCount();
+        ms.ax = m.ax.data(); ms.ay = m.ay.data(); ms.az = m.az.data(); ms.e1x = m.e1x.data(); ms.e1y = m.e1y.data(); ms.e1z = m.e1z.data();
+        ms.e2x = m.e2x.data(); ms.e2y = m.e2y.data(); ms.e2z = m.e2z.data(); ms.nx = m.nx.data(); ms.ny = m.ny.data(); ms.nz = m.nz.data();
+        ms.material = m.triMat.ToAbi();
+        ms.bvh = &f->mesh_bvh[i];
+    }
+    f->vols.resize(f->ex.volumes.size());
+    for (size_t i = 0; i < f->ex.volumes.size(); i++) {
+        const VolumeGrid &g = *f->ex.volumes[i];
+        ycge_volume &v = f->vols[i];
+        v.nx = g.nx; v.ny = g.ny; v.nz = g.nz;
+        v.min_corner[0] = g.minCorner.X; v.min_corner[1] = g.minCorner.Y; v.min_corner[2] = g.minCorner.Z;
+        v.voxel_size[0] = g.voxelSize.X; v.voxel_size[1] = g.voxelSize.Y; v.voxel_size[2] = g.voxelSize.Z;
+        v.mat = g.mat.data(); v.meta = g.meta.data();
+        v.wireframe = g.wireframe ? 1 : 0; v.wire_width_frac = g.wireWidthFrac; v.wire_max_distance = g.wireMaxDistance;
+        v.palette_n_ids = g.palette->n_ids; v.palette_meta_levels = g.palette->meta_levels;
+        v.palette = f->ex.volume_palettes[i].data();
+        v.palette_default = f->ex.volume_palettes[i].back();
+    }
+    return f;
+}
+
+// ---- CudaRaytraceRenderer ---------------------------------------------------------------------------------------
+void CudaRaytraceRenderer::Check(int rc, const char *what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + " failed with error " + std::to_string(rc) + ": " + ycge_last_error(ctx)); // cf. Win32TerminalRenderer.cs:99-104
+}
+CudaRaytraceRenderer::CudaRaytraceRenderer(Framebuffer &framebuffer, Scene &scene, float fovDeg, int pxW, int pxH, int superSample, int device, int tileRow0, int tileRows) {
+    (void)pxW; (void)pxH; // the reference ignores them too: hiW/hiH come from the framebuffer (RaytraceRenderer.cs:83-87)
+    ycge_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    ss = std::max(1, superSample);
+    fbW = framebuffer.Width; fbH = framebuffer.Height;
+    cfg.fb_w = fbW; cfg.fb_h = fbH; cfg.ss = ss; cfg.device = device; cfg.tile_row0 = tileRow0; cfg.tile_rows = tileRows;
+    ycge_default_params(&cfg.params);
+    int rc = ycge_create(&cfg, &ctx);
+    if (rc != 0) throw std::runtime_error(std::string("ycge_create failed with error ") + std::to_string(rc) + ": " + ycge_last_error(nullptr));
+    Check(ycge_set_fov(ctx, fovDeg), "ycge_set_fov");
+    UploadScene(scene); // scene.RebuildBVH()  :107
+}
+CudaRaytraceRenderer::~CudaRaytraceRenderer() { ycge_destroy(ctx); }
+void CudaRaytraceRenderer::UploadScene(Scene &scene) {
+    std::shared_ptr<Scene> alias(&scene, [](Scene *) {});
+    scene.RebuildBVH();
+    auto flat = Flatten(alias);
+    for (size_t i = 0; i < flat->mesh_soa.size(); i++) Check(ycge_mesh_upload_soa(ctx, (int)i, &flat->mesh_soa[i]), "ycge_mesh_upload_soa");
+    for (size_t i = 0; i < flat->vols.size(); i++) Check(ycge_volume_upload(ctx, (int)i, &flat->vols[i]), "ycge_volume_upload");
+    Check(ycge_scene_upload(ctx, &flat->scene), "ycge_scene_upload");
+    Check(ycge_reset_history(ctx), "ycge_reset_history");
+}
+void CudaRaytraceRenderer::SetCamera(Vec3 pos, float yaw, float pitch) { float p[3] = {pos.X, pos.Y, pos.Z}; Check(ycge_set_camera(ctx, p, yaw, pitch), "ycge_set_camera"); }
+void CudaRaytraceRenderer::SetFov(float fovDeg) { Check(ycge_set_fov(ctx, fovDeg), "ycge_set_fov"); }
+void CudaRaytraceRenderer::Resize(Framebuffer &fb, int superSample) {
+    ss = std::max(1, superSample); fbW = fb.Width; fbH = fb.Height;
+    Check(ycge_resize(ctx, fbW, fbH, ss), "ycge_resize");
+}
+void CudaRaytraceRenderer::RenderCells(ycge_cell *out) { Check(ycge_render_frame(ctx, out, 0), "ycge_render_frame"); }
+void CudaRaytraceRenderer::TryFlipAndBlit(Framebuffer &fb) {
+    staging.resize((size_t)fbW * fbH);
+    RenderCells(staging.data());
+    for (int cy = 0; cy < fbH; cy++) for (int cx = 0; cx < fbW; cx++) { // fb.SetChexel(cx, cy, new Chexel('▀', topSDR, botSDR))  :260-261
+        const ycge_cell &c = staging[(size_t)cy * fbW + cx];
+        Chexel ch;
+        ch.Char = (char16_t)c.glyph;
+        ch.ForegroundColor.color_16 = c.fg16; ch.ForegroundColor.color_f32 = Vec3(c.fg[0], c.fg[1], c.fg[2]); ch.ForegroundColor.ansi_256 = c.fg_ansi;
+        ch.BackgroundColor.color_16 = c.bg16; ch.BackgroundColor.color_f32 = Vec3(c.bg[0], c.bg[1], c.bg[2]); ch.BackgroundColor.ansi_256 = c.bg_ansi;
+        fb.SetChexel(cx, cy, ch);
+    }
+}
+
+// ---- ANSITerminalRenderer.Render (:86-153) ----------------------------------------------------------------------
+namespace {
+struct ByteOut {
+    std::vector<uint8_t> b;
+    void Ascii(const char *s) { while (*s) b.push_back((uint8_t)*s++); }
+    void Int(int v) { // AppendInt :181-202
+        if (v == 0) { b.push_back('0'); return; }
+        char tmp[16]; int n = 0;
+        while (v > 0) { tmp[n++] = (char)('0' + v % 10); v /= 10; }
+        while (n > 0) b.push_back((uint8_t)tmp[--n]);
+    }
+    void Utf8(unsigned ch) { // AppendCharUtf8 :204-224
+        if (ch <= 0x7F) b.push_back((uint8_t)ch);
+        else if (ch <= 0x7FF) { b.push_back((uint8_t)(0xC0 | (ch >> 6))); b.push_back((uint8_t)(0x80 | (ch & 0x3F))); }
+        else { b.push_back((uint8_t)(0xE0 | (ch >> 12))); b.push_back((uint8_t)(0x80 | ((ch >> 6) & 0x3F))); b.push_back((uint8_t)(0x80 | (ch & 0x3F))); }
+    }
+};
+template <class Get> std::vector<uint8_t> ansi_emit(int consoleWidth, int consoleHeight, Get get) {
+    ByteOut o;
+    o.b.reserve((size_t)64 + (size_t)consoleWidth * consoleHeight * 16);
+    int currentFgIdx = -1, currentBgIdx = -1;
+    for (int y = 0; y < consoleHeight; y++) {
+        o.Ascii("\x1b["); o.Int(y + 1); o.Ascii(";1H");
+        for (int x = 0; x < consoleWidth; x++) {
+            int fgIdx, bgIdx; unsigned ch;
+            get(x, y, fgIdx, bgIdx, ch);
+            if (fgIdx != currentFgIdx && bgIdx != currentBgIdx) {
+                o.Ascii("\x1b[38;5;"); o.Int(fgIdx); o.Ascii(";48;5;"); o.Int(bgIdx); o.Ascii("m");
+                currentFgIdx = fgIdx; currentBgIdx = bgIdx;
+            } else if (fgIdx != currentFgIdx) {
+                o.Ascii("\x1b[38;5;"); o.Int(fgIdx); o.Ascii("m");
+                currentFgIdx = fgIdx;
+            } else if (bgIdx != currentBgIdx) {
+                o.Ascii("\x1b[48;5;"); o.Int(bgIdx); o.Ascii("m");
+                currentBgIdx = bgIdx;
+            }
+            o.Utf8(ch);
+        }
+    }
+    o.Ascii("\x1b[0m");
+    return std::move(o.b);
+}
+} // namespace
+std::vector<uint8_t> ANSITerminalRenderer::Render(const Framebuffer &fb, int consoleWidth, int consoleHeight) {
+    return ansi_emit(consoleWidth, consoleHeight, [&](int x, int y, int &f, int &b, unsigned &ch) {
+        if (x < fb.Width && y < fb.Height) { Chexel c = fb.GetChexel(x, y); f = c.ForegroundColor.ansi_256; b = c.BackgroundColor.ansi_256; ch = c.Char; }
+        else { f = 231; b = 16; ch = ' '; } // new Chexel(' ', Console.ForegroundColor, Console.BackgroundColor): terminal defaults assumed white on black
+    });
+}
+std::vector<uint8_t> ANSITerminalRenderer::RenderCells(const ycge_cell *cells, int fbW, int fbH) {
+    return ansi_emit(fbW, fbH, [&](int x, int y, int &f, int &b, unsigned &ch) { const ycge_cell &c = cells[(size_t)y * fbW + x]; f = c.fg_ansi; b = c.bg_ansi; ch = c.glyph; });
+}
+std::vector<uint32_t> Win32TerminalRenderer::BuildCharInfo(const Framebuffer &fb) { // Win32TerminalRenderer.cs:82-91
+    std::vector<uint32_t> out((size_t)fb.Width * fb.Height);
+    for (int y = 0; y < fb.Height; y++) for (int x = 0; x < fb.Width; x++) {
+        Chexel c = fb.GetChexel(x, y);
+        unsigned ch = c.Char == 0 ? ' ' : c.Char;
+        unsigned attr = (unsigned)((c.ForegroundColor.color_16 & 0x0F) | ((c.BackgroundColor.color_16 & 0x0F) << 4));
+        out[(size_t)y * fb.Width + x] = ch | (attr << 16);
+    }
+    return out;
+}
+
+} // namespace ycge_host
+
+// ================================================================================================ C API for ctypes
+using namespace ycge_host;
+#define YH_API extern "C" __attribute__((visibility("default")))
+static thread_local std::string yh_error;
+YH_API const char *ycgeh_last_error() { return yh_error.c_str(); }
+
+struct SceneHandle { std::shared_ptr<Scene> scene; std::unique_ptr<FlatScene> flat; };
+
+YH_API void ycgeh_set_asset_dir(const char *dir) { MeshScenes::AssetDir = dir ? dir : "assets"; }
+YH_API void *ycgeh_scene_create(const char *name) {
+    try {
+        auto h = new SceneHandle();
+        h->scene = BuildSceneByName(name);
+        h->flat = Flatten(h->scene);
+        return h;
+    } catch (const std::exception &e) { yh_error = e.what(); return nullptr; }
+}
+YH_API void *ycgeh_scene_from_triangles(const char *name, int n_verts, const float *xyz, int n_faces, const int *faces) {
+    try {
+        ObjData d;
+        for (int i = 0; i < n_verts; i++) d.positions.push_back(Vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+        d.faces.assign(faces, faces + 3 * (size_t)n_faces);
+        auto h = new SceneHandle();
+        h->scene = MeshScenes::BuildMeshScene(d, Material(Vec3(0.0f, 0.85f, 0.0f), 0.12, 0.0, Vec3()), name);
+        h->flat = Flatten(h->scene);
+        return h;
+    } catch (const std::exception &e) { yh_error = e.what(); return nullptr; }
+}
+YH_API void ycgeh_scene_destroy(void *h) { delete (SceneHandle *)h; }
+YH_API const ycge_scene *ycgeh_scene_flat(void *h) { return &((SceneHandle *)h)->flat->scene; }
+YH_API int ycgeh_scene_n_meshes(void *h) { return (int)((SceneHandle *)h)->flat->mesh_soa.size(); }
+YH_API const ycge_mesh_soa *ycgeh_scene_mesh(void *h, int i) { return &((SceneHandle *)h)->flat->mesh_soa[i]; }
+YH_API int ycgeh_scene_n_volumes(void *h) { return (int)((SceneHandle *)h)->flat->vols.size(); }
+YH_API const ycge_volume *ycgeh_scene_volume(void *h, int i) { return &((SceneHandle *)h)->flat->vols[i]; }
+YH_API const float *ycgeh_scene_mesh_triangles(void *h, int i) { // A,B,C per triangle exactly as the loader produced them
+    return ((SceneHandle *)h)->flat->ex.meshes[i]->abc.data();
+}
+YH_API void ycgeh_scene_camera(void *h, float *pos3, float *yaw, float *pitch, float *fov) {
+    Scene &s = *((SceneHandle *)h)->scene;
+    pos3[0] = s.DefaultCameraPos.X; pos3[1] = s.DefaultCameraPos.Y; pos3[2] = s.DefaultCameraPos.Z; *yaw = s.DefaultYaw; *pitch = s.DefaultPitch; *fov = s.DefaultFovDeg;
+}
+YH_API const char *ycgeh_scene_name(void *h) { return ((SceneHandle *)h)->scene->Name.c_str(); }
+YH_API int ycgeh_scene_counts(void *h, int *n_objects, int *n_lights, int *n_materials, int64_t *n_tris, int64_t *n_voxels) {
+    FlatScene &f = *((SceneHandle *)h)->flat;
+    *n_objects = f.scene.n_objects; *n_lights = f.scene.n_lights; *n_materials = f.scene.n_materials;
+    int64_t t = 0, v = 0;
+    for (auto &m : f.mesh_soa) t += m.n_tris;
+    for (auto &g : f.vols) v += (int64_t)g.nx * g.ny * g.nz;
+    *n_tris = t; *n_voxels = v;
+    return 0;
+}
+
+struct RendererHandle { std::unique_ptr<Framebuffer> fb; std::unique_ptr<CudaRaytraceRenderer> r; std::vector<uint8_t> ansi; };
+YH_API void *ycgeh_renderer_create(void *scene, int fb_w, int fb_h, int ss, int device, int tile_row0, int tile_rows) {
+    try {
+        auto h = new RendererHandle();
+        h->fb.reset(new Framebuffer(fb_w, fb_h));
+        Scene &s = *((SceneHandle *)scene)->scene;
+        h->r.reset(new CudaRaytraceRenderer(*h->fb, s, s.DefaultFovDeg, fb_w * ss, fb_h * 2 * ss, ss, device, tile_row0, tile_rows));
+        h->r->SetCamera(s.CameraPos, s.Yaw, s.Pitch);
+        return h;
+    } catch (const std::exception &e) { yh_error = e.what(); return nullptr; }
+}
+YH_API void ycgeh_renderer_destroy(void *h) { delete (RendererHandle *)h; }
+YH_API ycge_ctx *ycgeh_renderer_ctx(void *h) { return ((RendererHandle *)h)->r->Context(); }
+YH_API int ycgeh_renderer_set_camera(void *h, const float *pos, float yaw, float pitch) {
+    try { ((RendererHandle *)h)->r->SetCamera(Vec3(pos[0], pos[1], pos[2]), yaw, pitch); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_renderer_set_fov(void *h, float fov) {
+    try { ((RendererHandle *)h)->r->SetFov(fov); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_renderer_resize(void *h, int fb_w, int fb_h, int ss) {
+    try {
+        RendererHandle *r = (RendererHandle *)h;
+        r->fb.reset(new Framebuffer(fb_w, fb_h));
+        r->r->Resize(*r->fb, ss);
+        return 0;
+    } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_renderer_render_cells(void *h, ycge_cell *out) { // TryFlipAndBlit without the Chexel unpack
+    try { ((RendererHandle *)h)->r->RenderCells(out); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int64_t ycgeh_renderer_blit_ansi(void *h, const uint8_t **bytes) { // TryFlipAndBlit(fb) + ANSITerminalRenderer.Render byte stream
+    try {
+        RendererHandle *r = (RendererHandle *)h;
+        r->r->TryFlipAndBlit(*r->fb);
+        r->ansi = ANSITerminalRenderer::Render(*r->fb, r->fb->Width, r->fb->Height);
+        *bytes = r->ansi.data();
+        return (int64_t)r->ansi.size();
+    } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_renderer_charinfo(void *h, uint32_t *out) {
+    RendererHandle *r = (RendererHandle *)h;
+    std::vector<uint32_t> v = Win32TerminalRenderer::BuildCharInfo(*r->fb);
+    memcpy(out, v.data(), v.size() * 4);
+    return 0;
+}
+YH_API int64_t ycgeh_ansi_from_cells(const ycge_cell *cells, int fb_w, int fb_h, uint8_t *out, int64_t cap) {
+    std::vector<uint8_t> v = ANSITerminalRenderer::RenderCells(cells, fb_w, fb_h);
+    if ((int64_t)v.size() > cap) return -(int64_t)v.size();
+    memcpy(out, v.data(), v.size());
+    return (int64_t)v.size();
+}
+/* builder access for parity tests: tree of the top level (which = -1) or of mesh `which` */
+YH_API int ycgeh_scene_bvh(void *h, int which, const ycge_bvh **out, uint64_t *sort_fallbacks) {
+    SceneHandle *s = (SceneHandle *)h;
+    if (which < 0) { *out = &s->flat->top; *sort_fallbacks = s->scene->bvh->tree.sort_fallbacks; return 0; }
+    if (which >= (int)s->flat->mesh_bvh.size()) return -1;
+    *out = &s->flat->mesh_bvh[which]; *sort_fallbacks = s->flat->ex.meshes[which]->tree.sort_fallbacks;
+    return 0;
+}
+YH_API float ycgeh_synthetic_height(int x, int z, int world_height) { return VolumeScenes::SyntheticHeight(x, z, world_height); }
