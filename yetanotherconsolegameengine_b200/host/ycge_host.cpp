@@ -728,6 +728,7 @@ struct FlatScene {
     std::vector<ycge_mesh_soa> mesh_soa;
     std::vector<ycge_volume> vols;
     std::shared_ptr<Scene> keep;
+    std::shared_ptr<BVH> keep_bvh; // the flat views below point into these vectors
 };
 static ycge_bvh bvh_view(const ycge::FlatTree &t) {
     ycge_bvh b;
@@ -741,6 +742,7 @@ static std::unique_ptr<FlatScene> Flatten(std::shared_ptr<Scene> sp) {
     if (!s.bvh) s.RebuildBVH();
     std::unique_ptr<FlatScene> f(new FlatScene());
     f->keep = sp;
+    f->keep_bvh = s.bvh;
     for (auto &o : s.Objects) o->Export(f->ex);
     for (auto &l : s.Lights) {
         ycge_light L;
@@ -806,7 +808,7 @@ CudaRaytraceRenderer::CudaRaytraceRenderer(Framebuffer &framebuffer, Scene &scen
 CudaRaytraceRenderer::~CudaRaytraceRenderer() { ycge_destroy(ctx); }
 void CudaRaytraceRenderer::UploadScene(Scene &scene) {
     std::shared_ptr<Scene> alias(&scene, [](Scene *) {});
-    scene.RebuildBVH();
+    if (!scene.bvh) scene.RebuildBVH(); // (the reference rebuilds unconditionally; the tree is a pure function of Objects)
     auto flat = Flatten(alias);
     for (size_t i = 0; i < flat->mesh_soa.size(); i++) Check(ycge_mesh_upload_soa(ctx, (int)i, &flat->mesh_soa[i]), "ycge_mesh_upload_soa");
     for (size_t i = 0; i < flat->vols.size(); i++) Check(ycge_volume_upload(ctx, (int)i, &flat->vols[i]), "ycge_volume_upload");
