@@ -206,6 +206,7 @@ typedef struct ycge_cell {
 typedef struct ycge_stats {
     uint64_t frames;          /* frames rendered since create */
     uint64_t rays;            /* Scene.Hit / Scene.Occluded invocations in the last frame */
+    uint64_t rays_total;      /* the same, accumulated since ycge_create (never reset) */
     /* reference-defined traversal events of the last frame; filled only by ycge_render_frame_stats */
     uint64_t top_nodes_popped, mesh_nodes_popped, leaf_refs, tris_tested, prims_tested, dda_cells;
     float ms_trace, ms_taa, ms_atrous, ms_exposure, ms_cells, ms_total; /* CUDA-event times of the last timed frame */

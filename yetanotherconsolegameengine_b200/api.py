@@ -86,7 +86,7 @@ class Config(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("frames", C.c_uint64), ("rays", C.c_uint64), ("top_nodes_popped", C.c_uint64), ("mesh_nodes_popped", C.c_uint64),
+    _fields_ = [("frames", C.c_uint64), ("rays", C.c_uint64), ("rays_total", C.c_uint64), ("top_nodes_popped", C.c_uint64), ("mesh_nodes_popped", C.c_uint64),
                 ("leaf_refs", C.c_uint64), ("tris_tested", C.c_uint64), ("prims_tested", C.c_uint64), ("dda_cells", C.c_uint64),
                 ("ms_trace", C.c_float), ("ms_taa", C.c_float), ("ms_atrous", C.c_float), ("ms_exposure", C.c_float), ("ms_cells", C.c_float),
                 ("ms_total", C.c_float), ("ae_exposure", C.c_float), ("log_sum", C.c_float), ("log_cnt", C.c_int32), ("kernel_launches", C.c_int32)]

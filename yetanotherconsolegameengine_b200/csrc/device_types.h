@@ -96,9 +96,10 @@ struct TraceParams {
     unsigned long long seed_salt;
 };
 
-struct TraceCounters { // device-side, 8 x u64
+struct TraceCounters { // device-side, 8 x u64, zeroed at the start of every frame
     unsigned long long rays, top_nodes, mesh_nodes, leaf_refs, tris, prims, dda, stack_overflow;
 };
+struct TraceTotals { unsigned long long rays_total; }; // never reset: lets a benchmark difference it around a timed region
 
 // Per-pixel image planes, all float4, row-major x + y*W over the FULL frame (every GPU allocates the full frame
 // and only touches its tile + halo; see DESIGN.md "Multi-GPU").

@@ -679,7 +679,7 @@ struct PathItem { RayD ray; V3 beta; int mirror, diffuse; };
 // Block = 128 threads = 4 warps; a warp covers an 8x4 pixel tile (coherent primary rays, 128-byte row segments
 // on every image write); the block covers 16x8 pixels.
 template <bool STATS>
-__global__ void __launch_bounds__(128) trace_kernel(DevScene sc, FrameConsts fc, TraceParams tp, ImagePlanes img, int parity, TraceCounters *counters) {
+__global__ void __launch_bounds__(128) trace_kernel(DevScene sc, FrameConsts fc, TraceParams tp, ImagePlanes img, int parity, TraceCounters *counters, TraceTotals *totals) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int py = fc.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(128) trace_kernel(DevScene sc, FrameConsts fc,
     // ---- counters: warp-reduce, one atomic per warp
     unsigned int rays = cnt.rays;
     for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
-    if (lane == 0 && rays) atomicAdd(&counters->rays, (unsigned long long)rays);
+    if (lane == 0 && rays) { atomicAdd(&counters->rays, (unsigned long long)rays); atomicAdd(&totals->rays_total, (unsigned long long)rays); }
     if (cnt.overflow) atomicAdd(&counters->stack_overflow, (unsigned long long)cnt.overflow);
     if (STATS) {
         unsigned int vals[6] = {cnt.top_nodes, cnt.mesh_nodes, cnt.leaf_refs, cnt.tris, cnt.prims, cnt.dda};

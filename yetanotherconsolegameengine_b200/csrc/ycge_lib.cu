@@ -79,6 +79,7 @@ struct ycge_ctx {
     DevBuf<ExposureState> expo;
     DevBuf<ycge_cell> cells;
     DevBuf<TraceCounters> counters;
+    DevBuf<TraceTotals> totals;
     int sw = 0, sh = 0;
     const float4 *denoised = nullptr;
 
@@ -317,8 +318,8 @@ int frame_begin_impl(ycge_ctx *c) {
         tp.mirror_threshold = c->P.mirror_threshold; tp.eps = c->P.eps; tp.sigma_rad = c->P.diffuse_sigma_deg * (3.14159274f / 180.0f); // :460
         tp.seed_salt = c->P.seed_salt;
         dim3 grid(div_up(W, 16), div_up(b - a, 8));
-        if (c->want_stats) trace_kernel<true><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p);
-        else trace_kernel<false><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p);
+        if (c->want_stats) trace_kernel<true><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
+        else trace_kernel<false><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
         launches++;
     }
     CK(c, cudaEventRecord(c->ev[1], s));
@@ -468,6 +469,8 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     CK(nullptr, cudaMemcpyAsync(c->expo.p, &es, sizeof es, cudaMemcpyHostToDevice, c->stream));
     CK(nullptr, c->counters.alloc(1));
     CK(nullptr, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), c->stream));
+    CK(nullptr, c->totals.alloc(1));
+    CK(nullptr, cudaMemsetAsync(c->totals.p, 0, sizeof(TraceTotals), c->stream));
     static const int bounds[5] = {48, 114, 154, 194, 234}; // ANSITerminalRenderer.cs:288-296
     for (int k = 0; k < 5; k++) c->ansi_th[k] = ansi_threshold(bounds[k]);
     int rc = set_geometry(c.get(), cfg->fb_w, cfg->fb_h, cfg->ss, cfg->tile_row0, cfg->tile_rows);
@@ -877,7 +880,9 @@ YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
     CK(c, cudaMemcpy(&tc, c->counters.p, sizeof tc, cudaMemcpyDeviceToHost));
     ExposureState es;
     CK(c, cudaMemcpy(&es, c->expo.p, sizeof es, cudaMemcpyDeviceToHost));
-    out->frames = (uint64_t)c->frame_counter; out->rays = tc.rays;
+    TraceTotals tt;
+    CK(c, cudaMemcpy(&tt, c->totals.p, sizeof tt, cudaMemcpyDeviceToHost));
+    out->frames = (uint64_t)c->frame_counter; out->rays = tc.rays; out->rays_total = tt.rays_total;
     out->top_nodes_popped = tc.top_nodes; out->mesh_nodes_popped = tc.mesh_nodes; out->leaf_refs = tc.leaf_refs;
     out->tris_tested = tc.tris; out->prims_tested = tc.prims; out->dda_cells = tc.dda;
     if (tc.stack_overflow) return fail(c, YCGE_ERR_LIMIT, "traversal stack overflow (tree deeper than the device stack)");
