@@ -35,6 +35,7 @@ def load_oracle():
         o.yo_volume_upload.argtypes = [vp, C.c_int, vp]
         o.yo_scene_upload.argtypes = [vp, vp]
         o.yo_lights_update.argtypes = [vp, C.c_int, vp]
+        o.yo_globals_update.argtypes = [vp, vp, vp, vp, C.c_float]
         o.yo_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
         o.yo_set_fov.argtypes = [vp, C.c_float]
         o.yo_reset_history.argtypes = [vp]
@@ -140,6 +141,18 @@ class Oracle:
 
     def reset_history(self):
         self.o.yo_reset_history(self.h)
+
+    def lights_update(self, lights):
+        arr = (api.Light * len(lights))()
+        for i, (pos, col, inten) in enumerate(lights):
+            arr[i].pos[:] = pos
+            arr[i].color[:] = col
+            arr[i].intensity = inten
+        assert self.o.yo_lights_update(self.h, len(lights), arr) == 0
+
+    def globals_update(self, bg_top, bg_bottom, ambient_color, ambient_intensity):
+        a, b, c = (C.c_float * 3)(*bg_top), (C.c_float * 3)(*bg_bottom), (C.c_float * 3)(*ambient_color)
+        assert self.o.yo_globals_update(self.h, a, b, c, ambient_intensity) == 0
 
     def resize(self, fb_w, fb_h, ss):
         self.o.yo_resize(self.h, fb_w, fb_h, ss)

@@ -1,0 +1,331 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path, called through the C ABI (libycge.so) behind the
+IConsoleRenderer mirror, against the CPU oracle and the committed golden vectors.
+
+Bar (BASELINE.json north_star): cells (glyph, ANSI-256, 16-colour index) and primary-hit ids bit-exact except documented
+float ties <= 0.1 % of cells; linear RGB within 1e-3 absolute.  Both sides evaluate transcendentals through
+include/ycge_detmath.h and never contract a*b+c, so the tests demand MORE: every intermediate plane bit-identical.
+"""
+import ctypes as C
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, require_cuda
+from yetanotherconsolegameengine_b200 import api
+from oracle_binding import Oracle
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import make_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 1e-3          # north_star: linear RGB within 1e-3 absolute per channel
+TIE_FRACTION = 0.001    # north_star: <= 0.1 % of cells may differ at documented float ties
+CELL_KEYS = ("glyph", "fg16", "bg16", "fg_ansi", "bg_ansi", "attr")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def bits_differ(a, b):
+    return int((np.ascontiguousarray(a).view(np.uint32) != np.ascontiguousarray(b).view(np.uint32)).sum())
+
+
+def assert_cells_equal(g, c, what=""):
+    for k in CELL_KEYS:
+        assert np.array_equal(g[k], c[k]), f"{what}: cell field {k} differs in {int((g[k] != c[k]).sum())} cells"
+    assert bits_differ(g["fg"], c["fg"]) == 0 and bits_differ(g["bg"], c["bg"]) == 0, f"{what}: SDR colour bits differ"
+
+
+def assert_frame_parity(r, o, what, check_rays=False):
+    """All taps of one rendered frame, GPU vs oracle.  First the north-star gates, then the stricter bit-identity."""
+    gp, cp = r.debug_read(api.DBG_PRIM_ID), o.debug_read(api.DBG_PRIM_ID)
+    assert (gp != cp).any(-1).mean() <= TIE_FRACTION, f"{what}: primary ids"
+    gd, cd = r.debug_read(api.DBG_DENOISED), o.debug_read(api.DBG_DENOISED)
+    finite = np.isfinite(cd) & np.isfinite(gd)
+    assert np.array_equal(np.isfinite(cd), np.isfinite(gd))
+    assert np.abs(gd[finite] - cd[finite]).max(initial=0.0) <= RGB_TOL, f"{what}: linear RGB"
+    assert np.array_equal(gp, cp), f"{what}: primary objId/subId not bit-exact"
+    kinds = [(api.DBG_HDR, "hdr"), (api.DBG_ALBEDO_SKY, "albedo/sky"), (api.DBG_NORMAL_DEPTH, "normal/depth"), (api.DBG_TAA, "taa"),
+             (api.DBG_DENOISED, "denoised"), (api.DBG_LOG_SAMPLES, "log samples")]
+    if check_rays:
+        kinds.insert(0, (api.DBG_RAYS, "rays"))
+    for kind, nm in kinds:
+        assert bits_differ(r.debug_read(kind), o.debug_read(kind)) == 0, f"{what}: {nm} not bit-identical"
+    gs, cs = r.stats(), o.stats()
+    assert gs["rays"] == cs["rays"], f"{what}: ray count"
+    assert np.float32(gs["ae_exposure"]).view(np.uint32) == np.float32(cs["ae_exposure"]).view(np.uint32), f"{what}: aeExposure"
+    assert np.float32(gs["log_sum"]).view(np.uint32) == np.float32(cs["log_sum"]).view(np.uint32) and gs["log_cnt"] == cs["log_cnt"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    require_cuda()
+
+
+# ------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("case", make_golden.CASES, ids=[c[0] for c in make_golden.CASES])
+def test_gpu_matches_golden(case):
+    name, scene, fb_w, fb_h, ss, frames, pose = case
+    gold = np.load(os.path.join(GOLDEN, f"oracle_{name}.npz"))
+    s = api.HostScene(scene)
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    if pose is not None:
+        r.SetCamera(*pose)
+    for f in range(1, frames + 1):
+        cells = r.TryFlipAndBlit()
+        assert_cells_equal(cells, gold[f"cells_{f}"], f"{name} frame {f}")
+        assert np.array_equal(r.debug_read(api.DBG_PRIM_ID), gold[f"prim_{f}"])
+        assert sha(r.debug_read(api.DBG_HDR)[..., :3]) == str(gold[f"sha_hdr_{f}"])
+        assert sha(r.debug_read(api.DBG_TAA)[..., :3]) == str(gold[f"sha_taa_{f}"])
+        assert sha(r.debug_read(api.DBG_DENOISED)[..., :3]) == str(gold[f"sha_den_{f}"])
+        st = r.stats()
+        assert st["rays"] == int(gold[f"rays_{f}"])
+        assert np.float32(st["ae_exposure"]).view(np.uint32) == gold[f"ae_{f}"].view(np.uint32)
+    r.close()
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------- live oracle, every tap
+LIVE = [  # scene, fb_w, fb_h, ss, frames, pose
+    ("cornell", 60, 34, 1, 3, None),
+    ("mirror_spheres", 48, 14, 4, 3, None),
+    ("cylinders_disks_triangles", 60, 34, 1, 2, None),
+    ("boxes", 33, 9, 3, 2, None),            # ragged: W = 99, H = 54 are not multiples of the 16x8 / 32x8 tiles
+    ("test", 31, 7, 2, 2, None),
+    ("volume_grid_test", 60, 34, 1, 2, None),
+    ("teapot", 48, 14, 4, 2, api.BENCH_POSE),
+    ("bunny", 64, 18, 2, 2, api.BENCH_POSE),
+    ("knot:60x16", 48, 14, 4, 2, api.BENCH_POSE),
+    ("voxel_world:64x64", 48, 14, 4, 2, None),
+    ("cornell", 1, 1, 1, 2, None),           # minimum size: 1x2 pixels
+]
+
+
+@pytest.mark.parametrize("case", LIVE, ids=[f"{c[0]}-{c[1]}x{c[2]}ss{c[3]}" for c in LIVE])
+def test_gpu_matches_oracle_every_tap(case):
+    scene, fb_w, fb_h, ss, frames, pose = case
+    s = api.HostScene(scene)
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    o = Oracle(s, fb_w, fb_h, ss)
+    if pose is not None:
+        r.SetCamera(*pose)
+        o.set_camera(*pose)
+    r.debug_read(api.DBG_RAYS)  # arms the ray tap
+    for f in range(frames):
+        g = r.render_frame_stats()
+        c = o.render_frame(threads=os.cpu_count() or 1, fast_post=True)
+        assert_cells_equal(g, c, f"{scene} frame {f + 1}")
+        assert_frame_parity(r, o, f"{scene} frame {f + 1}", check_rays=True)
+        gs, cs = r.stats(), o.stats()
+        for k in ("top_nodes_popped", "mesh_nodes_popped", "leaf_refs", "tris_tested", "prims_tested", "dda_cells"):
+            assert gs[k] == cs[k], f"{scene}: traversal event counter {k}: {gs[k]} vs {cs[k]}"
+    r.close()
+    o.close()
+    s.close()
+
+
+def test_library_builds_the_same_trees_as_the_host():
+    """ycge_scene_upload without a host tree / ycge_mesh_upload_triangles: the library's own builder (BVH.cs:258-459,
+    MeshBVH.cs:371-576) must give the same frame as the host's uploaded trees."""
+    s = api.HostScene("knot:40x12")
+    lib = api.load_lib()
+    r1 = api.CudaRaytraceRenderer(s, 40, 12, 2)
+    r1.SetCamera(*api.BENCH_POSE)
+    a = r1.TryFlipAndBlit().copy()
+    # second context fed with plain triangles and no top-level tree
+    cfg = api.Config()
+    cfg.fb_w, cfg.fb_h, cfg.ss = 40, 12, 2
+    lib.ycge_default_params(C.byref(cfg.params))
+    ctx = C.c_void_p()
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == 0
+    tris = s.mesh_triangles(0)
+    m = s.mesh(0).contents
+    assert lib.ycge_mesh_upload_triangles(ctx, 0, len(tris), tris.ctypes.data, C.byref(m.material)) == 0
+    s2 = api.Scene()
+    C.memmove(C.byref(s2), s.flat, C.sizeof(api.Scene))
+    s2.bvh = None
+    assert lib.ycge_scene_upload(ctx, C.byref(s2)) == 0
+    pos = (C.c_float * 3)(*api.BENCH_POSE[0])
+    lib.ycge_set_camera(ctx, pos, api.BENCH_POSE[1], api.BENCH_POSE[2])
+    b = np.empty((12, 40), api.CELL_DTYPE)
+    assert lib.ycge_render_frame(ctx, b.ctypes.data, 0) == 0
+    assert_cells_equal(a, b, "library-built trees")
+    lib.ycge_destroy(ctx)
+    r1.close()
+
+
+# ------------------------------------------------------------------------------------------- RNG known answers on the device
+def test_rng_known_answers_on_device():
+    s = api.HostScene("cornell")
+    r = api.CudaRaytraceRenderer(s, 4, 2, 1)
+    kat = [((0, 0, 1), 0x17EF7D0094EB2C76, 7379119), ((1, 0, 1), 0xE30B62FE1AC2EDC5, 1918614), ((0, 1, 1), 0x7EDFB4004F82140E, 13519905),
+           ((959, 539, 1), 0xC3C5BBAF2004442A, 15095364), ((1919, 1079, 64), 0x5BEAD3AD13E75BBB, 9491773)]
+    xs, ys, fs = zip(*[k[0] for k in kat])
+    bits, seeds = r.rng_kat(0, xs, ys, fs, 4)
+    for i, (_, seed, m24) in enumerate(kat):
+        assert int(seeds[i]) == seed
+        exp = np.float32(np.float32(m24) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+        assert int(bits[i, 0]) == int(np.float32(exp).view(np.uint32))
+    # both streams against the oracle over random inputs
+    from oracle_binding import load_oracle
+    lib = load_oracle()
+    rng = np.random.default_rng(5)
+    xs, ys, fs = rng.integers(0, 4000, 64), rng.integers(0, 4000, 64), rng.integers(1, 1 << 33, 64)
+    bits, seeds = r.rng_kat(0, xs, ys, fs, 8)
+    for i in range(64):
+        sd = lib.yo_per_frame_seed(int(xs[i]), int(ys[i]), int(fs[i]), 0, 0, 0x9E3779B97F4A7C15)
+        assert int(seeds[i]) == sd
+        b = np.zeros(8, np.uint32)
+        lib.yo_rng_draws(sd, 8, b.ctypes.data, None)
+        assert np.array_equal(b, bits[i])
+    bits, seeds = r.rng_kat(1, xs, ys, fs, 8)  # ConsoleRayTracing.Rng (Rng.cs)
+    for i in range(64):
+        b = np.zeros(8, np.uint32)
+        lib.yo_rng_cs_draws(int(seeds[i]), 8, b.ctypes.data)
+        assert np.array_equal(b, bits[i])
+    r.close()
+
+
+# ------------------------------------------------------------------------------------------- renderer state machine
+def test_camera_motion_reset_resize_lights_and_globals():
+    s = api.HostScene("mirror_spheres")
+    r = api.CudaRaytraceRenderer(s, 32, 10, 2)
+    o = Oracle(s, 32, 10, 2)
+    pos, yaw, pitch, fov = s.default_camera()
+
+    def both(fn):
+        fn(r)
+        fn(o)
+
+    def frame(tag):
+        g = r.TryFlipAndBlit()
+        c = o.render_frame(threads=4, fast_post=True)
+        assert_cells_equal(g, c, tag)
+        assert_frame_parity(r, o, tag)
+
+    frame("frame 1")
+    frame("frame 2 (history blend)")
+    r.SetCamera((pos[0] + 0.5, pos[1] + 0.1, pos[2]), yaw + 0.2, pitch - 0.05); o.set_camera((pos[0] + 0.5, pos[1] + 0.1, pos[2]), yaw + 0.2, pitch - 0.05)
+    frame("camera moved: history reset")
+    r.SetCamera((pos[0] + 0.501, pos[1] + 0.1, pos[2]), yaw + 0.2, pitch - 0.05); o.set_camera((pos[0] + 0.501, pos[1] + 0.1, pos[2]), yaw + 0.2, pitch - 0.05)
+    frame("sub-threshold motion: no reset, history is blended with a shifted frame")
+    r.SetFov(60.0); o.set_fov(60.0)
+    frame("fov change")
+    lights = [((0.0, 3.0, 1.0), (1.0, 0.5, 0.25), 30.0), ((-2.0, 2.0, -1.0), (0.2, 0.4, 1.0), 12.0), ((2.0, 4.0, 2.0), (1.0, 1.0, 1.0), 5.0)]
+    both(lambda x: x.lights_update(lights))
+    frame("lights_update (3 lights)")
+    both(lambda x: x.globals_update((0.1, 0.2, 0.6), (0.7, 0.8, 0.9), (1.0, 0.9, 0.8), 0.15))
+    frame("globals_update (sky + ambient)")
+    r.Resize(20, 7, 3); o.resize(20, 7, 3)
+    frame("after Resize (frame counter and exposure survive)")
+    assert r.stats()["frames"] == o.stats()["frames"] == 8
+    both(lambda x: x.reset_history())
+    frame("reset_history")
+    r.close()
+    o.close()
+
+
+def test_async_path_equals_synchronous_path():
+    s = api.HostScene("boxes")
+    a = api.CudaRaytraceRenderer(s, 40, 12, 2)
+    b = api.CudaRaytraceRenderer(s, 40, 12, 2)
+    for _ in range(5):
+        last = a.TryFlipAndBlit()
+    b.render_frames_async(5)
+    b.wait()
+    assert_cells_equal(last, b.read_cells(), "render_frames_async(5)")
+    assert a.stats()["rays_total"] == b.stats()["rays_total"]
+    a.close()
+    b.close()
+
+
+def test_ansi_stream_through_the_host_framebuffer():
+    s = api.HostScene("cornell")
+    a = api.CudaRaytraceRenderer(s, 30, 10, 1)
+    b = api.CudaRaytraceRenderer(s, 30, 10, 1)
+    stream = a.blit_ansi()          # TryFlipAndBlit(fb) -> Chexels -> ANSITerminalRenderer.Render
+    cells = b.TryFlipAndBlit()
+    assert stream == api.ansi_from_cells(cells)
+    assert stream.count(b"\xe2\x96\x80") == 300  # U+2580 per cell
+    a.close()
+    b.close()
+
+
+def test_errors_are_loud():
+    lib = api.load_lib()
+    cfg = api.Config()
+    cfg.fb_w, cfg.fb_h, cfg.ss = 8, 4, 1
+    lib.ycge_default_params(C.byref(cfg.params))
+    ctx = C.c_void_p()
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == 0
+    out = np.empty((4, 8), api.CELL_DTYPE)
+    assert lib.ycge_render_frame(ctx, out.ctypes.data, 0) == -3  # YCGE_ERR_NO_SCENE ("Scene BVH not built", Scene.cs:73)
+    assert b"BVH not built" in lib.ycge_last_error(ctx)
+    assert lib.ycge_resize(ctx, 0, 4, 1) == -1
+    assert lib.ycge_frame_finish(ctx) == -1
+    lib.ycge_destroy(ctx)
+    cfg.device = 99
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == -1
+    cfg.device = 0
+    cfg.fb_w = 0
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == -1
+
+
+# ------------------------------------------------------------------------------------------- BASELINE sizes
+def test_full_size_1080p_dragon_two_frames_vs_oracle():
+    """The north-star workload at its real size (1920x1080 internal = 480x135 cells, ss = 4): two frames (the second
+    blends TAA history) against the oracle on the box's host cores."""
+    s = api.HostScene("dragon")
+    r = api.CudaRaytraceRenderer(s, 480, 135, 4)
+    o = Oracle(s, 480, 135, 4)
+    r.SetCamera(*api.BENCH_POSE)
+    o.set_camera(*api.BENCH_POSE)
+    for f in range(2):
+        g = r.TryFlipAndBlit()
+        c = o.render_frame(threads=os.cpu_count() or 1, fast_post=True)
+        diff = sum((g[k] != c[k]).any() for k in CELL_KEYS)
+        assert_cells_equal(g, c, f"dragon 1080p frame {f + 1}")
+        assert_frame_parity(r, o, f"dragon 1080p frame {f + 1}")
+        assert diff == 0
+    r.close()
+    o.close()
+
+
+def test_full_size_mirror_spheres_1080p_vs_oracle():
+    """BASELINE config 2: mirror spheres on checker plane, 1920x1080 internal, one frame, reference constants."""
+    s = api.HostScene("mirror_spheres")
+    r = api.CudaRaytraceRenderer(s, 480, 135, 4)
+    o = Oracle(s, 480, 135, 4)
+    g = r.TryFlipAndBlit()
+    c = o.render_frame(threads=os.cpu_count() or 1, fast_post=True)
+    assert_cells_equal(g, c, "mirror spheres 1080p")
+    assert_frame_parity(r, o, "mirror spheres 1080p")
+    r.close()
+    o.close()
+
+
+def test_full_size_properties_voxel_world_1440p():
+    """BASELINE config 4 geometry (1024x256x1024 voxel world in 32^3 chunks, 2560x1440 internal): too slow for the CPU
+    oracle in a test, so size-independent properties: deterministic across contexts, frame 1 history == current HDR,
+    sky mask consistent with primary ids, all cells inside the ANSI cube, exposure inside its clamp."""
+    s = api.HostScene("voxel_world")
+    a = api.CudaRaytraceRenderer(s, 320, 90, 8)
+    b = api.CudaRaytraceRenderer(s, 320, 90, 8)
+    ca, cb = a.TryFlipAndBlit(), b.TryFlipAndBlit()
+    assert_cells_equal(ca, cb, "determinism")
+    hdr, taa = a.debug_read(api.DBG_HDR), a.debug_read(api.DBG_TAA)
+    assert bits_differ(hdr, taa) == 0
+    prim, sky = a.debug_read(api.DBG_PRIM_ID), a.debug_read(api.DBG_ALBEDO_SKY)[..., 3]
+    assert np.array_equal(prim[..., 0] < 0, sky != 0)
+    assert 0.05 < (sky != 0).mean() < 0.95
+    assert ca["fg_ansi"].min() >= 16 and ca["fg_ansi"].max() <= 231 and np.all(ca["glyph"] == 0x2580)
+    ca2, cb2 = a.TryFlipAndBlit(), b.TryFlipAndBlit()
+    assert_cells_equal(ca2, cb2, "determinism frame 2")
+    assert 0.10 <= a.stats()["ae_exposure"] <= 1.50
+    a.close()
+    b.close()

@@ -232,7 +232,8 @@ class HostScene:
     def __init__(self, name: str, asset_dir: Optional[str] = None):
         self._h = load_host()
         if asset_dir is None:
-            asset_dir = os.environ.get("YCGE_ASSETS", os.path.join(os.path.dirname(_PKG_DIR), "assets"))
+            # the engine's assets/ directory (ConsoleGame/assets); default: the committed binary twins of the reference meshes
+            asset_dir = os.environ.get("YCGE_ASSETS", os.path.join(os.path.dirname(_PKG_DIR), "tests", "golden", "meshes"))
         self._h.ycgeh_set_asset_dir(asset_dir.encode())
         self.handle = self._h.ycgeh_scene_create(name.encode())
         if not self.handle:
@@ -378,6 +379,19 @@ class CudaRaytraceRenderer:
 
     def reset_history(self):
         self._ck(self._lib.ycge_reset_history(self.ctx))
+
+    def lights_update(self, lights):
+        """Per-frame light changes without re-uploading geometry (DayNightCycle.cs:80-83): [(pos3, color3, intensity), ...]"""
+        arr = (Light * len(lights))()
+        for i, (pos, col, inten) in enumerate(lights):
+            arr[i].pos[:] = pos
+            arr[i].color[:] = col
+            arr[i].intensity = inten
+        self._ck(self._lib.ycge_lights_update(self.ctx, len(lights), arr))
+
+    def globals_update(self, bg_top, bg_bottom, ambient_color, ambient_intensity):
+        a, b, c = (C.c_float * 3)(*bg_top), (C.c_float * 3)(*bg_bottom), (C.c_float * 3)(*ambient_color)
+        self._ck(self._lib.ycge_globals_update(self.ctx, a, b, c, ambient_intensity))
 
     def render_frame_stats(self) -> np.ndarray:
         out = np.empty((self.tile_rows, self.fb_w), CELL_DTYPE)

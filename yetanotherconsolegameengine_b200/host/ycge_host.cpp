@@ -198,9 +198,32 @@ static int ParseIndex(const std::string &token, int count) { // MeshLoader.cs:99
     if (idx > 0) return idx - 1;
     return count + idx;
 }
+// Binary twin of a parsed OBJ (tests/golden/meshes/*.ymesh): "YMSH", int32 nVerts, int32 nFaceIndices, float32 xyz[], int32 faces[].
+// Holds exactly what ParseObj produced from the reference's asset (tools/make_mesh_fixtures.py), so the GPU box — where
+// the reference checkout does not exist — loads bit-identical input.
+static bool ReadYmesh(const std::string &path, ObjData &d) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f.good()) return false;
+    char magic[4]; int32_t nv = 0, nf = 0;
+    f.read(magic, 4); f.read((char *)&nv, 4); f.read((char *)&nf, 4);
+    if (!f.good() || memcmp(magic, "YMSH", 4) != 0 || nv <= 0 || nf <= 0 || nf % 3) throw std::runtime_error("bad .ymesh: " + path);
+    std::vector<float> xyz((size_t)nv * 3);
+    d.faces.resize((size_t)nf);
+    f.read((char *)xyz.data(), (std::streamsize)(xyz.size() * 4)); f.read((char *)d.faces.data(), (std::streamsize)((size_t)nf * 4));
+    if (!f.good()) throw std::runtime_error("truncated .ymesh: " + path);
+    d.positions.reserve((size_t)nv);
+    for (int i = 0; i < nv; i++) d.positions.push_back(Vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+    for (int v : d.faces) if (v < 0 || v >= nv) throw std::runtime_error("bad face index in .ymesh: " + path);
+    return true;
+}
 ObjData MeshLoader::ParseObj(const std::string &path) { // MeshLoader.cs:23-56
     std::ifstream f(path);
-    if (!f.good()) throw std::runtime_error("OBJ not found: " + path);
+    if (!f.good()) {
+        ObjData b;
+        size_t dot = path.rfind('.');
+        if (dot != std::string::npos && ReadYmesh(path.substr(0, dot) + ".ymesh", b)) return b;
+        throw std::runtime_error("OBJ not found: " + path);
+    }
     ObjData d;
     std::string line;
     std::vector<std::string> tok;
@@ -927,6 +950,17 @@ YH_API void *ycgeh_scene_from_triangles(const char *name, int n_verts, const flo
         h->flat = Flatten(h->scene);
         return h;
     } catch (const std::exception &e) { yh_error = e.what(); return nullptr; }
+}
+YH_API int ycgeh_obj_to_ymesh(const char *obj_path, const char *out_path) { // fixture generator (tools/make_mesh_fixtures.py)
+    try {
+        ObjData d = MeshLoader::ParseObj(obj_path);
+        std::ofstream o(out_path, std::ios::binary);
+        int32_t nv = (int32_t)d.positions.size(), nf = (int32_t)d.faces.size();
+        o.write("YMSH", 4); o.write((const char *)&nv, 4); o.write((const char *)&nf, 4);
+        for (const Vec3 &p : d.positions) { float v[3] = {p.X, p.Y, p.Z}; o.write((const char *)v, 12); }
+        o.write((const char *)d.faces.data(), (std::streamsize)((size_t)nf * 4));
+        return o.good() ? 0 : -1;
+    } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
 YH_API void ycgeh_scene_destroy(void *h) { delete (SceneHandle *)h; }
 YH_API const ycge_scene *ycgeh_scene_flat(void *h) { return &((SceneHandle *)h)->flat->scene; }
