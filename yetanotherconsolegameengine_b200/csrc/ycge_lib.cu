@@ -75,7 +75,6 @@ struct ycge_ctx {
     DevBuf<int2> prim;
     DevBuf<float> rays_dbg;
     DevBuf<float> logs;
-    DevBuf<int> progress;
     DevBuf<ExposureState> expo;
     DevBuf<ycge_cell> cells;
     DevBuf<TraceCounters> counters;
@@ -107,7 +106,7 @@ struct ycge_ctx {
     bool want_stats = false;
     bool debug_rays = false;
     float ansi_th[5] = {0, 0, 0, 0, 0};
-    int inplace_rows_per_launch = 0;
+    int inplace_ctas_per_launch = 0;
 
     // timing
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -214,7 +213,6 @@ int alloc_planes(ycge_ctx *c) {
     c->sw = (c->W + step - 1) / step;
     c->sh = (c->H + step - 1) / step;
     CK(c, c->logs.alloc((size_t)c->sw * c->sh));
-    CK(c, c->progress.alloc((size_t)c->H * 8));
     CK(c, c->cells.alloc((size_t)c->fbW * c->tile_rows));
     CK(c, cudaMemsetAsync(c->cur.p, 0, n * sizeof(float4), c->stream));
     CK(c, cudaMemsetAsync(c->hist.p, 0, n * sizeof(float4), c->stream));
@@ -346,23 +344,26 @@ int frame_begin_impl(ycge_ctx *c) {
             if (cur_id == dst_id) {
                 // in-place pass on scratch X: OLD = X, NEW = the other scratch (dead at this point), which then becomes X
                 int X = cur_id, Y = (X == 1) ? 2 : 1;
-                int C = std::max(1, std::min(step, 8));
                 AtrousInplaceArgs ia;
-                ia.old_ = phys[X]; ia.new_ = phys[Y]; ia.gnd = img.gnd[parity]; ia.gas = img.gas[parity]; ia.progress = c->progress.p;
-                ia.W = W; ia.H = H; ia.step = step; ia.C = C; ia.dc = dc; ia.dn = dn; ia.dz = dz; ia.da = da;
-                // rows above `a` (a sharded tile's upper halo, filled by the previous rank) already hold NEW values
-                if (a > 0) CK(c, cudaMemsetAsync(c->progress.p, 0x7f, (size_t)a * C * sizeof(int), s));
-                CK(c, cudaMemsetAsync(c->progress.p + (size_t)a * C, 0, (size_t)(H - a) * C * sizeof(int), s));
-                if (c->inplace_rows_per_launch <= 0) {
+                ia.old_ = phys[X]; ia.new_ = phys[Y]; ia.gnd = img.gnd[parity]; ia.gas = img.gas[parity];
+                ia.W = W; ia.H = H; ia.step = step; ia.dc = dc; ia.dn = dn; ia.dz = dz; ia.da = da;
+                // NEW starts as the sentinel on the rows this pass produces; rows above `a` (a sharded tile's upper halo,
+                // written by the previous rank) already hold NEW values
+                CK(c, cudaMemsetAsync(phys[Y] + (size_t)a * W, 0xFF, (size_t)(b - a) * W * sizeof(float4), s));
+                const int pairs = (step + 1) / 2; // warps per row
+                if (c->inplace_ctas_per_launch <= 0) {
                     int per_sm = 0;
-                    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_inplace_kernel, 256, 0));
+                    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_inplace_kernel, YCGE_AIP_WARPS * 32, 0));
                     cudaDeviceProp prop;
                     CK(c, cudaGetDeviceProperties(&prop, c->device));
-                    c->inplace_rows_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
+                    c->inplace_ctas_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
                 }
-                for (int r0 = a; r0 < b; r0 += c->inplace_rows_per_launch) {
-                    ia.y0 = r0; ia.y1 = std::min(b, r0 + c->inplace_rows_per_launch);
-                    atrous_inplace_kernel<<<ia.y1 - ia.y0, C * 32, 0, s>>>(ia);
+                // all CTAs of a launch must be co-resident (they wait on each other); rows are launched in order
+                const int rows_per_launch = std::max(1, c->inplace_ctas_per_launch * YCGE_AIP_WARPS / pairs);
+                for (int r0 = a; r0 < b; r0 += rows_per_launch) {
+                    ia.y0 = r0; ia.y1 = std::min(b, r0 + rows_per_launch);
+                    const int warps = (ia.y1 - ia.y0) * pairs;
+                    atrous_inplace_kernel<<<div_up(warps, YCGE_AIP_WARPS), YCGE_AIP_WARPS * 32, 0, s>>>(ia);
                     launches++;
                 }
                 std::swap(phys[X], phys[Y]);
