@@ -72,6 +72,7 @@ struct ycge_ctx {
 
     // image planes
     DevBuf<float4> cur, gnd0, gnd1, gas0, gas1, hist, sa, sb;
+    DevBuf<float4> pre; // in-place à-trous pass: 25 planes of per-tap precomputed terms / guide weights
     DevBuf<int2> prim;
     DevBuf<float> rays_dbg;
     DevBuf<float> logs;
@@ -107,6 +108,8 @@ struct ycge_ctx {
     bool debug_rays = false;
     float ansi_th[5] = {0, 0, 0, 0, 0};
     int inplace_ctas_per_launch = 0;
+    EdgeDiv edge_div;      // max(1e-6, phi) and reciprocals (RaytraceRenderer.cs:694-697)
+    bool fast_div = false; // the FMA division sequence was verified against IEEE division for these four divisors
 
     // timing
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -337,41 +340,52 @@ int frame_begin_impl(ycge_ctx *c) {
         // logical buffers of the reference: 0 = src (TAA history), 1 = scratchA, 2 = scratchB
         float4 *phys[3] = {c->hist.p, c->sa.p, c->sb.p};
         int cur_id = 0, dst_id = 1;
-        float dc = std::max(1e-6f, c->P.c_phi), dn = std::max(1e-6f, c->P.n_phi), dz = std::max(1e-6f, c->P.z_phi), da = std::max(1e-6f, c->P.a_phi);
+        const EdgeDiv ed = c->edge_div;
+        const bool fast = c->fast_div;
         for (int it = 0; it < K; it++) {
             int a, b; range(halo_after[it + 1], a, b);
             int step = 1 << it;
             if (cur_id == dst_id) {
                 // in-place pass on scratch X: OLD = X, NEW = the other scratch (dead at this point), which then becomes X
                 int X = cur_id, Y = (X == 1) ? 2 : 1;
-                AtrousInplaceArgs ia;
-                ia.old_ = phys[X]; ia.new_ = phys[Y]; ia.gnd = img.gnd[parity]; ia.gas = img.gas[parity];
-                ia.W = W; ia.H = H; ia.step = step; ia.dc = dc; ia.dn = dn; ia.dz = dz; ia.da = da;
-                // NEW starts as the sentinel on the rows this pass produces; rows above `a` (a sharded tile's upper halo,
-                // written by the previous rank) already hold NEW values
+                if (c->pre.n < (size_t)W * H * 25) CK(c, c->pre.alloc((size_t)W * H * 25));
+                // (1) everything that does not depend on new values, fully parallel
+                AtrousPreArgs pa;
+                pa.old_ = phys[X]; pa.gnd = img.gnd[parity]; pa.gas = img.gas[parity]; pa.pre = c->pre.p; pa.plane = (size_t)W * H;
+                pa.W = W; pa.H = H; pa.y0 = a; pa.y1 = b; pa.step = step; pa.e = ed;
+                if (fast) atrous_pre_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
+                else atrous_pre_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
+                launches++;
+                // (2) the wavefront.  NEW starts as the sentinel on the rows this pass produces; rows above `a` (a sharded
+                // tile's upper halo, written by the previous rank) already hold NEW values
+                AtrousChainArgs ia;
+                ia.old_ = phys[X]; ia.new_ = phys[Y]; ia.pre = c->pre.p; ia.plane = (size_t)W * H;
+                ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc;
                 CK(c, cudaMemsetAsync(phys[Y] + (size_t)a * W, 0xFF, (size_t)(b - a) * W * sizeof(float4), s));
-                const int pairs = (step + 1) / 2; // warps per row
                 if (c->inplace_ctas_per_launch <= 0) {
                     int per_sm = 0;
-                    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_inplace_kernel, YCGE_AIP_WARPS * 32, 0));
+                    if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<true>, YCGE_AIC_WARPS * 32, 0));
+                    else CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<false>, YCGE_AIC_WARPS * 32, 0));
                     cudaDeviceProp prop;
                     CK(c, cudaGetDeviceProperties(&prop, c->device));
                     c->inplace_ctas_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
                 }
                 // all CTAs of a launch must be co-resident (they wait on each other); rows are launched in order
-                const int rows_per_launch = std::max(1, c->inplace_ctas_per_launch * YCGE_AIP_WARPS / pairs);
+                const int rows_per_launch = std::max(1, c->inplace_ctas_per_launch * YCGE_AIC_WARPS / step);
                 for (int r0 = a; r0 < b; r0 += rows_per_launch) {
                     ia.y0 = r0; ia.y1 = std::min(b, r0 + rows_per_launch);
-                    const int warps = (ia.y1 - ia.y0) * pairs;
-                    atrous_inplace_kernel<<<div_up(warps, YCGE_AIP_WARPS), YCGE_AIP_WARPS * 32, 0, s>>>(ia);
+                    const int warps = (ia.y1 - ia.y0) * step; // one warp per chain, `step` chains per row
+                    if (fast) atrous_chain_kernel<true><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
+                    else atrous_chain_kernel<false><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
                     launches++;
                 }
                 std::swap(phys[X], phys[Y]);
             } else {
                 AtrousArgs aa;
                 aa.src = phys[cur_id]; aa.gnd = img.gnd[parity]; aa.gas = img.gas[parity]; aa.dst = phys[dst_id];
-                aa.W = W; aa.H = H; aa.y0 = a; aa.y1 = b; aa.step = step; aa.dc = dc; aa.dn = dn; aa.dz = dz; aa.da = da;
-                atrous_kernel<<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
+                aa.W = W; aa.H = H; aa.y0 = a; aa.y1 = b; aa.step = step; aa.e = ed;
+                if (fast) atrous_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
+                else atrous_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
                 launches++;
             }
             int tmp = cur_id; // var tmp = cur; cur = dst; dst = (tmp == scratchA) ? scratchB : scratchA;   :718
@@ -472,6 +486,20 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     CK(nullptr, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), c->stream));
     CK(nullptr, c->totals.alloc(1));
     CK(nullptr, cudaMemsetAsync(c->totals.p, 0, sizeof(TraceTotals), c->stream));
+    { // edge-stopping divisors; verify the fast division over every non-negative binary32 numerator (a few ms, once)
+        EdgeDiv &e = c->edge_div;
+        e.dc = std::max(1e-6f, c->P.c_phi); e.dn = std::max(1e-6f, c->P.n_phi); e.dz = std::max(1e-6f, c->P.z_phi); e.da = std::max(1e-6f, c->P.a_phi);
+        e.rc = (float)(1.0 / (double)e.dc); e.rn = (float)(1.0 / (double)e.dn); e.rz = (float)(1.0 / (double)e.dz); e.ra = (float)(1.0 / (double)e.da);
+        DevBuf<unsigned int> mm;
+        CK(nullptr, mm.alloc(4));
+        CK(nullptr, cudaMemsetAsync(mm.p, 0, 16, c->stream));
+        div_selftest_kernel<<<(0x7F800000u >> 8) + 1, 256, 0, c->stream>>>(e, mm.p);
+        unsigned int h[4] = {1, 1, 1, 1};
+        CK(nullptr, cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        CK(nullptr, cudaStreamSynchronize(c->stream));
+        c->fast_div = (h[0] | h[1] | h[2] | h[3]) == 0;
+        if (!(e.dc < 1e30f && e.dn < 1e30f && e.dz < 1e30f && e.da < 1e30f)) c->fast_div = false;
+    }
     static const int bounds[5] = {48, 114, 154, 194, 234}; // ANSITerminalRenderer.cs:288-296
     for (int k = 0; k < 5; k++) c->ansi_th[k] = ansi_threshold(bounds[k]);
     int rc = set_geometry(c.get(), cfg->fb_w, cfg->fb_h, cfg->ss, cfg->tile_row0, cfg->tile_rows);
