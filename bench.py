@@ -154,65 +154,122 @@ def main():
     n = max(1, world)
 
     scene = pkg.HostScene(args.scene)
-    # row tiles aligned to cell rows
-    row0 = rank * fb_h // n
-    rows = (rank + 1) * fb_h // n - row0
-    if n > 1:
-        raise SystemExit("bench.py: multi-GPU row-tile sharding is wired in a later commit")
-    r = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank, tile_row0=row0 if n > 1 else 0, tile_rows=rows if n > 1 else 0)
     pose = pkg.BENCH_POSE if scene.n_meshes else scene.default_camera()[:3]
-    r.SetCamera(*pose)
     stream = torch.cuda.Stream()
-    r.set_stream(stream.cuda_stream)
-
-    # untimed: one frame with the reference-defined event counters (feeds the algorithmic-bytes roofline)
-    r.render_frame_stats()
-    st_events = r.stats()
-    r.reset_history()
-
-    with torch.cuda.stream(stream):
-        r.render_frames_async(max(3, args.warmup))
-    r.wait()
-    st0 = r.stats()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0.record(stream)
-    r.render_frames_async(args.steps)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    st1 = r.stats()
-    clocks = sampler.stop()
-    rays_timed = st1["rays_total"] - st0["rays_total"]
-    fps = args.steps / (ms / 1e3)
-    mrays = rays_timed / (ms / 1e3) / 1e6
-
-    # per-stage device times of a steady-state frame (events recorded by the library on the same stream)
-    stage_ms = {k: st1[k] for k in ("ms_trace", "ms_taa", "ms_atrous", "ms_exposure", "ms_cells", "ms_total")}
-
-    # e2e: the public IConsoleRenderer call per step, camera in, cells out to pinned host memory
     pinned = torch.empty((fb_h * fb_w * api.CELL_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
     cells = pinned.numpy().view(api.CELL_DTYPE).reshape(fb_h, fb_w)
-    for _ in range(3):
-        r.SetCamera(*pose)
-        r.TryFlipAndBlit(cells)
-    st2 = r.stats()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r.SetCamera(*pose)
-        r.TryFlipAndBlit(cells)
-    e2e_s = time.perf_counter() - t0
-    st3 = r.stats()
-    e2e_mrays = (st3["rays_total"] - st2["rays_total"]) / e2e_s / 1e6
     h2d = C.sizeof(C.c_float) * 32 + 64  # FrameConsts + launch parameters; the scene stays resident
     d2h = fb_w * fb_h * api.CELL_DTYPE.itemsize
+
+    if n == 1:
+        r = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank)
+        r.SetCamera(*pose)
+        r.set_stream(stream.cuda_stream)
+        # untimed: one frame with the reference-defined event counters (feeds the algorithmic-bytes roofline)
+        r.render_frame_stats()
+        st_events = r.stats()
+        r.reset_history()
+        with torch.cuda.stream(stream):
+            r.render_frames_async(max(3, args.warmup))
+        r.wait()
+        st0 = r.stats()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        r.render_frames_async(args.steps)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        st1 = r.stats()
+        clocks = sampler.stop()
+        rays_timed = st1["rays_total"] - st0["rays_total"]
+        # per-stage device times of a steady-state frame (events recorded by the library on the same stream)
+        stage_ms = {k: st1[k] for k in ("ms_trace", "ms_taa", "ms_atrous", "ms_atrous_chain", "ms_exposure", "ms_cells", "ms_total")}
+        launches_per_frame = st1["kernel_launches"]
+        # e2e: the public IConsoleRenderer call per step, camera in, cells out to pinned host memory
+        for _ in range(3):
+            r.SetCamera(*pose)
+            r.TryFlipAndBlit(cells)
+        st2 = r.stats()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r.SetCamera(*pose)
+            r.TryFlipAndBlit(cells)
+        e2e_s = time.perf_counter() - t0
+        st3 = r.stats()
+        e2e_rays = st3["rays_total"] - st2["rays_total"]
+        r.close()
+    else:
+        # one process per GPU: contiguous row tiles of cell rows, scene replicated, boundary rows of the in-place pass
+        # handed rank -> rank+1, exposure samples all-reduced, cell tiles gathered on rank 0 (sharding.py)
+        from yetanotherconsolegameengine_b200 import sharding
+        row0, rows = sharding.tile_rows(rank, n, fb_h)
+        with torch.cuda.stream(stream):
+            b = sharding.CudaTileBackend(scene, fb_w, fb_h, ss, row0, rows, local_rank)
+            sr = sharding.ShardedRenderer(b, rank, n, fb_w, fb_h)
+            sr.SetCamera(*pose)
+            # the event counters of the whole frame come from an unsharded frame on rank 0's GPU (untimed)
+            st_events = None
+            if rank == 0:
+                r1 = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank)
+                r1.SetCamera(*pose)
+                r1.render_frame_stats()
+                st_events = r1.stats()
+                r1.close()
+            for _ in range(max(3, args.warmup)):
+                sr.render_device()
+            torch.cuda.synchronize()
+            st0 = b.r.stats()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(args.steps):
+                sr.render_device()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            ms_local = ev0.elapsed_time(ev1)
+            st1 = b.r.stats()
+            clocks = sampler.stop()
+            stage_ms = {k: st1[k] for k in ("ms_trace", "ms_taa", "ms_atrous", "ms_atrous_chain", "ms_exposure", "ms_cells", "ms_total")}
+            launches_per_frame = st1["kernel_launches"]
+            # e2e: camera in, assembled cells out to pinned host memory on rank 0, every step
+            def e2e_step():
+                sr.SetCamera(*pose)
+                g = sr.render_device()
+                if rank == 0:
+                    for rr, (t0_, tn) in enumerate(sr.tiles):
+                        nb = tn * fb_w * api.CELL_DTYPE.itemsize
+                        pinned[t0_ * fb_w * 32:t0_ * fb_w * 32 + nb].copy_(g[rr][:nb], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            for _ in range(3):
+                e2e_step()
+            st2 = b.r.stats()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()
+            dist.barrier()
+            e2e_local = time.perf_counter() - t0
+            st3 = b.r.stats()
+        # max over ranks of the device time; rays summed over ranks (halo rows are traced redundantly and counted as
+        # work done — rays/frame of the UNSHARDED frame is what the metric divides by, so use the unsharded count)
+        t = torch.tensor([ms_local, e2e_local], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        rays_frame = torch.tensor([st_events["rays"] if rank == 0 else 0], dtype=torch.int64, device="cuda")
+        dist.broadcast(rays_frame, 0)
+        rays_timed = int(rays_frame[0]) * args.steps
+        e2e_rays = int(rays_frame[0]) * args.steps
+        b.close()
+    fps = args.steps / (ms / 1e3)
+    mrays = rays_timed / (ms / 1e3) / 1e6
+    e2e_mrays = e2e_rays / e2e_s / 1e6
 
     # roofline of the dominant kernel
     peaks = {}
@@ -221,20 +278,24 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
     b_trav, b_trace, b_frame = algorithmic_bytes(st_events, W, H, fb_w, fb_h, ss)
-    dominant = max(("ms_trace", "ms_taa", "ms_atrous", "ms_exposure", "ms_cells"), key=lambda k: stage_ms[k])
-    if dominant == "ms_trace":
-        kname, kbytes, kms = "trace_kernel", b_trace, stage_ms["ms_trace"]
-    elif dominant == "ms_atrous":
-        kname, kbytes, kms = "atrous (3 passes incl. the in-place wavefront pass)", W * H * 3 * 53, stage_ms["ms_atrous"]
+    # the dominant single kernel: the trace megakernel or the wavefront kernel of the in-place à-trous pass
+    rows_here = H if n == 1 else min(H, (sharding.tile_rows(0, n, fb_h)[1]) * 2 * ss + 16)
+    if stage_ms["ms_trace"] >= stage_ms["ms_atrous_chain"]:
+        kname, kbytes, kms = "trace_kernel", b_trace * rows_here // H, stage_ms["ms_trace"]
     else:
-        kname, kbytes, kms = dominant, b_frame - b_trace, stage_ms[dominant]
+        kname, kbytes, kms = "atrous_chain_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
     achieved = kbytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": kbytes, "kernel_ms": kms,
                 "frame": {"algorithmic_bytes": b_frame, "achieved_GBps": b_frame * fps / 1e9, "frac": b_frame * fps / 1e9 / peak},
-                "note": "latency/occupancy-bound irregular traversal; acceleration data is L2-resident, see DESIGN.md"}
+                "note": "algorithmic bytes = SURVEY 8(d) per-pixel figures of the reference's own layout; both candidate kernels are latency-bound (divergent traversal; serial wavefront), "
+                        "not HBM-bound: see DESIGN.md and profiles/"}
 
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
@@ -243,16 +304,15 @@ def main():
 
     if rank == 0:
         line = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": max(3, args.warmup),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
                 "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}",
                            "l2": "per-frame working set (8 float4 image planes = %d MB) exceeds the 126 MB L2; no explicit flush" % (W * H * 128 // (1 << 20))},
                 "stage_ms": stage_ms,
                 "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": st1["kernel_launches"] * args.steps,
+                "gpu_launches": launches_per_frame * args.steps * n,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
-    r.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -214,6 +214,8 @@ typedef struct ycge_stats {
     float log_sum;            /* UpdateExposure's logSum of the last frame */
     int32_t log_cnt;
     int32_t kernel_launches;  /* kernels launched for the last frame */
+    float ms_atrous_chain;    /* the wavefront kernel of the in-place à-trous pass alone (part of ms_atrous) */
+    int32_t fast_div;         /* 1: the FMA division sequence passed its exhaustive check for this ctx's divisors */
 } ycge_stats;
 
 typedef enum ycge_debug_kind {
@@ -260,13 +262,30 @@ YCGE_API int ycge_wait(ycge_ctx *ctx);
 /* Copy the device-resident cells of the last frame to host memory (what ycge_render_frame does at its end). */
 YCGE_API int ycge_read_cells(ycge_ctx *ctx, ycge_cell *out, int32_t stride_cells);
 
-/* ---- row-tile sharding (one process per GPU; the collectives are the caller's, e.g. torch.distributed/NCCL)
- *   ycge_frame_begin   trace + TAA + à-trous on the tile (+halo), log-luminance samples of the tile's rows
- *                      written into the full-frame sample array (zeros elsewhere)
+/* ---- row-tile sharding (one process per GPU; the collectives are the caller's, e.g. torch.distributed/NCCL).
+ * A ctx created with tile_row0/tile_rows renders one row tile (cell rows) of the frame plus the pixel-row halo its
+ * image passes need (recomputed locally, bit-identical).  Per frame:
+ *   ycge_frame_begin     trace + TAA + à-trous passes up to the first in-place pass (RaytraceRenderer.cs:718 makes
+ *                        iteration 1 run in place: every row then depends on the rows above it, across tiles)
+ *   while (ycge_frame_halo(ctx, &h) == 1) {
+ *       <caller: receive h.recv_bytes into h.recv_ptr from the rank above  (the rows just above the tile's range)>
+ *       ycge_frame_inplace   the wavefront over this tile's rows, then the following passes up to the next in-place
+ *                            pass, or to the end: log-luminance samples of the tile's rows written into the full-frame
+ *                            sample array (zeros elsewhere)
+ *       <caller: send h.send_bytes from h.send_ptr to the rank below>
+ *   }
  *   <caller: sum-all-reduce of YCGE_PTR_LOG_SAMPLES over ranks (each slot is owned by one rank)>
- *   ycge_frame_finish  ordered exposure sum (identical on every rank), cell conversion of the tile
- *   <caller: gather YCGE_PTR_CELLS tiles to rank 0> */
+ *   ycge_frame_finish    ordered exposure sum (identical on every rank), cell conversion of the tile
+ *   <caller: gather YCGE_PTR_CELLS tiles to rank 0>
+ * An unsharded ctx runs everything inside ycge_frame_begin (ycge_frame_halo returns 0). All work is enqueued on the
+ * ctx's stream (ycge_set_stream), so a transfer enqueued on the same stream is ordered with it. */
+typedef struct ycge_halo {
+    void *recv_ptr;  size_t recv_bytes;  int32_t recv_row0, recv_rows;  /* NULL/0 for the top tile */
+    void *send_ptr;  size_t send_bytes;  int32_t send_row0, send_rows;  /* NULL/0 for the bottom tile; valid after ycge_frame_inplace */
+} ycge_halo;
 YCGE_API int ycge_frame_begin(ycge_ctx *ctx);
+YCGE_API int ycge_frame_halo(ycge_ctx *ctx, ycge_halo *out);  /* 1: an in-place pass is pending, 0: none (negative: error) */
+YCGE_API int ycge_frame_inplace(ycge_ctx *ctx);
 YCGE_API int ycge_frame_finish(ycge_ctx *ctx);
 typedef enum ycge_ptr_kind { YCGE_PTR_CELLS = 0, YCGE_PTR_LOG_SAMPLES = 1 } ycge_ptr_kind;
 YCGE_API int ycge_device_ptr(ycge_ctx *ctx, int32_t kind, void **ptr, size_t *bytes);

@@ -329,3 +329,51 @@ def test_full_size_properties_voxel_world_1440p():
     assert 0.10 <= a.stats()["ae_exposure"] <= 1.50
     a.close()
     b.close()
+
+
+# ------------------------------------------------------------------------------------------- row tiles (sharding kernels)
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss,n_tiles,pose", [("boxes", 40, 24, 2, 3, None), ("knot:60x16", 48, 27, 4, 4, api.BENCH_POSE),
+                                                             ("mirror_spheres", 33, 8, 1, 8, None), ("voxel_world:64x64", 40, 12, 2, 2, None)])
+def test_row_tiles_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pose):
+    """N row-tile contexts on ONE GPU, driven through the phase API with a loop-back exchange (device copies instead of
+    NCCL): boundary rows of the in-place pass handed tile -> tile, exposure samples summed, cells concatenated.  Must equal
+    the unsharded frame bit for bit, over several frames (TAA history and exposure state live per tile)."""
+    import torch
+    from yetanotherconsolegameengine_b200 import sharding
+    s = api.HostScene(scene)
+    full = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    tiles = []
+    with torch.cuda.device(0):
+        for r in range(n_tiles):
+            row0, rows = sharding.tile_rows(r, n_tiles, fb_h)
+            tiles.append(sharding.CudaTileBackend(s, fb_w, fb_h, ss, row0, rows, 0))
+        if pose is not None:
+            full.SetCamera(*pose)
+            for t in tiles:
+                t.set_camera(*pose)
+        for frame in range(3):
+            ref = full.TryFlipAndBlit()
+            for t in tiles:
+                t.begin()
+            while True:
+                halos = [t.halo() for t in tiles]
+                if halos[0] is None:
+                    assert all(h is None for h in halos)
+                    break
+                prev_send = None
+                for t, (recv, send) in zip(tiles, halos):
+                    if recv is not None:
+                        assert prev_send is not None and prev_send.numel() == recv.numel()
+                        recv.copy_(prev_send)
+                    t.inplace()
+                    prev_send = send
+            total = torch.stack([t.logs for t in tiles]).sum(0)  # each slot is owned by one tile, the others hold 0
+            for t in tiles:
+                t.logs.copy_(total)
+                t.finish()
+            torch.cuda.synchronize()
+            got = np.concatenate([t.cells.cpu().numpy().view(api.CELL_DTYPE).reshape(t.rows, fb_w) for t in tiles])
+            assert_cells_equal(got, ref, f"{scene} frame {frame + 1}, {n_tiles} tiles")
+    for t in tiles:
+        t.close()
+    full.close()

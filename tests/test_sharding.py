@@ -1,0 +1,122 @@
+"""Row-tile sharding, host-side logic on CPU: the tile partition, and the per-frame orchestration (boundary-row
+hand-off rank -> rank+1, sum all-reduce of the exposure samples, gather of the cell tiles on rank 0) run with
+world_size 2 and 3 over gloo.  The tile backend here is a fake built on the CPU oracle (each rank renders the whole
+frame with the oracle and exposes only its tile's slices), so this checks the plumbing, not the kernels; the kernels'
+tile/halo logic is checked on the GPU in test_gpu_parity.py::test_row_tiles_equal_the_unsharded_frame."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT, TESTS
+from yetanotherconsolegameengine_b200 import api, sharding
+
+
+def test_tile_partition_covers_every_cell_row_once():
+    for fb_h in (1, 2, 7, 90, 135):
+        for world in (1, 2, 3, 4, 8):
+            tiles = [sharding.tile_rows(r, world, fb_h) for r in range(world)]
+            assert tiles[0][0] == 0 and tiles[-1][0] + tiles[-1][1] == fb_h
+            for (a0, an), (b0, bn) in zip(tiles, tiles[1:]):
+                assert a0 + an == b0
+            sizes = [t[1] for t in tiles]
+            assert max(sizes) - min(sizes) <= 1 and sum(sizes) == fb_h
+
+
+class FakeTileBackend:
+    """TileBackend made of the CPU oracle: full frame per rank, tile slices exposed as torch CPU tensors."""
+
+    def __init__(self, scene_name, fb_w, fb_h, ss, rank, world):
+        from oracle_binding import Oracle
+        self.scene = api.HostScene(scene_name)
+        self.o = Oracle(self.scene, fb_w, fb_h, ss)
+        self.rank, self.world, self.fb_w, self.fb_h, self.ss = rank, world, fb_w, fb_h, ss
+        self.row0, self.rows = sharding.tile_rows(rank, world, fb_h)
+        step = max(2, 2 * ss)
+        self.sh, self.sw = (fb_h * 2 * ss + step - 1) // step, (fb_w * ss + step - 1) // step
+        self.logs = torch.zeros(self.sh * self.sw, dtype=torch.float32)
+        self.cells = torch.zeros(self.rows * fb_w * 32, dtype=torch.uint8)
+        self.frame = 0
+        self.errors = []
+
+    @staticmethod
+    def token(rank, frame, n):
+        return torch.full((n,), (17 * rank + 3 * frame + 1) % 251, dtype=torch.uint8)
+
+    def set_camera(self, pos, yaw, pitch):
+        self.o.set_camera(pos, yaw, pitch)
+
+    def begin(self):
+        self.frame += 1
+        self.full_cells = self.o.render_frame(threads=2, fast_post=True)
+        self.full_logs = self.o.debug_read(api.DBG_LOG_SAMPLES).reshape(-1).copy()
+        self._halo_calls = 0
+        self._recv = None
+
+    def halo(self):
+        self._halo_calls += 1
+        if self._halo_calls > 1:
+            return None
+        n = 4 * self.fb_w * self.ss * 16
+        self._recv = torch.zeros(n, dtype=torch.uint8) if self.rank > 0 else None
+        self._send = torch.zeros(n, dtype=torch.uint8) if self.rank < self.world - 1 else None
+        return self._recv, self._send
+
+    def inplace(self):
+        if self._recv is not None and not torch.equal(self._recv, self.token(self.rank - 1, self.frame, len(self._recv))):
+            self.errors.append(f"frame {self.frame}: boundary rows from rank {self.rank - 1} did not arrive before the in-place pass")
+        if self._send is not None:
+            self._send.copy_(self.token(self.rank, self.frame, len(self._send)))  # valid only after the pass, like the real buffer
+        # this rank's exposure samples: sample row k = cell row k (step = 2*ss)
+        self.logs.zero_()
+        own = torch.from_numpy(self.full_logs.reshape(self.sh, self.sw)[self.row0:self.row0 + self.rows].copy())
+        self.logs.view(self.sh, self.sw)[self.row0:self.row0 + self.rows] = own
+
+    def finish(self):
+        got, exp = self.logs.numpy(), self.full_logs
+        if not (np.array_equal(np.isnan(got), np.isnan(exp)) and np.array_equal(got[~np.isnan(exp)], exp[~np.isnan(exp)])):
+            self.errors.append(f"frame {self.frame}: all-reduced exposure samples differ from the full-frame samples")
+        tile = np.ascontiguousarray(self.full_cells[self.row0:self.row0 + self.rows])
+        self.cells.copy_(torch.from_numpy(tile.view(np.uint8).reshape(-1)))
+
+
+def _worker(rank, world, port, fb_w, fb_h, ss, frames, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path[:0] = [ROOT, TESTS]
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = FakeTileBackend("boxes", fb_w, fb_h, ss, rank, world)
+        r = sharding.ShardedRenderer(b, rank, world, fb_w, fb_h)
+        ok = True
+        for f in range(frames):
+            if f == 2:
+                r.SetCamera((0.3, 1.2, 0.1), 0.2, -0.1)  # every rank moves its camera identically -> history reset everywhere
+            out = r.TryFlipAndBlit()
+            if rank == 0:
+                ok &= out.tobytes() == b.full_cells.tobytes()
+            else:
+                ok &= out is None
+        q.put((rank, ok and not b.errors, b.errors))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,fb_h", [(2, 9), (3, 10)])
+def test_sharded_frame_orchestration_gloo(world, fb_h):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 24, fb_h, 2, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, errors in results:
+        assert ok, (rank, errors)

@@ -85,11 +85,17 @@ class Config(C.Structure):
                 ("tile_rows", C.c_int32), ("params", Params)]
 
 
+class Halo(C.Structure):
+    _fields_ = [("recv_ptr", C.c_void_p), ("recv_bytes", C.c_size_t), ("recv_row0", C.c_int32), ("recv_rows", C.c_int32),
+                ("send_ptr", C.c_void_p), ("send_bytes", C.c_size_t), ("send_row0", C.c_int32), ("send_rows", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("rays", C.c_uint64), ("rays_total", C.c_uint64), ("top_nodes_popped", C.c_uint64), ("mesh_nodes_popped", C.c_uint64),
                 ("leaf_refs", C.c_uint64), ("tris_tested", C.c_uint64), ("prims_tested", C.c_uint64), ("dda_cells", C.c_uint64),
                 ("ms_trace", C.c_float), ("ms_taa", C.c_float), ("ms_atrous", C.c_float), ("ms_exposure", C.c_float), ("ms_cells", C.c_float),
-                ("ms_total", C.c_float), ("ae_exposure", C.c_float), ("log_sum", C.c_float), ("log_cnt", C.c_int32), ("kernel_launches", C.c_int32)]
+                ("ms_total", C.c_float), ("ae_exposure", C.c_float), ("log_sum", C.c_float), ("log_cnt", C.c_int32), ("kernel_launches", C.c_int32),
+                ("ms_atrous_chain", C.c_float), ("fast_div", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -107,7 +113,8 @@ ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
     "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
     "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
-    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_frame_begin", "ycge_frame_finish", "ycge_device_ptr",
+    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
+    "ycge_frame_finish", "ycge_device_ptr",
     "ycge_set_stream", "ycge_debug_read", "ycge_get_stats", "ycge_get_frame_counter", "ycge_rng_kat",
 ]
 
@@ -148,6 +155,8 @@ def load_lib() -> C.CDLL:
         lib.ycge_read_cells.argtypes = [vp, vp, C.c_int32]
         lib.ycge_frame_begin.argtypes = [vp]
         lib.ycge_frame_finish.argtypes = [vp]
+        lib.ycge_frame_halo.argtypes = [vp, C.POINTER(Halo)]
+        lib.ycge_frame_inplace.argtypes = [vp]
         lib.ycge_device_ptr.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
         lib.ycge_set_stream.argtypes = [vp, vp]
         lib.ycge_debug_read.argtypes = [vp, C.c_int32, vp, C.c_size_t]
@@ -415,6 +424,17 @@ class CudaRaytraceRenderer:
 
     def frame_finish(self):
         self._ck(self._lib.ycge_frame_finish(self.ctx))
+
+    def frame_halo(self) -> Optional[Halo]:
+        """The boundary rows of a pending in-place pass (None when no pass is pending)."""
+        h = Halo()
+        rc = self._lib.ycge_frame_halo(self.ctx, C.byref(h))
+        if rc < 0:
+            self._ck(rc)
+        return h if rc == 1 else None
+
+    def frame_inplace(self):
+        self._ck(self._lib.ycge_frame_inplace(self.ctx))
 
     def set_stream(self, cuda_stream: int):
         self._ck(self._lib.ycge_set_stream(self.ctx, C.c_void_p(cuda_stream)))

@@ -108,11 +108,21 @@ struct ycge_ctx {
     bool debug_rays = false;
     float ansi_th[5] = {0, 0, 0, 0, 0};
     int inplace_ctas_per_launch = 0;
+    // resumable à-trous state of the frame in flight (a sharded tile pauses before every in-place pass so that the caller
+    // can move the boundary rows between ranks)
+    struct Denoise {
+        float4 *phys[3] = {nullptr, nullptr, nullptr}; // logical buffers of the reference: 0 = src (TAA history), 1 = scratchA, 2 = scratchB
+        int cur_id = 0, dst_id = 1, it = 0, K = 0, parity = 0, ty0 = 0, ty1 = 0;
+        int halo_after[10] = {0};
+        bool pending = false; // an in-place pass is prepared (pre-pass + sentinel done) and waits for ycge_frame_inplace
+        int pa = 0, pb = 0;   // its row range
+    } dn;
     EdgeDiv edge_div;      // max(1e-6, phi) and reciprocals (RaytraceRenderer.cs:694-697)
+    bool chain_timed = false;
     bool fast_div = false; // the FMA division sequence was verified against IEEE division for these four divisors
 
     // timing
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [7],[8] bracket the wavefront kernel
     int launches_last = 0;
     std::string err;
 };
@@ -266,6 +276,7 @@ bool should_reset_history(const ycge_ctx *c) { // TemporalAA.cs:58-67
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // ---- the per-frame launch sequence ----------------------------------------------------------------------------
+int denoise_run(ycge_ctx *c);
 int frame_begin_impl(ycge_ctx *c) {
     if (!c->have_scene) return fail(c, YCGE_ERR_NO_SCENE, "Scene BVH not built; call ycge_scene_upload() after populating the scene");
     if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_begin called twice without ycge_frame_finish");
@@ -336,70 +347,97 @@ int frame_begin_impl(ycge_ctx *c) {
         c->taa_valid = true;
     }
     CK(c, cudaEventRecord(c->ev[2], s));
-    { // K3: the reference's ping-pong including its in-place iteration (:648-719)
-        // logical buffers of the reference: 0 = src (TAA history), 1 = scratchA, 2 = scratchB
-        float4 *phys[3] = {c->hist.p, c->sa.p, c->sb.p};
-        int cur_id = 0, dst_id = 1;
-        const EdgeDiv ed = c->edge_div;
-        const bool fast = c->fast_div;
-        for (int it = 0; it < K; it++) {
-            int a, b; range(halo_after[it + 1], a, b);
-            int step = 1 << it;
-            if (cur_id == dst_id) {
-                // in-place pass on scratch X: OLD = X, NEW = the other scratch (dead at this point), which then becomes X
-                int X = cur_id, Y = (X == 1) ? 2 : 1;
+    { // K3: the reference's ping-pong including its in-place iteration (:648-719), resumable (see denoise_run)
+        ycge_ctx::Denoise &d = c->dn;
+        d.phys[0] = c->hist.p; d.phys[1] = c->sa.p; d.phys[2] = c->sb.p;
+        d.cur_id = 0; d.dst_id = 1; d.it = 0; d.K = K; d.parity = parity; d.ty0 = ty0; d.ty1 = ty1; d.pending = false;
+        for (int k = 0; k <= K; k++) d.halo_after[k] = halo_after[k];
+        c->launches_last = launches;
+        c->frame_open = true;
+        int rc = denoise_run(c);
+        if (rc) { c->frame_open = false; return rc; }
+        return 0;
+    }
+}
+
+// Runs à-trous passes from the saved state.  Unsharded: all of them, then the exposure samples.  Sharded: stops in
+// front of an in-place pass after preparing it (pre-pass + sentinel fill, neither needs the neighbour's rows).
+int denoise_run(ycge_ctx *c) {
+    ycge_ctx::Denoise &d = c->dn;
+    cudaStream_t s = c->stream;
+    const int W = c->W, H = c->H, ss = c->ss;
+    const EdgeDiv ed = c->edge_div;
+    const bool fast = c->fast_div;
+    const float4 *gnd = d.parity ? c->gnd1.p : c->gnd0.p, *gas = d.parity ? c->gas1.p : c->gas0.p;
+    int launches = 0;
+    auto range = [&](int halo, int &a, int &b) { a = std::max(0, d.ty0 - halo); b = std::min(H, d.ty1 + halo); };
+    while (d.it < d.K) {
+        const int it = d.it;
+        int a, b; range(d.halo_after[it + 1], a, b);
+        const int step = 1 << it;
+        if (d.cur_id == d.dst_id) {
+            // in-place pass on scratch X: OLD = X, NEW = the other scratch (dead at this point), which then becomes X
+            const int X = d.cur_id, Y = (X == 1) ? 2 : 1;
+            if (!d.pending) {
                 if (c->pre.n < (size_t)W * H * 25) CK(c, c->pre.alloc((size_t)W * H * 25));
                 // (1) everything that does not depend on new values, fully parallel
                 AtrousPreArgs pa;
-                pa.old_ = phys[X]; pa.gnd = img.gnd[parity]; pa.gas = img.gas[parity]; pa.pre = c->pre.p; pa.plane = (size_t)W * H;
+                pa.old_ = d.phys[X]; pa.gnd = gnd; pa.gas = gas; pa.pre = c->pre.p; pa.plane = (size_t)W * H;
                 pa.W = W; pa.H = H; pa.y0 = a; pa.y1 = b; pa.step = step; pa.e = ed;
                 if (fast) atrous_pre_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
                 else atrous_pre_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
                 launches++;
-                // (2) the wavefront.  NEW starts as the sentinel on the rows this pass produces; rows above `a` (a sharded
-                // tile's upper halo, written by the previous rank) already hold NEW values
-                AtrousChainArgs ia;
-                ia.old_ = phys[X]; ia.new_ = phys[Y]; ia.pre = c->pre.p; ia.plane = (size_t)W * H;
-                ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc;
-                CK(c, cudaMemsetAsync(phys[Y] + (size_t)a * W, 0xFF, (size_t)(b - a) * W * sizeof(float4), s));
-                if (c->inplace_ctas_per_launch <= 0) {
-                    int per_sm = 0;
-                    if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<true>, YCGE_AIC_WARPS * 32, 0));
-                    else CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<false>, YCGE_AIC_WARPS * 32, 0));
-                    cudaDeviceProp prop;
-                    CK(c, cudaGetDeviceProperties(&prop, c->device));
-                    c->inplace_ctas_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
-                }
-                // all CTAs of a launch must be co-resident (they wait on each other); rows are launched in order
-                const int rows_per_launch = std::max(1, c->inplace_ctas_per_launch * YCGE_AIC_WARPS / step);
-                for (int r0 = a; r0 < b; r0 += rows_per_launch) {
-                    ia.y0 = r0; ia.y1 = std::min(b, r0 + rows_per_launch);
-                    const int warps = (ia.y1 - ia.y0) * step; // one warp per chain, `step` chains per row
-                    if (fast) atrous_chain_kernel<true><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
-                    else atrous_chain_kernel<false><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
-                    launches++;
-                }
-                std::swap(phys[X], phys[Y]);
-            } else {
-                AtrousArgs aa;
-                aa.src = phys[cur_id]; aa.gnd = img.gnd[parity]; aa.gas = img.gas[parity]; aa.dst = phys[dst_id];
-                aa.W = W; aa.H = H; aa.y0 = a; aa.y1 = b; aa.step = step; aa.e = ed;
-                if (fast) atrous_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
-                else atrous_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
+                // NEW starts as the sentinel on the rows this pass produces; the rows just above `a` (a sharded tile's
+                // upper boundary, produced by the previous rank) are delivered by the caller before ycge_frame_inplace
+                CK(c, cudaMemsetAsync(d.phys[Y] + (size_t)a * W, 0xFF, (size_t)(b - a) * W * sizeof(float4), s));
+                d.pa = a; d.pb = b;
+                if (c->sharded) { d.pending = true; c->launches_last += launches; return 0; }
+            }
+            d.pending = false;
+            // (2) the wavefront
+            AtrousChainArgs ia;
+            ia.old_ = d.phys[X]; ia.new_ = d.phys[Y]; ia.pre = c->pre.p; ia.plane = (size_t)W * H;
+            ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc;
+            if (c->inplace_ctas_per_launch <= 0) {
+                int per_sm = 0;
+                if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<true>, YCGE_AIC_WARPS * 32, 0));
+                else CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<false>, YCGE_AIC_WARPS * 32, 0));
+                cudaDeviceProp prop;
+                CK(c, cudaGetDeviceProperties(&prop, c->device));
+                c->inplace_ctas_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
+            }
+            // all CTAs of a launch must be co-resident (they wait on each other); rows are launched in order
+            const int rows_per_launch = std::max(1, c->inplace_ctas_per_launch * YCGE_AIC_WARPS / step);
+            CK(c, cudaEventRecord(c->ev[7], s));
+            for (int r0 = a; r0 < b; r0 += rows_per_launch) {
+                ia.y0 = r0; ia.y1 = std::min(b, r0 + rows_per_launch);
+                const int warps = (ia.y1 - ia.y0) * step; // one warp per chain, `step` chains per row
+                if (fast) atrous_chain_kernel<true><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
+                else atrous_chain_kernel<false><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
                 launches++;
             }
-            int tmp = cur_id; // var tmp = cur; cur = dst; dst = (tmp == scratchA) ? scratchB : scratchA;   :718
-            cur_id = dst_id;
-            dst_id = (tmp == 1) ? 2 : 1;
+            CK(c, cudaEventRecord(c->ev[8], s));
+            c->chain_timed = true;
+            std::swap(d.phys[X], d.phys[Y]);
+        } else {
+            AtrousArgs aa;
+            aa.src = d.phys[d.cur_id]; aa.gnd = gnd; aa.gas = gas; aa.dst = d.phys[d.dst_id];
+            aa.W = W; aa.H = H; aa.y0 = a; aa.y1 = b; aa.step = step; aa.e = ed;
+            if (fast) atrous_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
+            else atrous_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(aa);
+            launches++;
         }
-        c->denoised = phys[cur_id];
+        const int tmp = d.cur_id; // var tmp = cur; cur = dst; dst = (tmp == scratchA) ? scratchB : scratchA;   :718
+        d.cur_id = d.dst_id;
+        d.dst_id = (tmp == 1) ? 2 : 1;
+        d.it++;
     }
+    c->denoised = d.phys[d.cur_id];
     CK(c, cudaEventRecord(c->ev[3], s));
     { // K4a
         int step = std::max(2, ss * 2); // :226; sample row k is pixel row k*step = top row of cell row k
-        int srow0 = div_up(ty0, step), srow1 = std::min(c->sh, div_up(ty1, step));
+        int srow0 = div_up(d.ty0, step), srow1 = std::min(c->sh, div_up(d.ty1, step));
         if (c->sharded) CK(c, cudaMemsetAsync(c->logs.p, 0, c->logs.n * sizeof(float), s));
-        const float4 *gas = (frame & 1) ? c->gas1.p : c->gas0.p;
         if (srow1 > srow0) {
             exposure_log_kernel<<<dim3(div_up(c->sw, 128), srow1 - srow0), 128, 0, s>>>(c->denoised, gas, c->logs.p, W, c->sw, step, srow0, srow1);
             launches++;
@@ -407,13 +445,25 @@ int frame_begin_impl(ycge_ctx *c) {
     }
     CK(c, cudaEventRecord(c->ev[4], s));
     CK(c, cudaGetLastError());
-    c->launches_last = launches;
-    c->frame_open = true;
+    c->launches_last += launches;
+    d.it = d.K + 1; // done
     return 0;
+}
+
+// the boundary rows of a prepared in-place pass: [lo, a) are needed from the rank above, [slo, sa) are owed to the rank below
+void halo_rows(const ycge_ctx *c, int &lo, int &a, int &slo, int &sa) {
+    const ycge_ctx::Denoise &d = c->dn;
+    a = d.pa; lo = std::max(0, a - (2 << d.it)); // the pass reaches 2 taps of stride 2^it upwards
+    sa = 0; slo = 0;
+    if (d.ty1 < c->H) { // the next tile starts at d.ty1 with the same halo
+        sa = std::max(0, d.ty1 - d.halo_after[d.it + 1]);
+        slo = std::max(0, sa - (2 << d.it));
+    }
 }
 
 int frame_finish_impl(ycge_ctx *c) {
     if (!c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish without ycge_frame_begin");
+    if (c->dn.it <= c->dn.K) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish while an in-place pass is pending (ycge_frame_halo / ycge_frame_inplace)");
     cudaStream_t s = c->stream;
     ExposureParams ep;
     ep.tone_exposure = c->P.tone_exposure; ep.ae_key = c->P.ae_key; ep.ae_speed = c->P.ae_speed; ep.ae_min = c->P.ae_min; ep.ae_max = c->P.ae_max;
@@ -826,9 +876,28 @@ YCGE_API int ycge_reset_history(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE
 
 YCGE_API int ycge_frame_begin(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); return frame_begin_impl(c); }
 YCGE_API int ycge_frame_finish(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); return frame_finish_impl(c); }
+YCGE_API int ycge_frame_halo(ycge_ctx *c, ycge_halo *h) {
+    if (!c || !h) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    memset(h, 0, sizeof *h);
+    if (!c->frame_open || !c->dn.pending) return 0;
+    int lo, a, slo, sa;
+    halo_rows(c, lo, a, slo, sa);
+    const int X = c->dn.cur_id, Y = (X == 1) ? 2 : 1;
+    float4 *nw = c->dn.phys[Y];
+    const size_t row = (size_t)c->W * sizeof(float4);
+    if (a > lo) { h->recv_ptr = nw + (size_t)lo * c->W; h->recv_bytes = (size_t)(a - lo) * row; h->recv_row0 = lo; h->recv_rows = a - lo; }
+    if (sa > slo) { h->send_ptr = nw + (size_t)slo * c->W; h->send_bytes = (size_t)(sa - slo) * row; h->send_row0 = slo; h->send_rows = sa - slo; }
+    return 1;
+}
+YCGE_API int ycge_frame_inplace(ycge_ctx *c) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (!c->frame_open || !c->dn.pending) return fail(c, YCGE_ERR_INVALID, "no in-place pass is pending");
+    return denoise_run(c);
+}
 
 YCGE_API int ycge_render_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
     int rc = frame_begin_impl(c);
     if (rc) return rc;
     rc = frame_finish_impl(c);
@@ -844,6 +913,7 @@ YCGE_API int ycge_render_frame_stats(ycge_ctx *c, ycge_cell *out, int32_t stride
 }
 YCGE_API int ycge_render_frames_async(ycge_ctx *c, int32_t n) {
     if (!c || n < 0) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
     for (int i = 0; i < n; i++) {
         int rc = frame_begin_impl(c);
         if (rc) return rc;
@@ -921,9 +991,11 @@ YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
         out->ms_trace = ms[0]; out->ms_taa = ms[1]; out->ms_atrous = ms[2]; out->ms_exposure = ms[3] + ms[4]; out->ms_cells = ms[5];
         float tot = 0.0f;
         if (cudaEventElapsedTime(&tot, c->ev[0], c->ev[6]) == cudaSuccess) out->ms_total = tot;
+        if (c->chain_timed && cudaEventElapsedTime(&tot, c->ev[7], c->ev[8]) == cudaSuccess) out->ms_atrous_chain = tot;
     }
     out->ae_exposure = es.ae_exposure; out->log_sum = es.log_sum; out->log_cnt = es.cnt;
     out->kernel_launches = c->launches_last;
+    out->fast_div = c->fast_div ? 1 : 0;
     return 0;
 }
 

@@ -1,0 +1,134 @@
+"""Row-tile sharding of one frame over N processes (one per GPU), SURVEY.md 8(e).
+
+The framebuffer is cut into contiguous tiles of cell rows; the scene is replicated.  Per frame every rank
+  1. traces / TAA-blends / filters its tile plus the pixel-row halo the image passes need (recomputed, bit-identical),
+  2. for the reference's in-place à-trous iteration (RaytraceRenderer.cs:718) — whose rows depend on ALL rows above —
+     receives the few boundary rows from the rank above, runs its part of the wavefront, and passes its own boundary
+     rows on to the rank below (point-to-point, the path's one real exchange step),
+  3. contributes its log-luminance samples to a sum all-reduce (every slot is owned by exactly one rank, so the sum is
+     a gather; every rank then adds them in the reference's serial order — identical exposure everywhere),
+  4. converts its tile to console cells, which are gathered on rank 0.
+
+`TileBackend` is the five-call interface of the C ABI (ycge_frame_begin / _halo / _inplace / _finish + buffers) seen
+as torch tensors; `CudaTileBackend` is the product implementation on libycge.so.  The collectives are torch.distributed
+(NCCL on GPUs; the orchestration is backend-agnostic and is tested on CPU with gloo and a fake tile backend).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import api
+
+
+def tile_rows(rank: int, world: int, fb_h: int) -> Tuple[int, int]:
+    """Cell rows [row0, row0 + rows) owned by `rank`: contiguous, aligned to cell rows, sizes differ by at most one."""
+    row0 = rank * fb_h // world
+    row1 = (rank + 1) * fb_h // world
+    return row0, row1 - row0
+
+
+class _DevMem:
+    """A raw device range exposed through __cuda_array_interface__ so that torch can alias it (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def device_bytes(ptr: int, nbytes: int, device: int) -> torch.Tensor:
+    return torch.as_tensor(_DevMem(ptr, nbytes), device=torch.device("cuda", device))
+
+
+class CudaTileBackend:
+    """One row tile on one GPU through the C ABI.  All work is enqueued on torch's current stream."""
+
+    def __init__(self, scene: api.HostScene, fb_w: int, fb_h: int, ss: int, row0: int, rows: int, device: int):
+        self.r = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device, tile_row0=row0, tile_rows=rows)
+        self.device = device
+        self.fb_w, self.fb_h, self.rows = fb_w, fb_h, rows
+        self.r.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        p, n = self.r.device_ptr(api.PTR_LOG_SAMPLES)
+        self.logs = device_bytes(p, n, device).view(torch.float32)
+        p, n = self.r.device_ptr(api.PTR_CELLS)
+        self.cells = device_bytes(p, n, device)
+
+    def set_camera(self, pos, yaw, pitch):
+        self.r.SetCamera(pos, yaw, pitch)
+
+    def begin(self):
+        self.r.frame_begin()
+
+    def halo(self) -> Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]:
+        h = self.r.frame_halo()
+        if h is None:
+            return None
+        recv = device_bytes(h.recv_ptr, h.recv_bytes, self.device) if h.recv_bytes else None
+        send = device_bytes(h.send_ptr, h.send_bytes, self.device) if h.send_bytes else None
+        return recv, send
+
+    def inplace(self):
+        self.r.frame_inplace()
+
+    def finish(self):
+        self.r.frame_finish()
+
+    def close(self):
+        self.r.close()
+
+
+class ShardedRenderer:
+    """IConsoleRenderer over N ranks: SetCamera + TryFlipAndBlit, the assembled frame lands on rank 0."""
+
+    def __init__(self, backend, rank: int, world: int, fb_w: int, fb_h: int, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.b, self.rank, self.world, self.fb_w, self.fb_h = backend, rank, world, fb_w, fb_h
+        self.tiles = [tile_rows(r, world, fb_h) for r in range(world)]
+        self.max_rows = max(t[1] for t in self.tiles)
+        self.cell_bytes = api.CELL_DTYPE.itemsize
+        dev = backend.cells.device
+        self._pad = torch.zeros(self.max_rows * fb_w * self.cell_bytes, dtype=torch.uint8, device=dev)
+        self._gather = [torch.zeros_like(self._pad) for _ in range(world)] if rank == 0 else None
+        self.launch_frames = 0
+
+    def SetCamera(self, pos, yaw, pitch):
+        self.b.set_camera(pos, yaw, pitch)
+
+    def render_device(self):
+        """One frame, everything enqueued on the current stream; returns the gathered tiles (rank 0) without host sync."""
+        dist, b = self.dist, self.b
+        b.begin()
+        while True:
+            h = b.halo()
+            if h is None:
+                break
+            recv, send = h
+            if recv is not None and self.rank > 0:
+                dist.recv(recv, src=self.rank - 1, group=self.group)
+            b.inplace()
+            if send is not None and self.rank < self.world - 1:
+                dist.send(send, dst=self.rank + 1, group=self.group)
+        if self.world > 1:
+            dist.all_reduce(b.logs, op=dist.ReduceOp.SUM, group=self.group)
+        b.finish()
+        n = self.tiles[self.rank][1] * self.fb_w * self.cell_bytes
+        if self.world == 1:
+            return [b.cells]
+        self._pad[:n].copy_(b.cells[:n])
+        dist.gather(self._pad, self._gather, dst=0, group=self.group)
+        return self._gather
+
+    def assemble(self, gathered) -> np.ndarray:
+        """Rank 0: the gathered tiles as one (fb_h, fb_w) cell array on the host."""
+        out = np.empty((self.fb_h, self.fb_w), api.CELL_DTYPE)
+        for r, (row0, rows) in enumerate(self.tiles):
+            n = rows * self.fb_w * self.cell_bytes
+            out[row0:row0 + rows] = gathered[r][:n].cpu().numpy().view(api.CELL_DTYPE).reshape(rows, self.fb_w)
+        return out
+
+    def TryFlipAndBlit(self) -> Optional[np.ndarray]:
+        g = self.render_device()
+        return self.assemble(g) if self.rank == 0 else None
