@@ -72,6 +72,7 @@ struct ycge_ctx {
 
     // image planes
     DevBuf<float4> cur, gnd0, gnd1, gas0, gas1, hist, sa, sb;
+    DevBuf<unsigned long long> chain_trace;
     DevBuf<float4> pre; // in-place à-trous pass: 25 planes of per-tap precomputed terms / guide weights
     DevBuf<int2> prim;
     DevBuf<float> rays_dbg;
@@ -397,7 +398,12 @@ int denoise_run(ycge_ctx *c) {
             // (2) the wavefront
             AtrousChainArgs ia;
             ia.old_ = d.phys[X]; ia.new_ = d.phys[Y]; ia.pre = c->pre.p; ia.plane = (size_t)W * H;
-            ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc;
+            ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc; ia.trace = nullptr;
+            if (getenv("YCGE_CHAIN_TRACE")) { // development aid: per-chain timestamps, dumped by ycge_get_stats
+                if (c->chain_trace.n < (size_t)H * step * 32) CK(c, c->chain_trace.alloc((size_t)H * step * 32));
+                CK(c, cudaMemsetAsync(c->chain_trace.p, 0, c->chain_trace.n * 8, s));
+                ia.trace = c->chain_trace.p;
+            }
             if (c->inplace_ctas_per_launch <= 0) {
                 int per_sm = 0;
                 if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<true>, YCGE_AIC_WARPS * 32, 0));
@@ -541,13 +547,13 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
         e.dc = std::max(1e-6f, c->P.c_phi); e.dn = std::max(1e-6f, c->P.n_phi); e.dz = std::max(1e-6f, c->P.z_phi); e.da = std::max(1e-6f, c->P.a_phi);
         e.rc = (float)(1.0 / (double)e.dc); e.rn = (float)(1.0 / (double)e.dn); e.rz = (float)(1.0 / (double)e.dz); e.ra = (float)(1.0 / (double)e.da);
         DevBuf<unsigned int> mm;
-        CK(nullptr, mm.alloc(4));
-        CK(nullptr, cudaMemsetAsync(mm.p, 0, 16, c->stream));
+        CK(nullptr, mm.alloc(8));
+        CK(nullptr, cudaMemsetAsync(mm.p, 0, 32, c->stream));
         div_selftest_kernel<<<(0x7F800000u >> 8) + 1, 256, 0, c->stream>>>(e, mm.p);
-        unsigned int h[4] = {1, 1, 1, 1};
-        CK(nullptr, cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        unsigned int h[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+        CK(nullptr, cudaMemcpyAsync(h, mm.p, 32, cudaMemcpyDeviceToHost, c->stream));
         CK(nullptr, cudaStreamSynchronize(c->stream));
-        c->fast_div = (h[0] | h[1] | h[2] | h[3]) == 0;
+        c->fast_div = (h[0] | h[1] | h[2] | h[3] | h[4]) == 0;
         if (!(e.dc < 1e30f && e.dn < 1e30f && e.dz < 1e30f && e.da < 1e30f)) c->fast_div = false;
     }
     static const int bounds[5] = {48, 114, 154, 194, 234}; // ANSITerminalRenderer.cs:288-296
@@ -994,6 +1000,13 @@ YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
         if (c->chain_timed && cudaEventElapsedTime(&tot, c->ev[7], c->ev[8]) == cudaSuccess) out->ms_atrous_chain = tot;
     }
     out->ae_exposure = es.ae_exposure; out->log_sum = es.log_sum; out->log_cnt = es.cnt;
+    if (const char *path = getenv("YCGE_CHAIN_TRACE")) {
+        if (c->chain_trace.n) {
+            std::vector<unsigned long long> h(c->chain_trace.n);
+            cudaMemcpy(h.data(), c->chain_trace.p, h.size() * 8, cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        }
+    }
     out->kernel_launches = c->launches_last;
     out->fast_div = c->fast_div ? 1 : 0;
     return 0;
