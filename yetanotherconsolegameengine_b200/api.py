@@ -18,7 +18,7 @@ from typing import Optional
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libycge.so")
+LIB_PATH = os.environ.get("YCGE_LIB", os.path.join(_PKG_DIR, "libycge.so"))  # YCGE_LIB: development aid (kernel build variants)
 HOST_LIB_PATH = os.path.join(_PKG_DIR, "libycge_host.so")
 
 

@@ -678,8 +678,11 @@ struct PathItem { RayD ray; V3 beta; int mirror, diffuse; };
 // ------------------------------------------------------------------------------------------------ the kernel
 // Block = 128 threads = 4 warps; a warp covers an 8x4 pixel tile (coherent primary rays, 128-byte row segments
 // on every image write); the block covers 16x8 pixels.
+#ifndef YCGE_TRACE_MIN_CTAS
+#define YCGE_TRACE_MIN_CTAS 8 // measured on B200 (dragon 1080p): 5 CTAs/SM 1.21 ms, 6: 1.22, 8: 1.19, 10: 1.21 — occupancy is not the limiter
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(128) trace_kernel(DevScene sc, FrameConsts fc, TraceParams tp, ImagePlanes img, int parity, TraceCounters *counters, TraceTotals *totals) {
+__global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScene sc, FrameConsts fc, TraceParams tp, ImagePlanes img, int parity, TraceCounters *counters, TraceTotals *totals) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int py = fc.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
