@@ -283,6 +283,17 @@ typedef struct ycge_halo {
     void *recv_ptr;  size_t recv_bytes;  int32_t recv_row0, recv_rows;  /* NULL/0 for the top tile */
     void *send_ptr;  size_t send_bytes;  int32_t send_row0, send_rows;  /* NULL/0 for the bottom tile; valid after ycge_frame_inplace */
 } ycge_halo;
+/* Peer hand-off (optional, replaces the caller's send/recv of ycge_frame_halo): every rank exports its two à-trous
+ * scratch buffers and a flag word (raw device pointers for ranks in one process, CUDA IPC handles across processes) and
+ * attaches to its neighbours.  The wavefront kernel of rank g then stores its boundary rows straight into rank g+1's
+ * output buffer over NVLink, pixel by pixel, and rank g+1's wavefront polls them like any other row: the wavefront
+ * crosses GPU boundaries without a kernel boundary.  With peers attached ycge_frame_halo reports 0 bytes. */
+typedef struct ycge_peer {
+    void *sa, *sb, *flags;                                   /* device pointers (valid inside the exporting process) */
+    unsigned char sa_ipc[64], sb_ipc[64], flags_ipc[64];     /* cudaIpcMemHandle_t of the same allocations */
+} ycge_peer;
+YCGE_API int ycge_peer_export(ycge_ctx *ctx, ycge_peer *out);
+YCGE_API int ycge_peer_attach(ycge_ctx *ctx, const ycge_peer *above, const ycge_peer *below, int32_t via_ipc); /* NULL: no neighbour */
 YCGE_API int ycge_frame_begin(ycge_ctx *ctx);
 YCGE_API int ycge_frame_halo(ycge_ctx *ctx, ycge_halo *out);  /* 1: an in-place pass is pending, 0: none (negative: error) */
 YCGE_API int ycge_frame_inplace(ycge_ctx *ctx);

@@ -332,9 +332,10 @@ def test_full_size_properties_voxel_world_1440p():
 
 
 # ------------------------------------------------------------------------------------------- row tiles (sharding kernels)
+@pytest.mark.parametrize("peers", [False, True], ids=["copy-handoff", "peer-handoff"])
 @pytest.mark.parametrize("scene,fb_w,fb_h,ss,n_tiles,pose", [("boxes", 40, 24, 2, 3, None), ("knot:60x16", 48, 27, 4, 4, api.BENCH_POSE),
                                                              ("mirror_spheres", 33, 8, 1, 8, None), ("voxel_world:64x64", 40, 12, 2, 2, None)])
-def test_row_tiles_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pose):
+def test_row_tiles_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pose, peers):
     """N row-tile contexts on ONE GPU, driven through the phase API with a loop-back exchange (device copies instead of
     NCCL): boundary rows of the in-place pass handed tile -> tile, exposure samples summed, cells concatenated.  Must equal
     the unsharded frame bit for bit, over several frames (TAA history and exposure state live per tile)."""
@@ -347,6 +348,19 @@ def test_row_tiles_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pos
         for r in range(n_tiles):
             row0, rows = sharding.tile_rows(r, n_tiles, fb_h)
             tiles.append(sharding.CudaTileBackend(s, fb_w, fb_h, ss, row0, rows, 0))
+        if peers and min(t.rows for t in tiles) * 2 * ss < 4:
+            # a tile shorter than the in-place pass reaches cannot use the peer hand-off: the library says so
+            ex = [t.peer_export() for t in tiles]
+            with pytest.raises(api.YcgeError):
+                tiles[0].peer_attach(None, ex[1], via_ipc=False)
+            for t in tiles:
+                t.close()
+            full.close()
+            return
+        if peers:  # the wavefront kernels store the boundary rows straight into the tile below (raw pointers: one process)
+            ex = [t.peer_export() for t in tiles]
+            for i, t in enumerate(tiles):
+                t.peer_attach(ex[i - 1] if i > 0 else None, ex[i + 1] if i + 1 < n_tiles else None, via_ipc=False)
         if pose is not None:
             full.SetCamera(*pose)
             for t in tiles:
@@ -362,6 +376,7 @@ def test_row_tiles_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pos
                     break
                 prev_send = None
                 for t, (recv, send) in zip(tiles, halos):
+                    assert not (peers and (recv is not None or send is not None))
                     if recv is not None:
                         assert prev_send is not None and prev_send.numel() == recv.numel()
                         recv.copy_(prev_send)

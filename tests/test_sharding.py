@@ -91,7 +91,7 @@ def _worker(rank, world, port, fb_w, fb_h, ss, frames, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         b = FakeTileBackend("boxes", fb_w, fb_h, ss, rank, world)
-        r = sharding.ShardedRenderer(b, rank, world, fb_w, fb_h)
+        r = sharding.ShardedRenderer(b, rank, world, fb_w, fb_h)  # (the fake backend has no peer buffers: send/recv path)
         ok = True
         for f in range(frames):
             if f == 2:

@@ -90,6 +90,11 @@ class Halo(C.Structure):
                 ("send_ptr", C.c_void_p), ("send_bytes", C.c_size_t), ("send_row0", C.c_int32), ("send_rows", C.c_int32)]
 
 
+class Peer(C.Structure):
+    _fields_ = [("sa", C.c_void_p), ("sb", C.c_void_p), ("flags", C.c_void_p),
+                ("sa_ipc", C.c_ubyte * 64), ("sb_ipc", C.c_ubyte * 64), ("flags_ipc", C.c_ubyte * 64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("rays", C.c_uint64), ("rays_total", C.c_uint64), ("top_nodes_popped", C.c_uint64), ("mesh_nodes_popped", C.c_uint64),
                 ("leaf_refs", C.c_uint64), ("tris_tested", C.c_uint64), ("prims_tested", C.c_uint64), ("dda_cells", C.c_uint64),
@@ -113,7 +118,7 @@ ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
     "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
     "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
-    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
+    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
     "ycge_frame_finish", "ycge_device_ptr",
     "ycge_set_stream", "ycge_debug_read", "ycge_get_stats", "ycge_get_frame_counter", "ycge_rng_kat",
 ]
@@ -156,6 +161,8 @@ def load_lib() -> C.CDLL:
         lib.ycge_frame_begin.argtypes = [vp]
         lib.ycge_frame_finish.argtypes = [vp]
         lib.ycge_frame_halo.argtypes = [vp, C.POINTER(Halo)]
+        lib.ycge_peer_export.argtypes = [vp, C.POINTER(Peer)]
+        lib.ycge_peer_attach.argtypes = [vp, C.POINTER(Peer), C.POINTER(Peer), C.c_int32]
         lib.ycge_frame_inplace.argtypes = [vp]
         lib.ycge_device_ptr.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
         lib.ycge_set_stream.argtypes = [vp, vp]
@@ -435,6 +442,15 @@ class CudaRaytraceRenderer:
 
     def frame_inplace(self):
         self._ck(self._lib.ycge_frame_inplace(self.ctx))
+
+    def peer_export(self) -> Peer:
+        p = Peer()
+        self._ck(self._lib.ycge_peer_export(self.ctx, C.byref(p)))
+        return p
+
+    def peer_attach(self, above: Optional[Peer], below: Optional[Peer], via_ipc: bool):
+        self._ck(self._lib.ycge_peer_attach(self.ctx, C.byref(above) if above is not None else None,
+                                            C.byref(below) if below is not None else None, 1 if via_ipc else 0))
 
     def set_stream(self, cuda_stream: int):
         self._ck(self._lib.ycge_set_stream(self.ctx, C.c_void_p(cuda_stream)))

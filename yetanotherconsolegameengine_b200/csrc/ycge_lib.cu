@@ -120,6 +120,12 @@ struct ycge_ctx {
     } dn;
     EdgeDiv edge_div;      // max(1e-6, phi) and reciprocals (RaytraceRenderer.cs:694-697)
     bool chain_timed = false;
+    // peer hand-off (ycge_peer_attach)
+    DevBuf<int> flags;                 // [0]: "the rank below has reset its buffer for frame N" (written by that rank)
+    float4 *below_sa = nullptr, *below_sb = nullptr;
+    int *above_flags = nullptr;
+    bool peers = false, has_above = false, has_below = false;
+    void *ipc_opened[3] = {nullptr, nullptr, nullptr};
     bool fast_div = false; // the FMA division sequence was verified against IEEE division for these four divisors
 
     // timing
@@ -278,6 +284,7 @@ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // ---- the per-frame launch sequence ----------------------------------------------------------------------------
 int denoise_run(ycge_ctx *c);
+void halo_rows(const ycge_ctx *c, int &lo, int &a, int &slo, int &sa);
 int frame_begin_impl(ycge_ctx *c) {
     if (!c->have_scene) return fail(c, YCGE_ERR_NO_SCENE, "Scene BVH not built; call ycge_scene_upload() after populating the scene");
     if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_begin called twice without ycge_frame_finish");
@@ -390,8 +397,11 @@ int denoise_run(ycge_ctx *c) {
                 launches++;
                 // NEW starts as the sentinel on the rows this pass produces; the rows just above `a` (a sharded tile's
                 // upper boundary, produced by the previous rank) are delivered by the caller before ycge_frame_inplace
-                CK(c, cudaMemsetAsync(d.phys[Y] + (size_t)a * W, 0xFF, (size_t)(b - a) * W * sizeof(float4), s));
                 d.pa = a; d.pb = b;
+                int m0 = a;
+                if (c->peers && c->has_above) { int lo, aa, slo, sa_; halo_rows(c, lo, aa, slo, sa_); m0 = lo; } // the boundary rows arrive through the sentinel too
+                CK(c, cudaMemsetAsync(d.phys[Y] + (size_t)m0 * W, 0xFF, (size_t)(b - m0) * W * sizeof(float4), s));
+                if (c->peers && c->has_above) { peer_signal_kernel<<<1, 1, 0, s>>>(c->above_flags, (int)c->frame_counter); launches++; }
                 if (c->sharded) { d.pending = true; c->launches_last += launches; return 0; }
             }
             d.pending = false;
@@ -399,6 +409,12 @@ int denoise_run(ycge_ctx *c) {
             AtrousChainArgs ia;
             ia.old_ = d.phys[X]; ia.new_ = d.phys[Y]; ia.pre = c->pre.p; ia.plane = (size_t)W * H;
             ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc; ia.trace = nullptr;
+            ia.peer_new = nullptr; ia.peer_y0 = ia.peer_y1 = 0; ia.ready = c->flags.p; ia.frame = (int)c->frame_counter;
+            if (c->peers && c->has_below) {
+                int lo, aa, slo, sa_; halo_rows(c, lo, aa, slo, sa_);
+                if (sa_ > slo) { ia.peer_new = (Y == 2) ? c->below_sb : c->below_sa; ia.peer_y0 = slo; ia.peer_y1 = sa_; }
+                // NOTE: the ping-pong is the same on every rank, so the rank below also has its NEW in physical buffer Y
+            }
             if (getenv("YCGE_CHAIN_TRACE")) { // development aid: per-chain timestamps, dumped by ycge_get_stats
                 if (c->chain_trace.n < (size_t)H * step * 32) CK(c, c->chain_trace.alloc((size_t)H * step * 32));
                 CK(c, cudaMemsetAsync(c->chain_trace.p, 0, c->chain_trace.n * 8, s));
@@ -540,6 +556,8 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     CK(nullptr, cudaMemcpyAsync(c->expo.p, &es, sizeof es, cudaMemcpyHostToDevice, c->stream));
     CK(nullptr, c->counters.alloc(1));
     CK(nullptr, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), c->stream));
+    CK(nullptr, c->flags.alloc(16));
+    CK(nullptr, cudaMemsetAsync(c->flags.p, 0, 16 * sizeof(int), c->stream));
     CK(nullptr, c->totals.alloc(1));
     CK(nullptr, cudaMemsetAsync(c->totals.p, 0, sizeof(TraceTotals), c->stream));
     { // edge-stopping divisors; verify the fast division over every non-negative binary32 numerator (a few ms, once)
@@ -570,6 +588,7 @@ YCGE_API void ycge_destroy(ycge_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -891,9 +910,53 @@ YCGE_API int ycge_frame_halo(ycge_ctx *c, ycge_halo *h) {
     const int X = c->dn.cur_id, Y = (X == 1) ? 2 : 1;
     float4 *nw = c->dn.phys[Y];
     const size_t row = (size_t)c->W * sizeof(float4);
+    if (c->peers) return 1; // the wavefront kernels exchange the rows themselves
     if (a > lo) { h->recv_ptr = nw + (size_t)lo * c->W; h->recv_bytes = (size_t)(a - lo) * row; h->recv_row0 = lo; h->recv_rows = a - lo; }
     if (sa > slo) { h->send_ptr = nw + (size_t)slo * c->W; h->send_bytes = (size_t)(sa - slo) * row; h->send_row0 = slo; h->send_rows = sa - slo; }
     return 1;
+}
+YCGE_API int ycge_peer_export(ycge_ctx *c, ycge_peer *out) {
+    if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    memset(out, 0, sizeof *out);
+    out->sa = c->sa.p; out->sb = c->sb.p; out->flags = c->flags.p;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ycge_peer assumes 64-byte IPC handles");
+    CK(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->sa_ipc, c->sa.p));
+    CK(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->sb_ipc, c->sb.p));
+    CK(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->flags_ipc, c->flags.p));
+    return 0;
+}
+YCGE_API int ycge_peer_attach(ycge_ctx *c, const ycge_peer *above, const ycge_peer *below, int32_t via_ipc) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (!c->sharded) return fail(c, YCGE_ERR_INVALID, "peers are for row-tile contexts");
+    { // a tile forwards nothing: the rows the rank below needs must be rows this rank computes itself
+        int need = 0;
+        for (int it = 1; it < std::max(1, c->P.atrous_iterations); it += 2) need = 2 << it; // in-place passes are the odd iterations
+        if (below && c->tile_rows * 2 * c->ss < need)
+            return fail(c, YCGE_ERR_INVALID, "tile too small for the peer hand-off (fewer pixel rows than the in-place pass reaches); use the send/recv hand-off of ycge_frame_halo");
+    }
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (auto &p : c->ipc_opened) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    c->has_above = above != nullptr; c->has_below = below != nullptr;
+    c->above_flags = nullptr; c->below_sa = c->below_sb = nullptr;
+    auto open = [&](const unsigned char *h, void *raw, int slot, void **out) -> int {
+        if (!via_ipc) { *out = raw; return 0; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, h, sizeof mh);
+        CK(c, cudaIpcOpenMemHandle(out, mh, cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_opened[slot] = *out;
+        return 0;
+    };
+    int rc;
+    if (above) { void *p; if ((rc = open(above->flags_ipc, above->flags, 0, &p))) return rc; c->above_flags = (int *)p; }
+    if (below) {
+        void *p;
+        if ((rc = open(below->sa_ipc, below->sa, 1, &p))) return rc; c->below_sa = (float4 *)p;
+        if ((rc = open(below->sb_ipc, below->sb, 2, &p))) return rc; c->below_sb = (float4 *)p;
+    }
+    c->peers = true;
+    return 0;
 }
 YCGE_API int ycge_frame_inplace(ycge_ctx *c) {
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");

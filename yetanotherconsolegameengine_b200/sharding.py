@@ -48,7 +48,7 @@ class CudaTileBackend:
     def __init__(self, scene: api.HostScene, fb_w: int, fb_h: int, ss: int, row0: int, rows: int, device: int):
         self.r = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device, tile_row0=row0, tile_rows=rows)
         self.device = device
-        self.fb_w, self.fb_h, self.rows = fb_w, fb_h, rows
+        self.fb_w, self.fb_h, self.rows, self.ss = fb_w, fb_h, rows, ss
         self.r.set_stream(torch.cuda.current_stream(device).cuda_stream)
         p, n = self.r.device_ptr(api.PTR_LOG_SAMPLES)
         self.logs = device_bytes(p, n, device).view(torch.float32)
@@ -57,6 +57,15 @@ class CudaTileBackend:
 
     def set_camera(self, pos, yaw, pitch):
         self.r.SetCamera(pos, yaw, pitch)
+
+    def peer_export(self) -> bytes:
+        return bytes(self.r.peer_export())
+
+    def peer_attach(self, above: Optional[bytes], below: Optional[bytes], via_ipc: bool):
+        """Attach to the neighbours' exported buffers: the wavefront kernels then hand the boundary rows of the in-place pass
+        over themselves (peer stores over NVLink) and `halo()` reports nothing to send or receive."""
+        mk = lambda b: api.Peer.from_buffer_copy(b) if b is not None else None
+        self.r.peer_attach(mk(above), mk(below), via_ipc)
 
     def begin(self):
         self.r.frame_begin()
@@ -82,7 +91,7 @@ class CudaTileBackend:
 class ShardedRenderer:
     """IConsoleRenderer over N ranks: SetCamera + TryFlipAndBlit, the assembled frame lands on rank 0."""
 
-    def __init__(self, backend, rank: int, world: int, fb_w: int, fb_h: int, group=None):
+    def __init__(self, backend, rank: int, world: int, fb_w: int, fb_h: int, group=None, peers: bool = True):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.b, self.rank, self.world, self.fb_w, self.fb_h = backend, rank, world, fb_w, fb_h
@@ -92,7 +101,16 @@ class ShardedRenderer:
         dev = backend.cells.device
         self._pad = torch.zeros(self.max_rows * fb_w * self.cell_bytes, dtype=torch.uint8, device=dev)
         self._gather = [torch.zeros_like(self._pad) for _ in range(world)] if rank == 0 else None
-        self.launch_frames = 0
+        self.peer_handoff = False
+        # the peer hand-off needs every tile to be at least as tall as the in-place pass reaches (4 pixel rows by default);
+        # every rank evaluates the same condition, so all of them take the same path
+        tall_enough = min(t[1] for t in self.tiles) * 2 * getattr(backend, "ss", 1) >= 4
+        if world > 1 and peers and tall_enough and hasattr(backend, "peer_export"):
+            mine = backend.peer_export()
+            everyone: List[Optional[bytes]] = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+            backend.peer_attach(everyone[rank - 1] if rank > 0 else None, everyone[rank + 1] if rank < world - 1 else None, via_ipc=True)
+            self.peer_handoff = True
 
     def SetCamera(self, pos, yaw, pitch):
         self.b.set_camera(pos, yaw, pitch)
