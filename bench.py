@@ -208,7 +208,8 @@ def main():
         row0, rows = sharding.tile_rows(rank, n, fb_h)
         with torch.cuda.stream(stream):
             b = sharding.CudaTileBackend(scene, fb_w, fb_h, ss, row0, rows, local_rank)
-            sr = sharding.ShardedRenderer(b, rank, n, fb_w, fb_h)
+            sr = sharding.ShardedRenderer(b, rank, n, fb_w, fb_h, peers=not os.environ.get("YCGE_NO_PEERS"))
+            peer_handoff = sr.peer_handoff
             sr.SetCamera(*pose)
             # the event counters of the whole frame come from an unsharded frame on rank 0's GPU (untimed)
             st_events = None
@@ -259,6 +260,8 @@ def main():
             st3 = b.r.stats()
         # max over ranks of the device time; rays summed over ranks (halo rows are traced redundantly and counted as
         # work done — rays/frame of the UNSHARDED frame is what the metric divides by, so use the unsharded count)
+        all_stage = [None] * n
+        dist.all_gather_object(all_stage, {k: round(v, 3) for k, v in stage_ms.items()})
         t = torch.tensor([ms_local, e2e_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
@@ -308,7 +311,7 @@ def main():
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
                 "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}",
                            "l2": "per-frame working set (8 float4 image planes = %d MB) exceeds the 126 MB L2; no explicit flush" % (W * H * 128 // (1 << 20))},
-                "stage_ms": stage_ms,
+                "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff} if n > 1 else {}),
                 "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_frame * args.steps * n,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}

@@ -1,0 +1,39 @@
+"""Run under torchrun on N GPUs: renders frames through the row-tile sharding (peer hand-off when possible) and checks the
+assembled cells on rank 0 against the unsharded frame rendered on rank 0's GPU, bit for bit.
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/multigpu_check.py [scene fb_w fb_h ss frames]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+import yetanotherconsolegameengine_b200 as pkg
+from yetanotherconsolegameengine_b200 import api, sharding
+
+scene_name = sys.argv[1] if len(sys.argv) > 1 else "dragon"
+fb_w, fb_h, ss, frames = (int(x) for x in (sys.argv[2:6] if len(sys.argv) > 5 else (480, 135, 4, 3)))
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+scene = pkg.HostScene(scene_name)
+pose = pkg.BENCH_POSE if scene.n_meshes else scene.default_camera()[:3]
+row0, rows = sharding.tile_rows(rank, world, fb_h)
+b = sharding.CudaTileBackend(scene, fb_w, fb_h, ss, row0, rows, local)
+sr = sharding.ShardedRenderer(b, rank, world, fb_w, fb_h, peers=not os.environ.get("YCGE_NO_PEERS"))
+sr.SetCamera(*pose)
+full = None
+if rank == 0:
+    full = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local)
+    full.SetCamera(*pose)
+ok = True
+for f in range(frames):
+    got = sr.TryFlipAndBlit()
+    if rank == 0:
+        ref = full.TryFlipAndBlit()
+        same = got.tobytes() == ref.tobytes()
+        ok &= same
+        print(f"frame {f + 1}: sharded x{world} (peer_handoff={sr.peer_handoff}) {'==' if same else '!='} unsharded", flush=True)
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, 0)
+dist.destroy_process_group()
+sys.exit(0 if int(flag[0]) else 1)

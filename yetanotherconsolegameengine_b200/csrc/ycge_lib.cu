@@ -120,6 +120,8 @@ struct ycge_ctx {
     } dn;
     EdgeDiv edge_div;      // max(1e-6, phi) and reciprocals (RaytraceRenderer.cs:694-697)
     bool chain_timed = false;
+    cudaStream_t aux = nullptr; // side stream: the peer-storing rows of the wavefront run as a concurrent kernel
+    cudaEvent_t e_fork = nullptr, e_join = nullptr;
     // peer hand-off (ycge_peer_attach)
     DevBuf<int> flags;                 // [0]: "the rank below has reset its buffer for frame N" (written by that rank)
     float4 *below_sa = nullptr, *below_sb = nullptr;
@@ -422,8 +424,8 @@ int denoise_run(ycge_ctx *c) {
             }
             if (c->inplace_ctas_per_launch <= 0) {
                 int per_sm = 0;
-                if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<true>, YCGE_AIC_WARPS * 32, 0));
-                else CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<false>, YCGE_AIC_WARPS * 32, 0));
+                if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<true, true>, YCGE_AIC_WARPS * 32, 0));
+                else CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<false, true>, YCGE_AIC_WARPS * 32, 0));
                 cudaDeviceProp prop;
                 CK(c, cudaGetDeviceProperties(&prop, c->device));
                 c->inplace_ctas_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
@@ -431,12 +433,29 @@ int denoise_run(ycge_ctx *c) {
             // all CTAs of a launch must be co-resident (they wait on each other); rows are launched in order
             const int rows_per_launch = std::max(1, c->inplace_ctas_per_launch * YCGE_AIC_WARPS / step);
             CK(c, cudaEventRecord(c->ev[7], s));
-            for (int r0 = a; r0 < b; r0 += rows_per_launch) {
-                ia.y0 = r0; ia.y1 = std::min(b, r0 + rows_per_launch);
-                const int warps = (ia.y1 - ia.y0) * step; // one warp per chain, `step` chains per row
-                if (fast) atrous_chain_kernel<true><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
-                else atrous_chain_kernel<false><<<div_up(warps, YCGE_AIC_WARPS), YCGE_AIC_WARPS * 32, 0, s>>>(ia);
+            auto launch_chain = [&](cudaStream_t st, int r0, int r1, bool peer) {
+                AtrousChainArgs q = ia;
+                q.y0 = r0; q.y1 = r1;
+                const int warps = (r1 - r0) * step; // one warp per chain, `step` chains per row
+                const dim3 g(div_up(warps, YCGE_AIC_WARPS)), t(YCGE_AIC_WARPS * 32);
+                if (fast && peer) atrous_chain_kernel<true, true><<<g, t, 0, st>>>(q);
+                else if (fast) atrous_chain_kernel<true, false><<<g, t, 0, st>>>(q);
+                else if (peer) atrous_chain_kernel<false, true><<<g, t, 0, st>>>(q);
+                else atrous_chain_kernel<false, false><<<g, t, 0, st>>>(q);
                 launches++;
+            };
+            if (ia.peer_new && rows_per_launch >= b - a) {
+                // the rows that are also stored into the rank below run the (slower) peer variant as a second, concurrent
+                // kernel on a side stream; everything above them runs the plain variant
+                const int split = std::max(a, ia.peer_y0 - ((ia.peer_y0 - a) % std::max(1, YCGE_AIC_WARPS / step)));
+                CK(c, cudaEventRecord(c->e_fork, s));
+                if (split > a) launch_chain(s, a, split, false);
+                CK(c, cudaStreamWaitEvent(c->aux, c->e_fork, 0));
+                launch_chain(c->aux, split, b, true);
+                CK(c, cudaEventRecord(c->e_join, c->aux));
+                CK(c, cudaStreamWaitEvent(s, c->e_join, 0));
+            } else {
+                for (int r0 = a; r0 < b; r0 += rows_per_launch) launch_chain(s, r0, std::min(b, r0 + rows_per_launch), ia.peer_new != nullptr);
             }
             CK(c, cudaEventRecord(c->ev[8], s));
             c->chain_timed = true;
@@ -550,6 +569,9 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (auto &ev : c->ev) CK(nullptr, cudaEventCreate(&ev));
+    CK(nullptr, cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    CK(nullptr, cudaEventCreateWithFlags(&c->e_fork, cudaEventDisableTiming));
+    CK(nullptr, cudaEventCreateWithFlags(&c->e_join, cudaEventDisableTiming));
     CK(nullptr, c->expo.alloc(1));
     ExposureState es;
     es.ae_exposure = 1.0f; es.effective = 1.0f; es.log_sum = 0.0f; es.cnt = 0; // ToneMapper.cs:13,17
@@ -589,6 +611,9 @@ YCGE_API void ycge_destroy(ycge_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
+    if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+    if (ctx->e_fork) cudaEventDestroy(ctx->e_fork);
+    if (ctx->e_join) cudaEventDestroy(ctx->e_join);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
