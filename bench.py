@@ -42,13 +42,35 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled during the timed region (B200_PROFILING.md): NVML every 5 ms when pynvml is
+    importable (a bench run lasts a fraction of a second), else nvidia-smi every 100 ms."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            R = n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown, n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap
+            while not self._halt.is_set():
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if rs & r else "Not Active" for r in R])
+                except Exception:
+                    pass
+                self._halt.wait(0.005)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._halt.is_set():
             try:
@@ -69,7 +91,8 @@ class ClockSampler(threading.Thread):
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def algorithmic_bytes(st, W, H, fb_w, fb_h, ss):
@@ -293,8 +316,20 @@ def main():
     else:
         kname, kbytes, kms = "atrous_chain_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
     achieved = kbytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
+    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this same command (single GPU)
+    traffic, traffic_src = None, None
+    try:
+        if n == 1:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full.json")))
+            key = next(k for k in cap if k.startswith("trace_kernel<0>" if kname == "trace_kernel" else "atrous_chain_kernel"))
+            c0 = cap[key][-1]
+            to_b = lambda v: float(v.split()[0]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[v.split()[1]]
+            traffic = to_b(c0["dram__bytes_read.sum"]) + to_b(c0["dram__bytes_write.sum"])
+            traffic_src = "profiles/r01_ncu_full.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": kbytes, "kernel_ms": kms,
                 "frame": {"algorithmic_bytes": b_frame, "achieved_GBps": b_frame * fps / 1e9, "frac": b_frame * fps / 1e9 / peak},
                 "note": "algorithmic bytes = SURVEY 8(d) per-pixel figures of the reference's own layout; both candidate kernels are latency-bound (divergent traversal; serial wavefront), "
