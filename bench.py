@@ -242,8 +242,12 @@ def main():
                 r1.render_frame_stats()
                 st_events = r1.stats()
                 r1.close()
-            for _ in range(max(3, args.warmup)):
-                sr.render_device()
+            pipelined = sr.peer_handoff and not os.environ.get("YCGE_NO_PIPELINE")
+            if pipelined:
+                sr.render_pipelined(max(3, args.warmup))
+            else:
+                for _ in range(max(3, args.warmup)):
+                    sr.render_device()
             torch.cuda.synchronize()
             st0 = b.r.stats()
             sampler = ClockSampler(local_rank)
@@ -252,8 +256,11 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
             ev0.record(stream)
-            for _ in range(args.steps):
-                sr.render_device()
+            if pipelined:  # frames pipelined over the ranks; the stream joins its finishing side stream at the end
+                sr.render_pipelined(args.steps)
+            else:
+                for _ in range(args.steps):
+                    sr.render_device()
             ev1.record(stream)
             torch.cuda.synchronize()
             dist.barrier()
@@ -344,9 +351,9 @@ def main():
         line = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
-                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}",
+                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ("" if n == 1 else (", peer hand-off" if peer_handoff else ", NCCL send/recv hand-off") + (", frames pipelined over ranks (value); lock-step (e2e)" if pipelined else "")),
                            "l2": "per-frame working set (8 float4 image planes = %d MB) exceeds the 126 MB L2; no explicit flush" % (W * H * 128 // (1 << 20))},
-                "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff} if n > 1 else {}),
+                "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff, "frame_pipelining": pipelined} if n > 1 else {}),
                 "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_frame * args.steps * n,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}

@@ -294,6 +294,15 @@ typedef struct ycge_peer {
 } ycge_peer;
 YCGE_API int ycge_peer_export(ycge_ctx *ctx, ycge_peer *out);
 YCGE_API int ycge_peer_attach(ycge_ctx *ctx, const ycge_peer *above, const ycge_peer *below, int32_t via_ipc); /* NULL: no neighbour */
+/* Frame pipelining across ranks (asynchronous path): instead of ycge_frame_finish, park the finished tile (its denoised
+ * rows and exposure samples) in a slot; the all-reduce of the slot's samples, ycge_frame_finish_stashed (ordered exposure
+ * sum + cells, enqueued on the GIVEN stream) and the gather run later on a side stream, in frame order, while the ctx's
+ * stream already renders the next frames.  With the peer hand-off this turns the serial wavefront of the in-place pass
+ * into a pipeline: rank g renders frame f while rank g-1 renders frame f+1 (sharding.py: render_pipelined). */
+YCGE_API int ycge_stash_config(ycge_ctx *ctx, int32_t n_slots);
+YCGE_API int ycge_frame_stash(ycge_ctx *ctx, int32_t slot);
+YCGE_API int ycge_frame_finish_stashed(ycge_ctx *ctx, int32_t slot, void *cuda_stream);
+YCGE_API int ycge_stash_logs_ptr(ycge_ctx *ctx, int32_t slot, void **ptr, size_t *bytes);
 YCGE_API int ycge_frame_begin(ycge_ctx *ctx);
 YCGE_API int ycge_frame_halo(ycge_ctx *ctx, ycge_halo *out);  /* 1: an in-place pass is pending, 0: none (negative: error) */
 YCGE_API int ycge_frame_inplace(ycge_ctx *ctx);

@@ -33,6 +33,16 @@ for f in range(frames):
         same = got.tobytes() == ref.tobytes()
         ok &= same
         print(f"frame {f + 1}: sharded x{world} (peer_handoff={sr.peer_handoff}) {'==' if same else '!='} unsharded", flush=True)
+# the pipelined asynchronous path: same frames, finished out of step with their rendering
+if sr.peer_handoff or world == 1:
+    got = sr.render_pipelined(frames + 3, collect=True)
+    torch.cuda.synchronize()
+    if rank == 0:
+        for f, g in enumerate(got):
+            ref = full.TryFlipAndBlit()
+            same = sr.assemble(g).tobytes() == ref.tobytes()
+            ok &= same
+            print(f"frame {frames + f + 1}: pipelined x{world} {'==' if same else '!='} unsharded", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.destroy_process_group()

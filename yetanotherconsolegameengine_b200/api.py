@@ -118,7 +118,8 @@ ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
     "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
     "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
-    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
+    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
+    "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
     "ycge_frame_finish", "ycge_device_ptr",
     "ycge_set_stream", "ycge_debug_read", "ycge_get_stats", "ycge_get_frame_counter", "ycge_rng_kat",
 ]
@@ -161,6 +162,10 @@ def load_lib() -> C.CDLL:
         lib.ycge_frame_begin.argtypes = [vp]
         lib.ycge_frame_finish.argtypes = [vp]
         lib.ycge_frame_halo.argtypes = [vp, C.POINTER(Halo)]
+        lib.ycge_stash_config.argtypes = [vp, C.c_int32]
+        lib.ycge_frame_stash.argtypes = [vp, C.c_int32]
+        lib.ycge_frame_finish_stashed.argtypes = [vp, C.c_int32, vp]
+        lib.ycge_stash_logs_ptr.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
         lib.ycge_peer_export.argtypes = [vp, C.POINTER(Peer)]
         lib.ycge_peer_attach.argtypes = [vp, C.POINTER(Peer), C.POINTER(Peer), C.c_int32]
         lib.ycge_frame_inplace.argtypes = [vp]
@@ -442,6 +447,20 @@ class CudaRaytraceRenderer:
 
     def frame_inplace(self):
         self._ck(self._lib.ycge_frame_inplace(self.ctx))
+
+    def stash_config(self, n_slots: int):
+        self._ck(self._lib.ycge_stash_config(self.ctx, n_slots))
+
+    def frame_stash(self, slot: int):
+        self._ck(self._lib.ycge_frame_stash(self.ctx, slot))
+
+    def frame_finish_stashed(self, slot: int, cuda_stream: int):
+        self._ck(self._lib.ycge_frame_finish_stashed(self.ctx, slot, C.c_void_p(cuda_stream)))
+
+    def stash_logs_ptr(self, slot: int):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.ycge_stash_logs_ptr(self.ctx, slot, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def peer_export(self) -> Peer:
         p = Peer()

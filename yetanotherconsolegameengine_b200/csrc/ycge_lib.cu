@@ -116,9 +116,14 @@ struct ycge_ctx {
         int cur_id = 0, dst_id = 1, it = 0, K = 0, parity = 0, ty0 = 0, ty1 = 0;
         int halo_after[10] = {0};
         bool pending = false; // an in-place pass is prepared (pre-pass + sentinel done) and waits for ycge_frame_inplace
+        bool early_reset = false; // the sentinel fill + ready signal of iteration 1 were issued at the start of the frame
         int pa = 0, pb = 0;   // its row range
     } dn;
     EdgeDiv edge_div;      // max(1e-6, phi) and reciprocals (RaytraceRenderer.cs:694-697)
+    // frame pipelining across ranks (ycge_frame_stash / ycge_frame_finish_stashed): the tile's denoised rows and the
+    // exposure samples of a frame are parked so that the next frames can start before the all-reduce of this one
+    struct Stash { DevBuf<float4> den; DevBuf<float> logs; };
+    std::vector<std::unique_ptr<Stash>> stash;
     bool chain_timed = false;
     cudaStream_t aux = nullptr; // side stream: the peer-storing rows of the wavefront run as a concurrent kernel
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
@@ -331,6 +336,18 @@ int frame_begin_impl(ycge_ctx *c) {
 
     int launches = 0;
     CK(c, cudaEventRecord(c->ev[0], s));
+    c->dn.early_reset = false;
+    if (c->sharded && c->peers && K >= 2) {
+        // Peer hand-off: the output buffer of the first in-place iteration (it = 1: OLD = scratchA, NEW = scratchB) is free
+        // as soon as the previous frame's following pass has read it, i.e. now.  Resetting it and telling the rank above
+        // right away (instead of after this frame's trace / TAA / pass 0 / pre-pass) lets that rank, which runs ahead in
+        // the frame pipeline, finish its boundary rows without waiting for this rank's whole front end.
+        int a1, b1; range(halo_after[2], a1, b1);
+        const int m0 = c->has_above ? std::max(0, a1 - 4) : a1;
+        CK(c, cudaMemsetAsync(c->sb.p + (size_t)m0 * W, 0xFF, (size_t)(b1 - m0) * W * sizeof(float4), s));
+        if (c->has_above) { peer_signal_kernel<<<1, 1, 0, s>>>(c->above_flags, (int)frame); launches++; }
+        c->dn.early_reset = true;
+    }
     CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), s));
     { // K1
         int a, b; range(halo_after[0] + 1, a, b);
@@ -400,10 +417,12 @@ int denoise_run(ycge_ctx *c) {
                 // NEW starts as the sentinel on the rows this pass produces; the rows just above `a` (a sharded tile's
                 // upper boundary, produced by the previous rank) are delivered by the caller before ycge_frame_inplace
                 d.pa = a; d.pb = b;
-                int m0 = a;
-                if (c->peers && c->has_above) { int lo, aa, slo, sa_; halo_rows(c, lo, aa, slo, sa_); m0 = lo; } // the boundary rows arrive through the sentinel too
-                CK(c, cudaMemsetAsync(d.phys[Y] + (size_t)m0 * W, 0xFF, (size_t)(b - m0) * W * sizeof(float4), s));
-                if (c->peers && c->has_above) { peer_signal_kernel<<<1, 1, 0, s>>>(c->above_flags, (int)c->frame_counter); launches++; }
+                if (!(d.early_reset && it == 1)) {
+                    int m0 = a;
+                    if (c->peers && c->has_above) { int lo, aa, slo, sa_; halo_rows(c, lo, aa, slo, sa_); m0 = lo; } // the boundary rows arrive through the sentinel too
+                    CK(c, cudaMemsetAsync(d.phys[Y] + (size_t)m0 * W, 0xFF, (size_t)(b - m0) * W * sizeof(float4), s));
+                    if (c->peers && c->has_above) { peer_signal_kernel<<<1, 1, 0, s>>>(c->above_flags, (int)c->frame_counter); launches++; }
+                }
                 if (c->sharded) { d.pending = true; c->launches_last += launches; return 0; }
             }
             d.pending = false;
@@ -502,23 +521,28 @@ void halo_rows(const ycge_ctx *c, int &lo, int &a, int &slo, int &sa) {
     }
 }
 
-int frame_finish_impl(ycge_ctx *c) {
-    if (!c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish without ycge_frame_begin");
-    if (c->dn.it <= c->dn.K) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish while an in-place pass is pending (ycge_frame_halo / ycge_frame_inplace)");
-    cudaStream_t s = c->stream;
+int finish_launch(ycge_ctx *c, const float *logs, const float4 *den, cudaStream_t s, bool timed) {
     ExposureParams ep;
     ep.tone_exposure = c->P.tone_exposure; ep.ae_key = c->P.ae_key; ep.ae_speed = c->P.ae_speed; ep.ae_min = c->P.ae_min; ep.ae_max = c->P.ae_max;
     ep.auto_exposure = c->P.auto_exposure;
-    exposure_finish_kernel<<<1, 1024, 0, s>>>(c->logs.p, c->sw * c->sh, ep, c->expo.p);
-    CK(c, cudaEventRecord(c->ev[5], s));
+    exposure_finish_kernel<<<1, 1024, 0, s>>>(logs, c->sw * c->sh, ep, c->expo.p);
+    if (timed) CK(c, cudaEventRecord(c->ev[5], s));
     CellArgs ca;
-    ca.den = c->denoised; ca.expo = c->expo.p; ca.cells = c->cells.p; ca.W = c->W; ca.fbW = c->fbW; ca.ss = c->ss;
+    ca.den = den; ca.expo = c->expo.p; ca.cells = c->cells.p; ca.W = c->W; ca.fbW = c->fbW; ca.ss = c->ss;
     ca.cy0 = c->tile_row0; ca.cy1 = c->tile_row0 + c->tile_rows;
     ca.gamma = c->P.tone_gamma; ca.saturation = c->P.saturation; ca.vibrance = c->P.vibrance;
     for (int k = 0; k < 5; k++) ca.th[k] = c->ansi_th[k];
     cells_kernel<<<dim3(div_up(c->fbW, 128), c->tile_rows), 128, 0, s>>>(ca);
-    CK(c, cudaEventRecord(c->ev[6], s));
+    if (timed) CK(c, cudaEventRecord(c->ev[6], s));
     CK(c, cudaGetLastError());
+    return 0;
+}
+
+int frame_finish_impl(ycge_ctx *c) {
+    if (!c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish without ycge_frame_begin");
+    if (c->dn.it <= c->dn.K) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish while an in-place pass is pending (ycge_frame_halo / ycge_frame_inplace)");
+    int rc = finish_launch(c, c->logs.p, c->denoised, c->stream, true);
+    if (rc) return rc;
     c->launches_last += 2;
     // taa.CommitCamera (:266, TemporalAA.cs:69-76)
     memcpy(c->last_cam, c->snap_cam, sizeof c->last_cam); c->last_yaw = c->snap_yaw; c->last_pitch = c->snap_pitch;
@@ -940,6 +964,42 @@ YCGE_API int ycge_frame_halo(ycge_ctx *c, ycge_halo *h) {
     if (sa > slo) { h->send_ptr = nw + (size_t)slo * c->W; h->send_bytes = (size_t)(sa - slo) * row; h->send_row0 = slo; h->send_rows = sa - slo; }
     return 1;
 }
+YCGE_API int ycge_stash_config(ycge_ctx *c, int32_t n_slots) {
+    if (!c || n_slots < 0 || n_slots > 64) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stash.clear();
+    const size_t rows = (size_t)c->tile_rows * 2 * c->ss;
+    for (int k = 0; k < n_slots; k++) {
+        std::unique_ptr<ycge_ctx::Stash> st(new ycge_ctx::Stash());
+        CK(c, st->den.alloc(rows * c->W));
+        CK(c, st->logs.alloc((size_t)c->sw * c->sh));
+        c->stash.push_back(std::move(st));
+    }
+    return 0;
+}
+YCGE_API int ycge_frame_stash(ycge_ctx *c, int32_t slot) {
+    if (!c || slot < 0 || slot >= (int)c->stash.size()) return fail(c, YCGE_ERR_INVALID, "bad stash slot");
+    if (!c->frame_open || c->dn.it <= c->dn.K) return fail(c, YCGE_ERR_INVALID, "no finished frame to stash");
+    ycge_ctx::Stash &st = *c->stash[slot];
+    const size_t row0 = (size_t)c->tile_row0 * 2 * c->ss, rows = (size_t)c->tile_rows * 2 * c->ss;
+    CK(c, cudaMemcpyAsync(st.den.p, c->denoised + row0 * c->W, rows * c->W * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(st.logs.p, c->logs.p, st.logs.n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    memcpy(c->last_cam, c->snap_cam, sizeof c->last_cam); c->last_yaw = c->snap_yaw; c->last_pitch = c->snap_pitch; // taa.CommitCamera
+    c->frame_open = false;
+    return 0;
+}
+YCGE_API int ycge_frame_finish_stashed(ycge_ctx *c, int32_t slot, void *cuda_stream) {
+    if (!c || slot < 0 || slot >= (int)c->stash.size()) return fail(c, YCGE_ERR_INVALID, "bad stash slot");
+    ycge_ctx::Stash &st = *c->stash[slot];
+    const size_t row0 = (size_t)c->tile_row0 * 2 * c->ss;
+    return finish_launch(c, st.logs.p, st.den.p - row0 * c->W, (cudaStream_t)cuda_stream, false); // cells_kernel indexes rows absolutely
+}
+YCGE_API int ycge_stash_logs_ptr(ycge_ctx *c, int32_t slot, void **ptr, size_t *bytes) {
+    if (!c || !ptr || !bytes || slot < 0 || slot >= (int)c->stash.size()) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    *ptr = c->stash[slot]->logs.p; *bytes = c->stash[slot]->logs.n * sizeof(float);
+    return 0;
+}
 YCGE_API int ycge_peer_export(ycge_ctx *c, ycge_peer *out) {
     if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
@@ -1086,6 +1146,7 @@ YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
         float tot = 0.0f;
         if (cudaEventElapsedTime(&tot, c->ev[0], c->ev[6]) == cudaSuccess) out->ms_total = tot;
         if (c->chain_timed && cudaEventElapsedTime(&tot, c->ev[7], c->ev[8]) == cudaSuccess) out->ms_atrous_chain = tot;
+        (void)cudaGetLastError(); // an event that was never recorded (e.g. the finish events on the pipelined path) must not poison later checks
     }
     out->ae_exposure = es.ae_exposure; out->log_sum = es.log_sum; out->log_cnt = es.cnt;
     if (const char *path = getenv("YCGE_CHAIN_TRACE")) {

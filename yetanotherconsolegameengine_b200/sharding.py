@@ -84,6 +84,20 @@ class CudaTileBackend:
     def finish(self):
         self.r.frame_finish()
 
+    # -- frame pipelining: park a finished tile, finish it later on another stream
+    def stash_config(self, n_slots: int):
+        self.r.stash_config(n_slots)
+        self.slot_logs = []
+        for k in range(n_slots):
+            p, n = self.r.stash_logs_ptr(k)
+            self.slot_logs.append(device_bytes(p, n, self.device).view(torch.float32))
+
+    def stash(self, slot: int):
+        self.r.frame_stash(slot)
+
+    def finish_stashed(self, slot: int, stream: "torch.cuda.Stream"):
+        self.r.frame_finish_stashed(slot, stream.cuda_stream)
+
     def close(self):
         self.r.close()
 
@@ -138,6 +152,60 @@ class ShardedRenderer:
         self._pad[:n].copy_(b.cells[:n])
         dist.gather(self._pad, self._gather, dst=0, group=self.group)
         return self._gather
+
+    def render_pipelined(self, n_frames: int, collect: bool = False, set_camera=None):
+        """Asynchronous path, frames pipelined over the ranks (needs the peer hand-off).  The current stream renders
+        frame after frame (front end, wavefront part, stash); a side stream finishes frames in order: all-reduce of the
+        stashed exposure samples, ordered exposure sum + cells, gather on rank 0.  Rank g finishes frame h only after it
+        has rendered frame h + (world-1-g): the ranks run skewed by one frame each (rank 0 ahead), so that rank g's part
+        of the wavefront of frame f overlaps with rank g-1's part of frame f+1, and the k-th collective of every rank
+        still is the same frame at about the same time.  Returns the gathered tiles of every frame when `collect`."""
+        assert self.world == 1 or self.peer_handoff, "render_pipelined needs the peer hand-off"
+        dist, b = self.dist, self.b
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_comm"):
+            self._comm = torch.cuda.Stream()
+            self._slots = max(2, 2 * self.world)
+            b.stash_config(self._slots)
+            self._ev_stash = [torch.cuda.Event() for _ in range(self._slots)]
+            self._ev_fin = [torch.cuda.Event() for _ in range(self._slots)]
+        comm, S, D = self._comm, self._slots, self.world - 1 - self.rank
+        n_tile = self.tiles[self.rank][1] * self.fb_w * self.cell_bytes
+        out = []
+
+        def finish(h):
+            slot = h % S
+            with torch.cuda.stream(comm):
+                comm.wait_event(self._ev_stash[slot])
+                if self.world > 1:
+                    dist.all_reduce(b.slot_logs[slot], op=dist.ReduceOp.SUM, group=self.group)
+                b.finish_stashed(slot, comm)
+                if self.world > 1:
+                    self._pad[:n_tile].copy_(b.cells[:n_tile])
+                    dist.gather(self._pad, self._gather, dst=0, group=self.group)
+                    if collect and self.rank == 0:
+                        out.append([g.clone() for g in self._gather])
+                elif collect:
+                    out.append([b.cells.clone()])
+                self._ev_fin[slot].record(comm)
+
+        for f in range(n_frames):
+            slot = f % S
+            if f >= S:
+                main.wait_event(self._ev_fin[slot])  # the slot's previous frame has been finished
+            if set_camera is not None:
+                set_camera(f)
+            b.begin()
+            while b.halo() is not None:
+                b.inplace()
+            b.stash(slot)
+            self._ev_stash[slot].record(main)
+            if f >= D:
+                finish(f - D)
+        for h in range(max(0, n_frames - D), n_frames):
+            finish(h)
+        main.wait_stream(comm)
+        return out
 
     def assemble(self, gathered) -> np.ndarray:
         """Rank 0: the gathered tiles as one (fb_h, fb_w) cell array on the host."""
