@@ -228,12 +228,26 @@ def main():
         # one process per GPU: contiguous row tiles of cell rows, scene replicated, boundary rows of the in-place pass
         # handed rank -> rank+1, exposure samples all-reduced, cell tiles gathered on rank 0 (sharding.py)
         from yetanotherconsolegameengine_b200 import sharding
-        row0, rows = sharding.tile_rows(rank, n, fb_h)
+        tiles = [sharding.tile_rows(r, n, fb_h) for r in range(n)]
         with torch.cuda.stream(stream):
-            b = sharding.CudaTileBackend(scene, fb_w, fb_h, ss, row0, rows, local_rank)
-            sr = sharding.ShardedRenderer(b, rank, n, fb_w, fb_h, peers=not os.environ.get("YCGE_NO_PEERS"))
+            # untimed set-up: four rounds of load balancing.  The trace cost of a row is very uneven (sky vs mesh), so equal
+            # tiles leave most ranks waiting for the one that holds the mesh; tiles are re-cut from the measured trace times.
+            for balance_round in range(5):
+                row0, rows = tiles[rank]
+                b = sharding.CudaTileBackend(scene, fb_w, fb_h, ss, row0, rows, local_rank)
+                sr = sharding.ShardedRenderer(b, rank, n, fb_w, fb_h, peers=not os.environ.get("YCGE_NO_PEERS"), tiles=tiles)
+                sr.SetCamera(*pose)
+                if balance_round == 4 or os.environ.get("YCGE_NO_BALANCE"):
+                    break
+                for _ in range(3):
+                    sr.render_device()
+                torch.cuda.synchronize()
+                tr = [None] * n
+                dist.all_gather_object(tr, float(b.r.stats()["ms_trace"]))
+                tiles = sharding.balanced_tiles(tiles, tr, fb_h, min_rows=max(1, -(-4 // (2 * ss))))
+                sr.close()
+                del sr, b
             peer_handoff = sr.peer_handoff
-            sr.SetCamera(*pose)
             # the event counters of the whole frame come from an unsharded frame on rank 0's GPU (untimed)
             st_events = None
             if rank == 0:
@@ -299,7 +313,7 @@ def main():
         dist.broadcast(rays_frame, 0)
         rays_timed = int(rays_frame[0]) * args.steps
         e2e_rays = int(rays_frame[0]) * args.steps
-        b.close()
+        sr.close()
     fps = args.steps / (ms / 1e3)
     mrays = rays_timed / (ms / 1e3) / 1e6
     e2e_mrays = e2e_rays / e2e_s / 1e6
@@ -317,7 +331,7 @@ def main():
         return 0
     b_trav, b_trace, b_frame = algorithmic_bytes(st_events, W, H, fb_w, fb_h, ss)
     # the dominant single kernel: the trace megakernel or the wavefront kernel of the in-place à-trous pass
-    rows_here = H if n == 1 else min(H, (sharding.tile_rows(0, n, fb_h)[1]) * 2 * ss + 16)
+    rows_here = H if n == 1 else min(H, tiles[0][1] * 2 * ss + 16)
     if stage_ms["ms_trace"] >= stage_ms["ms_atrous_chain"]:
         kname, kbytes, kms = "trace_kernel", b_trace * rows_here // H, stage_ms["ms_trace"]
     else:
@@ -353,7 +367,7 @@ def main():
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
                 "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ("" if n == 1 else (", peer hand-off" if peer_handoff else ", NCCL send/recv hand-off") + (", frames pipelined over ranks (value); lock-step (e2e)" if pipelined else "")),
                            "l2": "per-frame working set (8 float4 image planes = %d MB) exceeds the 126 MB L2; no explicit flush" % (W * H * 128 // (1 << 20))},
-                "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff, "frame_pipelining": pipelined} if n > 1 else {}),
+                "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff, "frame_pipelining": pipelined, "tiles_cell_rows": [t[1] for t in tiles]} if n > 1 else {}),
                 "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_frame * args.steps * n,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}

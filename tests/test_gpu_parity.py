@@ -392,3 +392,24 @@ def test_row_tiles_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pos
     for t in tiles:
         t.close()
     full.close()
+
+
+def test_stashed_finish_equals_the_synchronous_frame():
+    """The frame-pipelining path on one GPU (world = 1): frames are rendered back to back on one stream and finished from
+    their stash slots on a side stream (ordered exposure sum + cells), out of step with the rendering.  Same cells."""
+    import torch
+    from yetanotherconsolegameengine_b200 import sharding
+    s = api.HostScene("boxes")
+    ref = api.CudaRaytraceRenderer(s, 40, 24, 2)
+    with torch.cuda.device(0):
+        b = sharding.CudaTileBackend(s, 40, 24, 2, 0, 24, 0)
+        sr = sharding.ShardedRenderer(b, 0, 1, 40, 24)
+        got = sr.render_pipelined(7, collect=True)
+        torch.cuda.synchronize()
+        assert len(got) == 7
+        for f, g in enumerate(got):
+            assert_cells_equal(sr.assemble(g), ref.TryFlipAndBlit(), f"pipelined frame {f + 1}")
+        # and the two paths can be mixed: a synchronous frame after pipelined ones continues the same sequence
+        assert_cells_equal(sr.TryFlipAndBlit(), ref.TryFlipAndBlit(), "synchronous frame after pipelined frames")
+    b.close()
+    ref.close()

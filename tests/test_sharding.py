@@ -26,6 +26,26 @@ def test_tile_partition_covers_every_cell_row_once():
             assert max(sizes) - min(sizes) <= 1 and sum(sizes) == fb_h
 
 
+def test_balanced_tiles_equalise_the_modelled_cost():
+    fb_h, world = 135, 8
+    tiles = [sharding.tile_rows(r, world, fb_h) for r in range(world)]
+    trace = [0.03, 0.04, 0.66, 0.82, 0.56, 0.47, 0.45, 0.37]  # measured on 8 B200s (dragon, bench pose): sky on top, mesh in the middle
+    new = sharding.balanced_tiles(tiles, trace, fb_h)
+    assert new[0][0] == 0 and new[-1][0] + new[-1][1] == fb_h and all(n > 0 for _, n in new)
+    for (a0, an), (b0, _) in zip(new, new[1:]):
+        assert a0 + an == b0
+    assert new[0][1] > tiles[0][1] and new[3][1] < tiles[3][1]  # cheap sky tiles grow, the expensive mesh tile shrinks
+    # modelled cost per rank is within one row's cost of the mean
+    cost = np.zeros(fb_h)
+    for (r0, n), t in zip(tiles, trace):
+        cost[r0:r0 + n] = t / n + 0.019
+    per_rank = [cost[r0:r0 + n].sum() for r0, n in new]
+    assert max(per_rank) - min(per_rank) <= 2 * cost.max() + 1e-9
+    # degenerate input keeps a valid partition
+    flat = sharding.balanced_tiles(tiles, [0.0] * world, fb_h)
+    assert sum(n for _, n in flat) == fb_h and all(n > 0 for _, n in flat)
+
+
 class FakeTileBackend:
     """TileBackend made of the CPU oracle: full frame per rank, tile slices exposed as torch CPU tensors."""
 

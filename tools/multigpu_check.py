@@ -45,5 +45,6 @@ if sr.peer_handoff or world == 1:
             print(f"frame {frames + f + 1}: pipelined x{world} {'==' if same else '!='} unsharded", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
+sr.close()
 dist.destroy_process_group()
 sys.exit(0 if int(flag[0]) else 1)

@@ -31,6 +31,26 @@ def tile_rows(rank: int, world: int, fb_h: int) -> Tuple[int, int]:
     return row0, row1 - row0
 
 
+def balanced_tiles(tiles: List[Tuple[int, int]], trace_ms: List[float], fb_h: int, per_row_ms: float = 0.019, min_rows: int = 1) -> List[Tuple[int, int]]:
+    """Re-cut the row tiles so that every rank gets the same modelled cost.  The trace cost of a cell row is very uneven
+    (sky rows end after one ray, mesh rows trace six), everything else is proportional to the number of rows
+    (`per_row_ms`: à-trous passes + the wavefront's lag per row).  Density model: the measured trace time of a tile,
+    spread evenly over its rows.  Tiles stay contiguous (the wavefront hands rows from rank to rank)."""
+    world = len(tiles)
+    cost = np.zeros(fb_h)
+    for (row0, rows), t in zip(tiles, trace_ms):
+        cost[row0:row0 + rows] = max(t, 0.0) / max(rows, 1) + per_row_ms
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    edges = [0]
+    for g in range(1, world):
+        target = cum[-1] * g / world
+        e = int(np.searchsorted(cum, target))
+        e = min(max(e, edges[-1] + min_rows), fb_h - (world - g) * min_rows)
+        edges.append(e)
+    edges.append(fb_h)
+    return [(edges[g], edges[g + 1] - edges[g]) for g in range(world)]
+
+
 class _DevMem:
     """A raw device range exposed through __cuda_array_interface__ so that torch can alias it (no copy)."""
 
@@ -105,11 +125,11 @@ class CudaTileBackend:
 class ShardedRenderer:
     """IConsoleRenderer over N ranks: SetCamera + TryFlipAndBlit, the assembled frame lands on rank 0."""
 
-    def __init__(self, backend, rank: int, world: int, fb_w: int, fb_h: int, group=None, peers: bool = True):
+    def __init__(self, backend, rank: int, world: int, fb_w: int, fb_h: int, group=None, peers: bool = True, tiles=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.b, self.rank, self.world, self.fb_w, self.fb_h = backend, rank, world, fb_w, fb_h
-        self.tiles = [tile_rows(r, world, fb_h) for r in range(world)]
+        self.tiles = list(tiles) if tiles is not None else [tile_rows(r, world, fb_h) for r in range(world)]
         self.max_rows = max(t[1] for t in self.tiles)
         self.cell_bytes = api.CELL_DTYPE.itemsize
         dev = backend.cells.device
@@ -206,6 +226,16 @@ class ShardedRenderer:
             finish(h)
         main.wait_stream(comm)
         return out
+
+    def close(self):
+        """Unmap the neighbours' buffers on every rank BEFORE any rank frees them, then release the tile."""
+        if self.peer_handoff:
+            self.b.peer_attach(None, None, via_ipc=False)
+            self.peer_handoff = False
+        if self.world > 1:
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+        self.b.close()
 
     def assemble(self, gathered) -> np.ndarray:
         """Rank 0: the gathered tiles as one (fb_h, fb_w) cell array on the host."""
