@@ -146,6 +146,13 @@ __device__ __forceinline__ bool box_mesh(float mnx, float mny, float mnz, float 
 }
 
 // ------------------------------------------------------------------------------------------------ MeshBVH.Hit (MeshBVH.cs:132-304)
+// Measured and dropped (B200, dragon 1080p, trace 1.18 ms): (1) parking a leaf while the lane keeps walking inner nodes
+// until its next entry is a leaf too ("postponed leaves": same leaf order, same hits — every entry is re-tested against
+// the current `closest` when popped — verified bit-exact), with and without warp votes to enter the triangle loop
+// together: 1.30 / 1.33 ms; (2) scene_hit as one __noinline__ copy instead of three inlined ones (halves the code):
+// 1.20 ms; (3) 16..40 resident warps per SM via launch bounds: no change.  The triangle loop runs with 2-3 of 32 lanes
+// active and 21 % of the stall samples are instruction-fetch misses, but the kernel is bound by the dependent node /
+// triangle fetch latency of the longest paths in each warp, not by those.
 template <bool STATS>
 __device__ bool mesh_hit(const DevMesh &mesh, const RayD &r, float tMin, float tMax, Stack &st, int sp0, Cnt<STATS> &cnt,
                          float &tOut, int &slotOut) {
