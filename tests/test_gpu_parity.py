@@ -413,3 +413,65 @@ def test_stashed_finish_equals_the_synchronous_frame():
         assert_cells_equal(sr.TryFlipAndBlit(), ref.TryFlipAndBlit(), "synchronous frame after pipelined frames")
     b.close()
     ref.close()
+
+
+def test_taa_accumulation_over_64_frames_vs_oracle():
+    """BASELINE config 3: a mesh scene with a static camera over 64 frames — the TAA history (alpha = 0.01) and the exposure
+    recursion accumulate frame after frame; the 64th frame must still be bit-identical to the oracle's 64th frame."""
+    s = api.HostScene("teapot")
+    r = api.CudaRaytraceRenderer(s, 40, 12, 2)
+    o = Oracle(s, 40, 12, 2)
+    r.SetCamera(*api.BENCH_POSE)
+    o.set_camera(*api.BENCH_POSE)
+    for f in range(64):
+        g = r.TryFlipAndBlit()
+        c = o.render_frame(threads=os.cpu_count() or 1, fast_post=True)
+        if f in (0, 1, 15, 63):
+            assert_cells_equal(g, c, f"teapot frame {f + 1}")
+            assert_frame_parity(r, o, f"teapot frame {f + 1}")
+    assert r.stats()["frames"] == o.stats()["frames"] == 64
+    r.close()
+    o.close()
+
+
+def test_4k_internal_resolution_multi_launch_wavefront():
+    """BASELINE config 5 resolution (3840x2160 internal = 480x135 cells, ss = 8).  Too slow for the CPU oracle inside a
+    test; at this size the wavefront kernel does not fit the GPU in one co-resident launch, so the rows go out in several
+    launches.  Properties: two row tiles (loop-back hand-off, each tile fits one launch) assemble to exactly the unsharded
+    frame (computed by the multi-launch path), two frames (the second one blends history), deterministic across contexts."""
+    import torch
+    from yetanotherconsolegameengine_b200 import sharding
+    s = api.HostScene("knot:200x40")
+    fb_w, fb_h, ss = 480, 135, 8
+    full = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    full.SetCamera(*api.BENCH_POSE)
+    with torch.cuda.device(0):
+        tiles = []
+        for k in range(2):
+            row0, rows = sharding.tile_rows(k, 2, fb_h)
+            t = sharding.CudaTileBackend(s, fb_w, fb_h, ss, row0, rows, 0)
+            t.set_camera(*api.BENCH_POSE)
+            tiles.append(t)
+        for frame in range(2):
+            ref = full.TryFlipAndBlit()
+            assert ref["fg_ansi"].min() >= 16 and np.all(ref["glyph"] == 0x2580)
+            for t in tiles:
+                t.begin()
+            prev = None
+            halos = [t.halo() for t in tiles]
+            for t, (recv, send) in zip(tiles, halos):
+                if recv is not None:
+                    recv.copy_(prev)
+                t.inplace()
+                prev = send
+            assert all(t.halo() is None for t in tiles)
+            total = torch.stack([t.logs for t in tiles]).sum(0)
+            for t in tiles:
+                t.logs.copy_(total)
+                t.finish()
+            torch.cuda.synchronize()
+            got = np.concatenate([t.cells.cpu().numpy().view(api.CELL_DTYPE).reshape(t.rows, fb_w) for t in tiles])
+            assert_cells_equal(got, ref, f"4K frame {frame + 1}")
+    for t in tiles:
+        t.close()
+    full.close()
