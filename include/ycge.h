@@ -307,6 +307,11 @@ YCGE_API int ycge_frame_begin(ycge_ctx *ctx);
 YCGE_API int ycge_frame_halo(ycge_ctx *ctx, ycge_halo *out);  /* 1: an in-place pass is pending, 0: none (negative: error) */
 YCGE_API int ycge_frame_inplace(ycge_ctx *ctx);
 YCGE_API int ycge_frame_finish(ycge_ctx *ctx);
+/* ANSITerminalRenderer.Render's byte stream (ANSITerminalRenderer.cs:86-153: cursor address per row, colour escapes only
+ * where the 8-bit indices change, UTF-8 glyphs, final reset) for the cells of the last frame, produced on the device and
+ * copied to `out` (at most `cap` bytes; *n_bytes receives the length).  The resize prologue ("ESC[2J ESC[H", :103-106)
+ * is the host's.  For a row-tile ctx the stream covers the tile's rows and starts with unknown colour state. */
+YCGE_API int ycge_ansi_emit(ycge_ctx *ctx, uint8_t *out, size_t cap, size_t *n_bytes);
 typedef enum ycge_ptr_kind { YCGE_PTR_CELLS = 0, YCGE_PTR_LOG_SAMPLES = 1 } ycge_ptr_kind;
 YCGE_API int ycge_device_ptr(ycge_ctx *ctx, int32_t kind, void **ptr, size_t *bytes);
 YCGE_API int ycge_set_stream(ycge_ctx *ctx, void *cuda_stream); /* run on the caller's stream (e.g. torch's current stream) */

@@ -475,3 +475,18 @@ def test_4k_internal_resolution_multi_launch_wavefront():
     for t in tiles:
         t.close()
     full.close()
+
+
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss", [("cornell", 61, 17, 1), ("mirror_spheres", 240, 67, 2), ("voxel_world:64x64", 33, 40, 1), ("boxes", 1, 1, 1)])
+def test_ansi_stream_emitted_on_the_device(scene, fb_w, fb_h, ss):
+    """ANSITerminalRenderer.Render's byte stream produced by a kernel (row prefix, colour-change escapes,
+    UTF-8 glyph, final reset) equals the host mirror's Render over the same cells, byte for byte, frame after frame."""
+    s = api.HostScene(scene)
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    for _ in range(3):
+        cells = r.TryFlipAndBlit()
+        dev = r.ansi_stream()
+        host = api.ansi_from_cells(cells)
+        assert dev == host, (len(dev), len(host))
+    assert dev.startswith(b"\x1b[1;1H") and dev.endswith(b"\x1b[0m")
+    r.close()

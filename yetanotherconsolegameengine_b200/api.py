@@ -120,7 +120,7 @@ ABI_SYMBOLS = [
     "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
     "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
     "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
-    "ycge_frame_finish", "ycge_device_ptr",
+    "ycge_frame_finish", "ycge_ansi_emit", "ycge_device_ptr",
     "ycge_set_stream", "ycge_debug_read", "ycge_get_stats", "ycge_get_frame_counter", "ycge_rng_kat",
 ]
 
@@ -170,6 +170,7 @@ def load_lib() -> C.CDLL:
         lib.ycge_peer_attach.argtypes = [vp, C.POINTER(Peer), C.POINTER(Peer), C.c_int32]
         lib.ycge_frame_inplace.argtypes = [vp]
         lib.ycge_device_ptr.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        lib.ycge_ansi_emit.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.ycge_set_stream.argtypes = [vp, vp]
         lib.ycge_debug_read.argtypes = [vp, C.c_int32, vp, C.c_size_t]
         lib.ycge_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -447,6 +448,14 @@ class CudaRaytraceRenderer:
 
     def frame_inplace(self):
         self._ck(self._lib.ycge_frame_inplace(self.ctx))
+
+    def ansi_stream(self) -> bytes:
+        """ANSITerminalRenderer.Render's byte stream for the last frame, produced on the device (ycge_ansi_emit)."""
+        cap = 64 + self.tile_rows * 16 + self.tile_rows * self.fb_w * 24
+        buf = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        self._ck(self._lib.ycge_ansi_emit(self.ctx, _ptr(buf), cap, C.byref(n)))
+        return buf[:n.value].tobytes()
 
     def stash_config(self, n_slots: int):
         self._ck(self._lib.ycge_stash_config(self.ctx, n_slots))

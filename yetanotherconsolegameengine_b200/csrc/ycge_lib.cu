@@ -73,6 +73,8 @@ struct ycge_ctx {
     // image planes
     DevBuf<float4> cur, gnd0, gnd1, gas0, gas1, hist, sa, sb;
     DevBuf<unsigned long long> chain_trace;
+    DevBuf<unsigned char> ansi;       // device ANSI byte stream (ycge_ansi_emit)
+    DevBuf<unsigned int> ansi_rows;   // [rows] lengths, [rows] offsets, [1] total
     DevBuf<float4> pre; // in-place à-trous pass: 25 planes of per-tap precomputed terms / guide weights
     DevBuf<int2> prim;
     DevBuf<float> rays_dbg;
@@ -1084,6 +1086,30 @@ YCGE_API int ycge_wait(ycge_ctx *c) {
 YCGE_API int ycge_read_cells(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     return read_cells_impl(c, out, stride_cells);
+}
+YCGE_API int ycge_ansi_emit(ycge_ctx *c, uint8_t *out, size_t cap, size_t *n_bytes) {
+    if (!c || !out || !n_bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if (c->frame_counter == 0) return fail(c, YCGE_ERR_INVALID, "no frame rendered yet");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int rows = c->tile_rows, fbW = c->fbW;
+    const size_t worst = 64 + (size_t)rows * 16 + (size_t)rows * fbW * 24; // 21 bytes of escape + 3 of glyph per cell at most
+    if (c->ansi.n < worst) CK(c, c->ansi.alloc(worst));
+    if (c->ansi_rows.n < (size_t)2 * rows + 1) CK(c, c->ansi_rows.alloc((size_t)2 * rows + 1));
+    unsigned int *len = c->ansi_rows.p, *off = len + rows, *total = off + rows;
+    const int wpb = 8;
+    ansi_rows_kernel<false><<<div_up(rows, wpb), wpb * 32, 0, s>>>(c->cells.p, fbW, rows, c->tile_row0, len, nullptr, nullptr);
+    ansi_scan_kernel<<<1, 1024, 0, s>>>(len, off, rows, c->ansi.p, total);
+    ansi_rows_kernel<true><<<div_up(rows, wpb), wpb * 32, 0, s>>>(c->cells.p, fbW, rows, c->tile_row0, nullptr, off, c->ansi.p);
+    CK(c, cudaGetLastError());
+    unsigned int n = 0;
+    CK(c, cudaMemcpyAsync(&n, total, sizeof n, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    *n_bytes = n;
+    if (n > cap) return fail(c, YCGE_ERR_LIMIT, "ANSI stream larger than the caller's buffer");
+    CK(c, cudaMemcpyAsync(out, c->ansi.p, n, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
 }
 YCGE_API int ycge_device_ptr(ycge_ctx *c, int32_t kind, void **ptr, size_t *bytes) {
     if (!c || !ptr || !bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
