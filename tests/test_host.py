@@ -114,3 +114,36 @@ def test_ansi_byte_stream():
     got = api.ansi_from_cells(cells)
     assert got == ansi_render_py(cells)
     assert got.endswith(b"\x1b[0m") and got.startswith(b"\x1b[1;1H")
+
+
+def test_vg01_world_file_round_trip(tmp_path):
+    """the 'VG01' world file (WorldManager.cs:399-440 reader, :612-629 writer).  A file written in the
+    writer's layout loads into the same chunk VolumeGrids, top-level tree and camera as the in-memory builder."""
+    path = str(tmp_path / "world.vg01")
+    assert api.load_host().ycgeh_write_synthetic_world(path.encode(), 64, 64) == 0
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"VG01" and np.frombuffer(raw[4:16], np.int32).tolist() == [64, 64, 64]
+    assert len(raw) == 16 + 64 * 64 * 64 * 8
+    a = api.HostScene("voxel_world:64x64")
+    b = api.HostScene("voxel_world_file:" + path)
+    assert a.n_volumes == b.n_volumes and a.n_volumes > 0
+    for i in range(a.n_volumes):
+        va, vb = a.volume(i).contents, b.volume(i).contents
+        assert (va.nx, va.ny, va.nz) == (vb.nx, vb.ny, vb.nz) and list(va.min_corner) == list(vb.min_corner)
+        n = ((va.nx + 7) // 8) * ((va.ny + 7) // 8) * ((va.nz + 7) // 8) * 512
+        assert np.array_equal(np.ctypeslib.as_array(va.mat, (n,)), np.ctypeslib.as_array(vb.mat, (n,)))
+        assert np.array_equal(np.ctypeslib.as_array(va.meta, (n,)), np.ctypeslib.as_array(vb.meta, (n,)))
+    ta, tb = a.bvh_arrays(-1), b.bvh_arrays(-1)
+    for k in ("boxes", "lrsc", "leaf"):
+        assert np.array_equal(ta[k], tb[k])
+    a.close(); b.close()
+    # the reader's errors (WorldManager.cs:403-417)
+    bad = str(tmp_path / "bad.vg01")
+    open(bad, "wb").write(b"VG02" + raw[4:])
+    with pytest.raises(Exception, match="VG01"):
+        api.HostScene("voxel_world_file:" + bad)
+    open(bad, "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(Exception, match="[Tt]runcated"):
+        api.HostScene("voxel_world_file:" + bad)
+    with pytest.raises(Exception, match="not found"):
+        api.HostScene("voxel_world_file:" + str(tmp_path / "missing.vg01"))

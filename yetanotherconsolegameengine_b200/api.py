@@ -230,6 +230,7 @@ def load_host() -> C.CDLL:
         h.ycgeh_ansi_from_cells.restype = C.c_int64
         h.ycgeh_synthetic_height.argtypes = [C.c_int, C.c_int, C.c_int]
         h.ycgeh_synthetic_height.restype = C.c_float
+        h.ycgeh_write_synthetic_world.argtypes = [C.c_char_p, C.c_int, C.c_int]
         _host = h
     return _host
 

@@ -650,34 +650,26 @@ static std::shared_ptr<VoxelPalette> WorldPalette() { // Scenes/VoxelMaterialPal
     pal->def = 8; // Normalize(default) -> (Stone, 0) -> PalMat(8)
     return pal;
 }
-std::shared_ptr<Scene> BuildSyntheticWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds) {
-    auto s = std::make_shared<Scene>(); s->Name = "voxel_world_synthetic"; s->IsVolumeScene = true;
+// A voxel world as BuildMinecraftLike assembles it (VolumeScenes.cs:569-627, WorldManager.cs:712-760): 32^3 chunks as
+// separate VolumeGrids in the top-level BVH, all-air chunks skipped (`cell.Item1 != 0`, WorldManager.cs:720), the real
+// palette, sun/moon lights of DayNightEntity at `daySeconds`.  `cellAt(wx, wy, wz, mat, meta)` supplies the voxels.
+template <class CellAt>
+static std::shared_ptr<Scene> BuildWorldFromCells(int nx, int ny, int nz, int chunkSize, float daySeconds, const std::string &name, CellAt cellAt) {
+    auto s = std::make_shared<Scene>(); s->Name = name; s->IsVolumeScene = true;
     s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.0f);
     auto pal = WorldPalette();
-    const int seaLevel = worldHeight / 4 + 2;
-    int chunksX = worldSize / chunkSize, chunksY = worldHeight / chunkSize, chunksZ = worldSize / chunkSize;
-    Vec3 worldMin((float)(-worldSize / 2), 0.0f, (float)(-worldSize / 2)); // VolumeScenes.cs:588
-    std::vector<int> hmap((size_t)worldSize * worldSize);
-    for (int z = 0; z < worldSize; z++) for (int x = 0; x < worldSize; x++) hmap[(size_t)z * worldSize + x] = (int)SyntheticHeight(x, z, worldHeight);
+    int chunksX = nx / chunkSize, chunksY = ny / chunkSize, chunksZ = nz / chunkSize;
+    Vec3 worldMin((float)(-nx / 2), 0.0f, (float)(-nz / 2)); // VolumeScenes.cs:588
     for (int cz = 0; cz < chunksZ; cz++) for (int cy = 0; cy < chunksY; cy++) for (int cx = 0; cx < chunksX; cx++) {
         int baseX = cx * chunkSize, baseY = cy * chunkSize, baseZ = cz * chunkSize;
-        auto cell = [&](int ix, int iy, int iz, int &m, int &e) {
-            int wx = baseX + ix, wy = baseY + iy, wz = baseZ + iz;
-            int h = hmap[(size_t)wz * worldSize + wx];
-            e = 0;
-            if (wy > h) { m = (wy <= seaLevel) ? 4 : 0; return; }              // water fills up to sea level
-            if (wy == h) { m = h <= seaLevel + 1 ? 5 : (h > (int)(0.40f * worldHeight) ? 8 : 3); return; } // sand / snow / grass
-            if (wy >= h - 3) { m = 2; return; }                                // dirt
-            m = 1; e = (int)(hash2(wx * 7 + wy, wz * 13 - wy) % 3u);          // stone, strata meta 0..2
-        };
-        // all-air chunks are skipped (WorldManager.cs:720,759)
+        auto cell = [&](int ix, int iy, int iz, int &m, int &e) { cellAt(baseX + ix, baseY + iy, baseZ + iz, m, e); };
         bool any = false;
-        for (int iz = 0; iz < chunkSize && !any; iz++) for (int ix = 0; ix < chunkSize && !any; ix++) {
-            int h = std::max(hmap[(size_t)(baseZ + iz) * worldSize + baseX + ix], seaLevel);
-            if (h >= baseY) any = true;
+        for (int iz = 0; iz < chunkSize && !any; iz++) for (int iy = 0; iy < chunkSize && !any; iy++) for (int ix = 0; ix < chunkSize && !any; ix++) {
+            int m, e; cell(ix, iy, iz, m, e);
+            if (m != 0) any = true;
         }
         if (!any) continue;
-        Vec3 minCorner(worldMin.X + baseX * 1.0f, worldMin.Y + baseY * 1.0f, worldMin.Z + baseZ * 1.0f); // WorldManager.cs:764-768
+        Vec3 minCorner(worldMin.X + baseX * 1.0f, worldMin.Y + baseY * 1.0f, worldMin.Z + baseZ * 1.0f); // WorldManager.cs:724-728
         s->Add(std::make_shared<VolumeGrid>(chunkSize, chunkSize, chunkSize, cell, minCorner, Vec3(1.0f, 1.0f, 1.0f), pal));
     }
     // DayNightEntity.Update at time = daySeconds (Scenes/DayNightCycle.cs:41-91), cycle 120 s, radius 2000
@@ -699,12 +691,65 @@ std::shared_ptr<Scene> BuildSyntheticWorld(int worldSize, int worldHeight, int c
         s->BackgroundTop = lerp(Vec3(0.02, 0.03, 0.06), Vec3(0.30, 0.55, 0.95), skyBlend);
         s->BackgroundBottom = lerp(Vec3(0.00, 0.00, 0.00), Vec3(0.80, 0.90, 1.00), skyBlend);
     }
-    int hc = hmap[(size_t)(worldSize / 2) * worldSize + worldSize / 2];
-    s->DefaultCameraPos = Vec3(0.0f, (float)std::max(hc, seaLevel) + 1.0f + 1.8f, 0.0f);
+    // camera: standing on the highest non-air voxel of the centre column
+    int top = 0;
+    for (int wy = ny - 1; wy >= 0; wy--) { int m, e; cellAt(nx / 2, wy, nz / 2, m, e); if (m != 0) { top = wy; break; } }
+    s->DefaultCameraPos = Vec3(0.0f, (float)top + 1.0f + 1.8f, 0.0f);
     s->DefaultYaw = 0.6f; s->DefaultPitch = -0.25f;
     s->ResetCamera();
     s->RebuildBVH();
     return s;
+}
+// the synthetic stand-in for the (un-runnable) island generator: heightfield + strata, SURVEY 8(d) config C4
+static void SyntheticCell(const std::vector<int> &hmap, int worldSize, int worldHeight, int wx, int wy, int wz, int &m, int &e) {
+    const int seaLevel = worldHeight / 4 + 2;
+    int h = hmap[(size_t)wz * worldSize + wx];
+    e = 0;
+    if (wy > h) { m = (wy <= seaLevel) ? 4 : 0; return; }              // water fills up to sea level
+    if (wy == h) { m = h <= seaLevel + 1 ? 5 : (h > (int)(0.40f * worldHeight) ? 8 : 3); return; } // sand / snow / grass
+    if (wy >= h - 3) { m = 2; return; }                                // dirt
+    m = 1; e = (int)(hash2(wx * 7 + wy, wz * 13 - wy) % 3u);          // stone, strata meta 0..2
+}
+static std::vector<int> SyntheticHeights(int worldSize, int worldHeight) {
+    std::vector<int> hmap((size_t)worldSize * worldSize);
+    for (int z = 0; z < worldSize; z++) for (int x = 0; x < worldSize; x++) hmap[(size_t)z * worldSize + x] = (int)SyntheticHeight(x, z, worldHeight);
+    return hmap;
+}
+std::shared_ptr<Scene> BuildSyntheticWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds) {
+    std::vector<int> hmap = SyntheticHeights(worldSize, worldHeight);
+    return BuildWorldFromCells(worldSize, worldHeight, worldSize, chunkSize, daySeconds, "voxel_world_synthetic",
+                               [&](int wx, int wy, int wz, int &m, int &e) { SyntheticCell(hmap, worldSize, worldHeight, wx, wy, wz, m, e); });
+}
+// World file "VG01" (WorldManager.cs:399-440 reader, :612-629 writer): 'V','G','0','1', int32 nx, ny, nz, then
+// (int32 mat, int32 meta) per voxel with x outermost, then y, z innermost.
+std::shared_ptr<Scene> BuildWorldFromFile(const std::string &path, int chunkSize, float daySeconds) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f.good()) throw std::runtime_error("World file not found: " + path);
+    char magic[4]; int32_t dims[3];
+    f.read(magic, 4); f.read((char *)dims, 12);
+    if (!f.good() || memcmp(magic, "VG01", 4) != 0) throw std::runtime_error("Unsupported world file header. Expected 'VG01'.");
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+    if (nx <= 0 || ny <= 0 || nz <= 0) throw std::runtime_error("Invalid world dimensions.");
+    if (nx % chunkSize || ny % chunkSize || nz % chunkSize) throw std::runtime_error("World dimensions must be multiples of the chunk size.");
+    std::vector<int32_t> cells((size_t)nx * ny * nz * 2);
+    f.read((char *)cells.data(), (std::streamsize)(cells.size() * 4));
+    if (!f.good()) throw std::runtime_error("Truncated world file: " + path);
+    return BuildWorldFromCells(nx, ny, nz, chunkSize, daySeconds, "voxel_world_file", [&](int wx, int wy, int wz, int &m, int &e) {
+        const size_t k = (((size_t)wx * ny + wy) * nz + wz) * 2;
+        m = cells[k]; e = cells[k + 1];
+    });
+}
+void WriteSyntheticWorldFile(const std::string &path, int worldSize, int worldHeight) { // the writer's layout, WorldManager.cs:612-629
+    std::vector<int> hmap = SyntheticHeights(worldSize, worldHeight);
+    std::ofstream o(path, std::ios::binary);
+    int32_t dims[3] = {worldSize, worldHeight, worldSize};
+    o.write("VG01", 4); o.write((const char *)dims, 12);
+    std::vector<int32_t> col((size_t)worldSize * 2);
+    for (int x = 0; x < worldSize; x++) for (int y = 0; y < worldHeight; y++) {
+        for (int z = 0; z < worldSize; z++) { int m, e; SyntheticCell(hmap, worldSize, worldHeight, x, y, z, m, e); col[2 * z] = m; col[2 * z + 1] = e; }
+        o.write((const char *)col.data(), (std::streamsize)(col.size() * 4));
+    }
+    if (!o.good()) throw std::runtime_error("cannot write " + path);
 }
 } // namespace VolumeScenes
 
@@ -730,6 +775,7 @@ std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
         return VolumeScenes::BuildSyntheticWorld(ws, wh, 32, 45.0f);
     }
     if (name == "voxel_world") return VolumeScenes::BuildSyntheticWorld(1024, 256, 32, 45.0f);
+    if (name.rfind("voxel_world_file:", 0) == 0) return VolumeScenes::BuildWorldFromFile(name.substr(17), 32, 45.0f); // a VG01 world file
     throw std::invalid_argument("unknown scene: " + name);
 }
 
@@ -961,6 +1007,9 @@ YH_API int ycgeh_obj_to_ymesh(const char *obj_path, const char *out_path) { // f
         o.write((const char *)d.faces.data(), (std::streamsize)((size_t)nf * 4));
         return o.good() ? 0 : -1;
     } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_write_synthetic_world(const char *path, int world_size, int world_height) { // a VG01 file of the synthetic world (tests)
+    try { VolumeScenes::WriteSyntheticWorldFile(path, world_size, world_height); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
 YH_API void ycgeh_scene_destroy(void *h) { delete (SceneHandle *)h; }
 YH_API const ycge_scene *ycgeh_scene_flat(void *h) { return &((SceneHandle *)h)->flat->scene; }
