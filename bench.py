@@ -206,11 +206,49 @@ def main():
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         st1 = r.stats()
-        clocks = sampler.stop()
-        rays_timed = st1["rays_total"] - st0["rays_total"]
-        # per-stage device times of a steady-state frame (events recorded by the library on the same stream)
+        serial = {"ms_per_step": ms / args.steps, "frames_per_s": args.steps / (ms / 1e3), "mrays_per_s": (st1["rays_total"] - st0["rays_total"]) / (ms / 1e3) / 1e6}
+        # per-stage device times of a steady-state frame on the strictly serial schedule (events recorded by the library on
+        # the same stream; with frames in flight the kernels of different frames overlap and a per-kernel time means little)
         stage_ms = {k: st1[k] for k in ("ms_trace", "ms_taa", "ms_atrous", "ms_atrous_chain", "ms_exposure", "ms_cells", "ms_total")}
         launches_per_frame = st1["kernel_launches"]
+        # `value`: the same K frames with up to `slots` frames in flight on this GPU (ycge_pipeline_config; bit-identical)
+        slots = int(os.environ.get("YCGE_SLOTS", "3"))
+        if slots > 1:
+            r.pipeline_config(slots)
+            r.render_frames_async(max(3, args.warmup))
+            r.wait()
+            st0 = r.stats()
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            r.render_frames_async(args.steps)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            st1 = r.stats()
+        clocks = sampler.stop()
+        rays_timed = st1["rays_total"] - st0["rays_total"]
+        # streaming end to end: camera in, frame enqueued, cells copied to pinned host memory as part of the frame; the host
+        # waits for frame N - slots + 1 before it submits frame N + 1 (every frame's cells land on the host inside the region)
+        ring = [torch.empty((fb_h * fb_w * api.CELL_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True) for _ in range(max(1, slots))]
+        ring_np = [t.numpy().view(api.CELL_DTYPE).reshape(fb_h, fb_w) for t in ring]
+        def stream_frames(k):
+            ids = []
+            for i in range(k):
+                if len(ids) == max(1, slots):
+                    r.frame_wait(ids.pop(0))
+                r.SetCamera(*pose)
+                ids.append(r.submit_frame(ring_np[i % len(ring_np)]))
+            for fid in ids:
+                r.frame_wait(fid)
+        stream_frames(max(3, args.warmup))
+        sts0 = r.stats()
+        t0 = time.perf_counter()
+        stream_frames(args.steps)
+        stream_s = time.perf_counter() - t0
+        sts1 = r.stats()
+        streaming = {"value": (sts1["rays_total"] - sts0["rays_total"]) / stream_s / 1e6, "unit": "Mrays/s", "frames_per_s": args.steps / stream_s,
+                     "frames_in_flight": slots, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "api": "SetCamera + ycge_submit_frame per step, ycge_frame_wait %d frames later" % (slots - 1)}
         # e2e: the public IConsoleRenderer call per step, camera in, cells out to pinned host memory
         for _ in range(3):
             r.SetCamera(*pose)
@@ -365,10 +403,12 @@ def main():
         line = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
-                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ("" if n == 1 else (", peer hand-off" if peer_handoff else ", NCCL send/recv hand-off") + (", frames pipelined over ranks (value); lock-step (e2e)" if pipelined else "")),
+                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ((", %d frames in flight on the GPU (value, e2e_streaming); serial (e2e, stage_ms, roofline kernel time)" % slots) if n == 1 else (", peer hand-off" if peer_handoff else ", NCCL send/recv hand-off") + (", frames pipelined over ranks (value); lock-step (e2e)" if pipelined else "")),
                            "l2": "per-frame working set (8 float4 image planes = %d MB) exceeds the 126 MB L2; no explicit flush" % (W * H * 128 // (1 << 20))},
                 "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff, "frame_pipelining": pipelined, "tiles_cell_rows": [t[1] for t in tiles]} if n > 1 else {}),
-                "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "SetCamera + TryFlipAndBlit per step, synchronous (the drop-in call; latency of one frame)"},
+                **({"e2e_streaming": streaming, "serial_schedule": serial, "frames_in_flight": slots} if n == 1 else {}),
                 "gpu_launches": launches_per_frame * args.steps * n,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))

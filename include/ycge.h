@@ -259,6 +259,19 @@ YCGE_API int ycge_render_frame_stats(ycge_ctx *ctx, ycge_cell *out, int32_t stri
  * last frame stay in device memory (ycge_device_ptr(YCGE_PTR_CELLS)).  ycge_wait blocks until done. */
 YCGE_API int ycge_render_frames_async(ycge_ctx *ctx, int32_t n);
 YCGE_API int ycge_wait(ycge_ctx *ctx);
+/* Frame pipelining on one GPU.  The reference computes a frame strictly after the previous one
+ * (RaytraceRenderer.cs:157-267), but only three things actually flow from frame N to frame N+1: the TAA history with its
+ * guides (:207-216), ToneMapper.aeExposure (ToneMapper.cs:85-90) and the camera memory (:266); the denoised image never
+ * re-enters the history (:221-224).  With n_slots >= 2 the asynchronous entry points (ycge_render_frames_async,
+ * ycge_submit_frame) therefore run the à-trous passes of up to n_slots frames concurrently with the trace/TAA of the
+ * following ones (each slot owns its scratch buffers and a stream); the ordered exposure sum and the cell conversion
+ * are chained frame to frame.  Results are bit-identical to n_slots = 1.  Default 1; costs ~0.45 KB per pixel and slot. */
+YCGE_API int ycge_pipeline_config(ycge_ctx *ctx, int32_t n_slots);
+/* SetCamera + TryFlipAndBlit without the wait: enqueues one frame with the current camera and copies its cells into `out`
+ * (caller-owned, page-locked for a truly asynchronous copy) as part of that frame's work; *frame_id receives the frame
+ * number.  ycge_frame_wait(id) returns once the cells of that frame have landed.  At most n_slots frames may be un-waited. */
+YCGE_API int ycge_submit_frame(ycge_ctx *ctx, ycge_cell *out, int32_t stride_cells, int64_t *frame_id);
+YCGE_API int ycge_frame_wait(ycge_ctx *ctx, int64_t frame_id);
 /* Copy the device-resident cells of the last frame to host memory (what ycge_render_frame does at its end). */
 YCGE_API int ycge_read_cells(ycge_ctx *ctx, ycge_cell *out, int32_t stride_cells);
 

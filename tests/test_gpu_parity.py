@@ -244,6 +244,79 @@ def test_async_path_equals_synchronous_path():
     b.close()
 
 
+@pytest.mark.parametrize("n_slots", [2, 3, 5])
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss,pose", [("boxes", 40, 12, 2, None), ("knot:60x16", 48, 27, 4, api.BENCH_POSE)])
+def test_frames_pipelined_on_one_gpu_equal_serial_frames(scene, fb_w, fb_h, ss, pose, n_slots):
+    """ycge_pipeline_config: up to n_slots frames in flight (their à-trous passes overlap the next frames' trace / TAA).
+    Every frame's cells, the last frame's intermediate planes and the exposure recursion must be bit-identical to the
+    strictly serial schedule, and the two schedules can be mixed and re-configured between frames."""
+    s = api.HostScene(scene)
+    a = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    b = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    if pose is not None:
+        a.SetCamera(*pose)
+        b.SetCamera(*pose)
+    b.TryFlipAndBlit()                      # frame 1 on the serial schedule, before the slots exist
+    b.pipeline_config(n_slots)
+    serial = [a.TryFlipAndBlit().copy() for _ in range(12)]
+    # streaming: every frame's cells land in host memory, n_slots frames in flight
+    bufs = [np.empty((fb_h, fb_w), api.CELL_DTYPE) for _ in range(n_slots)]
+    ids = []
+    for f in range(2, 9):
+        if len(ids) == n_slots:
+            fid = ids.pop(0)
+            b.frame_wait(fid)
+            assert_cells_equal(bufs[fid % n_slots], serial[fid - 1], f"streamed frame {fid}")
+        ids.append(b.submit_frame(bufs[f % n_slots]))
+        assert ids[-1] == f
+    for fid in ids:
+        b.frame_wait(fid)
+        assert_cells_equal(bufs[fid % n_slots], serial[fid - 1], f"streamed frame {fid}")
+    with pytest.raises(api.YcgeError):
+        b.frame_wait(3)                      # already waited for
+    # headless: frames 9..11 enqueued at once
+    b.render_frames_async(3)
+    b.wait()
+    assert_cells_equal(b.read_cells(), serial[10], "pipelined render_frames_async")
+    # the serial renderer is at frame 12, the pipelined one at 11: re-configure, then one synchronous frame
+    b.pipeline_config(1 if n_slots != 3 else 4)
+    assert_cells_equal(b.TryFlipAndBlit(), serial[11], "synchronous frame after pipelined frames")
+    for kind, nm in [(api.DBG_HDR, "hdr"), (api.DBG_ALBEDO_SKY, "albedo/sky"), (api.DBG_NORMAL_DEPTH, "normal/depth"), (api.DBG_TAA, "taa"),
+                     (api.DBG_DENOISED, "denoised"), (api.DBG_LOG_SAMPLES, "log samples"), (api.DBG_PRIM_ID, "prim")]:
+        assert bits_differ(a.debug_read(kind), b.debug_read(kind)) == 0, f"{nm} differs after pipelined frames"
+    sa, sb = a.stats(), b.stats()
+    assert sa["rays_total"] == sb["rays_total"] and sa["frames"] == sb["frames"] == 12
+    assert np.float32(sa["ae_exposure"]).view(np.uint32) == np.float32(sb["ae_exposure"]).view(np.uint32)
+    a.close()
+    b.close()
+
+
+def test_pipelined_frames_follow_a_moving_camera():
+    """Camera motion inside a pipelined stream: the history reset decision (TemporalAA.cs:58-67) is taken per submitted
+    frame from the camera latched at submission, exactly as the serial path takes it."""
+    s = api.HostScene("cylinders_disks_triangles")
+    a = api.CudaRaytraceRenderer(s, 36, 10, 2)
+    b = api.CudaRaytraceRenderer(s, 36, 10, 2)
+    b.pipeline_config(3)
+    poses = [((0.0, 1.0, 0.0), 0.0, 0.0)] * 3 + [((0.0, 1.0, 0.001), 0.0, 0.0)] * 2 + [((0.2, 1.0, 0.0), 0.1, -0.05)] * 3
+    bufs = [np.empty((10, 36), api.CELL_DTYPE) for _ in poses]
+    ids = []
+    want = []
+    for k, p in enumerate(poses):
+        a.SetCamera(*p)
+        want.append(a.TryFlipAndBlit().copy())
+        b.SetCamera(*p)
+        if len(ids) == 3:
+            b.frame_wait(ids.pop(0))
+        ids.append(b.submit_frame(bufs[k]))
+    for fid in ids:
+        b.frame_wait(fid)
+    for k in range(len(poses)):
+        assert_cells_equal(bufs[k], want[k], f"moving camera, frame {k + 1}")
+    a.close()
+    b.close()
+
+
 def test_ansi_stream_through_the_host_framebuffer():
     s = api.HostScene("cornell")
     a = api.CudaRaytraceRenderer(s, 30, 10, 1)

@@ -118,7 +118,7 @@ ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
     "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
     "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
-    "ycge_render_frames_async", "ycge_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
+    "ycge_render_frames_async", "ycge_wait", "ycge_pipeline_config", "ycge_submit_frame", "ycge_frame_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
     "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
     "ycge_frame_finish", "ycge_ansi_emit", "ycge_device_ptr",
     "ycge_set_stream", "ycge_debug_read", "ycge_get_stats", "ycge_get_frame_counter", "ycge_rng_kat",
@@ -158,6 +158,9 @@ def load_lib() -> C.CDLL:
         lib.ycge_render_frame_stats.argtypes = [vp, vp, C.c_int32]
         lib.ycge_render_frames_async.argtypes = [vp, C.c_int32]
         lib.ycge_wait.argtypes = [vp]
+        lib.ycge_pipeline_config.argtypes = [vp, C.c_int32]
+        lib.ycge_submit_frame.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int64)]
+        lib.ycge_frame_wait.argtypes = [vp, C.c_int64]
         lib.ycge_read_cells.argtypes = [vp, vp, C.c_int32]
         lib.ycge_frame_begin.argtypes = [vp]
         lib.ycge_frame_finish.argtypes = [vp]
@@ -426,6 +429,20 @@ class CudaRaytraceRenderer:
 
     def wait(self):
         self._ck(self._lib.ycge_wait(self.ctx))
+
+    def pipeline_config(self, n_slots: int):
+        """Frames in flight on this GPU for render_frames_async / submit_frame (ycge_pipeline_config); 1 = strictly serial."""
+        self._ck(self._lib.ycge_pipeline_config(self.ctx, n_slots))
+
+    def submit_frame(self, out: np.ndarray) -> int:
+        """TryFlipAndBlit without the wait: the frame's cells land in ``out`` (keep it alive; pinned memory makes the copy
+        asynchronous) once ``frame_wait(id)`` returns."""
+        fid = C.c_int64()
+        self._ck(self._lib.ycge_submit_frame(self.ctx, _ptr(out), 0, C.byref(fid)))
+        return fid.value
+
+    def frame_wait(self, frame_id: int):
+        self._ck(self._lib.ycge_frame_wait(self.ctx, frame_id))
 
     def read_cells(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:

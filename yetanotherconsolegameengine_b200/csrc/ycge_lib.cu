@@ -110,7 +110,7 @@ struct ycge_ctx {
     bool want_stats = false;
     bool debug_rays = false;
     float ansi_th[5] = {0, 0, 0, 0, 0};
-    int inplace_ctas_per_launch = 0;
+    int inplace_ctas_per_launch = 0, inplace_ctas_static = 0;
     // resumable à-trous state of the frame in flight (a sharded tile pauses before every in-place pass so that the caller
     // can move the boundary rows between ranks)
     struct Denoise {
@@ -136,6 +136,38 @@ struct ycge_ctx {
     bool peers = false, has_above = false, has_below = false;
     void *ipc_opened[3] = {nullptr, nullptr, nullptr};
     bool fast_div = false; // the FMA division sequence was verified against IEEE division for these four divisors
+    DevBuf<unsigned int> tickets;      // [0]: plain wavefront launches, [1]: peer-storing launches (dispatch-order tickets)
+    std::vector<unsigned int> ticket_bases = std::vector<unsigned int>(132, 0u); // host mirror of the counters
+    unsigned int ticket_base_of(int peer, int slot) const { return ticket_bases[peer ? 1 : 2 * slot + 2]; }
+    void ticket_advance(int peer, int slot, unsigned int n) { ticket_bases[peer ? 1 : 2 * slot + 2] += n; }
+
+    // Frame pipelining on one GPU (ycge_pipeline_config, used by ycge_render_frames_async and ycge_submit_frame).
+    // Between consecutive frames the path has exactly three dependencies: the TAA history + guides (frame N+1's TAA
+    // reads what frame N's wrote), the exposure scalar (ToneMapper.aeExposure) and the output cells.  The à-trous
+    // passes of frame N -- among them the latency-bound wavefront -- feed nothing of frame N+1's trace / TAA, because the
+    // reference never writes the denoised image back into the history (RaytraceRenderer.cs:221-224).  So a frame is
+    // cut into FRONT (trace, TAA, à-trous pass 0; serial on the ctx's stream), BACK (pre-pass, wavefront, later
+    // passes, exposure samples; on the slot's own stream, concurrent with the next frames' fronts and backs) and FINISH
+    // (ordered exposure sum, cells, optional D2H; on the slot's stream but chained frame to frame by an event).
+    // Slot k = frame % n_slots owns the scratch pair, the pre-records, the samples and a guide set.
+    struct Slot {
+        DevBuf<float4> sa, sb, pre, gnd, gas;
+        DevBuf<float> logs;
+        cudaStream_t st = nullptr;
+        cudaEvent_t front_done = nullptr, fin_done = nullptr, host_done = nullptr;
+        ~Slot() { if (st) cudaStreamDestroy(st); if (front_done) cudaEventDestroy(front_done); if (fin_done) cudaEventDestroy(fin_done); if (host_done) cudaEventDestroy(host_done); }
+    };
+    std::vector<std::unique_ptr<Slot>> slots; // slots[k-1] for k >= 1; slot 0 is the ctx's own buffers and (unpipelined) stream
+    cudaStream_t st0 = nullptr;               // slot 0's back stream when pipelining
+    cudaEvent_t front_done0 = nullptr, fin_done0 = nullptr, host_done0 = nullptr;
+    int n_slots = 1;
+    bool pipelined = false;                   // set for the duration of a pipelined submission
+    int cur_slot = 0, cur_gset = 0, last_gset = 0;
+    cudaEvent_t last_fin = nullptr;           // FINISH of the most recently submitted pipelined frame
+    cudaStream_t back = nullptr;              // stream of the frame in flight after its front part
+    ycge_cell *host_out = nullptr;            // ycge_submit_frame: destination of the frame being submitted
+    int host_stride = 0;
+    std::vector<std::pair<long long, cudaEvent_t>> in_flight; // submitted frames whose cells have not been waited for
 
     // timing
     cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [7],[8] bracket the wavefront kernel
@@ -156,6 +188,17 @@ int fail(ycge_ctx *ctx, int code, const std::string &msg) {
         if (e__ != cudaSuccess)                                                                         \
             return fail(ctx, YCGE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
     } while (0)
+
+// ---- slots (frame pipelining) and guide sets ------------------------------------------------------------------
+struct SlotView { float4 *sa, *sb; DevBuf<float4> *pre; float *logs; size_t n_logs; cudaStream_t st; cudaEvent_t front_done, fin_done, host_done; };
+SlotView slot_view(ycge_ctx *c, int k) {
+    if (k == 0) return SlotView{c->sa.p, c->sb.p, &c->pre, c->logs.p, c->logs.n, c->st0, c->front_done0, c->fin_done0, c->host_done0};
+    ycge_ctx::Slot &s = *c->slots[k - 1];
+    return SlotView{s.sa.p, s.sb.p, &s.pre, s.logs.p, s.logs.n, s.st, s.front_done, s.fin_done, s.host_done};
+}
+int n_gsets(const ycge_ctx *c) { return std::max(2, c->n_slots); }
+float4 *gnd_of(ycge_ctx *c, int g) { return g == 0 ? c->gnd0.p : (g == 1 ? c->gnd1.p : c->slots[g - 1]->gnd.p); }
+float4 *gas_of(ycge_ctx *c, int g) { return g == 0 ? c->gas0.p : (g == 1 ? c->gas1.p : c->slots[g - 1]->gas.p); }
 
 // ---- reference SoA tree -> pair nodes (device_types.h) ------------------------------------------------------
 struct TreeView {
@@ -234,6 +277,42 @@ float ansi_threshold(int bound) {
     return c;
 }
 
+// Priority of the BACK streams.  Measured at 1080p with 3 slots: equal priority 302 frames/s, highest priority 287 (the next
+// frame's trace kernel then starves behind two resident wavefront kernels and the serial FRONT becomes the bottleneck).
+int back_priority() {
+    if (const char *e = getenv("YCGE_BACK_PRIORITY")) return atoi(e); // development aid
+    return 0;
+}
+
+// (re)allocates the extra slots for the current geometry; the caller has synchronised every stream
+int alloc_slots(ycge_ctx *c, int n) {
+    c->slots.clear();
+    c->n_slots = 1;
+    const size_t px = (size_t)c->W * c->H;
+    for (int k = 1; k < n; k++) {
+        std::unique_ptr<ycge_ctx::Slot> sl(new ycge_ctx::Slot());
+        CK(c, sl->sa.alloc(px)); CK(c, sl->sb.alloc(px));
+        CK(c, cudaMemsetAsync(sl->sa.p, 0, px * sizeof(float4), c->stream));
+        CK(c, cudaMemsetAsync(sl->sb.p, 0, px * sizeof(float4), c->stream));
+        if (k >= 2) {
+            CK(c, sl->gnd.alloc(px)); CK(c, sl->gas.alloc(px));
+            CK(c, cudaMemsetAsync(sl->gnd.p, 0, px * sizeof(float4), c->stream));
+            CK(c, cudaMemsetAsync(sl->gas.p, 0, px * sizeof(float4), c->stream));
+        }
+        CK(c, sl->logs.alloc((size_t)c->sw * c->sh));
+        CK(c, cudaMemsetAsync(sl->logs.p, 0, sl->logs.n * sizeof(float), c->stream));
+        CK(c, cudaStreamCreateWithPriority(&sl->st, cudaStreamNonBlocking, back_priority()));
+        CK(c, cudaEventCreateWithFlags(&sl->front_done, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&sl->fin_done, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&sl->host_done, cudaEventDisableTiming));
+        c->slots.push_back(std::move(sl));
+    }
+    c->n_slots = std::max(1, n);
+    c->last_fin = nullptr;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int alloc_planes(ycge_ctx *c) {
     size_t n = (size_t)c->W * c->H;
     CK(c, c->cur.alloc(n)); CK(c, c->gnd0.alloc(n)); CK(c, c->gnd1.alloc(n)); CK(c, c->gas0.alloc(n)); CK(c, c->gas1.alloc(n));
@@ -253,7 +332,8 @@ int alloc_planes(ycge_ctx *c) {
     CK(c, cudaMemsetAsync(c->cells.p, 0, c->cells.n * sizeof(ycge_cell), c->stream));
     c->taa_valid = false;
     c->denoised = nullptr;
-    return 0;
+    c->last_gset = 0;
+    return alloc_slots(c, c->n_slots);
 }
 
 int set_geometry(ycge_ctx *c, int fb_w, int fb_h, int ss, int tile_row0, int tile_rows) {
@@ -331,10 +411,17 @@ int frame_begin_impl(ycge_ctx *c) {
     for (int k = K - 1; k >= 0; k--) halo_after[k] = halo_after[k + 1] + 2 * (1 << k);
     auto range = [&](int halo, int &a, int &b) { a = std::max(0, ty0 - halo); b = std::min(H, ty1 + halo); };
 
-    const int parity = (int)(frame & 1);
+    // slot and guide set of this frame; `parity` selects the guide set the trace kernel writes (img.gnd/gas[parity])
+    const int slot = (int)(frame % c->n_slots), gset = (int)(frame % n_gsets(c)), gprev = c->last_gset == gset ? (gset + 1) % n_gsets(c) : c->last_gset;
+    c->cur_slot = slot; c->cur_gset = gset;
+    const SlotView sv = slot_view(c, slot);
+    c->back = c->pipelined ? sv.st : s;
+    if (c->pipelined) CK(c, cudaStreamWaitEvent(s, sv.fin_done, 0)); // the slot's previous frame has left its buffers (a never-recorded event does not wait)
+    else if (c->last_fin) { CK(c, cudaStreamWaitEvent(s, c->last_fin, 0)); c->last_fin = nullptr; } // a synchronous frame after pipelined ones
+    const int parity = 0;
     ImagePlanes img;
-    img.cur = c->cur.p; img.gnd[0] = c->gnd0.p; img.gnd[1] = c->gnd1.p; img.gas[0] = c->gas0.p; img.gas[1] = c->gas1.p;
-    img.hist = c->hist.p; img.sa = c->sa.p; img.sb = c->sb.p; img.prim = c->prim.p; img.rays = c->debug_rays ? c->rays_dbg.p : nullptr;
+    img.cur = c->cur.p; img.gnd[0] = gnd_of(c, gset); img.gnd[1] = gnd_of(c, gprev); img.gas[0] = gas_of(c, gset); img.gas[1] = gas_of(c, gprev);
+    img.hist = c->hist.p; img.sa = sv.sa; img.sb = sv.sb; img.prim = c->prim.p; img.rays = c->debug_rays ? c->rays_dbg.p : nullptr;
 
     int launches = 0;
     CK(c, cudaEventRecord(c->ev[0], s));
@@ -346,7 +433,7 @@ int frame_begin_impl(ycge_ctx *c) {
         // the frame pipeline, finish its boundary rows without waiting for this rank's whole front end.
         int a1, b1; range(halo_after[2], a1, b1);
         const int m0 = c->has_above ? std::max(0, a1 - 4) : a1;
-        CK(c, cudaMemsetAsync(c->sb.p + (size_t)m0 * W, 0xFF, (size_t)(b1 - m0) * W * sizeof(float4), s));
+        CK(c, cudaMemsetAsync(sv.sb + (size_t)m0 * W, 0xFF, (size_t)(b1 - m0) * W * sizeof(float4), s));
         if (c->has_above) { peer_signal_kernel<<<1, 1, 0, s>>>(c->above_flags, (int)frame); launches++; }
         c->dn.early_reset = true;
     }
@@ -378,8 +465,8 @@ int frame_begin_impl(ycge_ctx *c) {
     CK(c, cudaEventRecord(c->ev[2], s));
     { // K3: the reference's ping-pong including its in-place iteration (:648-719), resumable (see denoise_run)
         ycge_ctx::Denoise &d = c->dn;
-        d.phys[0] = c->hist.p; d.phys[1] = c->sa.p; d.phys[2] = c->sb.p;
-        d.cur_id = 0; d.dst_id = 1; d.it = 0; d.K = K; d.parity = parity; d.ty0 = ty0; d.ty1 = ty1; d.pending = false;
+        d.phys[0] = c->hist.p; d.phys[1] = sv.sa; d.phys[2] = sv.sb;
+        d.cur_id = 0; d.dst_id = 1; d.it = 0; d.K = K; d.parity = gset; c->last_gset = gset; d.ty0 = ty0; d.ty1 = ty1; d.pending = false;
         for (int k = 0; k <= K; k++) d.halo_after[k] = halo_after[k];
         c->launches_last = launches;
         c->frame_open = true;
@@ -397,21 +484,31 @@ int denoise_run(ycge_ctx *c) {
     const int W = c->W, H = c->H, ss = c->ss;
     const EdgeDiv ed = c->edge_div;
     const bool fast = c->fast_div;
-    const float4 *gnd = d.parity ? c->gnd1.p : c->gnd0.p, *gas = d.parity ? c->gas1.p : c->gas0.p;
+    const float4 *gnd = gnd_of(c, d.parity), *gas = gas_of(c, d.parity); // d.parity = guide set of the frame
+    const SlotView sv = slot_view(c, c->cur_slot);
+    DevBuf<float4> &pre = *sv.pre;
     int launches = 0;
     auto range = [&](int halo, int &a, int &b) { a = std::max(0, d.ty0 - halo); b = std::min(H, d.ty1 + halo); };
+    auto to_back = [&]() -> int { // FRONT ends here: everything later only reads this frame's own slot and guide set
+        if (!c->pipelined || s == c->back) return 0;
+        CK(c, cudaEventRecord(sv.front_done, s));
+        CK(c, cudaStreamWaitEvent(c->back, sv.front_done, 0));
+        s = c->back;
+        return 0;
+    };
     while (d.it < d.K) {
         const int it = d.it;
+        if (it >= 1) { int rc = to_back(); if (rc) return rc; }
         int a, b; range(d.halo_after[it + 1], a, b);
         const int step = 1 << it;
         if (d.cur_id == d.dst_id) {
             // in-place pass on scratch X: OLD = X, NEW = the other scratch (dead at this point), which then becomes X
             const int X = d.cur_id, Y = (X == 1) ? 2 : 1;
             if (!d.pending) {
-                if (c->pre.n < (size_t)W * H * 25) CK(c, c->pre.alloc((size_t)W * H * 25));
+                if (pre.n < (size_t)W * H * 25) { CK(c, cudaDeviceSynchronize()); CK(c, pre.alloc((size_t)W * H * 25)); }
                 // (1) everything that does not depend on new values, fully parallel
                 AtrousPreArgs pa;
-                pa.old_ = d.phys[X]; pa.gnd = gnd; pa.gas = gas; pa.pre = c->pre.p; pa.plane = (size_t)W * H;
+                pa.old_ = d.phys[X]; pa.gnd = gnd; pa.gas = gas; pa.pre = pre.p; pa.plane = (size_t)W * H;
                 pa.W = W; pa.H = H; pa.y0 = a; pa.y1 = b; pa.step = step; pa.e = ed;
                 if (fast) atrous_pre_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
                 else atrous_pre_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
@@ -430,7 +527,7 @@ int denoise_run(ycge_ctx *c) {
             d.pending = false;
             // (2) the wavefront
             AtrousChainArgs ia;
-            ia.old_ = d.phys[X]; ia.new_ = d.phys[Y]; ia.pre = c->pre.p; ia.plane = (size_t)W * H;
+            ia.old_ = d.phys[X]; ia.new_ = d.phys[Y]; ia.pre = pre.p; ia.plane = (size_t)W * H;
             ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc; ia.trace = nullptr;
             ia.peer_new = nullptr; ia.peer_y0 = ia.peer_y1 = 0; ia.ready = c->flags.p; ia.frame = (int)c->frame_counter;
             if (c->peers && c->has_below) {
@@ -444,39 +541,61 @@ int denoise_run(ycge_ctx *c) {
                 ia.trace = c->chain_trace.p;
             }
             if (c->inplace_ctas_per_launch <= 0) {
-                int per_sm = 0;
-                if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<true, true>, YCGE_AIC_WARPS * 32, 0));
-                else CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, atrous_chain_kernel<false, true>, YCGE_AIC_WARPS * 32, 0));
                 cudaDeviceProp prop;
                 CK(c, cudaGetDeviceProperties(&prop, c->device));
+                int per_sm = YCGE_AIC_CTAS_PER_SM; // persistent launch: the same number of CTAs on every SM
+                if (const char *e = getenv("YCGE_CHAIN_CTAS_PER_SM")) per_sm = std::max(1, atoi(e)); // development aid
                 c->inplace_ctas_per_launch = std::max(1, per_sm * prop.multiProcessorCount);
+                int occ = 0; // static launch: every CTA of a launch co-resident
+                if (fast) CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, atrous_chain_static_kernel<true, true>, YCGE_AIC_WARPS * 32, 0));
+                else CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, atrous_chain_static_kernel<false, true>, YCGE_AIC_WARPS * 32, 0));
+                c->inplace_ctas_static = std::max(1, occ * prop.multiProcessorCount);
             }
-            // all CTAs of a launch must be co-resident (they wait on each other); rows are launched in order
-            const int rows_per_launch = std::max(1, c->inplace_ctas_per_launch * YCGE_AIC_WARPS / step);
+            // A frame that has the GPU to itself uses the static form (rows in blockIdx order, launches sized so that all CTAs
+            // of one are co-resident); frames that overlap (pipelined) use the persistent ticket form, which waits for nothing
+            // that is not already running.
+            const bool use_static = !c->pipelined && !getenv("YCGE_CHAIN_PERSISTENT");
+            const int rows_per_launch = std::max(1, c->inplace_ctas_static * YCGE_AIC_WARPS / step);
             CK(c, cudaEventRecord(c->ev[7], s));
             auto launch_chain = [&](cudaStream_t st, int r0, int r1, bool peer) {
                 AtrousChainArgs q = ia;
                 q.y0 = r0; q.y1 = r1;
                 const int warps = (r1 - r0) * step; // one warp per chain, `step` chains per row
-                const dim3 g(div_up(warps, YCGE_AIC_WARPS)), t(YCGE_AIC_WARPS * 32);
+                const dim3 t(YCGE_AIC_WARPS * 32);
+                if (use_static) {
+                    const dim3 g(div_up(warps, YCGE_AIC_WARPS));
+                    q.ticket = nullptr; q.ticket_base = 0; q.n_chains = (unsigned int)warps;
+                    if (fast && peer) atrous_chain_static_kernel<true, true><<<g, t, 0, st>>>(q);
+                    else if (fast) atrous_chain_static_kernel<true, false><<<g, t, 0, st>>>(q);
+                    else if (peer) atrous_chain_static_kernel<false, true><<<g, t, 0, st>>>(q);
+                    else atrous_chain_static_kernel<false, false><<<g, t, 0, st>>>(q);
+                    launches++;
+                    return;
+                }
+                const dim3 g(std::min(div_up(warps, YCGE_AIC_WARPS), c->inplace_ctas_per_launch));
+                const int tk = (st == c->aux) ? 1 : 0; // launches that may overlap need separate ticket counters
+                q.ticket = c->tickets.p + 16 * (tk ? 1 : 2 * c->cur_slot + 2); q.ticket_base = c->ticket_base_of(tk, c->cur_slot);
+                q.n_chains = (unsigned int)warps;
+                c->ticket_advance(tk, c->cur_slot, (unsigned int)warps + g.x * YCGE_AIC_WARPS); // every warp's last ticket is a miss
                 if (fast && peer) atrous_chain_kernel<true, true><<<g, t, 0, st>>>(q);
                 else if (fast) atrous_chain_kernel<true, false><<<g, t, 0, st>>>(q);
                 else if (peer) atrous_chain_kernel<false, true><<<g, t, 0, st>>>(q);
                 else atrous_chain_kernel<false, false><<<g, t, 0, st>>>(q);
                 launches++;
             };
-            if (ia.peer_new && rows_per_launch >= b - a) {
+            if (ia.peer_new && (!use_static || rows_per_launch >= b - a)) {
                 // the rows that are also stored into the rank below run the (slower) peer variant as a second, concurrent
                 // kernel on a side stream; everything above them runs the plain variant
                 const int split = std::max(a, ia.peer_y0 - ((ia.peer_y0 - a) % std::max(1, YCGE_AIC_WARPS / step)));
-                CK(c, cudaEventRecord(c->e_fork, s));
+            CK(c, cudaEventRecord(c->e_fork, s));
                 if (split > a) launch_chain(s, a, split, false);
                 CK(c, cudaStreamWaitEvent(c->aux, c->e_fork, 0));
                 launch_chain(c->aux, split, b, true);
                 CK(c, cudaEventRecord(c->e_join, c->aux));
                 CK(c, cudaStreamWaitEvent(s, c->e_join, 0));
             } else {
-                for (int r0 = a; r0 < b; r0 += rows_per_launch) launch_chain(s, r0, std::min(b, r0 + rows_per_launch), ia.peer_new != nullptr);
+                const int per = use_static ? rows_per_launch : b - a;
+                for (int r0 = a; r0 < b; r0 += per) launch_chain(s, r0, std::min(b, r0 + per), ia.peer_new != nullptr);
             }
             CK(c, cudaEventRecord(c->ev[8], s));
             c->chain_timed = true;
@@ -494,14 +613,15 @@ int denoise_run(ycge_ctx *c) {
         d.dst_id = (tmp == 1) ? 2 : 1;
         d.it++;
     }
+    { int rc = to_back(); if (rc) return rc; }
     c->denoised = d.phys[d.cur_id];
     CK(c, cudaEventRecord(c->ev[3], s));
     { // K4a
         int step = std::max(2, ss * 2); // :226; sample row k is pixel row k*step = top row of cell row k
         int srow0 = div_up(d.ty0, step), srow1 = std::min(c->sh, div_up(d.ty1, step));
-        if (c->sharded) CK(c, cudaMemsetAsync(c->logs.p, 0, c->logs.n * sizeof(float), s));
+        if (c->sharded) CK(c, cudaMemsetAsync(sv.logs, 0, sv.n_logs * sizeof(float), s));
         if (srow1 > srow0) {
-            exposure_log_kernel<<<dim3(div_up(c->sw, 128), srow1 - srow0), 128, 0, s>>>(c->denoised, gas, c->logs.p, W, c->sw, step, srow0, srow1);
+            exposure_log_kernel<<<dim3(div_up(c->sw, 128), srow1 - srow0), 128, 0, s>>>(c->denoised, gas, sv.logs, W, c->sw, step, srow0, srow1);
             launches++;
         }
     }
@@ -543,8 +663,20 @@ int finish_launch(ycge_ctx *c, const float *logs, const float4 *den, cudaStream_
 int frame_finish_impl(ycge_ctx *c) {
     if (!c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish without ycge_frame_begin");
     if (c->dn.it <= c->dn.K) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish while an in-place pass is pending (ycge_frame_halo / ycge_frame_inplace)");
-    int rc = finish_launch(c, c->logs.p, c->denoised, c->stream, true);
+    const SlotView sv = slot_view(c, c->cur_slot);
+    cudaStream_t fs = c->pipelined ? c->back : c->stream;
+    if (c->pipelined && c->last_fin) CK(c, cudaStreamWaitEvent(fs, c->last_fin, 0)); // exposure state and cells are handed on frame to frame
+    int rc = finish_launch(c, sv.logs, c->denoised, fs, true);
     if (rc) return rc;
+    if (c->pipelined) {
+        if (c->host_out) { // streaming path: this frame's cells to the caller's (pinned) buffer, still inside the FINISH chain
+            CK(c, cudaMemcpy2DAsync(c->host_out, (size_t)c->host_stride * sizeof(ycge_cell), c->cells.p, (size_t)c->fbW * sizeof(ycge_cell),
+                                    (size_t)c->fbW * sizeof(ycge_cell), (size_t)c->tile_rows, cudaMemcpyDeviceToHost, fs));
+            CK(c, cudaEventRecord(sv.host_done, fs));
+        }
+        CK(c, cudaEventRecord(sv.fin_done, fs));
+        c->last_fin = sv.fin_done;
+    }
     c->launches_last += 2;
     // taa.CommitCamera (:266, TemporalAA.cs:69-76)
     memcpy(c->last_cam, c->snap_cam, sizeof c->last_cam); c->last_yaw = c->snap_yaw; c->last_pitch = c->snap_pitch;
@@ -552,8 +684,16 @@ int frame_finish_impl(ycge_ctx *c) {
     return 0;
 }
 
+// orders the ctx's stream after the FINISH of the last pipelined frame, so that "synchronise the ctx's stream" keeps meaning
+// "everything submitted is done"
+int join_pipeline(ycge_ctx *c) {
+    if (c->last_fin) { CK(c, cudaStreamWaitEvent(c->stream, c->last_fin, 0)); c->last_fin = nullptr; }
+    return 0;
+}
+
 int read_cells_impl(ycge_ctx *c, ycge_cell *out, int stride) {
     if (!out) return fail(c, YCGE_ERR_INVALID, "out is NULL");
+    { int rc = join_pipeline(c); if (rc) return rc; }
     if (stride <= 0) stride = c->fbW;
     if (stride < c->fbW) return fail(c, YCGE_ERR_INVALID, "stride smaller than fb_w");
     CK(c, cudaMemcpy2DAsync(out, (size_t)stride * sizeof(ycge_cell), c->cells.p, (size_t)c->fbW * sizeof(ycge_cell), (size_t)c->fbW * sizeof(ycge_cell),
@@ -604,6 +744,12 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     CK(nullptr, cudaMemcpyAsync(c->expo.p, &es, sizeof es, cudaMemcpyHostToDevice, c->stream));
     CK(nullptr, c->counters.alloc(1));
     CK(nullptr, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), c->stream));
+    CK(nullptr, c->tickets.alloc(132 * 16));
+    CK(nullptr, cudaMemsetAsync(c->tickets.p, 0, c->tickets.n * sizeof(unsigned int), c->stream));
+    CK(nullptr, cudaStreamCreateWithPriority(&c->st0, cudaStreamNonBlocking, back_priority()));
+    CK(nullptr, cudaEventCreateWithFlags(&c->front_done0, cudaEventDisableTiming));
+    CK(nullptr, cudaEventCreateWithFlags(&c->fin_done0, cudaEventDisableTiming));
+    CK(nullptr, cudaEventCreateWithFlags(&c->host_done0, cudaEventDisableTiming));
     CK(nullptr, c->flags.alloc(16));
     CK(nullptr, cudaMemsetAsync(c->flags.p, 0, 16 * sizeof(int), c->stream));
     CK(nullptr, c->totals.alloc(1));
@@ -636,6 +782,12 @@ YCGE_API void ycge_destroy(ycge_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
+    ctx->slots.clear();
+    if (ctx->st0) cudaStreamDestroy(ctx->st0);
+    if (ctx->front_done0) cudaEventDestroy(ctx->front_done0);
+    if (ctx->fin_done0) cudaEventDestroy(ctx->fin_done0);
+    if (ctx->host_done0) cudaEventDestroy(ctx->host_done0);
     for (auto &p : ctx->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
     if (ctx->e_fork) cudaEventDestroy(ctx->e_fork);
@@ -648,7 +800,8 @@ YCGE_API void ycge_destroy(ycge_ctx *ctx) {
 YCGE_API int ycge_resize(ycge_ctx *c, int32_t fb_w, int32_t fb_h, int32_t ss) {
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaDeviceSynchronize()); // pipelined frames may still run on the slots' streams
+    c->last_fin = nullptr; c->in_flight.clear(); c->pre.release();
     int row0 = c->sharded ? c->tile_row0 : 0, rows = c->sharded ? c->tile_rows : 0;
     if (c->sharded && row0 + rows > fb_h) return fail(c, YCGE_ERR_INVALID, "tile exceeds resized framebuffer");
     int rc = set_geometry(c, fb_w, fb_h, ss, row0, rows);
@@ -661,6 +814,7 @@ YCGE_API int ycge_resize(ycge_ctx *c, int32_t fb_w, int32_t fb_h, int32_t ss) {
 
 YCGE_API int ycge_set_stream(ycge_ctx *c, void *cuda_stream) {
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    { int rc = join_pipeline(c); if (rc) return rc; }
     CK(c, cudaStreamSynchronize(c->stream));
     if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)cuda_stream;
@@ -1070,16 +1224,80 @@ YCGE_API int ycge_render_frame_stats(ycge_ctx *c, ycge_cell *out, int32_t stride
 YCGE_API int ycge_render_frames_async(ycge_ctx *c, int32_t n) {
     if (!c || n < 0) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
-    for (int i = 0; i < n; i++) {
-        int rc = frame_begin_impl(c);
-        if (rc) return rc;
-        rc = frame_finish_impl(c);
-        if (rc) return rc;
+    c->pipelined = c->n_slots >= 2;
+    c->host_out = nullptr;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; i++) {
+        rc = frame_begin_impl(c);
+        if (!rc) rc = frame_finish_impl(c);
     }
+    c->pipelined = false;
+    if (rc) return rc;
+    // everything enqueued later on the ctx's stream (reads, synchronous frames, ycge_wait) comes after the last FINISH
+    if (c->last_fin) { CK(c, cudaStreamWaitEvent(c->stream, c->last_fin, 0)); c->last_fin = nullptr; }
     return 0;
+}
+YCGE_API int ycge_pipeline_config(ycge_ctx *c, int32_t n_slots) {
+    if (!c || n_slots < 1 || n_slots > 64) return fail(c, YCGE_ERR_INVALID, "n_slots must be in [1,64]");
+    if (c->sharded && n_slots > 1) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx pipelines over ranks (ycge_frame_stash), not over slots");
+    if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "a frame is open");
+    if (n_slots == c->n_slots) return 0;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaDeviceSynchronize());
+    c->in_flight.clear();
+    // the guide set of the last frame (next frame's TAA reads it) moves to where the new numbering expects it
+    const size_t px = (size_t)c->W * c->H;
+    const int keep = (int)(c->frame_counter % std::max(2, (int)n_slots)); // the next frame writes set (frame_counter + 1) % G
+    DevBuf<float4> tg, ta;
+    CK(c, tg.alloc(px)); CK(c, ta.alloc(px));
+    CK(c, cudaMemcpy(tg.p, gnd_of(c, c->last_gset), px * sizeof(float4), cudaMemcpyDeviceToDevice));
+    CK(c, cudaMemcpy(ta.p, gas_of(c, c->last_gset), px * sizeof(float4), cudaMemcpyDeviceToDevice));
+    int rc = alloc_slots(c, n_slots);
+    if (rc) return rc;
+    CK(c, cudaMemcpy(gnd_of(c, keep), tg.p, px * sizeof(float4), cudaMemcpyDeviceToDevice));
+    CK(c, cudaMemcpy(gas_of(c, keep), ta.p, px * sizeof(float4), cudaMemcpyDeviceToDevice));
+    c->last_gset = keep;
+    return 0;
+}
+/* Streaming path: SetCamera + TryFlipAndBlit without the wait.  The frame is enqueued (pipelined over the slots) and its
+ * cells are copied into `out` (caller-owned, should be pinned) as part of the frame's FINISH; ycge_frame_wait(id) blocks
+ * until that copy has landed.  At most n_slots frames may be un-waited. */
+YCGE_API int ycge_submit_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells, int64_t *frame_id) {
+    if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
+    if (stride_cells <= 0) stride_cells = c->fbW;
+    if (stride_cells < c->fbW) return fail(c, YCGE_ERR_INVALID, "stride smaller than fb_w");
+    if ((int)c->in_flight.size() >= c->n_slots) return fail(c, YCGE_ERR_LIMIT, "more un-waited frames than pipeline slots; call ycge_frame_wait");
+    c->pipelined = c->n_slots >= 2;
+    c->host_out = out; c->host_stride = stride_cells;
+    int rc = frame_begin_impl(c);
+    if (!rc) rc = frame_finish_impl(c);
+    const bool piped = c->pipelined;
+    c->pipelined = false; c->host_out = nullptr;
+    if (rc) return rc;
+    const SlotView sv = slot_view(c, c->cur_slot);
+    if (!piped) { // one slot: same stream, same order, still asynchronous to the host
+        CK(c, cudaMemcpy2DAsync(out, (size_t)stride_cells * sizeof(ycge_cell), c->cells.p, (size_t)c->fbW * sizeof(ycge_cell),
+                                (size_t)c->fbW * sizeof(ycge_cell), (size_t)c->tile_rows, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaEventRecord(sv.host_done, c->stream));
+    }
+    c->in_flight.push_back(std::make_pair(c->frame_counter, sv.host_done));
+    if (frame_id) *frame_id = c->frame_counter;
+    return 0;
+}
+YCGE_API int ycge_frame_wait(ycge_ctx *c, int64_t frame_id) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    for (size_t i = 0; i < c->in_flight.size(); i++) {
+        if (c->in_flight[i].first != frame_id) continue;
+        CK(c, cudaEventSynchronize(c->in_flight[i].second));
+        c->in_flight.erase(c->in_flight.begin(), c->in_flight.begin() + i + 1); // frames finish in order
+        return 0;
+    }
+    return fail(c, YCGE_ERR_INVALID, "frame id is not in flight");
 }
 YCGE_API int ycge_wait(ycge_ctx *c) {
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    { int rc = join_pipeline(c); if (rc) return rc; }
     CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1091,6 +1309,7 @@ YCGE_API int ycge_ansi_emit(ycge_ctx *c, uint8_t *out, size_t cap, size_t *n_byt
     if (!c || !out || !n_bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if (c->frame_counter == 0) return fail(c, YCGE_ERR_INVALID, "no frame rendered yet");
     CK(c, cudaSetDevice(c->device));
+    { int rc = join_pipeline(c); if (rc) return rc; }
     cudaStream_t s = c->stream;
     const int rows = c->tile_rows, fbW = c->fbW;
     const size_t worst = 64 + (size_t)rows * 16 + (size_t)rows * fbW * 24; // 21 bytes of escape + 3 of glyph per cell at most
@@ -1122,11 +1341,12 @@ YCGE_API int ycge_device_ptr(ycge_ctx *c, int32_t kind, void **ptr, size_t *byte
 YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes) {
     if (!c || !dst) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
+    { int rc = join_pipeline(c); if (rc) return rc; }
     CK(c, cudaStreamSynchronize(c->stream));
     size_t n = (size_t)c->W * c->H;
     const void *src = nullptr;
     size_t need = 0;
-    int parity = (int)(c->frame_counter & 1);
+    const int g = c->last_gset;
     switch (kind) {
         case YCGE_DBG_RAYS:
             if (!c->debug_rays) { // enable the tap; the next frame fills it
@@ -1136,12 +1356,12 @@ YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes)
             }
             src = c->rays_dbg.p; need = n * 24; break;
         case YCGE_DBG_HDR: src = c->cur.p; need = n * 16; break;
-        case YCGE_DBG_ALBEDO_SKY: src = parity ? c->gas1.p : c->gas0.p; need = n * 16; break;
-        case YCGE_DBG_NORMAL_DEPTH: src = parity ? c->gnd1.p : c->gnd0.p; need = n * 16; break;
+        case YCGE_DBG_ALBEDO_SKY: src = gas_of(c, g); need = n * 16; break;
+        case YCGE_DBG_NORMAL_DEPTH: src = gnd_of(c, g); need = n * 16; break;
         case YCGE_DBG_TAA: src = c->hist.p; need = n * 16; break;
         case YCGE_DBG_DENOISED: src = c->denoised; need = n * 16; break;
         case YCGE_DBG_PRIM_ID: src = c->prim.p; need = n * 8; break;
-        case YCGE_DBG_LOG_SAMPLES: src = c->logs.p; need = c->logs.n * 4; break;
+        case YCGE_DBG_LOG_SAMPLES: src = slot_view(c, c->cur_slot).logs; need = c->logs.n * 4; break;
         default: return fail(c, YCGE_ERR_INVALID, "unknown debug kind");
     }
     if (!src) return fail(c, YCGE_ERR_INVALID, "no frame rendered yet");
@@ -1153,6 +1373,7 @@ YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes)
 YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
     if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
+    { int rc = join_pipeline(c); if (rc) return rc; }
     CK(c, cudaStreamSynchronize(c->stream));
     memset(out, 0, sizeof *out);
     TraceCounters tc;
