@@ -241,6 +241,11 @@ YCGE_API int ycge_mesh_upload_soa(ycge_ctx *ctx, int32_t id, const ycge_mesh_soa
 YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *ctx, int32_t id, int32_t n_tris, const float *abc,
                                         const ycge_material *material);                       /* new MeshBVH(tris)  MeshBVH.cs:41-130 */
 YCGE_API int ycge_volume_upload(ycge_ctx *ctx, int32_t id, const ycge_volume *vol);              /* new VolumeGrid(...)  VolumeGrid.cs:55-93 */
+/* new Texture(path) (Renderer/Texture.cs:25-49, :81-90): `rgba` = the reference's int[] pixels (byte 0 = R, row-major, row 0
+ * first), read during the call.  Materials refer to it through ycge_material.tex_id; upload before ycge_scene_upload.
+ * Sampling is Texture.SampleBilinear (:143-162) inside SampleAlbedo (RaytraceRenderer.cs:724-735).  Static images only:
+ * camera/video-backed textures (isDynamic) are outside the path (VideoRenderer). */
+YCGE_API int ycge_texture_upload(ycge_ctx *ctx, int32_t id, int32_t w, int32_t h, const uint32_t *rgba);
 YCGE_API int ycge_scene_upload(ycge_ctx *ctx, const ycge_scene *scene);                          /* Scene.RebuildBVH  Scenes/Scene.cs:66-69 */
 YCGE_API int ycge_lights_update(ycge_ctx *ctx, int32_t n, const ycge_light *lights);             /* DayNightCycle.cs:80-83 */
 YCGE_API int ycge_globals_update(ycge_ctx *ctx, const float bg_top[3], const float bg_bottom[3],

@@ -764,6 +764,36 @@ struct VolumeGrid {
 /* ======================================================================================
  * Scene objects (Objects/BoundedObjects.cs, Surfaces.cs, Triangle.cs) and the top-level BVH
  * ====================================================================================== */
+/* Renderer/Texture.cs (static images): int[] pixels = RGBA bytes (byte 0 = R, InitializeFromRgbaMat :81-90), row-major,
+   row 0 first; SampleBilinear :143-162 */
+struct Texture {
+    int width = 0, height = 0;
+    std::vector<uint32_t> pixels;
+    static Vec3 Lerp(Vec3 a, Vec3 b, float t) { return a * (1.0f - t) + b * t; } /* :164-167 */
+    Vec3 Texel(int idx) const { /* new RGBA32(int).toVec3()  RGBA32.cs:14-21,:82-85 */
+        uint32_t v = pixels[(size_t)idx];
+        return Vec3((float)(v & 255u) / 255.0f, (float)((v >> 8) & 255u) / 255.0f, (float)((v >> 16) & 255u) / 255.0f);
+    }
+    Vec3 SampleBilinear(float u, float v) const {
+        if (width <= 0 || height <= 0 || pixels.empty()) return Vec3(1.0f, 1.0f, 1.0f);
+        u = u - FloorF(u);
+        v = v - FloorF(v);
+        float fx = u * (float)(width - 1);
+        float fy = v * (float)(height - 1);
+        int x0 = (int)FloorF(fx);
+        int y0 = (int)FloorF(fy);
+        int x1 = (x0 + 1) % width;
+        int y1 = (y0 + 1) % height;
+        float tx = fx - (float)x0;
+        float ty = fy - (float)y0;
+        Vec3 c00 = Texel(y0 * width + x0), c10 = Texel(y0 * width + x1), c01 = Texel(y1 * width + x0), c11 = Texel(y1 * width + x1);
+        Vec3 a = Lerp(c00, c10, tx);
+        Vec3 b = Lerp(c01, c11, tx);
+        Vec3 c = Lerp(a, b, ty);
+        return c.Saturate();
+    }
+};
+
 struct Scene;
 struct Object {
     int kind = 0, matA = 0, matB = 0, overrideSR = 0, refId = -1;
@@ -785,6 +815,7 @@ struct Scene {
     uint64_t sortFallbacks = 0;
     std::map<int, std::shared_ptr<MeshBVH>> *meshes = nullptr;
     std::map<int, std::shared_ptr<VolumeGrid>> *volumes = nullptr;
+    std::map<int, std::shared_ptr<Texture>> *textures = nullptr;
     std::vector<const MeshBVH *> objMesh;
     std::vector<const VolumeGrid *> objVol;
 
@@ -1344,6 +1375,7 @@ struct Renderer {
     bool haveScene = false;
     std::map<int, std::shared_ptr<MeshBVH>> meshes;
     std::map<int, std::shared_ptr<VolumeGrid>> volumes;
+    std::map<int, std::shared_ptr<Texture>> textures;
 
     std::vector<Ray> rays;
     std::vector<Vec3> currentHdr, gAlbedo, gNormal, spatialA, spatialB, taaHistory, prevNormal;
@@ -1436,8 +1468,15 @@ struct Renderer {
         Vec3 f = albedo * (on * InvPi);
         return f.Saturate();
     }
-    static Vec3 SampleAlbedo(const Material &mat) { /* :724-735; textures are SURVEY 8(f) "next" */
-        return mat.Albedo;
+    Vec3 SampleAlbedo(const Material &mat, float u, float v) const { /* :724-735 */
+        const Texture *tex = nullptr;
+        if (mat.Tex >= 0 && scene.textures) { auto it = scene.textures->find(mat.Tex); if (it != scene.textures->end()) tex = it->second.get(); }
+        if (tex == nullptr || mat.TextureWeight <= 0.0f) return mat.Albedo;
+        float tiles = (float)std::max(1e-6, (double)mat.UVScale);
+        Vec3 texel = tex->SampleBilinear(u * tiles, v * tiles);
+        float t = mat.TextureWeight < 0.0f ? 0.0f : (mat.TextureWeight > 1.0f ? 1.0f : mat.TextureWeight);
+        Vec3 outAlbedo = mat.Albedo * (1.0f - t) + texel * t;
+        return outAlbedo.Saturate();
     }
     Vec3 ComputeTransmittanceToLight(const Ray &shadow, float maxDist, float screenU, float screenV) const { /* :757-798 */
         if (scene.isVolumeScene) {
@@ -1503,7 +1542,7 @@ struct Renderer {
                     primaryHitSomething = true;
                     isSky = false;
                     if (!gbufValid) {
-                        Vec3 baseAlb = SampleAlbedo(rec.Mat);
+                        Vec3 baseAlb = SampleAlbedo(rec.Mat, rec.U, rec.V);
                         primary = PrimaryGBuffer{baseAlb, rec.N, rec.T, rec.ObjId, rec.SubId};
                         gbufValid = true;
                     }
@@ -1513,7 +1552,7 @@ struct Renderer {
                     Vec3 e = rec.Mat.Emission;
                     radiance = radiance + Vec3(beta.X * e.X, beta.Y * e.Y, beta.Z * e.Z);
                 }
-                Vec3 baseAlbedo = SampleAlbedo(rec.Mat);
+                Vec3 baseAlbedo = SampleAlbedo(rec.Mat, rec.U, rec.V);
                 if (rec.Mat.Transparency > 0.0f) {
                     if (mirrorDepth >= P.max_mirror_bounces) break;
                     Vec3 n = rec.N;
@@ -1885,7 +1924,7 @@ YO_API void *yo_create(const ycge_config *cfg) {
     r->tone.aeMin = cfg->params.ae_min; r->tone.aeMax = cfg->params.ae_max; r->tone.toneSaturation = cfg->params.saturation; r->tone.toneVibrance = cfg->params.vibrance;
     r->fbW = cfg->fb_w; r->fbH = cfg->fb_h; r->ss = cfg->ss < 1 ? 1 : cfg->ss;
     r->Alloc();
-    r->scene.meshes = &r->meshes; r->scene.volumes = &r->volumes;
+    r->scene.meshes = &r->meshes; r->scene.volumes = &r->volumes; r->scene.textures = &r->textures;
     return r;
 }
 YO_API void yo_destroy(void *h) { delete (Renderer *)h; }
@@ -1907,6 +1946,19 @@ YO_API int yo_volume_upload(void *h, int id, const ycge_volume *v) {
     vg->FromAbi(v);
     ((Renderer *)h)->volumes[id] = vg;
     return 0;
+}
+YO_API int yo_texture_upload(void *h, int id, int w, int hh, const uint32_t *rgba) {
+    auto t = std::make_shared<Texture>();
+    t->width = w; t->height = hh;
+    if (rgba && w > 0 && hh > 0) t->pixels.assign(rgba, rgba + (size_t)w * hh);
+    ((Renderer *)h)->textures[id] = t;
+    return 0;
+}
+YO_API void yo_texture_sample(int w, int hh, const uint32_t *rgba, float u, float v, float *out3) {
+    Texture t;
+    t.width = w; t.height = hh; t.pixels.assign(rgba, rgba + (size_t)w * hh);
+    Vec3 c = t.SampleBilinear(u, v);
+    out3[0] = c.X; out3[1] = c.Y; out3[2] = c.Z;
 }
 YO_API int yo_scene_upload(void *h, const ycge_scene *s) {
     Renderer *r = (Renderer *)h;

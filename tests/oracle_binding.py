@@ -34,6 +34,9 @@ def load_oracle():
         o.yo_mesh_upload_soa.argtypes = [vp, C.c_int, vp]
         o.yo_volume_upload.argtypes = [vp, C.c_int, vp]
         o.yo_scene_upload.argtypes = [vp, vp]
+        o.yo_texture_upload.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+        o.yo_texture_sample.argtypes = [C.c_int, C.c_int, vp, C.c_float, C.c_float, vp]
+        o.yo_texture_sample.restype = None
         o.yo_lights_update.argtypes = [vp, C.c_int, vp]
         o.yo_globals_update.argtypes = [vp, vp, vp, vp, C.c_float]
         o.yo_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
@@ -112,6 +115,9 @@ class Oracle:
                 assert self.o.yo_mesh_upload_triangles(self.h, i, len(tris), _ptr(tris), C.byref(m.material)) == 0
         for i in range(scene.n_volumes):
             assert self.o.yo_volume_upload(self.h, i, scene.volume(i)) == 0
+        for i in range(scene.n_textures):
+            t = scene.texture(i)
+            assert self.o.yo_texture_upload(self.h, i, t.shape[1], t.shape[0], _ptr(t)) == 0
         flat = scene.flat
         if use_host_trees:
             assert self.o.yo_scene_upload(self.h, flat) == 0

@@ -103,6 +103,9 @@ LIVE = [  # scene, fb_w, fb_h, ss, frames, pose
     ("knot:60x16", 48, 14, 4, 2, api.BENCH_POSE),
     ("voxel_world:64x64", 48, 14, 4, 2, None),
     ("cornell", 1, 1, 1, 2, None),           # minimum size: 1x2 pixels
+    ("texture_gallery", 64, 18, 3, 2, None),  # SampleAlbedo + Texture.SampleBilinear on rects, box faces, a triangle, a mesh, glass
+    ("texture_gallery", 48, 14, 2, 2, ((1.2, 1.4, -0.6), 0.5, -0.3)),
+    ("texture_test", 40, 12, 2, 2, ((0.6, 0.4, 0.0), 0.25, -0.2)),   # BuildTextureTestScene (Scenes.cs:337-358), stand-in image
 ]
 
 
@@ -327,6 +330,41 @@ def test_ansi_stream_through_the_host_framebuffer():
     assert stream.count(b"\xe2\x96\x80") == 300  # U+2580 per cell
     a.close()
     b.close()
+
+
+def test_texture_upload_through_the_c_abi_and_errors():
+    """ycge_texture_upload by hand: a material that names a texture that was never uploaded is an error; replacing the
+    pixels changes the picture; the scene's own textures give the oracle's picture."""
+    lib = api.load_lib()
+    s = api.HostScene("texture_test")
+    cfg = api.Config()
+    cfg.fb_w, cfg.fb_h, cfg.ss = 24, 8, 2
+    lib.ycge_default_params(C.byref(cfg.params))
+    ctx = C.c_void_p()
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == 0
+    assert lib.ycge_scene_upload(ctx, s.flat) != 0
+    assert b"texture" in lib.ycge_last_error(ctx)
+    t = s.texture(0)
+    assert lib.ycge_texture_upload(ctx, 0, t.shape[1], t.shape[0], t.ctypes.data) == 0
+    assert lib.ycge_texture_upload(ctx, -1, 1, 1, t.ctypes.data) != 0
+    assert lib.ycge_scene_upload(ctx, s.flat) == 0
+    pose = ((0.6, 0.4, 0.0), 0.25, -0.2)
+    lib.ycge_set_camera(ctx, (C.c_float * 3)(*pose[0]), pose[1], pose[2])
+    a = np.empty((8, 24), api.CELL_DTYPE)
+    assert lib.ycge_render_frame(ctx, a.ctypes.data, 0) == 0
+    o = Oracle(s, 24, 8, 2)
+    o.set_camera(*pose)
+    assert_cells_equal(a, o.render_frame(threads=2), "hand-uploaded texture")
+    white = np.full((3, 5), 0xFFFFFFFF, np.uint32)
+    assert lib.ycge_texture_upload(ctx, 0, 5, 3, white.ctypes.data) == 0
+    assert lib.ycge_scene_upload(ctx, s.flat) == 0
+    lib.ycge_reset_history(ctx)
+    b = np.empty((8, 24), api.CELL_DTYPE)
+    assert lib.ycge_render_frame(ctx, b.ctypes.data, 0) == 0
+    assert (a["fg"] != b["fg"]).any()
+    lib.ycge_destroy(ctx)
+    o.close()
+    s.close()
 
 
 def test_errors_are_loud():

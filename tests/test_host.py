@@ -9,7 +9,7 @@ from oracle_binding import Oracle
 
 SCENES = {  # name -> (objects, lights)   Scenes.cs:269-406, MeshScenes.cs:108-143
     "cornell": (8, 1), "mirror_spheres": (4, 2), "cylinders_disks_triangles": None, "boxes": (4, 2), "volume_grid_test": None,
-    "bunny": (2, 2), "teapot": (2, 2), "cow": (2, 2),
+    "bunny": (2, 2), "teapot": (2, 2), "cow": (2, 2), "texture_gallery": (6, 2),
 }
 
 
@@ -147,3 +147,31 @@ def test_vg01_world_file_round_trip(tmp_path):
         api.HostScene("voxel_world_file:" + bad)
     with pytest.raises(Exception, match="not found"):
         api.HostScene("voxel_world_file:" + str(tmp_path / "missing.vg01"))
+
+
+def test_texture_test_scene_and_png_decoder(tmp_path):
+    """BuildTextureTestScene (Scenes.cs:337-358): one textured box, ambient 0.5, no lights.  new Texture(path) decodes through
+    OpenCV in the reference (ImreadModes.Color, BGR2RGBA: Texture.cs:25-49); the mirror's zlib-only PNG decoder must give the
+    same pixels as an independent decoder for every colour type and row filter PNG writers emit."""
+    s = api.HostScene("texture_test")
+    assert s.name == "texture_test-standin" and s.n_textures == 1 and s.counts()["objects"] == 1 and s.counts()["lights"] == 0
+    m = s.flat.contents.materials[s.flat.contents.objects[0].mat_a]
+    assert (m.tex_id, m.tex_weight, m.uv_scale) == (0, 1.0, 1.0) and list(m.albedo) == [0.5, 0.5, 0.5]
+    s.close()
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, size=(19, 23, 4), dtype=np.uint8)
+    base[:, :12] = (base[:, :12] // 64) * 64  # flat runs make the writer pick different row filters
+    for mode in ("RGB", "RGBA", "L", "LA", "P"):
+        im = Image.fromarray(base, "RGBA").convert(mode)
+        d = tmp_path / mode
+        d.mkdir()
+        im.save(str(d / "image.png"))
+        rgb = np.asarray(im.convert("RGB")).astype(np.uint32)
+        want = rgb[..., 0] | (rgb[..., 1] << 8) | (rgb[..., 2] << 16) | np.uint32(255 << 24)
+        t = api.HostScene("texture_test", asset_dir=str(d))
+        assert t.name == "texture_test"
+        assert np.array_equal(t.texture(0), want), mode
+        t.set_texture(0, want[:5, :7])
+        assert t.texture(0).shape == (5, 7)
+        t.close()

@@ -264,3 +264,37 @@ def test_dotnet_sort_restatement(oracle_lib):
     pay = np.arange(8, dtype=np.int32)
     oracle_lib.yo_dotnet_sort_floats(keys.ctypes.data, pay.ctypes.data, 8)
     assert pay.tolist() == [1, 3, 5, 7, 0, 2, 4, 6]
+
+
+def test_texture_sample_bilinear_known_answers():
+    """Texture.SampleBilinear (Renderer/Texture.cs:143-162): fraction wrap, (size - 1) scaling, modulo neighbour, byte/255f
+    texels, two lerps, saturate -- transcribed independently with numpy binary32 scalars."""
+    from oracle_binding import load_oracle
+    o = load_oracle()
+    F = np.float32
+    rng = np.random.default_rng(7)
+    w, h = 13, 7
+    px = rng.integers(0, 1 << 32, size=(h, w), dtype=np.uint64).astype(np.uint32)
+
+    def texel(x, y):
+        v = int(px[y, x])
+        return [F(v & 255) / F(255.0), F((v >> 8) & 255) / F(255.0), F((v >> 16) & 255) / F(255.0)]
+
+    def sample(u, v):
+        u, v = F(u), F(v)
+        u = F(u - np.floor(u)); v = F(v - np.floor(v))
+        fx, fy = F(u * F(w - 1)), F(v * F(h - 1))
+        x0, y0 = int(np.floor(fx)), int(np.floor(fy))
+        x1, y1 = (x0 + 1) % w, (y0 + 1) % h
+        tx, ty = F(fx - F(x0)), F(fy - F(y0))
+        lerp = lambda a, b, t: [F(F(a[k] * F(F(1.0) - t)) + F(b[k] * t)) for k in range(3)]
+        c = lerp(lerp(texel(x0, y0), texel(x1, y0), tx), lerp(texel(x0, y1), texel(x1, y1), tx), ty)
+        return [min(max(x, F(0.0)), F(1.0)) for x in c]
+
+    uv = [(0.0, 0.0), (1.0, 1.0), (0.5, 0.5), (-0.25, 2.75), (0.99999994, 0.99999994), (1e-8, -1e-8), (12.0 / 12.0, 3.0 / 6.0), (1.0 / 12.0, 5.0 / 6.0)]
+    uv += [tuple(x) for x in rng.uniform(-3.0, 3.0, size=(200, 2))]
+    out = (C.c_float * 3)()
+    for u, v in uv:
+        o.yo_texture_sample(w, h, px.ctypes.data, C.c_float(u), C.c_float(v), out)
+        want = sample(u, v)
+        assert [bits(float(x)) for x in out] == [bits(float(x)) for x in want], (u, v)

@@ -28,6 +28,8 @@ CASES = [
     ("teapot", "teapot", 48, 14, 2, 2, api.BENCH_POSE),
     ("knot", "knot:60x16", 40, 12, 4, 2, api.BENCH_POSE),
     ("voxel_world", "voxel_world:64x64", 40, 12, 2, 2, None),
+    ("texture_gallery", "texture_gallery", 48, 14, 2, 2, None),
+    ("texture_test", "texture_test", 40, 12, 2, 2, ((0.6, 0.4, 0.0), 0.25, -0.2)),
 ]
 
 
@@ -59,7 +61,10 @@ def render_case(scene_name, fb_w, fb_h, ss, frames, pose, threads):
 
 if __name__ == "__main__":
     dst = os.path.join(ROOT, "tests", "golden")
+    only = set(sys.argv[1:])
     for name, scene, fb_w, fb_h, ss, frames, pose in CASES:
+        if only and name not in only:
+            continue
         out = render_case(scene, fb_w, fb_h, ss, frames, pose, threads=os.cpu_count() or 1)
         path = os.path.join(dst, f"oracle_{name}.npz")
         np.savez_compressed(path, **out)

@@ -116,7 +116,7 @@ PTR_CELLS, PTR_LOG_SAMPLES = 0, 1
 # every symbol include/ycge.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
-    "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
+    "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_texture_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
     "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
     "ycge_render_frames_async", "ycge_wait", "ycge_pipeline_config", "ycge_submit_frame", "ycge_frame_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
     "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
@@ -149,6 +149,7 @@ def load_lib() -> C.CDLL:
         lib.ycge_mesh_upload_triangles.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
         lib.ycge_volume_upload.argtypes = [vp, C.c_int32, vp]
         lib.ycge_scene_upload.argtypes = [vp, vp]
+        lib.ycge_texture_upload.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
         lib.ycge_lights_update.argtypes = [vp, C.c_int32, vp]
         lib.ycge_globals_update.argtypes = [vp, vp, vp, vp, C.c_float]
         lib.ycge_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
@@ -206,6 +207,10 @@ def load_host() -> C.CDLL:
         h.ycgeh_scene_mesh.argtypes = [vp, C.c_int]
         h.ycgeh_scene_mesh.restype = C.POINTER(MeshSoa)
         h.ycgeh_scene_n_volumes.argtypes = [vp]
+        h.ycgeh_scene_n_textures.argtypes = [vp]
+        h.ycgeh_scene_texture.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        h.ycgeh_scene_texture.restype = C.POINTER(C.c_uint32)
+        h.ycgeh_scene_set_texture.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
         h.ycgeh_scene_volume.argtypes = [vp, C.c_int]
         h.ycgeh_scene_volume.restype = C.POINTER(Volume)
         h.ycgeh_scene_mesh_triangles.argtypes = [vp, C.c_int]
@@ -296,6 +301,22 @@ class HostScene:
     @property
     def n_meshes(self) -> int:
         return self._h.ycgeh_scene_n_meshes(self.handle)
+
+    @property
+    def n_textures(self) -> int:
+        return self._h.ycgeh_scene_n_textures(self.handle)
+
+    def texture(self, i: int) -> np.ndarray:
+        """Texture i as an (h, w) uint32 array in the reference's int[] pixel layout (byte 0 = R; Texture.cs:81-90)."""
+        w, hh = C.c_int(), C.c_int()
+        p = self._h.ycgeh_scene_texture(self.handle, i, C.byref(w), C.byref(hh))
+        return np.ctypeslib.as_array(p, shape=(hh.value, w.value)).copy()
+
+    def set_texture(self, i: int, rgba: np.ndarray):
+        """Replace texture i (before a renderer is created), e.g. with an image decoded by the caller."""
+        a = np.ascontiguousarray(rgba, np.uint32)
+        if self._h.ycgeh_scene_set_texture(self.handle, i, a.shape[1], a.shape[0], _ptr(a)) != 0:
+            raise ValueError(self._h.ycgeh_last_error().decode())
 
     @property
     def n_volumes(self) -> int:

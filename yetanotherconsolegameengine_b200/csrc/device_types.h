@@ -62,6 +62,9 @@ struct DevObject {
 
 struct DevLight { float pos[3]; float color[3]; float intensity; float pad; };
 
+// Renderer/Texture.cs (static image): RGBA bytes, row-major, row 0 first (Texture.cs:81-90)
+struct DevTexture { const uchar4 *px; int w, h, pad; };
+
 struct DevScene {
     const PairNode *nodes;
     const int *leaf_obj;       // leaf slot -> object index (BVH.leafObjIndex order)
@@ -70,6 +73,8 @@ struct DevScene {
     const DevMesh *meshes;
     const DevVolume *volumes;
     const DevLight *lights;
+    const DevTexture *textures; // indexed by the slot stored in the material's 4th vector; n_textures == 0: no material is textured
+    int n_textures;
     TreeRoot root;
     int n_lights;
     int is_volume_scene;

@@ -50,6 +50,10 @@ struct MeshStore {
     ycge_material material;
     int n_tris = 0;
 };
+struct TextureStore {
+    DevBuf<uchar4> px;
+    int w = 0, h = 0;
+};
 struct VolumeStore {
     DevBuf<uint8_t> vox;
     DevBuf<int> raw_mat, raw_meta; // kept until the scene (and so the material indices) is known
@@ -89,6 +93,8 @@ struct ycge_ctx {
     // scene
     std::map<int, std::unique_ptr<MeshStore>> meshes;
     std::map<int, std::unique_ptr<VolumeStore>> volumes;
+    std::map<int, std::unique_ptr<TextureStore>> textures;
+    DevBuf<DevTexture> s_textures;
     DevBuf<PairNode> s_nodes;
     DevBuf<int> s_leaf;
     DevBuf<DevObject> s_objects;
@@ -920,6 +926,24 @@ YCGE_API int ycge_volume_upload(ycge_ctx *c, int32_t id, const ycge_volume *v) {
     return 0;
 }
 
+// ---- textures ----------------------------------------------------------------------------------------------
+YCGE_API int ycge_texture_upload(ycge_ctx *c, int32_t id, int32_t w, int32_t h, const uint32_t *rgba) {
+    if (!c || id < 0 || w < 0 || h < 0 || ((size_t)w * h > 0 && !rgba)) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if ((size_t)w * h > (size_t)0x7fffffff) return fail(c, YCGE_ERR_LIMIT, "texture larger than 2^31 texels (the reference indexes with int)");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    std::unique_ptr<TextureStore> t(new TextureStore());
+    t->w = w; t->h = h;
+    if ((size_t)w * h > 0) {
+        CK(c, t->px.alloc((size_t)w * h));
+        CK(c, cudaMemcpyAsync(t->px.p, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    c->textures[id] = std::move(t);
+    c->have_scene = false; // the texture table is rebuilt by ycge_scene_upload
+    return 0;
+}
+
 // ---- scene -------------------------------------------------------------------------------------------------
 static bool object_bounds(ycge_ctx *c, const ycge_object &o, Aabb &box, float cen[3]) {
     const float *p = o.p;
@@ -964,11 +988,26 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) {
     c->have_scene = false;
     // materials: the scene's table, then one entry per uploaded mesh
     std::vector<float4> mats;
+    std::vector<DevTexture> dtex;
+    std::map<int, int> tex_slot;
+    bool tex_missing = false;
     auto push_mat = [&](const ycge_material &m) {
         mats.push_back(make_float4(m.albedo[0], m.albedo[1], m.albedo[2], m.reflectivity));
         mats.push_back(make_float4(m.emission[0], m.emission[1], m.emission[2], m.transparency));
         mats.push_back(make_float4(m.transmission[0], m.transmission[1], m.transmission[2], m.ior));
-        int tex = m.tex_id; float texf; memcpy(&texf, &tex, 4);
+        int tex = -1; // slot in the device texture table (DiffuseTexture == null: -1)
+        if (m.tex_id >= 0) {
+            auto it = c->textures.find(m.tex_id);
+            if (it == c->textures.end()) tex_missing = true;
+            else {
+                if (!tex_slot.count(m.tex_id)) {
+                    tex_slot[m.tex_id] = (int)dtex.size();
+                    dtex.push_back(DevTexture{it->second->px.p, it->second->w, it->second->h, 0});
+                }
+                tex = tex_slot[m.tex_id];
+            }
+        }
+        float texf; memcpy(&texf, &tex, 4);
         mats.push_back(make_float4(m.specular, texf, m.tex_weight, m.uv_scale));
     };
     for (int i = 0; i < s->n_materials; i++) push_mat(s->materials[i]);
@@ -1049,6 +1088,7 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) {
         leaf = tree.leaf_index;
     }
     for (int v : leaf) if (v < 0 || v >= s->n_objects) return fail(c, YCGE_ERR_INVALID, "leafObjIndex out of range");
+    if (tex_missing) return fail(c, YCGE_ERR_INVALID, "material references a texture id that was not uploaded (ycge_texture_upload)");
     std::vector<DevLight> lights((size_t)s->n_lights);
     for (int i = 0; i < s->n_lights; i++) {
         for (int k = 0; k < 3; k++) { lights[i].pos[k] = s->lights[i].pos[k]; lights[i].color[k] = s->lights[i].color[k]; }
@@ -1061,8 +1101,10 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) {
     CK(c, c->s_meshes.upload(dmeshes, c->stream));
     CK(c, c->s_volumes.upload(dvols, c->stream));
     CK(c, c->s_lights.upload(lights, c->stream));
+    CK(c, c->s_textures.upload(dtex, c->stream));
     DevScene &ds = c->ds;
     memset(&ds, 0, sizeof ds);
+    ds.textures = c->s_textures.p; ds.n_textures = (int)dtex.size();
     ds.nodes = c->s_nodes.p; ds.leaf_obj = c->s_leaf.p; ds.objects = c->s_objects.p; ds.materials = c->s_materials.p;
     ds.meshes = c->s_meshes.p; ds.volumes = c->s_volumes.p; ds.lights = c->s_lights.p; ds.root = root;
     ds.n_lights = s->n_lights; ds.is_volume_scene = s->is_volume_scene;

@@ -7,12 +7,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <limits>
 #include <map>
 #include <set>
 #include <sstream>
 #include <unordered_map>
 #include <unordered_set>
+#include <zlib.h>
 
 namespace ycge_host {
 
@@ -404,6 +406,72 @@ BVH::BVH(const std::vector<std::shared_ptr<Hittable>> &objects) { // BVH.cs:29-9
     ycge::build_reference_tree(items, 4, false, tree);
 }
 
+// ---- Texture (Renderer/Texture.cs:25-49,:81-90) -----------------------------------------------------------------
+// The reference decodes through OpenCV; a PNG of the kind its assets use (8 bit, non-interlaced; grey, RGB, palette, with
+// or without alpha) is decoded here with zlib alone.  ImreadModes.Color drops alpha; BGR2RGBA then sets it to 255.
+Texture::Texture(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f.good()) throw std::invalid_argument("Failed to load image: " + path);
+    std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    if (d.size() < 8 || memcmp(d.data(), sig, 8) != 0) throw std::invalid_argument("not a PNG file: " + path);
+    auto be32 = [&](size_t o) { return ((uint32_t)d[o] << 24) | ((uint32_t)d[o + 1] << 16) | ((uint32_t)d[o + 2] << 8) | d[o + 3]; };
+    int depth = 0, ctype = 0, interlace = 0;
+    std::vector<unsigned char> idat, plte;
+    for (size_t o = 8; o + 12 <= d.size();) {
+        uint32_t len = be32(o);
+        std::string tag((const char *)&d[o + 4], 4);
+        if (o + 12 + len > d.size()) throw std::invalid_argument("truncated PNG: " + path);
+        const unsigned char *body = &d[o + 8];
+        if (tag == "IHDR") { width = (int)be32(o + 8); height = (int)be32(o + 12); depth = body[8]; ctype = body[9]; interlace = body[12]; }
+        else if (tag == "PLTE") plte.assign(body, body + len);
+        else if (tag == "IDAT") idat.insert(idat.end(), body, body + len);
+        else if (tag == "IEND") break;
+        o += 12 + len;
+    }
+    if (width <= 0 || height <= 0 || depth != 8 || interlace != 0) throw std::invalid_argument("unsupported PNG (need 8 bit, non-interlaced): " + path);
+    const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!ch) throw std::invalid_argument("unsupported PNG colour type: " + path);
+    const size_t stride = (size_t)width * ch;
+    std::vector<unsigned char> raw((stride + 1) * height);
+    uLongf rawLen = (uLongf)raw.size();
+    if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) throw std::invalid_argument("corrupt PNG data: " + path);
+    std::vector<unsigned char> img(stride * height);
+    for (int y = 0; y < height; y++) { // PNG filters 0..4 (None, Sub, Up, Average, Paeth)
+        const unsigned char *in = &raw[(stride + 1) * y];
+        unsigned char *out = &img[stride * y];
+        const unsigned char *up = y ? &img[stride * (y - 1)] : nullptr;
+        const int ft = in[0];
+        for (size_t i = 0; i < stride; i++) {
+            int a = i >= (size_t)ch ? out[i - ch] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)ch) ? up[i - ch] : 0, x = in[1 + i], pr = 0;
+            if (ft == 1) pr = a; else if (ft == 2) pr = b; else if (ft == 3) pr = (a + b) >> 1;
+            else if (ft == 4) { int pp = a + b - c, pa = std::abs(pp - a), pb = std::abs(pp - b), pc = std::abs(pp - c); pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            else if (ft != 0) throw std::invalid_argument("corrupt PNG filter: " + path);
+            out[i] = (unsigned char)(x + pr);
+        }
+    }
+    pixels.resize((size_t)width * height);
+    for (size_t i = 0; i < pixels.size(); i++) {
+        const unsigned char *q = &img[i * ch];
+        unsigned r, g, b;
+        if (ctype == 0 || ctype == 4) r = g = b = q[0];
+        else if (ctype == 3) { const size_t k = 3 * (size_t)q[0]; const bool ok = k + 2 < plte.size(); r = ok ? plte[k] : 0; g = ok ? plte[k + 1] : 0; b = ok ? plte[k + 2] : 0; }
+        else { r = q[0]; g = q[1]; b = q[2]; }
+        pixels[i] = r | (g << 8) | (b << 16) | (255u << 24);
+    }
+}
+Texture Texture::Procedural(int w, int h) {
+    Texture t;
+    t.width = w; t.height = h; t.pixels.resize((size_t)w * h);
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        unsigned r = (unsigned)(x * 255 / std::max(1, w - 1)), g = (unsigned)(y * 255 / std::max(1, h - 1));
+        unsigned b = (((x / 3) + (y / 2)) & 1) ? 230u : 25u;
+        if ((x * 7 + y * 13) % 11 == 0) { r = 255 - r; b = 128; }
+        t.pixels[(size_t)y * w + x] = r | (g << 8) | (b << 16) | (255u << 24);
+    }
+    return t;
+}
+
 // ---- scene factories: Scenes/Scenes.cs --------------------------------------------------------------------------
 namespace Scenes {
 std::shared_ptr<Scene> BuildTestScene() { // :11-35
@@ -482,6 +550,49 @@ std::shared_ptr<Scene> BuildBoxesShowcase() { // :385-406
     s->Add(std::make_shared<Box>(Vec3(1.0, 0.0, -3.0), Vec3(2.4, 2.0, -1.8), white, 0.0f, 0.0f));
     s->Lights.push_back(PointLight(Vec3(-2.0, 3.0, -2.0), Vec3(1.0, 0.95, 0.9), 70.0f));
     s->Lights.push_back(PointLight(Vec3(2.0, 2.5, -4.2), Vec3(0.9, 0.95, 1.0), 50.0f));
+    s->BackgroundTop = Vec3(0.6, 0.8, 1.0); s->BackgroundBottom = Vec3(0.95, 0.98, 1.0);
+    s->Update(0.0f);
+    return s;
+}
+std::shared_ptr<Scene> BuildTextureTestScene() { // :337-358
+    auto s = std::make_shared<Scene>(); s->Name = "texture_test";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.5f);
+    std::shared_ptr<Texture> tex;
+    std::ifstream probe(MeshScenes::AssetDir + "/image.png");
+    if (probe.good()) tex = std::make_shared<Texture>(MeshScenes::AssetDir + "/image.png");
+    else { tex = std::make_shared<Texture>(Texture::Procedural(96, 144)); s->Name = "texture_test-standin"; }
+    Material texMat(Vec3(0.5, 0.5, 0.5), 0.0, 0.0, Vec3());
+    texMat.DiffuseTexture = s->AddTexture(tex); texMat.TextureWeight = 1.0; texMat.UVScale = 1.0;
+    s->Add(std::make_shared<Box>(Vec3(-0.5, -0.5, -2.5), Vec3(0.5, 0.5, -1.5), Constant(texMat), 0.00f, 0.00f));
+    s->BackgroundTop = Vec3(0.0, 0.0, 0.0); s->BackgroundBottom = Vec3(0.0, 0.0, 0.0);
+    s->Update(0.0f);
+    return s;
+}
+std::shared_ptr<Scene> BuildTextureGallery() { // test scene, not in the reference: all U,V-carrying primitives, blended weights, tiling
+    auto s = std::make_shared<Scene>(); s->Name = "texture_gallery";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.05f);
+    int t0 = s->AddTexture(std::make_shared<Texture>(Texture::Procedural(37, 23)));
+    int t1 = s->AddTexture(std::make_shared<Texture>(Texture::Procedural(8, 5)));
+    Material floorM(Vec3(0.9, 0.9, 0.9), 0.05, 0.0, Vec3()); floorM.DiffuseTexture = t0; floorM.TextureWeight = 0.6; floorM.UVScale = 3.5;
+    Material boxM(Vec3(0.5, 0.5, 0.5), 0.0, 0.0, Vec3()); boxM.DiffuseTexture = t1; boxM.TextureWeight = 1.0; boxM.UVScale = 1.5;
+    Material triM(Vec3(0.9, 0.25, 0.25), 0.1, 0.0, Vec3()); triM.DiffuseTexture = t0; triM.TextureWeight = 1.0; triM.UVScale = 0.35;
+    Material wallM(Vec3(0.2, 0.3, 0.8), 0.0, 0.0, Vec3()); wallM.DiffuseTexture = t1; wallM.TextureWeight = 2.5; wallM.UVScale = 0.0; // clamps: weight -> 1, tiles -> 1e-6
+    Material meshM(Vec3(0.1, 0.8, 0.3), 0.1, 0.0, Vec3()); meshM.DiffuseTexture = t0; meshM.TextureWeight = 0.85; meshM.UVScale = 2.0;
+    Material glassM(Vec3(0.9, 0.95, 1.0), 0.0, 0.1, Vec3(), 0.8, 1.45, Vec3(0.9, 1.0, 0.9)); glassM.DiffuseTexture = t1; glassM.TextureWeight = 0.5; glassM.UVScale = 1.0;
+    s->Add(XZRect(-6.0f, 6.0f, -8.0f, 2.0f, 0.0f, Constant(floorM), 0.05f, 0.0f));
+    s->Add(std::make_shared<Box>(Vec3(-1.9, 0.0, -3.4), Vec3(-0.7, 1.2, -2.2), Constant(boxM), 0.0f, 0.0f));
+    s->Add(std::make_shared<Triangle>(Vec3(0.2, 0.0, -3.6), Vec3(1.5, 1.6, -3.0), Vec3(-0.5, 0.9, -2.6), triM));
+    s->Add(XYRect(-3.0f, 3.0f, 0.0f, 2.5f, -5.0f, Constant(wallM), 0.0f, 0.0f));
+    s->Add(YZRect(0.0f, 2.0f, -5.0f, -1.0f, 3.0f, Constant(glassM), 0.0f, 0.1f));
+    ObjData knot = MeshScenes::ProceduralKnot(40, 10);
+    std::vector<Triangle> tris;
+    for (size_t f = 0; f + 2 < knot.faces.size(); f += 3) {
+        auto P = [&](int i) { Vec3 p = knot.positions[(size_t)i]; return Vec3(1.6f + 0.22f * p.X, 0.9f + 0.22f * p.Y, -2.4f + 0.22f * p.Z); };
+        tris.push_back(Triangle(P(knot.faces[f]), P(knot.faces[f + 1]), P(knot.faces[f + 2]), meshM));
+    }
+    s->Add(std::make_shared<Mesh>(tris, Vec3(0.9f, 0.2f, -3.1f), Vec3(2.3f, 1.6f, -1.7f)));
+    s->Lights.push_back(PointLight(Vec3(-2.0, 3.0, -1.0), Vec3(1.0, 0.95, 0.9), 60.0f));
+    s->Lights.push_back(PointLight(Vec3(2.0, 2.5, -0.5), Vec3(0.9, 0.95, 1.0), 40.0f));
     s->BackgroundTop = Vec3(0.6, 0.8, 1.0); s->BackgroundBottom = Vec3(0.95, 0.98, 1.0);
     s->Update(0.0f);
     return s;
@@ -760,6 +871,8 @@ std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
     if (name == "cylinders_disks_triangles") return Scenes::BuildCylindersDisksAndTriangles();
     if (name == "boxes") return Scenes::BuildBoxesShowcase();
     if (name == "volume_grid_test") return Scenes::BuildVolumeGridTestScene();
+    if (name == "texture_test") return Scenes::BuildTextureTestScene();
+    if (name == "texture_gallery") return Scenes::BuildTextureGallery();
     if (name == "cow") return MeshScenes::BuildCowScene();
     if (name == "bunny") return MeshScenes::BuildBunnyScene();
     if (name == "teapot") return MeshScenes::BuildTeapotScene();
@@ -875,10 +988,14 @@ CudaRaytraceRenderer::CudaRaytraceRenderer(Framebuffer &framebuffer, Scene &scen
     UploadScene(scene); // scene.RebuildBVH()  :107
 }
 CudaRaytraceRenderer::~CudaRaytraceRenderer() { ycge_destroy(ctx); }
+void CudaRaytraceRenderer::UploadTexture(int id, const Texture &t) {
+    Check(ycge_texture_upload(ctx, id, t.width, t.height, t.pixels.data()), "ycge_texture_upload");
+}
 void CudaRaytraceRenderer::UploadScene(Scene &scene) {
     std::shared_ptr<Scene> alias(&scene, [](Scene *) {});
     if (!scene.bvh) scene.RebuildBVH(); // (the reference rebuilds unconditionally; the tree is a pure function of Objects)
     auto flat = Flatten(alias);
+    for (size_t i = 0; i < scene.Textures.size(); i++) UploadTexture((int)i, *scene.Textures[i]);
     for (size_t i = 0; i < flat->mesh_soa.size(); i++) Check(ycge_mesh_upload_soa(ctx, (int)i, &flat->mesh_soa[i]), "ycge_mesh_upload_soa");
     for (size_t i = 0; i < flat->vols.size(); i++) Check(ycge_volume_upload(ctx, (int)i, &flat->vols[i]), "ycge_volume_upload");
     Check(ycge_scene_upload(ctx, &flat->scene), "ycge_scene_upload");
@@ -1015,6 +1132,18 @@ YH_API void ycgeh_scene_destroy(void *h) { delete (SceneHandle *)h; }
 YH_API const ycge_scene *ycgeh_scene_flat(void *h) { return &((SceneHandle *)h)->flat->scene; }
 YH_API int ycgeh_scene_n_meshes(void *h) { return (int)((SceneHandle *)h)->flat->mesh_soa.size(); }
 YH_API const ycge_mesh_soa *ycgeh_scene_mesh(void *h, int i) { return &((SceneHandle *)h)->flat->mesh_soa[i]; }
+YH_API int ycgeh_scene_n_textures(void *h) { return (int)((SceneHandle *)h)->scene->Textures.size(); }
+YH_API const uint32_t *ycgeh_scene_texture(void *h, int i, int *w, int *hh) {
+    const Texture &t = *((SceneHandle *)h)->scene->Textures[(size_t)i];
+    *w = t.width; *hh = t.height;
+    return t.pixels.data();
+}
+YH_API int ycgeh_scene_set_texture(void *h, int i, int w, int hh, const uint32_t *rgba) { // e.g. an image decoded by the caller
+    Scene &s = *((SceneHandle *)h)->scene;
+    if (i < 0 || i >= (int)s.Textures.size() || w <= 0 || hh <= 0 || !rgba) { yh_error = "bad texture index or size"; return -1; }
+    s.Textures[(size_t)i] = std::make_shared<Texture>(w, hh, rgba);
+    return 0;
+}
 YH_API int ycgeh_scene_n_volumes(void *h) { return (int)((SceneHandle *)h)->flat->vols.size(); }
 YH_API const ycge_volume *ycgeh_scene_volume(void *h, int i) { return &((SceneHandle *)h)->flat->vols[i]; }
 YH_API const float *ycgeh_scene_mesh_triangles(void *h, int i) { // A,B,C per triangle exactly as the loader produced them

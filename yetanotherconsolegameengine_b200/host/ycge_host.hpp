@@ -46,6 +46,18 @@ struct Material { // RayTracing/Material.cs:5-61
     ycge_material ToAbi() const;
 };
 
+// Renderer/Texture.cs, static images only: int[] pixels = RGBA bytes (byte 0 = R), row-major, row 0 first (:81-90).
+// Sampling (SampleBilinear :143-162) runs on the GPU; Material.DiffuseTexture is the texture's index in Scene::Textures.
+class Texture {
+  public:
+    int width = 0, height = 0;
+    std::vector<uint32_t> pixels;
+    Texture() {}
+    Texture(int w, int h, const uint32_t *rgba) : width(w), height(h), pixels(rgba, rgba + (size_t)w * h) {}
+    explicit Texture(const std::string &pngPath);       // Cv2.ImRead(Color) + BGR2RGBA (:25-49): 8-bit non-interlaced PNG, alpha := 255
+    static Texture Procedural(int w, int h);            // deterministic stand-in when the asset is missing (tests, labelled in Scene::Name)
+};
+
 // Func<Vec3, Vec3, float, Material> as data: the closed set used by the reference (Scenes/Scenes.cs:408-428)
 struct MaterialFunc {
     Material a, b;
@@ -182,6 +194,8 @@ class Scene { // Scenes/Scene.cs
   public:
     std::vector<std::shared_ptr<Hittable>> Objects;
     std::vector<PointLight> Lights;
+    std::vector<std::shared_ptr<Texture>> Textures; // Material.DiffuseTexture indexes this list
+    int AddTexture(std::shared_ptr<Texture> t) { Textures.push_back(t); return (int)Textures.size() - 1; }
     Vec3 BackgroundTop = Vec3(0.6, 0.8, 1.0), BackgroundBottom = Vec3(1.0, 1.0, 1.0);
     AmbientLight Ambient;
     float DefaultFovDeg = 45.0f;
@@ -220,6 +234,8 @@ std::shared_ptr<Scene> BuildMirrorSpheresOnChecker();
 std::shared_ptr<Scene> BuildCylindersDisksAndTriangles();
 std::shared_ptr<Scene> BuildBoxesShowcase();
 std::shared_ptr<Scene> BuildVolumeGridTestScene();
+std::shared_ptr<Scene> BuildTextureTestScene(); // assets/image.png if present, else a procedural stand-in (labelled in Scene::Name)
+std::shared_ptr<Scene> BuildTextureGallery();   // NOT in the reference: every primitive kind that carries U,V, textured (tests)
 } // namespace Scenes
 namespace MeshScenes { // Scenes/MeshScenes.cs
 extern std::string AssetDir; // where cow.obj / stanford-bunny.obj / teapot.obj / xyzrgb_dragon.obj are looked up
@@ -267,6 +283,7 @@ class CudaRaytraceRenderer : public IConsoleRenderer {
     void SetFov(float fovDeg) override;
     void TryFlipAndBlit(Framebuffer &fb) override;
     void Resize(Framebuffer &fb, int superSample) override;
+    void UploadTexture(int id, const Texture &t);   // new Texture(path) -> ycge_texture_upload
     void UploadScene(Scene &scene);                 // scene switch (RaytraceEntity.SwitchToScene :234-246)
     void RenderCells(ycge_cell *out);               // TryFlipAndBlit without the Chexel unpack (headless)
     ycge_ctx *Context() { return ctx; }
