@@ -254,7 +254,10 @@ YCGE_API int ycge_globals_update(ycge_ctx *ctx, const float bg_top[3], const flo
 /* ---- per frame -------------------------------------------------------------------------- */
 YCGE_API int ycge_set_camera(ycge_ctx *ctx, const float pos[3], float yaw, float pitch);         /* SetCamera  RaytraceRenderer.cs:140-148 */
 YCGE_API int ycge_set_fov(ycge_ctx *ctx, float fov_deg);                                          /* SetFov     RaytraceRenderer.cs:150-153 */
-YCGE_API int ycge_reset_history(ycge_ctx *ctx);                                                   /* scene.HasDynamicTextures / scene switch */
+YCGE_API int ycge_reset_history(ycge_ctx *ctx);
+/* Two forms of the trace kernel with bit-identical results: 0 = one thread per pixel path, 1 (default) = ray stream (every
+ * lane carries one ray per round through a single traversal, finished lanes are refilled with new pixels at once). */
+YCGE_API int ycge_set_trace_variant(ycge_ctx *ctx, int32_t variant);                                                   /* scene.HasDynamicTextures / scene switch */
 /* TryFlipAndBlit (RaytraceRenderer.cs:157-267): synchronous; writes tile_rows*fb_w cells (the ctx's tile;
  * the whole frame when unsharded) into caller-owned host memory, row stride `stride_cells` (0 => fb_w). */
 YCGE_API int ycge_render_frame(ycge_ctx *ctx, ycge_cell *out, int32_t stride_cells);

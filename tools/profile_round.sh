@@ -10,7 +10,7 @@ python bench.py --steps 32 --warmup 4 > gpurun_out/bench_$TAG.json 2> gpurun_out
 kill $SMI
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'trace_kernel|atrous|taa_kernel|cells_kernel|exposure' -s 40 -c 12 -f -o gpurun_out/prof_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'trace|atrous|taa_kernel|cells_kernel|exposure' -s 40 -c 12 -f -o gpurun_out/prof_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out
 tail -c 1500 gpurun_out/bench_$TAG.json

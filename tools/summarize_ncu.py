@@ -46,6 +46,7 @@ if os.path.exists(rep):
             "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
+    want += [h for h in hdr if "issue_stalled" in h and h.endswith("per_warp_active.pct")]
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
     seen = OrderedDict()
     for r in rr[2:]:

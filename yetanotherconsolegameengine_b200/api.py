@@ -117,7 +117,7 @@ PTR_CELLS, PTR_LOG_SAMPLES = 0, 1
 ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
     "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_texture_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
-    "ycge_set_camera", "ycge_set_fov", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
+    "ycge_set_camera", "ycge_set_fov", "ycge_set_trace_variant", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
     "ycge_render_frames_async", "ycge_wait", "ycge_pipeline_config", "ycge_submit_frame", "ycge_frame_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
     "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
     "ycge_frame_finish", "ycge_ansi_emit", "ycge_device_ptr",
@@ -154,6 +154,7 @@ def load_lib() -> C.CDLL:
         lib.ycge_globals_update.argtypes = [vp, vp, vp, vp, C.c_float]
         lib.ycge_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
         lib.ycge_set_fov.argtypes = [vp, C.c_float]
+        lib.ycge_set_trace_variant.argtypes = [vp, C.c_int32]
         lib.ycge_reset_history.argtypes = [vp]
         lib.ycge_render_frame.argtypes = [vp, vp, C.c_int32]
         lib.ycge_render_frame_stats.argtypes = [vp, vp, C.c_int32]
@@ -426,6 +427,10 @@ class CudaRaytraceRenderer:
 
     def reset_history(self):
         self._ck(self._lib.ycge_reset_history(self.ctx))
+
+    def set_trace_variant(self, variant: int):
+        """0: one thread per pixel path; 1 (default): ray stream with lane refill.  Bit-identical results."""
+        self._ck(self._lib.ycge_set_trace_variant(self.ctx, variant))
 
     def lights_update(self, lights):
         """Per-frame light changes without re-uploading geometry (DayNightCycle.cs:80-83): [(pos3, color3, intensity), ...]"""

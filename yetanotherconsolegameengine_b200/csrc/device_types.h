@@ -101,8 +101,9 @@ struct TraceParams {
     unsigned long long seed_salt;
 };
 
-struct TraceCounters { // device-side, 8 x u64, zeroed at the start of every frame
+struct TraceCounters { // device-side, zeroed at the start of every frame
     unsigned long long rays, top_nodes, mesh_nodes, leaf_refs, tris, prims, dda, stack_overflow;
+    unsigned long long next_tile; // trace_stream_kernel: the next 8x4 pixel tile to hand out (low 32 bits)
 };
 struct TraceTotals { unsigned long long rays_total; }; // never reset: lets a benchmark difference it around a timed region
 

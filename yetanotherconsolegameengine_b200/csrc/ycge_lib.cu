@@ -1,6 +1,7 @@
 // ycge_lib.cu — the C ABI of include/ycge.h: context, scene flattening into HBM, per-frame launch sequence.
 // Product code: no CPU fallback.  Every entry point fails loudly (negative status + message) when CUDA is not usable.
 #include "post.cuh"
+#include "trace_stream.cuh"
 #include "bvh_build.hpp"
 
 #include <algorithm>
@@ -117,6 +118,8 @@ struct ycge_ctx {
     bool debug_rays = false;
     float ansi_th[5] = {0, 0, 0, 0, 0};
     int inplace_ctas_per_launch = 0, inplace_ctas_static = 0;
+    int trace_variant = 1;  // 0: one thread per pixel path (trace_kernel), 1: ray stream with lane refill (trace_stream_kernel)
+    int stream_ctas = 0, stream_ctas_stats = 0;
     // resumable à-trous state of the frame in flight (a sharded tile pauses before every in-place pass so that the caller
     // can move the boundary rows between ranks)
     struct Denoise {
@@ -451,9 +454,25 @@ int frame_begin_impl(ycge_ctx *c) {
         tp.diffuse_bounces = c->P.diffuse_bounces; tp.max_mirror_bounces = c->P.max_mirror_bounces; tp.max_refractions = c->P.max_refractions;
         tp.mirror_threshold = c->P.mirror_threshold; tp.eps = c->P.eps; tp.sigma_rad = c->P.diffuse_sigma_deg * (3.14159274f / 180.0f); // :460
         tp.seed_salt = c->P.seed_salt;
-        dim3 grid(div_up(W, 16), div_up(b - a, 8));
-        if (c->want_stats) trace_kernel<true><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
-        else trace_kernel<false><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
+        if (c->trace_variant == 1) { // ray stream: persistent warps, as many CTAs as fit the GPU at once
+            if (c->stream_ctas <= 0) {
+                int occ = 0, occ_s = 0;
+                cudaDeviceProp prop;
+                CK(c, cudaGetDeviceProperties(&prop, c->device));
+                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_stream_kernel<false>, 128, 0));
+                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, trace_stream_kernel<true>, 128, 0));
+                c->stream_ctas = std::max(1, occ * prop.multiProcessorCount);
+                c->stream_ctas_stats = std::max(1, occ_s * prop.multiProcessorCount);
+            }
+            const int n_tiles = div_up(W, 8) * div_up(b - a, 4);
+            const int refill_min = getenv("YCGE_STREAM_REFILL") ? atoi(getenv("YCGE_STREAM_REFILL")) : 32; // development aid; see trace_stream.cuh
+            if (c->want_stats) trace_stream_kernel<true><<<std::min(c->stream_ctas_stats, div_up(n_tiles, 4)), 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min);
+            else trace_stream_kernel<false><<<std::min(c->stream_ctas, div_up(n_tiles, 4)), 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min);
+        } else {
+            dim3 grid(div_up(W, 16), div_up(b - a, 8));
+            if (c->want_stats) trace_kernel<true><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
+            else trace_kernel<false><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
+        }
         launches++;
     }
     CK(c, cudaEventRecord(c->ev[1], s));
@@ -736,6 +755,7 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     std::unique_ptr<ycge_ctx> c(new ycge_ctx());
     c->device = cfg->device;
     c->P = cfg->params;
+    if (const char *e = getenv("YCGE_TRACE_VARIANT")) c->trace_variant = atoi(e) ? 1 : 0; // development aid
     if (c->P.atrous_iterations > 8) return fail(nullptr, YCGE_ERR_INVALID, "atrous_iterations > 8 not supported");
     CK(nullptr, cudaSetDevice(c->device));
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1141,6 +1161,11 @@ YCGE_API int ycge_globals_update(ycge_ctx *c, const float bg_top[3], const float
 YCGE_API int ycge_set_camera(ycge_ctx *c, const float pos[3], float yaw, float pitch) {
     if (!c || !pos) return fail(c, YCGE_ERR_INVALID, "bad argument");
     c->cam[0] = pos[0]; c->cam[1] = pos[1]; c->cam[2] = pos[2]; c->yaw = yaw; c->pitch = pitch;
+    return 0;
+}
+YCGE_API int ycge_set_trace_variant(ycge_ctx *c, int32_t variant) {
+    if (!c || variant < 0 || variant > 1) return fail(c, YCGE_ERR_INVALID, "trace variant must be 0 (thread per pixel path) or 1 (ray stream)");
+    c->trace_variant = variant;
     return 0;
 }
 YCGE_API int ycge_set_fov(ycge_ctx *c, float fov_deg) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); c->fov = fov_deg; return 0; }
