@@ -172,6 +172,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the ONE JSON line; NCCL's banner goes to stderr
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = max(1, world)
@@ -294,12 +295,27 @@ def main():
                 r1.render_frame_stats()
                 st_events = r1.stats()
                 r1.close()
+            # `value`: the asynchronous path.  Default: frames in parallel (FRONT on row tiles, BACK + FINISH of whole frames
+            # round-robin over the ranks, sharding.FrameParallelRenderer); YCGE_MULTI=rowpipe: row tiles with the wavefront
+            # handed from rank to rank and frames pipelined over the ranks (sharding.ShardedRenderer.render_pipelined)
+            mode = os.environ.get("YCGE_MULTI", "frames")
             pipelined = sr.peer_handoff and not os.environ.get("YCGE_NO_PIPELINE")
-            if pipelined:
-                sr.render_pipelined(max(3, args.warmup))
-            else:
-                for _ in range(max(3, args.warmup)):
+            fp, front_tiles = None, None
+            if mode == "frames":
+                tr = [None] * n
+                for _ in range(3):
                     sr.render_device()
+                torch.cuda.synchronize()
+                dist.all_gather_object(tr, float(b.r.stats()["ms_trace"]))
+                front_tiles = sharding.balanced_tiles(tiles, tr, fb_h, per_row_ms=0.001)
+                fp = sharding.FrameParallelRenderer(scene, rank, n, fb_w, fb_h, ss, local_rank, tiles=front_tiles, back_slots=int(os.environ.get("YCGE_BACK_SLOTS", "2")))
+                fp.SetCamera(*pose)
+                run = lambda k: fp.render(k)
+            elif pipelined:
+                run = lambda k: sr.render_pipelined(k)
+            else:
+                run = lambda k: [sr.render_device() for _ in range(k)]
+            run(max(3, args.warmup))
             torch.cuda.synchronize()
             st0 = b.r.stats()
             sampler = ClockSampler(local_rank)
@@ -308,17 +324,21 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
             ev0.record(stream)
-            if pipelined:  # frames pipelined over the ranks; the stream joins its finishing side stream at the end
-                sr.render_pipelined(args.steps)
-            else:
-                for _ in range(args.steps):
-                    sr.render_device()
+            run(args.steps)
             ev1.record(stream)
             torch.cuda.synchronize()
             dist.barrier()
             ms_local = ev0.elapsed_time(ev1)
-            st1 = b.r.stats()
             clocks = sampler.stop()
+            fp_stage = None
+            if fp is not None:
+                fs = fp.front.stats()
+                fp_stage = {"front_ms_trace": round(fs["ms_trace"], 3), "front_ms_taa": round(fs["ms_taa"], 3)}
+            # per-stage times of the lock-step row-tile path (the e2e path below)
+            for _ in range(2):
+                sr.render_device()
+            torch.cuda.synchronize()
+            st1 = b.r.stats()
             stage_ms = {k: st1[k] for k in ("ms_trace", "ms_taa", "ms_atrous", "ms_atrous_chain", "ms_exposure", "ms_cells", "ms_total")}
             launches_per_frame = st1["kernel_launches"]
             # e2e: camera in, assembled cells out to pinned host memory on rank 0, every step
@@ -343,7 +363,7 @@ def main():
         # max over ranks of the device time; rays summed over ranks (halo rows are traced redundantly and counted as
         # work done — rays/frame of the UNSHARDED frame is what the metric divides by, so use the unsharded count)
         all_stage = [None] * n
-        dist.all_gather_object(all_stage, {k: round(v, 3) for k, v in stage_ms.items()})
+        dist.all_gather_object(all_stage, dict({k: round(v, 3) for k, v in stage_ms.items()}, **(fp_stage or {})))
         t = torch.tensor([ms_local, e2e_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
@@ -351,6 +371,8 @@ def main():
         dist.broadcast(rays_frame, 0)
         rays_timed = int(rays_frame[0]) * args.steps
         e2e_rays = int(rays_frame[0]) * args.steps
+        if fp is not None:
+            fp.close()
         sr.close()
     fps = args.steps / (ms / 1e3)
     mrays = rays_timed / (ms / 1e3) / 1e6
@@ -403,9 +425,11 @@ def main():
         line = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
-                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ((", %d frames in flight on the GPU (value, e2e_streaming); serial (e2e, stage_ms, roofline kernel time)" % slots) if n == 1 else (", peer hand-off" if peer_handoff else ", NCCL send/recv hand-off") + (", frames pipelined over ranks (value); lock-step (e2e)" if pipelined else "")),
+                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ((", %d frames in flight on the GPU (value, e2e_streaming); serial (e2e, stage_ms, roofline kernel time)" % slots) if n == 1 else (", frames in parallel: FRONT on row tiles, BACK + FINISH of whole frames round-robin over the ranks (value); row tiles in lock step" if mode == "frames" else
+                            (", frames pipelined over ranks (value); lock-step" if pipelined else "")) + (", peer hand-off (e2e)" if peer_handoff else ", NCCL send/recv hand-off (e2e)")),
                            "l2": "per-frame working set (8 float4 image planes = %d MB) exceeds the 126 MB L2; no explicit flush" % (W * H * 128 // (1 << 20))},
-                "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff, "frame_pipelining": pipelined, "tiles_cell_rows": [t[1] for t in tiles]} if n > 1 else {}),
+                "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff, "frame_pipelining": pipelined, "multi_gpu_mode": mode, "tiles_cell_rows": [t[1] for t in tiles],
+                                              "front_tiles_cell_rows": [t[1] for t in front_tiles] if front_tiles else None} if n > 1 else {}),
                 "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "SetCamera + TryFlipAndBlit per step, synchronous (the drop-in call; latency of one frame)"},
                 **({"e2e_streaming": streaming, "serial_schedule": serial, "frames_in_flight": slots} if n == 1 else {}),

@@ -328,12 +328,31 @@ YCGE_API int ycge_frame_begin(ycge_ctx *ctx);
 YCGE_API int ycge_frame_halo(ycge_ctx *ctx, ycge_halo *out);  /* 1: an in-place pass is pending, 0: none (negative: error) */
 YCGE_API int ycge_frame_inplace(ycge_ctx *ctx);
 YCGE_API int ycge_frame_finish(ycge_ctx *ctx);
+/* Frame-parallel sharding (asynchronous path, sharding.FrameParallelRenderer).  Row tiles cannot shorten the wavefront
+ * of the in-place à-trous pass (every row depends on the rows above), but nothing of a frame's à-trous passes feeds the
+ * next frame (see ycge_pipeline_config).  So only the FRONT of a frame (trace + TAA, RaytraceRenderer.cs:181-216) is cut
+ * into row tiles -- ycge_frame_front on a row-tile ctx: the tile plus ONE halo row for the 3x3 luma clamp, no à-trous
+ * halo -- and the BACK (à-trous passes, exposure samples) and the FINISH (ordered exposure sum, cells) of whole frames go
+ * round-robin over the ranks: frame f's tiles of history + guides (YCGE_PTR_HIST/GND/GAS rows of every rank) are sent into
+ * a back slot of rank f mod N (ycge_back_ptr), which runs ycge_back_denoise and, once the exposure state of frame f-1 has
+ * arrived in YCGE_PTR_EXPOSURE, ycge_back_finish, then passes the state on.  Bit-identical to the unsharded frame. */
+YCGE_API int ycge_frame_front(ycge_ctx *ctx);
+YCGE_API int ycge_back_config(ycge_ctx *ctx, int32_t n_slots);                       /* whole-frame ctx only */
+YCGE_API int ycge_back_ptr(ycge_ctx *ctx, int32_t slot, int32_t kind, void **ptr, size_t *bytes);
+YCGE_API int ycge_back_denoise(ycge_ctx *ctx, int32_t slot, void *cuda_stream);
+YCGE_API int ycge_back_finish(ycge_ctx *ctx, int32_t slot, void *cuda_stream);
 /* ANSITerminalRenderer.Render's byte stream (ANSITerminalRenderer.cs:86-153: cursor address per row, colour escapes only
  * where the 8-bit indices change, UTF-8 glyphs, final reset) for the cells of the last frame, produced on the device and
  * copied to `out` (at most `cap` bytes; *n_bytes receives the length).  The resize prologue ("ESC[2J ESC[H", :103-106)
  * is the host's.  For a row-tile ctx the stream covers the tile's rows and starts with unknown colour state. */
 YCGE_API int ycge_ansi_emit(ycge_ctx *ctx, uint8_t *out, size_t cap, size_t *n_bytes);
-typedef enum ycge_ptr_kind { YCGE_PTR_CELLS = 0, YCGE_PTR_LOG_SAMPLES = 1 } ycge_ptr_kind;
+typedef enum ycge_ptr_kind {
+    YCGE_PTR_CELLS = 0, YCGE_PTR_LOG_SAMPLES = 1,
+    YCGE_PTR_HIST = 2,      /* taaHistory of the last frame: float4 rgb + luma, full-frame layout x + y*hiW */
+    YCGE_PTR_GND = 3,       /* guides of the last frame: normalised normal + depth */
+    YCGE_PTR_GAS = 4,       /* guides of the last frame: albedo + sky flag */
+    YCGE_PTR_EXPOSURE = 5   /* ToneMapper state (16 bytes: aeExposure, effective exposure, logSum, count) */
+} ycge_ptr_kind;
 YCGE_API int ycge_device_ptr(ycge_ctx *ctx, int32_t kind, void **ptr, size_t *bytes);
 YCGE_API int ycge_set_stream(ycge_ctx *ctx, void *cuda_stream); /* run on the caller's stream (e.g. torch's current stream) */
 

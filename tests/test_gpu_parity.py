@@ -532,6 +532,70 @@ def test_row_tiles_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pos
     full.close()
 
 
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss,n_tiles,pose", [("boxes", 40, 24, 2, 3, None), ("knot:60x16", 48, 27, 4, 4, api.BENCH_POSE), ("voxel_world:64x64", 32, 18, 1, 5, None)])
+def test_front_tiles_plus_whole_frame_back_equal_the_unsharded_frame(scene, fb_w, fb_h, ss, n_tiles, pose):
+    """Frame-parallel sharding on one GPU: FRONT (trace + TAA) on row-tile contexts with a single halo row, the tiles' rows
+    of history + guides copied into a back slot of a whole-frame context, BACK (à-trous passes, exposure samples) and
+    FINISH there -- what sharding.FrameParallelRenderer does with NCCL between ranks.  Cells of every frame and the
+    exposure recursion must equal the unsharded renderer's bit for bit, with two back slots used alternately."""
+    import torch
+    from yetanotherconsolegameengine_b200 import sharding
+    s = api.HostScene(scene)
+    ref = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    back = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    back.back_config(2)
+    tiles = [sharding.tile_rows(r, n_tiles, fb_h) for r in range(n_tiles)]
+    fronts = [api.CudaRaytraceRenderer(s, fb_w, fb_h, ss, tile_row0=t[0], tile_rows=t[1]) for t in tiles]
+    for r in [ref] + fronts:
+        if pose is not None:
+            r.SetCamera(*pose)
+    W, H = fb_w * ss, fb_h * 2 * ss
+    nbytes, row_bytes = W * H * 16, W * 16
+    kinds = (api.PTR_HIST, api.PTR_GND, api.PTR_GAS)
+    st = torch.cuda.Stream()
+    for f in range(5):
+        slot = f % 2
+        dst = [sharding.device_bytes(back.back_ptr(slot, k)[0], nbytes, 0) for k in kinds]
+        for fr, (row0, rows) in zip(fronts, tiles):
+            fr.frame_front()
+            fr.wait()
+            a, b = row0 * 2 * ss * row_bytes, (row0 + rows) * 2 * ss * row_bytes
+            for k, kind in enumerate(kinds):
+                src = sharding.device_bytes(fr.device_ptr(kind)[0], nbytes, 0)
+                dst[k][a:b].copy_(src[a:b])
+        torch.cuda.synchronize()
+        back.back_denoise(slot, st.cuda_stream)
+        back.back_finish(slot, st.cuda_stream)
+        st.synchronize()
+        got = sharding.device_bytes(*back.back_ptr(slot, api.PTR_CELLS), 0).cpu().numpy().view(api.CELL_DTYPE).reshape(fb_h, fb_w)
+        assert_cells_equal(got, ref.TryFlipAndBlit(), f"{scene}: frame {f + 1}, {n_tiles} front tiles + whole-frame back")
+    e_ref = ref.stats()["ae_exposure"]
+    e_got = sharding.device_bytes(*back.device_ptr(api.PTR_EXPOSURE), 0).cpu().numpy().view(np.float32)[0]
+    assert np.float32(e_ref).view(np.uint32) == np.float32(e_got).view(np.uint32)
+    for r in [ref, back] + fronts:
+        r.close()
+    s.close()
+
+
+def test_frame_parallel_renderer_on_one_rank():
+    """sharding.FrameParallelRenderer with world = 1: the orchestration (back slots, streams, FINISH chain, batches) without
+    the collectives; tools/multigpu_check.py runs it over real ranks."""
+    import torch
+    from yetanotherconsolegameengine_b200 import sharding
+    s = api.HostScene("boxes")
+    ref = api.CudaRaytraceRenderer(s, 40, 24, 2)
+    with torch.cuda.device(0):
+        fp = sharding.FrameParallelRenderer(s, 0, 1, 40, 24, 2, 0, back_slots=2)
+        got = fp.render(5, collect=True) + fp.render(3, collect=True)
+        torch.cuda.synchronize()
+        assert len(got) == 8
+        for f, g in enumerate(got):
+            assert_cells_equal(fp.cells_host(g), ref.TryFlipAndBlit(), f"frame-parallel frame {f + 1}")
+        fp.close()
+    ref.close()
+    s.close()
+
+
 def test_stashed_finish_equals_the_synchronous_frame():
     """The frame-pipelining path on one GPU (world = 1): frames are rendered back to back on one stream and finished from
     their stash slots on a side stream (ordered exposure sum + cells), out of step with the rendering.  Same cells."""

@@ -43,6 +43,23 @@ if sr.peer_handoff or world == 1:
             same = sr.assemble(g).tobytes() == ref.tobytes()
             ok &= same
             print(f"frame {frames + f + 1}: pipelined x{world} {'==' if same else '!='} unsharded", flush=True)
+# the frame-parallel asynchronous path: FRONT on row tiles, BACK + FINISH of whole frames round-robin over the ranks; its own
+# contexts, so it starts again at frame 1 (compared with a fresh unsharded renderer), two batches
+fp = sharding.FrameParallelRenderer(scene, rank, world, fb_w, fb_h, ss, local, back_slots=2)
+fp.SetCamera(*pose)
+n_fp = 2 * world + 3
+got = fp.render(n_fp, collect=True) + fp.render(world + 1, collect=True)
+torch.cuda.synchronize()
+if rank == 0:
+    full2 = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local)
+    full2.SetCamera(*pose)
+    for f, g in enumerate(got):
+        ref = full2.TryFlipAndBlit()
+        same = fp.cells_host(g).tobytes() == ref.tobytes()
+        ok &= same
+        print(f"frame {f + 1}: frame-parallel x{world} {'==' if same else '!='} unsharded", flush=True)
+    full2.close()
+fp.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 sr.close()

@@ -111,7 +111,7 @@ CELL_DTYPE = np.dtype([("glyph", "<u2"), ("fg16", "u1"), ("bg16", "u1"), ("fg_an
 assert CELL_DTYPE.itemsize == 32
 
 DBG_RAYS, DBG_HDR, DBG_ALBEDO_SKY, DBG_NORMAL_DEPTH, DBG_TAA, DBG_DENOISED, DBG_PRIM_ID, DBG_LOG_SAMPLES = range(8)
-PTR_CELLS, PTR_LOG_SAMPLES = 0, 1
+PTR_CELLS, PTR_LOG_SAMPLES, PTR_HIST, PTR_GND, PTR_GAS, PTR_EXPOSURE = 0, 1, 2, 3, 4, 5
 
 # every symbol include/ycge.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -120,7 +120,7 @@ ABI_SYMBOLS = [
     "ycge_set_camera", "ycge_set_fov", "ycge_set_trace_variant", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
     "ycge_render_frames_async", "ycge_wait", "ycge_pipeline_config", "ycge_submit_frame", "ycge_frame_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
     "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
-    "ycge_frame_finish", "ycge_ansi_emit", "ycge_device_ptr",
+    "ycge_frame_finish", "ycge_frame_front", "ycge_back_config", "ycge_back_ptr", "ycge_back_denoise", "ycge_back_finish", "ycge_ansi_emit", "ycge_device_ptr",
     "ycge_set_stream", "ycge_debug_read", "ycge_get_stats", "ycge_get_frame_counter", "ycge_rng_kat",
 ]
 
@@ -174,6 +174,11 @@ def load_lib() -> C.CDLL:
         lib.ycge_peer_export.argtypes = [vp, C.POINTER(Peer)]
         lib.ycge_peer_attach.argtypes = [vp, C.POINTER(Peer), C.POINTER(Peer), C.c_int32]
         lib.ycge_frame_inplace.argtypes = [vp]
+        lib.ycge_frame_front.argtypes = [vp]
+        lib.ycge_back_config.argtypes = [vp, C.c_int32]
+        lib.ycge_back_ptr.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        lib.ycge_back_denoise.argtypes = [vp, C.c_int32, vp]
+        lib.ycge_back_finish.argtypes = [vp, C.c_int32, vp]
         lib.ycge_device_ptr.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
         lib.ycge_ansi_emit.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.ycge_set_stream.argtypes = [vp, vp]
@@ -492,6 +497,24 @@ class CudaRaytraceRenderer:
 
     def frame_inplace(self):
         self._ck(self._lib.ycge_frame_inplace(self.ctx))
+
+    # -- frame-parallel sharding (ycge.h: FRONT on row tiles, BACK of whole frames round-robin over the ranks)
+    def frame_front(self):
+        self._ck(self._lib.ycge_frame_front(self.ctx))
+
+    def back_config(self, n_slots: int):
+        self._ck(self._lib.ycge_back_config(self.ctx, n_slots))
+
+    def back_ptr(self, slot: int, kind: int):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.ycge_back_ptr(self.ctx, slot, kind, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def back_denoise(self, slot: int, cuda_stream: int):
+        self._ck(self._lib.ycge_back_denoise(self.ctx, slot, C.c_void_p(cuda_stream)))
+
+    def back_finish(self, slot: int, cuda_stream: int):
+        self._ck(self._lib.ycge_back_finish(self.ctx, slot, C.c_void_p(cuda_stream)))
 
     def ansi_stream(self) -> bytes:
         """ANSITerminalRenderer.Render's byte stream for the last frame, produced on the device (ycge_ansi_emit)."""

@@ -166,6 +166,17 @@ struct ycge_ctx {
         cudaEvent_t front_done = nullptr, fin_done = nullptr, host_done = nullptr;
         ~Slot() { if (st) cudaStreamDestroy(st); if (front_done) cudaEventDestroy(front_done); if (fin_done) cudaEventDestroy(fin_done); if (host_done) cudaEventDestroy(host_done); }
     };
+    // Frame-parallel BACK over ranks (ycge_back_*): a rank receives whole TAA'd frames (history + guides, assembled from every
+    // rank's FRONT tile) into a back slot and runs the à-trous passes, the exposure samples and the FINISH of that frame.
+    struct BackSlot {
+        DevBuf<float4> hist, gnd, gas, sa, sb, pre;
+        DevBuf<float> logs;
+        DevBuf<ycge_cell> cells;
+        const float4 *denoised = nullptr;
+    };
+    std::vector<std::unique_ptr<BackSlot>> back_slots;
+    struct IoOverride { const float4 *gnd, *gas; DevBuf<float4> *pre; float *logs; size_t n_logs; cudaStream_t stream; int ticket_slot; };
+    const IoOverride *io = nullptr;          // set for the duration of ycge_back_denoise
     std::vector<std::unique_ptr<Slot>> slots; // slots[k-1] for k >= 1; slot 0 is the ctx's own buffers and (unpipelined) stream
     cudaStream_t st0 = nullptr;               // slot 0's back stream when pipelining
     cudaEvent_t front_done0 = nullptr, fin_done0 = nullptr, host_done0 = nullptr;
@@ -383,7 +394,7 @@ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 // ---- the per-frame launch sequence ----------------------------------------------------------------------------
 int denoise_run(ycge_ctx *c);
 void halo_rows(const ycge_ctx *c, int &lo, int &a, int &slo, int &sa);
-int frame_begin_impl(ycge_ctx *c) {
+int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
     if (!c->have_scene) return fail(c, YCGE_ERR_NO_SCENE, "Scene BVH not built; call ycge_scene_upload() after populating the scene");
     if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_begin called twice without ycge_frame_finish");
     CK(c, cudaSetDevice(c->device));
@@ -417,7 +428,7 @@ int frame_begin_impl(ycge_ctx *c) {
     const int K = std::max(1, c->P.atrous_iterations);
     const int ty0 = c->tile_row0 * 2 * ss, ty1 = (c->tile_row0 + c->tile_rows) * 2 * ss;
     std::vector<int> halo_after(K + 1, 0); // halo_after[k] = rows still needed around the tile after pass k-1 (k=0: TAA output)
-    for (int k = K - 1; k >= 0; k--) halo_after[k] = halo_after[k + 1] + 2 * (1 << k);
+    if (!front_only) for (int k = K - 1; k >= 0; k--) halo_after[k] = halo_after[k + 1] + 2 * (1 << k); // FRONT only: the passes run elsewhere
     auto range = [&](int halo, int &a, int &b) { a = std::max(0, ty0 - halo); b = std::min(H, ty1 + halo); };
 
     // slot and guide set of this frame; `parity` selects the guide set the trace kernel writes (img.gnd/gas[parity])
@@ -488,6 +499,13 @@ int frame_begin_impl(ycge_ctx *c) {
         c->taa_valid = true;
     }
     CK(c, cudaEventRecord(c->ev[2], s));
+    if (front_only) { // the frame's à-trous passes, exposure and cells run on another rank (ycge_back_*); taa.CommitCamera :266
+        c->launches_last = launches;
+        c->last_gset = gset;
+        memcpy(c->last_cam, c->snap_cam, sizeof c->last_cam); c->last_yaw = c->snap_yaw; c->last_pitch = c->snap_pitch;
+        CK(c, cudaGetLastError());
+        return 0;
+    }
     { // K3: the reference's ping-pong including its in-place iteration (:648-719), resumable (see denoise_run)
         ycge_ctx::Denoise &d = c->dn;
         d.phys[0] = c->hist.p; d.phys[1] = sv.sa; d.phys[2] = sv.sb;
@@ -509,8 +527,10 @@ int denoise_run(ycge_ctx *c) {
     const int W = c->W, H = c->H, ss = c->ss;
     const EdgeDiv ed = c->edge_div;
     const bool fast = c->fast_div;
-    const float4 *gnd = gnd_of(c, d.parity), *gas = gas_of(c, d.parity); // d.parity = guide set of the frame
-    const SlotView sv = slot_view(c, c->cur_slot);
+    const float4 *gnd = c->io ? c->io->gnd : gnd_of(c, d.parity), *gas = c->io ? c->io->gas : gas_of(c, d.parity); // d.parity = guide set of the frame
+    SlotView sv = slot_view(c, c->io ? 0 : c->cur_slot);
+    if (c->io) { sv.pre = c->io->pre; sv.logs = c->io->logs; sv.n_logs = c->io->n_logs; s = c->io->stream; }
+    const int ticket_slot = c->io ? c->io->ticket_slot : c->cur_slot;
     DevBuf<float4> &pre = *sv.pre;
     int launches = 0;
     auto range = [&](int halo, int &a, int &b) { a = std::max(0, d.ty0 - halo); b = std::min(H, d.ty1 + halo); };
@@ -579,7 +599,7 @@ int denoise_run(ycge_ctx *c) {
             // A frame that has the GPU to itself uses the static form (rows in blockIdx order, launches sized so that all CTAs
             // of one are co-resident); frames that overlap (pipelined) use the persistent ticket form, which waits for nothing
             // that is not already running.
-            const bool use_static = !c->pipelined && !getenv("YCGE_CHAIN_PERSISTENT");
+            const bool use_static = !c->pipelined && !c->io && !getenv("YCGE_CHAIN_PERSISTENT");
             const int rows_per_launch = std::max(1, c->inplace_ctas_static * YCGE_AIC_WARPS / step);
             CK(c, cudaEventRecord(c->ev[7], s));
             auto launch_chain = [&](cudaStream_t st, int r0, int r1, bool peer) {
@@ -599,9 +619,9 @@ int denoise_run(ycge_ctx *c) {
                 }
                 const dim3 g(std::min(div_up(warps, YCGE_AIC_WARPS), c->inplace_ctas_per_launch));
                 const int tk = (st == c->aux) ? 1 : 0; // launches that may overlap need separate ticket counters
-                q.ticket = c->tickets.p + 16 * (tk ? 1 : 2 * c->cur_slot + 2); q.ticket_base = c->ticket_base_of(tk, c->cur_slot);
+                q.ticket = c->tickets.p + 16 * (tk ? 1 : 2 * ticket_slot + 2); q.ticket_base = c->ticket_base_of(tk, ticket_slot);
                 q.n_chains = (unsigned int)warps;
-                c->ticket_advance(tk, c->cur_slot, (unsigned int)warps + g.x * YCGE_AIC_WARPS); // every warp's last ticket is a miss
+                c->ticket_advance(tk, ticket_slot, (unsigned int)warps + g.x * YCGE_AIC_WARPS); // every warp's last ticket is a miss
                 if (fast && peer) atrous_chain_kernel<true, true><<<g, t, 0, st>>>(q);
                 else if (fast) atrous_chain_kernel<true, false><<<g, t, 0, st>>>(q);
                 else if (peer) atrous_chain_kernel<false, true><<<g, t, 0, st>>>(q);
@@ -668,14 +688,14 @@ void halo_rows(const ycge_ctx *c, int &lo, int &a, int &slo, int &sa) {
     }
 }
 
-int finish_launch(ycge_ctx *c, const float *logs, const float4 *den, cudaStream_t s, bool timed) {
+int finish_launch(ycge_ctx *c, const float *logs, const float4 *den, cudaStream_t s, bool timed, ycge_cell *cells = nullptr) {
     ExposureParams ep;
     ep.tone_exposure = c->P.tone_exposure; ep.ae_key = c->P.ae_key; ep.ae_speed = c->P.ae_speed; ep.ae_min = c->P.ae_min; ep.ae_max = c->P.ae_max;
     ep.auto_exposure = c->P.auto_exposure;
     exposure_finish_kernel<<<1, 1024, 0, s>>>(logs, c->sw * c->sh, ep, c->expo.p);
     if (timed) CK(c, cudaEventRecord(c->ev[5], s));
     CellArgs ca;
-    ca.den = den; ca.expo = c->expo.p; ca.cells = c->cells.p; ca.W = c->W; ca.fbW = c->fbW; ca.ss = c->ss;
+    ca.den = den; ca.expo = c->expo.p; ca.cells = cells ? cells : c->cells.p; ca.W = c->W; ca.fbW = c->fbW; ca.ss = c->ss;
     ca.cy0 = c->tile_row0; ca.cy1 = c->tile_row0 + c->tile_rows;
     ca.gamma = c->P.tone_gamma; ca.saturation = c->P.saturation; ca.vibrance = c->P.vibrance;
     for (int k = 0; k < 5; k++) ca.th[k] = c->ansi_th[k];
@@ -1272,6 +1292,69 @@ YCGE_API int ycge_frame_inplace(ycge_ctx *c) {
     return denoise_run(c);
 }
 
+// ---- frame-parallel sharding: FRONT on row tiles, BACK of whole frames round-robin over the ranks ------------------
+YCGE_API int ycge_frame_front(ycge_ctx *c) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (c->peers) return fail(c, YCGE_ERR_INVALID, "a ctx with attached peers runs whole frames (ycge_frame_begin)");
+    return frame_begin_impl(c, true);
+}
+YCGE_API int ycge_back_config(ycge_ctx *c, int32_t n_slots) {
+    if (!c || n_slots < 0 || n_slots > 16) return fail(c, YCGE_ERR_INVALID, "n_slots must be in [0,16]");
+    if (c->sharded) return fail(c, YCGE_ERR_INVALID, "the BACK runs on a whole-frame ctx");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaDeviceSynchronize());
+    c->back_slots.clear();
+    const size_t px = (size_t)c->W * c->H;
+    for (int k = 0; k < n_slots; k++) {
+        std::unique_ptr<ycge_ctx::BackSlot> b(new ycge_ctx::BackSlot());
+        CK(c, b->hist.alloc(px)); CK(c, b->gnd.alloc(px)); CK(c, b->gas.alloc(px)); CK(c, b->sa.alloc(px)); CK(c, b->sb.alloc(px));
+        CK(c, b->pre.alloc(px * 25));
+        CK(c, b->logs.alloc((size_t)c->sw * c->sh));
+        CK(c, b->cells.alloc((size_t)c->fbW * c->fbH));
+        CK(c, cudaMemset(b->sa.p, 0, px * sizeof(float4))); CK(c, cudaMemset(b->sb.p, 0, px * sizeof(float4)));
+        CK(c, cudaMemset(b->logs.p, 0, b->logs.n * sizeof(float)));
+        c->back_slots.push_back(std::move(b));
+    }
+    return 0;
+}
+YCGE_API int ycge_back_ptr(ycge_ctx *c, int32_t slot, int32_t kind, void **ptr, size_t *bytes) {
+    if (!c || !ptr || !bytes || slot < 0 || slot >= (int)c->back_slots.size()) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    ycge_ctx::BackSlot &b = *c->back_slots[slot];
+    switch (kind) {
+        case YCGE_PTR_CELLS: *ptr = b.cells.p; *bytes = b.cells.n * sizeof(ycge_cell); return 0;
+        case YCGE_PTR_LOG_SAMPLES: *ptr = b.logs.p; *bytes = b.logs.n * sizeof(float); return 0;
+        case YCGE_PTR_HIST: *ptr = b.hist.p; *bytes = b.hist.n * sizeof(float4); return 0;
+        case YCGE_PTR_GND: *ptr = b.gnd.p; *bytes = b.gnd.n * sizeof(float4); return 0;
+        case YCGE_PTR_GAS: *ptr = b.gas.p; *bytes = b.gas.n * sizeof(float4); return 0;
+        default: return fail(c, YCGE_ERR_INVALID, "unknown pointer kind");
+    }
+}
+YCGE_API int ycge_back_denoise(ycge_ctx *c, int32_t slot, void *cuda_stream) {
+    if (!c || slot < 0 || slot >= (int)c->back_slots.size()) return fail(c, YCGE_ERR_INVALID, "bad back slot");
+    if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "a frame is open on this ctx");
+    CK(c, cudaSetDevice(c->device));
+    ycge_ctx::BackSlot &b = *c->back_slots[slot];
+    ycge_ctx::IoOverride io = {b.gnd.p, b.gas.p, &b.pre, b.logs.p, b.logs.n, (cudaStream_t)cuda_stream, 32 + slot};
+    ycge_ctx::Denoise &d = c->dn;
+    const int K = std::max(1, c->P.atrous_iterations);
+    d.phys[0] = b.hist.p; d.phys[1] = b.sa.p; d.phys[2] = b.sb.p;
+    d.cur_id = 0; d.dst_id = 1; d.it = 0; d.K = K; d.parity = 0; d.ty0 = 0; d.ty1 = c->H; d.pending = false; d.early_reset = false;
+    for (int k = 0; k <= K; k++) d.halo_after[k] = 0;
+    c->io = &io;
+    c->launches_last = 0;
+    int rc = denoise_run(c);
+    c->io = nullptr;
+    b.denoised = c->denoised;
+    return rc;
+}
+YCGE_API int ycge_back_finish(ycge_ctx *c, int32_t slot, void *cuda_stream) {
+    if (!c || slot < 0 || slot >= (int)c->back_slots.size()) return fail(c, YCGE_ERR_INVALID, "bad back slot");
+    ycge_ctx::BackSlot &b = *c->back_slots[slot];
+    if (!b.denoised) return fail(c, YCGE_ERR_INVALID, "ycge_back_finish before ycge_back_denoise");
+    CK(c, cudaSetDevice(c->device));
+    return finish_launch(c, b.logs.p, b.denoised, (cudaStream_t)cuda_stream, false, b.cells.p);
+}
+
 YCGE_API int ycge_render_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
@@ -1401,6 +1484,10 @@ YCGE_API int ycge_device_ptr(ycge_ctx *c, int32_t kind, void **ptr, size_t *byte
     if (!c || !ptr || !bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if (kind == YCGE_PTR_CELLS) { *ptr = c->cells.p; *bytes = c->cells.n * sizeof(ycge_cell); return 0; }
     if (kind == YCGE_PTR_LOG_SAMPLES) { *ptr = c->logs.p; *bytes = c->logs.n * sizeof(float); return 0; }
+    if (kind == YCGE_PTR_HIST) { *ptr = c->hist.p; *bytes = c->hist.n * sizeof(float4); return 0; }
+    if (kind == YCGE_PTR_GND) { *ptr = gnd_of(c, c->last_gset); *bytes = (size_t)c->W * c->H * sizeof(float4); return 0; }
+    if (kind == YCGE_PTR_GAS) { *ptr = gas_of(c, c->last_gset); *bytes = (size_t)c->W * c->H * sizeof(float4); return 0; }
+    if (kind == YCGE_PTR_EXPOSURE) { *ptr = c->expo.p; *bytes = sizeof(ExposureState); return 0; }
     return fail(c, YCGE_ERR_INVALID, "unknown pointer kind");
 }
 

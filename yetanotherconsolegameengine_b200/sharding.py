@@ -248,3 +248,158 @@ class ShardedRenderer:
     def TryFlipAndBlit(self) -> Optional[np.ndarray]:
         g = self.render_device()
         return self.assemble(g) if self.rank == 0 else None
+
+
+class FrameParallelRenderer:
+    """Asynchronous path over N ranks, frames in parallel (ycge.h "Frame-parallel sharding").
+
+    Row tiles cannot shorten the wavefront of the in-place à-trous pass, and running it rank after rank leaves most GPUs
+    waiting.  But nothing of a frame's à-trous passes feeds the next frame: only the TAA history + guides, the exposure
+    scalar and the camera memory do.  So per frame f
+      FRONT   every rank traces + TAA-blends its row tile (+1 halo row) on its tile ctx            [all ranks, in step]
+      GATHER  the tiles' rows of history + guides go to rank f mod N ("root") into a back slot       [NCCL send/recv]
+      BACK    the root runs the à-trous passes and the exposure samples of the whole frame on its whole-frame ctx, on the
+              slot's own stream, while all ranks go on with the fronts of the next frames            [N frames in flight]
+      FINISH  in frame order around the ring: the root receives the exposure state of frame f-1 from rank (f-1) mod N,
+              runs the ordered exposure sum + cells, sends the cells to rank 0 and the state on to rank (f+1) mod N.
+    Every frame is bit-identical to the unsharded frame (tools/multigpu_check.py)."""
+
+    def __init__(self, scene: api.HostScene, rank: int, world: int, fb_w: int, fb_h: int, ss: int, device: int, tiles=None, back_slots: int = 2):
+        import torch.distributed as dist
+        self.dist, self.rank, self.world, self.device = dist, rank, world, device
+        self.fb_w, self.fb_h, self.ss = fb_w, fb_h, ss
+        self.tiles = list(tiles) if tiles is not None else [tile_rows(r, world, fb_h) for r in range(world)]
+        row0, rows = self.tiles[rank]
+        self.front = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device, tile_row0=row0, tile_rows=rows)
+        self.back = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device)
+        self.S = back_slots
+        self.back.back_config(back_slots)
+        self.main = torch.cuda.current_stream(device)
+        self.front.set_stream(self.main.cuda_stream)
+        self.s_back = [torch.cuda.Stream(device) for _ in range(back_slots)]
+        self.s_fin = torch.cuda.Stream(device)
+        self.ev_recv = [torch.cuda.Event() for _ in range(back_slots)]
+        self.ev_back = [torch.cuda.Event() for _ in range(back_slots)]
+        self.ev_fin = [torch.cuda.Event() for _ in range(back_slots)]
+        self.slot_used = [False] * back_slots
+        W, H = fb_w * ss, fb_h * 2 * ss
+        self.row_bytes = W * 16
+        self.n_px_bytes = W * H * 16
+        kinds = (api.PTR_HIST, api.PTR_GND, api.PTR_GAS)
+        self.slot_planes = [[device_bytes(self.back.back_ptr(k, kind)[0], self.n_px_bytes, device) for kind in kinds] for k in range(back_slots)]
+        self.slot_cells = [device_bytes(*self.back.back_ptr(k, api.PTR_CELLS), device) for k in range(back_slots)]
+        p, n = self.back.device_ptr(api.PTR_EXPOSURE)
+        self.expo = device_bytes(p, n, device)
+        self.cell_bytes = fb_w * fb_h * api.CELL_DTYPE.itemsize
+        self.out_ring = [torch.zeros(self.cell_bytes, dtype=torch.uint8, device=torch.device("cuda", device)) for _ in range(4)] if rank == 0 else None
+        self.frame = 0  # global frame index (0-based) of the next frame
+        self.pg_fin = None
+        if world > 1:
+            # two communicators: the gathers run in step with the fronts, the FINISH ring runs frames behind them
+            self.pg_fin = dist.new_group(list(range(world)))
+            t = torch.zeros(1, device=torch.device("cuda", device))
+            dist.all_reduce(t)
+            dist.all_reduce(t, group=self.pg_fin)
+            torch.cuda.synchronize(device)
+            # Open every point-to-point connection NOW, pair by pair, with nothing else in flight.  NCCL sets a connection up
+            # on first use with host-side rendezvous and device allocations; if that happens in the render loop while a
+            # send/recv kernel of the other communicator is already spinning on one of the two GPUs, the set-up waits for
+            # that kernel, the kernel for its peer, and the peer's host for the set-up: a deadlock (seen on 2 GPUs).
+            for grp, pairs in ((None, [(a, b) for a in range(world) for b in range(a + 1, world)]),
+                               (self.pg_fin, sorted({(min(r, (r + 1) % world), max(r, (r + 1) % world)) for r in range(world)} | {(0, r) for r in range(1, world)}))):
+                for a, b in pairs:
+                    if rank == a:
+                        dist.send(t, dst=b, group=grp)
+                        dist.recv(t, src=b, group=grp)
+                    elif rank == b:
+                        dist.recv(t, src=a, group=grp)
+                        dist.send(t, dst=a, group=grp)
+                    torch.cuda.synchronize(device)
+            dist.barrier()
+
+    def SetCamera(self, pos, yaw, pitch):
+        self.front.SetCamera(pos, yaw, pitch)
+
+    def _front_planes(self):
+        """This rank's history + guide planes of the frame just rendered (full-frame layout)."""
+        return [device_bytes(self.front.device_ptr(kind)[0], self.n_px_bytes, self.device) for kind in (api.PTR_HIST, api.PTR_GND, api.PTR_GAS)]
+
+    def render(self, n_frames: int, collect: bool = False, set_camera=None):
+        dist, N, S, rank = self.dist, self.world, self.S, self.rank
+        main, s_fin = self.main, self.s_fin
+        out = []
+        py = [(t[0] * 2 * self.ss, (t[0] + t[1]) * 2 * self.ss) for t in self.tiles]
+        last_root = None
+        for i in range(n_frames):
+            f = self.frame
+            root, slot = f % N, (f // N) % S
+            if set_camera is not None:
+                set_camera(f)
+            # ---- FRONT (all ranks)
+            self.front.frame_front()
+            src = self._front_planes()
+            # ---- GATHER to the root's back slot
+            if rank == root:
+                if self.slot_used[slot]:
+                    main.wait_event(self.ev_fin[slot])  # the slot's previous frame has been finished
+                ops = []
+                for r in range(N):
+                    a, b = py[r][0] * self.row_bytes, py[r][1] * self.row_bytes
+                    for k in range(3):
+                        if r == rank:
+                            self.slot_planes[slot][k][a:b].copy_(src[k][a:b], non_blocking=True)
+                        else:
+                            ops.append(dist.P2POp(dist.irecv, self.slot_planes[slot][k][a:b], r))
+                if ops:
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                self.ev_recv[slot].record(main)
+                self.slot_used[slot] = True
+                # ---- BACK on the slot's stream
+                sb = self.s_back[slot]
+                sb.wait_event(self.ev_recv[slot])
+                self.back.back_denoise(slot, sb.cuda_stream)
+                self.ev_back[slot].record(sb)
+            else:
+                a, b = py[rank][0] * self.row_bytes, py[rank][1] * self.row_bytes
+                ops = [dist.P2POp(dist.isend, src[k][a:b], root) for k in range(3)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            # ---- FINISH ring (frame order), cells to rank 0
+            with torch.cuda.stream(s_fin):
+                if rank == root:
+                    s_fin.wait_event(self.ev_back[slot])
+                    if N > 1 and i > 0:
+                        dist.recv(self.expo, src=(root - 1) % N, group=self.pg_fin)
+                    self.back.back_finish(slot, s_fin.cuda_stream)
+                    if rank == 0:
+                        self.out_ring[f % 4].copy_(self.slot_cells[slot], non_blocking=True)
+                    else:
+                        dist.send(self.slot_cells[slot], dst=0, group=self.pg_fin)
+                    if N > 1 and i + 1 < n_frames:
+                        dist.send(self.expo, dst=(root + 1) % N, group=self.pg_fin)
+                    self.ev_fin[slot].record(s_fin)
+                elif rank == 0:
+                    dist.recv(self.out_ring[f % 4], src=root, group=self.pg_fin)
+                if collect and rank == 0:
+                    out.append(self.out_ring[f % 4].clone())
+            last_root = root
+            self.frame += 1
+        # ---- end of the batch: every rank gets the exposure state, so that the next batch starts without a hand-off
+        with torch.cuda.stream(s_fin):
+            if N > 1 and last_root is not None:
+                dist.broadcast(self.expo, src=last_root, group=self.pg_fin)
+        main.wait_stream(s_fin)
+        for sb in self.s_back:
+            main.wait_stream(sb)
+        return out
+
+    def cells_host(self, t: torch.Tensor) -> np.ndarray:
+        return t.cpu().numpy().view(api.CELL_DTYPE).reshape(self.fb_h, self.fb_w)
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            self.dist.barrier()
+        self.front.close()
+        self.back.close()
