@@ -274,8 +274,11 @@ class FrameParallelRenderer:
         self.back = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device)
         self.S = back_slots
         self.back.back_config(back_slots)
-        self.main = torch.cuda.current_stream(device)
+        # FRONT stream at high priority: its kernels are short and every rank's front of frame f+1 waits for them, while the
+        # BACK kernels of other frames (large grids) would otherwise occupy every SM slot ahead of them
+        self.main = torch.cuda.Stream(device, priority=-1)
         self.front.set_stream(self.main.cuda_stream)
+        self.s_comm = torch.cuda.Stream(device, priority=-1)   # the gathers: decoupled from the fronts by a staging ring
         self.s_back = [torch.cuda.Stream(device) for _ in range(back_slots)]
         self.s_fin = torch.cuda.Stream(device)
         self.ev_recv = [torch.cuda.Event() for _ in range(back_slots)]
@@ -293,6 +296,14 @@ class FrameParallelRenderer:
         self.cell_bytes = fb_w * fb_h * api.CELL_DTYPE.itemsize
         self.out_ring = [torch.zeros(self.cell_bytes, dtype=torch.uint8, device=torch.device("cuda", device)) for _ in range(4)] if rank == 0 else None
         self.frame = 0  # global frame index (0-based) of the next frame
+        # staging ring: a copy of this rank's tile rows of (history, normal+depth, albedo+sky) per frame in flight, so that the
+        # next frame's TAA may overwrite the history while the rows are still on their way to the root
+        self.D = 4
+        tile_bytes = self.tiles[rank][1] * 2 * ss * self.row_bytes
+        self.stage = [[torch.empty(tile_bytes, dtype=torch.uint8, device=torch.device("cuda", device)) for _ in range(3)] for _ in range(self.D)]
+        self.ev_stage = [torch.cuda.Event() for _ in range(self.D)]
+        self.ev_sent = [torch.cuda.Event() for _ in range(self.D)]
+        self.stage_used = [False] * self.D
         self.pg_fin = None
         if world > 1:
             # two communicators: the gathers run in step with the fronts, the FINISH ring runs frames behind them
@@ -326,45 +337,58 @@ class FrameParallelRenderer:
 
     def render(self, n_frames: int, collect: bool = False, set_camera=None):
         dist, N, S, rank = self.dist, self.world, self.S, self.rank
-        main, s_fin = self.main, self.s_fin
+        main, s_comm, s_fin = self.main, self.s_comm, self.s_fin
+        caller = torch.cuda.current_stream(self.device)
+        main.wait_stream(caller)
         out = []
         py = [(t[0] * 2 * self.ss, (t[0] + t[1]) * 2 * self.ss) for t in self.tiles]
+        my_a, my_b = py[rank][0] * self.row_bytes, py[rank][1] * self.row_bytes
         last_root = None
         for i in range(n_frames):
             f = self.frame
-            root, slot = f % N, (f // N) % S
+            root, slot, d = f % N, (f // N) % S, f % self.D
             if set_camera is not None:
                 set_camera(f)
-            # ---- FRONT (all ranks)
-            self.front.frame_front()
-            src = self._front_planes()
-            # ---- GATHER to the root's back slot
-            if rank == root:
-                if self.slot_used[slot]:
-                    main.wait_event(self.ev_fin[slot])  # the slot's previous frame has been finished
-                ops = []
-                for r in range(N):
-                    a, b = py[r][0] * self.row_bytes, py[r][1] * self.row_bytes
-                    for k in range(3):
-                        if r == rank:
-                            self.slot_planes[slot][k][a:b].copy_(src[k][a:b], non_blocking=True)
-                        else:
-                            ops.append(dist.P2POp(dist.irecv, self.slot_planes[slot][k][a:b], r))
-                if ops:
+            # ---- FRONT (all ranks), then a copy of the tile's rows into the staging ring
+            with torch.cuda.stream(main):
+                self.front.frame_front()
+                src = self._front_planes()
+                if self.stage_used[d]:
+                    main.wait_event(self.ev_sent[d])
+                for k in range(3):
+                    self.stage[d][k].copy_(src[k][my_a:my_b], non_blocking=True)
+                self.ev_stage[d].record(main)
+                self.stage_used[d] = True
+            # ---- GATHER to the root's back slot (its own stream: the fronts run ahead by up to D frames)
+            with torch.cuda.stream(s_comm):
+                s_comm.wait_event(self.ev_stage[d])
+                if rank == root:
+                    if self.slot_used[slot]:
+                        s_comm.wait_event(self.ev_fin[slot])  # the slot's previous frame has been finished
+                    ops = []
+                    for r in range(N):
+                        a, b = py[r][0] * self.row_bytes, py[r][1] * self.row_bytes
+                        for k in range(3):
+                            if r == rank:
+                                self.slot_planes[slot][k][a:b].copy_(self.stage[d][k], non_blocking=True)
+                            else:
+                                ops.append(dist.P2POp(dist.irecv, self.slot_planes[slot][k][a:b], r))
+                    if ops:
+                        for w in dist.batch_isend_irecv(ops):
+                            w.wait()
+                    self.ev_recv[slot].record(s_comm)
+                    self.slot_used[slot] = True
+                else:
+                    ops = [dist.P2POp(dist.isend, self.stage[d][k], root) for k in range(3)]
                     for w in dist.batch_isend_irecv(ops):
                         w.wait()
-                self.ev_recv[slot].record(main)
-                self.slot_used[slot] = True
-                # ---- BACK on the slot's stream
+                self.ev_sent[d].record(s_comm)
+            # ---- BACK on the slot's stream
+            if rank == root:
                 sb = self.s_back[slot]
                 sb.wait_event(self.ev_recv[slot])
                 self.back.back_denoise(slot, sb.cuda_stream)
                 self.ev_back[slot].record(sb)
-            else:
-                a, b = py[rank][0] * self.row_bytes, py[rank][1] * self.row_bytes
-                ops = [dist.P2POp(dist.isend, src[k][a:b], root) for k in range(3)]
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
             # ---- FINISH ring (frame order), cells to rank 0
             with torch.cuda.stream(s_fin):
                 if rank == root:
@@ -389,9 +413,8 @@ class FrameParallelRenderer:
         with torch.cuda.stream(s_fin):
             if N > 1 and last_root is not None:
                 dist.broadcast(self.expo, src=last_root, group=self.pg_fin)
-        main.wait_stream(s_fin)
-        for sb in self.s_back:
-            main.wait_stream(sb)
+        for st in [main, s_comm, s_fin] + self.s_back:
+            caller.wait_stream(st)
         return out
 
     def cells_host(self, t: torch.Tensor) -> np.ndarray:
