@@ -405,18 +405,18 @@ def main():
     if stage_ms["ms_trace"] >= stage_ms["ms_atrous_chain"]:
         kname, kbytes, kms = "trace_kernel", b_trace * rows_here // H, stage_ms["ms_trace"]
     else:
-        kname, kbytes, kms = "atrous_chain_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
+        kname, kbytes, kms = "atrous_chain_static_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
     achieved = kbytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
     # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this same command (single GPU)
     traffic, traffic_src = None, None
     try:
         if n == 1:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full.json")))
-            key = next(k for k in cap if k.startswith("trace_kernel<0>" if kname == "trace_kernel" else "atrous_chain_kernel"))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_full.json")))
+            key = next(k for k in cap if k.startswith("trace_stream_kernel<0>" if kname == "trace_kernel" else "atrous_chain_static_kernel"))
             c0 = cap[key][-1]
             to_b = lambda v: float(v.split()[0]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[v.split()[1]]
             traffic = to_b(c0["dram__bytes_read.sum"]) + to_b(c0["dram__bytes_write.sum"])
-            traffic_src = "profiles/r01_ncu_full.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+            traffic_src = "profiles/r01b_ncu_full.json (dram__bytes_read.sum + dram__bytes_write.sum)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

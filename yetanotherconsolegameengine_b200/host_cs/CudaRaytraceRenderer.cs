@@ -116,6 +116,10 @@ namespace ConsoleGame.RayTracing
         [DllImport(Lib)] private static extern int ycge_set_fov(IntPtr ctx, float fovDeg);
         [DllImport(Lib)] private static extern int ycge_reset_history(IntPtr ctx);
         [DllImport(Lib)] private static extern int ycge_render_frame(IntPtr ctx, IntPtr cells, int strideCells);
+        [DllImport(Lib)] private static extern int ycge_texture_upload(IntPtr ctx, int id, int w, int h, [In] int[] rgba);
+        [DllImport(Lib)] private static extern int ycge_pipeline_config(IntPtr ctx, int nSlots);
+        [DllImport(Lib)] private static extern int ycge_submit_frame(IntPtr ctx, IntPtr cells, int strideCells, out long frameId);
+        [DllImport(Lib)] private static extern int ycge_frame_wait(IntPtr ctx, long frameId);
 
         static CudaRaytraceRenderer()
         {
@@ -177,6 +181,13 @@ namespace ConsoleGame.RayTracing
             }
         }
 
+        /// Frames in flight (include/ycge.h, ycge_pipeline_config): SubmitFrame enqueues SetCamera's pose and returns at once; the
+        /// cells land in `dst` (pinned) when WaitFrame(id) returns.  A host loop that can show frame N-2 while frame N renders
+        /// gets the GPU's throughput instead of one frame's latency; TryFlipAndBlit above stays the strict drop-in.
+        public void ConfigurePipeline(int framesInFlight) { Check(ycge_pipeline_config(ctx, framesInFlight)); }
+        public long SubmitFrame(IntPtr dst) { Check(ycge_submit_frame(ctx, dst, fbW, out long id)); return id; }
+        public void WaitFrame(long id) { Check(ycge_frame_wait(ctx, id)); }
+
         /// Per-frame light / sky changes without re-uploading geometry (DayNightCycle.cs:80-89).
         public void UpdateLightsAndGlobals()
         {
@@ -193,7 +204,21 @@ namespace ConsoleGame.RayTracing
             var objects = new List<YObject>();
             var pins = new List<GCHandle>();
             IntPtr Pin(Array a) { var h = GCHandle.Alloc(a, GCHandleType.Pinned); pins.Add(h); return h.AddrOfPinnedObject(); }
-            int AddMat(Material m) { materials.Add(ToMaterial(m)); return materials.Count - 1; }
+            // new Texture(path) (Renderer/Texture.cs:25-49): the int[] pixels (RGBA bytes, row 0 first, :81-90) go to the device once per
+            // distinct Texture object; Material.DiffuseTexture becomes its id.  Needs one internal accessor, Texture.Pixels.
+            var texIds = new Dictionary<ConsoleGame.Renderer.Texture, int>();
+            int TexId(Material m)
+            {
+                if (m.DiffuseTexture == null) return -1;
+                if (!texIds.TryGetValue(m.DiffuseTexture, out int id))
+                {
+                    id = texIds.Count;
+                    Check(ycge_texture_upload(ctx, id, m.DiffuseTexture.width, m.DiffuseTexture.height, m.DiffuseTexture.Pixels));
+                    texIds[m.DiffuseTexture] = id;
+                }
+                return id;
+            }
+            int AddMat(Material m) { var ym = ToMaterial(m); ym.TexId = TexId(m); materials.Add(ym); return materials.Count - 1; }
             try
             {
                 int meshId = 0, volId = 0;
