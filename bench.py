@@ -7,9 +7,11 @@
                                                            reference cannot run here) on the box's host cores
 
 A "step" is one frame of the hot path (TryFlipAndBlit: raygen -> trace -> TAA -> a-trous -> exposure -> cells).
-`value` times K frames enqueued back to back with the scene resident in HBM (CUDA events on the launching stream);
-`e2e` times the same K frames through the public IConsoleRenderer call (SetCamera + TryFlipAndBlit) with the cell
-array copied to pinned host memory every step.  Prints ONE JSON line on rank 0.
+`value` times K frames enqueued back to back with the scene resident in HBM (CUDA events on the launching stream), frames
+in flight (one GPU: ycge_pipeline_config; N GPUs: frames in parallel over the ranks).  `e2e` times K frames submitted one
+by one from the host -- SetCamera + submit per step, every frame's cells copied to pinned host memory inside the region,
+the host a few frames ahead of the arrivals; `e2e_synchronous` is the strict drop-in call (SetCamera + TryFlipAndBlit,
+one frame's latency per step).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes as C
@@ -370,17 +372,39 @@ def main():
             dist.barrier()
             e2e_local = time.perf_counter() - t0
             st3 = b.r.stats()
+            # streaming end to end on the frame-parallel path: camera in on every rank per frame, every frame's cells copied
+            # to pinned host memory on rank 0, the host at most N x back slots + 2 frames ahead of the arrivals
+            stream_local = None
+            if fp is not None:
+                n_ring = n * fp.S + 2  # as many host buffers as frames can be in flight (N ranks x back slots), or the host's pacing caps them
+                ring = [torch.empty((fb_h * fb_w * api.CELL_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True) for _ in range(n_ring)] if rank == 0 else None
+                cam = lambda f: fp.SetCamera(*pose)
+                fp.render(max(3, args.warmup), set_camera=cam, host_ring=ring)
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+                fp.render(args.steps, set_camera=cam, host_ring=ring)
+                torch.cuda.synchronize()
+                dist.barrier()
+                stream_local = time.perf_counter() - t0
         # max over ranks of the device time; rays summed over ranks (halo rows are traced redundantly and counted as
         # work done — rays/frame of the UNSHARDED frame is what the metric divides by, so use the unsharded count)
         all_stage = [None] * n
         dist.all_gather_object(all_stage, dict({k: round(v, 3) for k, v in stage_ms.items()}, **(fp_stage or {})))
-        t = torch.tensor([ms_local, e2e_local], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_local, e2e_local, stream_local or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
+        streaming = None
+        if stream_local:
+            stream_s = float(t[2])
         rays_frame = torch.tensor([st_events["rays"] if rank == 0 else 0], dtype=torch.int64, device="cuda")
         dist.broadcast(rays_frame, 0)
         rays_timed = int(rays_frame[0]) * args.steps
         e2e_rays = int(rays_frame[0]) * args.steps
+        if stream_local:
+            streaming = {"value": e2e_rays / stream_s / 1e6, "unit": "Mrays/s", "frames_per_s": args.steps / stream_s, "frames_in_flight": "host at most %d frames ahead; %d back slots per rank" % (n * fp.S + 2, fp.S),
+                         "h2d_bytes_per_step": h2d * n, "d2h_bytes_per_step": d2h,
+                         "api": "SetCamera on every rank + FrameParallelRenderer.render per step, every frame's cells copied to pinned host memory on rank 0"}
         if fp is not None:
             fp.close()
         sr.close()
@@ -431,18 +455,21 @@ def main():
         leg = cpu_leg(args, fb_w, fb_h, ss, seconds=args.cpu_seconds)
         cpu = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample", "frames_per_s_scaled_to_workload", "ms_per_stage_sample")}
 
+    sync_e2e = {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "SetCamera + TryFlipAndBlit per step, synchronous (the drop-in call; latency of one frame)"}
     if rank == 0:
         line = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
-                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ((", %d frames in flight on the GPU (value, e2e_streaming); serial (e2e, stage_ms, roofline kernel time)" % slots) if n == 1 else (", frames in parallel: FRONT on row tiles, BACK + FINISH of whole frames round-robin over the ranks (value); row tiles in lock step" if mode == "frames" else
-                            (", frames pipelined over ranks (value); lock-step" if pipelined else "")) + (", peer hand-off (e2e)" if peer_handoff else ", NCCL send/recv hand-off (e2e)")),
+                "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ((", %d frames in flight on the GPU (value, e2e); strictly serial (e2e_synchronous, serial_schedule, stage_ms, roofline kernel time)" % slots) if n == 1 else (", frames in parallel: FRONT on row tiles, BACK + FINISH of whole frames round-robin over the ranks (value, e2e); row tiles in lock step" if mode == "frames" else
+                            (", frames pipelined over ranks (value); lock-step" if pipelined else "")) + (", peer hand-off (e2e_synchronous)" if peer_handoff else ", NCCL send/recv hand-off (e2e_synchronous)")),
                            "l2": "per-frame working set (8 float4 image planes = %d MB) exceeds the 126 MB L2; no explicit flush" % (W * H * 128 // (1 << 20))},
                 "stage_ms": stage_ms, **({"stage_ms_ranks": all_stage, "peer_handoff": peer_handoff, "frame_pipelining": pipelined, "multi_gpu_mode": mode, "tiles_cell_rows": [t[1] for t in tiles],
                                               "front_tiles_cell_rows": [t[1] for t in front_tiles] if front_tiles else None} if n > 1 else {}),
-                "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "SetCamera + TryFlipAndBlit per step, synchronous (the drop-in call; latency of one frame)"},
-                **({"e2e_streaming": streaming, "serial_schedule": serial, "frames_in_flight": slots} if n == 1 else {}),
+                # e2e: frames in flight (the host submits frame N while earlier frames finish; every frame's cells are copied to pinned
+                # host memory inside the timed region).  e2e_synchronous: the strict drop-in call, one frame's latency per step.
+                "e2e": streaming if streaming else sync_e2e, "e2e_synchronous": sync_e2e,
+                **({"serial_schedule": serial, "frames_in_flight": slots} if n == 1 else {}),
                 "gpu_launches": launches_per_frame * args.steps * n,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))

@@ -296,6 +296,7 @@ class FrameParallelRenderer:
         self.cell_bytes = fb_w * fb_h * api.CELL_DTYPE.itemsize
         self.out_ring = [torch.zeros(self.cell_bytes, dtype=torch.uint8, device=torch.device("cuda", device)) for _ in range(4)] if rank == 0 else None
         self.frame = 0  # global frame index (0-based) of the next frame
+        self._plane_cache = {}
         # staging ring: a copy of this rank's tile rows of (history, normal+depth, albedo+sky) per frame in flight, so that the
         # next frame's TAA may overwrite the history while the rows are still on their way to the root
         self.D = 4
@@ -332,11 +333,24 @@ class FrameParallelRenderer:
         self.front.SetCamera(pos, yaw, pitch)
 
     def _front_planes(self):
-        """This rank's history + guide planes of the frame just rendered (full-frame layout)."""
-        return [device_bytes(self.front.device_ptr(kind)[0], self.n_px_bytes, self.device) for kind in (api.PTR_HIST, api.PTR_GND, api.PTR_GAS)]
+        """This rank's history + guide planes of the frame just rendered (full-frame layout); the guide planes alternate between
+        two sets, so the aliasing tensors are cached by pointer."""
+        out = []
+        for kind in (api.PTR_HIST, api.PTR_GND, api.PTR_GAS):
+            p = self.front.device_ptr(kind)[0]
+            t = self._plane_cache.get(p)
+            if t is None:
+                t = self._plane_cache[p] = device_bytes(p, self.n_px_bytes, self.device)
+            out.append(t)
+        return out
 
-    def render(self, n_frames: int, collect: bool = False, set_camera=None):
+    def render(self, n_frames: int, collect: bool = False, set_camera=None, host_ring=None):
+        """Enqueue n_frames frames.  `set_camera(f)` is called before frame f is submitted (every rank).  `host_ring` (rank 0):
+        a list of pinned uint8 tensors; frame f's cells are copied into host_ring[f % len] as part of the frame, and the host
+        waits for that copy before it reuses the entry, i.e. it runs len(host_ring) frames ahead at most (streaming end to
+        end: every frame's cells land in host memory)."""
         dist, N, S, rank = self.dist, self.world, self.S, self.rank
+        ev_host = [None] * len(host_ring) if host_ring else None
         main, s_comm, s_fin = self.main, self.s_comm, self.s_fin
         caller = torch.cuda.current_stream(self.device)
         main.wait_stream(caller)
@@ -407,6 +421,13 @@ class FrameParallelRenderer:
                     dist.recv(self.out_ring[f % 4], src=root, group=self.pg_fin)
                 if collect and rank == 0:
                     out.append(self.out_ring[f % 4].clone())
+                if host_ring and rank == 0:
+                    h = i % len(host_ring)
+                    if ev_host[h] is not None:
+                        ev_host[h].synchronize()  # the host paces itself on the arrival of the frame len(host_ring) frames back
+                    host_ring[h].copy_(self.out_ring[f % 4], non_blocking=True)
+                    ev_host[h] = torch.cuda.Event()
+                    ev_host[h].record(s_fin)
             last_root = root
             self.frame += 1
         # ---- end of the batch: every rank gets the exposure state, so that the next batch starts without a hand-off
@@ -415,6 +436,10 @@ class FrameParallelRenderer:
                 dist.broadcast(self.expo, src=last_root, group=self.pg_fin)
         for st in [main, s_comm, s_fin] + self.s_back:
             caller.wait_stream(st)
+        if host_ring and rank == 0:
+            for e in ev_host:
+                if e is not None:
+                    e.synchronize()
         return out
 
     def cells_host(self, t: torch.Tensor) -> np.ndarray:
