@@ -344,7 +344,7 @@ def main():
             clocks = sampler.stop()
             fp_stage = None
             if fp is not None:
-                fs = fp.front.stats()
+                fs = fp.b.front_r.stats()
                 fp_stage = {"front_ms_trace": round(fs["ms_trace"], 3), "front_ms_taa": round(fs["ms_taa"], 3)}
             # per-stage times of the lock-step row-tile path (the e2e path below)
             for _ in range(2):

@@ -1,8 +1,14 @@
-"""Row-tile sharding, host-side logic on CPU: the tile partition, and the per-frame orchestration (boundary-row
-hand-off rank -> rank+1, sum all-reduce of the exposure samples, gather of the cell tiles on rank 0) run with
-world_size 2 and 3 over gloo.  The tile backend here is a fake built on the CPU oracle (each rank renders the whole
-frame with the oracle and exposes only its tile's slices), so this checks the plumbing, not the kernels; the kernels'
-tile/halo logic is checked on the GPU in test_gpu_parity.py::test_row_tiles_equal_the_unsharded_frame."""
+"""Sharding, host-side logic on CPU, world_size 2 and 3 over gloo.
+
+Row tiles in lock step (sharding.ShardedRenderer): the tile partition and the per-frame orchestration (boundary-row hand-off
+rank -> rank+1, sum all-reduce of the exposure samples, gather of the cell tiles on rank 0).
+Frames in parallel (sharding.FrameParallelRenderer): FRONT tiles gathered into a back slot of the frame's root, BACK + FINISH
+round-robin over the ranks, exposure state around the ring, cells to rank 0, two batches.
+
+The backends here are fakes built on the CPU oracle (each rank renders the whole frame with the oracle and exposes only its
+tile's slices), so this checks the plumbing, not the kernels; the kernels' tile / halo / front-back logic is checked on the
+GPU in test_gpu_parity.py (test_row_tiles_equal_the_unsharded_frame, test_front_tiles_plus_whole_frame_back_equal_the_
+unsharded_frame) and over real ranks by tools/multigpu_check.py."""
 import os
 import sys
 
@@ -135,6 +141,130 @@ def test_sharded_frame_orchestration_gloo(world, fb_h):
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, errors in results:
+        assert ok, (rank, errors)
+
+
+class FakeFrameBackend:
+    """Backend of sharding.FrameParallelRenderer made of the CPU oracle: every rank renders every frame with its own oracle
+    (identical everywhere), exposes only its tile's rows of the frame's history / guide planes as the FRONT result, and as
+    the frame's root checks what the gather assembled and what the FINISH ring delivered."""
+    is_cuda = False
+
+    def __init__(self, scene_name, fb_w, fb_h, ss, rank, world, tiles, back_slots):
+        from oracle_binding import Oracle
+        self.scene = api.HostScene(scene_name)
+        self.o = Oracle(self.scene, fb_w, fb_h, ss)
+        self.rank, self.world, self.fb_w, self.fb_h, self.ss = rank, world, fb_w, fb_h, ss
+        self.device = torch.device("cpu")
+        self.main, self.s_comm, self.s_fin = sharding.NullStream(), sharding.NullStream(), sharding.NullStream()
+        self.s_back = [sharding.NullStream() for _ in range(back_slots)]
+        W, H = fb_w * ss, fb_h * 2 * ss
+        self.n_px_bytes = W * H * 16
+        self.py0, self.py1 = tiles[rank][0] * 2 * ss * W * 16, (tiles[rank][0] + tiles[rank][1]) * 2 * ss * W * 16
+        self.slot_planes = [[torch.zeros(self.n_px_bytes, dtype=torch.uint8) for _ in range(3)] for _ in range(back_slots)]
+        self.slot_cells = [torch.zeros(fb_w * fb_h * 32, dtype=torch.uint8) for _ in range(back_slots)]
+        self.expo = torch.zeros(16, dtype=torch.uint8)
+        self.frames = []      # per rendered frame: (planes, cells, exposure state after the frame)
+        self.slot_frame = {}  # slot -> index of the frame whose BACK ran there
+        self.done = 0         # frames finished so far, over all ranks (the root of frame f is the only one that counts f)
+        self.errors = []
+
+    def event(self):
+        return sharding.NullEvent()
+
+    def on(self, stream):
+        return stream
+
+    def current_stream(self):
+        return sharding.NullStream()
+
+    def synchronize(self):
+        pass
+
+    def alloc(self, nbytes):
+        return torch.zeros(nbytes, dtype=torch.uint8)
+
+    def set_camera(self, pos, yaw, pitch):
+        self.o.set_camera(pos, yaw, pitch)
+
+    @staticmethod
+    def state_token(frame_index, ae):
+        t = np.zeros(4, np.float32)
+        t[0], t[1] = ae, frame_index
+        return torch.from_numpy(t.view(np.uint8).copy())
+
+    def front(self):
+        cells = self.o.render_frame(threads=2, fast_post=True)
+        planes = [torch.from_numpy(self.o.debug_read(k).view(np.uint8).reshape(-1).copy()) for k in (api.DBG_TAA, api.DBG_NORMAL_DEPTH, api.DBG_ALBEDO_SKY)]
+        self.frames.append((planes, cells.copy(), self.state_token(len(self.frames), self.o.stats()["ae_exposure"])))
+
+    def front_planes(self):
+        out = []
+        for p in self.frames[-1][0]:  # only this rank's tile rows are valid, like the tile ctx's planes
+            t = torch.full_like(p, 0xEE)
+            t[self.py0:self.py1] = p[self.py0:self.py1]
+            out.append(t)
+        return out
+
+    def back_denoise(self, slot, stream):
+        f = len(self.frames) - 1  # synchronous backend: the BACK of a frame runs right after its gather
+        self.slot_frame[slot] = f
+        for k in range(3):
+            if not torch.equal(self.slot_planes[slot][k], self.frames[f][0][k]):
+                self.errors.append(f"frame {f}: plane {k} assembled in back slot {slot} differs from the full-frame plane")
+
+    def back_finish(self, slot, stream):
+        f = self.slot_frame[slot]
+        if f > 0 and not torch.equal(self.expo, self.frames[f - 1][2]):
+            self.errors.append(f"frame {f}: exposure state of frame {f - 1} had not arrived before FINISH")
+        self.slot_cells[slot].copy_(torch.from_numpy(self.frames[f][1].view(np.uint8).reshape(-1)))
+        self.expo.copy_(self.frames[f][2])
+
+    def close(self):
+        self.o.close()
+        self.scene.close()
+
+
+def _fp_worker(rank, world, port, fb_w, fb_h, ss, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path[:0] = [ROOT, TESTS]
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tiles = [sharding.tile_rows(r, world, fb_h) for r in range(world)]
+        b = FakeFrameBackend("boxes", fb_w, fb_h, ss, rank, world, tiles, back_slots=2)
+        fp = sharding.FrameParallelRenderer(b, rank, world, fb_w, fb_h, ss, tiles=tiles, back_slots=2)
+        moved = lambda f: fp.SetCamera((0.3, 1.2, 0.1), 0.2, -0.1) if f == 3 else None  # every rank moves identically
+        got = fp.render(2 * world + 1, collect=True, set_camera=moved) + fp.render(world + 2, collect=True)  # two batches
+        ok = True
+        if rank == 0:
+            ok &= len(got) == 3 * world + 3
+            for f, g in enumerate(got):
+                ok &= fp.cells_host(g).tobytes() == b.frames[f][1].tobytes()
+        else:
+            ok &= got == []
+        # after a batch every rank holds the exposure state of the last frame
+        ok &= torch.equal(b.expo, b.frames[-1][2])
+        q.put((rank, bool(ok) and not b.errors, b.errors))
+        fp.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,fb_h", [(2, 9), (3, 10)])
+def test_frame_parallel_orchestration_gloo(world, fb_h):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_fp_worker, args=(r, world, port, 24, fb_h, 2, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -250,6 +250,103 @@ class ShardedRenderer:
         return self.assemble(g) if self.rank == 0 else None
 
 
+class NullEvent:
+    """Stream / event stand-ins for a backend whose work is synchronous (the CPU fake of tests/test_sharding.py)."""
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class NullStream:
+    cuda_stream = 0
+
+    def wait_event(self, ev):
+        pass
+
+    def wait_stream(self, st):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class CudaFrameBackend:
+    """One rank of the frame-parallel path on one GPU: a row-tile ctx for the FRONT, a whole-frame ctx with back slots for
+    BACK + FINISH, and the streams they run on, through the C ABI (ycge_frame_front, ycge_back_*)."""
+    is_cuda = True
+
+    def __init__(self, scene: api.HostScene, fb_w: int, fb_h: int, ss: int, device: int, row0: int, rows: int, back_slots: int):
+        self.dev_index = device
+        self.device = torch.device("cuda", device)
+        self.front_r = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device, tile_row0=row0, tile_rows=rows)
+        self.back_r = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device)
+        self.back_r.back_config(back_slots)
+        # FRONT stream at high priority: its kernels are short and every rank's front of frame f+1 waits for them, while the
+        # BACK kernels of other frames (large grids) would otherwise occupy every SM slot ahead of them
+        self.main = torch.cuda.Stream(device, priority=-1)
+        self.front_r.set_stream(self.main.cuda_stream)
+        self.s_comm = torch.cuda.Stream(device, priority=-1)   # the gathers: decoupled from the fronts by a staging ring
+        self.s_back = [torch.cuda.Stream(device) for _ in range(back_slots)]
+        self.s_fin = torch.cuda.Stream(device)
+        W, H = fb_w * ss, fb_h * 2 * ss
+        self.n_px_bytes = W * H * 16
+        kinds = (api.PTR_HIST, api.PTR_GND, api.PTR_GAS)
+        self.slot_planes = [[device_bytes(self.back_r.back_ptr(k, kind)[0], self.n_px_bytes, device) for kind in kinds] for k in range(back_slots)]
+        self.slot_cells = [device_bytes(*self.back_r.back_ptr(k, api.PTR_CELLS), device) for k in range(back_slots)]
+        p, n = self.back_r.device_ptr(api.PTR_EXPOSURE)
+        self.expo = device_bytes(p, n, device)
+        self._plane_cache = {}
+
+    def event(self):
+        return torch.cuda.Event()
+
+    def on(self, stream):
+        return torch.cuda.stream(stream)
+
+    def current_stream(self):
+        return torch.cuda.current_stream(self.dev_index)
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.dev_index)
+
+    def alloc(self, nbytes: int) -> torch.Tensor:
+        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+
+    def set_camera(self, pos, yaw, pitch):
+        self.front_r.SetCamera(pos, yaw, pitch)
+
+    def front(self):
+        self.front_r.frame_front()
+
+    def front_planes(self):
+        """This rank's history + guide planes of the frame just rendered (full-frame layout); the guide planes alternate between
+        two sets, so the aliasing tensors are cached by pointer."""
+        out = []
+        for kind in (api.PTR_HIST, api.PTR_GND, api.PTR_GAS):
+            p = self.front_r.device_ptr(kind)[0]
+            t = self._plane_cache.get(p)
+            if t is None:
+                t = self._plane_cache[p] = device_bytes(p, self.n_px_bytes, self.dev_index)
+            out.append(t)
+        return out
+
+    def back_denoise(self, slot: int, stream):
+        self.back_r.back_denoise(slot, stream.cuda_stream)
+
+    def back_finish(self, slot: int, stream):
+        self.back_r.back_finish(slot, stream.cuda_stream)
+
+    def close(self):
+        self.front_r.close()
+        self.back_r.close()
+
+
 class FrameParallelRenderer:
     """Asynchronous path over N ranks, frames in parallel (ycge.h "Frame-parallel sharding").
 
@@ -262,97 +359,84 @@ class FrameParallelRenderer:
               slot's own stream, while all ranks go on with the fronts of the next frames            [N frames in flight]
       FINISH  in frame order around the ring: the root receives the exposure state of frame f-1 from rank (f-1) mod N,
               runs the ordered exposure sum + cells, sends the cells to rank 0 and the state on to rank (f+1) mod N.
-    Every frame is bit-identical to the unsharded frame (tools/multigpu_check.py)."""
+    Every frame is bit-identical to the unsharded frame (tools/multigpu_check.py).  The orchestration is backend-agnostic
+    (`scene` may be a ready backend object): tests/test_sharding.py runs it over gloo with a fake backend on the CPU."""
 
-    def __init__(self, scene: api.HostScene, rank: int, world: int, fb_w: int, fb_h: int, ss: int, device: int, tiles=None, back_slots: int = 2):
+    def __init__(self, scene, rank: int, world: int, fb_w: int, fb_h: int, ss: int, device: int = 0, tiles=None, back_slots: int = 2):
         import torch.distributed as dist
-        self.dist, self.rank, self.world, self.device = dist, rank, world, device
+        self.dist, self.rank, self.world = dist, rank, world
         self.fb_w, self.fb_h, self.ss = fb_w, fb_h, ss
         self.tiles = list(tiles) if tiles is not None else [tile_rows(r, world, fb_h) for r in range(world)]
         row0, rows = self.tiles[rank]
-        self.front = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device, tile_row0=row0, tile_rows=rows)
-        self.back = api.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=device)
         self.S = back_slots
-        self.back.back_config(back_slots)
-        # FRONT stream at high priority: its kernels are short and every rank's front of frame f+1 waits for them, while the
-        # BACK kernels of other frames (large grids) would otherwise occupy every SM slot ahead of them
-        self.main = torch.cuda.Stream(device, priority=-1)
-        self.front.set_stream(self.main.cuda_stream)
-        self.s_comm = torch.cuda.Stream(device, priority=-1)   # the gathers: decoupled from the fronts by a staging ring
-        self.s_back = [torch.cuda.Stream(device) for _ in range(back_slots)]
-        self.s_fin = torch.cuda.Stream(device)
-        self.ev_recv = [torch.cuda.Event() for _ in range(back_slots)]
-        self.ev_back = [torch.cuda.Event() for _ in range(back_slots)]
-        self.ev_fin = [torch.cuda.Event() for _ in range(back_slots)]
+        self.b = scene if hasattr(scene, "front_planes") else CudaFrameBackend(scene, fb_w, fb_h, ss, device, row0, rows, back_slots)
+        b = self.b
+        self.main, self.s_comm, self.s_back, self.s_fin = b.main, b.s_comm, b.s_back, b.s_fin
+        self.ev_recv = [b.event() for _ in range(back_slots)]
+        self.ev_back = [b.event() for _ in range(back_slots)]
+        self.ev_fin = [b.event() for _ in range(back_slots)]
         self.slot_used = [False] * back_slots
-        W, H = fb_w * ss, fb_h * 2 * ss
+        W = fb_w * ss
         self.row_bytes = W * 16
-        self.n_px_bytes = W * H * 16
-        kinds = (api.PTR_HIST, api.PTR_GND, api.PTR_GAS)
-        self.slot_planes = [[device_bytes(self.back.back_ptr(k, kind)[0], self.n_px_bytes, device) for kind in kinds] for k in range(back_slots)]
-        self.slot_cells = [device_bytes(*self.back.back_ptr(k, api.PTR_CELLS), device) for k in range(back_slots)]
-        p, n = self.back.device_ptr(api.PTR_EXPOSURE)
-        self.expo = device_bytes(p, n, device)
+        self.slot_planes, self.slot_cells, self.expo = b.slot_planes, b.slot_cells, b.expo
         self.cell_bytes = fb_w * fb_h * api.CELL_DTYPE.itemsize
-        self.out_ring = [torch.zeros(self.cell_bytes, dtype=torch.uint8, device=torch.device("cuda", device)) for _ in range(4)] if rank == 0 else None
+        self.out_ring = [b.alloc(self.cell_bytes) for _ in range(4)] if rank == 0 else None
         self.frame = 0  # global frame index (0-based) of the next frame
-        self._plane_cache = {}
+        self._pending = []  # host-blocking backends (gloo): sends in flight, waited for at the end of a batch
         # staging ring: a copy of this rank's tile rows of (history, normal+depth, albedo+sky) per frame in flight, so that the
         # next frame's TAA may overwrite the history while the rows are still on their way to the root
         self.D = 4
         tile_bytes = self.tiles[rank][1] * 2 * ss * self.row_bytes
-        self.stage = [[torch.empty(tile_bytes, dtype=torch.uint8, device=torch.device("cuda", device)) for _ in range(3)] for _ in range(self.D)]
-        self.ev_stage = [torch.cuda.Event() for _ in range(self.D)]
-        self.ev_sent = [torch.cuda.Event() for _ in range(self.D)]
+        self.stage = [[b.alloc(tile_bytes) for _ in range(3)] for _ in range(self.D)]
+        self.ev_stage = [b.event() for _ in range(self.D)]
+        self.ev_sent = [b.event() for _ in range(self.D)]
         self.stage_used = [False] * self.D
         self.pg_fin = None
         if world > 1:
             # two communicators: the gathers run in step with the fronts, the FINISH ring runs frames behind them
             self.pg_fin = dist.new_group(list(range(world)))
-            t = torch.zeros(1, device=torch.device("cuda", device))
+            t = b.alloc(4).view(torch.float32)
             dist.all_reduce(t)
             dist.all_reduce(t, group=self.pg_fin)
-            torch.cuda.synchronize(device)
+            b.synchronize()
             # Open every point-to-point connection NOW, pair by pair, with nothing else in flight.  NCCL sets a connection up
             # on first use with host-side rendezvous and device allocations; if that happens in the render loop while a
             # send/recv kernel of the other communicator is already spinning on one of the two GPUs, the set-up waits for
             # that kernel, the kernel for its peer, and the peer's host for the set-up: a deadlock (seen on 2 GPUs).
-            for grp, pairs in ((None, [(a, b) for a in range(world) for b in range(a + 1, world)]),
+            for grp, pairs in ((None, [(a, c) for a in range(world) for c in range(a + 1, world)]),
                                (self.pg_fin, sorted({(min(r, (r + 1) % world), max(r, (r + 1) % world)) for r in range(world)} | {(0, r) for r in range(1, world)}))):
-                for a, b in pairs:
+                for a, c in pairs:
                     if rank == a:
-                        dist.send(t, dst=b, group=grp)
-                        dist.recv(t, src=b, group=grp)
-                    elif rank == b:
+                        dist.send(t, dst=c, group=grp)
+                        dist.recv(t, src=c, group=grp)
+                    elif rank == c:
                         dist.recv(t, src=a, group=grp)
                         dist.send(t, dst=a, group=grp)
-                    torch.cuda.synchronize(device)
+                    b.synchronize()
             dist.barrier()
 
     def SetCamera(self, pos, yaw, pitch):
-        self.front.SetCamera(pos, yaw, pitch)
+        self.b.set_camera(pos, yaw, pitch)
 
-    def _front_planes(self):
-        """This rank's history + guide planes of the frame just rendered (full-frame layout); the guide planes alternate between
-        two sets, so the aliasing tensors are cached by pointer."""
-        out = []
-        for kind in (api.PTR_HIST, api.PTR_GND, api.PTR_GAS):
-            p = self.front.device_ptr(kind)[0]
-            t = self._plane_cache.get(p)
-            if t is None:
-                t = self._plane_cache[p] = device_bytes(p, self.n_px_bytes, self.device)
-            out.append(t)
-        return out
+    def _send(self, t: torch.Tensor, dst: int, group):
+        """A send that never blocks the host.  NCCL: enqueued, the current stream waits for it.  Host-blocking backends (gloo): a
+        copy is sent asynchronously and waited for at the end of the batch; a blocking send in the FINISH ring would keep this
+        rank from serving the next gathers, which the receiver may be waiting for first."""
+        if self.b.is_cuda:
+            self.dist.send(t, dst=dst, group=group)
+        else:
+            keep = t.clone()
+            self._pending.append((self.dist.isend(keep, dst=dst, group=group), keep))
 
     def render(self, n_frames: int, collect: bool = False, set_camera=None, host_ring=None):
         """Enqueue n_frames frames.  `set_camera(f)` is called before frame f is submitted (every rank).  `host_ring` (rank 0):
         a list of pinned uint8 tensors; frame f's cells are copied into host_ring[f % len] as part of the frame, and the host
         waits for that copy before it reuses the entry, i.e. it runs len(host_ring) frames ahead at most (streaming end to
         end: every frame's cells land in host memory)."""
-        dist, N, S, rank = self.dist, self.world, self.S, self.rank
+        dist, N, S, rank, b = self.dist, self.world, self.S, self.rank, self.b
         ev_host = [None] * len(host_ring) if host_ring else None
         main, s_comm, s_fin = self.main, self.s_comm, self.s_fin
-        caller = torch.cuda.current_stream(self.device)
+        caller = b.current_stream()
         main.wait_stream(caller)
         out = []
         py = [(t[0] * 2 * self.ss, (t[0] + t[1]) * 2 * self.ss) for t in self.tiles]
@@ -364,9 +448,9 @@ class FrameParallelRenderer:
             if set_camera is not None:
                 set_camera(f)
             # ---- FRONT (all ranks), then a copy of the tile's rows into the staging ring
-            with torch.cuda.stream(main):
-                self.front.frame_front()
-                src = self._front_planes()
+            with b.on(main):
+                b.front()
+                src = b.front_planes()
                 if self.stage_used[d]:
                     main.wait_event(self.ev_sent[d])
                 for k in range(3):
@@ -374,19 +458,19 @@ class FrameParallelRenderer:
                 self.ev_stage[d].record(main)
                 self.stage_used[d] = True
             # ---- GATHER to the root's back slot (its own stream: the fronts run ahead by up to D frames)
-            with torch.cuda.stream(s_comm):
+            with b.on(s_comm):
                 s_comm.wait_event(self.ev_stage[d])
                 if rank == root:
                     if self.slot_used[slot]:
                         s_comm.wait_event(self.ev_fin[slot])  # the slot's previous frame has been finished
                     ops = []
                     for r in range(N):
-                        a, b = py[r][0] * self.row_bytes, py[r][1] * self.row_bytes
+                        lo, hi = py[r][0] * self.row_bytes, py[r][1] * self.row_bytes
                         for k in range(3):
                             if r == rank:
-                                self.slot_planes[slot][k][a:b].copy_(self.stage[d][k], non_blocking=True)
+                                self.slot_planes[slot][k][lo:hi].copy_(self.stage[d][k], non_blocking=True)
                             else:
-                                ops.append(dist.P2POp(dist.irecv, self.slot_planes[slot][k][a:b], r))
+                                ops.append(dist.P2POp(dist.irecv, self.slot_planes[slot][k][lo:hi], r))
                     if ops:
                         for w in dist.batch_isend_irecv(ops):
                             w.wait()
@@ -401,21 +485,21 @@ class FrameParallelRenderer:
             if rank == root:
                 sb = self.s_back[slot]
                 sb.wait_event(self.ev_recv[slot])
-                self.back.back_denoise(slot, sb.cuda_stream)
+                b.back_denoise(slot, sb)
                 self.ev_back[slot].record(sb)
             # ---- FINISH ring (frame order), cells to rank 0
-            with torch.cuda.stream(s_fin):
+            with b.on(s_fin):
                 if rank == root:
                     s_fin.wait_event(self.ev_back[slot])
                     if N > 1 and i > 0:
                         dist.recv(self.expo, src=(root - 1) % N, group=self.pg_fin)
-                    self.back.back_finish(slot, s_fin.cuda_stream)
+                    b.back_finish(slot, s_fin)
                     if rank == 0:
                         self.out_ring[f % 4].copy_(self.slot_cells[slot], non_blocking=True)
                     else:
-                        dist.send(self.slot_cells[slot], dst=0, group=self.pg_fin)
+                        self._send(self.slot_cells[slot], 0, self.pg_fin)
                     if N > 1 and i + 1 < n_frames:
-                        dist.send(self.expo, dst=(root + 1) % N, group=self.pg_fin)
+                        self._send(self.expo, (root + 1) % N, self.pg_fin)
                     self.ev_fin[slot].record(s_fin)
                 elif rank == 0:
                     dist.recv(self.out_ring[f % 4], src=root, group=self.pg_fin)
@@ -426,12 +510,15 @@ class FrameParallelRenderer:
                     if ev_host[h] is not None:
                         ev_host[h].synchronize()  # the host paces itself on the arrival of the frame len(host_ring) frames back
                     host_ring[h].copy_(self.out_ring[f % 4], non_blocking=True)
-                    ev_host[h] = torch.cuda.Event()
+                    ev_host[h] = b.event()
                     ev_host[h].record(s_fin)
             last_root = root
             self.frame += 1
         # ---- end of the batch: every rank gets the exposure state, so that the next batch starts without a hand-off
-        with torch.cuda.stream(s_fin):
+        for w, _ in self._pending:
+            w.wait()
+        self._pending = []
+        with b.on(s_fin):
             if N > 1 and last_root is not None:
                 dist.broadcast(self.expo, src=last_root, group=self.pg_fin)
         for st in [main, s_comm, s_fin] + self.s_back:
@@ -446,8 +533,7 @@ class FrameParallelRenderer:
         return t.cpu().numpy().view(api.CELL_DTYPE).reshape(self.fb_h, self.fb_w)
 
     def close(self):
-        torch.cuda.synchronize(self.device)
+        self.b.synchronize()
         if self.world > 1:
             self.dist.barrier()
-        self.front.close()
-        self.back.close()
+        self.b.close()
