@@ -1,5 +1,8 @@
 """Host mirror (libycge_host.so): the C# host side restated in C++ — scene factories of BuildSceneTable(), MeshLoader,
 the BVH builders whose trees are uploaded, Framebuffer/Chexel, ANSITerminalRenderer.Render's byte stream."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -175,3 +178,98 @@ def test_texture_test_scene_and_png_decoder(tmp_path):
         t.set_texture(0, want[:5, :7])
         assert t.texture(0).shape == (5, 7)
         t.close()
+
+
+def parse_scne(b):
+    """SceneSyncProtocol.ReadSnapshot (Scenes/SyncScene.cs:395-520) transcribed with struct, independent of the C++ mirror."""
+    import struct
+    at = [0]
+
+    def rd(fmt):
+        v = struct.unpack_from("<" + fmt, b, at[0])
+        at[0] += struct.calcsize("<" + fmt)
+        return v if len(v) > 1 else v[0]
+
+    mat = lambda: {"albedo": rd("3f"), "spec": rd("f"), "refl": rd("f"), "emit": rd("3f"), "transp": rd("f"), "ior": rd("f"), "tint": rd("3f")}
+    assert rd("I") == 0x53434E45 and rd("I") == 1
+    out = {"bg_top": rd("3f"), "bg_bottom": rd("3f"), "amb": rd("3f"), "amb_i": rd("f"), "fov": rd("f"), "cam": rd("3f"), "yaw": rd("f"), "pitch": rd("f")}
+    out["lights"] = [(rd("3f"), rd("3f"), rd("f")) for _ in range(rd("i"))]
+    objs = []
+    for _ in range(rd("i")):
+        tag = rd("B")
+        if tag == 1:
+            objs.append(("sphere", rd("3f"), rd("f"), mat()))
+        elif tag == 2:
+            objs.append(("plane", rd("3f"), rd("3f"), mat()))
+        elif tag == 3:
+            objs.append(("disk", rd("3f"), rd("3f"), rd("f"), mat()))
+        elif tag in (4, 5, 6):
+            objs.append(({4: "xyrect", 5: "xzrect", 6: "yzrect"}[tag], rd("5f"), mat()))
+        elif tag == 7:
+            objs.append(("box", rd("3f"), rd("3f"), mat()))
+        elif tag == 8:
+            objs.append(("cyl", rd("3f"), rd("f"), rd("f"), rd("f"), rd("B"), mat()))
+        elif tag == 9:
+            objs.append(("tri", rd("3f"), rd("3f"), rd("3f"), mat()))
+        else:
+            raise AssertionError(f"unknown tag {tag}")
+    assert at[0] == len(b)
+    out["objects"] = objs
+    return out
+
+
+def test_scne_snapshot_format_and_round_trip(tmp_path):
+    """The engine's 'SCNE' v1 scene snapshot (SceneSyncProtocol, Scenes/SyncScene.cs:267-569) as a scene interchange: the bytes
+    the mirror writes parse with an independent transcription of ReadSnapshot, the writer's quirks are kept (material functions
+    baked at one point, boxes written as the grey stand-in, meshes skipped), and a snapshot loads back into a renderable scene."""
+    f32 = lambda x: float(np.float32(x))
+    # mirror spheres: checker floor (XZRect) + 3 spheres, 2 lights (Scenes.cs:311-335)
+    s = api.HostScene("mirror_spheres")
+    p = str(tmp_path / "ms.scne")
+    n = s.write_snapshot(p)
+    d = parse_scne(open(p, "rb").read())
+    assert n == os.path.getsize(p) == 8 + 4 * (3 + 3 + 3 + 1 + 1 + 3 + 1 + 1) + 4 + 2 * 28 + 4 + (1 + 20 + 52) + 3 * (1 + 16 + 52)  # a material is 13 floats
+    assert d["fov"] == 45.0 and d["cam"] == (0.0, 1.0, 0.0) and d["amb_i"] == f32(0.01) and len(d["lights"]) == 2
+    assert d["lights"][0] == ((-2.5, 3.5, -1.5), (1.0, f32(0.95), f32(0.9)), 90.0)
+    kinds = [o[0] for o in d["objects"]]
+    assert kinds == ["xzrect", "sphere", "sphere", "sphere"]
+    floor = d["objects"][0]
+    assert floor[1] == (-8.0, 8.0, -8.0, 4.0, 0.0)
+    # Checker(0.8, 0.15, 0.6) baked at the rect's centre (0, 0, -2): cx = 0, cz = floor(-2/0.6) = -4 -> even -> colour a; specular 0.1
+    assert floor[2]["albedo"] == (f32(0.8),) * 3 and floor[2]["spec"] == f32(0.1) and floor[2]["refl"] == 0.0
+    assert d["objects"][1][1:3] == ((f32(-1.2), 1.0, -2.0), 1.0) and d["objects"][1][3]["refl"] == f32(0.1)
+    t = api.HostScene("snapshot:" + p)
+    assert t.name == "snapshot" and t.counts()["objects"] == 4 and t.counts()["lights"] == 2
+    # a snapshot of the snapshot is the same bytes (the format is a fixed point of write . read)
+    p2 = str(tmp_path / "ms2.scne")
+    t.write_snapshot(p2)
+    assert open(p2, "rb").read() == open(p, "rb").read()
+    # the loaded scene renders (CPU oracle), and differs from the original only where the checker was baked to one colour
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_binding import Oracle
+    a, b = Oracle(s, 24, 8, 2), Oracle(t, 24, 8, 2)
+    ca, cb = a.render_frame(threads=2), b.render_frame(threads=2)
+    assert ca.shape == cb.shape and (ca["fg_ansi"] != cb["fg_ansi"]).mean() < 0.5
+    assert np.array_equal(a.debug_read(api.DBG_PRIM_ID), b.debug_read(api.DBG_PRIM_ID))  # same geometry, same primary hits
+    a.close(); b.close(); s.close(); t.close()
+    # boxes: every Box is written with the writer's grey stand-in material; the plane keeps its baked checker colour
+    s = api.HostScene("boxes")
+    p = str(tmp_path / "bx.scne")
+    s.write_snapshot(p)
+    d = parse_scne(open(p, "rb").read())
+    assert [o[0] for o in d["objects"]] == ["plane", "box", "box", "box"]
+    for o in d["objects"][1:]:
+        assert o[3]["albedo"] == (f32(0.82),) * 3 and o[3]["spec"] == f32(0.02) and o[3]["refl"] == 0.0
+    s.close()
+    # cylinders / disks / triangles, and a mesh scene: the mesh is skipped, the ground plane stays
+    s = api.HostScene("cylinders_disks_triangles")
+    s.write_snapshot(p)
+    assert [o[0] for o in parse_scne(open(p, "rb").read())["objects"]] == ["plane", "cyl", "disk", "tri"]
+    s.close()
+    s = api.HostScene("teapot")
+    s.write_snapshot(p)
+    assert [o[0] for o in parse_scne(open(p, "rb").read())["objects"]] == ["plane"]
+    s.close()
+    with pytest.raises(ValueError):
+        open(p, "wb").write(b"NOPE" + bytes(60))
+        api.HostScene("snapshot:" + p)

@@ -213,6 +213,7 @@ def load_host() -> C.CDLL:
         h.ycgeh_scene_mesh.argtypes = [vp, C.c_int]
         h.ycgeh_scene_mesh.restype = C.POINTER(MeshSoa)
         h.ycgeh_scene_n_volumes.argtypes = [vp]
+        h.ycgeh_scene_write_snapshot.argtypes = [vp, C.c_char_p]
         h.ycgeh_scene_n_textures.argtypes = [vp]
         h.ycgeh_scene_texture.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         h.ycgeh_scene_texture.restype = C.POINTER(C.c_uint32)
@@ -307,6 +308,14 @@ class HostScene:
     @property
     def n_meshes(self) -> int:
         return self._h.ycgeh_scene_n_meshes(self.handle)
+
+    def write_snapshot(self, path: str) -> int:
+        """SceneSyncProtocol.WriteSnapshot (Scenes/SyncScene.cs:282-393): the engine's 'SCNE' v1 snapshot of this scene; load it
+        back with HostScene("snapshot:<path>").  Returns the number of bytes written."""
+        n = self._h.ycgeh_scene_write_snapshot(self.handle, path.encode())
+        if n < 0:
+            raise ValueError(self._h.ycgeh_last_error().decode())
+        return n
 
     @property
     def n_textures(self) -> int:

@@ -888,9 +888,136 @@ std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
         return VolumeScenes::BuildSyntheticWorld(ws, wh, 32, 45.0f);
     }
     if (name == "voxel_world") return VolumeScenes::BuildSyntheticWorld(1024, 256, 32, 45.0f);
+    if (name.rfind("snapshot:", 0) == 0) { // an 'SCNE' v1 file (SceneSyncProtocol)
+        std::ifstream f(name.substr(9), std::ios::binary);
+        if (!f.good()) throw std::invalid_argument("cannot open scene snapshot: " + name.substr(9));
+        std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        auto sc = SceneSyncProtocol::ReadSnapshot(bytes);
+        sc->Update(0.0f);
+        return sc;
+    }
     if (name.rfind("voxel_world_file:", 0) == 0) return VolumeScenes::BuildWorldFromFile(name.substr(17), 32, 45.0f); // a VG01 world file
     throw std::invalid_argument("unknown scene: " + name);
 }
+
+
+// ---- SceneSyncProtocol: Scenes/SyncScene.cs:267-569 -------------------------------------------------------------
+namespace SceneSyncProtocol {
+namespace {
+const uint32_t MAGIC = 0x53434E45u, VERSION = 1u; // 'SCNE' :269-270
+enum : uint8_t { T_SPHERE = 1, T_PLANE_SOLID = 2, T_DISK_SOLID = 3, T_XYRECT_SOLID = 4, T_XZRECT_SOLID = 5, T_YZRECT_SOLID = 6, T_BOX_SOLID = 7, T_CYL_Y = 8, T_TRIANGLE = 9 };
+struct Writer { // BinaryWriter: little endian, no padding
+    std::vector<uint8_t> b;
+    void Raw(const void *p, size_t n) { const uint8_t *q = (const uint8_t *)p; b.insert(b.end(), q, q + n); }
+    void U32(uint32_t v) { Raw(&v, 4); }
+    void I32(int32_t v) { Raw(&v, 4); }
+    void F32(float v) { Raw(&v, 4); }
+    void U8(uint8_t v) { b.push_back(v); }
+    void V3(Vec3 v) { F32(v.X); F32(v.Y); F32(v.Z); }                                       // :552-557
+    void Mat(const Material &m) {                                                          // :531-542 (textures are not serialised)
+        V3(m.Albedo); F32((float)m.Specular); F32((float)m.Reflectivity); V3(m.Emission);
+        F32((float)m.Transparency); F32((float)m.IndexOfRefraction); V3(m.TransmissionColor);
+    }
+};
+struct Reader {
+    const std::vector<uint8_t> &b;
+    size_t at = 0;
+    explicit Reader(const std::vector<uint8_t> &bytes) : b(bytes) {}
+    void Raw(void *p, size_t n) { if (at + n > b.size()) throw std::invalid_argument("Unable to read beyond the end of the stream."); memcpy(p, &b[at], n); at += n; }
+    uint32_t U32() { uint32_t v; Raw(&v, 4); return v; }
+    int32_t I32() { int32_t v; Raw(&v, 4); return v; }
+    float F32() { float v; Raw(&v, 4); return v; }
+    uint8_t U8() { uint8_t v; Raw(&v, 1); return v; }
+    Vec3 V3() { float x = F32(), y = F32(), z = F32(); return Vec3(x, y, z); }               // :559-565
+    Material Mat() {                                                                        // :544-554
+        Vec3 albedo = V3(); float spec = F32(), refl = F32(); Vec3 emit = V3(); float transp = F32(), ior = F32(); Vec3 transCol = V3();
+        return Material(albedo, spec, refl, emit, transp, ior, transCol);
+    }
+};
+// MaterialFunc(pos, n, u) for the closed set of material functions (Scenes.cs:408-428)
+Material Eval(const MaterialFunc &f, Vec3 pos) {
+    if (f.scale == 0.0f) return f.a;
+    int cx = (int)std::floor(pos.X / f.scale), cz = (int)std::floor(pos.Z / f.scale);
+    return ((cx + cz) & 1) == 0 ? f.a : f.b;
+}
+Material BakeSpecRefl(const Material &m, float specular, float reflectivity) { // :522-529 (the texture reference is kept in memory, never written)
+    Material o(m.Albedo, specular, reflectivity, m.Emission, m.Transparency, m.IndexOfRefraction, m.TransmissionColor);
+    o.DiffuseTexture = m.DiffuseTexture; o.TextureWeight = m.TextureWeight; o.UVScale = m.UVScale;
+    return o;
+}
+} // namespace
+
+std::vector<uint8_t> WriteSnapshot(const Scene &scene) { // :282-393
+    Writer w;
+    w.U32(MAGIC); w.U32(VERSION);
+    w.V3(scene.BackgroundTop); w.V3(scene.BackgroundBottom); w.V3(scene.Ambient.Color); w.F32(scene.Ambient.Intensity);
+    w.F32(scene.DefaultFovDeg); w.V3(scene.DefaultCameraPos); w.F32(scene.DefaultYaw); w.F32(scene.DefaultPitch);
+    w.I32((int32_t)scene.Lights.size());
+    for (const PointLight &L : scene.Lights) { w.V3(L.Position); w.V3(L.Color); w.F32(L.Intensity); }
+    const size_t countAt = w.b.size();
+    w.I32(0);
+    int32_t written = 0;
+    for (const auto &o : scene.Objects) {
+        if (auto s = dynamic_cast<const Sphere *>(o.get())) {
+            w.U8(T_SPHERE); w.V3(s->Center); w.F32(s->Radius); w.Mat(s->Mat); written++;
+        } else if (auto p = dynamic_cast<const Plane *>(o.get())) {
+            w.U8(T_PLANE_SOLID); w.V3(p->Point); w.V3(p->Normal); w.Mat(BakeSpecRefl(Eval(p->MatFunc, p->Point), p->Specular, p->Reflectivity)); written++;
+        } else if (auto d = dynamic_cast<const Disk *>(o.get())) {
+            w.U8(T_DISK_SOLID); w.V3(d->Center); w.V3(d->Normal); w.F32(d->Radius); w.Mat(BakeSpecRefl(Eval(d->MatFunc, d->Center), d->Specular, d->Reflectivity)); written++;
+        } else if (auto r = dynamic_cast<const AxisRect *>(o.get())) {
+            float ca = (r->A0 + r->A1) * 0.5f, cb = (r->B0 + r->B1) * 0.5f;
+            Vec3 c = r->Kind == YCGE_XYRECT ? Vec3(ca, cb, r->K) : r->Kind == YCGE_XZRECT ? Vec3(ca, r->K, cb) : Vec3(r->K, ca, cb);
+            w.U8(r->Kind == YCGE_XYRECT ? T_XYRECT_SOLID : r->Kind == YCGE_XZRECT ? T_XZRECT_SOLID : T_YZRECT_SOLID);
+            w.F32(r->A0); w.F32(r->A1); w.F32(r->B0); w.F32(r->B1); w.F32(r->K);
+            w.Mat(BakeSpecRefl(Eval(r->MatFunc, c), r->Specular, r->Reflectivity)); written++;
+        } else if (auto bx = dynamic_cast<const Box *>(o.get())) { // the writer cannot see the faces' material: a grey stand-in (:350-359)
+            w.U8(T_BOX_SOLID); w.V3(bx->Min); w.V3(bx->Max);
+            w.Mat(BakeSpecRefl(Material(Vec3(0.82f, 0.82f, 0.82f), 0.02, 0.0, Vec3()), 0.02f, 0.0f)); written++;
+        } else if (auto cy = dynamic_cast<const CylinderY *>(o.get())) {
+            w.U8(T_CYL_Y); w.V3(cy->Center); w.F32(cy->Radius); w.F32(cy->YMin); w.F32(cy->YMax); w.U8(cy->Capped ? 1 : 0); w.Mat(cy->Mat); written++;
+        } else if (auto t = dynamic_cast<const Triangle *>(o.get())) {
+            w.U8(T_TRIANGLE); w.V3(t->A); w.V3(t->B); w.V3(t->C); w.Mat(t->Mat); written++;
+        } // Mesh, VolumeGrid: skipped (:384-387)
+    }
+    memcpy(&w.b[countAt], &written, 4);
+    return w.b;
+}
+
+std::shared_ptr<Scene> ReadSnapshot(const std::vector<uint8_t> &bytes) { // :395-520
+    Reader r(bytes);
+    if (r.U32() != MAGIC) throw std::invalid_argument("Bad scene snapshot magic.");
+    if (r.U32() != VERSION) throw std::invalid_argument("Unsupported scene snapshot version.");
+    auto s = std::make_shared<Scene>();
+    s->Name = "snapshot";
+    s->BackgroundTop = r.V3(); s->BackgroundBottom = r.V3();
+    Vec3 ambC = r.V3(); float ambI = r.F32();
+    s->Ambient = AmbientLight(ambC, ambI);
+    s->DefaultFovDeg = r.F32(); s->DefaultCameraPos = r.V3(); s->DefaultYaw = r.F32(); s->DefaultPitch = r.F32();
+    int lightCount = r.I32();
+    for (int i = 0; i < lightCount; i++) { Vec3 lp = r.V3(), lc = r.V3(); float li = r.F32(); s->Lights.push_back(PointLight(lp, lc, li)); }
+    int objCount = r.I32();
+    for (int i = 0; i < objCount; i++) {
+        uint8_t tag = r.U8();
+        switch (tag) {
+            case T_SPHERE: { Vec3 c = r.V3(); float rad = r.F32(); Material m = r.Mat(); s->Add(std::make_shared<Sphere>(c, rad, m)); break; }
+            case T_PLANE_SOLID: { Vec3 p = r.V3(), n = r.V3(); Material m = r.Mat(); s->Add(std::make_shared<Plane>(p, n, Constant(m), (float)m.Specular, (float)m.Reflectivity)); break; }
+            case T_DISK_SOLID: { Vec3 c = r.V3(), n = r.V3(); float rad = r.F32(); Material m = r.Mat(); s->Add(std::make_shared<Disk>(c, n, rad, Constant(m), (float)m.Specular, (float)m.Reflectivity)); break; }
+            case T_XYRECT_SOLID: case T_XZRECT_SOLID: case T_YZRECT_SOLID: {
+                float a0 = r.F32(), a1 = r.F32(), b0 = r.F32(), b1 = r.F32(), k = r.F32();
+                Material m = r.Mat();
+                int kind = tag == T_XYRECT_SOLID ? YCGE_XYRECT : tag == T_XZRECT_SOLID ? YCGE_XZRECT : YCGE_YZRECT;
+                s->Add(std::make_shared<AxisRect>(kind, a0, a1, b0, b1, k, Constant(m), (float)m.Specular, (float)m.Reflectivity));
+                break; }
+            case T_BOX_SOLID: { Vec3 mn = r.V3(), mx = r.V3(); Material m = r.Mat(); s->Add(std::make_shared<Box>(mn, mx, Constant(m), (float)m.Specular, (float)m.Reflectivity)); break; }
+            case T_CYL_Y: { Vec3 c = r.V3(); float rad = r.F32(), yMin = r.F32(), yMax = r.F32(); bool capped = r.U8() != 0; Material m = r.Mat(); s->Add(std::make_shared<CylinderY>(c, rad, yMin, yMax, capped, m)); break; }
+            case T_TRIANGLE: { Vec3 a = r.V3(), b = r.V3(), c = r.V3(); Material m = r.Mat(); s->Add(std::make_shared<Triangle>(a, b, c, m)); break; }
+            default: throw std::invalid_argument("Unknown object tag in snapshot.");
+        }
+    }
+    s->ResetCamera(); // as the client's CopyFrom does with the snapshot (:244-258)
+    return s;
+}
+} // namespace SceneSyncProtocol
 
 // ---- Framebuffer ------------------------------------------------------------------------------------------------
 Framebuffer::Framebuffer(int width, int height) : Width(width), Height(height), chexels((size_t)width * height) {
@@ -1123,6 +1250,15 @@ YH_API int ycgeh_obj_to_ymesh(const char *obj_path, const char *out_path) { // f
         for (const Vec3 &p : d.positions) { float v[3] = {p.X, p.Y, p.Z}; o.write((const char *)v, 12); }
         o.write((const char *)d.faces.data(), (std::streamsize)((size_t)nf * 4));
         return o.good() ? 0 : -1;
+    } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_scene_write_snapshot(void *h, const char *path) { // SceneSyncProtocol.WriteSnapshot of the scene
+    try {
+        std::vector<uint8_t> b = SceneSyncProtocol::WriteSnapshot(*((SceneHandle *)h)->scene);
+        std::ofstream f(path, std::ios::binary);
+        if (!f.good()) { yh_error = std::string("cannot write ") + path; return -1; }
+        f.write((const char *)b.data(), (std::streamsize)b.size());
+        return (int)b.size();
     } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
 YH_API int ycgeh_write_synthetic_world(const char *path, int world_size, int world_height) { // a VG01 file of the synthetic world (tests)

@@ -226,6 +226,15 @@ class SceneExport {
     void AddFunc(ycge_object &o, const MaterialFunc &f, float specular, float reflectivity);
 };
 
+// ---- SceneSyncProtocol (Scenes/SyncScene.cs:267-569): the engine's 'SCNE' v1 scene snapshot, used here as a scene
+// interchange format for the harness.  Quirks kept: material functions are baked by ONE call at a fixed point (a checker
+// floor becomes the colour under that point), a Box is always written as the writer's grey stand-in material (:350-359),
+// textures are not serialised (:541), meshes and volume grids are skipped (:384-387).
+namespace SceneSyncProtocol {
+std::vector<uint8_t> WriteSnapshot(const Scene &scene);
+std::shared_ptr<Scene> ReadSnapshot(const std::vector<uint8_t> &bytes);
+} // namespace SceneSyncProtocol
+
 // ---- scene factories (BuildSceneTable(), RaytraceEntity.cs:319-344) --------------------------------------------
 namespace Scenes { // Scenes/Scenes.cs
 std::shared_ptr<Scene> BuildTestScene();
