@@ -333,6 +333,25 @@ int alloc_slots(ycge_ctx *c, int n) {
     return 0;
 }
 
+// back slots of the frame-parallel path (ycge_back_config); re-created by ycge_resize
+int alloc_back_slots(ycge_ctx *c, int n_slots) { // the caller has synchronised the device
+    c->back_slots.clear();
+    const size_t px = (size_t)c->W * c->H;
+    for (int k = 0; k < n_slots; k++) {
+        std::unique_ptr<ycge_ctx::BackSlot> b(new ycge_ctx::BackSlot());
+        CK(c, b->hist.alloc(px)); CK(c, b->gnd.alloc(px)); CK(c, b->gas.alloc(px)); CK(c, b->sa.alloc(px)); CK(c, b->sb.alloc(px));
+        CK(c, b->pre.alloc(px * 25));
+        CK(c, b->logs.alloc((size_t)c->sw * c->sh));
+        CK(c, b->cells.alloc((size_t)c->fbW * c->fbH));
+        CK(c, cudaMemset(b->hist.p, 0, px * sizeof(float4))); CK(c, cudaMemset(b->gnd.p, 0, px * sizeof(float4))); CK(c, cudaMemset(b->gas.p, 0, px * sizeof(float4)));
+        CK(c, cudaMemset(b->sa.p, 0, px * sizeof(float4))); CK(c, cudaMemset(b->sb.p, 0, px * sizeof(float4)));
+        CK(c, cudaMemset(b->logs.p, 0, b->logs.n * sizeof(float)));
+        CK(c, cudaMemset(b->cells.p, 0, b->cells.n * sizeof(ycge_cell)));
+        c->back_slots.push_back(std::move(b));
+    }
+    return 0;
+}
+
 int alloc_planes(ycge_ctx *c) {
     size_t n = (size_t)c->W * c->H;
     CK(c, c->cur.alloc(n)); CK(c, c->gnd0.alloc(n)); CK(c, c->gnd1.alloc(n)); CK(c, c->gas0.alloc(n)); CK(c, c->gas1.alloc(n));
@@ -852,6 +871,7 @@ YCGE_API int ycge_resize(ycge_ctx *c, int32_t fb_w, int32_t fb_h, int32_t ss) {
     if (c->sharded && row0 + rows > fb_h) return fail(c, YCGE_ERR_INVALID, "tile exceeds resized framebuffer");
     int rc = set_geometry(c, fb_w, fb_h, ss, row0, rows);
     if (rc) return rc;
+    if (!c->back_slots.empty()) { rc = alloc_back_slots(c, (int)c->back_slots.size()); if (rc) return rc; } // same number, new geometry
     if (c->debug_rays) CK(c, c->rays_dbg.alloc((size_t)c->W * c->H * 6));
     // TemporalAA.Resize (TemporalAA.cs:33-45): the camera memory is cleared; frame counter and exposure survive (:110-138)
     c->last_cam[0] = c->last_cam[1] = c->last_cam[2] = NAN; c->last_yaw = NAN; c->last_pitch = NAN;
@@ -1303,19 +1323,7 @@ YCGE_API int ycge_back_config(ycge_ctx *c, int32_t n_slots) {
     if (c->sharded) return fail(c, YCGE_ERR_INVALID, "the BACK runs on a whole-frame ctx");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaDeviceSynchronize());
-    c->back_slots.clear();
-    const size_t px = (size_t)c->W * c->H;
-    for (int k = 0; k < n_slots; k++) {
-        std::unique_ptr<ycge_ctx::BackSlot> b(new ycge_ctx::BackSlot());
-        CK(c, b->hist.alloc(px)); CK(c, b->gnd.alloc(px)); CK(c, b->gas.alloc(px)); CK(c, b->sa.alloc(px)); CK(c, b->sb.alloc(px));
-        CK(c, b->pre.alloc(px * 25));
-        CK(c, b->logs.alloc((size_t)c->sw * c->sh));
-        CK(c, b->cells.alloc((size_t)c->fbW * c->fbH));
-        CK(c, cudaMemset(b->sa.p, 0, px * sizeof(float4))); CK(c, cudaMemset(b->sb.p, 0, px * sizeof(float4)));
-        CK(c, cudaMemset(b->logs.p, 0, b->logs.n * sizeof(float)));
-        c->back_slots.push_back(std::move(b));
-    }
-    return 0;
+    return alloc_back_slots(c, n_slots);
 }
 YCGE_API int ycge_back_ptr(ycge_ctx *c, int32_t slot, int32_t kind, void **ptr, size_t *bytes) {
     if (!c || !ptr || !bytes || slot < 0 || slot >= (int)c->back_slots.size()) return fail(c, YCGE_ERR_INVALID, "bad argument");
