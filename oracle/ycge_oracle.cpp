@@ -2022,6 +2022,12 @@ YO_API int yo_debug_read(void *h, int kind, void *dst, size_t bytes) {
     }
     return YCGE_ERR_INVALID;
 }
+/* gNormal as TraceFull wrote it (not normalised), hiW*hiH*3 floats: input of the literal TAA transcription in the tests */
+YO_API int yo_debug_raw_normal(void *h, float *dst) {
+    Renderer *r = (Renderer *)h;
+    for (size_t i = 0; i < r->gNormal.size(); i++) { dst[3 * i] = r->gNormal[i].X; dst[3 * i + 1] = r->gNormal[i].Y; dst[3 * i + 2] = r->gNormal[i].Z; }
+    return 0;
+}
 /* ---- tree export for builder-parity tests: which = -1 top-level, else mesh id ---- */
 YO_API int yo_bvh_info(void *h, int which, int *n_nodes, int *root, int *n_leaf, uint64_t *sort_fallbacks) {
     Renderer *r = (Renderer *)h;

@@ -45,6 +45,7 @@ def load_oracle():
         o.yo_render_frame.argtypes = [vp, vp, C.c_int, C.c_int]
         o.yo_get_stats.argtypes = [vp, C.POINTER(api.Stats)]
         o.yo_debug_read.argtypes = [vp, C.c_int, vp, C.c_size_t]
+        o.yo_debug_raw_normal.argtypes = [vp, vp]
         o.yo_bvh_info.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         o.yo_bvh_read.argtypes = [vp, C.c_int, vp, vp, vp]
         o.yo_mesh_soa_read.argtypes = [vp, C.c_int, vp]
@@ -194,6 +195,11 @@ class Oracle:
         else:
             a = np.empty((self.hi_h, self.hi_w, 4), np.float32)
         assert self.o.yo_debug_read(self.h, kind, _ptr(a), a.nbytes) == 0
+        return a
+
+    def raw_normal(self):
+        a = np.empty((self.hi_h, self.hi_w, 3), np.float32)
+        assert self.o.yo_debug_raw_normal(self.h, _ptr(a)) == 0
         return a
 
     def bvh_arrays(self, which=-1):

@@ -181,3 +181,167 @@ def test_history_reset_and_exposure_state_machine():
     assert o.stats()["frames"] == 4
     assert 0.10 <= o.stats()["ae_exposure"] <= 1.50 and ae1 != 1.0
     o.close()
+
+
+# ---- literal transcriptions of the image stages around the à-trous filter, numpy binary32 scalars, one operation at a time ----
+F = np.float32
+
+
+def _luma(c):  # RaytraceRenderer.cs:269-272
+    return F(F(F(F(0.2126) * c[0]) + F(F(0.7152) * c[1])) + F(F(0.0722) * c[2]))
+
+
+def _normalized(v):  # Vec3.cs:98-107
+    l2 = F(F(F(v[0] * v[0]) + F(v[1] * v[1])) + F(v[2] * v[2]))
+    if l2 <= 0:
+        return v
+    inv = F(F(1.0) / np.sqrt(l2, dtype=F))
+    return np.array([v[0] * inv, v[1] * inv, v[2] * inv], F)
+
+
+class TaaLiteral:
+    """TemporalBlendWithClamp (RaytraceRenderer.cs:274-398): state = taaHistory, prevNormal, prevDepth, prevSky."""
+
+    def __init__(self, alpha=0.01, pad=0.10):
+        self.valid, self.alpha, self.pad = False, F(alpha), F(pad)
+
+    def blend(self, current, normal, depth, sky, force_reset):
+        h, w = sky.shape
+        if not self.valid or force_reset:
+            self.hist, self.pn, self.pd, self.ps = current.copy(), normal.copy(), depth.copy(), sky.copy()
+            self.valid = True
+            return self.hist
+        alpha = max(F(0), min(F(1), self.alpha))
+        for y in range(h):
+            for x in range(w):
+                cur, prev = current[y, x], self.hist[y, x].copy()
+                local = alpha
+                if sky[y, x] != self.ps[y, x]:
+                    local = F(1)
+                else:
+                    z_now, z_prev = depth[y, x], self.pd[y, x]
+                    n_now, n_prev = _normalized(normal[y, x]), _normalized(self.pn[y, x])
+                    if not np.isfinite(z_now) or not np.isfinite(z_prev):
+                        local = F(1)
+                    else:
+                        dz = abs(F(z_now - z_prev))
+                        rel = F(dz / max(F(1e-4), min(z_now, z_prev)))
+                        ndot = F(F(F(n_now[0] * n_prev[0]) + F(n_now[1] * n_prev[1])) + F(n_now[2] * n_prev[2]))
+                        if rel > F(0.05) or ndot < F(0.8):
+                            local = F(1)
+                min_l, max_l = F(np.inf), F(-np.inf)
+                for oy in (-1, 0, 1):
+                    sy = min(max(y + oy, 0), h - 1)
+                    for ox in (-1, 0, 1):
+                        sx = min(max(x + ox, 0), w - 1)
+                        if sky[sy, sx] != sky[y, x]:
+                            continue
+                        l = _luma(current[sy, sx])
+                        if l < min_l:
+                            min_l = l
+                        if l > max_l:
+                            max_l = l
+                rng = F(max_l - min_l)
+                l_min, l_max = F(min_l - F(rng * self.pad)), F(max_l + F(rng * self.pad))
+                prev_l = _luma(prev)
+                if prev_l > l_max:
+                    s = F(l_max / max(F(1e-6), prev_l))
+                    prev = np.array([prev[0] * s, prev[1] * s, prev[2] * s], F)
+                elif prev_l < l_min:
+                    s = F(l_min / max(F(1e-6), prev_l))
+                    prev = np.array([prev[0] * s, prev[1] * s, prev[2] * s], F)
+                one_m = F(F(1) - local)
+                self.hist[y, x] = [F(F(prev[k] * one_m) + F(cur[k] * local)) for k in range(3)]
+        self.pn, self.pd, self.ps = normal.copy(), depth.copy(), sky.copy()
+        return self.hist
+
+
+def update_exposure_literal(ae, hdr, sky, step, log_f, exp_f, key=0.18, speed=0.2, lo=0.10, hi=1.50):
+    """ToneMapper.UpdateExposure (ToneMapper.cs:49-91); returns the new aeExposure (= effectiveExposure: toneExposure is 1)."""
+    h, w = sky.shape
+    log_sum, cnt = F(0), 0
+    for py in range(0, h, step):
+        for px in range(0, w, step):
+            if sky[py, px]:
+                continue
+            c = hdr[py, px]
+            lum = F(F(F(F(0.2126) * c[0]) + F(F(0.7152) * c[1])) + F(F(0.0722) * c[2]))
+            if lum > 0:
+                log_sum = F(log_sum + log_f(F(F(1e-6) + lum)))
+                cnt += 1
+    avg_log = F(log_sum / F(max(1, cnt))) if cnt > 0 else F(0)
+    avg_lum = exp_f(avg_log)
+    target = F(F(key) / max(F(1e-6), avg_lum)) if cnt > 0 else ae
+    target = min(max(target, F(lo)), F(hi))
+    s = F(F(1) - exp_f(F(-F(speed))))
+    return F(ae + F(F(target - ae) * s))
+
+
+def cells_literal(den, fb_w, fb_h, ss, exposure, pow_f, gamma=2.2, saturation=2.0, vibrance=0.0):
+    """The cell loop (RaytraceRenderer.cs:229-264) + ToneMapper.MapPixel (ToneMapper.cs:155-159, :204-260): fg = top, bg = bottom."""
+    sat01 = lambda v: F(0) if v < 0 else (F(1) if v > 1 else v)
+
+    def aces(x):
+        num = F(x * F(F(F(2.51) * x) + F(0.03)))
+        den_ = F(F(x * F(F(F(2.43) * x) + F(0.59))) + F(0.14))
+        y = F(num / den_) if den_ > 0 else F(0)
+        return sat01(y)
+
+    def map_pixel(c):
+        rgb = [aces(F(max(F(0), c[k]) * exposure)) for k in range(3)]
+        inv_gamma = F(F(1) / max(F(0.1), F(gamma)))
+        r, g, b = (sat01(pow_f(sat01(v), inv_gamma)) for v in rgb)
+        y = F(F(F(F(0.2126) * r) + F(F(0.7152) * g)) + F(F(0.0722) * b))
+        chroma = F(max(r, max(g, b)) - min(r, min(g, b)))
+        f = F(F(saturation) * F(F(1) + F(F(vibrance) * F(F(1) - chroma))))
+        return [sat01(F(y + F(F(v - y) * f))) for v in (r, g, b)]
+
+    fg, bg = np.zeros((fb_h, fb_w, 3), F), np.zeros((fb_h, fb_w, 3), F)
+    inv = F(F(1) / F(ss * ss))
+    for cy in range(fb_h):
+        for cx in range(fb_w):
+            top, bot = np.zeros(3, F), np.zeros(3, F)
+            for sy in range(ss):
+                for sx in range(ss):
+                    top = top + den[cy * 2 * ss + sy, cx * ss + sx]
+                    bot = bot + den[(cy * 2 + 1) * ss + sy, cx * ss + sx]
+            fg[cy, cx] = map_pixel([F(top[k] * inv) for k in range(3)])
+            bg[cy, cx] = map_pixel([F(bot[k] * inv) for k in range(3)])
+    return fg, bg
+
+
+def test_taa_exposure_and_cell_conversion_match_literal_restatements():
+    """Four frames of a scene with sky and geometry (the camera moves before the fourth, below the reset threshold): the
+    oracle's TAA history, exposure recursion and cell colours against transcriptions written straight from
+    RaytraceRenderer.cs:229-398 and ToneMapper.cs:49-260, which share nothing with the oracle but the three transcendental
+    functions of include/ycge_detmath.h."""
+    lib = load_oracle()
+    lib.yo_set_math_mode(0)
+    exp_f = lambda x: F(lib.yo_math(0, float(x), 0.0))
+    log_f = lambda x: F(lib.yo_math(1, float(x), 0.0))
+    pow_f = lambda x, y: F(lib.yo_math(2, float(x), float(y)))
+    s = api.HostScene("boxes")
+    fb_w, fb_h, ss = 12, 5, 2
+    o = Oracle(s, fb_w, fb_h, ss)
+    taa, ae = TaaLiteral(), F(1.0)
+    pos, yaw, pitch, _ = s.default_camera()
+    with np.errstate(over="ignore", invalid="ignore"):
+        for f in range(4):
+            if f == 3:
+                o.set_camera((pos[0] + 0.001, pos[1], pos[2]), yaw, pitch)  # moves, but by less than the reset threshold 0.0025
+            cells = o.render_frame(threads=1)
+            hdr = o.debug_read(api.DBG_HDR)[..., :3].copy()
+            nd, als = o.debug_read(api.DBG_NORMAL_DEPTH), o.debug_read(api.DBG_ALBEDO_SKY)
+            sky = als[..., 3] != 0
+            assert 0 < sky.sum() < sky.size
+            hist = taa.blend(hdr, o.raw_normal(), nd[..., 3].copy(), sky, force_reset=False)
+            assert np.array_equal(hist.view(np.uint32), o.debug_read(api.DBG_TAA)[..., :3].view(np.uint32)), f"TAA history, frame {f + 1}"
+            den = o.debug_read(api.DBG_DENOISED)[..., :3].copy()
+            ae = update_exposure_literal(ae, den, sky, max(2, 2 * ss), log_f, exp_f)
+            assert ae.view(np.uint32) == F(o.stats()["ae_exposure"]).view(np.uint32), f"aeExposure, frame {f + 1}"
+            fg, bg = cells_literal(den, fb_w, fb_h, ss, ae, pow_f)
+            assert np.array_equal(fg.view(np.uint32), np.ascontiguousarray(cells["fg"]).view(np.uint32)), f"cell fg, frame {f + 1}"
+            assert np.array_equal(bg.view(np.uint32), np.ascontiguousarray(cells["bg"]).view(np.uint32)), f"cell bg, frame {f + 1}"
+    assert (taa.hist != hdr).any()  # frames 2-4 really blended
+    o.close()
+    s.close()
