@@ -1,0 +1,454 @@
+"""The trace stage pinned by a second, independent restatement: MakeJitteredRay, the per-pixel RNG, TraceFull with its explicit
+work stack, ComputeTransmittanceToLight, OrenNayarBRDF, CosineSampleHemisphere, Scene.Hit -> BVH.Hit / BoxHitFast, Sphere.Hit,
+Plane.Hit, the three axis rects, Box.Hit (six rects, shrinking closest) and the Checker material function, transcribed from
+the C# source into numpy binary32 scalars, one operation at a time (RayTracing/RaytraceRenderer.cs:413-620,:757-831, RaytraceSampler.cs, Objects/BVH.cs:99-236, BoundedObjects.cs:31-69,
+:78-115, Surfaces.cs:184-358, Scenes/Scenes.cs:418-428).  It shares nothing with the oracle's C++ but the transcendental functions
+of include/ycge_detmath.h (sin, cos, tan) and the scene description; the tree it walks is the HOST mirror's, built by a
+third implementation.  Radiance, G-buffer, sky flag and primary ids of every pixel must equal the oracle's bit for bit,
+on a scene with a true mirror (reflectivity 0.9 = MirrorThreshold), one with a checker floor, the Cornell box (emissive
+rect, closed room, boxes) and the boxes showcase (plane + boxes), over two frames.  (Disks, cylinders, triangles, meshes,
+voxels and transparent materials are outside this transcription.)
+"""
+import numpy as np
+import pytest
+
+from yetanotherconsolegameengine_b200 import api
+from oracle_binding import Oracle, load_oracle
+
+F = np.float32
+M64 = (1 << 64) - 1
+FLT_MAX = F(3.4028234663852886e38)
+BLUE = [[0, 32, 8, 40, 2, 34, 10, 42], [48, 16, 56, 24, 50, 18, 58, 26], [12, 44, 4, 36, 14, 46, 6, 38], [60, 28, 52, 20, 62, 30, 54, 22],
+        [3, 35, 11, 43, 1, 33, 9, 41], [51, 19, 59, 27, 49, 17, 57, 25], [15, 47, 7, 39, 13, 45, 5, 37], [63, 31, 55, 23, 61, 29, 53, 21]]  # RaytraceSampler.cs:9-19
+
+EPS, MIRROR_THRESHOLD, MAX_MIRROR, MAX_REFR, DIFFUSE_BOUNCES = F(1e-4), F(0.9), 2, 2, 1  # RaytraceRenderer.cs:31-36
+PI, SIGMA_DEG = F(3.14159265358979323846), F(25.0)                                       # :63-65
+MATHF_PI = F(3.14159274)
+
+
+def v3(x, y, z):
+    return np.array([x, y, z], F)
+
+
+def dot(a, b):  # Vec3.Dot: (x*x' + y*y') + z*z'
+    return F(F(F(a[0] * b[0]) + F(a[1] * b[1])) + F(a[2] * b[2]))
+
+
+def cross(a, b):
+    return v3(F(F(a[1] * b[2]) - F(a[2] * b[1])), F(F(a[2] * b[0]) - F(a[0] * b[2])), F(F(a[0] * b[1]) - F(a[1] * b[0])))
+
+
+def normalized(v):  # Vec3.cs:98-107
+    l2 = F(F(F(v[0] * v[0]) + F(v[1] * v[1])) + F(v[2] * v[2]))
+    if l2 <= 0:
+        return v
+    inv = F(F(1) / np.sqrt(l2, dtype=F))
+    return v3(v[0] * inv, v[1] * inv, v[2] * inv)
+
+
+def vdiv(v, s):  # Vec3 operator / (Vec3.cs:68-71): multiply by the reciprocal
+    inv = F(F(1) / s)
+    return v3(v[0] * inv, v[1] * inv, v[2] * inv)
+
+
+def max_f(a, b):  # MathF.Max: NaN propagates
+    if a != a:
+        return a
+    if b != b:
+        return b
+    return a if a > b else b
+
+
+def min_f(a, b):
+    if a != a:
+        return a
+    if b != b:
+        return b
+    return a if a < b else b
+
+
+def frac(v):
+    return F(v - np.floor(v))
+
+
+def sm64(z):  # RaytraceSampler.cs:71-80
+    z = (z + 0x9E3779B97F4A7C15) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+class Rng:  # RaytraceSampler.cs:36-53
+    def __init__(self, seed):
+        self.state = seed if seed != 0 else 0x9E3779B97F4A7C15
+
+    def next_unit(self):
+        self.state = sm64(self.state)
+        m24 = self.state >> 40
+        return F(F(F(m24) + F(0.5)) * F(1.0 / 16777216.0))
+
+
+def per_frame_seed(x, y, frame, salt=0x9E3779B97F4A7C15):  # :56-68 with jx = jy = 0
+    h = 1469598103934665603
+    for v, k in ((x, 0x9E3779B97F4A7C15), (y, 0xC2B2AE3D27D4EB4F), (frame, 0x165667B19E3779F9)):
+        h ^= ((v & M64) * k) & M64
+        h = sm64(h)
+    h = sm64(h)  # h ^= 0
+    return sm64(h ^ salt)
+
+
+class LiteralTracer:
+    def __init__(self, scene: api.HostScene, lib):
+        flat = scene.flat.contents
+        self.mats = [flat.materials[i] for i in range(flat.n_materials)]
+        self.objs = [flat.objects[i] for i in range(flat.n_objects)]
+        self.lights = [(v3(*flat.lights[i].pos), v3(*flat.lights[i].color), F(flat.lights[i].intensity)) for i in range(flat.n_lights)]
+        self.bg_top, self.bg_bottom = v3(*flat.bg_top), v3(*flat.bg_bottom)
+        self.amb_c, self.amb_i = v3(*flat.ambient_color), F(flat.ambient_intensity)
+        self.tree = scene.bvh_arrays(-1)
+        self.sin = lambda x: F(lib.yo_math(3, float(x), 0.0))
+        self.cos = lambda x: F(lib.yo_math(4, float(x), 0.0))
+        self.tan = lambda x: F(lib.yo_math(5, float(x), 0.0))
+        self.rays = 0
+
+    # ---- materials: constant or Checker(a, b, scale) (Scenes.cs:418-428), then the object's Specular / Reflectivity (Surfaces.cs:279-281)
+    def material(self, o, pos):
+        m = self.mats[o.mat_a]
+        if o.checker_scale != 0.0:
+            cx = int(np.floor(F(pos[0] / F(o.checker_scale))))
+            cz = int(np.floor(F(pos[2] / F(o.checker_scale))))
+            m = self.mats[o.mat_a if ((cx + cz) & 1) == 0 else o.mat_b]
+        refl = F(o.reflectivity) if o.override_sr else F(m.reflectivity)
+        return dict(albedo=v3(*m.albedo), refl=refl, emission=v3(*m.emission), transparency=F(m.transparency), tint=v3(*m.transmission))
+
+    # ---- Sphere.Hit BoundedObjects.cs:31-69
+    def sphere_hit(self, o, ro, rd, t_min, t_max):
+        c, radius = v3(*o.p[0:3]), F(o.p[3])
+        ox, oy, oz = F(ro[0] - c[0]), F(ro[1] - c[1]), F(ro[2] - c[2])
+        dx, dy, dz = rd
+        a = F(F(F(dx * dx) + F(dy * dy)) + F(dz * dz))
+        half_b = F(F(F(ox * dx) + F(oy * dy)) + F(oz * dz))
+        cc = F(F(F(F(ox * ox) + F(oy * oy)) + F(oz * oz)) - F(radius * radius))
+        disc = F(F(half_b * half_b) - F(a * cc))
+        if disc < 0:
+            return None
+        s = np.sqrt(disc, dtype=F)
+        inv_a = F(F(1) / a)
+        t = F(F(-half_b - s) * inv_a)
+        if t < t_min or t > t_max:
+            t = F(F(-half_b + s) * inv_a)
+            if t < t_min or t > t_max:
+                return None
+        p = v3(F(ro[0] + F(t * dx)), F(ro[1] + F(t * dy)), F(ro[2] + F(t * dz)))
+        inv_r = F(F(1) / radius)
+        n = v3(F(F(p[0] - c[0]) * inv_r), F(F(p[1] - c[1]) * inv_r), F(F(p[2] - c[2]) * inv_r))
+        return dict(t=t, P=p, N=n, mat=self.material(o, p))
+
+    # ---- XYRect / XZRect / YZRect.Hit (Surfaces.cs:184-214, :256-286, :328-358); k = index of the constant coordinate,
+    #      (a, b) = the two free coordinates in the order the class names them
+    def rect_hit(self, o, k, a, b, a0, a1, b0, b1, c, ro, rd, t_min, t_max):
+        dir_k = rd[k]
+        adir = abs(dir_k)
+        safe = np.copysign(max_f(adir, F(1e-8)), dir_k)
+        t = F(F(c - ro[k]) / safe)
+        pa, pb = F(ro[a] + F(t * rd[a])), F(ro[b] + F(t * rd[b]))
+        ok = adir >= F(1e-8) and t_min <= t <= t_max and a0 <= pa <= a1 and b0 <= pb <= b1
+        if not ok:
+            return None
+        p, n = v3(0, 0, 0), v3(0, 0, 0)
+        p[k], p[a], p[b] = c, pa, pb
+        n[k] = np.copysign(F(1), -dir_k)
+        return dict(t=t, P=p, N=n, mat=self.material(o, p))
+
+    # ---- Plane.Hit (Surfaces.cs:39-71); p = point.xyz, normal.xyz (normalised by the ctor, :21), ndotPoint :25
+    def plane_hit(self, o, ro, rd, t_min, t_max):
+        pt, n = v3(*o.p[0:3]), v3(*o.p[3:6])
+        ndot_point = F(F(F(n[0] * pt[0]) + F(n[1] * pt[1])) + F(n[2] * pt[2]))
+        denom = F(F(F(n[0] * rd[0]) + F(n[1] * rd[1])) + F(n[2] * rd[2]))
+        if F(-1e-6) < denom < F(1e-6):
+            return None
+        t = F(F(ndot_point - F(F(F(n[0] * ro[0]) + F(n[1] * ro[1])) + F(n[2] * ro[2]))) / denom)
+        if t < t_min or t > t_max:
+            return None
+        p = v3(F(ro[0] + F(t * rd[0])), F(ro[1] + F(t * rd[1])), F(ro[2] + F(t * rd[2])))
+        return dict(t=t, P=p, N=n if denom < 0 else v3(-n[0], -n[1], -n[2]), mat=self.material(o, p))
+
+    # ---- Box.Hit (BoundedObjects.cs:78-115): six rects in a fixed order, the accepted hit shrinks `closest`
+    def box_hit_obj(self, o, ro, rd, t_min, t_max):
+        mnx, mny, mnz, mxx, mxy, mxz = (F(v) for v in o.p[0:6])
+        faces = [(2, 0, 1, mnx, mxx, mny, mxy, mxz), (2, 0, 1, mnx, mxx, mny, mxy, mnz), (1, 0, 2, mnx, mxx, mnz, mxz, mxy),
+                 (1, 0, 2, mnx, mxx, mnz, mxz, mny), (0, 1, 2, mny, mxy, mnz, mxz, mxx), (0, 1, 2, mny, mxy, mnz, mxz, mnx)]
+        best, closest = None, t_max
+        for i, (k, a, b, a0, a1, b0, b1, c) in enumerate(faces):
+            tmp = self.rect_hit(o, k, a, b, a0, a1, b0, b1, c, ro, rd, t_min, closest)
+            if tmp is not None:
+                closest, best = tmp["t"], dict(tmp, sub=i)
+        return best
+
+    def object_hit(self, obj_id, ro, rd, t_min, t_max):
+        o = self.objs[obj_id]
+        q = [F(v) for v in o.p[0:5]]
+        if o.kind == 0:
+            return self.sphere_hit(o, ro, rd, t_min, t_max)
+        if o.kind == 1:
+            return self.plane_hit(o, ro, rd, t_min, t_max)
+        if o.kind == 3:  # XYRect(x0, x1, y0, y1, z)
+            return self.rect_hit(o, 2, 0, 1, q[0], q[1], q[2], q[3], q[4], ro, rd, t_min, t_max)
+        if o.kind == 4:  # XZRect(x0, x1, z0, z1, y)
+            return self.rect_hit(o, 1, 0, 2, q[0], q[1], q[2], q[3], q[4], ro, rd, t_min, t_max)
+        if o.kind == 5:  # YZRect(y0, y1, z0, z1, x)
+            return self.rect_hit(o, 0, 1, 2, q[0], q[1], q[2], q[3], q[4], ro, rd, t_min, t_max)
+        if o.kind == 6:
+            return self.box_hit_obj(o, ro, rd, t_min, t_max)
+        raise NotImplementedError(f"object kind {o.kind} is outside this transcription")
+
+    # ---- BVH.BoxHitFast BVH.cs:201-236
+    @staticmethod
+    def box_hit(box, ro, inv, t_min, t_max):
+        ent, ext = [], []
+        for k in range(3):
+            e, x = F(F(box[k] - ro[k]) * inv[k]), F(F(box[3 + k] - ro[k]) * inv[k])
+            if e > x:
+                e, x = x, e
+            ent.append(e)
+            ext.append(x)
+        t_enter = max_f(ent[0], max_f(ent[1], ent[2]))
+        t_exit = min_f(ext[0], min_f(ext[1], ext[2]))
+        if t_enter < t_min:
+            t_enter = t_min
+        if t_exit > t_max:
+            t_exit = t_max
+        return bool(t_exit >= t_enter), t_enter
+
+    # ---- Scene.Hit -> BVH.Hit BVH.cs:99-198
+    def scene_hit(self, ro, rd, t_min, t_max):
+        self.rays += 1
+        tr = self.tree
+        if tr["root"] < 0:
+            return None
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = [F(F(1) / rd[0]), F(F(1) / rd[1]), F(F(1) / rd[2])]
+            closest, best = t_max, None
+            stack = [tr["root"]]
+            while stack:
+                ni = stack.pop()
+                hit, _ = self.box_hit(tr["boxes"][ni], ro, inv, t_min, closest)
+                if not hit:
+                    continue
+                left, right, start, count = (int(v) for v in tr["lrsc"][ni])
+                if count > 0:
+                    for i in range(count):
+                        obj_id = int(tr["leaf"][start + i])
+                        tmp = self.object_hit(obj_id, ro, rd, t_min, closest)
+                        if tmp is not None:
+                            closest, best = tmp["t"], dict(tmp, obj=obj_id, sub=tmp.get("sub", 0))
+                else:
+                    hit_l = hit_r = False
+                    l_near = r_near = F(0)
+                    if left >= 0:
+                        hit_l, l_near = self.box_hit(tr["boxes"][left], ro, inv, t_min, closest)
+                    if right >= 0:
+                        hit_r, r_near = self.box_hit(tr["boxes"][right], ro, inv, t_min, closest)
+                    if hit_l and hit_r:
+                        if l_near < r_near:
+                            stack += [right, left]
+                        else:
+                            stack += [left, right]
+                    elif hit_l:
+                        stack.append(left)
+                    elif hit_r:
+                        stack.append(right)
+        return best
+
+    # ---- OrenNayarBRDF :810-831
+    @staticmethod
+    def oren_nayar(albedo, n, wo, wi, sigma):
+        cos_i, cos_o = max_f(F(0), dot(n, wi)), max_f(F(0), dot(n, wo))
+        if cos_i <= 0 or cos_o <= 0:
+            return v3(0, 0, 0)
+        sin_i = np.sqrt(max_f(F(0), F(F(1) - F(cos_i * cos_i))), dtype=F)
+        sin_o = np.sqrt(max_f(F(0), F(F(1) - F(cos_o * cos_o))), dtype=F)
+        proj_i = normalized(v3(*(F(wi[k] - F(n[k] * cos_i)) for k in range(3))))
+        proj_o = normalized(v3(*(F(wo[k] - F(n[k] * cos_o)) for k in range(3))))
+        cos_phi = max_f(F(0), dot(proj_i, proj_o))
+        s2 = F(sigma * sigma)
+        a = F(F(1) - F(s2 / F(F(2) * F(s2 + F(0.33)))))
+        b = F(F(F(0.45) * s2) / F(s2 + F(0.09)))
+        sin_alpha = max_f(sin_i, sin_o)
+        tan_beta = min_f(F(sin_i / max_f(F(1e-6), cos_i)), F(sin_o / max_f(F(1e-6), cos_o)))
+        on = F(a + F(F(F(b * cos_phi) * sin_alpha) * tan_beta))
+        k = F(on * F(F(1) / PI))
+        return v3(*(min(max(F(albedo[c] * k), F(0)), F(1)) for c in range(3)))
+
+    # ---- CosineSampleHemisphere RaytraceSampler.cs:83-111
+    def cosine_sample(self, n, rng):
+        u1, u2 = rng.next_unit(), rng.next_unit()
+        r = np.sqrt(u1, dtype=F)
+        phi = F(F(6.2831853071795864769) * u2)
+        x, y = F(r * self.cos(phi)), F(r * self.sin(phi))
+        z = np.sqrt(F(F(1) - u1), dtype=F)
+        w = n
+        if w[2] < F(-0.999999):
+            u, v = v3(0, -1, 0), v3(-1, 0, 0)
+        else:
+            a = F(F(1) / F(F(1) + w[2]))
+            b = F(F(-w[0] * w[1]) * a)
+            u = v3(F(1.0 - float(F(F(w[0] * w[0]) * a))), b, -w[0])
+            v = v3(b, F(1.0 - float(F(F(w[1] * w[1]) * a))), -w[1])
+        return v3(*(F(F(F(u[k] * x) + F(v[k] * y)) + F(w[k] * z)) for k in range(3)))
+
+    # ---- ComputeTransmittanceToLight :757-798 (not a VolumeScene)
+    def transmittance(self, ro, rd, max_dist):
+        tr, tmin, counter = [F(1), F(1), F(1)], F(F(0) + EPS), 0
+        while counter < MAX_REFR:
+            block = self.scene_hit(ro, rd, tmin, max_dist)
+            if block is None:
+                break
+            counter += 1
+            m = block["mat"]
+            if m["transparency"] <= 0:
+                return v3(0, 0, 0)
+            tr = [F(tr[k] * F(m["tint"][k] * m["transparency"])) for k in range(3)]
+            if all(t <= F(1e-6) for t in tr):
+                return v3(0, 0, 0)
+            if block["t"] > max_dist:
+                break
+            tmin = F(block["t"] + EPS)
+        return v3(*tr)
+
+    # ---- MakeJitteredRay :419-437
+    def make_ray(self, cam, yaw, pitch, fov, aspect, px, py, w, h, jrx, jry, frame_idx):
+        def blue(channel):  # RaytraceSampler.cs:27-34
+            base = F(F(F(BLUE[py & 7][px & 7]) + F(0.5)) * F(1.0 / 64.0))
+            rot = frac(F(F(frame_idx + 1) * (F(0.7548776662466927) if channel == 0 else F(0.5698402909980532))))
+            return frac(F(base + rot))
+        jx, jy = F(frac(F(blue(0) + jrx)) - F(0.5)), F(frac(F(blue(1) + jry)) - F(0.5))
+        u = F(F(F(F(F(F(px) + F(0.5)) + jx) / F(w)) * F(2)) - F(1))
+        v = F(F(1) - F(F(F(F(F(py) + F(0.5)) + jy) / F(h)) * F(2)))
+        fov_rad = F(fov * F(MATHF_PI / F(180)))
+        half_h = self.tan(F(F(0.5) * fov_rad))
+        half_w = F(half_h * aspect)
+        cp = self.cos(pitch)
+        fwd = normalized(v3(F(self.sin(yaw) * cp), self.sin(pitch), F(-self.cos(yaw) * cp)))
+        right = normalized(cross(fwd, v3(0, 1, 0)))
+        up = normalized(cross(right, fwd))
+        su, sv = F(u * half_w), F(v * half_h)
+        d = normalized(v3(*(F(F(fwd[k] + F(right[k] * su)) + F(up[k] * sv)) for k in range(3))))
+        return cam, normalized(d)  # new Ray(...) normalises again (Ray.cs:8-12)
+
+    # ---- TraceFull :448-620
+    def trace_full(self, ro, rd, rng):
+        stack = [dict(ro=ro, rd=rd, beta=v3(1, 1, 1), mirror=0, diffuse=0, primary=True)]
+        radiance = v3(0, 0, 0)
+        primary_hit, is_sky, gbuf_valid = False, False, False
+        g = dict(albedo=v3(0, 0, 0), normal=v3(0, 0, 0), depth=FLT_MAX, obj=-1, sub=-1)
+        sigma = F(SIGMA_DEG * F(MATHF_PI / F(180)))
+        add = lambda acc, beta, c: v3(*(F(acc[k] + F(beta[k] * c[k])) for k in range(3)))
+        while stack:
+            item = stack.pop()
+            ro, rd, beta, mirror, diffuse = item["ro"], item["rd"], item["beta"], item["mirror"], item["diffuse"]
+            while True:
+                rec = self.scene_hit(ro, rd, F(0.001), FLT_MAX)
+                if rec is None:
+                    tbg = F(F(0.5) * F(rd[1] + F(1)))
+                    sky = v3(*(F(F(self.bg_bottom[k] * F(F(1) - tbg)) + F(self.bg_top[k] * tbg)) for k in range(3)))  # Lerp :805-808
+                    if item["primary"] and not primary_hit:
+                        is_sky = True
+                        if not gbuf_valid:
+                            g = dict(albedo=v3(0, 0, 0), normal=v3(0, 0, 0), depth=FLT_MAX, obj=-1, sub=-1)
+                            gbuf_valid = True
+                    radiance = add(radiance, beta, sky)
+                    break
+                m = rec["mat"]
+                if item["primary"]:
+                    primary_hit, is_sky = True, False
+                    if not gbuf_valid:
+                        g = dict(albedo=m["albedo"], normal=rec["N"], depth=rec["t"], obj=rec["obj"], sub=rec["sub"])
+                        gbuf_valid = True
+                    item["primary"] = False
+                if m["emission"].any():
+                    radiance = add(radiance, beta, m["emission"])
+                base = m["albedo"]
+                if m["transparency"] > 0:
+                    raise NotImplementedError("transparent materials are outside this transcription")
+                if m["refl"] >= MIRROR_THRESHOLD:
+                    if mirror >= MAX_MIRROR:
+                        break
+                    k2 = F(F(2) * dot(rd, rec["N"]))
+                    refl = normalized(v3(*(F(rd[k] - F(rec["N"][k] * k2)) for k in range(3))))  # Reflect :800-803
+                    ro = v3(*(F(rec["P"][k] + F(rec["N"][k] * EPS)) for k in range(3)))
+                    rd = normalized(refl)
+                    beta = v3(*(F(beta[k] * base[k]) for k in range(3)))
+                    mirror += 1
+                    continue
+                if self.amb_i > 0:
+                    amb = v3(*(F(F(self.amb_c[k] * self.amb_i) * base[k]) for k in range(3)))
+                    radiance = add(radiance, beta, amb)
+                wo = normalized(v3(*(F(rd[k] * F(-1)) for k in range(3))))
+                for lpos, lcol, lint in self.lights:
+                    to_l = v3(*(F(lpos[k] - rec["P"][k]) for k in range(3)))
+                    dist2 = dot(to_l, to_l)
+                    dist = np.sqrt(dist2, dtype=F)
+                    ldir = vdiv(to_l, dist)
+                    n_dot_l = max_f(F(0), dot(rec["N"], ldir))
+                    if n_dot_l <= 0:
+                        continue
+                    so = v3(*(F(rec["P"][k] + F(rec["N"][k] * EPS)) for k in range(3)))
+                    trans = self.transmittance(so, normalized(ldir), F(dist - EPS))
+                    if all(t <= F(1e-6) for t in trans):
+                        continue
+                    atten = F(lint / dist2)
+                    f_d = self.oren_nayar(base, rec["N"], wo, ldir, sigma)
+                    contrib = v3(*(F(F(F(f_d[k] * n_dot_l) * F(lcol[k] * atten)) * trans[k]) for k in range(3)))
+                    radiance = add(radiance, beta, contrib)
+                if diffuse < DIFFUSE_BOUNCES:
+                    bounce = self.cosine_sample(rec["N"], rng)
+                    f_on = self.oren_nayar(base, rec["N"], wo, bounce, sigma)
+                    ro = v3(*(F(rec["P"][k] + F(rec["N"][k] * EPS)) for k in range(3)))
+                    rd = normalized(bounce)
+                    beta = v3(*(F(beta[k] * F(f_on[k] * PI)) for k in range(3)))
+                    diffuse += 1
+                    continue
+                break
+        return radiance, is_sky, g
+
+
+@pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1)])
+def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb_h, ss):
+    lib = load_oracle()
+    lib.yo_set_math_mode(0)
+    scene = api.HostScene(scene_name)
+    o = Oracle(scene, fb_w, fb_h, ss)
+    lt = LiteralTracer(scene, lib)
+    pos, yaw, pitch, fov = scene.default_camera()
+    cam, yaw, pitch, fov = v3(*pos), F(yaw), F(pitch), F(fov)
+    w, h = fb_w * ss, fb_h * 2 * ss
+    aspect = F(F(w) / F(h))
+    saw_mirror = False
+    with np.errstate(over="ignore"):
+        for frame in (1, 2):
+            o.render_frame(threads=2)
+            hdr, als, nd, prim = o.debug_read(api.DBG_HDR), o.debug_read(api.DBG_ALBEDO_SKY), o.debug_read(api.DBG_NORMAL_DEPTH), o.debug_read(api.DBG_PRIM_ID)
+            raw_n, rays_ref = o.raw_normal(), o.debug_read(api.DBG_RAYS)
+            frame_idx = frame & 0x7FFFFFFF
+            jrx, jry = frac(F(F(frame_idx + 1) * F(0.61803398875))), frac(F(F(frame_idx + 1) * F(0.38196601125)))  # :178-179
+            lt.rays = 0
+            for py in range(h):
+                for px in range(w):
+                    ro, rd = lt.make_ray(cam, yaw, pitch, fov, aspect, px, py, w, h, jrx, jry, frame_idx)
+                    assert np.array_equal(np.concatenate([ro, rd]).view(np.uint32), rays_ref[py, px].view(np.uint32)), (frame, px, py, "ray")
+                    rad, is_sky, g = lt.trace_full(ro, rd, Rng(per_frame_seed(px, py, frame)))
+                    where = (scene_name, frame, px, py)
+                    assert np.array_equal(rad.view(np.uint32), hdr[py, px, :3].view(np.uint32)), where + ("radiance", rad, hdr[py, px, :3])
+                    assert bool(als[py, px, 3]) == is_sky, where + ("sky",)
+                    assert np.array_equal(g["albedo"].view(np.uint32), als[py, px, :3].view(np.uint32)), where + ("albedo",)
+                    assert np.array_equal(g["normal"].view(np.uint32), raw_n[py, px].view(np.uint32)), where + ("normal",)
+                    assert F(g["depth"]).view(np.uint32) == nd[py, px, 3].view(np.uint32), where + ("depth",)
+                    assert (g["obj"], g["sub"]) == tuple(prim[py, px]), where + ("primary ids",)
+                    if g["obj"] >= 0 and F(lt.objs[g["obj"]].reflectivity if lt.objs[g["obj"]].override_sr else lt.mats[lt.objs[g["obj"]].mat_a].reflectivity) >= MIRROR_THRESHOLD:
+                        saw_mirror = True
+            assert lt.rays == o.stats()["rays"], (scene_name, frame, "Scene.Hit invocations")
+    if scene_name == "test":
+        assert saw_mirror, "the mirror sphere must be in view, or the mirror branch is not exercised"
+    o.close()
+    scene.close()
