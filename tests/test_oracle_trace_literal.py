@@ -1,13 +1,15 @@
 """The trace stage pinned by a second, independent restatement: MakeJitteredRay, the per-pixel RNG, TraceFull with its explicit
 work stack, ComputeTransmittanceToLight, OrenNayarBRDF, CosineSampleHemisphere, Scene.Hit -> BVH.Hit / BoxHitFast, Sphere.Hit,
-Plane.Hit, the three axis rects, Box.Hit (six rects, shrinking closest) and the Checker material function, transcribed from
+Plane.Hit, the three axis rects, Box.Hit (six rects, shrinking closest), Mesh.Hit -> MeshBVH.Hit with its sign-indexed
+BoxHitFast and the deferred-division TriHit (MeshBVH.cs:132-332) and the Checker material function, transcribed from
 the C# source into numpy binary32 scalars, one operation at a time (RayTracing/RaytraceRenderer.cs:413-620,:757-831, RaytraceSampler.cs, Objects/BVH.cs:99-236, BoundedObjects.cs:31-69,
 :78-115, Surfaces.cs:184-358, Scenes/Scenes.cs:418-428).  It shares nothing with the oracle's C++ but the transcendental functions
 of include/ycge_detmath.h (sin, cos, tan) and the scene description; the tree it walks is the HOST mirror's, built by a
 third implementation.  Radiance, G-buffer, sky flag and primary ids of every pixel must equal the oracle's bit for bit,
 on a scene with a true mirror (reflectivity 0.9 = MirrorThreshold), one with a checker floor, the Cornell box (emissive
-rect, closed room, boxes) and the boxes showcase (plane + boxes), over two frames.  (Disks, cylinders, triangles, meshes,
-voxels and transparent materials are outside this transcription.)
+rect, closed room, boxes), the boxes showcase (plane + boxes) and a mesh scene (120-triangle knot over the ground plane, the
+path of the Dragon workload), over two frames.  (Disks, cylinders, standalone triangles, voxels and transparent materials
+are outside this transcription.)
 """
 import numpy as np
 import pytest
@@ -106,6 +108,13 @@ class LiteralTracer:
         self.bg_top, self.bg_bottom = v3(*flat.bg_top), v3(*flat.bg_bottom)
         self.amb_c, self.amb_i = v3(*flat.ambient_color), F(flat.ambient_intensity)
         self.tree = scene.bvh_arrays(-1)
+        self.meshes = []
+        for i in range(scene.n_meshes):  # MeshBVH.cs:18-39: triangle SoA + the host mirror's tree
+            m = scene.mesh(i).contents
+            soa = {k: np.ctypeslib.as_array(getattr(m, k), shape=(m.n_tris,)).copy() for k in ("ax", "ay", "az", "e1x", "e1y", "e1z", "e2x", "e2y", "e2z", "nx", "ny", "nz")}
+            mm = m.material
+            mat = dict(albedo=v3(*mm.albedo), refl=F(mm.reflectivity), emission=v3(*mm.emission), transparency=F(mm.transparency), tint=v3(*mm.transmission))
+            self.meshes.append(dict(soa=soa, tree=scene.bvh_arrays(i), mat=mat))
         self.sin = lambda x: F(lib.yo_math(3, float(x), 0.0))
         self.cos = lambda x: F(lib.yo_math(4, float(x), 0.0))
         self.tan = lambda x: F(lib.yo_math(5, float(x), 0.0))
@@ -173,6 +182,90 @@ class LiteralTracer:
         p = v3(F(ro[0] + F(t * rd[0])), F(ro[1] + F(t * rd[1])), F(ro[2] + F(t * rd[2])))
         return dict(t=t, P=p, N=n if denom < 0 else v3(-n[0], -n[1], -n[2]), mat=self.material(o, p))
 
+    # ---- MeshBVH.TriHit (MeshBVH.cs:239-304): division deferred, bounds scaled by |det|
+    @staticmethod
+    def tri_hit(soa, i, ro, rd, t_min, t_max):
+        e1, e2, a = [soa[k][i] for k in ("e1x", "e1y", "e1z")], [soa[k][i] for k in ("e2x", "e2y", "e2z")], [soa[k][i] for k in ("ax", "ay", "az")]
+        px = F(F(rd[1] * e2[2]) - F(rd[2] * e2[1]))
+        py = F(F(rd[2] * e2[0]) - F(rd[0] * e2[2]))
+        pz = F(F(rd[0] * e2[1]) - F(rd[1] * e2[0]))
+        det = F(F(F(e1[0] * px) + F(e1[1] * py)) + F(e1[2] * pz))
+        if F(-1e-8) < det < F(1e-8):
+            return None
+        sx, sy, sz = F(ro[0] - a[0]), F(ro[1] - a[1]), F(ro[2] - a[2])
+        u_num = F(F(F(sx * px) + F(sy * py)) + F(sz * pz))
+        sgn = F(1) if det > 0 else F(-1)
+        det_abs, u_s = F(det * sgn), F(u_num * sgn)
+        if u_s < 0 or u_s > det_abs:
+            return None
+        qx = F(F(sy * e1[2]) - F(sz * e1[1]))
+        qy = F(F(sz * e1[0]) - F(sx * e1[2]))
+        qz = F(F(sx * e1[1]) - F(sy * e1[0]))
+        v_num = F(F(F(rd[0] * qx) + F(rd[1] * qy)) + F(rd[2] * qz))
+        v_s = F(v_num * sgn)
+        if v_s < 0 or F(u_s + v_s) > det_abs:
+            return None
+        t_num = F(F(F(e2[0] * qx) + F(e2[1] * qy)) + F(e2[2] * qz))
+        t_s = F(t_num * sgn)
+        if t_s < F(t_min * det_abs) or t_s > F(t_max * det_abs):
+            return None
+        return F(t_num * F(F(1) / det))
+
+    # ---- MeshBVH.BoxHitFast (MeshBVH.cs:308-332): sign-indexed slabs with early outs
+    @staticmethod
+    def mesh_box_hit(box, ro, inv, sign, t_min, t_max):
+        for k in range(3):
+            lo, hi = (box[k], box[3 + k]) if sign[k] == 0 else (box[3 + k], box[k])
+            t_en, t_ex = F(F(lo - ro[k]) * inv[k]), F(F(hi - ro[k]) * inv[k])
+            if t_en > t_min:
+                t_min = t_en
+            if t_ex < t_max:
+                t_max = t_ex
+            if k < 2 and t_max < t_min:
+                return False, t_min
+        return bool(t_max >= t_min), t_min
+
+    # ---- Mesh.Hit -> MeshBVH.Hit (Mesh.cs:23-26, MeshBVH.cs:132-236)
+    def mesh_hit(self, o, ro, rd, t_min, t_max):
+        mesh = self.meshes[o.ref_id]
+        tr, soa = mesh["tree"], mesh["soa"]
+        if tr["root"] < 0:
+            return None
+        inv = [F(F(1) / rd[0]), F(F(1) / rd[1]), F(F(1) / rd[2])]
+        sign = [1 if v < 0 else 0 for v in inv]
+        closest, best = t_max, None
+        stack = [tr["root"]]
+        while stack:
+            ni = stack.pop()
+            hit, _ = self.mesh_box_hit(tr["boxes"][ni], ro, inv, sign, t_min, closest)
+            if not hit:
+                continue
+            left, right, start, count = (int(v) for v in tr["lrsc"][ni])
+            if count > 0:
+                for i in range(count):
+                    tri = int(tr["leaf"][start + i])
+                    t = self.tri_hit(soa, tri, ro, rd, t_min, closest)
+                    if t is not None:
+                        closest = t
+                        p = v3(F(ro[0] + F(t * rd[0])), F(ro[1] + F(t * rd[1])), F(ro[2] + F(t * rd[2])))
+                        n = v3(soa["nx"][tri], soa["ny"][tri], soa["nz"][tri])
+                        ndotd = F(F(F(n[0] * rd[0]) + F(n[1] * rd[1])) + F(n[2] * rd[2]))
+                        best = dict(t=t, P=p, N=n if ndotd < 0 else v3(-n[0], -n[1], -n[2]), mat=mesh["mat"], sub=tri)
+            else:
+                hit_l = hit_r = False
+                l_near = r_near = F(0)
+                if left >= 0:
+                    hit_l, l_near = self.mesh_box_hit(tr["boxes"][left], ro, inv, sign, t_min, closest)
+                if right >= 0:
+                    hit_r, r_near = self.mesh_box_hit(tr["boxes"][right], ro, inv, sign, t_min, closest)
+                if hit_l and hit_r:
+                    stack += [right, left] if l_near < r_near else [left, right]
+                elif hit_l:
+                    stack.append(left)
+                elif hit_r:
+                    stack.append(right)
+        return best
+
     # ---- Box.Hit (BoundedObjects.cs:78-115): six rects in a fixed order, the accepted hit shrinks `closest`
     def box_hit_obj(self, o, ro, rd, t_min, t_max):
         mnx, mny, mnz, mxx, mxy, mxz = (F(v) for v in o.p[0:6])
@@ -200,6 +293,8 @@ class LiteralTracer:
             return self.rect_hit(o, 0, 1, 2, q[0], q[1], q[2], q[3], q[4], ro, rd, t_min, t_max)
         if o.kind == 6:
             return self.box_hit_obj(o, ro, rd, t_min, t_max)
+        if o.kind == 9:
+            return self.mesh_hit(o, ro, rd, t_min, t_max)
         raise NotImplementedError(f"object kind {o.kind} is outside this transcription")
 
     # ---- BVH.BoxHitFast BVH.cs:201-236
@@ -413,7 +508,7 @@ class LiteralTracer:
         return radiance, is_sky, g
 
 
-@pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1)])
+@pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1), ("knot:12x5", 8, 3, 2)])
 def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb_h, ss):
     lib = load_oracle()
     lib.yo_set_math_mode(0)
@@ -421,10 +516,13 @@ def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb
     o = Oracle(scene, fb_w, fb_h, ss)
     lt = LiteralTracer(scene, lib)
     pos, yaw, pitch, fov = scene.default_camera()
+    if scene.n_meshes:  # the default pose of the mesh scenes looks away from the mesh
+        pos, yaw, pitch = api.BENCH_POSE
+        o.set_camera(pos, yaw, pitch)
     cam, yaw, pitch, fov = v3(*pos), F(yaw), F(pitch), F(fov)
     w, h = fb_w * ss, fb_h * 2 * ss
     aspect = F(F(w) / F(h))
-    saw_mirror = False
+    saw_mirror, saw_mesh = False, False
     with np.errstate(over="ignore"):
         for frame in (1, 2):
             o.render_frame(threads=2)
@@ -445,9 +543,11 @@ def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb
                     assert np.array_equal(g["normal"].view(np.uint32), raw_n[py, px].view(np.uint32)), where + ("normal",)
                     assert F(g["depth"]).view(np.uint32) == nd[py, px, 3].view(np.uint32), where + ("depth",)
                     assert (g["obj"], g["sub"]) == tuple(prim[py, px]), where + ("primary ids",)
-                    if g["obj"] >= 0 and F(lt.objs[g["obj"]].reflectivity if lt.objs[g["obj"]].override_sr else lt.mats[lt.objs[g["obj"]].mat_a].reflectivity) >= MIRROR_THRESHOLD:
+                    saw_mesh |= g["obj"] >= 0 and lt.objs[g["obj"]].kind == 9
+                    if g["obj"] >= 0 and lt.objs[g["obj"]].kind != 9 and F(lt.objs[g["obj"]].reflectivity if lt.objs[g["obj"]].override_sr else lt.mats[lt.objs[g["obj"]].mat_a].reflectivity) >= MIRROR_THRESHOLD:
                         saw_mirror = True
             assert lt.rays == o.stats()["rays"], (scene_name, frame, "Scene.Hit invocations")
+    assert saw_mesh == (scene.n_meshes > 0), "the mesh must be in view, or MeshBVH.Hit is not exercised on primary rays"
     if scene_name == "test":
         assert saw_mirror, "the mirror sphere must be in view, or the mirror branch is not exercised"
     o.close()
