@@ -1,15 +1,20 @@
 """The trace stage pinned by a second, independent restatement: MakeJitteredRay, the per-pixel RNG, TraceFull with its explicit
 work stack, ComputeTransmittanceToLight, OrenNayarBRDF, CosineSampleHemisphere, Scene.Hit -> BVH.Hit / BoxHitFast, Sphere.Hit,
-Plane.Hit, the three axis rects, Box.Hit (six rects, shrinking closest), Mesh.Hit -> MeshBVH.Hit with its sign-indexed
-BoxHitFast and the deferred-division TriHit (MeshBVH.cs:132-332) and the Checker material function, transcribed from
+Plane.Hit, Disk.Hit, CylinderY.Hit, Triangle.Hit (scalar path), the three axis rects, Box.Hit (six rects, shrinking closest),
+Mesh.Hit -> MeshBVH.Hit with its sign-indexed
+BoxHitFast and the deferred-division TriHit (MeshBVH.cs:132-332), VolumeGrid.Hit (the DDA with its entry-axis / tie rules, bricked
+Morton addressing and the binary64 wireframe test, VolumeGrid.cs:99-355), Scene.Occluded for volume scenes and the Checker
+material function, transcribed from
 the C# source into numpy binary32 scalars, one operation at a time (RayTracing/RaytraceRenderer.cs:413-620,:757-831, RaytraceSampler.cs, Objects/BVH.cs:99-236, BoundedObjects.cs:31-69,
 :78-115, Surfaces.cs:184-358, Scenes/Scenes.cs:418-428).  It shares nothing with the oracle's C++ but the transcendental functions
 of include/ycge_detmath.h (sin, cos, tan) and the scene description; the tree it walks is the HOST mirror's, built by a
 third implementation.  Radiance, G-buffer, sky flag and primary ids of every pixel must equal the oracle's bit for bit,
 on a scene with a true mirror (reflectivity 0.9 = MirrorThreshold), one with a checker floor, the Cornell box (emissive
 rect, closed room, boxes), the boxes showcase (plane + boxes) and a mesh scene (120-triangle knot over the ground plane, the
-path of the Dragon workload), over two frames.  (Disks, cylinders, standalone triangles, voxels and transparent materials
-are outside this transcription.)
+path of the Dragon workload), the voxel test grid and a 32x32x32 voxel world of chunk grids (a VolumeScene: binary shadow
+rays; its test grid holds a transparent block, so the Fresnel split with Refract / FresnelSchlick runs too) and the
+cylinder / disk / triangle showcase, over two frames.  Nothing of the trace stage is outside this transcription except
+textures (SampleBilinear has its own transcription in test_oracle_kat.py).
 """
 import numpy as np
 import pytest
@@ -113,11 +118,23 @@ class LiteralTracer:
             m = scene.mesh(i).contents
             soa = {k: np.ctypeslib.as_array(getattr(m, k), shape=(m.n_tris,)).copy() for k in ("ax", "ay", "az", "e1x", "e1y", "e1z", "e2x", "e2y", "e2z", "nx", "ny", "nz")}
             mm = m.material
-            mat = dict(albedo=v3(*mm.albedo), refl=F(mm.reflectivity), emission=v3(*mm.emission), transparency=F(mm.transparency), tint=v3(*mm.transmission))
+            mat = dict(albedo=v3(*mm.albedo), refl=F(mm.reflectivity), emission=v3(*mm.emission), transparency=F(mm.transparency), tint=v3(*mm.transmission), ior=F(mm.ior))
             self.meshes.append(dict(soa=soa, tree=scene.bvh_arrays(i), mat=mat))
+        self.volumes = []
+        for i in range(scene.n_volumes):  # VolumeGrid.cs:25-32: the int arrays in bricked-Morton order + the material lookup as a table
+            v = scene.volume(i).contents
+            nb = ((v.nx + 7) >> 3) * ((v.ny + 7) >> 3) * ((v.nz + 7) >> 3) * 512
+            levels = max(1, v.palette_meta_levels)
+            self.volumes.append(dict(n=(v.nx, v.ny, v.nz), mn=v3(*v.min_corner), size=v3(*v.voxel_size),
+                                     mat=np.ctypeslib.as_array(v.mat, shape=(nb,)).copy(), meta=np.ctypeslib.as_array(v.meta, shape=(nb,)).copy(),
+                                     wire=bool(v.wireframe), wire_frac=F(v.wire_width_frac), wire_max=F(v.wire_max_distance),
+                                     palette=np.ctypeslib.as_array(v.palette, shape=(v.palette_n_ids * levels,)).copy(), n_ids=v.palette_n_ids, levels=levels,
+                                     default=v.palette_default))
+        self.is_volume_scene = bool(flat.is_volume_scene)
         self.sin = lambda x: F(lib.yo_math(3, float(x), 0.0))
         self.cos = lambda x: F(lib.yo_math(4, float(x), 0.0))
         self.tan = lambda x: F(lib.yo_math(5, float(x), 0.0))
+        self.pow = lambda x, y: F(lib.yo_math(2, float(x), float(y)))
         self.rays = 0
 
     # ---- materials: constant or Checker(a, b, scale) (Scenes.cs:418-428), then the object's Specular / Reflectivity (Surfaces.cs:279-281)
@@ -128,7 +145,7 @@ class LiteralTracer:
             cz = int(np.floor(F(pos[2] / F(o.checker_scale))))
             m = self.mats[o.mat_a if ((cx + cz) & 1) == 0 else o.mat_b]
         refl = F(o.reflectivity) if o.override_sr else F(m.reflectivity)
-        return dict(albedo=v3(*m.albedo), refl=refl, emission=v3(*m.emission), transparency=F(m.transparency), tint=v3(*m.transmission))
+        return dict(albedo=v3(*m.albedo), refl=refl, emission=v3(*m.emission), transparency=F(m.transparency), tint=v3(*m.transmission), ior=F(m.ior))
 
     # ---- Sphere.Hit BoundedObjects.cs:31-69
     def sphere_hit(self, o, ro, rd, t_min, t_max):
@@ -181,6 +198,87 @@ class LiteralTracer:
             return None
         p = v3(F(ro[0] + F(t * rd[0])), F(ro[1] + F(t * rd[1])), F(ro[2] + F(t * rd[2])))
         return dict(t=t, P=p, N=n if denom < 0 else v3(-n[0], -n[1], -n[2]), mat=self.material(o, p))
+
+    # ---- CylinderY.Hit (BoundedObjects.cs:148-247); p = center.xyz, radius, yMin, yMax, capped
+    def cylinder_hit(self, o, ro, rd, t_min, t_max):
+        cx, cz, radius, y_min, y_max, capped = F(o.p[0]), F(o.p[2]), F(o.p[3]), F(o.p[4]), F(o.p[5]), o.p[6] != 0.0
+        radius2 = F(radius * radius)
+        ox, oy, oz = F(ro[0] - cx), ro[1], F(ro[2] - cz)
+        dx, dy, dz = rd
+        a = F(F(dx * dx) + F(dz * dz))
+        hit_t, hit_n, hit = FLT_MAX, v3(0, 0, 0), False
+        if a > F(1e-12):
+            half_b = F(F(ox * dx) + F(oz * dz))
+            c = F(F(F(ox * ox) + F(oz * oz)) - radius2)
+            disc = F(F(half_b * half_b) - F(a * c))
+            if disc >= 0:
+                s = np.sqrt(disc, dtype=F)
+                inv_a = F(F(1) / a)
+                for root in (F(F(-half_b - s) * inv_a), F(F(-half_b + s) * inv_a)):
+                    if hit:
+                        break
+                    if t_min < root < t_max:
+                        y = F(oy + F(root * dy))
+                        if y_min <= y <= y_max:
+                            hit_t, hit = root, True
+                            hit_n = v3(F(F(ox + F(root * dx)) / radius), F(0), F(F(oz + F(root * dz)) / radius))
+        if capped and abs(dy) > F(1e-8):
+            for y_cap, ny in ((y_max, F(1)), (y_min, F(-1))):
+                t_cap = F(F(y_cap - oy) / dy)
+                if t_min < t_cap < t_max:
+                    rx, rz = F(ox + F(t_cap * dx)), F(oz + F(t_cap * dz))
+                    if F(F(rx * rx) + F(rz * rz)) <= radius2 and t_cap < hit_t:
+                        hit_t, hit_n, hit = t_cap, v3(0, ny, 0), True
+        if not hit:
+            return None
+        p = v3(F(ro[0] + F(hit_t * dx)), F(ro[1] + F(hit_t * dy)), F(ro[2] + F(hit_t * dz)))
+        n = hit_n if dot(hit_n, rd) < 0 else v3(-hit_n[0], -hit_n[1], -hit_n[2])
+        return dict(t=hit_t, P=p, N=n, mat=self.material(o, p))
+
+    # ---- Disk.Hit (Surfaces.cs:108-142): the radius test uses dx, dz only; p = center.xyz, normal.xyz (normalised), radius
+    def disk_hit(self, o, ro, rd, t_min, t_max):
+        c, n, radius = v3(*o.p[0:3]), v3(*o.p[3:6]), F(o.p[6])
+        denom = dot(n, rd)
+        adenom = abs(denom)
+        safe = np.copysign(max_f(adenom, F(1e-8)), denom)
+        t = F(F(dot(n, c) - dot(n, ro)) / safe)
+        p = v3(F(ro[0] + F(t * rd[0])), F(ro[1] + F(t * rd[1])), F(ro[2] + F(t * rd[2])))
+        ddx, ddz = F(p[0] - c[0]), F(p[2] - c[2])
+        rr = F(F(ddx * ddx) + F(ddz * ddz))
+        if not (adenom >= F(1e-6) and t_min <= t <= t_max and rr <= F(radius * radius)):
+            return None
+        return dict(t=t, P=p, N=n if denom < 0 else v3(-n[0], -n[1], -n[2]), mat=self.material(o, p))
+
+    # ---- Triangle.Hit, scalar path (Triangle.cs:130-175); edges and normal as the ctor derives them (:36-44)
+    def triangle_hit(self, o, ro, rd, t_min, t_max):
+        a, b, c = v3(*o.p[0:3]), v3(*o.p[3:6]), v3(*o.p[6:9])
+        e1, e2 = [F(b[k] - a[k]) for k in range(3)], [F(c[k] - a[k]) for k in range(3)]
+        nn = [F(F(e1[1] * e2[2]) - F(e1[2] * e2[1])), F(F(e1[2] * e2[0]) - F(e1[0] * e2[2])), F(F(e1[0] * e2[1]) - F(e1[1] * e2[0]))]
+        inv_len = F(F(1) / max_f(F(1e-20), np.sqrt(F(F(F(nn[0] * nn[0]) + F(nn[1] * nn[1])) + F(nn[2] * nn[2])), dtype=F)))
+        n = v3(nn[0] * inv_len, nn[1] * inv_len, nn[2] * inv_len)
+        px = F(F(rd[1] * e2[2]) - F(rd[2] * e2[1]))
+        py = F(F(rd[2] * e2[0]) - F(rd[0] * e2[2]))
+        pz = F(F(rd[0] * e2[1]) - F(rd[1] * e2[0]))
+        det = F(F(F(e1[0] * px) + F(e1[1] * py)) + F(e1[2] * pz))
+        if abs(det) < F(1e-8):
+            return None
+        inv_det = F(F(1) / det)
+        sx, sy, sz = F(ro[0] - a[0]), F(ro[1] - a[1]), F(ro[2] - a[2])
+        u = F(F(F(F(sx * px) + F(sy * py)) + F(sz * pz)) * inv_det)
+        if u < 0 or u > 1:
+            return None
+        qx = F(F(sy * e1[2]) - F(sz * e1[1]))
+        qy = F(F(sz * e1[0]) - F(sx * e1[2]))
+        qz = F(F(sx * e1[1]) - F(sy * e1[0]))
+        v = F(F(F(F(rd[0] * qx) + F(rd[1] * qy)) + F(rd[2] * qz)) * inv_det)
+        if v < 0 or F(u + v) > 1:
+            return None
+        t = F(F(F(F(e2[0] * qx) + F(e2[1] * qy)) + F(e2[2] * qz)) * inv_det)
+        if t < t_min or t > t_max:
+            return None
+        p = v3(F(ro[0] + F(t * rd[0])), F(ro[1] + F(t * rd[1])), F(ro[2] + F(t * rd[2])))
+        nd = F(F(F(n[0] * rd[0]) + F(n[1] * rd[1])) + F(n[2] * rd[2]))
+        return dict(t=t, P=p, N=n if nd < 0 else v3(-n[0], -n[1], -n[2]), mat=self.material(o, p))
 
     # ---- MeshBVH.TriHit (MeshBVH.cs:239-304): division deferred, bounds scaled by |det|
     @staticmethod
@@ -266,6 +364,95 @@ class LiteralTracer:
                     stack.append(right)
         return best
 
+    # ---- VolumeGrid.Hit (VolumeGrid.cs:99-231) with RayAabb / Slab (:319-355), IndexOf / Morton3_3bits (:235-252), IsWireOnFace
+    #      (:256-283).  The racy centre-block highlight (:181-186) needs |u - 0.5| <= 1e-6 and is unreachable at even resolutions.
+    def volume_hit(self, o, ro, rd, t_min, t_max):
+        g = self.volumes[o.ref_id]
+        nx, ny, nz = g["n"]
+        mn, size = g["mn"], g["size"]
+        mx = [F(mn[k] + F(F(g["n"][k]) * size[k])) for k in range(3)]
+        t_enter, t_exit, enter_axis = F(-np.inf), F(np.inf), -1
+        for k in range(3):  # Slab
+            if abs(rd[k]) < F(1e-12):
+                if ro[k] < mn[k] or ro[k] > mx[k]:
+                    return None
+                continue
+            inv = F(F(1) / rd[k])
+            t0, t1 = F(F(mn[k] - ro[k]) * inv), F(F(mx[k] - ro[k]) * inv)
+            if t0 > t1:
+                t0, t1 = t1, t0
+            if t0 > t_enter:
+                t_enter, enter_axis = t0, k
+            if t1 < t_exit:
+                t_exit = t1
+            if not t_exit >= t_enter:
+                return None
+        if not t_exit >= max_f(F(0), t_enter):
+            return None
+        t = t_enter
+        if t < t_min:
+            t = t_min
+        if t > t_max or t > t_exit:
+            return None
+        t = F(t + F(1e-6))
+        p = [F(ro[k] + F(rd[k] * t)) for k in range(3)]
+        idx = [min(max(int(np.floor(F(F(p[k] - mn[k]) / size[k]))), 0), g["n"][k] - 1) for k in range(3)]
+        step = [1 if rd[k] > 0 else (-1 if rd[k] < 0 else 0) for k in range(3)]
+        inv_d = [F(0) if step[k] == 0 else F(F(1) / rd[k]) for k in range(3)]
+        next_v = [F(mn[k] + (F(F(idx[k] + 1) * size[k]) if step[k] > 0 else F(F(idx[k]) * size[k]))) for k in range(3)]
+        t_max_a = [F(np.inf) if step[k] == 0 else F(F(next_v[k] - ro[k]) * inv_d[k]) for k in range(3)]
+        t_delta = [F(np.inf) if step[k] == 0 else abs(F(size[k] * inv_d[k])) for k in range(3)]
+        if enter_axis < 0:
+            last_axis = 0 if (t_max_a[0] <= t_max_a[1] and t_max_a[0] <= t_max_a[2]) else (1 if t_max_a[1] <= t_max_a[2] else 2)
+        else:
+            last_axis = enter_axis
+        wire_max2 = F(-1) if g["wire_max"] <= 0 else F(g["wire_max"] * g["wire_max"])
+        dir_len2 = F(F(F(rd[0] * rd[0]) + F(rd[1] * rd[1])) + F(rd[2] * rd[2]))
+        nbx, nby = (nx + 7) >> 3, (ny + 7) >> 3
+        while t <= t_exit and t <= t_max:
+            ix, iy, iz = idx
+            if 0 <= ix < nx and 0 <= iy < ny and 0 <= iz < nz:
+                lx, ly, lz = ix & 7, iy & 7, iz & 7
+                morton = ((lx & 1) << 0) | ((ly & 1) << 1) | ((lz & 1) << 2) | ((lx & 2) << 2) | ((ly & 2) << 3) | ((lz & 2) << 4) | ((lx & 4) << 4) | ((ly & 4) << 5) | ((lz & 4) << 6)
+                at = ((((iz >> 3) * nby) + (iy >> 3)) * nbx + (ix >> 3)) * 512 + morton
+                mat_id = int(g["mat"][at])
+                if mat_id > 0:
+                    meta_id = int(g["meta"][at])
+                    axis = last_axis  # never < 0 here: resolved above
+                    hit_t = max_f(t, t_min)
+                    n = v3(0, 0, 0)
+                    n[axis] = F(-1) if step[axis] > 0 else F(1)
+                    hp = v3(*(F(ro[k] + F(rd[k] * hit_t)) for k in range(3)))  # Ray.At
+                    within = False
+                    if g["wire"] and wire_max2 >= 0:
+                        within = F(F(hit_t * hit_t) * dir_len2) <= wire_max2
+                    mi = g["default"] if mat_id >= g["n_ids"] else int(g["palette"][mat_id * g["levels"] + min(max(meta_id, 0), g["levels"] - 1)])
+                    m = self.mats[mi]
+                    albedo = v3(*m.albedo)
+                    if g["wire"] and within:  # IsWireOnFace: binary32 products widened to binary64
+                        lo = [float(F(mn[k] + F(F(idx[k]) * size[k]))) for k in range(3)]
+                        hi = [lo[k] + float(size[k]) for k in range(3)]
+                        edge = lambda k: min(max(float(hp[k]) - lo[k], 0.0), max(hi[k] - float(hp[k]), 0.0))
+                        a, b = [k for k in range(3) if k != axis]
+                        w = float(F(g["wire_frac"] * min_f(size[a], size[b])))
+                        if edge(a) <= w or edge(b) <= w:
+                            albedo = v3(0, 0, 0)  # WireColor
+                    mat = dict(albedo=albedo, refl=F(m.reflectivity), emission=v3(*m.emission), transparency=F(m.transparency), tint=v3(*m.transmission), ior=F(m.ior))
+                    return dict(t=hit_t, P=hp, N=n, mat=mat, sub=ix + nx * (iy + ny * iz))
+            if t_max_a[0] <= t_max_a[1] and t_max_a[0] <= t_max_a[2]:
+                k = 0
+            elif t_max_a[1] <= t_max_a[2]:
+                k = 1
+            else:
+                k = 2
+            idx[k] += step[k]
+            t = t_max_a[k]
+            t_max_a[k] = F(t_max_a[k] + t_delta[k])
+            last_axis = k
+            if not (0 <= idx[0] < nx and 0 <= idx[1] < ny and 0 <= idx[2] < nz):
+                break
+        return None
+
     # ---- Box.Hit (BoundedObjects.cs:78-115): six rects in a fixed order, the accepted hit shrinks `closest`
     def box_hit_obj(self, o, ro, rd, t_min, t_max):
         mnx, mny, mnz, mxx, mxy, mxz = (F(v) for v in o.p[0:6])
@@ -291,10 +478,18 @@ class LiteralTracer:
             return self.rect_hit(o, 1, 0, 2, q[0], q[1], q[2], q[3], q[4], ro, rd, t_min, t_max)
         if o.kind == 5:  # YZRect(y0, y1, z0, z1, x)
             return self.rect_hit(o, 0, 1, 2, q[0], q[1], q[2], q[3], q[4], ro, rd, t_min, t_max)
+        if o.kind == 2:
+            return self.disk_hit(o, ro, rd, t_min, t_max)
         if o.kind == 6:
             return self.box_hit_obj(o, ro, rd, t_min, t_max)
+        if o.kind == 7:
+            return self.cylinder_hit(o, ro, rd, t_min, t_max)
+        if o.kind == 8:
+            return self.triangle_hit(o, ro, rd, t_min, t_max)
         if o.kind == 9:
             return self.mesh_hit(o, ro, rd, t_min, t_max)
+        if o.kind == 10:
+            return self.volume_hit(o, ro, rd, t_min, t_max)
         raise NotImplementedError(f"object kind {o.kind} is outside this transcription")
 
     # ---- BVH.BoxHitFast BVH.cs:201-236
@@ -392,8 +587,10 @@ class LiteralTracer:
             v = v3(b, F(1.0 - float(F(F(w[1] * w[1]) * a))), -w[1])
         return v3(*(F(F(F(u[k] * x) + F(v[k] * y)) + F(w[k] * z)) for k in range(3)))
 
-    # ---- ComputeTransmittanceToLight :757-798 (not a VolumeScene)
+    # ---- ComputeTransmittanceToLight :757-798
     def transmittance(self, ro, rd, max_dist):
+        if self.is_volume_scene:  # Scene.Occluded (Scene.cs:77-82): a nearest-hit query from 0.001, binary result
+            return v3(0, 0, 0) if self.scene_hit(ro, rd, F(0.001), max_dist) is not None else v3(1, 1, 1)
         tr, tmin, counter = [F(1), F(1), F(1)], F(F(0) + EPS), 0
         while counter < MAX_REFR:
             block = self.scene_hit(ro, rd, tmin, max_dist)
@@ -464,8 +661,37 @@ class LiteralTracer:
                 if m["emission"].any():
                     radiance = add(radiance, beta, m["emission"])
                 base = m["albedo"]
-                if m["transparency"] > 0:
-                    raise NotImplementedError("transparent materials are outside this transcription")
+                if m["transparency"] > 0:  # :506-558: Fresnel split into two deferred work items (reflection pushed first, refraction popped first)
+                    if mirror >= MAX_MIRROR:
+                        break
+                    n, wo = rec["N"], rd
+                    front = dot(n, wo) < 0
+                    nl = n if front else v3(*(F(n[k] * F(-1)) for k in range(3)))
+                    eta_i, eta_t = (F(1), m["ior"]) if front else (m["ior"], F(1))
+                    eta = F(eta_i / eta_t)
+                    k2 = F(F(2) * dot(wo, nl))
+                    refl_dir = normalized(v3(*(F(wo[k] - F(nl[k] * k2)) for k in range(3))))
+                    cosi = -max_f(F(-1), min_f(F(1), dot(wo, nl)))                       # Refract :737-748
+                    kk = F(F(1) - F(F(eta * eta) * F(F(1) - F(cosi * cosi))))
+                    has_refract = not kk < 0
+                    refr_dir = v3(0, 0, 0)
+                    if has_refract:
+                        c2 = F(F(eta * cosi) - np.sqrt(kk, dtype=F))
+                        refr_dir = v3(*(F(F(wo[k] * eta) + F(nl[k] * c2)) for k in range(3)))
+                    cos_theta = abs(dot(nl, v3(*(F(wo[k] * F(-1)) for k in range(3)))))
+                    r0 = F(F(eta_i - eta_t) / F(eta_i + eta_t))                          # FresnelSchlick :750-755
+                    r0 = F(r0 * r0)
+                    R = F(r0 + F(F(F(1) - r0) * self.pow(F(F(1) - cos_theta), F(5))))
+                    tr_c = min(max(m["transparency"], F(0)), F(1))
+                    T = F(F(F(1) - R) * tr_c) if has_refract else F(0)
+                    R = min(max(F(R + F(m["refl"] * F(F(1) - R))), F(0)), F(1))
+                    if R > 0 and len(stack) < 16:
+                        o2 = v3(*(F(rec["P"][k] + F(nl[k] * EPS)) for k in range(3)))
+                        stack.append(dict(ro=o2, rd=normalized(refl_dir), beta=v3(*(F(F(beta[k] * base[k]) * R) for k in range(3))), mirror=mirror + 1, diffuse=diffuse, primary=False))
+                    if T > 0 and len(stack) < 16:
+                        o2 = v3(*(F(rec["P"][k] - F(nl[k] * EPS)) for k in range(3)))
+                        stack.append(dict(ro=o2, rd=normalized(normalized(refr_dir)), beta=v3(*(F(F(beta[k] * m["tint"][k]) * T) for k in range(3))), mirror=mirror + 1, diffuse=diffuse, primary=False))
+                    break
                 if m["refl"] >= MIRROR_THRESHOLD:
                     if mirror >= MAX_MIRROR:
                         break
@@ -508,7 +734,8 @@ class LiteralTracer:
         return radiance, is_sky, g
 
 
-@pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1), ("knot:12x5", 8, 3, 2)])
+@pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1), ("knot:12x5", 8, 3, 2),
+                                                     ("volume_grid_test", 10, 4, 2), ("voxel_world:32x32", 8, 4, 2), ("cylinders_disks_triangles", 10, 4, 2)])
 def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb_h, ss):
     lib = load_oracle()
     lib.yo_set_math_mode(0)
