@@ -1,0 +1,224 @@
+"""The two tree builders pinned by a third implementation in another language: BVH.BuildRecursive (Objects/BVH.cs:258-459, leaf <= 4,
+16 SAH bins, and its quirk: the partition re-derives origin / extent from the UNSORTED first and last items, :394-396) and
+MeshBVH.BuildRecursive (Objects/MeshBVH.cs:371-576, leaf <= 8, consistent pivot), with every TryGetBounds that feeds them,
+transcribed from the C# source into numpy binary32 scalars.  The node arrays (boxes, left / right / start / count), the root and
+the leaf order must equal the host mirror's trees -- the ones the GPU traverses -- field by field; the oracle's own builder is
+compared with the mirror's in test_host.py.  Array.Sort (the builders' fallback) is not transcribed a third time: when a build
+reaches it, the oracle's restatement of .NET's introsort is called, and the test reports whether that happened.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from yetanotherconsolegameengine_b200 import api
+from oracle_binding import load_oracle
+
+F = np.float32
+INF = F(np.inf)
+BINS = 16
+
+
+def surface_area(b):  # BVH.cs:462-466
+    dx, dy, dz = F(b[3] - b[0]), F(b[4] - b[1]), F(b[5] - b[2])
+    return F(F(2) * F(F(F(dx * dy) + F(dx * dz)) + F(dy * dz)))
+
+
+def surround(box, o):  # BVH.cs:253-257
+    for k in range(3):
+        if o[k] < box[k]:
+            box[k] = o[k]
+        if o[3 + k] > box[3 + k]:
+            box[3 + k] = o[3 + k]
+
+
+class Builder:
+    def __init__(self, items, leaf_size, consistent_pivot, sort_lib):
+        self.arr = items  # list of dicts: index, box[6], c[3]
+        self.leaf_size, self.consistent, self.sort_lib = leaf_size, consistent_pivot, sort_lib
+        self.nodes, self.leaf, self.sorts = [], [], 0
+        self.root = self.build(0, len(items))
+
+    def sort_range(self, start, count, axis):  # Array.Sort(arr, start, count, by centroid[axis]) through the oracle's introsort restatement
+        self.sorts += 1
+        keys = np.array([self.arr[start + i]["c"][axis] for i in range(count)], F)
+        payload = np.arange(count, dtype=np.int32)
+        self.sort_lib.yo_dotnet_sort_floats(keys.ctypes.data_as(C.c_void_p), payload.ctypes.data_as(C.c_void_p), count)
+        chunk = [self.arr[start + int(j)] for j in payload]
+        self.arr[start:start + count] = chunk
+
+    def build(self, start, count):
+        arr = self.arr
+        if count <= 0:
+            return -1
+        if count <= self.leaf_size:
+            box = list(arr[start]["box"])
+            for i in range(1, count):
+                surround(box, arr[start + i]["box"])
+            base = len(self.leaf)
+            self.leaf += [arr[start + i]["index"] for i in range(count)]
+            self.nodes.append(dict(box=box, left=-1, right=-1, start=base, count=count))
+            return len(self.nodes) - 1
+        cmin, cmax = list(arr[start]["c"]), list(arr[start]["c"])
+        for i in range(start + 1, start + count):
+            for k in range(3):
+                c = arr[i]["c"][k]
+                if c < cmin[k]:
+                    cmin[k] = c
+                if c > cmax[k]:
+                    cmax[k] = c
+        ext = [F(cmax[k] - cmin[k]) for k in range(3)]
+        axis = 0
+        if ext[1] > ext[0] and ext[1] >= ext[2]:
+            axis = 1
+        elif ext[2] > ext[0] and ext[2] >= ext[1]:
+            axis = 2
+        split_bin, best_axis, best_cost = -1, axis, INF
+        for ax in range(3):
+            extent = ext[ax]
+            if not extent > 0:
+                continue
+            origin, inv_extent = cmin[ax], F(F(1) / extent)
+            counts = [0] * BINS
+            boxes = [[INF, INF, INF, -INF, -INF, -INF] for _ in range(BINS)]
+            for i in range(start, start + count):
+                b = int(F(F(F(arr[i]["c"][ax] - origin) * inv_extent) * F(BINS - 1)))
+                b = min(max(b, 0), BINS - 1)
+                counts[b] += 1
+                surround(boxes[b], arr[i]["box"])
+            left_count, right_count, left_area, right_area = [0] * BINS, [0] * BINS, [F(0)] * BINS, [F(0)] * BINS
+            cur, acc = [INF, INF, INF, -INF, -INF, -INF], 0
+            with np.errstate(invalid="ignore", over="ignore"):
+                for b in range(BINS):
+                    if counts[b] > 0:
+                        surround(cur, boxes[b])
+                    acc += counts[b]
+                    left_count[b], left_area[b] = acc, surface_area(cur)
+                cur, acc = [INF, INF, INF, -INF, -INF, -INF], 0
+                for b in range(BINS - 1, -1, -1):
+                    if counts[b] > 0:
+                        surround(cur, boxes[b])
+                    acc += counts[b]
+                    right_count[b], right_area[b] = acc, surface_area(cur)
+                for b in range(BINS - 1):
+                    lc, rc = left_count[b], right_count[b + 1]
+                    if lc == 0 or rc == 0:
+                        continue
+                    cost = F(F(left_area[b] * F(lc)) + F(right_area[b + 1] * F(rc)))
+                    if cost < best_cost:
+                        best_cost, best_axis, split_bin = cost, ax, b
+        if split_bin < 0:
+            self.sort_range(start, count, best_axis)
+            mid = start + (count >> 1)
+        else:
+            if self.consistent:  # MeshBVH.cs:511-513
+                origin, extent = cmin[best_axis], ext[best_axis]
+                inv_extent = F(F(1) / extent)
+            else:                # BVH.cs:394-396: from the unsorted first / last item
+                origin = arr[start]["c"][best_axis]
+                extent = F(arr[start + count - 1]["c"][best_axis] - origin)
+                inv_extent = F(F(1) / extent) if extent != 0 else F(0)
+            i0, i1 = start, start + count - 1
+            while i0 <= i1:
+                c0 = arr[i0]["c"][best_axis]
+                b0 = int(F(F(F(c0 - origin) * inv_extent) * F(BINS - 1))) if (self.consistent or inv_extent != 0) else 0
+                if b0 <= split_bin:
+                    i0 += 1
+                else:
+                    arr[i0], arr[i1] = arr[i1], arr[i0]
+                    i1 -= 1
+            mid = i0
+            if mid == start or mid == start + count:
+                self.sort_range(start, count, best_axis)
+                mid = start + (count >> 1)
+        my = len(self.nodes)
+        self.nodes.append(None)
+        left = self.build(start, mid - start)
+        right = self.build(mid, start + count - mid)
+        if left >= 0 and right >= 0:
+            lb, rb = self.nodes[left]["box"], self.nodes[right]["box"]
+            box = [min(lb[k], rb[k]) for k in range(3)] + [max(lb[3 + k], rb[3 + k]) for k in range(3)]
+        else:
+            box = list(self.nodes[left if left >= 0 else right]["box"])
+        self.nodes[my] = dict(box=box, left=left, right=right, start=0, count=0)
+        return my
+
+
+def assert_tree_equal(b, tree, what):
+    assert b.root == tree["root"], what
+    assert len(b.nodes) == len(tree["boxes"]), (what, len(b.nodes), len(tree["boxes"]))
+    got_boxes = np.array([n["box"] for n in b.nodes], F)
+    assert np.array_equal(got_boxes.view(np.uint32), np.ascontiguousarray(tree["boxes"]).view(np.uint32)), what + ": node boxes"
+    got = np.array([[n["left"], n["right"], n["start"], n["count"]] for n in b.nodes], np.int32)
+    assert np.array_equal(got, tree["lrsc"]), what + ": left / right / start / count"
+    assert np.array_equal(np.array(b.leaf, np.int32), tree["leaf"]), what + ": leaf order"
+
+
+def triangle_item(i, t):  # MeshBVH.TryComputeBounds :336-349 and the centroid :56-58; Triangle ctor :55-66 uses the same rule
+    a, b, c = t[0:3], t[3:6], t[6:9]
+    e = F(1e-4)
+    box = [F(min(a[k], min(b[k], c[k])) - e) for k in range(3)] + [F(max(a[k], max(b[k], c[k])) + e) for k in range(3)]
+    return dict(index=i, box=box, c=[F(F(0.5) * F(box[k] + box[3 + k])) for k in range(3)])
+
+
+def object_item(i, o, mesh_roots, volumes):  # TryGetBounds of every Hittable
+    p = [F(v) for v in o.p]
+    e = F(1e-4)
+    if o.kind == 1:  # Plane, Surfaces.cs:30-36: a +-1e6 box with centroid exactly 0
+        return dict(index=i, box=[F(-1e6)] * 3 + [F(1e6)] * 3, c=[F(0)] * 3)
+    if o.kind in (0, 2):  # Sphere BoundedObjects.cs:20-28, Disk Surfaces.cs:96-105: centre -+ (r, r, r)
+        r = p[3] if o.kind == 0 else p[6]
+        box = [F(p[k] - r) for k in range(3)] + [F(p[k] + r) for k in range(3)]
+    elif o.kind == 3:  # XYRect :175-181
+        box = [p[0], p[2], F(p[4] - e), p[1], p[3], F(p[4] + e)]
+    elif o.kind == 4:  # XZRect :247-253
+        box = [p[0], F(p[4] - e), p[2], p[1], F(p[4] + e), p[3]]
+    elif o.kind == 5:  # YZRect :319-325
+        box = [F(p[4] - e), p[0], p[2], F(p[4] + e), p[1], p[3]]
+    elif o.kind == 6:  # Box BoundedObjects.cs:92-97
+        box = p[0:6]
+    elif o.kind == 7:  # CylinderY :140-145
+        box = [F(p[0] - p[3]), p[4], F(p[2] - p[3]), F(p[0] + p[3]), p[5], F(p[2] + p[3])]
+    elif o.kind == 8:  # Triangle
+        return dict(triangle_item(i, p[0:9]), index=i)
+    elif o.kind == 9:  # Mesh -> MeshBVH.TryGetBounds: the root node's box
+        box = [F(v) for v in mesh_roots[o.ref_id]]
+    elif o.kind == 10:  # VolumeGrid.TryGetBounds (VolumeGrid.cs:386-403): minCorner .. minCorner + n * voxelSize
+        v = volumes[o.ref_id]
+        box = [F(v.min_corner[k]) for k in range(3)] + [F(F(v.min_corner[k]) + F(F(getattr(v, "nx ny nz".split()[k])) * F(v.voxel_size[k]))) for k in range(3)]
+    else:
+        raise NotImplementedError(o.kind)
+    return dict(index=i, box=list(box), c=[F(F(0.5) * F(box[k] + box[3 + k])) for k in range(3)])
+
+
+@pytest.mark.parametrize("scene_name", ["knot:12x5", "knot:40x10", "teapot"])
+def test_mesh_builder_matches_a_literal_python_transcription(scene_name):
+    lib = load_oracle()
+    lib.yo_set_sort_mode(0)
+    s = api.HostScene(scene_name)
+    tris = s.mesh_triangles(0)
+    items = [triangle_item(i, [F(v) for v in tris[i].reshape(-1)]) for i in range(len(tris))]
+    b = Builder(items, leaf_size=8, consistent_pivot=True, sort_lib=lib)
+    assert_tree_equal(b, s.bvh_arrays(0), scene_name)
+    assert b.sorts == s.bvh_arrays(0)["sort_fallbacks"], "the sort fallback must be reached exactly as often as in the mirror's build"
+    s.close()
+
+
+@pytest.mark.parametrize("scene_name", ["cornell", "mirror_spheres", "cylinders_disks_triangles", "boxes", "test", "volume_grid_test", "teapot",
+                                        "voxel_world:64x64", "texture_gallery"])
+def test_top_level_builder_matches_a_literal_python_transcription(scene_name):
+    lib = load_oracle()
+    lib.yo_set_sort_mode(0)
+    s = api.HostScene(scene_name)
+    flat = s.flat.contents
+    mesh_roots = {}
+    for i in range(s.n_meshes):
+        t = s.bvh_arrays(i)
+        mesh_roots[i] = t["boxes"][t["root"]]
+    volumes = {i: s.volume(i).contents for i in range(s.n_volumes)}
+    items = [object_item(i, flat.objects[i], mesh_roots, volumes) for i in range(flat.n_objects)]
+    b = Builder(items, leaf_size=4, consistent_pivot=False, sort_lib=lib)
+    tree = s.bvh_arrays(-1)
+    assert_tree_equal(b, tree, scene_name)
+    assert b.sorts == tree["sort_fallbacks"]
+    s.close()
