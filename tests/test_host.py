@@ -273,3 +273,42 @@ def test_scne_snapshot_format_and_round_trip(tmp_path):
     with pytest.raises(ValueError):
         open(p, "wb").write(b"NOPE" + bytes(60))
         api.HostScene("snapshot:" + p)
+
+
+KIND = {"sphere": 0, "plane": 1, "disk": 2, "xyrect": 3, "xzrect": 4, "yzrect": 5, "box": 6, "cylinder_y": 7, "triangle": 8}
+N_PARAMS = {"sphere": 4, "plane": 6, "disk": 7, "xyrect": 5, "xzrect": 5, "yzrect": 5, "box": 6, "cylinder_y": 7, "triangle": 9}
+
+
+@pytest.mark.parametrize("name", ["test", "cornell", "mirror_spheres", "cylinders_disks_triangles", "boxes", "texture_test"])
+def test_scene_factories_match_the_reference_source(name):
+    """The mirror's scene factories against tests/golden/scene_literals.json, which tools/extract_scene_literals.py produces by
+    EXECUTING the reference's C# factories (Scenes/Scenes.cs: statements rewritten into Python syntax, run against recording
+    classes with the reference's float conversions): every object in order with its constructor values, material function
+    (constant or checker with both materials and the scale), Specular / Reflectivity override, lights, ambient, background."""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scene_literals.json")))[name]
+    s = api.HostScene(name)
+    flat = s.flat.contents
+    f32 = lambda x: float(np.float32(x))
+    assert [f32(v) for v in flat.bg_top] == gold["bg_top"] and [f32(v) for v in flat.bg_bottom] == gold["bg_bottom"]
+    assert [f32(v) for v in flat.ambient_color] == gold["ambient"]["color"] and f32(flat.ambient_intensity) == gold["ambient"]["intensity"]
+    assert flat.n_lights == len(gold["lights"])
+    for i, l in enumerate(gold["lights"]):
+        assert ([f32(v) for v in flat.lights[i].pos], [f32(v) for v in flat.lights[i].color], f32(flat.lights[i].intensity)) == (l["pos"], l["color"], l["intensity"]), ("light", i)
+    assert flat.n_objects == len(gold["objects"])
+
+    def mat(m):
+        return dict(albedo=[f32(v) for v in m.albedo], specular=f32(m.specular), reflectivity=f32(m.reflectivity), emission=[f32(v) for v in m.emission],
+                    transparency=f32(m.transparency), ior=f32(m.ior), tint=[f32(v) for v in m.transmission], textured=m.tex_id >= 0, tex_weight=f32(m.tex_weight),
+                    uv_scale=f32(m.uv_scale))
+
+    for i, g in enumerate(gold["objects"]):
+        o = flat.objects[i]
+        assert o.kind == KIND[g["kind"]], (i, g["kind"])
+        assert [f32(v) for v in o.p[0:N_PARAMS[g["kind"]]]] == g["p"], (i, g["kind"], "constructor values")
+        assert f32(o.checker_scale) == g["checker_scale"] and bool(o.override_sr) == g["override_sr"], (i, "material function")
+        assert mat(flat.materials[o.mat_a]) == g["a"], (i, "material a")
+        assert mat(flat.materials[o.mat_b]) == g["b"], (i, "material b")
+        if g["override_sr"]:
+            assert (f32(o.specular), f32(o.reflectivity)) == (g["specular"], g["reflectivity"]), (i, "Specular / Reflectivity override")
+    s.close()

@@ -1,0 +1,158 @@
+"""Generates tests/golden/scene_literals.json from the reference's C# scene factories (RayTracing/Scenes/Scenes.cs), so that the
+host mirror's factories (host/ycge_host.cpp) can be checked against the source mechanically instead of by reading.
+
+The factories are straight-line C#: declarations with literal arithmetic, `new X(...)`, `s.Add(...)`, `s.Lights.Add(...)`.  Each
+statement is rewritten into Python syntax (type prefixes dropped, `new` dropped, `1.5f` -> binary32, lambdas that return a captured
+material -> Constant(m)) and executed against small recording classes that apply the reference's own conversions (Vec3(double,
+double,double) casts to float, `float` arithmetic stays binary32).  Needs /root/reference; the JSON it writes is the fixture
+tests/test_host.py::test_scene_factories_match_the_reference_source reads.
+    python tools/extract_scene_literals.py [path/to/ConsoleGame]
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+F = np.float32
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FUNCS = {"test": "BuildTestScene", "cornell": "BuildCornellBox", "mirror_spheres": "BuildMirrorSpheresOnChecker",
+         "cylinders_disks_triangles": "BuildCylindersDisksAndTriangles", "boxes": "BuildBoxesShowcase", "texture_test": "BuildTextureTestScene"}
+
+
+def f32(x):
+    return float(F(x))
+
+
+class Vec3:
+    def __init__(self, x, y, z):
+        self.v = [f32(x), f32(y), f32(z)]  # Vec3(double, double, double) casts each component to float (Vec3.cs:21-26)
+
+
+class Material:  # Material.cs:5-61: scalars are doubles; the path reads them through (float) casts
+    def __init__(self, albedo, specular, reflectivity, emission, transparency=0.0, ior=1.5, tint=None):
+        self.albedo, self.specular, self.reflectivity, self.emission = albedo.v, float(specular), float(reflectivity), emission.v
+        self.transparency, self.ior, self.tint = float(transparency), float(ior), (tint.v if tint else [1.0, 1.0, 1.0])
+        self.DiffuseTexture, self.TextureWeight, self.UVScale = None, 1.0, 1.0
+
+    def dump(self):
+        return dict(albedo=self.albedo, specular=f32(self.specular), reflectivity=f32(self.reflectivity), emission=self.emission, transparency=f32(self.transparency),
+                    ior=f32(self.ior), tint=self.tint, textured=self.DiffuseTexture is not None, tex_weight=f32(self.TextureWeight), uv_scale=f32(self.UVScale))
+
+
+class MatFunc:
+    def __init__(self, a, b, scale):
+        self.a, self.b, self.scale = a, b, f32(scale)
+
+
+def Solid(albedo):  # Scenes.cs:408-411
+    m = Material(albedo, 0.0, 0.0, Vec3(0, 0, 0))
+    return MatFunc(m, m, 0.0)
+
+
+def Emissive(emission):  # :413-416
+    m = Material(Vec3(0.0, 0.0, 0.0), 0.0, 0.0, emission)
+    return MatFunc(m, m, 0.0)
+
+
+def Checker(a, b, scale):  # :418-428
+    return MatFunc(Material(a, 0.0, 0.0, Vec3(0, 0, 0)), Material(b, 0.0, 0.0, Vec3(0, 0, 0)), scale)
+
+
+def Constant(m):
+    return MatFunc(m, m, 0.0)
+
+
+class Texture:
+    def __init__(self, path):
+        self.path = path
+
+
+class Scene:
+    def __init__(self):
+        self.objects, self.lights = [], []
+        self.Lights = self
+        self.Ambient, self.BackgroundTop, self.BackgroundBottom = None, None, None
+
+    def Add(self, o):
+        (self.lights if o["kind"] == "light" else self.objects).append(o)
+
+    def Update(self, dt):
+        pass
+
+
+def obj(kind, p, func=None, specular=None, reflectivity=None, mat=None):
+    d = dict(kind=kind, p=[f32(v) for v in p])
+    if func is not None:  # flat primitives and Box overwrite Specular / Reflectivity of the function's result (Surfaces.cs:64-66)
+        d.update(a=func.a.dump(), b=func.b.dump(), checker_scale=func.scale, override_sr=True, specular=f32(specular), reflectivity=f32(reflectivity))
+    else:
+        d.update(a=mat.dump(), b=mat.dump(), checker_scale=0.0, override_sr=False)
+    return d
+
+
+def normalized(v):  # Vec3.Normalized (Vec3.cs:98-107) as the Plane / Disk ctors apply it
+    l2 = F(F(F(F(v[0]) * F(v[0])) + F(F(v[1]) * F(v[1]))) + F(F(v[2]) * F(v[2])))
+    if l2 <= 0:
+        return v
+    inv = F(F(1) / np.sqrt(l2, dtype=F))
+    return [f32(F(v[0]) * inv), f32(F(v[1]) * inv), f32(F(v[2]) * inv)]
+
+
+NS = dict(
+    F=F, Vec3=Vec3, Material=Material, Solid=Solid, Emissive=Emissive, Checker=Checker, Constant=Constant, Scene=Scene, Texture=Texture, true=True, false=False,
+    AmbientLight=lambda c, i: dict(color=c.v, intensity=f32(i)),
+    PointLight=lambda p, c, i: dict(kind="light", pos=p.v, color=c.v, intensity=f32(i)),
+    Sphere=lambda c, r, m: obj("sphere", c.v + [r], mat=m),
+    Plane=lambda p, n, f, s, r: obj("plane", p.v + normalized(n.v), f, s, r),
+    Disk=lambda c, n, rad, f, s, r: obj("disk", c.v + normalized(n.v) + [rad], f, s, r),
+    XYRect=lambda a0, a1, b0, b1, k, f, s, r: obj("xyrect", [a0, a1, b0, b1, k], f, s, r),
+    XZRect=lambda a0, a1, b0, b1, k, f, s, r: obj("xzrect", [a0, a1, b0, b1, k], f, s, r),
+    YZRect=lambda a0, a1, b0, b1, k, f, s, r: obj("yzrect", [a0, a1, b0, b1, k], f, s, r),
+    Box=lambda mn, mx, f, s, r: obj("box", mn.v + mx.v, f, s, r),
+    CylinderY=lambda c, rad, y0, y1, capped, m: obj("cylinder_y", c.v + [rad, y0, y1, 1.0 if capped else 0.0], mat=m),
+    Triangle=lambda a, b, c, m: obj("triangle", a.v + b.v + c.v, mat=m),
+)
+
+
+def function_body(src, name):
+    at = src.index("public static Scene " + name + "()")
+    i = src.index("{", at)
+    depth, j = 0, i
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[j], 0)
+        if depth == 0:
+            return src[i + 1:j]
+        j += 1
+
+
+def to_python(stmt):
+    s = stmt.strip()
+    if not s or s.startswith("return"):
+        return None
+    s = re.sub(r"^(?:[\w\.]+(?:<[^=]*>)?)\s+(\w+)\s*=", r"\1 =", s)             # `Type name = ...` -> `name = ...`
+    s = re.sub(r"\(\s*\w+\s*,\s*\w+\s*,\s*\w+\s*\)\s*=>\s*(\w+)", r"Constant(\1)", s)   # (pos, n, u) => capturedMaterial
+    s = s.replace("ConsoleGame.Renderer.Texture", "Texture").replace("Vec3.Zero", "Vec3(0, 0, 0)").replace("new ", "")
+    s = re.sub(r'@"([^"]*)"', r'"\1"', s)
+    s = re.sub(r"(?<![\w.])(\d+\.\d+|\d+)f\b", r"F(\1)", s)                        # binary32 literals
+    return s
+
+
+def extract(src, name):
+    body = re.sub(r"//[^\n]*", "", function_body(src, name))
+    ns = dict(NS)
+    for stmt in body.split(";"):
+        py = to_python(stmt)
+        if py:
+            exec(py, ns)
+    s = ns["s"]
+    return dict(ambient=s.Ambient, bg_top=s.BackgroundTop.v, bg_bottom=s.BackgroundBottom.v, lights=[{k: v for k, v in l.items() if k != "kind"} for l in s.lights], objects=s.objects)
+
+
+if __name__ == "__main__":
+    ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/ConsoleGame"
+    src = open(os.path.join(ref, "RayTracing", "Scenes", "Scenes.cs"), encoding="utf-8-sig").read()
+    out = {scene: extract(src, fn) for scene, fn in FUNCS.items()}
+    dst = os.path.join(ROOT, "tests", "golden", "scene_literals.json")
+    json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
+    print(dst, {k: (len(v["objects"]), len(v["lights"])) for k, v in out.items()})
