@@ -72,7 +72,8 @@ class Texture:
 class Scene:
     def __init__(self):
         self.objects, self.lights = [], []
-        self.Lights = self
+        self.Lights = self.Objects = self
+        self.DefaultCameraPos = None
         self.Ambient, self.BackgroundTop, self.BackgroundBottom = None, None, None
 
     def Add(self, o):
@@ -116,7 +117,7 @@ NS = dict(
 
 
 def function_body(src, name):
-    at = src.index("public static Scene " + name + "()")
+    at = re.search(r"(?:public|private) static Scene " + name + r"\(\)", src).start()
     i = src.index("{", at)
     depth, j = 0, i
     while True:
@@ -138,9 +139,62 @@ def to_python(stmt):
     return s
 
 
+CONSOLE_COLORS = ["Black", "DarkBlue", "DarkGreen", "DarkCyan", "DarkRed", "DarkMagenta", "DarkYellow", "Gray", "DarkGray", "Blue", "Green", "Cyan", "Red", "Magenta",
+                  "Yellow", "White"]  # System.ConsoleColor, values 0..15
+
+
+def mesh_swatches(src):
+    """MeshSwatches (MeshScenes.cs:12-103): the Palette16 table and the named swatches, evaluated from the source text."""
+    table = re.search(r"Palette16 = new Vec3\[\]\s*\{(.*?)\};", src, re.S).group(1)
+    palette = [Vec3(*(F(v) for v in m)) for m in re.findall(r"new Vec3\(([\d.]+)f,([\d.]+)f,([\d.]+)f\)", table)]
+    assert len(palette) == 16
+
+    def from_console(name):
+        return palette[CONSOLE_COLORS.index(name)]
+
+    def scale(name, k):  # :43-49
+        k = min(max(F(k), F(0)), F(1))
+        v = from_console(name)
+        return Vec3(F(v.v[0]) * k, F(v.v[1]) * k, F(v.v[2]) * k)
+
+    out = {}
+    for name, expr in re.findall(r"public static readonly Vec3 (\w+) = ([^;]+);", src):
+        m = re.match(r"FromConsole\(ConsoleColor\.(\w+)\)", expr)
+        if m:
+            out[name] = from_console(m.group(1))
+            continue
+        m = re.match(r"Scale\(ConsoleColor\.(\w+), ([\d.]+)f\)", expr)
+        if m:
+            out[name] = scale(m.group(1), m.group(2))
+            continue
+        m = re.match(r"new Vec3\(([\d.]+)f, ([\d.]+)f, ([\d.]+)f\)", expr)
+        out[name] = Vec3(*(F(v) for v in m.groups()))
+    return out
+
+
+def mesh_scene_materials(src):
+    """Build{Cow,Bunny,Teapot,Dragon}Scene (:108-143): the mesh material (MeshSwatches.Matte / Mirror of a swatch) and the camera."""
+    sw = mesh_swatches(src)
+    out = {}
+    for scene, fn in (("cow", "BuildCowScene"), ("bunny", "BuildBunnyScene"), ("teapot", "BuildTeapotScene"), ("dragon", "BuildDragonScene")):
+        body = function_body(src, fn)
+        kind, swatch, args = re.search(r"MeshSwatches\.(Matte|Mirror)\(MeshSwatches\.(\w+)((?:, [\d.]+)*)\)", body).groups()
+        nums = [float(v) for v in re.findall(r"[\d.]+", args)]
+        if kind == "Matte":   # Matte(albedo, specular = 0.10, reflectivity = 0.00) :92-95
+            spec, refl = (nums + [0.10, 0.00][len(nums):])[:2]
+        else:                 # Mirror(tint, reflectivity = 0.85) :96-99
+            spec, refl = 0.0, (nums + [0.85])[0]
+        cam = re.search(r"s\.DefaultCameraPos = new Vec3\(([^)]*)\)", body)
+        target = re.search(r"targetPos: new Vec3\(([^)]*)\)", body).group(1)
+        out[scene] = dict(material=Material(sw[swatch], spec, refl, Vec3(0, 0, 0)).dump(),
+                          camera=[f32(v) for v in cam.group(1).split(",")] if cam else None,
+                          target_pos=[f32(v.strip().rstrip("f")) for v in target.split(",")])
+    return out
+
+
 def extract(src, name):
     body = re.sub(r"//[^\n]*", "", function_body(src, name))
-    ns = dict(NS)
+    ns = dict(NS, FloorMat=Solid, MeshBVH=type("MeshBVH", (), {}))  # FloorMat (MeshScenes.cs:372-375) is Solid by another name
     for stmt in body.split(";"):
         py = to_python(stmt)
         if py:
@@ -153,6 +207,9 @@ if __name__ == "__main__":
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/ConsoleGame"
     src = open(os.path.join(ref, "RayTracing", "Scenes", "Scenes.cs"), encoding="utf-8-sig").read()
     out = {scene: extract(src, fn) for scene, fn in FUNCS.items()}
+    msrc = open(os.path.join(ref, "RayTracing", "Scenes", "MeshScenes.cs"), encoding="utf-8-sig").read()
+    out["mesh_base"] = extract(msrc, "NewBaseScene")
+    out["mesh_scenes"] = mesh_scene_materials(msrc)
     dst = os.path.join(ROOT, "tests", "golden", "scene_literals.json")
     json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
-    print(dst, {k: (len(v["objects"]), len(v["lights"])) for k, v in out.items()})
+    print(dst, {k: (len(v["objects"]), len(v["lights"])) for k, v in out.items() if "objects" in v}, out["mesh_scenes"]["dragon"])
