@@ -130,3 +130,29 @@ def test_missing_extension_raises(monkeypatch):
     monkeypatch.setattr(api, "LIB_PATH", os.path.join(PKG, "does_not_exist.so"))
     with pytest.raises(ImportError):
         api.load_lib()
+
+
+def test_default_params_are_the_reference_constants():
+    """ycge_default_params (and the oracle's) against the constants extracted from RaytraceRenderer.cs:31-43,:65,:222,:281 and
+    ToneMapper.cs:8-21 by tools/extract_scene_literals.py (tests/golden/scene_literals.json)."""
+    import ctypes as C
+    import json
+    import os
+    import sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    from oracle_binding import load_oracle
+    gold = json.load(open(os.path.join(here, "golden", "scene_literals.json")))["params"]
+    for fill in (api.load_lib().ycge_default_params, load_oracle().yo_default_params):
+        p = api.Params()
+        fill(C.byref(p))
+        for k, want in gold.items():
+            got = getattr(p, k)
+            if isinstance(want, bool):
+                assert bool(got) == want, k
+            elif isinstance(want, int):
+                assert int(got) == want, k
+            else:
+                assert float(np.float32(got)) == want, (k, got, want)
+        assert set(gold) == {f[0] for f in api.Params._fields_}, "every field of ycge_params has a reference constant behind it"

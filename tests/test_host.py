@@ -349,3 +349,28 @@ def test_mesh_scenes_match_the_reference_source(name):
     assert abs(lo[1] - (ms["target_pos"][1] + 0.01)) < 0.15
     assert abs(0.5 * (lo[0] + hi[0]) - ms["target_pos"][0]) < 0.51 and abs(0.5 * (lo[2] + hi[2]) - ms["target_pos"][2]) < 0.51
     s.close()
+
+
+def test_voxel_palette_matches_the_reference_source():
+    """VoxelMaterialPalette.MaterialLookup (Scenes/VoxelMaterialPalette.cs:8-98) crosses the C ABI as a table (ycge_volume.palette);
+    every (block id, meta) of the mirror's table against the lookup evaluated from the C# switch statements by
+    tools/extract_scene_literals.py, including the meta clamp of Stone / Ore, unknown ids, PalMat's specular and reflectivity."""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scene_literals.json")))["voxel_palette"]
+    s = api.HostScene("voxel_world:32x32")
+    flat, v = s.flat.contents, s.volume(0).contents
+    levels, f32 = max(1, v.palette_meta_levels), lambda x: float(np.float32(x))
+
+    def lookup(bid, meta):  # the library's rule (csrc/post.cuh voxel_pack_kernel)
+        mi = v.palette_default if bid >= v.palette_n_ids else v.palette[bid * levels + min(max(meta, 0), levels - 1)]
+        return flat.materials[mi]
+
+    for key, albedo in gold["lookup"].items():
+        bid, meta = (int(x) for x in key.split(","))
+        if bid == 0:
+            continue  # Air is never looked up: matId > 0 is the solidity test (VolumeGrid.cs:158)
+        m = lookup(bid, meta)
+        assert [f32(x) for x in m.albedo] == albedo, (key, list(m.albedo), albedo)
+        assert (f32(m.specular), f32(m.reflectivity), list(m.emission), f32(m.transparency)) == (gold["specular"], gold["reflectivity"], [0.0, 0.0, 0.0], 0.0), key
+    assert [f32(x) for x in lookup(999, 0).albedo] == gold["default"]
+    s.close()

@@ -192,6 +192,59 @@ def mesh_scene_materials(src):
     return out
 
 
+def renderer_constants(ref):
+    """The compile-time constants of the path (RaytraceRenderer.cs:31-43,:65,:222,:281; ToneMapper.cs:8-21) = ycge_default_params."""
+    rr = open(os.path.join(ref, "RayTracing", "RaytraceRenderer.cs"), encoding="utf-8-sig").read()
+    tm = open(os.path.join(ref, "RayTracing", "ToneMapper.cs"), encoding="utf-8-sig").read()
+
+    def num(src, name):
+        m = re.search(r"\b" + name + r"\s*[=:]\s*([-\d.e]+|0x[0-9A-Fa-f]+|true|false)(?:f|UL)?\b", src)
+        v = m.group(1)
+        return int(v, 16) if v.startswith("0x") else (v == "true") if v in ("true", "false") else (int(v) if re.fullmatch(r"-?\d+", v) else f32(v))
+
+    return dict(diffuse_bounces=num(rr, "DiffuseBounces"), max_mirror_bounces=num(rr, "MaxMirrorBounces"), max_refractions=num(rr, "MaxRefractions"),
+                mirror_threshold=num(rr, "MirrorThreshold"), eps=num(rr, "Eps"), seed_salt=num(rr, "SeedSalt"), taa_alpha=num(rr, "taaAlpha"),
+                motion_trans_reset=num(rr, "MotionTransReset"), motion_rot_reset=num(rr, "MotionRotReset"), diffuse_sigma_deg=num(rr, "DiffuseSigmaDeg"),
+                luminance_pad=num(rr, "luminancePad"), atrous_iterations=num(rr, "iterations"), c_phi=num(rr, "cPhi"), n_phi=num(rr, "nPhi"), z_phi=num(rr, "zPhi"),
+                a_phi=num(rr, "aPhi"), tone_exposure=num(tm, "toneExposure"), tone_gamma=num(tm, "toneGamma"), auto_exposure=num(tm, "autoExposure"),
+                ae_key=num(tm, "aeKey"), ae_speed=num(tm, "aeSpeed"), ae_min=num(tm, "aeMin"), ae_max=num(tm, "aeMax"), saturation=num(tm, "toneSaturation"),
+                vibrance=num(tm, "toneVibrance"))
+
+
+def voxel_palette(ref):
+    """VoxelMaterialPalette (Scenes/VoxelMaterialPalette.cs:8-98): MaterialLookup(id, meta) for every block id and meta 0..2, evaluated
+    from the two switch statements (Normalize, CreateMaterial), the Palette16 table and PalMat."""
+    src = open(os.path.join(ref, "RayTracing", "Scenes", "VoxelMaterialPalette.cs"), encoding="utf-8-sig").read()
+    blocks = dict(re.findall(r"public const int (\w+) = (\d+);", open(os.path.join(ref, "RayTracing", "Scenes", "WorldGeneration", "WorldGenSettings.cs"), encoding="utf-8-sig").read().split("class Blocks")[1].split("}")[0]))
+    table = re.search(r"Palette16 = new Vec3\[\]\s*\{(.*?)\};", src, re.S).group(1)
+    palette = [[f32(v) for v in m] for m in re.findall(r"new Vec3\(([\d.]+),([\d.]+),([\d.]+)\)", table)]
+    spec, refl = re.search(r"new Material\(c, ([\d.]+), ([\d.]+),", src).groups()
+    norm_src = src[src.index("Normalize(int id, int meta)"):src.index("CreateMaterial((int id, int meta) key)")]
+    normalize = {}
+    for name, nid, meta in re.findall(r"case WorldGenSettings\.Blocks\.(\w+): return \((\d+), (0|Clamp\(meta, 0, 2\))\);", norm_src):
+        normalize[int(blocks[name])] = (int(nid), meta != "0")
+    norm_default = tuple(int(v) for v in re.search(r"default: return \((\d+), (\d+)\);", norm_src).groups())
+    create_src = src[src.index("CreateMaterial((int id, int meta) key)"):src.index("private static void Prewarm()")]
+    create = {}
+    for m in re.finditer(r"case (\d+):\s*(?:return PalMat\((\d+)\);|switch \(key\.meta\)\s*\{(.*?)\})", create_src, re.S):
+        if m.group(2) is not None:
+            create[int(m.group(1))] = {None: int(m.group(2))}
+        else:
+            inner = {int(a): int(b) for a, b in re.findall(r"case (\d+): return PalMat\((\d+)\);", m.group(3))}
+            inner[None] = int(re.search(r"default: return PalMat\((\d+)\);", m.group(3)).group(1))
+            create[int(m.group(1))] = inner
+    lookup = {}
+    for bid in range(0, 13):
+        for meta in range(3):
+            if bid in normalize:
+                nid, nmeta = normalize[bid][0], (min(max(meta, 0), 2) if normalize[bid][1] else 0)
+            else:
+                nid, nmeta = norm_default
+            entry = create[nid]
+            lookup[f"{bid},{meta}"] = palette[entry.get(nmeta, entry[None])]
+    return dict(lookup=lookup, specular=f32(spec), reflectivity=f32(refl), default=palette[create[norm_default[0]].get(norm_default[1], create[norm_default[0]][None])])
+
+
 def extract(src, name):
     body = re.sub(r"//[^\n]*", "", function_body(src, name))
     ns = dict(NS, FloorMat=Solid, MeshBVH=type("MeshBVH", (), {}))  # FloorMat (MeshScenes.cs:372-375) is Solid by another name
@@ -210,6 +263,8 @@ if __name__ == "__main__":
     msrc = open(os.path.join(ref, "RayTracing", "Scenes", "MeshScenes.cs"), encoding="utf-8-sig").read()
     out["mesh_base"] = extract(msrc, "NewBaseScene")
     out["mesh_scenes"] = mesh_scene_materials(msrc)
+    out["params"] = renderer_constants(ref)
+    out["voxel_palette"] = voxel_palette(ref)
     dst = os.path.join(ROOT, "tests", "golden", "scene_literals.json")
     json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
-    print(dst, {k: (len(v["objects"]), len(v["lights"])) for k, v in out.items() if "objects" in v}, out["mesh_scenes"]["dragon"])
+    print(dst, {k: (len(v["objects"]), len(v["lights"])) for k, v in out.items() if "objects" in v}, out["params"])
