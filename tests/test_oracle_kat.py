@@ -298,3 +298,17 @@ def test_texture_sample_bilinear_known_answers():
         o.yo_texture_sample(w, h, px.ctypes.data, C.c_float(u), C.c_float(v), out)
         want = sample(u, v)
         assert [bits(float(x)) for x in out] == [bits(float(x)) for x in want], (u, v)
+
+
+def test_tables_match_the_reference_source(oracle_lib):
+    """BlueNoise8x8, the 16-colour console palette and the colour-cube thresholds as the oracle holds them, against the tables
+    extracted from RaytraceSampler.cs:9-19, Renderer/Chexel.cs:11-29 and ANSITerminalRenderer.cs:288-296 by
+    tools/extract_scene_literals.py (tests/golden/scene_literals.json)."""
+    import json
+    import os
+    t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scene_literals.json")))["tables"]
+    assert [[oracle_lib.yo_blue_noise_table(iy, ix) for ix in range(8)] for iy in range(8)] == t["blue_noise"]
+    for i, (r, g, b) in enumerate(t["palette16"]):  # every palette entry is its own nearest colour; 7 (0.75 grey) and 8 (0.5 grey) are distinct
+        assert oracle_lib.yo_nearest16(r, g, b) == i
+    level = lambda v: next((lv for bound, lv in t["cube_thresholds"] if v < bound), 5)
+    assert [oracle_lib.yo_cube_level(v) for v in range(256)] == [level(v) for v in range(256)]

@@ -245,6 +245,21 @@ def voxel_palette(ref):
     return dict(lookup=lookup, specular=f32(spec), reflectivity=f32(refl), default=palette[create[norm_default[0]].get(norm_default[1], create[norm_default[0]][None])])
 
 
+def tables(ref):
+    """Small tables of the path: BlueNoise8x8 (RaytraceSampler.cs:9-19), the 16-colour palette (Renderer/Chexel.cs:11-29), the colour
+    cube thresholds (ANSITerminalRenderer.cs:288-296)."""
+    rs = open(os.path.join(ref, "RayTracing", "RaytraceSampler.cs"), encoding="utf-8-sig").read()
+    blue = [[int(v) for v in row.split(",")] for row in re.findall(r"\{\s*((?:\d+\s*,\s*){7}\d+)\s*\}", rs)]
+    ch = open(os.path.join(ref, "Renderer", "Chexel.cs"), encoding="utf-8-sig").read()
+    pal = re.search(r"s_Palette16 = new Vec3\[\]\s*\{(.*?)\};", ch, re.S).group(1)
+    palette = [[f32(v) for v in m] for m in re.findall(r"new Vec3\(([\d.]+)f,([\d.]+)f,([\d.]+)f\)", pal)]
+    an = open(os.path.join(ref, "Renderer", "ANSITerminalRenderer.cs"), encoding="utf-8-sig").read()
+    cube = an[an.index("ToCubeLevelSrgb(byte v)"):]
+    thresholds = [[int(a), int(b)] for a, b in re.findall(r"if \(v < (\d+)\) return (\d+);", cube[:cube.index("}")])]
+    assert len(blue) == 8 and len(palette) == 16 and len(thresholds) == 5
+    return dict(blue_noise=blue, palette16=palette, cube_thresholds=thresholds)
+
+
 def extract(src, name):
     body = re.sub(r"//[^\n]*", "", function_body(src, name))
     ns = dict(NS, FloorMat=Solid, MeshBVH=type("MeshBVH", (), {}))  # FloorMat (MeshScenes.cs:372-375) is Solid by another name
@@ -265,6 +280,7 @@ if __name__ == "__main__":
     out["mesh_scenes"] = mesh_scene_materials(msrc)
     out["params"] = renderer_constants(ref)
     out["voxel_palette"] = voxel_palette(ref)
+    out["tables"] = tables(ref)
     dst = os.path.join(ROOT, "tests", "golden", "scene_literals.json")
     json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
     print(dst, {k: (len(v["objects"]), len(v["lights"])) for k, v in out.items() if "objects" in v}, out["params"])
