@@ -7,8 +7,12 @@
  *
  * PARITY UNPINNED: the reference (C#/.NET 8) has no tests, golden vectors or fixtures for this path
  * and cannot be compiled or run here (no dotnet/mono).  This file follows the reference source line
- * by line (citations are relative to /root/reference/ConsoleGame/); it is pinned only by known-answer
- * vectors derived by hand from the integer-defined parts (tests/test_oracle_kat.py).
+ * by line (citations are relative to /root/reference/ConsoleGame/).  What pins it instead:
+ * known-answer vectors derived by hand from the integer-defined parts (tests/test_oracle_kat.py); a SECOND restatement of
+ * every stage in another language, transcribed from the C# source into numpy binary32 scalars, that reproduces this file bit
+ * for bit (trace: tests/test_oracle_trace_literal.py; TAA, exposure, cells, à-trous: tests/test_oracle_render.py; both BVH
+ * builders: tests/test_bvh_builder_literal.py); scene factories, palettes, tables and constants compared with values
+ * extracted mechanically from the C# text (tools/extract_scene_literals.py).
  *
  * Arithmetic rules: binary32 everywhere the reference uses float, evaluated in the reference's
  * order, no FMA contraction (build with -O2 -ffp-contract=off, no -ffast-math, x86-64 SSE2).
