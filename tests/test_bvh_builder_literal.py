@@ -3,8 +3,8 @@
 MeshBVH.BuildRecursive (Objects/MeshBVH.cs:371-576, leaf <= 8, consistent pivot), with every TryGetBounds that feeds them,
 transcribed from the C# source into numpy binary32 scalars.  The node arrays (boxes, left / right / start / count), the root and
 the leaf order must equal the host mirror's trees -- the ones the GPU traverses -- field by field; the oracle's own builder is
-compared with the mirror's in test_host.py.  Array.Sort (the builders' fallback) is not transcribed a third time: when a build
-reaches it, the oracle's restatement of .NET's introsort is called, and the test reports whether that happened.
+compared with the mirror's in test_host.py.  Array.Sort (the builders' fallback) is reached by two scenes, on ranges of at most
+16 items, where .NET's introsort is an insertion sort: that path is transcribed too (Builder.sort_range).
 """
 import ctypes as C
 
@@ -36,16 +36,44 @@ class Builder:
     def __init__(self, items, leaf_size, consistent_pivot, sort_lib):
         self.arr = items  # list of dicts: index, box[6], c[3]
         self.leaf_size, self.consistent, self.sort_lib = leaf_size, consistent_pivot, sort_lib
-        self.nodes, self.leaf, self.sorts = [], [], 0
+        self.nodes, self.leaf, self.sorts, self.sort_sizes = [], [], 0, []
         self.root = self.build(0, len(items))
 
-    def sort_range(self, start, count, axis):  # Array.Sort(arr, start, count, by centroid[axis]) through the oracle's introsort restatement
+    def sort_range(self, start, count, axis):
+        """Array.Sort(arr, start, count, by centroid[axis]).  Up to 16 elements .NET's IntroSort (ArraySortHelper<T>.IntroSort,
+        dotnet/runtime, .NET 8) is two or three SwapIfGreater calls or an insertion sort; those paths are transcribed here, so the
+        trees of the scenes below confirm them independently of the oracle.  Longer ranges (never reached by any scene or mesh in
+        this repository) go through the oracle's restatement of the full introsort."""
         self.sorts += 1
-        keys = np.array([self.arr[start + i]["c"][axis] for i in range(count)], F)
-        payload = np.arange(count, dtype=np.int32)
-        self.sort_lib.yo_dotnet_sort_floats(keys.ctypes.data_as(C.c_void_p), payload.ctypes.data_as(C.c_void_p), count)
-        chunk = [self.arr[start + int(j)] for j in payload]
-        self.arr[start:start + count] = chunk
+        self.sort_sizes.append(count)
+        key = lambda it: it["c"][axis]
+        a = self.arr
+
+        def swap_if_greater(i, j):
+            if key(a[start + i]) > key(a[start + j]):
+                a[start + i], a[start + j] = a[start + j], a[start + i]
+
+        if count < 2:
+            return
+        if count == 2:
+            swap_if_greater(0, 1)
+        elif count == 3:
+            swap_if_greater(0, 1)
+            swap_if_greater(0, 2)
+            swap_if_greater(1, 2)
+        elif count <= 16:
+            for i in range(count - 1):  # InsertionSort
+                t = a[start + i + 1]
+                j = i
+                while j >= 0 and key(t) < key(a[start + j]):
+                    a[start + j + 1] = a[start + j]
+                    j -= 1
+                a[start + j + 1] = t
+        else:
+            keys = np.array([key(a[start + i]) for i in range(count)], F)
+            payload = np.arange(count, dtype=np.int32)
+            self.sort_lib.yo_dotnet_sort_floats(keys.ctypes.data_as(C.c_void_p), payload.ctypes.data_as(C.c_void_p), count)
+            a[start:start + count] = [a[start + int(j)] for j in payload]
 
     def build(self, start, count):
         arr = self.arr
@@ -221,4 +249,7 @@ def test_top_level_builder_matches_a_literal_python_transcription(scene_name):
     tree = s.bvh_arrays(-1)
     assert_tree_equal(b, tree, scene_name)
     assert b.sorts == tree["sort_fallbacks"]
+    assert all(n <= 16 for n in b.sort_sizes), "a scene reached the long-range introsort: transcribe it too"
+    if scene_name in ("cornell", "volume_grid_test"):
+        assert b.sorts > 0  # these two scenes do reach Array.Sort (identical centroids along every axis with extent)
     s.close()
