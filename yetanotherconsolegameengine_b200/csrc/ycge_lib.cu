@@ -484,7 +484,11 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
         tp.diffuse_bounces = c->P.diffuse_bounces; tp.max_mirror_bounces = c->P.max_mirror_bounces; tp.max_refractions = c->P.max_refractions;
         tp.mirror_threshold = c->P.mirror_threshold; tp.eps = c->P.eps; tp.sigma_rad = c->P.diffuse_sigma_deg * (3.14159274f / 180.0f); // :460
         tp.seed_salt = c->P.seed_salt;
-        if (c->trace_variant == 1) { // ray stream: persistent warps, as many CTAs as fit the GPU at once
+        // Frames in flight on this GPU: the thread-per-path form, whose CTAs come and go, shares the SMs better with the resident
+        // wavefront kernels of the previous frames than the persistent ray-stream form does (measured, 3 slots: 300 against 284
+        // frames/s); a frame that has the GPU to itself takes the ray-stream form (1.09 against 1.18 ms).  Same results either way.
+        const int variant = c->pipelined ? 0 : c->trace_variant;
+        if (variant == 1) { // ray stream: persistent warps, as many CTAs as fit the GPU at once
             if (c->stream_ctas <= 0) {
                 int occ = 0, occ_s = 0;
                 cudaDeviceProp prop;
