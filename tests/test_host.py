@@ -374,3 +374,38 @@ def test_voxel_palette_matches_the_reference_source():
         assert (f32(m.specular), f32(m.reflectivity), list(m.emission), f32(m.transparency)) == (gold["specular"], gold["reflectivity"], [0.0, 0.0, 0.0], 0.0), key
     assert [f32(x) for x in lookup(999, 0).albedo] == gold["default"]
     s.close()
+
+
+def test_world_file_cells_land_in_the_chunk_grids_at_the_reference_addresses(tmp_path):
+    """A VG01 file with a pattern that identifies every cell, written by an independent struct writer in the reader's loop order
+    (WorldManager.cs:420-437: x outermost, z innermost, (mat, meta) int32 pairs).  Every voxel of every 32^3 chunk grid the mirror
+    builds from it must sit where VolumeGrid.IndexOf puts it (VolumeGrid.cs:235-252: 8^3 bricks, brick index ((bz*nby)+by)*nbx+bx,
+    Morton order x0 y0 z0 x1 y1 z1 x2 y2 z2 inside a brick) -- computed here with vectorised integer arithmetic, not by the mirror."""
+    n = 64
+    ix, iy, iz = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    mat = ((ix * 7 + iy * 13 + iz * 29) % 11 + 1).astype(np.int32)          # block ids 1..11, never air: every cell is checked
+    mat[(ix + iy + iz) % 5 == 0] = 0                                          # ... except a lattice of air cells
+    meta = ((ix + 2 * iy + 3 * iz) % 3).astype(np.int32)
+    path = str(tmp_path / "pattern.vg01")
+    with open(path, "wb") as f:
+        f.write(b"VG01" + np.array([n, n, n], np.int32).tobytes())
+        f.write(np.stack([mat, meta], -1).astype("<i4").tobytes())           # C order of [x][y][z][2] == the reader's loop order
+    s = api.HostScene("voxel_world_file:" + path)
+    assert s.n_volumes == 8                                                   # 2 x 2 x 2 chunks of 32^3
+    seen = np.zeros((n, n, n), bool)
+    world_min = np.min([list(s.volume(i).contents.min_corner) for i in range(s.n_volumes)], axis=0)
+    lx, ly, lz = np.meshgrid(np.arange(32), np.arange(32), np.arange(32), indexing="ij")
+    morton = ((lx & 1) << 0) | ((ly & 1) << 1) | ((lz & 1) << 2) | ((lx & 2) << 2) | ((ly & 2) << 3) | ((lz & 2) << 4) | ((lx & 4) << 4) | ((ly & 4) << 5) | ((lz & 4) << 6)
+    at = ((((lz >> 3) * 4) + (ly >> 3)) * 4 + (lx >> 3)) * 512 + morton       # IndexOf for a 32^3 grid: nbx = nby = 4
+    for i in range(s.n_volumes):
+        v = s.volume(i).contents
+        assert (v.nx, v.ny, v.nz) == (32, 32, 32)
+        org = np.round((np.array(list(v.min_corner)) - world_min) / np.array(list(v.voxel_size))).astype(int)  # the chunk's first cell
+        nb = 4 * 4 * 4 * 512
+        gm, ge = np.ctypeslib.as_array(v.mat, (nb,)), np.ctypeslib.as_array(v.meta, (nb,))
+        wx, wy, wz = lx + org[0], ly + org[1], lz + org[2]
+        assert np.array_equal(gm[at], mat[wx, wy, wz]) and np.array_equal(ge[at], meta[wx, wy, wz]), f"chunk {i} at cell origin {org.tolist()}"
+        assert not seen[wx, wy, wz].any()
+        seen[wx, wy, wz] = True
+    assert seen.all(), "every cell of the file belongs to exactly one chunk grid"
+    s.close()
