@@ -156,3 +156,25 @@ def test_default_params_are_the_reference_constants():
             else:
                 assert float(np.float32(got)) == want, (k, got, want)
         assert set(gold) == {f[0] for f in api.Params._fields_}, "every field of ycge_params has a reference constant behind it"
+
+
+def test_csharp_binding_declares_only_exported_entry_points_with_matching_layouts():
+    """host_cs/CudaRaytraceRenderer.cs cannot be compiled here (no .NET toolchain), so it is checked as text: every [DllImport]
+    extern is an exported symbol of libycge.so with the same number of parameters as the header's declaration, and the struct
+    sizes its static constructor asserts are the C ABI's."""
+    import ctypes as C
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cs = open(os.path.join(root, "yetanotherconsolegameengine_b200", "host_cs", "CudaRaytraceRenderer.cs"), encoding="utf-8").read()
+    hdr = open(os.path.join(root, "include", "ycge.h")).read()
+    externs = re.findall(r"\[DllImport\(Lib\)\]\s*private static extern \w+ (ycge_\w+)\(([^)]*)\);", cs)
+    assert len(externs) >= 15
+    n_params = lambda text: 0 if text.strip() in ("", "void") else text.count(",") + 1
+    for name, params in externs:
+        assert name in api.ABI_SYMBOLS, f"{name} is not exported"
+        m = re.search(r"YCGE_API[^;]*?\b" + name + r"\s*\(([^;]*?)\)\s*;", hdr, re.S)
+        assert m, name
+        assert n_params(params) == n_params(m.group(1)), (name, params, m.group(1))
+    sizes = dict(re.findall(r"Marshal\.SizeOf<(\w+)>\(\) != (\d+)", cs))
+    assert sizes == {"YMaterial": str(C.sizeof(api.Material)), "YObject": str(C.sizeof(api.Object)), "YCell": str(api.CELL_DTYPE.itemsize)}
