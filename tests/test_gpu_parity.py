@@ -159,6 +159,44 @@ def test_trace_kernel_forms_are_bit_identical(scene, fb_w, fb_h, ss, pose):
     s.close()
 
 
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss", [("test", 8, 3, 2), ("knot:12x5", 8, 3, 2), ("volume_grid_test", 8, 3, 2)])
+def test_gpu_trace_matches_the_literal_python_transcription(scene, fb_w, fb_h, ss):
+    """The CUDA trace stage against the numpy transcription of the C# source (tests/test_oracle_trace_literal.py) directly, without
+    the C++ oracle in between: radiance, G-buffer, sky flag, primary ids and the ray count of every pixel, bit for bit."""
+    from test_oracle_trace_literal import F, LiteralTracer, Rng, frac, per_frame_seed, v3
+    from oracle_binding import load_oracle
+    lib = load_oracle()  # only ycge_detmath.h's sin / cos / tan / pow behind yo_math
+    lib.yo_set_math_mode(0)
+    s = api.HostScene(scene)
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    lt = LiteralTracer(s, lib)
+    pos, yaw, pitch, fov = s.default_camera()
+    if scene.startswith("knot"):
+        pos, yaw, pitch = api.BENCH_POSE
+        r.SetCamera(pos, yaw, pitch)
+    cam, yaw, pitch, fov = v3(*pos), F(yaw), F(pitch), F(fov)
+    w, h = fb_w * ss, fb_h * 2 * ss
+    aspect = F(F(w) / F(h))
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for frame in (1, 2):
+            r.TryFlipAndBlit()
+            hdr, als, nd, prim = r.debug_read(api.DBG_HDR), r.debug_read(api.DBG_ALBEDO_SKY), r.debug_read(api.DBG_NORMAL_DEPTH), r.debug_read(api.DBG_PRIM_ID)
+            frame_idx = frame & 0x7FFFFFFF
+            jrx, jry = frac(F(F(frame_idx + 1) * F(0.61803398875))), frac(F(F(frame_idx + 1) * F(0.38196601125)))
+            lt.rays = 0
+            for py in range(h):
+                for px in range(w):
+                    ro, rd = lt.make_ray(cam, yaw, pitch, fov, aspect, px, py, w, h, jrx, jry, frame_idx)
+                    rad, is_sky, g = lt.trace_full(ro, rd, Rng(per_frame_seed(px, py, frame)))
+                    where = (scene, frame, px, py)
+                    assert np.array_equal(rad.view(np.uint32), hdr[py, px, :3].view(np.uint32)), where + ("radiance",)
+                    assert bool(als[py, px, 3]) == is_sky and np.array_equal(g["albedo"].view(np.uint32), als[py, px, :3].view(np.uint32)), where + ("albedo / sky",)
+                    assert F(g["depth"]).view(np.uint32) == nd[py, px, 3].view(np.uint32) and (g["obj"], g["sub"]) == tuple(prim[py, px]), where + ("depth / ids",)
+            assert lt.rays == r.stats()["rays"], (scene, frame, "Scene.Hit invocations")
+    r.close()
+    s.close()
+
+
 def test_library_builds_the_same_trees_as_the_host():
     """ycge_scene_upload without a host tree / ycge_mesh_upload_triangles: the library's own builder (BVH.cs:258-459,
     MeshBVH.cs:371-576) must give the same frame as the host's uploaded trees."""
