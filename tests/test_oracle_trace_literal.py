@@ -805,3 +805,41 @@ def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb
         assert saw_mirror, "the mirror sphere must be in view, or the mirror branch is not exercised"
     o.close()
     scene.close()
+
+
+@pytest.mark.parametrize("scene_name", ["cornell", "cylinders_disks_triangles", "volume_grid_test", "texture_gallery"])
+def test_trace_stage_matches_the_transcription_from_random_poses(scene_name):
+    """The same comparison from camera poses drawn at random (seeded): inside and outside the geometry, looking up, down and along
+    surfaces, so that grazing hits, back faces, the inside of boxes, misses of every slab and total internal reflection occur."""
+    lib = load_oracle()
+    lib.yo_set_math_mode(0)
+    scene = api.HostScene(scene_name)
+    fb_w, fb_h, ss = 6, 3, 1
+    o = Oracle(scene, fb_w, fb_h, ss)
+    lt = LiteralTracer(scene, lib)
+    w, h = fb_w * ss, fb_h * 2 * ss
+    aspect = F(F(w) / F(h))
+    rng = np.random.default_rng(len(scene_name) * 7919)
+    frame = 0
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for _ in range(5):
+            pos = (float(rng.uniform(-2.5, 2.5)), float(rng.uniform(0.05, 3.0)), float(rng.uniform(-5.0, 1.0)))
+            yaw, pitch = float(F(rng.uniform(-3.1, 3.1))), float(F(rng.uniform(-1.2, 1.2)))
+            o.set_camera(pos, yaw, pitch)
+            o.render_frame(threads=2)
+            frame += 1
+            hdr, als, nd, prim = o.debug_read(api.DBG_HDR), o.debug_read(api.DBG_ALBEDO_SKY), o.debug_read(api.DBG_NORMAL_DEPTH), o.debug_read(api.DBG_PRIM_ID)
+            frame_idx = frame & 0x7FFFFFFF
+            jrx, jry = frac(F(F(frame_idx + 1) * F(0.61803398875))), frac(F(F(frame_idx + 1) * F(0.38196601125)))
+            lt.rays = 0
+            for py in range(h):
+                for px in range(w):
+                    ro, rd = lt.make_ray(v3(*pos), F(yaw), F(pitch), F(45.0), aspect, px, py, w, h, jrx, jry, frame_idx)
+                    rad, is_sky, g = lt.trace_full(ro, rd, Rng(per_frame_seed(px, py, frame)))
+                    where = (scene_name, pos, yaw, pitch, px, py)
+                    assert np.array_equal(rad.view(np.uint32), hdr[py, px, :3].view(np.uint32)), where + ("radiance",)
+                    assert bool(als[py, px, 3]) == is_sky and (g["obj"], g["sub"]) == tuple(prim[py, px]), where + ("sky / ids",)
+                    assert F(g["depth"]).view(np.uint32) == nd[py, px, 3].view(np.uint32), where + ("depth",)
+            assert lt.rays == o.stats()["rays"], (scene_name, pos, "Scene.Hit invocations")
+    o.close()
+    scene.close()
