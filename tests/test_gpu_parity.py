@@ -432,6 +432,39 @@ def test_texture_upload_through_the_c_abi_and_errors():
     s.close()
 
 
+def test_non_default_params_through_the_config_struct():
+    """ycge_params carries the reference's compile-time constants (RaytraceRenderer.cs:31-43,:65,:222; ToneMapper.cs:8-21) as data.
+    Other values must act the same on both sides: the mirror threshold lowered so that the 0.6 / 0.85 spheres really mirror, four
+    mirror bounces (BASELINE config 2 as its text describes it -- not reachable with the reference's constants, hence no parity
+    claim against the engine, only GPU = oracle), two diffuse bounces, two à-trous iterations, another TAA alpha and exposure."""
+    lib = api.load_lib()
+    s = api.HostScene("mirror_spheres")
+    cfg = api.Config()
+    cfg.fb_w, cfg.fb_h, cfg.ss = 40, 12, 2
+    lib.ycge_default_params(C.byref(cfg.params))
+    P = cfg.params
+    P.mirror_threshold, P.max_mirror_bounces, P.diffuse_bounces, P.atrous_iterations = 0.5, 4, 2, 2
+    P.taa_alpha, P.ae_key, P.ae_speed, P.saturation, P.tone_gamma, P.diffuse_sigma_deg = 0.2, 0.25, 0.5, 1.3, 2.0, 10.0
+    ctx = C.c_void_p()
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == 0
+    assert lib.ycge_scene_upload(ctx, s.flat) == 0
+    o = Oracle(s, 40, 12, 2, params=P)
+    d = Oracle(s, 40, 12, 2)
+    for f in range(3):
+        g = np.empty((12, 40), api.CELL_DTYPE)
+        assert lib.ycge_render_frame(ctx, g.ctypes.data, 0) == 0
+        c = o.render_frame(threads=4)
+        assert_cells_equal(g, c, f"non-default params, frame {f + 1}")
+        ref_default = d.render_frame(threads=4)
+    st = api.Stats()
+    assert lib.ycge_get_stats(ctx, C.byref(st)) == 0
+    assert st.rays == o.stats()["rays"] and st.rays > d.stats()["rays"], "more bounces trace more rays"
+    assert np.float32(st.ae_exposure).view(np.uint32) == np.float32(o.stats()["ae_exposure"]).view(np.uint32)
+    assert (g["fg_ansi"] != ref_default["fg_ansi"]).any(), "the parameters must change the picture"
+    lib.ycge_destroy(ctx)
+    o.close(); d.close(); s.close()
+
+
 def test_errors_are_loud():
     lib = api.load_lib()
     cfg = api.Config()
