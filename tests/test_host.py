@@ -152,6 +152,29 @@ def test_vg01_world_file_round_trip(tmp_path):
         api.HostScene("voxel_world_file:" + str(tmp_path / "missing.vg01"))
 
 
+def test_island_world_scene_equals_its_world_file(tmp_path):
+    """BuildMinecraftLike (VolumeScenes.cs:604-616) generates the island world, saves it and loads the file back: the mirror's
+    in-memory route (voxel_island) must give the chunk grids, tree and camera of its own file loaded through the VG01 reader."""
+    path = str(tmp_path / "island.vg")
+    assert api.load_host().ycgeh_write_island_world(path.encode(), 64, 128) == 0
+    a = api.HostScene("voxel_island:64x128")
+    b = api.HostScene("voxel_world_file:" + path)
+    assert a.name == "voxel_island" and a.n_volumes == b.n_volumes and 8 <= a.n_volumes <= 16
+    for i in range(a.n_volumes):
+        va, vb = a.volume(i).contents, b.volume(i).contents
+        assert list(va.min_corner) == list(vb.min_corner)
+        n = 4 * 4 * 4 * 512
+        assert np.array_equal(np.ctypeslib.as_array(va.mat, (n,)), np.ctypeslib.as_array(vb.mat, (n,)))
+        assert np.array_equal(np.ctypeslib.as_array(va.meta, (n,)), np.ctypeslib.as_array(vb.meta, (n,)))
+    ta, tb = a.bvh_arrays(-1), b.bvh_arrays(-1)
+    for k in ("boxes", "lrsc", "leaf"):
+        assert np.array_equal(ta[k], tb[k])
+    assert a.default_camera() == b.default_camera()
+    a.close(); b.close()
+    with pytest.raises(Exception, match="multiples of 32"):
+        api.HostScene("voxel_island:48x64")
+
+
 def test_texture_test_scene_and_png_decoder(tmp_path):
     """BuildTextureTestScene (Scenes.cs:337-358): one textured box, ambient 0.5, no lights.  new Texture(path) decodes through
     OpenCV in the reference (ImreadModes.Color, BGR2RGBA: Texture.cs:25-49); the mirror's zlib-only PNG decoder must give the

@@ -246,6 +246,10 @@ def load_host() -> C.CDLL:
         h.ycgeh_synthetic_height.argtypes = [C.c_int, C.c_int, C.c_int]
         h.ycgeh_synthetic_height.restype = C.c_float
         h.ycgeh_write_synthetic_world.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        h.ycgeh_write_island_world.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        h.ycgeh_island_height.argtypes = [C.c_int] * 5
+        h.ycgeh_gradient_noise2d.argtypes = [C.c_float, C.c_float, C.c_int]
+        h.ycgeh_gradient_noise2d.restype = C.c_float
         _host = h
     return _host
 

@@ -2,6 +2,7 @@
 #include "ycge_host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,7 @@
 #include <map>
 #include <set>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <zlib.h>
@@ -727,6 +729,383 @@ std::shared_ptr<Scene> BuildDragonScene() { // :135-143; Sapphire = Scale(Blue, 
 }
 } // namespace MeshScenes
 
+// ---- the island generator the reference pre-generates its voxel world with -------------------------------------------
+// WorldManager.GenerateAndSaveWorld (Scenes/WorldGeneration/WorldManager.cs:510-631) restated: global heights, the D8 "river"
+// pass, slope / biome / inland water, strata fill, global flora.  All arithmetic is binary32 in the reference's operation
+// order (the build uses -ffp-contract=off).  One libm dependence: MathF.Pow(nMount, 1.35f) (TerrainNoise.cs:76) is powf here.
+namespace WorldGeneration {
+enum Block { Air = 0, Stone = 1, Dirt = 2, Grass = 3, Water = 4, Sand = 5, Wood = 6, Leaves = 7, Snow = 8, TallGrass = 10 }; // WorldGenSettings.cs:10-21
+enum Biome { Ocean, Beach, Lakes, Plains, Forest, Desert, Taiga, Alpine, SnowBiome };                                        // Biome.cs:3-14
+struct Config { // WorldConfig.cs:19-33
+    int WorldWidth, WorldHeight, WorldDepth, WorldSeed, WaterLevel, SnowLevel;
+    Config(int w, int h, int d, int seed) : WorldWidth(w), WorldHeight(h), WorldDepth(d), WorldSeed(seed), WaterLevel(std::max(1, h / 4)), SnowLevel((int)(h * 0.8f)) {}
+};
+namespace Island { // IslandSettings.cs:5-55
+const float IslandRadius = 10000.0f, MaskFadeFraction = 0.18f, MaxRiseFraction = 0.45f;
+const int SeaFloorDepth = 12, BeachBuffer = 2, DirtDepth = 3;
+const float CoastJitterFreq = 0.00022f, CoastJitterAmp = 600.0f;
+const float Warp1Freq = 0.00025f, Warp1Amp = 350.0f, Warp2Freq = 0.0012f, Warp2Amp = 90.0f;
+const float ContinentFreq = 0.00045f, MountainFreq = 0.0011f, Detail1Freq = 0.0025f, Detail2Freq = 0.0060f;
+const int ContinentOctaves = 6, MountainOctaves = 5, Detail1Octaves = 6, Detail2Octaves = 5;
+const float LakeFreq1 = 0.0008f, LakeFreq2 = 0.0016f, LakeRiseMax = 60.0f, LakeBaseAboveSea = 8.0f, LakeSlopeMax = 0.60f, LakeMaskThreshold = 0.05f, LakeMinDepth = 1.0f;
+const float RiverAccumThreshold = 50.0f, RiverMaxCarve = 3.5f, RiverWaterDepth = 2.0f, RiverBankSand = 1.5f;
+} // namespace Island
+
+// GenMath.cs:53-186
+static int FastHash(int x, int y, int z, int seed) {
+    uint32_t h = 2166136261u ^ (uint32_t)seed;
+    h ^= (uint32_t)x; h *= 16777619u;
+    h ^= (uint32_t)y; h *= 16777619u;
+    h ^= (uint32_t)z; h *= 16777619u;
+    return (int)h;
+}
+static int FastFloor(float t) { return t >= 0.0f ? (int)t : (int)t - 1; } // :110 (a negative whole number floors one too low, as there)
+static float Fade(float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); }
+static float Lerp(float a, float b, float t) { return a + (b - a) * t; }
+static float Saturate(float x) { if (x < 0.0f) return 0.0f; if (x > 1.0f) return 1.0f; return x; }
+static float SmoothStep(float e0, float e1, float x) { float t = Saturate((x - e0) / (e1 - e0)); return t * t * (3.0f - 2.0f * t); }
+static float GradDot2(int ix, int iz, int seed, float x, float z) { // Grad2 :114-128 and Dot :153
+    static const float R = 0.70710678118f;
+    static const float G[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {R, R}, {-R, R}, {R, -R}, {-R, -R}};
+    const float *g = G[(FastHash(ix, 0, iz, seed) >> 13) & 7]; // an arithmetic shift of the signed hash, then & 7
+    return g[0] * x + g[1] * z;
+}
+float GradientNoise2D(float x, float z, int seed) { // :53-71
+    int x0 = FastFloor(x), z0 = FastFloor(z), x1 = x0 + 1, z1 = z0 + 1;
+    float tx = x - (float)x0, tz = z - (float)z0;
+    float u = Fade(tx), v = Fade(tz);
+    float n00 = GradDot2(x0, z0, seed, tx, tz);
+    float n10 = GradDot2(x1, z0, seed, tx - 1.0f, tz);
+    float n01 = GradDot2(x0, z1, seed, tx, tz - 1.0f);
+    float n11 = GradDot2(x1, z1, seed, tx - 1.0f, tz - 1.0f);
+    float val = Lerp(Lerp(n00, n10, u), Lerp(n01, n11, u), v) * 1.41421356237f;
+    if (val < -1.0f) return -1.0f;
+    if (val > 1.0f) return 1.0f;
+    return val;
+}
+float FBM2D(float x, float z, int octaves, float lacunarity, float gain, float baseFreq, int seed) { // :8-19
+    float sum = 0.0f, amp = 1.0f, freq = baseFreq;
+    for (int i = 0; i < octaves; i++) {
+        float n = GradientNoise2D(x * freq, z * freq, seed + i * 131);
+        sum += n * amp; freq *= lacunarity; amp *= gain;
+    }
+    return 0.5f * sum + 0.5f;
+}
+float RidgedFBM2D(float x, float z, int octaves, float lacunarity, float gain, float baseFreq, int seed) { // :21-37
+    float sum = 0.0f, amp = 0.5f, freq = baseFreq, weight = 1.0f;
+    for (int i = 0; i < octaves; i++) {
+        float n = GradientNoise2D(x * freq, z * freq, seed + i * 733);
+        n = 1.0f - std::fabs(n); n *= n; n *= weight;
+        weight = n * gain; if (weight > 1.0f) weight = 1.0f;
+        sum += n * amp; freq *= lacunarity; amp *= 0.5f;
+    }
+    return sum;
+}
+
+// TerrainNoise.cs
+static void Warp(float &x, float &z, int seed) { // :24-39
+    using namespace Island;
+    float wx1 = FBM2D(x * Warp1Freq, z * Warp1Freq, 4, 2.0f, 0.5f, 1.0f, seed + 101);
+    float wz1 = FBM2D((x + 137.0f) * Warp1Freq, (z - 271.0f) * Warp1Freq, 4, 2.0f, 0.5f, 1.0f, seed + 103);
+    wx1 = (wx1 - 0.5f) * 2.0f; wz1 = (wz1 - 0.5f) * 2.0f;
+    x += wx1 * Warp1Amp; z += wz1 * Warp1Amp;
+    float wx2 = FBM2D(x * Warp2Freq, z * Warp2Freq, 3, 2.0f, 0.5f, 1.0f, seed + 151);
+    float wz2 = FBM2D((x - 911.0f) * Warp2Freq, (z + 643.0f) * Warp2Freq, 3, 2.0f, 0.5f, 1.0f, seed + 157);
+    wx2 = (wx2 - 0.5f) * 2.0f; wz2 = (wz2 - 0.5f) * 2.0f;
+    x += wx2 * Warp2Amp; z += wz2 * Warp2Amp;
+}
+static float ShoreMask(float x, float z, int seed) { // the shared part of IslandMask01 :13-21 and Height01 :48-53, on warped x, z
+    using namespace Island;
+    float dist = std::sqrt(x * x + z * z);
+    float coastJitter = (FBM2D(x * CoastJitterFreq, z * CoastJitterFreq, 3, 2.0f, 0.5f, 1.0f, seed + 333) - 0.5f) * 2.0f * CoastJitterAmp;
+    dist = std::max(0.0f, dist - coastJitter);
+    float fadeW = std::max(8.0f, IslandRadius * MaskFadeFraction);
+    float edgeStart = IslandRadius - fadeW;
+    return 1.0f - SmoothStep(edgeStart, IslandRadius, dist);
+}
+float IslandMask01(float gx, float gz, const Config &cfg) { float x = gx, z = gz; Warp(x, z, cfg.WorldSeed); return ShoreMask(x, z, cfg.WorldSeed); }
+float Height01(float gx, float gz, const Config &cfg) { // :42-103 (TerraceStep is 0: the terrace branch is never taken)
+    using namespace Island;
+    float x = gx, z = gz;
+    Warp(x, z, cfg.WorldSeed);
+    float mask = ShoreMask(x, z, cfg.WorldSeed);
+    int seed = cfg.WorldSeed;
+    float nCont = RidgedFBM2D(x * ContinentFreq, z * ContinentFreq, ContinentOctaves, 2.0f, 0.5f, 1.0f, seed + 1001);
+    float nMount = RidgedFBM2D(x * MountainFreq, z * MountainFreq, MountainOctaves, 2.0f, 0.5f, 1.0f, seed + 1003);
+    float d1 = FBM2D(x * Detail1Freq, z * Detail1Freq, Detail1Octaves, 2.0f, 0.5f, 1.0f, seed + 1005);
+    float d2 = FBM2D(x * Detail2Freq, z * Detail2Freq, Detail2Octaves, 2.0f, 0.5f, 1.0f, seed + 1006);
+    float mountainMask = Saturate((nCont * 1.15f + nMount * 1.10f) - 0.90f);
+    float plains = d1 * 0.65f + d2 * 0.35f;
+    float mountains = powf(nMount, 1.35f);
+    float h01 = Lerp(plains, mountains, mountainMask);
+    float centerDist = std::sqrt(x * x + z * z);
+    float centerFlatten = Saturate(centerDist / (IslandRadius * 0.55f));
+    h01 *= Lerp(0.55f, 1.00f, centerFlatten);
+    h01 = std::min(h01, mask);
+    return Saturate(h01);
+}
+int HeightY(int gx, int gz, const Config &cfg) { // :105-133
+    using namespace Island;
+    int sea = cfg.WaterLevel;
+    int oceanFloor = std::max(1, sea - SeaFloorDepth);
+    float h01 = Height01((float)gx, (float)gz, cfg);
+    float maxRise = (float)cfg.WorldHeight * MaxRiseFraction;
+    int h = (int)std::nearbyint((float)sea + h01 * maxRise); // MathF.Round: ties to even
+    float dx = (float)gx, dz = (float)gz;
+    float radial = Saturate(1.0f - std::sqrt(dx * dx + dz * dz) / IslandRadius);
+    if (radial <= 0.0005f) {
+        float bed = FBM2D((float)gx * 0.0015f, (float)gz * 0.0015f, 3, 2.0f, 0.5f, 1.0f, cfg.WorldSeed + 1303);
+        h = oceanFloor + (int)std::nearbyint((bed - 0.5f) * 6.0f);
+    } else h = std::max(h, oceanFloor);
+    if (h < 0) h = 0;
+    if (h >= cfg.WorldHeight) h = cfg.WorldHeight - 1;
+    return h;
+}
+int LocalWaterY(int gx, int gz, const Config &cfg, int groundY, float slope01) { // :136-161
+    using namespace Island;
+    int sea = cfg.WaterLevel;
+    if (IslandMask01((float)gx, (float)gz, cfg) < LakeMaskThreshold) return sea;
+    int seed = cfg.WorldSeed;
+    float n1 = FBM2D((float)gx * LakeFreq1, (float)gz * LakeFreq1, 5, 2.0f, 0.5f, 1.0f, seed + 8101);
+    float n2 = FBM2D((float)gx * LakeFreq2, (float)gz * LakeFreq2, 4, 2.0f, 0.5f, 1.0f, seed + 8107);
+    float lakeField = 0.65f * n1 + 0.35f * n2;
+    float lowlandBias = Saturate(1.0f - (float)(groundY - sea) / std::max(1.0f, (float)(cfg.SnowLevel - sea)));
+    float candidate = (float)sea + LakeBaseAboveSea + (lakeField * 0.75f + lowlandBias * 0.25f) * LakeRiseMax;
+    if (slope01 <= LakeSlopeMax && (float)groundY + LakeMinDepth < candidate) {
+        int wy = (int)std::floor(candidate);
+        if (wy > sea) return wy;
+    }
+    return sea;
+}
+Biome EvaluateBiome(int gx, int gz, int heightY, int sea, const Config &cfg) { // BiomeMap.cs:7-21
+    if (heightY <= sea - 1) return Ocean;
+    if (std::abs(heightY - sea) <= Island::BeachBuffer) return Beach;
+    int seed = cfg.WorldSeed;
+    float m1 = FBM2D((float)gx * 0.0025f, (float)gz * 0.0025f, 5, 2.0f, 0.5f, 1.0f, seed + 5002);
+    float d1 = RidgedFBM2D((float)gx * 0.0020f, (float)gz * 0.0020f, 4, 2.0f, 0.5f, 1.0f, seed + 5003);
+    float dryness = 0.55f * d1 + 0.45f * (1.0f - m1);
+    return dryness > 0.52f ? Desert : Forest;
+}
+static int ChooseSurfaceBlock(Biome biome, int heightY, int sea, int snow, float slope01) { // Layering.cs:7-28
+    if (heightY >= snow) return Snow;
+    if (std::abs(heightY - sea) <= Island::BeachBuffer) return Sand;
+    if (slope01 > 0.80f) return Stone;
+    if (biome == Desert) return Sand;
+    if (biome == Alpine) return slope01 > 0.60f ? Stone : Grass;
+    return Grass;
+}
+static int ChooseSubsurfaceBlock(Biome biome, int gy, int groundY, int sea) { // Layering.cs:30-45 (UnderwaterSandBuffer = 1)
+    if (groundY <= sea + 1) return Sand;
+    if (biome == Desert) return Sand;
+    return groundY - gy <= Island::DirtDepth ? Dirt : Stone;
+}
+static uint32_t FloraHash(int x, int z, int seed) { // FloraPlacer.cs:7-16
+    uint32_t h = (uint32_t)FastHash(x, 0, z, seed);
+    h ^= h << 13; h ^= h >> 17; h ^= h << 5;
+    return h;
+}
+
+// The generated world: one byte per voxel, block id in the low nibble and meta above it, [x][y][z] like the world file.
+struct World {
+    int nx, ny, nz;
+    std::vector<int> ground, localWater;
+    std::vector<uint8_t> biome;
+    std::vector<float> slope01;
+    std::vector<uint8_t> cells;
+    size_t at(int x, int y, int z) const { return ((size_t)x * ny + y) * nz + z; }
+    int id(int x, int y, int z) const { return cells[at(x, y, z)] & 15; }
+    void set(int x, int y, int z, int id, int meta) { cells[at(x, y, z)] = (uint8_t)(id | (meta << 4)); }
+};
+
+// RiverNetworkGlobal.Compute (RiverNetworkGlobal.cs:7-84).  Cells are visited in ascending height and each adds its current
+// accumulation (or 1 when it has none) to its steepest strictly-lower neighbour.  That neighbour was visited earlier, and
+// whatever flows into a cell arrives after the cell itself was visited, so every cell forwards exactly 1 and a cell's total is
+// the number of neighbours draining into it (at most 8, far below RiverAccumThreshold = 50): the outcome does not depend on
+// how Array.Sort orders equal heights, and with the shipped constants nothing is ever carved.  Restated in full anyway, with a
+// counting sort standing in for Array.Sort.
+static void RiverNetwork(int nx, int nz, const Config &cfg, const std::vector<int> &ground, std::vector<float> &carveDepth, std::vector<int> &riverWaterY) {
+    using namespace Island;
+    const int sea = cfg.WaterLevel;
+    auto G = [&](int x, int z) { return ground[(size_t)x * nz + z]; };
+    std::vector<int8_t> dirX((size_t)nx * nz), dirZ((size_t)nx * nz);
+    for (int x = 0; x < nx; x++) for (int z = 0; z < nz; z++) {
+        int h0 = G(x, z), bestDrop = 0; int8_t bx = 0, bz = 0;
+        for (int oz = -1; oz <= 1; oz++) for (int ox = -1; ox <= 1; ox++) {
+            if (ox == 0 && oz == 0) continue;
+            int x2 = x + ox, z2 = z + oz;
+            if (x2 < 0 || x2 >= nx || z2 < 0 || z2 >= nz) continue;
+            int drop = h0 - G(x2, z2);
+            if (drop > bestDrop) { bestDrop = drop; bx = (int8_t)ox; bz = (int8_t)oz; }
+        }
+        dirX[(size_t)x * nz + z] = bx; dirZ[(size_t)x * nz + z] = bz;
+    }
+    std::vector<uint32_t> start((size_t)cfg.WorldHeight + 1, 0), order((size_t)nx * nz);
+    for (int h : ground) start[(size_t)h + 1]++;
+    for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+    for (uint32_t k = 0; k < (uint32_t)ground.size(); k++) order[start[(size_t)ground[k]]++] = k;
+    std::vector<float> accum((size_t)nx * nz, 0.0f);
+    for (uint32_t k : order) {
+        float a = accum[k];
+        if (a <= 0) a = 1.0f;
+        if (dirX[k] != 0 || dirZ[k] != 0) {
+            int x2 = (int)(k / (uint32_t)nz) + dirX[k], z2 = (int)(k % (uint32_t)nz) + dirZ[k];
+            if (x2 >= 0 && x2 < nx && z2 >= 0 && z2 < nz) accum[(size_t)x2 * nz + z2] += a;
+        }
+    }
+    carveDepth.assign((size_t)nx * nz, 0.0f); riverWaterY.assign((size_t)nx * nz, sea);
+    for (size_t k = 0; k < accum.size(); k++) {
+        float t = (accum[k] - RiverAccumThreshold) / RiverAccumThreshold;
+        if (t <= 0) continue;
+        float carve = std::min(RiverMaxCarve, std::max(0.0f, t) * RiverMaxCarve);
+        carveDepth[k] = carve;
+        int bedY = ground[k] - (int)std::floor(carve);
+        riverWaterY[k] = std::max(sea, bedY + (int)std::ceil(RiverWaterDepth));
+    }
+}
+
+// FloraPlacer.PlaceTreesGlobal (FloraPlacer.cs:139-253): trees in Forest columns, then cacti and rock piles in Desert ones.
+static void PlaceFlora(const Config &cfg, World &w) {
+    const int nx = w.nx, ny = w.ny, nz = w.nz, snow = cfg.SnowLevel;
+    auto open = [&](int x, int y, int z) { int b = w.id(x, y, z); return b == Air || b == TallGrass; };
+    for (int gx = 0; gx < nx; gx++) {
+        for (int gz = 0; gz < nz; gz++) {
+            const size_t c = (size_t)gx * nz + gz;
+            int gY = w.ground[c], wY = w.localWater[c];
+            Biome b = (Biome)w.biome[c];
+            if (gY <= wY || gY >= snow - 2) continue;
+            if (b != Forest) continue; // density 0.03 in Forest, none elsewhere
+            uint32_t h = FloraHash(gx, gz, cfg.WorldSeed + 90001);
+            float r = (float)(h & 0xFFFF) / 65535.0f;
+            if (r > 0.03f) continue;
+            bool conifer = (b == Taiga) || ((h >> 16 & 3) == 0);
+            int trunkBase = gY + 1;
+            int trunkH = conifer ? 6 + (int)(h >> 2 & 7) : 4 + (int)(h >> 3 & 5);
+            int canopyR = conifer ? 2 : 2 + (int)(h >> 6 & 1);
+            if (trunkBase + trunkH + 2 >= ny) trunkH = std::max(3, ny - trunkBase - 2);
+            for (int t = 0; t < trunkH; t++) {
+                int y = trunkBase + t; if (y < 0 || y >= ny) break;
+                if (open(gx, y, gz)) w.set(gx, y, gz, Wood, 0);
+            }
+            int canopyBase = trunkBase + trunkH - (conifer ? 2 : 1);
+            bool anyLeaves = false;
+            for (int dy = -(conifer ? 0 : 1); dy <= 2; dy++) {
+                int y = canopyBase + dy; if (y < 0 || y >= ny) continue;
+                int radius = conifer ? std::max(1, canopyR - std::abs(dy)) : canopyR - (dy == 2 ? 1 : 0);
+                for (int rx = -radius; rx <= radius; rx++) {
+                    int x2 = gx + rx; if (x2 < 0 || x2 >= nx) continue;
+                    for (int rz = -radius; rz <= radius; rz++) {
+                        int z2 = gz + rz; if (z2 < 0 || z2 >= nz) continue;
+                        if (open(x2, y, z2)) { w.set(x2, y, z2, Leaves, 0); anyLeaves = true; }
+                    }
+                }
+            }
+            if (!anyLeaves) {
+                int y = trunkBase + trunkH - 1;
+                if (y >= 0 && y < ny)
+                    for (int rx = -1; rx <= 1; rx++) {
+                        int x2 = gx + rx; if (x2 < 0 || x2 >= nx) continue;
+                        for (int rz = -1; rz <= 1; rz++) {
+                            int z2 = gz + rz; if (z2 < 0 || z2 >= nz) continue;
+                            if (w.id(x2, y, z2) == Air) w.set(x2, y, z2, Leaves, 0);
+                        }
+                    }
+            }
+        }
+        for (int gz = 0; gz < nz; gz++) { // desert props of this x, after its trees (:205-250)
+            const size_t c = (size_t)gx * nz + gz;
+            if ((Biome)w.biome[c] != Desert) continue;
+            int gY = w.ground[c], wY = w.localWater[c];
+            if (gY <= wY) continue;
+            if (w.slope01[c] > 0.25f) continue;
+            const uint32_t ux = (uint32_t)gx, uz = (uint32_t)gz; // int products wrap (unchecked)
+            uint32_t h = FloraHash((int)(ux * 73856093u ^ uz * 19349663u), (int)(uz * 83492791u ^ ux * 297121507u), cfg.WorldSeed + 1234567);
+            float r = (float)(h & 0xFFFF) / 65535.0f;
+            if (r < 0.70f) continue;
+            if (r < 0.85f) { // cactus: a wood column 2..5 high
+                int height = 2 + (int)((h >> 16) & 3);
+                for (int t = 1; t <= height; t++) {
+                    int y = gY + t; if (y >= ny) break;
+                    if (w.id(gx, y, gz) == Air) w.set(gx, y, gz, Wood, 0);
+                }
+            } else { // a plus-shaped pile of stone, meta 1
+                int y = gY + 1; if (y >= ny) continue;
+                for (int rx = -1; rx <= 1; rx++) {
+                    int x2 = gx + rx; if (x2 < 0 || x2 >= nx) continue;
+                    for (int rz = -1; rz <= 1; rz++) {
+                        int z2 = gz + rz; if (z2 < 0 || z2 >= nz) continue;
+                        if (std::abs(rx) + std::abs(rz) > 1) continue;
+                        if (w.id(x2, y, z2) == Air) w.set(x2, y, z2, Stone, 1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// rows of columns over the host's cores; every column is a pure function of (x, z)
+template <class F> static void ParallelRows(int nx, F f) {
+    unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> ts;
+    std::atomic<int> next{0};
+    for (unsigned t = 0; t < nt; t++) ts.emplace_back([&] { for (int x; (x = next.fetch_add(1)) < nx;) f(x); });
+    for (auto &t : ts) t.join();
+}
+
+World Generate(int nx, int ny, int nz, int seed) { // WorldManager.cs:510-606
+    Config cfg(nx, ny, nz, seed);
+    World w; w.nx = nx; w.ny = ny; w.nz = nz;
+    const size_t ncol = (size_t)nx * nz;
+    w.ground.resize(ncol); w.localWater.resize(ncol); w.biome.resize(ncol); w.slope01.resize(ncol);
+    ParallelRows(nx, [&](int x) { for (int z = 0; z < nz; z++) w.ground[(size_t)x * nz + z] = HeightY(x, z, cfg); });
+    std::vector<float> carve; std::vector<int> riverWater;
+    RiverNetwork(nx, nz, cfg, w.ground, carve, riverWater);
+    for (size_t k = 0; k < ncol; k++) w.ground[k] = std::max(0, w.ground[k] - (int)std::floor(carve[k]));
+    const int sea = cfg.WaterLevel, snow = cfg.SnowLevel;
+    auto G = [&](int x, int z) { return w.ground[(size_t)x * nz + z]; };
+    std::vector<uint8_t> rock(ncol); // StrataMap.RockMetaAt's noise class of the column: 0, 1, or 2 = "use the altitude band"
+    ParallelRows(nx, [&](int x) {
+        for (int z = 0; z < nz; z++) {
+            const size_t c = (size_t)x * nz + z;
+            int x0 = std::max(0, x - 1), x1 = std::min(nx - 1, x + 1), z0 = std::max(0, z - 1), z1 = std::min(nz - 1, z + 1);
+            float dx = (float)(G(x1, z) - G(x0, z)) * 0.5f, dz = (float)(G(x, z1) - G(x, z0)) * 0.5f;
+            float s = Saturate(std::sqrt(dx * dx + dz * dz) / 6.0f); // Normalization.SlopeNormalize
+            w.slope01[c] = s;
+            Biome b = EvaluateBiome(x, z, G(x, z), sea, cfg);
+            int lw = std::max(LocalWaterY(x, z, cfg, G(x, z), s), riverWater[c]);
+            w.localWater[c] = lw;
+            if (lw > sea && G(x, z) <= lw) b = Lakes;
+            w.biome[c] = (uint8_t)b;
+            float n = FBM2D((float)x * 0.004f, (float)z * 0.004f, 3, 2.0f, 0.5f, 1.0f, cfg.WorldSeed + 4201); // StrataMap.cs:16
+            rock[c] = n < 0.33f ? 0 : (n < 0.66f ? 1 : 2);
+        }
+    });
+    w.cells.assign(ncol * ny, 0);
+    ParallelRows(nx, [&](int x) {
+        for (int z = 0; z < nz; z++) {
+            const size_t c = (size_t)x * nz + z;
+            const int gY = w.ground[c], wY = w.localWater[c];
+            const Biome b = (Biome)w.biome[c];
+            for (int y = 0; y < ny; y++) {
+                int id, meta = 0;
+                if (y > gY) id = y <= wY ? Water : Air;
+                else if (y == gY) {
+                    if (wY > sea && (float)(wY - gY) <= (float)Island::BeachBuffer + Island::RiverBankSand) id = Sand;
+                    else id = ChooseSurfaceBlock(b, gY, sea, snow, w.slope01[c]);
+                } else if (y >= gY - 3) id = ChooseSubsurfaceBlock(b, y, gY, sea); // Terrain.DirtDepth = 3
+                else {
+                    id = Stone;
+                    if (rock[c] < 2) meta = rock[c];
+                    else { float hBand = (float)(y % 24) / 24.0f; meta = hBand < 0.33f ? 0 : (hBand < 0.66f ? 1 : 2); } // StrataMap.cs:11-12
+                }
+                w.set(x, y, z, id, meta);
+            }
+        }
+    });
+    PlaceFlora(cfg, w);
+    return w;
+}
+} // namespace WorldGeneration
+
 // ---- synthetic voxel world with the structure BuildMinecraftLike produces ---------------------------------------
 namespace VolumeScenes {
 static uint32_t hash2(int x, int z) {
@@ -862,6 +1241,24 @@ void WriteSyntheticWorldFile(const std::string &path, int worldSize, int worldHe
     }
     if (!o.good()) throw std::runtime_error("cannot write " + path);
 }
+// The reference's own world: BuildMinecraftLike (VolumeScenes.cs:569-627) generates it with seed 0 and loads it back.
+std::shared_ptr<Scene> BuildIslandWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds) {
+    WorldGeneration::World w = WorldGeneration::Generate(worldSize, worldHeight, worldSize, 0);
+    return BuildWorldFromCells(worldSize, worldHeight, worldSize, chunkSize, daySeconds, "voxel_island",
+                               [&](int wx, int wy, int wz, int &m, int &e) { uint8_t c = w.cells[w.at(wx, wy, wz)]; m = c & 15; e = c >> 4; });
+}
+void WriteIslandWorldFile(const std::string &path, int worldSize, int worldHeight) { // WorldManager.cs:612-629
+    WorldGeneration::World w = WorldGeneration::Generate(worldSize, worldHeight, worldSize, 0);
+    std::ofstream o(path, std::ios::binary);
+    int32_t dims[3] = {worldSize, worldHeight, worldSize};
+    o.write("VG01", 4); o.write((const char *)dims, 12);
+    std::vector<int32_t> row((size_t)worldSize * 2);
+    for (int x = 0; x < worldSize; x++) for (int y = 0; y < worldHeight; y++) {
+        for (int z = 0; z < worldSize; z++) { uint8_t c = w.cells[w.at(x, y, z)]; row[2 * z] = c & 15; row[2 * z + 1] = c >> 4; }
+        o.write((const char *)row.data(), (std::streamsize)(row.size() * 4));
+    }
+    if (!o.good()) throw std::runtime_error("cannot write " + path);
+}
 } // namespace VolumeScenes
 
 std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
@@ -888,6 +1285,12 @@ std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
         return VolumeScenes::BuildSyntheticWorld(ws, wh, 32, 45.0f);
     }
     if (name == "voxel_world") return VolumeScenes::BuildSyntheticWorld(1024, 256, 32, 45.0f);
+    if (name.rfind("voxel_island:", 0) == 0) { // voxel_island:<size>x<height> — the reference's generator on a smaller world
+        int ws = 0, wh = 0;
+        if (sscanf(name.c_str() + 13, "%dx%d", &ws, &wh) != 2 || ws <= 0 || wh <= 0 || ws % 32 || wh % 32) throw std::invalid_argument("voxel_island:<size>x<height>, multiples of 32");
+        return VolumeScenes::BuildIslandWorld(ws, wh, 32, 45.0f);
+    }
+    if (name == "voxel_island") return VolumeScenes::BuildIslandWorld(1024, 256, 32, 45.0f); // BuildMinecraftLike's dimensions
     if (name.rfind("snapshot:", 0) == 0) { // an 'SCNE' v1 file (SceneSyncProtocol)
         std::ifstream f(name.substr(9), std::ios::binary);
         if (!f.good()) throw std::invalid_argument("cannot open scene snapshot: " + name.substr(9));
@@ -1261,6 +1664,13 @@ YH_API int ycgeh_scene_write_snapshot(void *h, const char *path) { // SceneSyncP
         return (int)b.size();
     } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
+YH_API int ycgeh_write_island_world(const char *path, int world_size, int world_height) { // GenerateAndSaveWorld's VG01 file
+    try { VolumeScenes::WriteIslandWorldFile(path, world_size, world_height); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_island_height(int gx, int gz, int world_size, int world_height, int seed) { // TerrainNoise.HeightY
+    return WorldGeneration::HeightY(gx, gz, WorldGeneration::Config(world_size, world_height, world_size, seed));
+}
+YH_API float ycgeh_gradient_noise2d(float x, float z, int seed) { return WorldGeneration::GradientNoise2D(x, z, seed); }
 YH_API int ycgeh_write_synthetic_world(const char *path, int world_size, int world_height) { // a VG01 file of the synthetic world (tests)
     try { VolumeScenes::WriteSyntheticWorldFile(path, world_size, world_height); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }

@@ -257,6 +257,8 @@ ObjData ProceduralKnot(int segU, int segV); // "dragon-standin": 2*segU*segV tri
 } // namespace MeshScenes
 namespace VolumeScenes { // structure of Scenes/VolumeScenes.cs:569-627 over a synthetic heightfield (generator is out of scope)
 std::shared_ptr<Scene> BuildSyntheticWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds);
+std::shared_ptr<Scene> BuildIslandWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds); // the reference's generator, seed 0
+void WriteIslandWorldFile(const std::string &path, int worldSize, int worldHeight);
 float SyntheticHeight(int x, int z, int worldHeight);
 } // namespace VolumeScenes
 std::shared_ptr<Scene> BuildSceneByName(const std::string &name);
