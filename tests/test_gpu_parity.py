@@ -102,6 +102,7 @@ LIVE = [  # scene, fb_w, fb_h, ss, frames, pose
     ("bunny", 64, 18, 2, 2, api.BENCH_POSE),
     ("knot:60x16", 48, 14, 4, 2, api.BENCH_POSE),
     ("voxel_world:64x64", 48, 14, 4, 2, None),
+    ("voxel_island:64x128", 48, 14, 4, 2, None),  # the reference's own generator (GenerateAndSaveWorld) on a small world
     ("cornell", 1, 1, 1, 2, None),           # minimum size: 1x2 pixels
     ("texture_gallery", 64, 18, 3, 2, None),  # SampleAlbedo + Texture.SampleBilinear on rects, box faces, a triangle, a mesh, glass
     ("texture_gallery", 48, 14, 2, 2, ((1.2, 1.4, -0.6), 0.5, -0.3)),
