@@ -175,6 +175,51 @@ def test_island_world_scene_equals_its_world_file(tmp_path):
         api.HostScene("voxel_island:48x64")
 
 
+def test_day_night_entity_matches_a_literal_transcription():
+    """DayNightEntity.Update (Scenes/DayNightCycle.cs:41-91) in numpy binary32, cosf / sinf from the C library like the mirror: sun
+    and moon positions (y clamped to 50 below the horizon), intensities 300000 * sunN^2 and 8000 * 0.1 * sqrt(moonN), the sky
+    gradient; time accumulates in binary32 and wraps with `%` at the 120 s cycle.  The voxel worlds start at 45 s."""
+    import ctypes as C
+    import ctypes.util
+    libm = C.CDLL(ctypes.util.find_library("m"))
+    for fn in (libm.cosf, libm.sinf, libm.fmodf):
+        fn.restype = C.c_float
+    libm.cosf.argtypes = libm.sinf.argtypes = [C.c_float]
+    libm.fmodf.argtypes = [C.c_float, C.c_float]
+    F = np.float32
+    s = api.HostScene("voxel_world:32x32")
+    t = F(45.0)
+    assert len(s.lights()) == 2
+    for dt in [0.0, 1.0 / 60.0, 7.25, 20.0, 30.0, 0.016, 33.0, 100.0, -5.0]:
+        s.update(dt)
+        t = F(t + max(F(0.0), F(dt)))                                                       # :46 (negative dt ignored)
+        t01 = F(F(libm.fmodf(t, F(120.0))) / F(120.0))
+        pi = F(np.pi)
+        theta = F(F(F(t01 * F(2.0)) * pi) - F(pi * F(0.5)))
+        sx, sy, sz = F(libm.cosf(theta)), F(libm.sinf(theta)), F(0.25)
+        norm = np.sqrt(F(F(F(sx * sx) + F(sy * sy)) + F(sz * sz)))
+        sx, sy, sz = F(sx / norm), F(sy / norm), F(sz / norm)
+        sun = (F(sx * F(2000.0)), F(max(50.0, float(F(sy * F(2000.0))))), F(sz * F(2000.0)))  # Math.Max(50.0, (double)float) -> (float)
+        moon = (F(-sun[0]), F(max(50.0, -float(sun[1]))), F(-sun[2]))
+        sun_n, moon_n = max(F(0.0), sy), max(F(0.0), F(-sy))
+        sun_i, moon_i = F(sun_n * sun_n), F(np.sqrt(moon_n) * F(0.10))
+        blend = min(F(1.0), max(F(0.0), F(sun_i * F(1.5))))
+        lerp = lambda a, b: tuple(F(F(F(x) * F(F(1.0) - blend)) + F(F(y) * blend)) for x, y in zip(a, b))
+        want_top, want_bottom = lerp((0.02, 0.03, 0.06), (0.30, 0.55, 0.95)), lerp((0.0, 0.0, 0.0), (0.80, 0.90, 1.00))
+        (p0, c0, i0), (p1, c1, i1) = s.lights()
+        assert tuple(map(F, p0)) == sun and tuple(map(F, p1)) == moon, (dt, p0, sun)
+        assert F(i0) == F(F(300000.0) * sun_i) and F(i1) == F(F(8000.0) * moon_i)
+        assert tuple(map(F, c0)) == (F(1.00), F(0.96), F(0.88)) and tuple(map(F, c1)) == (F(0.65), F(0.70), F(0.90))
+        top, bottom = s.background()
+        assert tuple(map(F, top)) == want_top and tuple(map(F, bottom)) == want_bottom
+    assert len(s.lights()) == 2                                                              # the entity keeps its two lights, never adds more
+    s.close()
+    t = api.HostScene("cornell")
+    before = t.lights()
+    assert t.update(1.0) == 0 and t.lights() == before                                        # a scene without entities: nothing moves
+    t.close()
+
+
 def test_texture_test_scene_and_png_decoder(tmp_path):
     """BuildTextureTestScene (Scenes.cs:337-358): one textured box, ambient 0.5, no lights.  new Texture(path) decodes through
     OpenCV in the reference (ImreadModes.Color, BGR2RGBA: Texture.cs:25-49); the mirror's zlib-only PNG decoder must give the

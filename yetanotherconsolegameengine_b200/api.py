@@ -236,6 +236,8 @@ def load_host() -> C.CDLL:
         h.ycgeh_renderer_ctx.restype = vp
         h.ycgeh_renderer_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
         h.ycgeh_renderer_set_fov.argtypes = [vp, C.c_float]
+        h.ycgeh_renderer_sync_lights.argtypes = [vp, vp]
+        h.ycgeh_scene_update.argtypes = [vp, C.c_float]
         h.ycgeh_renderer_resize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         h.ycgeh_renderer_render_cells.argtypes = [vp, vp]
         h.ycgeh_renderer_blit_ansi.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint8))]
@@ -352,6 +354,22 @@ class HostScene:
     def volume(self, i):
         return self._h.ycgeh_scene_volume(self.handle, i)
 
+    def update(self, dt: float) -> int:
+        """Scene.Update(dt) (Scenes/Scene.cs:100-163): scene entities (DayNightEntity) rewrite the lights and the sky gradient;
+        the flat view follows.  Returns the scene's light version; push the change with CudaRaytraceRenderer.SyncLights."""
+        v = self._h.ycgeh_scene_update(self.handle, dt)
+        if v < 0:
+            raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+        return v
+
+    def lights(self):
+        f = self.flat.contents
+        return [(tuple(f.lights[i].pos), tuple(f.lights[i].color), f.lights[i].intensity) for i in range(f.n_lights)]
+
+    def background(self):
+        f = self.flat.contents
+        return tuple(f.bg_top), tuple(f.bg_bottom)
+
     def default_camera(self):
         pos = (C.c_float * 3)()
         yaw, pitch, fov = C.c_float(), C.c_float(), C.c_float()
@@ -410,6 +428,12 @@ class CudaRaytraceRenderer:
     def SetCamera(self, pos, yaw: float, pitch: float):
         p = (C.c_float * 3)(*pos)
         if self._h.ycgeh_renderer_set_camera(self.handle, p, yaw, pitch) != 0:
+            raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+
+    def SyncLights(self, scene: "HostScene"):
+        """After scene.update(dt): ycge_lights_update + ycge_globals_update with what the entities changed (no history reset,
+        like the reference, whose renderer simply reads scene.Lights on the next frame)."""
+        if self._h.ycgeh_renderer_sync_lights(self.handle, scene.handle) != 0:
             raise YcgeError(-1, self._h.ycgeh_last_error().decode())
 
     def SetFov(self, fov_deg: float):

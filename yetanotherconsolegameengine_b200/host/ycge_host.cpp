@@ -1106,6 +1106,29 @@ World Generate(int nx, int ny, int nz, int seed) { // WorldManager.cs:510-606
 }
 } // namespace WorldGeneration
 
+void DayNightEntity::Update(float dt, Scene &scene) { // DayNightCycle.cs:41-91
+    if (!Enabled) return;
+    const float PI = 3.14159274f;
+    time += std::max(0.0f, dt);
+    float t01 = std::fmod(time, cycleSeconds) / cycleSeconds;
+    float theta = (t01 * 2.0f * PI) - PI * 0.5f;
+    float sx = std::cos(theta), sy = std::sin(theta), sz = 0.25f;
+    float norm = std::sqrt(sx * sx + sy * sy + sz * sz);
+    sx /= norm; sy /= norm; sz /= norm;
+    Vec3 sunPos((double)(sx * sunRadius), std::max(50.0, (double)(sy * sunRadius)), (double)(sz * sunRadius));
+    Vec3 moonPos((double)-sunPos.X, std::max(50.0, (double)-sunPos.Y), (double)-sunPos.Z);
+    if (sun < 0) { scene.Lights.push_back(PointLight(sunPos, Vec3(1.00, 0.96, 0.88), 0.0f)); sun = (int)scene.Lights.size() - 1; }
+    if (moon < 0) { scene.Lights.push_back(PointLight(moonPos, Vec3(0.65, 0.70, 0.90), 0.0f)); moon = (int)scene.Lights.size() - 1; }
+    float sunN = std::max(0.0f, sy), moonN = std::max(0.0f, -sy);
+    float sunI = sunN * sunN, moonI = std::sqrt(moonN) * 0.10f;
+    scene.Lights[sun].Position = sunPos; scene.Lights[sun].Intensity = 300000.0f * sunI;
+    scene.Lights[moon].Position = moonPos; scene.Lights[moon].Intensity = 8000.0f * moonI;
+    float skyBlend = sunI * 1.5f; skyBlend = skyBlend < 0.0f ? 0.0f : (skyBlend > 1.0f ? 1.0f : skyBlend);
+    auto lerp = [&](Vec3 a, Vec3 b, float t) { return a * (1.0f - t) + b * t; };
+    scene.BackgroundTop = lerp(Vec3(0.02, 0.03, 0.06), Vec3(0.30, 0.55, 0.95), skyBlend);
+    scene.BackgroundBottom = lerp(Vec3(0.00, 0.00, 0.00), Vec3(0.80, 0.90, 1.00), skyBlend);
+}
+
 // ---- synthetic voxel world with the structure BuildMinecraftLike produces ---------------------------------------
 namespace VolumeScenes {
 static uint32_t hash2(int x, int z) {
@@ -1162,25 +1185,9 @@ static std::shared_ptr<Scene> BuildWorldFromCells(int nx, int ny, int nz, int ch
         Vec3 minCorner(worldMin.X + baseX * 1.0f, worldMin.Y + baseY * 1.0f, worldMin.Z + baseZ * 1.0f); // WorldManager.cs:724-728
         s->Add(std::make_shared<VolumeGrid>(chunkSize, chunkSize, chunkSize, cell, minCorner, Vec3(1.0f, 1.0f, 1.0f), pal));
     }
-    // DayNightEntity.Update at time = daySeconds (Scenes/DayNightCycle.cs:41-91), cycle 120 s, radius 2000
-    {
-        const float cycleSeconds = 120.0f, sunRadius = 2000.0f, PI = 3.14159274f;
-        float t01 = std::fmod(daySeconds, cycleSeconds) / cycleSeconds;
-        float theta = (t01 * 2.0f * PI) - PI * 0.5f;
-        float sx = std::cos(theta), sy = std::sin(theta), sz = 0.25f;
-        float norm = std::sqrt(sx * sx + sy * sy + sz * sz);
-        sx /= norm; sy /= norm; sz /= norm;
-        Vec3 sunPos((double)(sx * sunRadius), std::max(50.0, (double)(sy * sunRadius)), (double)(sz * sunRadius));
-        Vec3 moonPos((double)-sunPos.X, std::max(50.0, (double)-sunPos.Y), (double)-sunPos.Z);
-        float sunN = std::max(0.0f, sy), moonN = std::max(0.0f, -sy);
-        float sunI = sunN * sunN, moonI = std::sqrt(moonN) * 0.10f;
-        s->Lights.push_back(PointLight(sunPos, Vec3(1.00, 0.96, 0.88), 300000.0f * sunI));
-        s->Lights.push_back(PointLight(moonPos, Vec3(0.65, 0.70, 0.90), 8000.0f * moonI));
-        float skyBlend = sunI * 1.5f; skyBlend = skyBlend < 0.0f ? 0.0f : (skyBlend > 1.0f ? 1.0f : skyBlend);
-        auto lerp = [&](Vec3 a, Vec3 b, float t) { return a * (1.0f - t) + b * t; };
-        s->BackgroundTop = lerp(Vec3(0.02, 0.03, 0.06), Vec3(0.30, 0.55, 0.95), skyBlend);
-        s->BackgroundBottom = lerp(Vec3(0.00, 0.00, 0.00), Vec3(0.80, 0.90, 1.00), skyBlend);
-    }
+    // DayNightEntity(cycleSeconds: 120, sunRadius: 2000) (VolumeScenes.cs:599-602), advanced to time = daySeconds
+    s->Entities.push_back(std::make_shared<DayNightEntity>(120.0f, 2000.0f));
+    s->Entities.back()->Update(daySeconds, *s);
     // camera: standing on the highest non-air voxel of the centre column
     int top = 0;
     for (int wy = ny - 1; wy >= 0; wy--) { int m, e; cellAt(nx / 2, wy, nz / 2, m, e); if (m != 0) { top = wy; break; } }
@@ -1449,6 +1456,7 @@ static ycge_bvh bvh_view(const ycge::FlatTree &t) {
     b.left = t.left.data(); b.right = t.right.data(); b.start = t.start.data(); b.count = t.count.data(); b.leaf_index = t.leaf_index.data();
     return b;
 }
+static void FlattenLights(const Scene &s, std::vector<ycge_light> &out);
 static std::unique_ptr<FlatScene> Flatten(std::shared_ptr<Scene> sp) {
     Scene &s = *sp;
     if (!s.bvh) s.RebuildBVH();
@@ -1456,11 +1464,7 @@ static std::unique_ptr<FlatScene> Flatten(std::shared_ptr<Scene> sp) {
     f->keep = sp;
     f->keep_bvh = s.bvh;
     for (auto &o : s.Objects) o->Export(f->ex);
-    for (auto &l : s.Lights) {
-        ycge_light L;
-        L.pos[0] = l.Position.X; L.pos[1] = l.Position.Y; L.pos[2] = l.Position.Z; L.color[0] = l.Color.X; L.color[1] = l.Color.Y; L.color[2] = l.Color.Z; L.intensity = l.Intensity;
-        f->ex.lights.push_back(L);
-    }
+    FlattenLights(s, f->ex.lights);
     f->top = bvh_view(s.bvh->tree);
     ycge_scene &sc = f->scene;
     memset(&sc, 0, sizeof sc);
@@ -1530,6 +1534,23 @@ void CudaRaytraceRenderer::UploadScene(Scene &scene) {
     for (size_t i = 0; i < flat->vols.size(); i++) Check(ycge_volume_upload(ctx, (int)i, &flat->vols[i]), "ycge_volume_upload");
     Check(ycge_scene_upload(ctx, &flat->scene), "ycge_scene_upload");
     Check(ycge_reset_history(ctx), "ycge_reset_history");
+}
+static void FlattenLights(const Scene &s, std::vector<ycge_light> &out) {
+    out.clear();
+    for (auto &l : s.Lights) {
+        ycge_light L;
+        L.pos[0] = l.Position.X; L.pos[1] = l.Position.Y; L.pos[2] = l.Position.Z; L.color[0] = l.Color.X; L.color[1] = l.Color.Y; L.color[2] = l.Color.Z; L.intensity = l.Intensity;
+        out.push_back(L);
+    }
+}
+void CudaRaytraceRenderer::SyncLights(const Scene &scene) { // what DayNightEntity.Update changes (DayNightCycle.cs:80-88): no geometry, no history reset
+    std::vector<ycge_light> L;
+    FlattenLights(scene, L);
+    Check(ycge_lights_update(ctx, (int)L.size(), L.data()), "ycge_lights_update");
+    float top[3] = {(float)scene.BackgroundTop.X, (float)scene.BackgroundTop.Y, (float)scene.BackgroundTop.Z};
+    float bot[3] = {(float)scene.BackgroundBottom.X, (float)scene.BackgroundBottom.Y, (float)scene.BackgroundBottom.Z};
+    float amb[3] = {(float)scene.Ambient.Color.X, (float)scene.Ambient.Color.Y, (float)scene.Ambient.Color.Z};
+    Check(ycge_globals_update(ctx, top, bot, amb, scene.Ambient.Intensity), "ycge_globals_update");
 }
 void CudaRaytraceRenderer::SetCamera(Vec3 pos, float yaw, float pitch) { float p[3] = {pos.X, pos.Y, pos.Z}; Check(ycge_set_camera(ctx, p, yaw, pitch), "ycge_set_camera"); }
 void CudaRaytraceRenderer::SetFov(float fovDeg) { Check(ycge_set_fov(ctx, fovDeg), "ycge_set_fov"); }
@@ -1674,6 +1695,19 @@ YH_API float ycgeh_gradient_noise2d(float x, float z, int seed) { return WorldGe
 YH_API int ycgeh_write_synthetic_world(const char *path, int world_size, int world_height) { // a VG01 file of the synthetic world (tests)
     try { VolumeScenes::WriteSyntheticWorldFile(path, world_size, world_height); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
+YH_API int ycgeh_scene_update(void *h, float dt) { // Scene.Update(dt): entities rewrite lights and sky; the flat view follows
+    try {
+        SceneHandle *sh = (SceneHandle *)h;
+        Scene &s = *sh->scene;
+        s.Update(dt);
+        FlatScene &f = *sh->flat;
+        FlattenLights(s, f.ex.lights);
+        f.scene.n_lights = (int)f.ex.lights.size(); f.scene.lights = f.ex.lights.data();
+        f.scene.bg_top[0] = s.BackgroundTop.X; f.scene.bg_top[1] = s.BackgroundTop.Y; f.scene.bg_top[2] = s.BackgroundTop.Z;
+        f.scene.bg_bottom[0] = s.BackgroundBottom.X; f.scene.bg_bottom[1] = s.BackgroundBottom.Y; f.scene.bg_bottom[2] = s.BackgroundBottom.Z;
+        return (int)s.LightsVersion;
+    } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
 YH_API void ycgeh_scene_destroy(void *h) { delete (SceneHandle *)h; }
 YH_API const ycge_scene *ycgeh_scene_flat(void *h) { return &((SceneHandle *)h)->flat->scene; }
 YH_API int ycgeh_scene_n_meshes(void *h) { return (int)((SceneHandle *)h)->flat->mesh_soa.size(); }
@@ -1725,6 +1759,9 @@ YH_API void ycgeh_renderer_destroy(void *h) { delete (RendererHandle *)h; }
 YH_API ycge_ctx *ycgeh_renderer_ctx(void *h) { return ((RendererHandle *)h)->r->Context(); }
 YH_API int ycgeh_renderer_set_camera(void *h, const float *pos, float yaw, float pitch) {
     try { ((RendererHandle *)h)->r->SetCamera(Vec3(pos[0], pos[1], pos[2]), yaw, pitch); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_renderer_sync_lights(void *h, void *scene) { // after ycgeh_scene_update: push what the entities changed
+    try { ((RendererHandle *)h)->r->SyncLights(*((SceneHandle *)scene)->scene); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
 YH_API int ycgeh_renderer_set_fov(void *h, float fov) {
     try { ((RendererHandle *)h)->r->SetFov(fov); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }

@@ -190,6 +190,20 @@ class BVH { // Objects/BVH.cs: top-level tree over Scene.Objects
     explicit BVH(const std::vector<std::shared_ptr<Hittable>> &objects); // throws std::runtime_error("Unbounded Hittable") :39
 };
 
+class Scene;
+// Scenes/DayNightCycle.cs: the one scene entity that changes the path's inputs every frame (sun / moon PointLights, sky
+// gradient).  The rest of the entity layer (ISceneEntity with hittables, physics) is out of scope.
+class DayNightEntity {
+  public:
+    bool Enabled = true;
+    explicit DayNightEntity(float cycleSeconds = 120.0f, float sunRadius = 2000.0f) : cycleSeconds(std::max(1.0f, cycleSeconds)), sunRadius(sunRadius) {}
+    void Update(float dt, Scene &scene); // DayNightCycle.cs:41-91
+    float Time() const { return time; }
+  private:
+    float time = 0.0f, cycleSeconds, sunRadius;
+    int sun = -1, moon = -1; // indices into Scene::Lights (the reference keeps the PointLight objects)
+};
+
 class Scene { // Scenes/Scene.cs
   public:
     std::vector<std::shared_ptr<Hittable>> Objects;
@@ -210,7 +224,12 @@ class Scene { // Scenes/Scene.cs
     void Add(std::shared_ptr<Hittable> h) { Objects.push_back(h); }
     void RebuildBVH() { bvh = std::make_shared<BVH>(Objects); } // Scene.cs:66-69
     void ResetCamera() { CameraPos = DefaultCameraPos; Yaw = DefaultYaw; Pitch = DefaultPitch; }
-    void Update(float) { if (!bvh) RebuildBVH(); } // Scene.cs:100-163 (entity layer is out of scope)
+    std::vector<std::shared_ptr<DayNightEntity>> Entities;
+    unsigned LightsVersion = 0; // bumped whenever an entity rewrote Lights / Background*: CudaRaytraceRenderer::SyncLights pushes them
+    void Update(float dt) { // Scene.cs:100-163: entities first, then the tree if the object list changed
+        for (auto &e : Entities) { e->Update(dt, *this); LightsVersion++; }
+        if (!bvh) RebuildBVH();
+    }
 };
 
 // Flat arrays handed to the C ABI (what host_cs/CudaRaytraceRenderer.cs marshals)
@@ -296,6 +315,7 @@ class CudaRaytraceRenderer : public IConsoleRenderer {
     void Resize(Framebuffer &fb, int superSample) override;
     void UploadTexture(int id, const Texture &t);   // new Texture(path) -> ycge_texture_upload
     void UploadScene(Scene &scene);                 // scene switch (RaytraceEntity.SwitchToScene :234-246)
+    void SyncLights(const Scene &scene);            // after scene.Update(dt): ycge_lights_update + ycge_globals_update when an entity moved them
     void RenderCells(ycge_cell *out);               // TryFlipAndBlit without the Chexel unpack (headless)
     ycge_ctx *Context() { return ctx; }
     int fbW, fbH, ss;
