@@ -233,7 +233,7 @@ def test_mesh_builder_matches_a_literal_python_transcription(scene_name):
 
 
 @pytest.mark.parametrize("scene_name", ["cornell", "mirror_spheres", "cylinders_disks_triangles", "boxes", "test", "volume_grid_test", "teapot",
-                                        "voxel_world:64x64", "texture_gallery"])
+                                        "voxel_world:64x64", "texture_gallery", "all_meshes:40x10", "voxel_island:64x128"])
 def test_top_level_builder_matches_a_literal_python_transcription(scene_name):
     lib = load_oracle()
     lib.yo_set_sort_mode(0)

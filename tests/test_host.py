@@ -419,6 +419,41 @@ def test_mesh_scenes_match_the_reference_source(name):
     s.close()
 
 
+def test_all_meshes_scene_matches_the_reference_source():
+    """MeshScenes.BuildAllMeshesScene (MeshScenes.cs:145-158): NewBaseScene plus cow, bunny, teapot and dragon, each with its own
+    swatch material and targetPos, in Objects order; values extracted from the C# text by tools/extract_scene_literals.py.  The
+    triangles of the three real meshes must be MeshLoader's normalisation moved to their targetPos (the numpy transcription of
+    tests/test_mesh_loader_literal.py)."""
+    import json
+    from test_mesh_loader_literal import read_ymesh, normalize_all_used, bounds_normalized_largest_component
+    from conftest import GOLDEN
+    gold = json.load(open(os.path.join(GOLDEN, "scene_literals.json")))
+    s = api.HostScene("all_meshes:40x10")
+    flat = s.flat.contents
+    f32 = lambda x: float(np.float32(x))
+    F = np.float32
+    assert s.name == "all_meshes-standin" and s.n_meshes == 4 and flat.n_objects == 5 and flat.n_lights == 2
+    assert flat.objects[0].kind == 1 and [flat.objects[i].kind for i in range(1, 5)] == [flat.objects[1].kind] * 4
+    assert [flat.objects[i].ref_id for i in range(1, 5)] == [0, 1, 2, 3]                      # Objects order = mesh upload ids
+    for i, g in enumerate(gold["all_meshes"]):
+        m = s.mesh(i).contents.material
+        assert ([f32(v) for v in m.albedo], f32(m.specular), f32(m.reflectivity), [f32(v) for v in m.emission], f32(m.transparency)) == \
+            (g["material"]["albedo"], g["material"]["specular"], g["material"]["reflectivity"], g["material"]["emission"], g["material"]["transparency"]), g["asset"]
+        got = s.mesh_triangles(i)
+        if g["asset"] == "xyzrgb_dragon.obj":                                                  # the stand-in: placement only
+            lo, hi = got.reshape(-1, 3).min(0), got.reshape(-1, 3).max(0)
+            assert abs(0.5 * (lo[0] + hi[0]) - g["target_pos"][0]) < 0.01 and abs(lo[1] - 0.51) < 0.1
+            continue
+        xyz, faces = read_ymesh(os.path.join(GOLDEN, "meshes", g["asset"].replace(".obj", ".ymesh")))
+        target, scale = np.array(g["target_pos"], F), F(g["scale"])
+        mn_n, _ = bounds_normalized_largest_component(xyz, faces)
+        t = np.array([target[0], F(F(target[1] - F(mn_n[1] * scale)) + F(0.01)), target[2]], F)
+        pos = ((normalize_all_used(xyz, faces) * scale).astype(F) + t).astype(F)
+        tris = np.concatenate([pos[faces[:, 0]], pos[faces[:, 1]], pos[faces[:, 2]]], axis=1)
+        assert got.shape == tris.shape and np.array_equal(got.view(np.uint32), tris.view(np.uint32)), g["asset"]
+    s.close()
+
+
 def test_voxel_palette_matches_the_reference_source():
     """VoxelMaterialPalette.MaterialLookup (Scenes/VoxelMaterialPalette.cs:8-98) crosses the C ABI as a table (ycge_volume.palette);
     every (block id, meta) of the mirror's table against the lookup evaluated from the C# switch statements by

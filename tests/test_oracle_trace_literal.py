@@ -761,7 +761,7 @@ class LiteralTracer:
 
 @pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1), ("knot:12x5", 8, 3, 2),
                                                      ("volume_grid_test", 10, 4, 2), ("voxel_world:32x32", 8, 4, 2), ("cylinders_disks_triangles", 10, 4, 2),
-                                                     ("texture_gallery", 14, 5, 2), ("voxel_island:96x128", 8, 4, 2)])
+                                                     ("texture_gallery", 14, 5, 2), ("voxel_island:96x128", 8, 4, 2), ("all_meshes:40x10", 16, 3, 2)])
 def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb_h, ss):
     lib = load_oracle()
     lib.yo_set_math_mode(0)

@@ -1,0 +1,76 @@
+"""GPU parity tests written after this round's GPU minutes were spent: they have passed against the oracle's half on the CPU (the
+scenes build, the oracle renders them, the literal transcriptions agree) but have NOT yet run on a B200.  They use only entry
+points the verified suite (test_gpu_parity.py) already exercises, on new inputs.  The file sorts last so that, under `-x`, a
+surprise here cannot hide the verified results.  Once they have passed on the GPU they belong in test_gpu_parity.py.
+"""
+import os
+
+import pytest
+
+from conftest import require_cuda
+from yetanotherconsolegameengine_b200 import api
+from oracle_binding import Oracle
+from test_gpu_parity import assert_cells_equal, assert_frame_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    require_cuda()
+
+
+NEW_SCENES = [  # scene, fb_w, fb_h, ss, frames, pose
+    ("voxel_island:64x128", 48, 14, 4, 2, None),   # the reference's own generator (GenerateAndSaveWorld) on a small world
+    ("all_meshes:40x10", 64, 18, 2, 2, None),       # BuildAllMeshesScene: four meshes with their own materials in one scene
+    ("all_meshes:40x10", 48, 14, 3, 2, ((0.5, 1.6, -1.0), 0.3, -0.25)),
+]
+
+
+@pytest.mark.parametrize("case", NEW_SCENES, ids=[f"{c[0]}-{c[1]}x{c[2]}ss{c[3]}-{i}" for i, c in enumerate(NEW_SCENES)])
+def test_gpu_matches_oracle_on_the_new_scenes(case):
+    scene, fb_w, fb_h, ss, frames, pose = case
+    s = api.HostScene(scene)
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    o = Oracle(s, fb_w, fb_h, ss)
+    if pose is not None:
+        r.SetCamera(*pose)
+        o.set_camera(*pose)
+    r.debug_read(api.DBG_RAYS)  # arms the ray tap
+    for f in range(frames):
+        g = r.render_frame_stats()
+        c = o.render_frame(threads=os.cpu_count() or 1, fast_post=True)
+        assert_cells_equal(g, c, f"{scene} frame {f + 1}")
+        assert_frame_parity(r, o, f"{scene} frame {f + 1}", check_rays=True)
+        gs, cs = r.stats(), o.stats()
+        for k in ("top_nodes_popped", "mesh_nodes_popped", "leaf_refs", "tris_tested", "prims_tested", "dda_cells"):
+            assert gs[k] == cs[k], f"{scene}: traversal event counter {k}: {gs[k]} vs {cs[k]}"
+    r.close()
+    o.close()
+    s.close()
+
+
+def test_day_night_cycle_moves_the_sun_between_frames():
+    """DayNightEntity (Scenes/DayNightCycle.cs:41-91) rewrites the sun / moon lights and the sky gradient on every Scene.Update;
+    the renderer reads them on the next frame without a history reset.  Here: scene.update(dt) on the host mirror,
+    CudaRaytraceRenderer.SyncLights -> ycge_lights_update + ycge_globals_update, the oracle fed the same values; from afternoon
+    through dusk into the night (moon only) and on to the next sunrise."""
+    s = api.HostScene("voxel_world:64x64")
+    r = api.CudaRaytraceRenderer(s, 40, 12, 2)
+    o = Oracle(s, 40, 12, 2)
+    saw_night = False
+    for f, dt in enumerate([0.0, 1.0 / 60.0, 10.0, 6.0, 30.0, 0.5, 70.0]):
+        s.update(dt)
+        r.SyncLights(s)
+        top, bottom = s.background()
+        o.lights_update(s.lights())
+        o.globals_update(top, bottom, (1.0, 1.0, 1.0), 0.0)           # the world scenes' ambient (VolumeScenes.cs:595)
+        saw_night |= s.lights()[0][2] == 0.0 and s.lights()[1][2] > 0.0
+        g = r.TryFlipAndBlit()
+        c = o.render_frame(threads=4, fast_post=True)
+        assert_cells_equal(g, c, f"day/night frame {f + 1}")
+        assert_frame_parity(r, o, f"day/night frame {f + 1}")
+    assert saw_night
+    r.close()
+    o.close()
+    s.close()

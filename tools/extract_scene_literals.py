@@ -192,6 +192,22 @@ def mesh_scene_materials(src):
     return out
 
 
+def all_meshes_scene(src):
+    """BuildAllMeshesScene (:145-158): per mesh the asset, its material (a named local built from a swatch) and targetPos, in order."""
+    sw = mesh_swatches(src)
+    body = function_body(src, "BuildAllMeshesScene")
+    mats = {}
+    for var, kind, swatch, args in re.findall(r"Material (\w+) = MeshSwatches\.(Matte|Mirror)\(MeshSwatches\.(\w+)((?:, [\d.]+)*)\);", body):
+        nums = [float(v) for v in re.findall(r"[\d.]+", args)]
+        spec, refl = ((nums + [0.10, 0.00][len(nums):])[:2]) if kind == "Matte" else (0.0, (nums + [0.85])[0])
+        mats[var] = Material(sw[swatch], spec, refl, Vec3(0, 0, 0)).dump()
+    out = []
+    for asset, var, scale, target in re.findall(r'AddMeshAutoGround\(s, @"assets\\([\w.-]+)", (\w+), scale: ([\d.]+)f, targetPos: new Vec3\(([^)]*)\)\);', body):
+        out.append(dict(asset=asset, material=mats[var], scale=f32(scale), target_pos=[f32(v.strip().rstrip("f")) for v in target.split(",")]))
+    assert len(out) == 4
+    return out
+
+
 def renderer_constants(ref):
     """The compile-time constants of the path (RaytraceRenderer.cs:31-43,:65,:222,:281; ToneMapper.cs:8-21) = ycge_default_params."""
     rr = open(os.path.join(ref, "RayTracing", "RaytraceRenderer.cs"), encoding="utf-8-sig").read()
@@ -278,6 +294,7 @@ if __name__ == "__main__":
     msrc = open(os.path.join(ref, "RayTracing", "Scenes", "MeshScenes.cs"), encoding="utf-8-sig").read()
     out["mesh_base"] = extract(msrc, "NewBaseScene")
     out["mesh_scenes"] = mesh_scene_materials(msrc)
+    out["all_meshes"] = all_meshes_scene(msrc)
     out["params"] = renderer_constants(ref)
     out["voxel_palette"] = voxel_palette(ref)
     out["tables"] = tables(ref)

@@ -727,6 +727,24 @@ std::shared_ptr<Scene> BuildDragonScene() { // :135-143; Sapphire = Scale(Blue, 
     s->DefaultCameraPos = Vec3(0.0f, 10.0f, 0.0f);
     return s;
 }
+// BuildAllMeshesScene (:145-158): the four meshes side by side in front of the default camera.  The reference throws
+// FileNotFoundException when an asset is missing (:176-179) -- as it does for the dragon in the distributed checkout; here the
+// dragon falls back to the same labelled stand-in as BuildDragonScene.  `knotU x knotV` sizes that stand-in (tests use a small one).
+std::shared_ptr<Scene> BuildAllMeshesScene(int knotU, int knotV) {
+    auto s = NewBaseScene(); s->Name = "all_meshes";
+    Material cowMat(Vec3(0.80f, 0.45f, 0.25f), 0.10, 0.00, Vec3());                       // Matte(Copper, 0.10, 0.00)
+    Material bunnyMat(ScaleC(Vec3(0.0f, 0.5f, 0.5f), 1.00f), 0.12, 0.00, Vec3());         // Matte(Jade = Scale(DarkCyan, 1.00), 0.12, 0.00)
+    Material teapotMat(ScaleC(Vec3(1.0f, 1.0f, 0.0f), 0.90f), 0.28, 0.06, Vec3());        // Matte(Gold, 0.28, 0.06)
+    Material dragonMat(ScaleC(Vec3(1.0f, 0.0f, 1.0f), 0.88f), 0.0, 0.65, Vec3());         // Mirror(Amethyst, 0.65): diffuse, 0.65 < 0.9
+    AddMeshAutoGround(*s, MeshLoader::ParseObj(AssetDir + "/cow.obj"), cowMat, 1.0f, Vec3(-3.2f, 0.5f, -4.0f));
+    AddMeshAutoGround(*s, MeshLoader::ParseObj(AssetDir + "/stanford-bunny.obj"), bunnyMat, 1.0f, Vec3(-1.0f, 0.5f, -3.0f));
+    AddMeshAutoGround(*s, MeshLoader::ParseObj(AssetDir + "/teapot.obj"), teapotMat, 1.0f, Vec3(1.6f, 0.5f, -3.2f));
+    std::ifstream probe(AssetDir + "/xyzrgb_dragon.obj");
+    if (probe.good()) AddMeshAutoGround(*s, MeshLoader::ParseObj(AssetDir + "/xyzrgb_dragon.obj"), dragonMat, 1.0f, Vec3(3.2f, 0.5f, -4.6f));
+    else { AddMeshAutoGround(*s, ProceduralKnot(knotU, knotV), dragonMat, 1.0f, Vec3(3.2f, 0.5f, -4.6f)); s->Name = "all_meshes-standin"; }
+    s->RebuildBVH();
+    return s;
+}
 } // namespace MeshScenes
 
 // ---- the island generator the reference pre-generates its voxel world with -------------------------------------------
@@ -1281,6 +1299,12 @@ std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
     if (name == "bunny") return MeshScenes::BuildBunnyScene();
     if (name == "teapot") return MeshScenes::BuildTeapotScene();
     if (name == "dragon") return MeshScenes::BuildDragonScene();
+    if (name == "all_meshes") return MeshScenes::BuildAllMeshesScene(1400, 100);
+    if (name.rfind("all_meshes:", 0) == 0) { // all_meshes:<segU>x<segV> — a smaller dragon stand-in (tests)
+        int su = 0, sv = 0;
+        if (sscanf(name.c_str() + 11, "%dx%d", &su, &sv) != 2 || su < 3 || sv < 3) throw std::invalid_argument("all_meshes:<segU>x<segV>");
+        return MeshScenes::BuildAllMeshesScene(su, sv);
+    }
     if (name.rfind("knot:", 0) == 0) { // knot:<segU>x<segV> — procedural mesh of a chosen size (tests)
         int su = 0, sv = 0;
         if (sscanf(name.c_str() + 5, "%dx%d", &su, &sv) != 2 || su < 3 || sv < 3) throw std::invalid_argument("knot:<segU>x<segV>");

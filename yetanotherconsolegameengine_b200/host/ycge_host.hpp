@@ -271,6 +271,7 @@ std::shared_ptr<Scene> BuildCowScene();
 std::shared_ptr<Scene> BuildBunnyScene();
 std::shared_ptr<Scene> BuildTeapotScene();
 std::shared_ptr<Scene> BuildDragonScene(); // real xyzrgb_dragon.obj if present, else the procedural stand-in (labelled in Scene::Name)
+std::shared_ptr<Scene> BuildAllMeshesScene(int knotU = 1400, int knotV = 100); // cow, bunny, teapot, dragon (or its stand-in) in one scene
 std::shared_ptr<Scene> BuildMeshScene(const ObjData &mesh, Material mat, const std::string &name, Vec3 targetPos = Vec3(0.0f, 0.5f, 1.0f));
 ObjData ProceduralKnot(int segU, int segV); // "dragon-standin": 2*segU*segV triangles
 } // namespace MeshScenes
