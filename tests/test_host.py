@@ -454,6 +454,100 @@ def test_all_meshes_scene_matches_the_reference_source():
     s.close()
 
 
+def diorama_cells(name):
+    """The cell loops of TestScenes.BuildVolumeDioramaA / B (TestScenes.cs:217-254, :282-308), restated with numpy slices."""
+    if name == "BuildVolumeDioramaA":
+        c = np.zeros((16, 8, 16), np.int32)
+        c[:, 0, :] = 1                                                            # floor
+        c[:, 1:4, 0] = c[:, 1:4, 15] = 1                                          # walls, three high
+        c[0, 1:4, :] = c[15, 1:4, :] = 1
+        for cx, cz, h, m in ((4, 4, 4, 2), (11, 4, 3, 3), (4, 11, 5, 4), (11, 11, 4, 5)):
+            c[cx, 1:h + 1, cz] = m                                                # Pillar
+        xs, zs = np.meshgrid(np.arange(6, 10), np.arange(6, 10), indexing="ij")
+        c[6:10, 1, 6:10] = np.where((xs + zs) % 2 == 0, 1, 4)                     # checker inlay
+        return c
+    c = np.zeros((14, 7, 14), np.int32)
+    xs, zs = np.meshgrid(np.arange(14), np.arange(14), indexing="ij")
+    c[:, 0, :] = np.where((xs + zs) % 2 == 0, 6, 7)
+    for i in range(2, 12, 3):
+        c[i, 1:4, 2] = 2
+        c[i, 1:4, 11] = 3
+    return c
+
+
+def test_museum_scene_matches_the_reference_source():
+    """TestScenes.BuildTestScene -- entry 0 of the engine's scene table (RaytraceEntity.cs:325): 62 objects in order (three Cornell
+    rooms, the mesh gallery with MeshLoader.FromObj at scale 3 / 3 / 2, pedestals, a triangle, a textured sphere and wall, two
+    voxel dioramas with their own `switch (id)` palettes, the teapot on its stand) and 6 lights, against the values
+    tools/extract_scene_literals.py gets by executing the C# text.  The video exhibits need Assets/TestVideo.mp4 (absent) and the
+    dragon its asset (absent): skipped, exactly as the reference skips them."""
+    import json
+    from test_mesh_loader_literal import read_ymesh, normalize_all_used
+    from conftest import GOLDEN
+    gold = json.load(open(os.path.join(GOLDEN, "scene_literals.json")))["museum"]
+    s = api.HostScene("museum")
+    flat = s.flat.contents
+    f32 = lambda x: float(np.float32(x))
+    F = np.float32
+    assert [f32(v) for v in flat.bg_top] == gold["bg_top"] and [f32(v) for v in flat.bg_bottom] == gold["bg_bottom"]
+    assert [f32(v) for v in flat.ambient_color] == gold["ambient"]["color"] and f32(flat.ambient_intensity) == gold["ambient"]["intensity"]
+    assert list(s.default_camera()[0]) == gold["camera"]
+    assert flat.n_lights == len(gold["lights"]) == 6
+    for i, l in enumerate(gold["lights"]):
+        assert ([f32(v) for v in flat.lights[i].pos], [f32(v) for v in flat.lights[i].color], f32(flat.lights[i].intensity)) == (l["pos"], l["color"], l["intensity"]), ("light", i)
+    assert flat.n_objects == len(gold["objects"]) == 62
+
+    def mat(m):
+        return dict(albedo=[f32(v) for v in m.albedo], specular=f32(m.specular), reflectivity=f32(m.reflectivity), emission=[f32(v) for v in m.emission],
+                    transparency=f32(m.transparency), ior=f32(m.ior), tint=[f32(v) for v in m.transmission], textured=m.tex_id >= 0, tex_weight=f32(m.tex_weight),
+                    uv_scale=f32(m.uv_scale))
+
+    n_mesh = n_vol = 0
+    for i, g in enumerate(gold["objects"]):
+        o = flat.objects[i]
+        if g["kind"] == "mesh":
+            assert o.kind == 9 and o.ref_id == n_mesh, (i, "mesh id")
+            assert mat(s.mesh(n_mesh).contents.material) == g["material"], (i, g["asset"])
+            xyz, faces = read_ymesh(os.path.join(GOLDEN, "meshes", g["asset"].replace(".obj", ".ymesh")))
+            pos = ((normalize_all_used(xyz, faces) * F(g["scale"])).astype(F) + np.array(g["translate"], F)).astype(F)   # MeshLoader.cs:62-68
+            tris = np.concatenate([pos[faces[:, 0]], pos[faces[:, 1]], pos[faces[:, 2]]], axis=1)
+            got = s.mesh_triangles(n_mesh)
+            assert got.shape == tris.shape and np.array_equal(got.view(np.uint32), tris.view(np.uint32)), (i, g["asset"])
+            n_mesh += 1
+            continue
+        if g["kind"] == "volume":
+            assert o.kind == 10 and o.ref_id == n_vol, (i, "volume id")
+            v = s.volume(n_vol).contents
+            cells = diorama_cells(g["cells"])
+            assert (v.nx, v.ny, v.nz) == cells.shape and [f32(x) for x in v.min_corner] == g["min_corner"] and [f32(x) for x in v.voxel_size] == g["voxel_size"]
+            assert (v.wireframe, f32(v.wire_width_frac), v.wire_max_distance) == (1, f32(0.06), 16.0)            # VolumeGrid ctor defaults
+            nbx, nby, nbz = (v.nx + 7) // 8, (v.ny + 7) // 8, (v.nz + 7) // 8
+            ix, iy, iz = np.meshgrid(np.arange(v.nx), np.arange(v.ny), np.arange(v.nz), indexing="ij")
+            lx, ly, lz = ix & 7, iy & 7, iz & 7
+            morton = ((lx & 1) << 0) | ((ly & 1) << 1) | ((lz & 1) << 2) | ((lx & 2) << 2) | ((ly & 2) << 3) | ((lz & 2) << 4) | ((lx & 4) << 4) | ((ly & 4) << 5) | ((lz & 4) << 6)
+            at = ((((iz >> 3) * nby) + (iy >> 3)) * nbx + (ix >> 3)) * 512 + morton                           # VolumeGrid.IndexOf :235-252
+            want = np.zeros(nbx * nby * nbz * 512, np.int32)
+            want[at.ravel()] = cells.ravel()
+            assert np.array_equal(np.ctypeslib.as_array(v.mat, (want.size,)), want), (i, "cells")
+            assert not np.ctypeslib.as_array(v.meta, (want.size,)).any()
+            assert v.palette_meta_levels == 1 and mat(flat.materials[v.palette_default]) == g["lookup"]["default"]
+            for bid in range(v.palette_n_ids):                                                                 # the `switch (id)` lookup
+                assert mat(flat.materials[v.palette[bid]]) == g["lookup"].get(str(bid), g["lookup"]["default"]), (i, "block id", bid)
+            assert max(int(k) for k in g["lookup"] if k != "default") < v.palette_n_ids
+            n_vol += 1
+            continue
+        assert o.kind == KIND[g["kind"]], (i, g["kind"])
+        assert [f32(x) for x in o.p[0:N_PARAMS[g["kind"]]]] == g["p"], (i, g["kind"], "constructor values")
+        assert f32(o.checker_scale) == g["checker_scale"] and bool(o.override_sr) == g["override_sr"], (i, "material function")
+        assert mat(flat.materials[o.mat_a]) == g["a"], (i, "material a")
+        assert mat(flat.materials[o.mat_b]) == g["b"], (i, "material b")
+        if g["override_sr"]:
+            assert (f32(o.specular), f32(o.reflectivity)) == (g["specular"], g["reflectivity"]), (i, "Specular / Reflectivity override")
+    assert (n_mesh, n_vol) == (s.n_meshes, s.n_volumes) == (4, 2)
+    assert s.n_textures == 2                                                      # new Texture(texPath) twice (:103, :109)
+    s.close()
+
+
 def test_voxel_palette_matches_the_reference_source():
     """VoxelMaterialPalette.MaterialLookup (Scenes/VoxelMaterialPalette.cs:8-98) crosses the C ABI as a table (ycge_volume.palette);
     every (block id, meta) of the mirror's table against the lookup evaluated from the C# switch statements by

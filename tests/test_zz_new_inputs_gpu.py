@@ -24,6 +24,10 @@ NEW_SCENES = [  # scene, fb_w, fb_h, ss, frames, pose
     ("voxel_island:64x128", 48, 14, 4, 2, None),   # the reference's own generator (GenerateAndSaveWorld) on a small world
     ("all_meshes:40x10", 64, 18, 2, 2, None),       # BuildAllMeshesScene: four meshes with their own materials in one scene
     ("all_meshes:40x10", 48, 14, 3, 2, ((0.5, 1.6, -1.0), 0.3, -0.25)),
+    ("museum", 64, 18, 2, 2, None),                                           # TestScenes.BuildTestScene from its entrance
+    ("museum", 48, 14, 2, 2, ((9.0, 3.0, -35.5), 0.0, -0.35)),                # the mesh gallery
+    ("museum", 48, 14, 2, 2, ((5.5, 2.6, -84.5), 1.45, -0.3)),                # voxel diorama B: 14 x 7 x 14 cells (partial 8^3 bricks), teapot
+    ("museum", 40, 12, 3, 2, ((-1.6, 1.0, -7.5), 0.0, -0.1)),                 # the textured sphere (U = V = 0) and the textured end wall
 ]
 
 

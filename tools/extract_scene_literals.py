@@ -29,6 +29,16 @@ class Vec3:
     def __init__(self, x, y, z):
         self.v = [f32(x), f32(y), f32(z)]  # Vec3(double, double, double) casts each component to float (Vec3.cs:21-26)
 
+    X = property(lambda self: F(self.v[0]))
+    Y = property(lambda self: F(self.v[1]))
+    Z = property(lambda self: F(self.v[2]))
+
+    def __add__(self, o):  # Vec3.cs:31-35, component-wise binary32
+        return Vec3(F(self.v[0]) + F(o.v[0]), F(self.v[1]) + F(o.v[1]), F(self.v[2]) + F(o.v[2]))
+
+    def __sub__(self, o):  # :37-41
+        return Vec3(F(self.v[0]) - F(o.v[0]), F(self.v[1]) - F(o.v[1]), F(self.v[2]) - F(o.v[2]))
+
 
 class Material:  # Material.cs:5-61: scalars are doubles; the path reads them through (float) casts
     def __init__(self, albedo, specular, reflectivity, emission, transparency=0.0, ior=1.5, tint=None):
@@ -80,6 +90,9 @@ class Scene:
         (self.lights if o["kind"] == "light" else self.objects).append(o)
 
     def Update(self, dt):
+        pass
+
+    def RebuildBVH(self):
         pass
 
 
@@ -134,7 +147,7 @@ def to_python(stmt):
     s = re.sub(r"^(?:[\w\.]+(?:<[^=]*>)?)\s+(\w+)\s*=", r"\1 =", s)             # `Type name = ...` -> `name = ...`
     s = re.sub(r"\(\s*\w+\s*,\s*\w+\s*,\s*\w+\s*\)\s*=>\s*(\w+)", r"Constant(\1)", s)   # (pos, n, u) => capturedMaterial
     s = s.replace("ConsoleGame.Renderer.Texture", "Texture").replace("Vec3.Zero", "Vec3(0, 0, 0)").replace("new ", "")
-    s = re.sub(r'@"([^"]*)"', r'"\1"', s)
+    s = re.sub(r'@"([^"]*)"', r'r"\1"', s)
     s = re.sub(r"(?<![\w.])(\d+\.\d+|\d+)f\b", r"F(\1)", s)                        # binary32 literals
     return s
 
@@ -206,6 +219,105 @@ def all_meshes_scene(src):
         out.append(dict(asset=asset, material=mats[var], scale=f32(scale), target_pos=[f32(v.strip().rstrip("f")) for v in target.split(",")]))
     assert len(out) == 4
     return out
+
+
+def any_function_body(src, name):
+    at = re.search(r"(?:public|private) static \w+ " + name + r"\(", src).start()
+    i = src.index("{", at)
+    depth, j = 0, i
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[j], 0)
+        if depth == 0:
+            return src[i + 1:j]
+        j += 1
+
+
+def drop_guarded_blocks(body, guard):
+    """Removes `if(<guard>) { ... }` blocks: the museum's video exhibits exist only when Assets/TestVideo.mp4 does (it does not)."""
+    while True:
+        m = re.search(r"if\s*\(\s*" + guard + r"\s*\)\s*\{", body)
+        if not m:
+            return body
+        depth, j = 0, m.end() - 1
+        while True:
+            depth += {"{": 1, "}": -1}.get(body[j], 0)
+            if depth == 0:
+                break
+            j += 1
+        body = body[:m.start()] + body[j + 1:]
+
+
+def inline_material_lambdas(stmt):
+    """`(p, n, u) => new Material(...)` -> `Constant(Material(...))` (the lambda ignores its arguments)."""
+    while True:
+        m = re.search(r"\(\s*\w+\s*,\s*\w+\s*,\s*\w+\s*\)\s*=>\s*new Material\(", stmt)
+        if not m:
+            return stmt
+        depth, j = 0, m.end() - 1
+        while True:
+            depth += {"(": 1, ")": -1}.get(stmt[j], 0)
+            if depth == 0:
+                break
+            j += 1
+        stmt = stmt[:m.start()] + "Constant(new Material(" + stmt[m.end():j + 1] + ")" + stmt[j + 1:]
+
+
+def run_statements(body, ns):
+    """Straight-line C# (declarations, calls, nested plain blocks) executed statement by statement; log / timing calls dropped."""
+    body = re.sub(r"//[^\n]*", "", body).replace("{", " ").replace("}", " ")
+    for stmt in body.split(";"):
+        st = stmt.strip()
+        if not st or re.match(r"(Console\.|Stopwatch |\w*[sS]w\.)", st):
+            continue
+        py = to_python(inline_material_lambdas(st))
+        if py:
+            exec(py, ns)
+
+
+def museum_scene(src):
+    """TestScenes.BuildTestScene (TestScenes.cs:16-159) with AddCornellBoxRoom (:161-213), TryAddMeshAutoGround (:363-379) and the
+    statements of the two voxel dioramas after their cell loops (:256-277, :310-330), all executed from the source text.  The cell
+    loops themselves are compared separately (tests/test_host.py re-states them in numpy); the `switch (id)` material lookups are
+    parsed case by case."""
+    s, base = Scene(), {}
+    meshes_present = {"cow.obj", "stanford-bunny.obj", "teapot.obj"}  # the assets shipped with the reference; the dragon is not
+
+    def try_add_mesh(scene, path, mat, scale, target):
+        asset = path.replace("\\", "/").split("/")[-1]
+        if asset not in meshes_present:
+            return
+        y = F(F(target.Y + F(0.5)) + F(0.01))
+        scene.Add(dict(kind="mesh", asset=asset, material=mat.dump(), scale=f32(scale), translate=[f32(target.X), f32(y), f32(target.Z)]))
+
+    def room(scene, anchor, width, height, left, right, white, power, emissive):
+        ns = dict(NS, s=scene, anchor=anchor, width=F(width), height=F(height), leftColor=left, rightColor=right, whiteColor=white, lightPower=F(power), emissive=emissive)
+        run_statements(any_function_body(src, "AddCornellBoxRoom"), ns)
+
+    def diorama(name):
+        def build(scene, min_corner, *mats):
+            body = any_function_body(src, name)
+            params = re.search(name + r"\(Scene s, Vec3 minCorner, ([^)]*)\)", src).group(1)
+            ns = dict(base, s=scene, minCorner=min_corner, cells=name, **{p.split()[-1]: m for p, m in zip(params.split(","), mats)})
+            lookup_src = body[body.index("Func<int, int, Material> materialLookup"):]
+            lookup_src = lookup_src[:lookup_src.index("};") + 2]
+            table = {}
+            for key, expr in re.findall(r"(case \d+|default):\s*return ([^;]+);", lookup_src):
+                exec("_m = " + to_python(expr.strip() + " "), ns)
+                table["default" if key == "default" else key.split()[1]] = ns["_m"].dump()
+            ns["materialLookup"] = table
+            tail = body[body.index("Vec3 voxelSize"):].replace(lookup_src, "")
+            run_statements(tail, ns)
+        return build
+
+    base.update(NS, TryAddMeshAutoGround=try_add_mesh,
+                VolumeGrid=lambda cells, mn, size, lookup: dict(kind="volume", cells=cells, min_corner=mn.v, voxel_size=size.v, lookup=lookup))
+    ns = dict(base, s=s, AddCornellBoxRoom=room, BuildVolumeDioramaA=diorama("BuildVolumeDioramaA"), BuildVolumeDioramaB=diorama("BuildVolumeDioramaB"),
+              BuildVideoDiorama=lambda *a: None)
+    body = drop_guarded_blocks(any_function_body(src, "BuildTestScene"), r'File\.Exists\("Assets/TestVideo\.mp4"\)')
+    run_statements(body, ns)
+    s = ns["s"]  # `Scene s = new Scene();` is the factory's first statement
+    return dict(ambient=s.Ambient, bg_top=s.BackgroundTop.v, bg_bottom=s.BackgroundBottom.v, camera=s.DefaultCameraPos.v,
+                lights=[{k: v for k, v in l.items() if k != "kind"} for l in s.lights], objects=s.objects)
 
 
 def renderer_constants(ref):
@@ -295,6 +407,7 @@ if __name__ == "__main__":
     out["mesh_base"] = extract(msrc, "NewBaseScene")
     out["mesh_scenes"] = mesh_scene_materials(msrc)
     out["all_meshes"] = all_meshes_scene(msrc)
+    out["museum"] = museum_scene(open(os.path.join(ref, "RayTracing", "Scenes", "TestScenes.cs"), encoding="utf-8-sig").read())
     out["params"] = renderer_constants(ref)
     out["voxel_palette"] = voxel_palette(ref)
     out["tables"] = tables(ref)

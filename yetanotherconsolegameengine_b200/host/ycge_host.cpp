@@ -747,6 +747,139 @@ std::shared_ptr<Scene> BuildAllMeshesScene(int knotU, int knotV) {
 }
 } // namespace MeshScenes
 
+// ---- Scenes/TestScenes.cs: the "museum", entry 0 of the engine's scene table (RaytraceEntity.cs:325) -------------------------
+namespace TestScenes {
+static void TryAddMeshAutoGround(Scene &s, const std::string &file, Material mat, float scale, Vec3 targetPos) { // :363-379: no auto-ground at all
+    const std::string path = MeshScenes::AssetDir + "/" + file; // File.Exists; the committed binary twin (.ymesh) of an asset counts as the asset
+    if (!std::ifstream(path).good() && !std::ifstream(path.substr(0, path.rfind('.')) + ".ymesh").good()) return; // "Mesh file missing, skipped" :367-372
+    float yTranslate = targetPos.Y + 0.5f + 0.01f;
+    s.Objects.push_back(MeshLoader::FromObj(MeshScenes::AssetDir + "/" + file, mat, scale, Vec3(targetPos.X, yTranslate, targetPos.Z)));
+}
+static void AddCornellBoxRoom(Scene &s, Vec3 anchor, float width, float height, Vec3 leftColor, Vec3 rightColor, Vec3 whiteColor, float lightPower, Material emissive) { // :161-213
+    float xL = anchor.X - width, xR = anchor.X - width * 0.0f, yB = anchor.Y + 0.0f, yT = anchor.Y + height, zB = anchor.Z - width, zF = anchor.Z + 0.0f;
+    MaterialFunc white = Solid(whiteColor), leftWall = Solid(leftColor), rightWall = Solid(rightColor);
+    s.Add(YZRect(yB, yT, zB, zF, xL, leftWall, 0.0f, 0.0f));
+    s.Add(YZRect(yB, yT, zB, zF, xR, rightWall, 0.0f, 0.0f));
+    s.Add(XZRect(xL, xR, zB, zF, yB, white, 0.0f, 0.0f));
+    s.Add(XZRect(xL, xR, zB, zF, yT, white, 0.0f, 0.0f));
+    s.Add(XYRect(xL, xR, yB, yT, zB, white, 0.0f, 0.0f));
+    float lx0 = xL + 0.20f * width, lx1 = xR - 0.20f * width, lz0 = zB + 0.35f * width, lz1 = zB + 0.55f * width, ly = yT - 0.01f;
+    s.Add(XZRect(lx0, lx1, lz0, lz1, ly, Constant(emissive), 0.0f, 0.0f));
+    s.Lights.push_back(PointLight(Vec3((lx0 + lx1) * 0.5f, yT - 0.2f, (lz0 + lz1) * 0.5f), Vec3(1.0f, 0.98f, 0.95f), lightPower));
+    float cx = (xL + xR) * 0.5f, cz = (zB + zF) * 0.5f;
+    Material ped(Vec3(0.88, 0.88, 0.88), 0.00, 0.00, Vec3()), objA(Vec3(0.90, 0.20, 0.20), 0.08, 0.02, Vec3()), objB(Vec3(0.20, 0.80, 0.95), 0.10, 0.06, Vec3());
+    Material mirrorish(Vec3(0.98, 0.98, 0.98), 0.0, 0.85, Vec3()), glassish(Vec3(1.0, 1.0, 1.0), 0.0, 0.02, Vec3(), 1.0, 1.5, Vec3(1.0, 1.0, 1.0));
+    Vec3 stand0(cx - 0.8f, yB, cz + 0.2f), stand1(cx + 0.8f, yB, cz - 0.2f);
+    s.Add(std::make_shared<Disk>(Vec3(cx, yB + 0.01f, cz), Vec3(0.0f, 1.0f, 0.0f), width * 0.32f, Solid(Vec3(0.90f, 0.90f, 0.92f)), 0.0f, 0.0f));
+    s.Add(std::make_shared<CylinderY>(stand0, 0.28f, 0.0f, 0.9f, true, ped));
+    s.Add(std::make_shared<Sphere>(stand0 + Vec3(0.0f, 0.9f + 0.35f, 0.0f), 0.35f, mirrorish));
+    s.Add(std::make_shared<CylinderY>(stand1, 0.28f, 0.0f, 0.9f, true, ped));
+    s.Add(std::make_shared<Sphere>(stand1 + Vec3(0.0f, 0.9f + 0.32f, 0.0f), 0.32f, glassish));
+    s.Add(std::make_shared<Sphere>(Vec3(cx, yB + 0.35f, cz - 0.9f), 0.35f, objA));
+    s.Add(std::make_shared<Sphere>(Vec3(cx, yB + 0.22f, cz + 0.9f), 0.22f, objB));
+}
+// a voxel palette from a `switch (id)` lookup (:258-269, :312-323): `byId[id]` or the default; meta ignored
+static std::shared_ptr<VoxelPalette> SwitchPalette(int nIds, Material def, std::initializer_list<std::pair<int, Material>> byId) {
+    auto pal = std::make_shared<VoxelPalette>();
+    pal->n_ids = nIds; pal->meta_levels = 1; pal->def = 0;
+    pal->materials.push_back(def);
+    pal->table.assign((size_t)nIds, 0);
+    for (auto &kv : byId) { pal->materials.push_back(kv.second); pal->table[(size_t)kv.first] = (int)pal->materials.size() - 1; }
+    return pal;
+}
+static void BuildVolumeDioramaA(Scene &s, Vec3 minCorner, Material red, Material green, Material blue, Material mirror, Material glassClear, Material pedestal) { // :215-278
+    const int nx = 16, ny = 8, nz = 16;
+    std::vector<int> cm((size_t)nx * ny * nz, 0);
+    auto at = [&](int x, int y, int z) { return ((size_t)x * ny + y) * nz + z; };
+    for (int x = 0; x < nx; x++) for (int z = 0; z < nz; z++) cm[at(x, 0, z)] = 1;
+    for (int y = 1; y <= 3; y++) {
+        for (int x = 0; x < nx; x++) { cm[at(x, y, 0)] = 1; cm[at(x, y, nz - 1)] = 1; }
+        for (int z = 0; z < nz; z++) { cm[at(0, y, z)] = 1; cm[at(nx - 1, y, z)] = 1; }
+    }
+    auto Pillar = [&](int cx, int cz, int height, int m) { for (int y = 1; y <= height && y < ny; y++) cm[at(cx, y, cz)] = m; };
+    Pillar(4, 4, 4, 2); Pillar(11, 4, 3, 3); Pillar(4, 11, 5, 4); Pillar(11, 11, 4, 5);
+    for (int x = 6; x <= 9; x++) for (int z = 6; z <= 9; z++) cm[at(x, 1, z)] = ((x + z) & 1) == 0 ? 1 : 4;
+    auto pal = SwitchPalette(6, Material(Vec3(0.7, 0.7, 0.7), 0.0, 0.0, Vec3()),
+                             {{1, Material(Vec3(0.82, 0.82, 0.85), 0.0, 0.0, Vec3())}, {2, red}, {3, green}, {4, blue}, {5, mirror}});
+    s.Add(std::make_shared<VolumeGrid>(nx, ny, nz, [&](int x, int y, int z, int &m, int &e) { m = cm[at(x, y, z)]; e = 0; }, minCorner, Vec3(0.5, 0.5, 0.5), pal));
+    Vec3 pedC = minCorner + Vec3(4.0f, 0.0f, 2.0f);
+    s.Add(std::make_shared<CylinderY>(pedC, 0.35f, 0.0f, 1.4f, true, pedestal));
+    s.Add(std::make_shared<Sphere>(pedC + Vec3(0.0f, 1.4f + 0.45f, 0.0f), 0.45f, glassClear));
+    s.Lights.push_back(PointLight(minCorner + Vec3(4.0f, 3.0f, 1.0f), Vec3(0.9f, 0.95f, 1.0f), 110.0f));
+}
+static void BuildVolumeDioramaB(Scene &s, Vec3 minCorner, Material red, Material green, Material blue, Material gold, Material pedestal) { // :280-331
+    const int nx = 14, ny = 7, nz = 14;
+    std::vector<int> cm((size_t)nx * ny * nz, 0);
+    auto at = [&](int x, int y, int z) { return ((size_t)x * ny + y) * nz + z; };
+    for (int x = 0; x < nx; x++) for (int z = 0; z < nz; z++) cm[at(x, 0, z)] = ((x + z) & 1) == 0 ? 6 : 7;
+    for (int i = 2; i < nx - 2; i += 3) for (int y = 1; y <= 3 && y < ny; y++) { cm[at(i, y, 2)] = 2; cm[at(i, y, nz - 3)] = 3; }
+    auto pal = SwitchPalette(8, Material(Vec3(0.7, 0.7, 0.7), 0.0, 0.0, Vec3()),
+                             {{2, red}, {3, green}, {4, blue}, {6, Material(Vec3(0.80, 0.80, 0.82), 0.0, 0.0, Vec3())}, {7, Material(Vec3(0.15, 0.15, 0.18), 0.0, 0.0, Vec3())}});
+    s.Add(std::make_shared<VolumeGrid>(nx, ny, nz, [&](int x, int y, int z, int &m, int &e) { m = cm[at(x, y, z)]; e = 0; }, minCorner, Vec3(0.45, 0.45, 0.45), pal));
+    Vec3 stand = minCorner + Vec3(3.0f, 0.0f, 6.0f);
+    s.Add(std::make_shared<CylinderY>(stand, 0.30f, 0.0f, 1.1f, true, pedestal));
+    TryAddMeshAutoGround(s, "teapot.obj", gold, 1.0f, stand + Vec3(0.0f, 1.12f, 0.0f));
+    s.Lights.push_back(PointLight(minCorner + Vec3(2.5f, 2.8f, 7.0f), Vec3(1.0f, 0.95f, 0.9f), 85.0f));
+}
+// BuildTestScene :16-159.  The two blocks guarded by File.Exists("Assets/TestVideo.mp4") (:120-132 and BuildVideoDiorama :333-361)
+// are video-textured (dynamic textures: out of scope) and absent from the distributed checkout: not built.
+std::shared_ptr<Scene> BuildTestScene() {
+    auto sp = std::make_shared<Scene>(); Scene &s = *sp; s.Name = "museum";
+    s.Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.06f);
+    s.Add(std::make_shared<Plane>(Vec3(0.0f, 0.0f, 0.0f), Vec3(0.0f, 1.0f, 0.0f), Checker(Vec3(0.82f, 0.82f, 0.85f), Vec3(0.12f, 0.12f, 0.12f), 0.8f), 0.02f, 0.00f));
+    s.Add(std::make_shared<Plane>(Vec3(0.0f, 0.0f, -100.0f), Vec3(0.0f, 0.0f, 1.0f), Constant(Material(Vec3(0.02, 0.02, 0.03), 0.0, 0.0, Vec3())), 0.0f, 0.0f));
+    Material mirror(Vec3(0.98, 0.98, 0.98), 0.0, 0.90, Vec3()), red(Vec3(0.95, 0.15, 0.15), 0.08, 0.02, Vec3()), green(Vec3(0.15, 0.95, 0.20), 0.06, 0.02, Vec3());
+    Material blue(Vec3(0.15, 0.25, 0.95), 0.06, 0.02, Vec3()), gold(Vec3(1.00, 0.85, 0.57), 0.25, 0.10, Vec3()), brass(Vec3(0.78, 0.60, 0.20), 0.18, 0.06, Vec3());
+    Material pedestal(Vec3(0.85, 0.85, 0.85), 0.00, 0.00, Vec3());
+    Material glassClear(Vec3(1.0, 1.0, 1.0), 0.0, 0.02, Vec3(), 1.0, 1.5, Vec3(1.0, 1.0, 1.0)), glassBlue(Vec3(0.9, 0.95, 1.0), 0.0, 0.02, Vec3(), 1.0, 1.52, Vec3(0.9, 0.95, 1.0));
+    Material emissiveSoft(Vec3(0.0, 0.0, 0.0), 0.0, 0.0, Vec3(4.0, 4.0, 4.0));
+    float cornellW = 6.0f;
+    Vec3 cornellAnchorA(-9.0f, 0.0f, -12.0f), cornellAnchorB(9.0f, 0.0f, -28.0f), cornellAnchorC(-9.0f, 0.0f, -48.0f);
+    Vec3 meshGalleryAnchor(9.0f, 0.0f, -40.0f), pedestalQuadAnchor(-8.6f, 0.0f, -30.0f), volumeAnchorA(-9.0f, 0.0f, -72.0f), volumeAnchorB(9.0f, 0.0f, -88.0f);
+    AddCornellBoxRoom(s, cornellAnchorA, cornellW, 5.0f, Vec3(0.80, 0.10, 0.10), Vec3(0.10, 0.80, 0.10), Vec3(0.82, 0.82, 0.82), 65.0f, emissiveSoft);
+    AddCornellBoxRoom(s, cornellAnchorB, cornellW, 5.0f, Vec3(0.70, 0.10, 0.70), Vec3(0.10, 0.70, 0.70), Vec3(0.82, 0.82, 0.82), 75.0f, emissiveSoft);
+    AddCornellBoxRoom(s, cornellAnchorC, cornellW, 5.0f, Vec3(0.80, 0.20, 0.10), Vec3(0.20, 0.80, 0.10), Vec3(0.90, 0.90, 0.90), 90.0f, emissiveSoft);
+    TryAddMeshAutoGround(s, "cow.obj", gold, 3.0f, meshGalleryAnchor + Vec3(-2.6f, 1.0f, -0.4f));
+    TryAddMeshAutoGround(s, "stanford-bunny.obj", green, 3.0f, meshGalleryAnchor + Vec3(0.0f, 1.0f, 0.0f));
+    TryAddMeshAutoGround(s, "teapot.obj", red, 2.0f, meshGalleryAnchor + Vec3(2.6f, 1.0f, 0.4f));
+    TryAddMeshAutoGround(s, "xyzrgb_dragon.obj", mirror, 8.0f, meshGalleryAnchor + Vec3(5.2f, 2.0f, -0.8f));
+    s.Add(std::make_shared<Disk>(meshGalleryAnchor + Vec3(2.6f, 0.01f, 0.4f), Vec3(0.0f, 1.0f, 0.0f), 0.9f, Solid(Vec3(0.85, 0.85, 0.1)), 0.0f, 0.0f));
+    {
+        float pedH = 1.2f, sphR = 0.35f;
+        Vec3 baseC = pedestalQuadAnchor, dx(1.8f, 0.0f, 0.0f), dz(0.0f, 0.0f, -1.8f);
+        Vec3 p0 = baseC, p1 = baseC + dx, p2 = baseC + dz, p3 = baseC + dx + dz;
+        for (Vec3 p : {p0, p1, p2, p3}) s.Add(std::make_shared<CylinderY>(p, 0.32f, 0.0f, pedH, true, pedestal));
+        s.Add(std::make_shared<Sphere>(p0 + Vec3(0.0f, pedH + sphR, 0.0f), sphR, mirror));
+        s.Add(std::make_shared<Sphere>(p1 + Vec3(0.0f, pedH + sphR, 0.0f), sphR, glassBlue));
+        s.Add(std::make_shared<Sphere>(p2 + Vec3(0.0f, pedH + sphR, 0.0f), sphR, red));
+        s.Add(std::make_shared<Sphere>(p3 + Vec3(0.0f, pedH + sphR, 0.0f), sphR, blue));
+    }
+    s.Add(std::make_shared<Triangle>(Vec3(2.2f, 0.0f, -6.0f), Vec3(2.8f, 1.2f, -6.4f), Vec3(1.6f, 0.7f, -6.8f), brass));
+    {
+        auto load = [&]() -> std::shared_ptr<Texture> { // new Texture(@"assets\image.png"), twice (:103, :109)
+            std::ifstream probe(MeshScenes::AssetDir + "/image.png");
+            if (probe.good()) return std::make_shared<Texture>(MeshScenes::AssetDir + "/image.png");
+            s.Name = "museum-standin";
+            return std::make_shared<Texture>(Texture::Procedural(96, 144));
+        };
+        Material textured(Vec3(1.0, 1.0, 1.0), 0.05, 0.02, Vec3());
+        textured.DiffuseTexture = s.AddTexture(load()); textured.TextureWeight = 1.0; textured.UVScale = 1.5;
+        s.Add(std::make_shared<Sphere>(Vec3(-1.6f, 0.6f, -10.0f), 0.6f, textured));
+        Material texMat(Vec3(1.0, 1.0, 1.0), 0.02, 0.00, Vec3());
+        texMat.DiffuseTexture = s.AddTexture(load()); texMat.TextureWeight = 1.0; texMat.UVScale = 0.35;
+        s.Add(std::make_shared<Plane>(Vec3(0.0f, 0.0f, -98.0f), Vec3(0.0f, 0.0f, 1.0f), Constant(texMat), 0.02f, 0.00f));
+    }
+    BuildVolumeDioramaA(s, volumeAnchorA, red, green, blue, mirror, glassClear, pedestal);
+    BuildVolumeDioramaB(s, volumeAnchorB, red, green, blue, gold, pedestal);
+    s.Lights.push_back(PointLight(Vec3(0.0f, 12.0f, -50.0f), Vec3(1.0f, 1.0f, 1.0f), 900.0f));
+    s.BackgroundTop = Vec3(0.06, 0.08, 0.10); s.BackgroundBottom = Vec3(0.01, 0.01, 0.02);
+    s.DefaultCameraPos = Vec3(0.0, 1.7, 2.5);
+    s.ResetCamera();
+    s.RebuildBVH();
+    return sp;
+}
+} // namespace TestScenes
+
 // ---- the island generator the reference pre-generates its voxel world with -------------------------------------------
 // WorldManager.GenerateAndSaveWorld (Scenes/WorldGeneration/WorldManager.cs:510-631) restated: global heights, the D8 "river"
 // pass, slope / biome / inland water, strata fill, global flora.  All arithmetic is binary32 in the reference's operation
@@ -1287,6 +1420,7 @@ void WriteIslandWorldFile(const std::string &path, int worldSize, int worldHeigh
 } // namespace VolumeScenes
 
 std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
+    if (name == "museum") return TestScenes::BuildTestScene();
     if (name == "test") return Scenes::BuildTestScene();
     if (name == "cornell") return Scenes::BuildCornellBox();
     if (name == "mirror_spheres") return Scenes::BuildMirrorSpheresOnChecker();

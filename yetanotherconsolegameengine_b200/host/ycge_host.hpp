@@ -265,6 +265,9 @@ std::shared_ptr<Scene> BuildVolumeGridTestScene();
 std::shared_ptr<Scene> BuildTextureTestScene(); // assets/image.png if present, else a procedural stand-in (labelled in Scene::Name)
 std::shared_ptr<Scene> BuildTextureGallery();   // NOT in the reference: every primitive kind that carries U,V, textured (tests)
 } // namespace Scenes
+namespace TestScenes { // Scenes/TestScenes.cs
+std::shared_ptr<Scene> BuildTestScene(); // the "museum": three Cornell rooms, a mesh gallery, pedestals, textures, two voxel dioramas
+} // namespace TestScenes
 namespace MeshScenes { // Scenes/MeshScenes.cs
 extern std::string AssetDir; // where cow.obj / stanford-bunny.obj / teapot.obj / xyzrgb_dragon.obj are looked up
 std::shared_ptr<Scene> BuildCowScene();
