@@ -220,6 +220,49 @@ def test_day_night_entity_matches_a_literal_transcription():
     t.close()
 
 
+@pytest.mark.parametrize("name", ["voxel_island:64x128", "voxel_island:96x128", "voxel_island:128x256"])
+def test_island_camera_placement_rule(name):
+    """VolumeScene.PlaceCameraOnSurfaceXZ(0, 0) (VolumeScenes.cs:547-558, TrySampleGroundYFan :478-518, TrySampleGroundY :520-531):
+    five rays straight down from min(WorldHeight + 16, 4096), at the spot and 0.35 to each side, then a selection rule.  The mirror
+    evaluates the rule on voxel columns.  Here the five rays are cast through the oracle's Scene.Hit (tMin 1e-5, tMax start + 8),
+    nudged 1e-3 off the cell boundary, and the rule is applied to the hits in double precision.
+
+    Not reproduced (divergences): with x = 0 or z = 0 EXACTLY, as the reference casts them, four of the five
+    rays run along a chunk boundary, (min - origin) * (1 / 0) is NaN in the slab tests, and what they hit is an accident of NaN
+    comparisons (asserted below: they land on lower chunks or miss the world, unless 0 is not a chunk face).  The default pose is harness input -- the GPU
+    and the oracle receive the same one -- so parity does not depend on it."""
+    s = api.HostScene(name)
+    H = int(name.rsplit("x", 1)[1])
+    o = Oracle(s, 8, 4, 1)
+    F = np.float32
+    start = float(min(F(H) + F(16.0), F(4096.0)))
+    r, nudge = float(F(0.35)), 1e-3
+    offs = ((0.0, 0.0), (r, 0.0), (-r, 0.0), (0.0, r), (0.0, -r))
+    rays = [[ox + nudge, start, oz + nudge, 0.0, -1.0, 0.0] for ox, oz in offs]
+    t, ids, _ = o.scene_hit(rays, tmin=float(F(0.00001)), tmax=float(F(start + 8.0)))
+    cam_y, eye, clear, guard = 120.0, float(F(1.7)), float(F(0.10)), float(F(0.05))
+    ground, best, any_hit, any_ok = -np.inf, -np.inf, False, False
+    for ray, tt, idd in zip(rays, t, ids):
+        if idd[0] < 0:
+            continue
+        y = float(F(F(ray[1]) + F(F(tt) * F(-1.0))))                              # Ray.At: Origin + Dir * t in binary32 (Ray.cs)
+        any_hit = True
+        if y + eye + clear <= cam_y + guard:
+            best = y if (not any_ok or y > best) else best
+            any_ok = True
+        if not any_ok and y > ground:
+            ground = y
+    assert any_hit
+    g = best if any_ok else ground
+    assert s.default_camera()[0] == (0.0, float(F(g + eye + clear)), 0.0)
+    exact = [[ox, start, oz, 0.0, -1.0, 0.0] for ox, oz in offs]
+    t_exact, _, _ = o.scene_hit(exact, tmin=float(F(0.00001)), tmax=float(F(start + 8.0)))
+    on_chunk_boundary = (int(name.split(":")[1].split("x")[0]) // 2) % 32 == 0
+    assert (not np.array_equal(t_exact, t)) == on_chunk_boundary, "exact-boundary probes go astray exactly where x = 0 / z = 0 is a chunk face"
+    o.close()
+    s.close()
+
+
 def test_texture_test_scene_and_png_decoder(tmp_path):
     """BuildTextureTestScene (Scenes.cs:337-358): one textured box, ambient 0.5, no lights.  new Texture(path) decodes through
     OpenCV in the reference (ImreadModes.Color, BGR2RGBA: Texture.cs:25-49); the mirror's zlib-only PNG decoder must give the

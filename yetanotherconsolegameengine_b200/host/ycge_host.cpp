@@ -1318,7 +1318,7 @@ static std::shared_ptr<VoxelPalette> WorldPalette() { // Scenes/VoxelMaterialPal
 // separate VolumeGrids in the top-level BVH, all-air chunks skipped (`cell.Item1 != 0`, WorldManager.cs:720), the real
 // palette, sun/moon lights of DayNightEntity at `daySeconds`.  `cellAt(wx, wy, wz, mat, meta)` supplies the voxels.
 template <class CellAt>
-static std::shared_ptr<Scene> BuildWorldFromCells(int nx, int ny, int nz, int chunkSize, float daySeconds, const std::string &name, CellAt cellAt) {
+static std::shared_ptr<Scene> BuildWorldFromCells(int nx, int ny, int nz, int chunkSize, float daySeconds, const std::string &name, bool fanPlacement, CellAt cellAt) {
     auto s = std::make_shared<Scene>(); s->Name = name; s->IsVolumeScene = true;
     s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.0f);
     auto pal = WorldPalette();
@@ -1339,10 +1339,38 @@ static std::shared_ptr<Scene> BuildWorldFromCells(int nx, int ny, int nz, int ch
     // DayNightEntity(cycleSeconds: 120, sunRadius: 2000) (VolumeScenes.cs:599-602), advanced to time = daySeconds
     s->Entities.push_back(std::make_shared<DayNightEntity>(120.0f, 2000.0f));
     s->Entities.back()->Update(daySeconds, *s);
-    // camera: standing on the highest non-air voxel of the centre column
-    int top = 0;
-    for (int wy = ny - 1; wy >= 0; wy--) { int m, e; cellAt(nx / 2, wy, nz / 2, m, e); if (m != 0) { top = wy; break; } }
-    s->DefaultCameraPos = Vec3(0.0f, (float)top + 1.0f + 1.8f, 0.0f);
+    auto columnTop = [&](int cx, int cz) { // y of the top face of the highest non-air voxel of a column, -1 when the column is empty
+        for (int wy = ny - 1; wy >= 0; wy--) { int m, e; cellAt(cx, wy, cz, m, e); if (m != 0) return wy + 1; }
+        return -1;
+    };
+    if (!fanPlacement) { // the synthetic world: standing on the centre column
+        s->DefaultCameraPos = Vec3(0.0f, (float)std::max(0, columnTop(nx / 2, nz / 2) - 1) + 1.0f + 1.8f, 0.0f);
+    } else {
+        // VolumeScene.PlaceCameraOnSurfaceXZ(0, 0) (VolumeScenes.cs:547-558) after DefaultCameraPos = (0, 120, 0) (:594): five rays
+        // straight down from y = min(WorldHeight + 16, 4096), at the spot and 0.35 to each side (TrySampleGroundYFan :478-518); the
+        // highest ground that keeps the eyes (ground + 1.7 + 0.10) at or below the current camera height + 0.05 wins, else the
+        // highest ground of all; without any hit the camera floats at WaterLevel + 1.7 + 4.  A downward ray meets the top face of
+        // the column it starts in; which column a ray ON a cell boundary (x = 0 or z = 0 exactly) belongs to follows
+        // VolumeGrid.Hit's floor((p - min) / size): the higher-index one (tests/test_host.py casts the same five rays through
+        // the oracle's Scene.Hit).
+        const double EyeHeight = 1.7f, GroundClearance = 0.10f, StepUpGuardEpsilon = 0.05f, ProbeRadius = 0.35f, camY = 120.0;
+        const double offs[5][2] = {{0.0, 0.0}, {ProbeRadius, 0.0}, {-ProbeRadius, 0.0}, {0.0, ProbeRadius}, {0.0, -ProbeRadius}};
+        double groundY = -std::numeric_limits<double>::infinity(), bestAcceptable = groundY;
+        bool anyHit = false, anyAcceptable = false;
+        for (auto &o : offs) {
+            int cx = (int)std::floor(o[0] - (double)worldMin.X), cz = (int)std::floor(o[1] - (double)worldMin.Z);
+            if (cx < 0 || cx >= nx || cz < 0 || cz >= nz) continue;
+            int topFace = columnTop(cx, cz);
+            if (topFace < 0) continue;
+            double y = (double)topFace;
+            anyHit = true;
+            if (y + EyeHeight + GroundClearance <= camY + StepUpGuardEpsilon) { if (!anyAcceptable || y > bestAcceptable) bestAcceptable = y; anyAcceptable = true; }
+            if (!anyAcceptable && y > groundY) groundY = y;
+        }
+        if (anyAcceptable) groundY = bestAcceptable;
+        if (anyHit) s->DefaultCameraPos = Vec3(0.0, groundY + EyeHeight + GroundClearance, 0.0);
+        else s->DefaultCameraPos = Vec3(0.0, (double)((float)std::max(1, ny / 4) + 1.7f + 4.0f), 0.0);
+    }
     s->DefaultYaw = 0.6f; s->DefaultPitch = -0.25f;
     s->ResetCamera();
     s->RebuildBVH();
@@ -1365,7 +1393,7 @@ static std::vector<int> SyntheticHeights(int worldSize, int worldHeight) {
 }
 std::shared_ptr<Scene> BuildSyntheticWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds) {
     std::vector<int> hmap = SyntheticHeights(worldSize, worldHeight);
-    return BuildWorldFromCells(worldSize, worldHeight, worldSize, chunkSize, daySeconds, "voxel_world_synthetic",
+    return BuildWorldFromCells(worldSize, worldHeight, worldSize, chunkSize, daySeconds, "voxel_world_synthetic", false,
                                [&](int wx, int wy, int wz, int &m, int &e) { SyntheticCell(hmap, worldSize, worldHeight, wx, wy, wz, m, e); });
 }
 // World file "VG01" (WorldManager.cs:399-440 reader, :612-629 writer): 'V','G','0','1', int32 nx, ny, nz, then
@@ -1382,7 +1410,7 @@ std::shared_ptr<Scene> BuildWorldFromFile(const std::string &path, int chunkSize
     std::vector<int32_t> cells((size_t)nx * ny * nz * 2);
     f.read((char *)cells.data(), (std::streamsize)(cells.size() * 4));
     if (!f.good()) throw std::runtime_error("Truncated world file: " + path);
-    return BuildWorldFromCells(nx, ny, nz, chunkSize, daySeconds, "voxel_world_file", [&](int wx, int wy, int wz, int &m, int &e) {
+    return BuildWorldFromCells(nx, ny, nz, chunkSize, daySeconds, "voxel_world_file", true, [&](int wx, int wy, int wz, int &m, int &e) {
         const size_t k = (((size_t)wx * ny + wy) * nz + wz) * 2;
         m = cells[k]; e = cells[k + 1];
     });
@@ -1402,7 +1430,7 @@ void WriteSyntheticWorldFile(const std::string &path, int worldSize, int worldHe
 // The reference's own world: BuildMinecraftLike (VolumeScenes.cs:569-627) generates it with seed 0 and loads it back.
 std::shared_ptr<Scene> BuildIslandWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds) {
     WorldGeneration::World w = WorldGeneration::Generate(worldSize, worldHeight, worldSize, 0);
-    return BuildWorldFromCells(worldSize, worldHeight, worldSize, chunkSize, daySeconds, "voxel_island",
+    return BuildWorldFromCells(worldSize, worldHeight, worldSize, chunkSize, daySeconds, "voxel_island", true,
                                [&](int wx, int wy, int wz, int &m, int &e) { uint8_t c = w.cells[w.at(wx, wy, wz)]; m = c & 15; e = c >> 4; });
 }
 void WriteIslandWorldFile(const std::string &path, int worldSize, int worldHeight) { // WorldManager.cs:612-629
