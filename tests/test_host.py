@@ -190,9 +190,10 @@ def test_day_night_entity_matches_a_literal_transcription():
     s = api.HostScene("voxel_world:32x32")
     t = F(45.0)
     assert len(s.lights()) == 2
-    for dt in [0.0, 1.0 / 60.0, 7.25, 20.0, 30.0, 0.016, 33.0, 100.0, -5.0]:
-        s.update(dt)
-        t = F(t + max(F(0.0), F(dt)))                                                       # :46 (negative dt ignored)
+    for ms in [0.0, 1000.0 / 60.0, 7250.0, 20000.0, 30000.0, 16.0, 33000.0, 100000.0, -5000.0]:
+        dt = F(F(ms) * F(0.001))                                                            # Scene.Update(deltaTimeMS), Scene.cs:107
+        s.update(ms)
+        t = F(t + max(F(0.0), dt))                                                          # :46 (negative dt ignored)
         t01 = F(F(libm.fmodf(t, F(120.0))) / F(120.0))
         pi = F(np.pi)
         theta = F(F(F(t01 * F(2.0)) * pi) - F(pi * F(0.5)))
@@ -216,7 +217,7 @@ def test_day_night_entity_matches_a_literal_transcription():
     s.close()
     t = api.HostScene("cornell")
     before = t.lights()
-    assert t.update(1.0) == 0 and t.lights() == before                                        # a scene without entities: nothing moves
+    assert t.update(1000.0) == (0, 1) and t.lights() == before                                # a scene without entities: nothing moves
     t.close()
 
 
@@ -260,6 +261,47 @@ def test_island_camera_placement_rule(name):
     on_chunk_boundary = (int(name.split(":")[1].split("x")[0]) // 2) % 32 == 0
     assert (not np.array_equal(t_exact, t)) == on_chunk_boundary, "exact-boundary probes go astray exactly where x = 0 / z = 0 is a chunk face"
     o.close()
+    s.close()
+
+
+def test_animated_entities_match_a_literal_transcription():
+    """BobbingSphereEntity, OrbitingLightEntity, PulsingLightEntity (Scenes/TestScenesRandom.cs:688-798) through Scene.Update
+    (Scene.cs:100-127: milliseconds in, seconds to the entities, tree rebuilt when an entity asked for it), on the harness scene
+    entities_demo; numpy binary32 with sinf / cosf from the C library, like the mirror."""
+    import ctypes as C
+    import ctypes.util
+    libm = C.CDLL(ctypes.util.find_library("m"))
+    for fn in (libm.cosf, libm.sinf):
+        fn.restype, fn.argtypes = C.c_float, [C.c_float]
+    F = np.float32
+    sin, cos = (lambda x: F(libm.sinf(F(x)))), (lambda x: F(libm.cosf(F(x))))
+    s = api.HostScene("entities_demo")
+    flat = lambda: s.flat.contents
+    assert flat().n_objects == 6 and [flat().objects[i].kind for i in range(6)] == [1, 0, 0, 7, 6, 2]
+    bob = [dict(i=1, base=F(1.0), amp=F(0.35), speed=F(1.7), phase=F(0.0), t=F(0)), dict(i=2, base=F(0.8), amp=F(0.25), speed=F(2.3), phase=F(1.1), t=F(0))]
+    orbit = dict(pivot=(F(0.0), F(-3.0)), radius=F(3.0), height=F(3.5), speed=F(0.8), phase=F(0.4), angle=F(0))
+    bs, amp = F(1.0), F(0.4)
+    pulse = dict(initial=F(45.0), lo=max(F(0), F(bs * F(F(1.0) - amp))), hi=F(bs * F(F(1.0) + amp)), speed=F(2.0), t=F(0))
+    tree0 = s.bvh_arrays(-1)["boxes"].copy()
+    gv0 = s.update(0.0)[1]
+    for step, ms in enumerate([16.0, 16.0, 250.0, 1000.0, -40.0, 3333.0]):
+        lv, gv = s.update(ms)
+        assert gv == gv0 + step + 1                                               # a bobbing sphere asks for a rebuild on every update
+        dt = max(F(0.0), F(F(ms) * F(0.001)))
+        for b in bob:
+            b["t"] = F(b["t"] + dt)
+            y = F(b["base"] + F(b["amp"] * sin(F(F(b["speed"] * b["t"]) + b["phase"]))))
+            assert F(flat().objects[b["i"]].p[1]) == y, (step, b["i"])
+        orbit["angle"] = F(orbit["angle"] + F(orbit["speed"] * dt))
+        a = F(orbit["angle"] + orbit["phase"])
+        want = (F(orbit["pivot"][0] + F(orbit["radius"] * cos(a))), orbit["height"], F(orbit["pivot"][1] + F(orbit["radius"] * sin(a))))
+        pulse["t"] = F(pulse["t"] + dt)
+        k = F(F(0.5) + F(F(0.5) * sin(F(pulse["speed"] * pulse["t"]))))
+        mult = F(pulse["lo"] + F(F(pulse["hi"] - pulse["lo"]) * k))
+        (p0, _, i0), (p1, _, i1) = s.lights()
+        assert tuple(map(F, p0)) == want and F(i0) == F(60.0), step
+        assert F(i1) == F(pulse["initial"] * max(F(0), mult)) and tuple(map(F, p1)) == (F(-2.5), F(3.0), F(-2.0)), step
+    assert not np.array_equal(s.bvh_arrays(-1)["boxes"], tree0)                     # the tree follows the spheres
     s.close()
 
 

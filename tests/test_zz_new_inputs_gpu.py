@@ -63,8 +63,8 @@ def test_day_night_cycle_moves_the_sun_between_frames():
     r = api.CudaRaytraceRenderer(s, 40, 12, 2)
     o = Oracle(s, 40, 12, 2)
     saw_night = False
-    for f, dt in enumerate([0.0, 1.0 / 60.0, 10.0, 6.0, 30.0, 0.5, 70.0]):
-        s.update(dt)
+    for f, ms in enumerate([0.0, 1000.0 / 60.0, 10000.0, 6000.0, 30000.0, 500.0, 70000.0]):
+        s.update(ms)
         r.SyncLights(s)
         top, bottom = s.background()
         o.lights_update(s.lights())
@@ -75,6 +75,31 @@ def test_day_night_cycle_moves_the_sun_between_frames():
         assert_cells_equal(g, c, f"day/night frame {f + 1}")
         assert_frame_parity(r, o, f"day/night frame {f + 1}")
     assert saw_night
+    r.close()
+    o.close()
+    s.close()
+
+
+def test_animated_scene_geometry_and_lights_follow_the_entities():
+    """Moving geometry between frames: Scene.Update(ms) lets BobbingSphereEntity move two spheres (tree rebuilt every frame,
+    Scene.cs:121-126), OrbitingLightEntity and PulsingLightEntity rewrite the lights; CudaRaytraceRenderer.SyncGeometry uploads the
+    object list and the new tree (ycge_scene_upload), SyncLights the lights; the TAA history is NOT reset -- the reference renders
+    on and lets the disocclusion tests of TemporalBlendWithClamp deal with what moved.  The oracle gets the same uploads."""
+    s = api.HostScene("entities_demo")
+    r = api.CudaRaytraceRenderer(s, 48, 14, 2)
+    o = Oracle(s, 48, 14, 2)
+    gv_prev = None
+    for f, ms in enumerate([0.0, 16.0, 16.0, 33.0, 250.0, 16.0]):
+        lv, gv = s.update(ms)
+        assert gv_prev is None or gv == gv_prev + 1
+        gv_prev = gv
+        r.SyncGeometry(s)
+        r.SyncLights(s)
+        o.upload_scene(s)
+        g = r.TryFlipAndBlit()
+        c = o.render_frame(threads=4, fast_post=True)
+        assert_cells_equal(g, c, f"animated frame {f + 1}")
+        assert_frame_parity(r, o, f"animated frame {f + 1}")
     r.close()
     o.close()
     s.close()

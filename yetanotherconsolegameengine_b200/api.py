@@ -237,7 +237,8 @@ def load_host() -> C.CDLL:
         h.ycgeh_renderer_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
         h.ycgeh_renderer_set_fov.argtypes = [vp, C.c_float]
         h.ycgeh_renderer_sync_lights.argtypes = [vp, vp]
-        h.ycgeh_scene_update.argtypes = [vp, C.c_float]
+        h.ycgeh_scene_update.argtypes = [vp, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        h.ycgeh_renderer_sync_geometry.argtypes = [vp, vp]
         h.ycgeh_renderer_resize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         h.ycgeh_renderer_render_cells.argtypes = [vp, vp]
         h.ycgeh_renderer_blit_ansi.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint8))]
@@ -354,13 +355,15 @@ class HostScene:
     def volume(self, i):
         return self._h.ycgeh_scene_volume(self.handle, i)
 
-    def update(self, dt: float) -> int:
-        """Scene.Update(dt) (Scenes/Scene.cs:100-163): scene entities (DayNightEntity) rewrite the lights and the sky gradient;
-        the flat view follows.  Returns the scene's light version; push the change with CudaRaytraceRenderer.SyncLights."""
-        v = self._h.ycgeh_scene_update(self.handle, dt)
-        if v < 0:
+    def update(self, delta_time_ms: float):
+        """Scene.Update(deltaTimeMS) (Scenes/Scene.cs:100-127): the scene's entities run with dt = ms / 1000 (DayNightEntity rewrites
+        the lights and the sky gradient, the animated entities move spheres and lights), then the tree is rebuilt if geometry
+        changed; the flat view follows.  Returns (lights_version, geometry_version): push what changed with
+        CudaRaytraceRenderer.SyncLights / SyncGeometry."""
+        lv, gv = C.c_int(), C.c_int()
+        if self._h.ycgeh_scene_update(self.handle, delta_time_ms, C.byref(lv), C.byref(gv)) != 0:
             raise YcgeError(-1, self._h.ycgeh_last_error().decode())
-        return v
+        return lv.value, gv.value
 
     def lights(self):
         f = self.flat.contents
@@ -434,6 +437,12 @@ class CudaRaytraceRenderer:
         """After scene.update(dt): ycge_lights_update + ycge_globals_update with what the entities changed (no history reset,
         like the reference, whose renderer simply reads scene.Lights on the next frame)."""
         if self._h.ycgeh_renderer_sync_lights(self.handle, scene.handle) != 0:
+            raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+
+    def SyncGeometry(self, scene: "HostScene"):
+        """After scene.update(ms) moved objects: the object list and the rebuilt top-level tree again (ycge_scene_upload); meshes,
+        volumes, textures and the TAA history stay (the reference rebuilds its BVH and renders on, Scene.cs:121-126)."""
+        if self._h.ycgeh_renderer_sync_geometry(self.handle, scene.handle) != 0:
             raise YcgeError(-1, self._h.ycgeh_last_error().decode())
 
     def SetFov(self, fov_deg: float):

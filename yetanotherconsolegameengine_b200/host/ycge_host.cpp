@@ -570,6 +570,26 @@ std::shared_ptr<Scene> BuildTextureTestScene() { // :337-358
     s->Update(0.0f);
     return s;
 }
+std::shared_ptr<Scene> BuildEntitiesDemo() { // test scene, not in the reference: the animated entities of TestScenesRandom.cs on a small stage
+    auto s = std::make_shared<Scene>(); s->Name = "entities_demo";
+    s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.05f);
+    s->Add(std::make_shared<Plane>(Vec3(0.0f, 0.0f, 0.0f), Vec3(0.0f, 1.0f, 0.0f), Checker(Vec3(0.8f, 0.8f, 0.8f), Vec3(0.15f, 0.15f, 0.15f), 0.7f), 0.02f, 0.0f));
+    auto mirrorBall = std::make_shared<Sphere>(Vec3(-1.1f, 1.0f, -3.2f), 0.6f, Material(Vec3(0.98, 0.98, 0.98), 0.0, 0.92, Vec3()));
+    auto redBall = std::make_shared<Sphere>(Vec3(1.0f, 0.8f, -2.6f), 0.45f, Material(Vec3(0.9, 0.2, 0.15), 0.1, 0.0, Vec3()));
+    s->Add(mirrorBall); s->Add(redBall);
+    s->Add(std::make_shared<CylinderY>(Vec3(0.0f, 0.0f, -4.2f), 0.35f, 0.0f, 1.3f, true, Material(Vec3(0.85, 0.85, 0.85), 0.0, 0.0, Vec3())));
+    s->Add(std::make_shared<Box>(Vec3(1.8f, 0.0f, -4.6f), Vec3(2.6f, 0.9f, -3.8f), Solid(Vec3(0.2f, 0.6f, 0.9f)), 0.05f, 0.0f));
+    s->Add(std::make_shared<Disk>(Vec3(-2.4f, 0.02f, -2.0f), Vec3(0.0f, 1.0f, 0.0f), 0.8f, Solid(Vec3(0.9f, 0.8f, 0.2f)), 0.0f, 0.0f));
+    s->Lights.push_back(PointLight(Vec3(2.0f, 3.5f, -1.0f), Vec3(1.0f, 0.95f, 0.9f), 60.0f));
+    s->Lights.push_back(PointLight(Vec3(-2.5f, 3.0f, -2.0f), Vec3(0.8f, 0.9f, 1.0f), 45.0f));
+    s->AddEntity(std::make_shared<BobbingSphereEntity>(mirrorBall, 0.35f, 1.7f, 0.0f));
+    s->AddEntity(std::make_shared<BobbingSphereEntity>(redBall, 0.25f, 2.3f, 1.1f));
+    s->AddEntity(std::make_shared<OrbitingLightEntity>(0, Vec3(0.0f, 0.0f, -3.0f), 3.0f, 3.5f, 0.8f, 0.4f));
+    s->AddEntity(std::make_shared<PulsingLightEntity>(*s, 1, 1.0f, 0.4f, 2.0f));
+    s->BackgroundTop = Vec3(0.25, 0.4, 0.7); s->BackgroundBottom = Vec3(0.7, 0.8, 0.9);
+    s->Update(0.0f);
+    return s;
+}
 std::shared_ptr<Scene> BuildTextureGallery() { // test scene, not in the reference: all U,V-carrying primitives, blended weights, tiling
     auto s = std::make_shared<Scene>(); s->Name = "texture_gallery";
     s->Ambient = AmbientLight(Vec3(1.0, 1.0, 1.0), 0.05f);
@@ -1257,8 +1277,34 @@ World Generate(int nx, int ny, int nz, int seed) { // WorldManager.cs:510-606
 }
 } // namespace WorldGeneration
 
+void BobbingSphereEntity::Update(float dt, Scene &scene) { // TestScenesRandom.cs:707-713
+    t += dt;
+    float y = baseY + amplitude * std::sin(speed * t + phase);
+    sphere->Center = Vec3((float)sphere->Center.X, y, (float)sphere->Center.Z);
+    scene.RequestGeometryRebuild();
+}
+void OrbitingLightEntity::Update(float dt, Scene &scene) { // :743-750
+    angle += speed * dt;
+    float a = angle + phase;
+    float x = (float)(pivot.X + radius * std::cos(a));
+    float z = (float)(pivot.Z + radius * std::sin(a));
+    scene.Lights[(size_t)light].Position = Vec3(x, height, z);
+}
+PulsingLightEntity::PulsingLightEntity(const Scene &scene, int light, float baseScale, float ampFraction, float speed) : light(light), speed(speed) { // :770-781
+    if (ampFraction < 0.0f) ampFraction = 0.0f;
+    initialIntensity = scene.Lights[(size_t)light].Intensity;
+    float bs = std::max(0.0f, baseScale);
+    minMult = std::max(0.0f, bs * (1.0f - ampFraction));
+    maxMult = bs * (1.0f + ampFraction);
+}
+void PulsingLightEntity::Update(float dt, Scene &scene) { // :783-792
+    if (dt < 0.0f) dt = 0.0f;
+    t += dt;
+    float s = 0.5f + 0.5f * std::sin(speed * t);
+    float mult = minMult + (maxMult - minMult) * s;
+    scene.Lights[(size_t)light].Intensity = initialIntensity * std::max(0.0f, mult);
+}
 void DayNightEntity::Update(float dt, Scene &scene) { // DayNightCycle.cs:41-91
-    if (!Enabled) return;
     const float PI = 3.14159274f;
     time += std::max(0.0f, dt);
     float t01 = std::fmod(time, cycleSeconds) / cycleSeconds;
@@ -1457,6 +1503,7 @@ std::shared_ptr<Scene> BuildSceneByName(const std::string &name) {
     if (name == "volume_grid_test") return Scenes::BuildVolumeGridTestScene();
     if (name == "texture_test") return Scenes::BuildTextureTestScene();
     if (name == "texture_gallery") return Scenes::BuildTextureGallery();
+    if (name == "entities_demo") return Scenes::BuildEntitiesDemo();
     if (name == "cow") return MeshScenes::BuildCowScene();
     if (name == "bunny") return MeshScenes::BuildBunnyScene();
     if (name == "teapot") return MeshScenes::BuildTeapotScene();
@@ -1738,6 +1785,11 @@ void CudaRaytraceRenderer::SyncLights(const Scene &scene) { // what DayNightEnti
     float amb[3] = {(float)scene.Ambient.Color.X, (float)scene.Ambient.Color.Y, (float)scene.Ambient.Color.Z};
     Check(ycge_globals_update(ctx, top, bot, amb, scene.Ambient.Intensity), "ycge_globals_update");
 }
+void CudaRaytraceRenderer::SyncGeometry(Scene &scene) { // Scene.Update rebuilt Objects' tree (Scene.cs:121-126); meshes, volumes and textures are unchanged
+    std::shared_ptr<Scene> alias(&scene, [](Scene *) {});
+    auto flat = Flatten(alias);
+    Check(ycge_scene_upload(ctx, &flat->scene), "ycge_scene_upload");
+}
 void CudaRaytraceRenderer::SetCamera(Vec3 pos, float yaw, float pitch) { float p[3] = {pos.X, pos.Y, pos.Z}; Check(ycge_set_camera(ctx, p, yaw, pitch), "ycge_set_camera"); }
 void CudaRaytraceRenderer::SetFov(float fovDeg) { Check(ycge_set_fov(ctx, fovDeg), "ycge_set_fov"); }
 void CudaRaytraceRenderer::Resize(Framebuffer &fb, int superSample) {
@@ -1881,17 +1933,21 @@ YH_API float ycgeh_gradient_noise2d(float x, float z, int seed) { return WorldGe
 YH_API int ycgeh_write_synthetic_world(const char *path, int world_size, int world_height) { // a VG01 file of the synthetic world (tests)
     try { VolumeScenes::WriteSyntheticWorldFile(path, world_size, world_height); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
-YH_API int ycgeh_scene_update(void *h, float dt) { // Scene.Update(dt): entities rewrite lights and sky; the flat view follows
+YH_API int ycgeh_scene_update(void *h, float delta_time_ms, int *lights_version, int *geometry_version) { // Scene.Update(deltaTimeMS); the flat view follows
     try {
         SceneHandle *sh = (SceneHandle *)h;
         Scene &s = *sh->scene;
-        s.Update(dt);
+        const unsigned g0 = s.GeometryVersion;
+        s.Update(delta_time_ms);
+        if (s.GeometryVersion != g0) sh->flat = Flatten(sh->scene); // objects moved: flatten again (the tree was rebuilt)
         FlatScene &f = *sh->flat;
         FlattenLights(s, f.ex.lights);
         f.scene.n_lights = (int)f.ex.lights.size(); f.scene.lights = f.ex.lights.data();
         f.scene.bg_top[0] = s.BackgroundTop.X; f.scene.bg_top[1] = s.BackgroundTop.Y; f.scene.bg_top[2] = s.BackgroundTop.Z;
         f.scene.bg_bottom[0] = s.BackgroundBottom.X; f.scene.bg_bottom[1] = s.BackgroundBottom.Y; f.scene.bg_bottom[2] = s.BackgroundBottom.Z;
-        return (int)s.LightsVersion;
+        if (lights_version) *lights_version = (int)s.LightsVersion;
+        if (geometry_version) *geometry_version = (int)s.GeometryVersion;
+        return 0;
     } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
 YH_API void ycgeh_scene_destroy(void *h) { delete (SceneHandle *)h; }
@@ -1948,6 +2004,9 @@ YH_API int ycgeh_renderer_set_camera(void *h, const float *pos, float yaw, float
 }
 YH_API int ycgeh_renderer_sync_lights(void *h, void *scene) { // after ycgeh_scene_update: push what the entities changed
     try { ((RendererHandle *)h)->r->SyncLights(*((SceneHandle *)scene)->scene); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API int ycgeh_renderer_sync_geometry(void *h, void *scene) { // after ycgeh_scene_update moved objects: objects + tree again, history kept
+    try { ((RendererHandle *)h)->r->SyncGeometry(*((SceneHandle *)scene)->scene); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }
 }
 YH_API int ycgeh_renderer_set_fov(void *h, float fov) {
     try { ((RendererHandle *)h)->r->SetFov(fov); return 0; } catch (const std::exception &e) { yh_error = e.what(); return -1; }

@@ -191,17 +191,47 @@ class BVH { // Objects/BVH.cs: top-level tree over Scene.Objects
 };
 
 class Scene;
-// Scenes/DayNightCycle.cs: the one scene entity that changes the path's inputs every frame (sun / moon PointLights, sky
-// gradient).  The rest of the entity layer (ISceneEntity with hittables, physics) is out of scope.
-class DayNightEntity {
+// Scene entities (Scenes/Scene.cs:528-533 ISceneEntity): the ones that change the path's inputs between frames.  GetHittables and
+// the entity -> Objects sync (:518-534) are folded into Scene::Objects, which keeps the same order.
+class ISceneEntity {
   public:
     bool Enabled = true;
+    virtual ~ISceneEntity() {}
+    virtual void Update(float dt, Scene &scene) = 0; // dt in seconds
+};
+// Scenes/DayNightCycle.cs: sun / moon PointLights and the sky gradient of the voxel worlds.
+class DayNightEntity : public ISceneEntity {
+  public:
     explicit DayNightEntity(float cycleSeconds = 120.0f, float sunRadius = 2000.0f) : cycleSeconds(std::max(1.0f, cycleSeconds)), sunRadius(sunRadius) {}
-    void Update(float dt, Scene &scene); // DayNightCycle.cs:41-91
+    void Update(float dt, Scene &scene) override; // DayNightCycle.cs:41-91
     float Time() const { return time; }
   private:
     float time = 0.0f, cycleSeconds, sunRadius;
     int sun = -1, moon = -1; // indices into Scene::Lights (the reference keeps the PointLight objects)
+};
+// Scenes/TestScenesRandom.cs:688-798, the animated exhibits' entities.  (UVWobbleEntity :800-828 is not mirrored: Material is a
+// struct, the entity wobbles its own copy and the scene never sees it.)
+class BobbingSphereEntity : public ISceneEntity { // :688-720: moves the sphere and requests a geometry rebuild every update
+  public:
+    BobbingSphereEntity(std::shared_ptr<Sphere> sphere, float amplitude, float speed, float phase)
+        : sphere(sphere), baseY((float)sphere->Center.Y), amplitude(amplitude), speed(speed), phase(phase) {}
+    void Update(float dt, Scene &scene) override;
+  private:
+    std::shared_ptr<Sphere> sphere; float baseY, amplitude, speed, phase, t = 0.0f;
+};
+class OrbitingLightEntity : public ISceneEntity { // :722-757
+  public:
+    OrbitingLightEntity(int light, Vec3 pivot, float radius, float height, float speed, float phase) : light(light), pivot(pivot), radius(radius), height(height), speed(speed), phase(phase) {}
+    void Update(float dt, Scene &scene) override;
+  private:
+    int light; Vec3 pivot; float radius, height, speed, phase, angle = 0.0f;
+};
+class PulsingLightEntity : public ISceneEntity { // :759-798
+  public:
+    PulsingLightEntity(const Scene &scene, int light, float baseScale, float ampFraction, float speed);
+    void Update(float dt, Scene &scene) override;
+  private:
+    int light; float initialIntensity, minMult, maxMult, speed, t = 0.0f;
 };
 
 class Scene { // Scenes/Scene.cs
@@ -224,11 +254,18 @@ class Scene { // Scenes/Scene.cs
     void Add(std::shared_ptr<Hittable> h) { Objects.push_back(h); }
     void RebuildBVH() { bvh = std::make_shared<BVH>(Objects); } // Scene.cs:66-69
     void ResetCamera() { CameraPos = DefaultCameraPos; Yaw = DefaultYaw; Pitch = DefaultPitch; }
-    std::vector<std::shared_ptr<DayNightEntity>> Entities;
-    unsigned LightsVersion = 0; // bumped whenever an entity rewrote Lights / Background*: CudaRaytraceRenderer::SyncLights pushes them
-    void Update(float dt) { // Scene.cs:100-163: entities first, then the tree if the object list changed
-        for (auto &e : Entities) { e->Update(dt, *this); LightsVersion++; }
-        if (!bvh) RebuildBVH();
+    std::vector<std::shared_ptr<ISceneEntity>> Entities;
+    bool GeometryDirty = false;
+    unsigned LightsVersion = 0;   // bumped when entities ran (they may have rewritten Lights / Background*): CudaRaytraceRenderer::SyncLights
+    unsigned GeometryVersion = 0; // bumped when the tree was rebuilt: CudaRaytraceRenderer::SyncGeometry
+    void AddEntity(std::shared_ptr<ISceneEntity> e) { if (e) Entities.push_back(e); }
+    void RequestGeometryRebuild() { GeometryDirty = true; } // Scene.cs:508-511
+    void Update(float deltaTimeMS) { // Scene.cs:100-127: milliseconds in, entities get seconds; then the tree if geometry changed
+        float dt = deltaTimeMS * 0.001f;
+        if (dt < 0.0f) dt = 0.0f;
+        for (auto &e : Entities) if (e && e->Enabled) e->Update(dt, *this);
+        if (!Entities.empty()) LightsVersion++;
+        if (GeometryDirty || !bvh) { GeometryDirty = false; RebuildBVH(); GeometryVersion++; }
     }
 };
 
@@ -263,6 +300,7 @@ std::shared_ptr<Scene> BuildCylindersDisksAndTriangles();
 std::shared_ptr<Scene> BuildBoxesShowcase();
 std::shared_ptr<Scene> BuildVolumeGridTestScene();
 std::shared_ptr<Scene> BuildTextureTestScene(); // assets/image.png if present, else a procedural stand-in (labelled in Scene::Name)
+std::shared_ptr<Scene> BuildEntitiesDemo();     // NOT in the reference: bobbing spheres, an orbiting and a pulsing light (tests)
 std::shared_ptr<Scene> BuildTextureGallery();   // NOT in the reference: every primitive kind that carries U,V, textured (tests)
 } // namespace Scenes
 namespace TestScenes { // Scenes/TestScenes.cs
@@ -319,7 +357,8 @@ class CudaRaytraceRenderer : public IConsoleRenderer {
     void Resize(Framebuffer &fb, int superSample) override;
     void UploadTexture(int id, const Texture &t);   // new Texture(path) -> ycge_texture_upload
     void UploadScene(Scene &scene);                 // scene switch (RaytraceEntity.SwitchToScene :234-246)
-    void SyncLights(const Scene &scene);            // after scene.Update(dt): ycge_lights_update + ycge_globals_update when an entity moved them
+    void SyncLights(const Scene &scene);            // after scene.Update(ms): ycge_lights_update + ycge_globals_update when an entity moved them
+    void SyncGeometry(Scene &scene);                // after scene.Update(ms) rebuilt the tree: objects + top-level BVH again, history kept
     void RenderCells(ycge_cell *out);               // TryFlipAndBlit without the Chexel unpack (headless)
     ycge_ctx *Context() { return ctx; }
     int fbW, fbH, ss;
