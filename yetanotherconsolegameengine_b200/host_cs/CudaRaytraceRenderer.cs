@@ -134,6 +134,7 @@ namespace ConsoleGame.RayTracing
         private GCHandle cellsPin; // long-lived pinned buffer, as VolumeGrid pins its arrays (VolumeGrid.cs:70-73)
         private int fbW, fbH, ss;
         private readonly float[] camTmp = new float[3];
+        private BVH uploadedBvh; // the tree object the device copy was made from
 
         /// Same arguments as RaytraceRenderer's ctor (RaytraceRenderer.cs:74): hiW = fbW*ss, hiH = fbH*2*ss.
         public CudaRaytraceRenderer(Framebuffer framebuffer, Scene scene, float fovDeg, int pxW, int pxH, int superSample, int device = 0)
@@ -168,6 +169,11 @@ namespace ConsoleGame.RayTracing
         public void TryFlipAndBlit(Framebuffer fb)
         {
             if (scene.HasDynamicTextures) Check(ycge_reset_history(ctx)); // :171
+            // The reference's renderer reads scene.Objects / scene.Lights afresh every frame.  Scene.Update (Scene.cs:100-127) may have
+            // run entities since the last one: a rebuilt tree is a new BVH object (Scene.cs:66-69) -> flatten again, history kept;
+            // otherwise lights and sky may still have moved (DayNightCycle.cs:80-89, Orbiting/PulsingLightEntity) -> two small calls.
+            if (!ReferenceEquals(scene.Bvh, uploadedBvh)) UploadScene();
+            else if (scene.Entities.Count > 0) UpdateLightsAndGlobals();
             Check(ycge_render_frame(ctx, cellsPin.AddrOfPinnedObject(), fbW));
             for (int cy = 0; cy < fbH; cy++)
             {
@@ -285,6 +291,7 @@ namespace ConsoleGame.RayTracing
                     NObjects = objects.Count, Objects = Pin(objects.ToArray()), Bvh = Pin(topTree)
                 };
                 Check(ycge_scene_upload(ctx, ref ys));
+                uploadedBvh = scene.Bvh;
             }
             finally { foreach (var h in pins) h.Free(); } // the library copies everything during the call
         }
