@@ -29,6 +29,12 @@ FB_W, FB_H, SS = 480, 135, 4  # 1920x1080 internal (hiW = fbW*ss, hiH = fbH*2*ss
 SCENE = "dragon"              # real xyzrgb_dragon.obj when present in assets/, else the procedural stand-in
 
 
+def uses_bench_pose(scene_name):
+    """The single-mesh scenes put the mesh at (0, 0.5, 1) behind the default camera: they are timed from the bench pose.
+    Every other scene (the museum, the all-meshes scene, the voxel worlds, the primitive scenes) from its own default camera."""
+    return scene_name in ("cow", "bunny", "teapot", "dragon") or scene_name.startswith("knot")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -116,7 +122,7 @@ def cpu_leg(args, fb_w, fb_h, ss, seconds, steps=None, warmup=1):
     sfw, sfh = max(8, fb_w // 4), max(4, fb_h // 4)
     scene = pkg.HostScene(args.scene)
     o = Oracle(scene, sfw, sfh, ss)
-    if scene.n_meshes:
+    if uses_bench_pose(args.scene):
         o.set_camera(*pkg.BENCH_POSE)
     for _ in range(warmup):
         o.render_frame(threads=cores)
@@ -149,7 +155,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"{args.scene} scene, {W}x{H} internal ({fb_w}x{fb_h} cells, ss={ss}), 1 spp, reference bounce constants, TAA + a-trous + auto-exposure, bench pose"
+    workload = f"{args.scene} scene, {W}x{H} internal ({fb_w}x{fb_h} cells, ss={ss}), 1 spp, reference bounce constants, TAA + a-trous + auto-exposure, {'bench pose' if uses_bench_pose(args.scene) else 'default pose'}"
 
     if args.impl == "reference":
         if rank != 0:
@@ -190,7 +196,7 @@ def main():
     n = max(1, world)
 
     scene = pkg.HostScene(args.scene)
-    pose = pkg.BENCH_POSE if scene.n_meshes else scene.default_camera()[:3]
+    pose = pkg.BENCH_POSE if uses_bench_pose(args.scene) else scene.default_camera()[:3]
     stream = torch.cuda.Stream()
     pinned = torch.empty((fb_h * fb_w * api.CELL_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
     cells = pinned.numpy().view(api.CELL_DTYPE).reshape(fb_h, fb_w)

@@ -16,7 +16,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 scene = pkg.HostScene(scene_name)
-pose = pkg.BENCH_POSE if scene.n_meshes else scene.default_camera()[:3]
+pose = pkg.BENCH_POSE if (scene.n_meshes == 1 and scene.n_volumes == 0) else scene.default_camera()[:3]
 row0, rows = sharding.tile_rows(rank, world, fb_h)
 b = sharding.CudaTileBackend(scene, fb_w, fb_h, ss, row0, rows, local)
 sr = sharding.ShardedRenderer(b, rank, world, fb_w, fb_h, peers=not os.environ.get("YCGE_NO_PEERS"))
