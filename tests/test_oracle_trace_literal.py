@@ -810,7 +810,7 @@ def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb
     scene.close()
 
 
-@pytest.mark.parametrize("scene_name", ["cornell", "cylinders_disks_triangles", "volume_grid_test", "texture_gallery", "museum"])
+@pytest.mark.parametrize("scene_name", ["cornell", "cylinders_disks_triangles", "volume_grid_test", "texture_gallery", "museum", "all_meshes:40x10", "voxel_island:96x128", "entities_demo"])
 def test_trace_stage_matches_the_transcription_from_random_poses(scene_name):
     """The same comparison from camera poses drawn at random (seeded): inside and outside the geometry, looking up, down and along
     surfaces, so that grazing hits, back faces, the inside of boxes, misses of every slab and total internal reflection occur."""
