@@ -305,6 +305,20 @@ def test_animated_entities_match_a_literal_transcription():
     s.close()
 
 
+def test_rebuilding_the_tree_is_idempotent_and_cheap():
+    """Scene.RebuildBVH() (Scenes/Scene.cs:66-69) on unchanged objects gives the same tree, field by field (the builder has no hidden
+    state); its cost on the host is what a per-frame geometry change adds before the upload."""
+    for name, limit_ms in (("museum", 50.0), ("voxel_island:128x128", 50.0)):
+        s = api.HostScene(name)
+        t0 = s.bvh_arrays(-1)
+        ms = s.rebuild_bvh_ms()
+        t1 = s.bvh_arrays(-1)
+        for k in ("boxes", "lrsc", "leaf"):
+            assert np.array_equal(t0[k], t1[k]), (name, k)
+        assert 0.0 <= ms < limit_ms
+        s.close()
+
+
 def test_texture_test_scene_and_png_decoder(tmp_path):
     """BuildTextureTestScene (Scenes.cs:337-358): one textured box, ambient 0.5, no lights.  new Texture(path) decodes through
     OpenCV in the reference (ImreadModes.Color, BGR2RGBA: Texture.cs:25-49); the mirror's zlib-only PNG decoder must give the

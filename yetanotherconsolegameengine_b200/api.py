@@ -239,6 +239,8 @@ def load_host() -> C.CDLL:
         h.ycgeh_renderer_sync_lights.argtypes = [vp, vp]
         h.ycgeh_scene_update.argtypes = [vp, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         h.ycgeh_renderer_sync_geometry.argtypes = [vp, vp]
+        h.ycgeh_scene_rebuild_bvh_ms.argtypes = [vp]
+        h.ycgeh_scene_rebuild_bvh_ms.restype = C.c_double
         h.ycgeh_renderer_resize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         h.ycgeh_renderer_render_cells.argtypes = [vp, vp]
         h.ycgeh_renderer_blit_ansi.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint8))]
@@ -364,6 +366,13 @@ class HostScene:
         if self._h.ycgeh_scene_update(self.handle, delta_time_ms, C.byref(lv), C.byref(gv)) != 0:
             raise YcgeError(-1, self._h.ycgeh_last_error().decode())
         return lv.value, gv.value
+
+    def rebuild_bvh_ms(self) -> float:
+        """Scene.RebuildBVH() (Scenes/Scene.cs:66-69) again, timed: the host-side cost of a geometry change, before SyncGeometry."""
+        ms = self._h.ycgeh_scene_rebuild_bvh_ms(self.handle)
+        if ms < 0:
+            raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+        return ms
 
     def lights(self):
         f = self.flat.contents

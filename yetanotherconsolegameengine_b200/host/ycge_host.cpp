@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1949,6 +1950,17 @@ YH_API int ycgeh_scene_update(void *h, float delta_time_ms, int *lights_version,
         if (geometry_version) *geometry_version = (int)s.GeometryVersion;
         return 0;
     } catch (const std::exception &e) { yh_error = e.what(); return -1; }
+}
+YH_API double ycgeh_scene_rebuild_bvh_ms(void *h) { // Scene.RebuildBVH (Scene.cs:66-69) timed on this host: what a geometry change costs before the upload
+    try {
+        SceneHandle *sh = (SceneHandle *)h;
+        auto t0 = std::chrono::steady_clock::now();
+        sh->scene->RebuildBVH();
+        auto t1 = std::chrono::steady_clock::now();
+        sh->scene->GeometryVersion++;
+        sh->flat = Flatten(sh->scene);
+        return std::chrono::duration<double, std::milli>(t1 - t0).count();
+    } catch (const std::exception &e) { yh_error = e.what(); return -1.0; }
 }
 YH_API void ycgeh_scene_destroy(void *h) { delete (SceneHandle *)h; }
 YH_API const ycge_scene *ycgeh_scene_flat(void *h) { return &((SceneHandle *)h)->flat->scene; }
