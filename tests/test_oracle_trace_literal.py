@@ -761,11 +761,11 @@ class LiteralTracer:
 
 @pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1), ("knot:12x5", 8, 3, 2),
                                                      ("volume_grid_test", 10, 4, 2), ("voxel_world:32x32", 8, 4, 2), ("cylinders_disks_triangles", 10, 4, 2),
-                                                     ("texture_gallery", 14, 5, 2), ("voxel_island:96x128", 8, 4, 2), ("all_meshes:40x10", 16, 3, 2), ("museum", 14, 5, 2)])
+                                                     ("texture_gallery", 14, 5, 2), ("voxel_island:96x128", 8, 4, 2), ("all_meshes:40x10", 16, 3, 2), ("museum", 14, 5, 2), ("museum-diorama", 12, 4, 2)])
 def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb_h, ss):
     lib = load_oracle()
     lib.yo_set_math_mode(0)
-    scene = api.HostScene(scene_name)
+    scene = api.HostScene(scene_name.split("-")[0])
     o = Oracle(scene, fb_w, fb_h, ss)
     lt = LiteralTracer(scene, lib)
     pos, yaw, pitch, fov = scene.default_camera()
@@ -774,6 +774,10 @@ def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb
         o.set_camera(pos, yaw, pitch)
     if scene_name == "museum":         # from the entrance the mesh gallery (x = 9, z = -40) is out of sight: stand in front of it
         pos, yaw, pitch = (9.0, 3.0, -35.5), 0.0, -0.35
+        o.set_camera(pos, yaw, pitch)
+    if scene_name == "museum-diorama": # voxel diorama B: 14 x 7 x 14 cells of 0.45 -- partial 8^3 bricks -- with the teapot on its stand
+        scene_name = "museum"
+        pos, yaw, pitch = (5.5, 2.6, -84.5), 1.45, -0.3
         o.set_camera(pos, yaw, pitch)
     cam, yaw, pitch, fov = v3(*pos), F(yaw), F(pitch), F(fov)
     w, h = fb_w * ss, fb_h * 2 * ss
