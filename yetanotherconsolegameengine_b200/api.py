@@ -361,7 +361,8 @@ class HostScene:
         """Scene.Update(deltaTimeMS) (Scenes/Scene.cs:100-127): the scene's entities run with dt = ms / 1000 (DayNightEntity rewrites
         the lights and the sky gradient, the animated entities move spheres and lights), then the tree is rebuilt if geometry
         changed; the flat view follows.  Returns (lights_version, geometry_version): push what changed with
-        CudaRaytraceRenderer.SyncLights / SyncGeometry."""
+        CudaRaytraceRenderer.SyncLights / SyncGeometry.  When geometry_version moved, the scene was flattened again: pointers
+        taken earlier from .flat, .mesh(i), .volume(i) are stale -- fetch them again."""
         lv, gv = C.c_int(), C.c_int()
         if self._h.ycgeh_scene_update(self.handle, delta_time_ms, C.byref(lv), C.byref(gv)) != 0:
             raise YcgeError(-1, self._h.ycgeh_last_error().decode())
