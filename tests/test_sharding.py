@@ -170,6 +170,7 @@ class FakeFrameBackend:
         self.expo = torch.zeros(16, dtype=torch.uint8)
         self.frames = []      # per rendered frame: (planes, cells, exposure state after the frame)
         self.slot_frame = {}  # slot -> index of the frame whose BACK ran there
+        self.syncs = []       # (frames rendered before the call, geometry) of every sync_scene
         self.done = 0         # frames finished so far, over all ranks (the root of frame f is the only one that counts f)
         self.errors = []
 
@@ -190,6 +191,12 @@ class FakeFrameBackend:
 
     def set_camera(self, pos, yaw, pitch):
         self.o.set_camera(pos, yaw, pitch)
+
+    def sync_scene(self, scene, geometry):
+        self.syncs.append((len(self.frames), geometry))
+        if geometry:
+            self.o.upload_scene(scene)
+        self.o.lights_update(scene.lights())
 
     @staticmethod
     def state_token(frame_index, ae):
@@ -237,11 +244,18 @@ def _fp_worker(rank, world, port, fb_w, fb_h, ss, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         tiles = [sharding.tile_rows(r, world, fb_h) for r in range(world)]
-        b = FakeFrameBackend("boxes", fb_w, fb_h, ss, rank, world, tiles, back_slots=2)
+        b = FakeFrameBackend("entities_demo", fb_w, fb_h, ss, rank, world, tiles, back_slots=2)
         fp = sharding.FrameParallelRenderer(b, rank, world, fb_w, fb_h, ss, tiles=tiles, back_slots=2)
-        moved = lambda f: fp.SetCamera((0.3, 1.2, 0.1), 0.2, -0.1) if f == 3 else None  # every rank moves identically
-        got = fp.render(2 * world + 1, collect=True, set_camera=moved) + fp.render(world + 2, collect=True)  # two batches
-        ok = True
+
+        def per_frame(f):  # every rank runs the same deterministic scene update, then moves the camera once
+            b.scene.update(16.0)
+            fp.SyncScene(b.scene, geometry=True)
+            if f == 3:
+                fp.SetCamera((0.3, 1.2, 0.1), 0.2, -0.1)
+
+        got = fp.render(2 * world + 1, collect=True, set_camera=per_frame) + fp.render(world + 2, collect=True)  # two batches
+        ok = b.syncs == [(f, True) for f in range(2 * world + 1)]                          # before each frame's FRONT, in order
+        ok &= len({b.frames[f][1].tobytes() for f in range(2 * world + 1)}) > 1             # the scene did move between frames
         if rank == 0:
             ok &= len(got) == 3 * world + 3
             for f, g in enumerate(got):

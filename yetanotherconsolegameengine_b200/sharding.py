@@ -321,6 +321,13 @@ class CudaFrameBackend:
     def set_camera(self, pos, yaw, pitch):
         self.front_r.SetCamera(pos, yaw, pitch)
 
+    def sync_scene(self, scene: api.HostScene, geometry: bool):
+        """After scene.update(ms): only the FRONT context traces, so only it needs the moved lights / objects; both calls are
+        ordered on its stream behind the fronts already enqueued."""
+        if geometry:
+            self.front_r.SyncGeometry(scene)
+        self.front_r.SyncLights(scene)
+
     def front(self):
         self.front_r.frame_front()
 
@@ -418,6 +425,12 @@ class FrameParallelRenderer:
     def SetCamera(self, pos, yaw, pitch):
         self.b.set_camera(pos, yaw, pitch)
 
+    def SyncScene(self, scene, geometry: bool = False):
+        """Per-frame scene changes (Scene.Update: DayNightEntity, orbiting / pulsing lights, bobbing spheres).  Every rank runs the
+        same deterministic scene.update(ms) and calls this from the per-frame hook of render() before the frame's FRONT; the
+        BACK and FINISH stages read image planes only."""
+        self.b.sync_scene(scene, geometry)
+
     def _send(self, t: torch.Tensor, dst: int, group):
         """A send that never blocks the host.  NCCL: enqueued, the current stream waits for it.  Host-blocking backends (gloo): a
         copy is sent asynchronously and waited for at the end of the batch; a blocking send in the FINISH ring would keep this
@@ -429,7 +442,8 @@ class FrameParallelRenderer:
             self._pending.append((self.dist.isend(keep, dst=dst, group=group), keep))
 
     def render(self, n_frames: int, collect: bool = False, set_camera=None, host_ring=None):
-        """Enqueue n_frames frames.  `set_camera(f)` is called before frame f is submitted (every rank).  `host_ring` (rank 0):
+        """Enqueue n_frames frames.  `set_camera(f)` is called before frame f is submitted (every rank): the per-frame hook, for
+        SetCamera and for SyncScene after a scene.update(ms).  `host_ring` (rank 0):
         a list of pinned uint8 tensors; frame f's cells are copied into host_ring[f % len] as part of the frame, and the host
         waits for that copy before it reuses the entry, i.e. it runs len(host_ring) frames ahead at most (streaming end to
         end: every frame's cells land in host memory)."""
