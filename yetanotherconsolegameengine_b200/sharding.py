@@ -322,8 +322,8 @@ class CudaFrameBackend:
         self.front_r.SetCamera(pos, yaw, pitch)
 
     def sync_scene(self, scene: api.HostScene, geometry: bool):
-        """After scene.update(ms): only the FRONT context traces, so only it needs the moved lights / objects; both calls are
-        ordered on its stream behind the fronts already enqueued."""
+        """After scene.update(ms): only the FRONT context traces, so only it needs the moved lights / objects.  Both calls wait
+        for the FRONT stream (the fronts already enqueued: short kernels), never for the BACK / FINISH streams."""
         if geometry:
             self.front_r.SyncGeometry(scene)
         self.front_r.SyncLights(scene)
