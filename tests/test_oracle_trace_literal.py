@@ -761,7 +761,7 @@ class LiteralTracer:
 
 @pytest.mark.parametrize("scene_name,fb_w,fb_h,ss", [("test", 10, 4, 2), ("mirror_spheres", 10, 4, 2), ("cornell", 9, 4, 2), ("boxes", 5, 9, 1), ("knot:12x5", 8, 3, 2),
                                                      ("volume_grid_test", 10, 4, 2), ("voxel_world:32x32", 8, 4, 2), ("cylinders_disks_triangles", 10, 4, 2),
-                                                     ("texture_gallery", 14, 5, 2), ("voxel_island:96x128", 8, 4, 2), ("all_meshes:40x10", 16, 3, 2), ("museum", 14, 5, 2), ("museum-diorama", 12, 4, 2)])
+                                                     ("texture_gallery", 14, 5, 2), ("voxel_island:96x128", 8, 4, 2), ("all_meshes:40x10", 16, 3, 2), ("museum", 14, 5, 2), ("museum-diorama", 12, 4, 2), ("museum-texture", 12, 4, 2)])
 def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb_h, ss):
     lib = load_oracle()
     lib.yo_set_math_mode(0)
@@ -769,11 +769,16 @@ def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb
     o = Oracle(scene, fb_w, fb_h, ss)
     lt = LiteralTracer(scene, lib)
     pos, yaw, pitch, fov = scene.default_camera()
+    mesh_in_view = scene.n_meshes > 0
     if scene_name.startswith("knot"):  # the default pose of the mesh scenes looks away from the mesh
         pos, yaw, pitch = api.BENCH_POSE
         o.set_camera(pos, yaw, pitch)
     if scene_name == "museum":         # from the entrance the mesh gallery (x = 9, z = -40) is out of sight: stand in front of it
         pos, yaw, pitch = (9.0, 3.0, -35.5), 0.0, -0.35
+        o.set_camera(pos, yaw, pitch)
+    if scene_name == "museum-texture": # the textured sphere (Sphere.Hit leaves U = V = 0: one texel) in front of the textured end wall (a Plane: likewise)
+        scene_name, mesh_in_view = "museum", False
+        pos, yaw, pitch = (-1.6, 1.0, -7.5), 0.0, -0.1
         o.set_camera(pos, yaw, pitch)
     if scene_name == "museum-diorama": # voxel diorama B: 14 x 7 x 14 cells of 0.45 -- partial 8^3 bricks -- with the teapot on its stand
         scene_name = "museum"
@@ -807,7 +812,7 @@ def test_trace_stage_matches_a_literal_python_transcription(scene_name, fb_w, fb
                     if g["obj"] >= 0 and lt.objs[g["obj"]].kind != 9 and F(lt.objs[g["obj"]].reflectivity if lt.objs[g["obj"]].override_sr else lt.mats[lt.objs[g["obj"]].mat_a].reflectivity) >= MIRROR_THRESHOLD:
                         saw_mirror = True
             assert lt.rays == o.stats()["rays"], (scene_name, frame, "Scene.Hit invocations")
-    assert saw_mesh == (scene.n_meshes > 0), "the mesh must be in view, or MeshBVH.Hit is not exercised on primary rays"
+    assert saw_mesh == mesh_in_view, "the mesh must be in view, or MeshBVH.Hit is not exercised on primary rays"
     if scene_name == "test":
         assert saw_mirror, "the mirror sphere must be in view, or the mirror branch is not exercised"
     o.close()
