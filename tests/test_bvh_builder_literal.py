@@ -7,6 +7,7 @@ compared with the mirror's in test_host.py.  Array.Sort (the builders' fallback)
 16 items, where .NET's introsort is an insertion sort: that path is transcribed too (Builder.sort_range).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -362,3 +363,49 @@ def test_introsort_transcription_equals_the_oracle_restatement(n, distinct):
     assert (np.diff(k2) >= 0).all()
     if distinct < n // 4:
         assert payload.tolist() != sorted(range(n), key=lambda i: (keys[i], i)), "the order must differ from a stable sort, or the case proves nothing"
+
+
+def _mesh_tree(make_scene, serial, task_items=None):
+    old = os.environ.pop("YCGE_HOST_SERIAL_BVH", None)
+    os.environ.pop("YCGE_HOST_BVH_TASK_ITEMS", None)
+    if serial:
+        os.environ["YCGE_HOST_SERIAL_BVH"] = "1"
+    if task_items:
+        os.environ["YCGE_HOST_BVH_TASK_ITEMS"] = str(task_items)
+    try:
+        s = make_scene()
+        t = s.bvh_arrays(0)
+        out = dict(root=t["root"], boxes=t["boxes"].copy(), lrsc=t["lrsc"].copy(), leaf=t["leaf"].copy(), sort_fallbacks=t["sort_fallbacks"])
+        s.close()
+        return out
+    finally:
+        os.environ.pop("YCGE_HOST_SERIAL_BVH", None)
+        os.environ.pop("YCGE_HOST_BVH_TASK_ITEMS", None)
+        if old is not None:
+            os.environ["YCGE_HOST_SERIAL_BVH"] = old
+
+
+@pytest.mark.parametrize("name", ["teapot", "knot:300x40", "bunny", "degenerate"])
+def test_threaded_mesh_builder_gives_the_serial_tree(name):
+    """csrc/bvh_build_parallel.hpp: the top of the tree cut like the serial builder cuts it, subtrees built on other threads, pieces
+    concatenated in pre-order.  Node for node, leaf reference for leaf reference and fallback for fallback the serial tree
+    (which the literal transcription above pins) -- also on a mesh of stacked duplicate triangles, where ranges of identical
+    centroids force the Array.Sort fallback inside the tasks and in the top cuts."""
+    if name == "degenerate":
+        rng = np.random.default_rng(3)
+        base = rng.uniform(-1, 1, (90, 3)).astype(F)
+        centres = np.repeat(base, 70, axis=0)                                       # 6300 triangles, 70 copies at each of 90 places
+        verts = np.concatenate([centres + F(0.01) * np.array(d, F) for d in ((1, 0, 0), (0, 1, 0), (0, 0, 1))]).astype(F)
+        n = len(centres)
+        faces = np.stack([np.arange(n), np.arange(n) + n, np.arange(n) + 2 * n], axis=1).astype(np.int32)
+        make = lambda: api.HostScene.from_triangles("degenerate", verts, faces)
+    else:
+        make = lambda: api.HostScene(name)
+    ser = _mesh_tree(make, serial=True)
+    for task_items in (None, 16):                                                  # default task size; top cuts down to 16 items
+        par = _mesh_tree(make, serial=False, task_items=task_items)
+        assert par["root"] == ser["root"] and par["sort_fallbacks"] == ser["sort_fallbacks"], (name, task_items)
+        for k in ("boxes", "lrsc", "leaf"):
+            assert np.array_equal(par[k], ser[k]), (name, task_items, k)
+    if name == "degenerate":
+        assert ser["sort_fallbacks"] > 0

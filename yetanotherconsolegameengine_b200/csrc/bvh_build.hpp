@@ -147,7 +147,29 @@ class SahBuilder {
     int32_t build(BuildItem *arr, int start, int count) {
         if (count <= 0) return -1;
         if (count <= leaf_) return make_leaf(arr, start, count);
-
+        const int mid = choose_mid(arr, start, count);
+        int32_t me = (int32_t)nodes.size();
+        nodes.push_back(TmpNode{});
+        int32_t l = build(arr, start, mid - start);
+        int32_t r = build(arr, mid, start + count - mid);
+        nodes[me] = join(l, r);
+        return me;
+    }
+    bool is_leaf_range(int count) const { return count <= leaf_; }
+    // an inner node from its finished children (BVH.cs:430-457)
+    TmpNode join(int32_t l, int32_t r) const {
+        TmpNode cur{};
+        cur.left = l; cur.right = r; cur.start = 0; cur.count = 0;
+        if (l >= 0 && r >= 0) {
+            for (int k = 0; k < 3; k++) {
+                cur.box.lo[k] = net_min(nodes[l].box.lo[k], nodes[r].box.lo[k]);
+                cur.box.hi[k] = net_max(nodes[l].box.hi[k], nodes[r].box.hi[k]);
+            }
+        } else cur.box = nodes[l >= 0 ? l : r].box;
+        return cur;
+    }
+    // where a range of more than leaf-size items is cut: items [start, mid) go left (the range is permuted in place)
+    int choose_mid(BuildItem *arr, int start, int count) {
         float cmin[3] = {arr[start].c[0], arr[start].c[1], arr[start].c[2]};
         float cmax[3] = {cmin[0], cmin[1], cmin[2]};
         for (int i = start + 1; i < start + count; i++)
@@ -227,21 +249,7 @@ class SahBuilder {
             mid = i0;
             if (mid == start || mid == start + count) mid = median_split(arr, start, count, best_axis);
         }
-
-        int32_t me = (int32_t)nodes.size();
-        nodes.push_back(TmpNode{});
-        int32_t l = build(arr, start, mid - start);
-        int32_t r = build(arr, mid, start + count - mid);
-        TmpNode cur{};
-        cur.left = l; cur.right = r; cur.start = 0; cur.count = 0;
-        if (l >= 0 && r >= 0) {
-            for (int k = 0; k < 3; k++) {
-                cur.box.lo[k] = net_min(nodes[l].box.lo[k], nodes[r].box.lo[k]);
-                cur.box.hi[k] = net_max(nodes[l].box.hi[k], nodes[r].box.hi[k]);
-            }
-        } else cur.box = nodes[l >= 0 ? l : r].box;
-        nodes[me] = cur;
-        return me;
+        return mid;
     }
 
   private:
@@ -268,6 +276,7 @@ class SahBuilder {
 
 } // namespace detail
 
+namespace detail { inline void to_flat(SahBuilder &b, FlatTree &out); }
 // Build the reference tree over `items` (which is permuted in place, as the reference permutes its Item[]).
 inline void build_reference_tree(std::vector<BuildItem> &items, int leaf_size, bool mesh_variant, FlatTree &out) {
     out = FlatTree();
@@ -276,6 +285,10 @@ inline void build_reference_tree(std::vector<BuildItem> &items, int leaf_size, b
     b.nodes.reserve(2 * items.size());
     b.leaves.reserve(items.size());
     out.root = b.build(items.data(), 0, (int)items.size());
+    detail::to_flat(b, out);
+}
+namespace detail {
+inline void to_flat(SahBuilder &b, FlatTree &out) {
     size_t n = b.nodes.size();
     out.min_x.resize(n); out.min_y.resize(n); out.min_z.resize(n);
     out.max_x.resize(n); out.max_y.resize(n); out.max_z.resize(n);
@@ -289,6 +302,7 @@ inline void build_reference_tree(std::vector<BuildItem> &items, int leaf_size, b
     out.leaf_index = std::move(b.leaves);
     out.sort_fallbacks = b.fallbacks;
 }
+} // namespace detail
 
 // Triangle -> build item, MeshBVH.TryComputeBounds (MeshBVH.cs:351-361) and the centroid rule (MeshBVH.cs:55-57).
 inline BuildItem triangle_item(int index, const float *abc) {

@@ -180,7 +180,11 @@ MeshBVH::MeshBVH(const std::vector<Triangle> &tris) { // MeshBVH.cs:41-130
         nx[i] = nnx * invLen; ny[i] = nny * invLen; nz[i] = nnz * invLen;
     }
     if (n) triMat = tris[0].Mat; // MeshLoader gives every triangle the same defaultMaterial (MeshLoader.cs:82)
-    ycge::build_reference_tree(items, 8, true, tree);
+    // node for node the tree of the serial builder, subtrees built on the host's cores (csrc/bvh_build_parallel.hpp);
+    // YCGE_HOST_SERIAL_BVH=1 keeps one thread (tests compare the two)
+    const char *taskItems = getenv("YCGE_HOST_BVH_TASK_ITEMS"); // test hook: how small a range still is cut at the top
+    if (getenv("YCGE_HOST_SERIAL_BVH")) ycge::build_reference_tree(items, 8, true, tree);
+    else ycge::build_reference_tree_parallel(items, 8, true, tree, 0, taskItems ? atoi(taskItems) : 0);
 }
 bool Mesh::TryGetBounds(float &minX, float &minY, float &minZ, float &maxX, float &maxY, float &maxZ, float &cx, float &cy, float &cz) const { // MeshBVH.cs:585-603
     const ycge::FlatTree &t = bvh->tree;

@@ -8,7 +8,7 @@
 // File references are relative to /root/reference/ConsoleGame/.
 #pragma once
 #include "../../include/ycge.h"
-#include "../csrc/bvh_build.hpp"
+#include "../csrc/bvh_build_parallel.hpp"
 
 #include <cstdint>
 #include <functional>
