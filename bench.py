@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--ss", type=int, default=SS)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=240.0, help="cap of the timed part of --impl reference (complete frames)")
     return ap.parse_args()
 
 
@@ -113,15 +114,15 @@ def algorithmic_bytes(st, W, H, fb_w, fb_h, ss):
 
 
 def cpu_leg(args, fb_w, fb_h, ss, seconds, steps=None, warmup=1):
-    """The reference's CPU path (oracle restatement, reference thread partitioning) on a bounded sample of the workload:
-    same scene and pose at 1/16 of the cells (same ss), so Mrays/s is comparable and frames/s is scaled by the pixel ratio."""
+    """The reference's CPU path (oracle restatement, reference thread partitioning) on the workload itself: the same scene,
+    pose and FULL internal resolution; the sample is bounded in FRAMES (each one a complete TryFlipAndBlit), never in pixels.
+    `steps`: render exactly that many frames (the reference arm, capped by `seconds`); else as many as fit `seconds` (>= 2)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import yetanotherconsolegameengine_b200 as pkg
     from oracle_binding import Oracle
     cores = os.cpu_count() or 1
-    sfw, sfh = max(8, fb_w // 4), max(4, fb_h // 4)
     scene = pkg.HostScene(args.scene)
-    o = Oracle(scene, sfw, sfh, ss)
+    o = Oracle(scene, fb_w, fb_h, ss)
     if uses_bench_pose(args.scene):
         o.set_camera(*pkg.BENCH_POSE)
     for _ in range(warmup):
@@ -136,15 +137,13 @@ def cpu_leg(args, fb_w, fb_h, ss, seconds, steps=None, warmup=1):
         for k in stage:
             stage[k] += st[k]
         el = time.perf_counter() - t0
-        if (steps is not None and frames >= steps) or (steps is None and (el >= seconds or frames >= 64)):
+        if (steps is not None and frames >= steps) or (frames >= 2 and el >= seconds) or frames >= 64:
             break
     el = time.perf_counter() - t0
-    ratio = (sfw * sfh) / float(fb_w * fb_h)
     return {"value": rays / el / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-            "sample": f"{frames} frames of the same scene/pose at {sfw}x{sfh} cells ss={ss} ({sfw*ss}x{sfh*2*ss} px = {ratio:.4f} of the workload's pixels), "
-                      f"reference threading (trace on all cores; TAA, a-trous, exposure serial)",
-            "frames_per_s_sample": frames / el, "frames_per_s_scaled_to_workload": frames / el * ratio,
-            "ms_per_stage_sample": {k: v / frames for k, v in stage.items()}, "seconds": el, "frames": frames}
+            "sample": f"{frames} complete frames (after {warmup} untimed) of the workload itself: same scene/pose at the full {fb_w}x{fb_h} cells ss={ss} "
+                      f"({fb_w*ss}x{fb_h*2*ss} px), reference threading (trace on all {cores} cores; TAA, a-trous, exposure serial, RaytraceRenderer.cs:218-227)",
+            "frames_per_s": frames / el, "ms_per_stage": {k: v / frames for k, v in stage.items()}, "seconds": el, "frames": frames}
 
 
 def main():
@@ -160,11 +159,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        leg = cpu_leg(args, fb_w, fb_h, ss, seconds=0.0, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+        # every step is one complete frame of the headline configuration on all host cores; the run is capped at
+        # --ref-seconds of CPU time (a 1080p frame costs ~3 s on 16 cores, so the driver's 20 + 5 steps fit)
+        leg = cpu_leg(args, fb_w, fb_h, ss, seconds=args.ref_seconds, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
         line = {"impl": "reference", "metric": "Mrays/s", "value": leg["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * leg["seconds"] / leg["frames"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "frames_per_s": leg["frames_per_s_scaled_to_workload"],
-                "config": {"workload": workload, "note": "CPU restatement of the C# reference (no .NET toolchain here); each step is a bounded sample"},
+                "steps_run": leg["frames"], "ms_per_step": 1e3 * leg["seconds"] / leg["frames"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "frames_per_s": leg["frames_per_s"], "same_config": True,
+                "config": {"workload": workload, "note": "CPU restatement of the C# reference (no .NET toolchain here), all host cores; every step is a complete frame at the workload's full resolution"},
+                "stage_ms": leg["ms_per_stage"],
                 "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": leg["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
@@ -194,8 +196,13 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     n = max(1, world)
+    rc = 0
 
+    # what a scene switch costs (RaytraceEntity.cs:234-246): the host builds the scene (parse, normalise, both SAH trees),
+    # then the renderer is created and everything is uploaded and flattened; timed once, here, on the box's host
+    t_sw = time.perf_counter()
     scene = pkg.HostScene(args.scene)
+    scene_switch = {"host_build_ms": 1e3 * (time.perf_counter() - t_sw)}
     pose = pkg.BENCH_POSE if uses_bench_pose(args.scene) else scene.default_camera()[:3]
     stream = torch.cuda.Stream()
     pinned = torch.empty((fb_h * fb_w * api.CELL_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
@@ -204,7 +211,11 @@ def main():
     d2h = fb_w * fb_h * api.CELL_DTYPE.itemsize
 
     if n == 1:
+        torch.cuda.synchronize()
+        t_sw = time.perf_counter()
         r = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank)
+        torch.cuda.synchronize()
+        scene_switch["create_and_upload_ms"] = 1e3 * (time.perf_counter() - t_sw)
         r.SetCamera(*pose)
         r.set_stream(stream.cuda_stream)
         # untimed: one frame with the reference-defined event counters (feeds the algorithmic-bytes roofline)
@@ -333,7 +344,11 @@ def main():
                 run = lambda k: sr.render_pipelined(k)
             else:
                 run = lambda k: [sr.render_device() for _ in range(k)]
-            run(max(3, args.warmup))
+            # warm-up: every back slot of every rank, every staging-ring entry and every NCCL channel is used at least twice
+            # before the timed region (the frame-parallel pipeline is N x back slots frames deep)
+            back_slots = fp.S if fp is not None else 2
+            n_warm = max(3, args.warmup, 2 * n * back_slots + 2)
+            run(n_warm)
             torch.cuda.synchronize()
             st0 = b.r.stats()
             sampler = ClockSampler(local_rank)
@@ -385,7 +400,7 @@ def main():
                 n_ring = n * fp.S + 2  # as many host buffers as frames can be in flight (N ranks x back slots), or the host's pacing caps them
                 ring = [torch.empty((fb_h * fb_w * api.CELL_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True) for _ in range(n_ring)] if rank == 0 else None
                 cam = lambda f: fp.SetCamera(*pose)
-                fp.render(max(3, args.warmup), set_camera=cam, host_ring=ring)
+                fp.render(n_warm, set_camera=cam, host_ring=ring)
                 torch.cuda.synchronize()
                 dist.barrier()
                 t0 = time.perf_counter()
@@ -393,6 +408,35 @@ def main():
                 torch.cuda.synchronize()
                 dist.barrier()
                 stream_local = time.perf_counter() - t0
+            # ---- parity of the objects just timed (untimed): the next frames of the sharded paths against an unsharded context on
+            # rank 0's GPU that has rendered the same number of frames from the same start (static camera); cells bit for bit
+            parity = {}
+            n_chk = 2
+            if fp is not None:
+                done = fp.frame
+                got = fp.render(n_chk, collect=True)
+                torch.cuda.synchronize()
+                if rank == 0:
+                    full = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank)
+                    full.SetCamera(*pose)
+                    if done:
+                        full.render_frames_async(done)
+                        full.wait()
+                    parity["frames_in_parallel"] = all(fp.cells_host(g).tobytes() == full.TryFlipAndBlit().tobytes() for g in got)
+                    parity["frames_in_parallel_checked"] = "frames %d..%d" % (done + 1, done + n_chk)
+                    full.close()
+            done = b.r.stats()["frames"]
+            got = [sr.TryFlipAndBlit() for _ in range(n_chk)]
+            if rank == 0:
+                full = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank)
+                full.SetCamera(*pose)
+                if done:
+                    full.render_frames_async(int(done))
+                    full.wait()
+                parity["row_tiles_lock_step"] = all(g.tobytes() == full.TryFlipAndBlit().tobytes() for g in got)
+                parity["row_tiles_lock_step_checked"] = "frames %d..%d" % (done + 1, done + n_chk)
+                full.close()
+            dist.barrier()
         # max over ranks of the device time; rays summed over ranks (halo rows are traced redundantly and counted as
         # work done — rays/frame of the UNSHARDED frame is what the metric divides by, so use the unsharded count)
         all_stage = [None] * n
@@ -437,16 +481,18 @@ def main():
     else:
         kname, kbytes, kms = "atrous_chain_static_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
     achieved = kbytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
-    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this same command (single GPU)
+    # DRAM traffic of that kernel per launch: only from an `ncu --set full` capture of THIS build of the library and this
+    # command (tools/summarize_ncu.py records the sha256 of libycge.so beside dram__bytes_read.sum + dram__bytes_write.sum);
+    # a capture of any other build is not this run's traffic -> null
     traffic, traffic_src = None, None
     try:
-        if n == 1:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_full.json")))
-            key = next(k for k in cap if k.startswith("trace_stream_kernel<0>" if kname == "trace_kernel" else "atrous_chain_static_kernel"))
-            c0 = cap[key][-1]
-            to_b = lambda v: float(v.split()[0]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[v.split()[1]]
-            traffic = to_b(c0["dram__bytes_read.sum"]) + to_b(c0["dram__bytes_write.sum"])
-            traffic_src = "profiles/r01b_ncu_full.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+        import hashlib
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        sha = hashlib.sha256(open(api.LIB_PATH, "rb").read()).hexdigest()
+        if n == 1 and cap.get("lib_sha256") == sha and cap.get("workload") == f"{args.scene} {fb_w}x{fb_h} ss={ss}":
+            key = next(k for k in cap["kernels"] if k.startswith("trace_" if kname == "trace_kernel" else kname.split(" ")[0]))
+            traffic = float(cap["kernels"][key]["dram_bytes"])
+            traffic_src = "profiles/ncu_traffic.json (%s; dram__bytes_read.sum + dram__bytes_write.sum of %s, same libycge.so sha256)" % (cap.get("captured", "?"), key)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -459,12 +505,12 @@ def main():
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         leg = cpu_leg(args, fb_w, fb_h, ss, seconds=args.cpu_seconds)
-        cpu = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample", "frames_per_s_scaled_to_workload", "ms_per_stage_sample")}
+        cpu = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample", "frames_per_s", "ms_per_stage")}
 
     sync_e2e = {"value": e2e_mrays, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "SetCamera + TryFlipAndBlit per step, synchronous (the drop-in call; latency of one frame)"}
     if rank == 0:
-        line = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": max(3, args.warmup),
+        line = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": max(3, args.warmup) if n == 1 else n_warm,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "frames_per_s": fps, "rays_per_frame": rays_timed / args.steps, "mpaths_per_s": W * H * fps / 1e6,
                 "config": {"workload": workload, "scene": scene.name, "triangles": scene.counts()["triangles"], "parallelism": f"row-tiles x{n}" + ((", %d frames in flight on the GPU (value, e2e); strictly serial (e2e_synchronous, serial_schedule, stage_ms, roofline kernel time)" % slots) if n == 1 else (", frames in parallel: FRONT on row tiles, BACK + FINISH of whole frames round-robin over the ranks (value, e2e); row tiles in lock step" if mode == "frames" else
@@ -477,11 +523,16 @@ def main():
                 "e2e": streaming if streaming else sync_e2e, "e2e_synchronous": sync_e2e,
                 **({"serial_schedule": serial, "frames_in_flight": slots} if n == 1 else {}),
                 "gpu_launches": launches_per_frame * args.steps * n,
+                **({"parity_vs_unsharded": bool(parity) and all(v for k, v in parity.items() if not k.endswith("_checked")), "parity_detail": parity} if n > 1 else {}),
+                "scene_switch_ms": scene_switch,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
+        if n > 1 and not line["parity_vs_unsharded"]:
+            sys.stderr.write("bench.py: the sharded frame differs from the unsharded frame: %r\n" % (parity,))
+            rc = 3
     if dist is not None:
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

@@ -312,9 +312,11 @@ std::shared_ptr<Scene> BuildCowScene();
 std::shared_ptr<Scene> BuildBunnyScene();
 std::shared_ptr<Scene> BuildTeapotScene();
 std::shared_ptr<Scene> BuildDragonScene(); // real xyzrgb_dragon.obj if present, else the procedural stand-in (labelled in Scene::Name)
-std::shared_ptr<Scene> BuildAllMeshesScene(int knotU = 1400, int knotV = 100); // cow, bunny, teapot, dragon (or its stand-in) in one scene
+std::shared_ptr<Scene> BuildAllMeshesScene(int knotU = 0, int knotV = 0); // cow, bunny, teapot, dragon (or its stand-in: bunny x4; a knot when knotU > 0) in one scene
+ObjData SubdivideMidpoint(const ObjData &in);
+ObjData DragonStandin(); // stanford-bunny with one level of midpoint subdivision, 277 804 triangles
 std::shared_ptr<Scene> BuildMeshScene(const ObjData &mesh, Material mat, const std::string &name, Vec3 targetPos = Vec3(0.0f, 0.5f, 1.0f));
-ObjData ProceduralKnot(int segU, int segV); // "dragon-standin": 2*segU*segV triangles
+ObjData ProceduralKnot(int segU, int segV); // procedural mesh of a chosen size (tests): 2*segU*segV triangles
 } // namespace MeshScenes
 namespace VolumeScenes { // structure of Scenes/VolumeScenes.cs:569-627 over a synthetic heightfield (generator is out of scope)
 std::shared_ptr<Scene> BuildSyntheticWorld(int worldSize, int worldHeight, int chunkSize, float daySeconds);
