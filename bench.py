@@ -437,6 +437,51 @@ def main():
                 parity["row_tiles_lock_step_checked"] = "frames %d..%d" % (done + 1, done + n_chk)
                 full.close()
             dist.barrier()
+            # ---- the same N GPUs behind ONE context of the library (ycge_config.n_devices, include/ycge.h): what the C# host gets
+            # from a single ycge_create.  Rank 0 drives all GPUs from one thread while the other ranks wait at the barrier.
+            in_library = None
+            torch.cuda.synchronize()
+            store = dist.distributed_c10d._get_default_store() # a HOST-side wait: an NCCL barrier would keep a kernel spinning on every other GPU
+            if rank != 0:
+                store.wait(["ycge_in_library_done"])
+            if rank == 0 and os.environ.get("YCGE_NO_INLIB"):
+                store.set("ycge_in_library_done", "1")
+            if rank == 0 and not os.environ.get("YCGE_NO_INLIB"):
+                try:
+                    ml = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, devices=list(range(n)))
+                    ml.SetCamera(*pose)
+                    depth = 2 * n
+                    ring_ml = [torch.empty((fb_h * fb_w * api.CELL_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
+                    ring_ml_np = [t_.numpy().view(api.CELL_DTYPE).reshape(fb_h, fb_w) for t_ in ring_ml]
+                    def ml_frames(k):
+                        ids = []
+                        for i_ in range(k):
+                            if len(ids) == depth:
+                                ml.frame_wait(ids.pop(0))
+                            ml.SetCamera(*pose)
+                            ids.append(ml.submit_frame(ring_ml_np[i_ % depth]))
+                        for fid in ids:
+                            ml.frame_wait(fid)
+                    ml_frames(n_warm)
+                    t0 = time.perf_counter()
+                    ml_frames(args.steps)
+                    ml_s = time.perf_counter() - t0
+                    done = n_warm + args.steps
+                    full = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank)
+                    full.SetCamera(*pose)
+                    full.render_frames_async(done)
+                    full.wait()
+                    same = all(ml.TryFlipAndBlit().tobytes() == full.TryFlipAndBlit().tobytes() for _ in range(2))
+                    full.close()
+                    ml.close()
+                    in_library = {"frames_per_s": args.steps / ml_s, "value": st_events["rays"] * args.steps / ml_s / 1e6, "unit": "Mrays/s", "parity_vs_one_device": same,
+                                  "d2h_bytes_per_step": d2h, "api": "ONE ycge_create with n_devices = %d, SetCamera + ycge_submit_frame per step from one host thread, ycge_frame_wait %d frames later; "
+                                                                    "every frame's cells copied to pinned host memory" % (n, depth)}
+                    parity["in_library"] = same
+                except Exception as e:  # noqa: BLE001
+                    in_library = {"error": str(e)[:300]}
+                store.set("ycge_in_library_done", "1")
+            dist.barrier()
         # max over ranks of the device time; rays summed over ranks (halo rows are traced redundantly and counted as
         # work done — rays/frame of the UNSHARDED frame is what the metric divides by, so use the unsharded count)
         all_stage = [None] * n
@@ -520,10 +565,14 @@ def main():
                                               "front_tiles_cell_rows": [t[1] for t in front_tiles] if front_tiles else None} if n > 1 else {}),
                 # e2e: frames in flight (the host submits frame N while earlier frames finish; every frame's cells are copied to pinned
                 # host memory inside the timed region).  e2e_synchronous: the strict drop-in call, one frame's latency per step.
-                "e2e": streaming if streaming else sync_e2e, "e2e_synchronous": sync_e2e,
+                # on N GPUs the call a user makes is ONE ycge_create over all of them (in_library); the one-process-per-GPU NCCL path is e2e_per_process
+                "e2e": ({"value": in_library["value"], "unit": "Mrays/s", "frames_per_s": in_library["frames_per_s"], "h2d_bytes_per_step": h2d * n, "d2h_bytes_per_step": d2h, "api": in_library["api"]}
+                        if (n > 1 and in_library and "value" in in_library) else (streaming if streaming else sync_e2e)),
+                **({"e2e_per_process": streaming} if (n > 1 and streaming) else {}), "e2e_synchronous": sync_e2e,
                 **({"serial_schedule": serial, "frames_in_flight": slots} if n == 1 else {}),
                 "gpu_launches": launches_per_frame * args.steps * n,
                 **({"parity_vs_unsharded": bool(parity) and all(v for k, v in parity.items() if not k.endswith("_checked")), "parity_detail": parity} if n > 1 else {}),
+                **({"in_library": in_library} if n > 1 else {}),
                 "scene_switch_ms": scene_switch,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))

@@ -188,6 +188,17 @@ typedef struct ycge_config {
     int32_t tile_row0;        /* first cell row owned by this ctx (row-tile sharding); 0 for a whole frame */
     int32_t tile_rows;        /* number of cell rows owned; 0 => fb_h - tile_row0 */
     ycge_params params;
+    /* Several GPUs of one box behind ONE context ("device list 1/2/4/8").  n_devices >= 2: the library owns
+     * devices[0 .. n_devices), enables peer access between them and renders frames in parallel: every GPU traces and
+     * TAA-blends a row tile of each frame (scene replicated, tiles balanced by measured trace time), the tiles' history +
+     * guide rows go by peer copies over NVLink to the GPU that runs this frame's a-trous passes, exposure and cell
+     * conversion (round robin), the 16-byte exposure state travels GPU to GPU in frame order, and the cells land in the
+     * caller's buffer -- bit-identical to a one-GPU context.  Such a context takes the scene / camera / light calls and
+     * ycge_render_frame, ycge_submit_frame / ycge_frame_wait (up to 2 * n_devices frames in flight), ycge_wait,
+     * ycge_get_stats, ycge_get_frame_counter.  n_devices 0 or 1: one GPU, `device`.  tile_row0 / tile_rows must be 0.  An ordinal may
+     * be listed more than once (several tiles on one GPU; the test suite does that on a one-GPU box). */
+    int32_t n_devices;
+    int32_t devices[8];
 } ycge_config;
 
 /* ---- One console cell = one Chexel (Renderer/Chexel.cs:99-125) plus the two quantisations
@@ -254,10 +265,14 @@ YCGE_API int ycge_globals_update(ycge_ctx *ctx, const float bg_top[3], const flo
 /* ---- per frame -------------------------------------------------------------------------- */
 YCGE_API int ycge_set_camera(ycge_ctx *ctx, const float pos[3], float yaw, float pitch);         /* SetCamera  RaytraceRenderer.cs:140-148 */
 YCGE_API int ycge_set_fov(ycge_ctx *ctx, float fov_deg);                                          /* SetFov     RaytraceRenderer.cs:150-153 */
-YCGE_API int ycge_reset_history(ycge_ctx *ctx);
+YCGE_API int ycge_reset_history(ycge_ctx *ctx);                                                   /* scene.HasDynamicTextures / scene switch */
 /* Two forms of the trace kernel with bit-identical results: 0 = one thread per pixel path, 1 (default) = ray stream (every
- * lane carries one ray per round through a single traversal, finished lanes are refilled with new pixels at once). */
-YCGE_API int ycge_set_trace_variant(ycge_ctx *ctx, int32_t variant);                                                   /* scene.HasDynamicTextures / scene switch */
+ * lane carries one ray per round through a single traversal; a warp takes its next 8x4 pixel tile when all of its lanes
+ * are done -- refilling single lanes was measured slower, see csrc/trace_stream.cuh). */
+YCGE_API int ycge_set_trace_variant(ycge_ctx *ctx, int32_t variant);
+/* Two forms of the in-place a-trous iteration (RaytraceRenderer.cs:718) with bit-identical results: 0 (default) = one warp
+ * per chain, rows handed over through L2 (csrc/post.cuh); 1 = systolic bands in lock step (csrc/wavefront.cuh). */
+YCGE_API int ycge_set_inplace_variant(ycge_ctx *ctx, int32_t variant);
 /* TryFlipAndBlit (RaytraceRenderer.cs:157-267): synchronous; writes tile_rows*fb_w cells (the ctx's tile;
  * the whole frame when unsharded) into caller-owned host memory, row stride `stride_cells` (0 => fb_w). */
 YCGE_API int ycge_render_frame(ycge_ctx *ctx, ycge_cell *out, int32_t stride_cells);

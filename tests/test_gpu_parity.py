@@ -90,6 +90,40 @@ def test_gpu_matches_golden(case):
     s.close()
 
 
+@pytest.mark.parametrize("case", make_golden.CASES, ids=[c[0] for c in make_golden.CASES])
+def test_systolic_in_place_pass_matches_golden(case):
+    """The other form of the in-place a-trous iteration (ycge_set_inplace_variant(1): bands of 4 rows in lock step, csrc/wavefront.cuh;
+    its schedule is replayed on the CPU by tests/test_wavefront_layout.py) against the same golden vectors."""
+    name, scene, fb_w, fb_h, ss, frames, pose = case
+    gold = np.load(os.path.join(GOLDEN, f"oracle_{name}.npz"))
+    s = api.HostScene(scene)
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    r.set_inplace_variant(1)
+    if pose is not None:
+        r.SetCamera(*pose)
+    for f in range(1, frames + 1):
+        cells = r.TryFlipAndBlit()
+        assert sha(r.debug_read(api.DBG_DENOISED)[..., :3]) == str(gold[f"sha_den_{f}"]), f"{name} frame {f}"
+        assert_cells_equal(cells, gold[f"cells_{f}"], f"{name} frame {f}")
+    r.close()
+    s.close()
+
+
+def test_systolic_in_place_pass_full_size_equals_the_default_form():
+    """1920x1080 (dragon stand-in, bench pose) and an odd-sized frame: both forms of the in-place pass, every denoised bit."""
+    for scene, fb_w, fb_h, ss, pose in (("dragon", 480, 135, 4, api.BENCH_POSE), ("bunny", 61, 23, 3, api.BENCH_POSE)):
+        s = api.HostScene(scene)
+        a, b = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss), api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+        b.set_inplace_variant(1)
+        for r in (a, b):
+            r.SetCamera(*pose)
+        for f in range(2):
+            ca, cb = a.TryFlipAndBlit(), b.TryFlipAndBlit()
+            assert bits_differ(a.debug_read(api.DBG_DENOISED), b.debug_read(api.DBG_DENOISED)) == 0, f"{scene} frame {f + 1}"
+            assert_cells_equal(ca, cb, f"{scene} frame {f + 1}")
+        a.close(); b.close(); s.close()
+
+
 # ------------------------------------------------------------------------------------------- live oracle, every tap
 LIVE = [  # scene, fb_w, fb_h, ss, frames, pose
     ("cornell", 60, 34, 1, 3, None),
@@ -485,6 +519,45 @@ def test_errors_are_loud():
     assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == -1
 
 
+def test_bad_caller_input_is_rejected_not_executed():
+    """negative counts, NULL arrays behind positive counts, a palette default outside the material table and bounce
+    limits beyond the device's branch stack must come back as a status, never as undefined behaviour or a C++ exception."""
+    lib = api.load_lib()
+    cfg = api.Config()
+    cfg.fb_w, cfg.fb_h, cfg.ss = 8, 4, 1
+    lib.ycge_default_params(C.byref(cfg.params))
+    ctx = C.c_void_p()
+    cfg.params.max_mirror_bounces = 16
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == -5 and b"max_mirror_bounces" in lib.ycge_last_error(None)
+    cfg.params.max_mirror_bounces = 2
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == 0
+    s = api.HostScene("volume_grid_test")
+    v = s.volume(0).contents
+    bad = api.Volume.from_buffer_copy(v)
+    bad.palette_n_ids = -3
+    assert lib.ycge_volume_upload(ctx, 0, C.byref(bad)) == -1
+    ok = api.Volume.from_buffer_copy(v)
+    ok.palette_default = 200  # inside [0, 254] but outside this scene's material table
+    assert lib.ycge_volume_upload(ctx, 0, C.byref(ok)) == 0
+    assert lib.ycge_scene_upload(ctx, s.flat) == -1 and b"default" in lib.ycge_last_error(ctx)
+    assert lib.ycge_volume_upload(ctx, 0, s.volume(0)) == 0
+    sc = api.Scene.from_buffer_copy(s.flat.contents)
+    sc.lights = None
+    assert sc.n_lights > 0 and lib.ycge_scene_upload(ctx, C.byref(sc)) == -1
+    m = api.MeshSoa()
+    m.n_tris = -1
+    m.bvh = C.pointer(api.Bvh())
+    assert lib.ycge_mesh_upload_soa(ctx, 0, C.byref(m)) == -1
+    m.n_tris = 4
+    assert lib.ycge_mesh_upload_soa(ctx, 0, C.byref(m)) == -1  # NULL triangle arrays
+    assert lib.ycge_set_inplace_variant(ctx, 7) == -1
+    assert lib.ycge_scene_upload(ctx, s.flat) == 0             # and the context is still usable
+    out = np.empty((4, 8), api.CELL_DTYPE)
+    assert lib.ycge_render_frame(ctx, out.ctypes.data, 0) == 0
+    lib.ycge_destroy(ctx)
+    s.close()
+
+
 # ------------------------------------------------------------------------------------------- BASELINE sizes
 def test_full_size_1080p_dragon_two_frames_vs_oracle():
     """The north-star workload at its real size (1920x1080 internal = 480x135 cells, ss = 4): two frames (the second
@@ -518,10 +591,51 @@ def test_full_size_mirror_spheres_1080p_vs_oracle():
     o.close()
 
 
+def _fullsize():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "fullsize_hashes.json")))
+
+
+def _frame_digest(r, cells):
+    import make_golden_fullsize
+    return make_golden_fullsize.frame_digest(cells, r.debug_read(api.DBG_PRIM_ID), r.debug_read(api.DBG_HDR), r.debug_read(api.DBG_TAA),
+                                            r.debug_read(api.DBG_DENOISED), r.stats())
+
+
+FULLSIZE = ["c3_cylinders_disks_triangles", "c3_boxes", "c3_bunny", "c3_teapot", "c4_voxel_world_1440p", "c4_voxel_island_1440p", "c5_dragon_2160p", "c5_dragon_1080p"]
+
+
+@pytest.mark.parametrize("name", FULLSIZE)
+def test_full_size_vs_oracle_hashes(name):
+    """BASELINE.json's configurations at their FULL sizes against the CPU oracle: the oracle rendered them once on the CPU
+    (tools/make_golden_fullsize.py -> tests/golden/fullsize_hashes.json: SHA-256 of the cells, the primary ids, the HDR / TAA /
+    denoised planes, plus ray count and exposure scalars); the GPU must reproduce every digest.  C3: showcase scenes and meshes
+    at 1920x1080 with TAA accumulated over 64 frames; C4: both voxel worlds at 2560x1440; C5: the dragon at 3840x2160."""
+    import make_golden_fullsize
+    gold = _fullsize().get(name)
+    if gold is None:
+        pytest.fail(f"{name} is missing from tests/golden/fullsize_hashes.json: run tools/make_golden_fullsize.py {name}")
+    scene, fb_w, fb_h, ss, frames, pose = make_golden_fullsize.CASES[name]
+    s = api.HostScene(scene)
+    assert s.name == gold["scene"] and s.counts()["triangles"] == gold["triangles"]
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    if pose is not None:
+        r.SetCamera(*pose)
+    for f in range(1, max(frames) + 1):
+        if f in frames:
+            cells = r.TryFlipAndBlit()
+            got, want = _frame_digest(r, cells), gold["frames"][str(f)]
+            bad = [k for k in want if got[k] != want[k]]
+            assert not bad, f"{name} frame {f}: {bad} differ from the oracle"
+        else:
+            r.TryFlipAndBlit()
+    r.close()
+    s.close()
+
+
 def test_full_size_properties_voxel_world_1440p():
-    """BASELINE config 4 geometry (1024x256x1024 voxel world in 32^3 chunks, 2560x1440 internal): too slow for the CPU
-    oracle in a test, so size-independent properties: deterministic across contexts, frame 1 history == current HDR,
-    sky mask consistent with primary ids, all cells inside the ANSI cube, exposure inside its clamp."""
+    """Size-independent properties at config 4's size (the digests above pin the values): deterministic across contexts, frame 1
+    history == current HDR, sky mask consistent with primary ids, all cells inside the ANSI cube, exposure inside its clamp."""
     s = api.HostScene("voxel_world")
     a = api.CudaRaytraceRenderer(s, 320, 90, 8)
     b = api.CudaRaytraceRenderer(s, 320, 90, 8)
@@ -533,11 +647,69 @@ def test_full_size_properties_voxel_world_1440p():
     assert np.array_equal(prim[..., 0] < 0, sky != 0)
     assert 0.05 < (sky != 0).mean() < 0.95
     assert ca["fg_ansi"].min() >= 16 and ca["fg_ansi"].max() <= 231 and np.all(ca["glyph"] == 0x2580)
-    ca2, cb2 = a.TryFlipAndBlit(), b.TryFlipAndBlit()
-    assert_cells_equal(ca2, cb2, "determinism frame 2")
     assert 0.10 <= a.stats()["ae_exposure"] <= 1.50
     a.close()
     b.close()
+
+
+# ------------------------------------------------------------------------------------------- several GPUs behind one context
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss,n,pose", [("boxes", 40, 24, 2, 3, None), ("knot:60x16", 48, 27, 4, 4, api.BENCH_POSE), ("mirror_spheres", 33, 9, 1, 2, None),
+                                                       ("voxel_world:64x64", 40, 12, 2, 5, None), ("entities_demo", 40, 16, 2, 3, None)])
+def test_multi_device_context_equals_one_device_context(scene, fb_w, fb_h, ss, n, pose):
+    """ycge_config.n_devices >= 2 (include/ycge.h): ONE context, the library renders frames in parallel over the listed devices --
+    FRONT on balanced row tiles, peer copies into a back slot of the frame's root device, BACK and FINISH there, exposure state
+    handed on in frame order.  Here the list names device 0 n times (this box may have one GPU; tests/test_multigpu.py runs it
+    over distinct GPUs): frames submitted several at a time, a moving camera, moving lights; every cell equals the one-device frame."""
+    s = api.HostScene(scene)
+    one = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    many = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss, devices=[0] * n)
+    if pose is None:
+        pose = s.default_camera()[:3]
+    bufs = [np.empty((fb_h, fb_w), api.CELL_DTYPE) for _ in range(2 * n)]
+    frame = 0
+    for batch in (1, 2 * n, 3, n + 1):
+        ids, want = [], []
+        for k in range(batch):
+            p = ((pose[0][0] + 0.0005 * frame, pose[0][1], pose[0][2] + (0.02 if frame == 5 else 0.0)), pose[1], pose[2])
+            if scene == "entities_demo":
+                s.update(16.0)
+                for r in (one, many):
+                    r.SyncLights(s)
+                    r.SyncGeometry(s)
+            one.SetCamera(*p)
+            many.SetCamera(*p)
+            want.append(one.TryFlipAndBlit())
+            ids.append(many.submit_frame(bufs[k]))
+            frame += 1
+        for k, fid in enumerate(ids):
+            many.frame_wait(fid)
+            assert_cells_equal(bufs[k], want[k], f"{scene} x{n}: frame {frame - batch + k + 1}")
+    assert_cells_equal(many.TryFlipAndBlit(), one.TryFlipAndBlit(), "the synchronous call on the multi-device context")
+    st1, stn = one.stats(), many.stats()
+    assert stn["frames"] == st1["frames"] == frame + 1
+    assert np.float32(stn["ae_exposure"]).view(np.uint32) == np.float32(st1["ae_exposure"]).view(np.uint32)
+    many.close(); one.close(); s.close()
+
+
+def test_multi_device_context_refuses_what_it_cannot_do():
+    lib = api.load_lib()
+    cfg = api.Config()
+    cfg.fb_w, cfg.fb_h, cfg.ss = 16, 8, 1
+    lib.ycge_default_params(C.byref(cfg.params))
+    cfg.n_devices = 2
+    cfg.devices[0], cfg.devices[1] = 0, 99
+    ctx = C.c_void_p()
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == -1
+    cfg.devices[1] = 0
+    cfg.tile_rows = 4
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == -1
+    cfg.tile_rows = 0
+    assert lib.ycge_create(C.byref(cfg), C.byref(ctx)) == 0
+    out = np.empty((8, 16), api.CELL_DTYPE)
+    assert lib.ycge_render_frame(ctx, out.ctypes.data, 0) == -3  # no scene yet
+    assert lib.ycge_frame_begin(ctx) == -1 and b"multi-GPU" in lib.ycge_last_error(ctx)
+    assert lib.ycge_debug_read(ctx, api.DBG_HDR, out.ctypes.data, out.nbytes) == -1
+    lib.ycge_destroy(ctx)
 
 
 # ------------------------------------------------------------------------------------------- row tiles (sharding kernels)

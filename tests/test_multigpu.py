@@ -24,3 +24,27 @@ def test_sharded_frame_equals_unsharded_on_real_gpus(scene, fb_w, fb_h, ss):
         assert r.returncode == 0, r.stdout[-2000:]
         assert "!= unsharded" not in r.stdout, r.stdout[-2000:]
         assert r.stdout.count(": sharded x") == 3 and r.stdout.count("== unsharded") >= 3, r.stdout[-2000:]  # + the pipelined frames with the peer hand-off
+
+
+def test_multi_device_context_on_real_gpus():
+    """ycge_config.n_devices over DISTINCT GPUs (peer copies over NVLink, cross-device events): equal to the one-GPU frame, bit for bit."""
+    import numpy as np
+    import torch
+    from yetanotherconsolegameengine_b200 import api
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    for scene, fb_w, fb_h, ss, pose in (("knot:60x16", 96, 54, 4, api.BENCH_POSE), ("dragon", 480, 135, 4, api.BENCH_POSE)):
+        s = api.HostScene(scene)
+        one = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+        many = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss, devices=list(range(n)))
+        one.SetCamera(*pose)
+        many.SetCamera(*pose)
+        bufs = [np.empty((fb_h, fb_w), api.CELL_DTYPE) for _ in range(2 * n)]
+        for batch in (1, 2 * n, n + 1):
+            want = [one.TryFlipAndBlit() for _ in range(batch)]
+            ids = [many.submit_frame(bufs[k]) for k in range(batch)]
+            for k, fid in enumerate(ids):
+                many.frame_wait(fid)
+                assert bufs[k].tobytes() == want[k].tobytes(), f"{scene}: frame {k} of a batch of {batch} on {n} GPUs"
+        many.close(); one.close(); s.close()

@@ -82,7 +82,7 @@ class Params(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("fb_w", C.c_int32), ("fb_h", C.c_int32), ("ss", C.c_int32), ("device", C.c_int32), ("tile_row0", C.c_int32),
-                ("tile_rows", C.c_int32), ("params", Params)]
+                ("tile_rows", C.c_int32), ("params", Params), ("n_devices", C.c_int32), ("devices", C.c_int32 * 8)]
 
 
 class Halo(C.Structure):
@@ -117,7 +117,7 @@ PTR_CELLS, PTR_LOG_SAMPLES, PTR_HIST, PTR_GND, PTR_GAS, PTR_EXPOSURE = 0, 1, 2, 
 ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
     "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_texture_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
-    "ycge_set_camera", "ycge_set_fov", "ycge_set_trace_variant", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
+    "ycge_set_camera", "ycge_set_fov", "ycge_set_trace_variant", "ycge_set_inplace_variant", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
     "ycge_render_frames_async", "ycge_wait", "ycge_pipeline_config", "ycge_submit_frame", "ycge_frame_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
     "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
     "ycge_frame_finish", "ycge_frame_front", "ycge_back_config", "ycge_back_ptr", "ycge_back_denoise", "ycge_back_finish", "ycge_ansi_emit", "ycge_device_ptr",
@@ -155,6 +155,7 @@ def load_lib() -> C.CDLL:
         lib.ycge_set_camera.argtypes = [vp, vp, C.c_float, C.c_float]
         lib.ycge_set_fov.argtypes = [vp, C.c_float]
         lib.ycge_set_trace_variant.argtypes = [vp, C.c_int32]
+        lib.ycge_set_inplace_variant.argtypes = [vp, C.c_int32]
         lib.ycge_reset_history.argtypes = [vp]
         lib.ycge_render_frame.argtypes = [vp, vp, C.c_int32]
         lib.ycge_render_frame_stats.argtypes = [vp, vp, C.c_int32]
@@ -230,6 +231,8 @@ def load_host() -> C.CDLL:
         h.ycgeh_scene_bvh.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(Bvh)), C.POINTER(C.c_uint64)]
         h.ycgeh_renderer_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         h.ycgeh_renderer_create.restype = vp
+        h.ycgeh_renderer_create_multi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        h.ycgeh_renderer_create_multi.restype = vp
         h.ycgeh_renderer_destroy.argtypes = [vp]
         h.ycgeh_renderer_destroy.restype = None
         h.ycgeh_renderer_ctx.argtypes = [vp]
@@ -414,14 +417,20 @@ class CudaRaytraceRenderer:
     """Mirror of RaytraceRenderer's public surface (RaytraceRenderer.cs:74,110,140,150,157) behind IConsoleRenderer,
     producing frames through libycge.so.  ``tile_row0/tile_rows`` select a row tile for one-process-per-GPU sharding."""
 
-    def __init__(self, scene: HostScene, fb_w: int, fb_h: int, super_sample: int = 1, device: int = 0, tile_row0: int = 0, tile_rows: int = 0):
+    def __init__(self, scene: HostScene, fb_w: int, fb_h: int, super_sample: int = 1, device: int = 0, tile_row0: int = 0, tile_rows: int = 0, devices=None):
+        """``devices``: two or more CUDA ordinals of one box -> ONE renderer over all of them (ycge_config.n_devices): frames in parallel
+        inside the library, bit-identical to a one-GPU renderer; TryFlipAndBlit, submit_frame / frame_wait, wait, stats."""
         self._h = load_host()
         self._lib = load_lib()
         self.scene = scene
         self.fb_w, self.fb_h, self.ss = fb_w, fb_h, max(1, super_sample)
         self.tile_row0 = tile_row0
         self.tile_rows = tile_rows if tile_rows > 0 else fb_h - tile_row0
-        self.handle = self._h.ycgeh_renderer_create(scene.handle, fb_w, fb_h, self.ss, device, tile_row0, tile_rows)
+        if devices is not None and len(devices) >= 2:
+            arr = (C.c_int * len(devices))(*devices)
+            self.handle = self._h.ycgeh_renderer_create_multi(scene.handle, fb_w, fb_h, self.ss, len(devices), arr)
+        else:
+            self.handle = self._h.ycgeh_renderer_create(scene.handle, fb_w, fb_h, self.ss, device, tile_row0, tile_rows)
         if not self.handle:
             raise YcgeError(-2, self._h.ycgeh_last_error().decode())
         self.ctx = C.c_void_p(self._h.ycgeh_renderer_ctx(self.handle))
@@ -492,6 +501,10 @@ class CudaRaytraceRenderer:
     def set_trace_variant(self, variant: int):
         """0: one thread per pixel path; 1 (default): ray stream with lane refill.  Bit-identical results."""
         self._ck(self._lib.ycge_set_trace_variant(self.ctx, variant))
+
+    def set_inplace_variant(self, variant: int):
+        """0 (default): one warp per chain of the in-place a-trous iteration; 1: systolic bands (wavefront.cuh).  Bit-identical."""
+        self._ck(self._lib.ycge_set_inplace_variant(self.ctx, variant))
 
     def lights_update(self, lights):
         """Per-frame light changes without re-uploading geometry (DayNightCycle.cs:80-83): [(pos3, color3, intensity), ...]"""

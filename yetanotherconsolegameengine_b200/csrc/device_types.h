@@ -99,6 +99,7 @@ struct TraceParams {
     int diffuse_bounces, max_mirror_bounces, max_refractions;
     float mirror_threshold, eps, sigma_rad;
     unsigned long long seed_salt;
+    int *host_err; // mapped host memory: a pixel whose traversal overflowed the device stack sets bit 1 (the frame call then fails)
 };
 
 struct TraceCounters { // device-side, zeroed at the start of every frame

@@ -944,7 +944,7 @@ __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScen
     unsigned int rays = cnt.rays;
     for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
     if (lane == 0 && rays) { atomicAdd(&counters->rays, (unsigned long long)rays); atomicAdd(&totals->rays_total, (unsigned long long)rays); }
-    if (cnt.overflow) atomicAdd(&counters->stack_overflow, (unsigned long long)cnt.overflow);
+    if (cnt.overflow) { atomicAdd(&counters->stack_overflow, (unsigned long long)cnt.overflow); if (tp.host_err) *(volatile int *)tp.host_err = 2; }
     if (STATS) {
         unsigned int vals[6] = {cnt.top_nodes, cnt.mesh_nodes, cnt.leaf_refs, cnt.tris, cnt.prims, cnt.dda};
         unsigned long long *dst[6] = {&counters->top_nodes, &counters->mesh_nodes, &counters->leaf_refs, &counters->tris, &counters->prims, &counters->dda};

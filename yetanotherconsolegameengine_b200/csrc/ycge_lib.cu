@@ -1,6 +1,7 @@
 // ycge_lib.cu — the C ABI of include/ycge.h: context, scene flattening into HBM, per-frame launch sequence.
 // Product code: no CPU fallback.  Every entry point fails loudly (negative status + message) when CUDA is not usable.
 #include "post.cuh"
+#include "wavefront.cuh"
 #include "trace_stream.cuh"
 #include "bvh_build.hpp"
 
@@ -66,7 +67,10 @@ struct VolumeStore {
 
 } // namespace
 
+struct YcgeGroup;
 struct ycge_ctx {
+    std::unique_ptr<YcgeGroup> group; // several GPUs behind this context (ycge_multi.inl); every other member then describes the frame only
+    ~ycge_ctx();
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -145,6 +149,9 @@ struct ycge_ctx {
     bool peers = false, has_above = false, has_below = false;
     void *ipc_opened[3] = {nullptr, nullptr, nullptr};
     bool fast_div = false; // the FMA division sequence was verified against IEEE division for these four divisors
+    volatile int *wave_err_host = nullptr; // pinned, mapped: set by a wavefront kernel whose poll gave up (a value that never arrived)
+    int *wave_err_dev = nullptr;
+    bool use_wave = false;             // stride-2 in-place pass: true = the systolic form (wavefront.cuh, bit-identical, measured SLOWER: 3.1 vs 2.2 ms at 1080p); false: one warp per chain (post.cuh)
     DevBuf<unsigned int> tickets;      // [0]: plain wavefront launches, [1]: peer-storing launches (dispatch-order tickets)
     std::vector<unsigned int> ticket_bases = std::vector<unsigned int>(132, 0u); // host mirror of the counters
     unsigned int ticket_base_of(int peer, int slot) const { return ticket_bases[peer ? 1 : 2 * slot + 2]; }
@@ -201,6 +208,21 @@ int fail(ycge_ctx *ctx, int code, const std::string &msg) {
     tl_error = msg;
     if (ctx) ctx->err = msg;
     return code;
+}
+// No C++ exception may cross the C ABI (a P/Invoke or ctypes host would abort): every exported function that allocates is a
+// function-try-block ending in YCGE_CATCH.
+#define YCGE_CATCH                                                                                                          \
+    catch (const std::bad_alloc &) { return fail(nullptr, YCGE_ERR_LIMIT, "out of host memory"); }                          \
+    catch (const std::exception &e) { return fail(nullptr, YCGE_ERR_INVALID, std::string("exception: ") + e.what()); }      \
+    catch (...) { return fail(nullptr, YCGE_ERR_INVALID, "unknown exception"); }
+int wave_check(ycge_ctx *c) { // after a wait: did a kernel of the frame(s) just finished raise the mapped "failed" flag?
+    if (c->wave_err_host && *c->wave_err_host) {
+        const int e = *c->wave_err_host;
+        *c->wave_err_host = 0;
+        if (e & 2) return fail(c, YCGE_ERR_LIMIT, "traversal stack overflow (tree deeper than the device stack): the frame is not valid");
+        return fail(c, YCGE_ERR_CUDA, "in-place a-trous wavefront: a filtered value it waited for never arrived (poll limit reached; a peer or an earlier launch failed)");
+    }
+    return 0;
 }
 #define CK(ctx, call)                                                                                   \
     do {                                                                                                \
@@ -484,6 +506,7 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
         tp.diffuse_bounces = c->P.diffuse_bounces; tp.max_mirror_bounces = c->P.max_mirror_bounces; tp.max_refractions = c->P.max_refractions;
         tp.mirror_threshold = c->P.mirror_threshold; tp.eps = c->P.eps; tp.sigma_rad = c->P.diffuse_sigma_deg * (3.14159274f / 180.0f); // :460
         tp.seed_salt = c->P.seed_salt;
+        tp.host_err = c->wave_err_dev;
         // Frames in flight on this GPU: the thread-per-path form, whose CTAs come and go, shares the SMs better with the resident
         // wavefront kernels of the previous frames than the persistent ray-stream form does (measured, 3 slots: 300 against 284
         // frames/s); a frame that has the GPU to itself takes the ray-stream form (1.09 against 1.18 ms).  Same results either way.
@@ -572,14 +595,25 @@ int denoise_run(ycge_ctx *c) {
         if (d.cur_id == d.dst_id) {
             // in-place pass on scratch X: OLD = X, NEW = the other scratch (dead at this point), which then becomes X
             const int X = d.cur_id, Y = (X == 1) ? 2 : 1;
+            const bool wave = step == 2 && c->use_wave; // the systolic form covers the stride of the reference's one in-place pass
             if (!d.pending) {
-                if (pre.n < (size_t)W * H * 25) { CK(c, cudaDeviceSynchronize()); CK(c, pre.alloc((size_t)W * H * 25)); }
                 // (1) everything that does not depend on new values, fully parallel
-                AtrousPreArgs pa;
-                pa.old_ = d.phys[X]; pa.gnd = gnd; pa.gas = gas; pa.pre = pre.p; pa.plane = (size_t)W * H;
-                pa.W = W; pa.H = H; pa.y0 = a; pa.y1 = b; pa.step = step; pa.e = ed;
-                if (fast) atrous_pre_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
-                else atrous_pre_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
+                if (wave) {
+                    const WfGeom wg = wf_geom(W, H, a, b);
+                    const size_t need = std::max((size_t)W * H * 25, wf_record_count(wg));
+                    if (pre.n < need) { CK(c, cudaDeviceSynchronize()); CK(c, pre.alloc(need)); }
+                    WavePreArgs pa;
+                    pa.old_ = d.phys[X]; pa.gnd = gnd; pa.gas = gas; pa.rec = pre.p; pa.g = wg; pa.e = ed;
+                    if (fast) atrous_wave_pre_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
+                    else atrous_wave_pre_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
+                } else {
+                    if (pre.n < (size_t)W * H * 25) { CK(c, cudaDeviceSynchronize()); CK(c, pre.alloc((size_t)W * H * 25)); }
+                    AtrousPreArgs pa;
+                    pa.old_ = d.phys[X]; pa.gnd = gnd; pa.gas = gas; pa.pre = pre.p; pa.plane = (size_t)W * H;
+                    pa.W = W; pa.H = H; pa.y0 = a; pa.y1 = b; pa.step = step; pa.e = ed;
+                    if (fast) atrous_pre_kernel<true><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
+                    else atrous_pre_kernel<false><<<dim3(div_up(W, 32), div_up(b - a, 8)), dim3(32, 8), 0, s>>>(pa);
+                }
                 launches++;
                 // NEW starts as the sentinel on the rows this pass produces; the rows just above `a` (a sharded tile's
                 // upper boundary, produced by the previous rank) are delivered by the caller before ycge_frame_inplace
@@ -594,6 +628,40 @@ int denoise_run(ycge_ctx *c) {
             }
             d.pending = false;
             // (2) the wavefront
+            if (wave) {
+                WaveArgs wa;
+                wa.rec = pre.p; wa.new_ = d.phys[Y]; wa.g = wf_geom(W, H, d.pa, d.pb); wa.dc = ed.dc; wa.rc = ed.rc;
+                wa.err = c->wave_err_dev; wa.trace = nullptr;
+                wa.peer_new = nullptr; wa.peer_y0 = wa.peer_y1 = 0; wa.ready = c->flags.p; wa.frame = (int)c->frame_counter;
+                if (c->peers && c->has_below) {
+                    int lo, aa, slo, sa_; halo_rows(c, lo, aa, slo, sa_);
+                    if (sa_ > slo) { wa.peer_new = (Y == 2) ? c->below_sb : c->below_sa; wa.peer_y0 = slo; wa.peer_y1 = sa_; }
+                }
+                if (getenv("YCGE_CHAIN_TRACE")) { // development aid: first / last step of every band, dumped by ycge_get_stats
+                    if (c->chain_trace.n < (size_t)2 * wa.g.n_warps) CK(c, c->chain_trace.alloc((size_t)2 * wa.g.n_warps));
+                    CK(c, cudaMemsetAsync(c->chain_trace.p, 0, c->chain_trace.n * 8, s));
+                    wa.trace = c->chain_trace.p;
+                }
+                wa.ticket = c->tickets.p + 16 * (2 * ticket_slot + 2); wa.ticket_base = c->ticket_base_of(0, ticket_slot);
+                c->ticket_advance(0, ticket_slot, (unsigned int)wa.g.n_warps); // one ticket per CTA
+                CK(c, cudaEventRecord(c->ev[7], s));
+                if (wa.g.n_warps > 0) {
+                    const dim3 gr(wa.g.n_warps), th(YCGE_WF_ROWS * 32); // one CTA per band, one warp per row
+                    if (fast && wa.peer_new) atrous_wave_kernel<true, true><<<gr, th, 0, s>>>(wa);
+                    else if (fast) atrous_wave_kernel<true, false><<<gr, th, 0, s>>>(wa);
+                    else if (wa.peer_new) atrous_wave_kernel<false, true><<<gr, th, 0, s>>>(wa);
+                    else atrous_wave_kernel<false, false><<<gr, th, 0, s>>>(wa);
+                    launches++;
+                }
+                CK(c, cudaEventRecord(c->ev[8], s));
+                c->chain_timed = true;
+                std::swap(d.phys[X], d.phys[Y]);
+                const int tmp = d.cur_id;
+                d.cur_id = d.dst_id;
+                d.dst_id = (tmp == 1) ? 2 : 1;
+                d.it++;
+                continue;
+            }
             AtrousChainArgs ia;
             ia.old_ = d.phys[X]; ia.new_ = d.phys[Y]; ia.pre = pre.p; ia.plane = (size_t)W * H;
             ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc; ia.trace = nullptr;
@@ -767,10 +835,13 @@ int read_cells_impl(ycge_ctx *c, ycge_cell *out, int stride) {
     CK(c, cudaMemcpy2DAsync(out, (size_t)stride * sizeof(ycge_cell), c->cells.p, (size_t)c->fbW * sizeof(ycge_cell), (size_t)c->fbW * sizeof(ycge_cell),
                             (size_t)c->tile_rows, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    return wave_check(c);
 }
 
 } // namespace
+
+#include "ycge_multi.inl"
+ycge_ctx::~ycge_ctx() {}
 
 // =============================================================================================== exported C ABI
 extern "C" {
@@ -787,9 +858,11 @@ YCGE_API void ycge_default_params(ycge_params *p) {
 
 YCGE_API const char *ycge_last_error(ycge_ctx *ctx) { return ctx ? ctx->err.c_str() : tl_error.c_str(); }
 
-YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
+YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) try {
     if (!cfg || !out) return fail(nullptr, YCGE_ERR_INVALID, "cfg/out is NULL");
     *out = nullptr;
+    if (cfg->n_devices < 0) return fail(nullptr, YCGE_ERR_INVALID, "negative n_devices");
+    if (cfg->n_devices >= 2) return group_create(cfg, out);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -800,6 +873,10 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     c->P = cfg->params;
     if (const char *e = getenv("YCGE_TRACE_VARIANT")) c->trace_variant = atoi(e) ? 1 : 0; // development aid
     if (c->P.atrous_iterations > 8) return fail(nullptr, YCGE_ERR_INVALID, "atrous_iterations > 8 not supported");
+    // the deferred reflection / refraction branches of one pixel (RaytraceRenderer.cs:463-468) live in a stack of YCGE_PATH_STACK
+    // items: a transparent hit pushes two and continues with one, so mirror depth d needs d + 1 slots
+    if (c->P.max_mirror_bounces < 0 || c->P.max_mirror_bounces + 1 > YCGE_PATH_STACK) return fail(nullptr, YCGE_ERR_LIMIT, "max_mirror_bounces must be in [0, 15] (depth of the device's per-pixel branch stack)");
+    if (c->P.max_refractions < 0 || c->P.diffuse_bounces < 0) return fail(nullptr, YCGE_ERR_INVALID, "negative bounce count");
     CK(nullptr, cudaSetDevice(c->device));
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
@@ -821,6 +898,14 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     CK(nullptr, cudaEventCreateWithFlags(&c->host_done0, cudaEventDisableTiming));
     CK(nullptr, c->flags.alloc(16));
     CK(nullptr, cudaMemsetAsync(c->flags.p, 0, 16 * sizeof(int), c->stream));
+    { // the wavefront kernels' "gave up waiting" flag lives in mapped host memory: the host reads it after any wait, for free
+        int *h = nullptr;
+        CK(nullptr, cudaHostAlloc((void **)&h, sizeof(int), cudaHostAllocMapped));
+        *h = 0;
+        c->wave_err_host = h;
+        CK(nullptr, cudaHostGetDevicePointer((void **)&c->wave_err_dev, h, 0));
+    }
+    if (const char *e = getenv("YCGE_WAVE")) c->use_wave = atoi(e) != 0; // 1 = the systolic wavefront kernels (wavefront.cuh)
     CK(nullptr, c->totals.alloc(1));
     CK(nullptr, cudaMemsetAsync(c->totals.p, 0, sizeof(TraceTotals), c->stream));
     { // edge-stopping divisors; verify the fast division over every non-negative binary32 numerator (a few ms, once)
@@ -845,10 +930,11 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) {
     memset(&c->ds, 0, sizeof c->ds);
     *out = c.release();
     return 0;
-}
+} YCGE_CATCH
 
 YCGE_API void ycge_destroy(ycge_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->group) { delete ctx; return; } // the group's destructor releases its per-device contexts, streams and events
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaDeviceSynchronize();
@@ -863,10 +949,12 @@ YCGE_API void ycge_destroy(ycge_ctx *ctx) {
     if (ctx->e_join) cudaEventDestroy(ctx->e_join);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->wave_err_host) cudaFreeHost((void *)ctx->wave_err_host);
     delete ctx;
 }
 
-YCGE_API int ycge_resize(ycge_ctx *c, int32_t fb_w, int32_t fb_h, int32_t ss) {
+YCGE_API int ycge_resize(ycge_ctx *c, int32_t fb_w, int32_t fb_h, int32_t ss) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_resize is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaDeviceSynchronize()); // pipelined frames may still run on the slots' streams
@@ -880,16 +968,17 @@ YCGE_API int ycge_resize(ycge_ctx *c, int32_t fb_w, int32_t fb_h, int32_t ss) {
     // TemporalAA.Resize (TemporalAA.cs:33-45): the camera memory is cleared; frame counter and exposure survive (:110-138)
     c->last_cam[0] = c->last_cam[1] = c->last_cam[2] = NAN; c->last_yaw = NAN; c->last_pitch = NAN;
     return 0;
-}
+} YCGE_CATCH
 
-YCGE_API int ycge_set_stream(ycge_ctx *c, void *cuda_stream) {
+YCGE_API int ycge_set_stream(ycge_ctx *c, void *cuda_stream) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_set_stream is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     { int rc = join_pipeline(c); if (rc) return rc; }
     CK(c, cudaStreamSynchronize(c->stream));
     if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)cuda_stream;
     return 0;
-}
+} YCGE_CATCH
 
 // ---- meshes ------------------------------------------------------------------------------------------------
 static int store_mesh(ycge_ctx *c, int id, int n, const float *soa12 /* n x (A,e1,e2,n) */, const TreeView &tv, const ycge_material &mat) {
@@ -918,8 +1007,12 @@ static int store_mesh(ycge_ctx *c, int id, int n, const float *soa12 /* n x (A,e
     return 0;
 }
 
-YCGE_API int ycge_mesh_upload_soa(ycge_ctx *c, int32_t id, const ycge_mesh_soa *mesh) {
+YCGE_API int ycge_mesh_upload_soa(ycge_ctx *c, int32_t id, const ycge_mesh_soa *mesh) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_mesh_upload_soa(f, id, mesh); });
     if (!c || !mesh || !mesh->bvh) return fail(c, YCGE_ERR_INVALID, "ctx/mesh/mesh->bvh is NULL");
+    if (mesh->n_tris < 0) return fail(c, YCGE_ERR_INVALID, "negative triangle count");
+    if (mesh->n_tris > 0 && (!mesh->ax || !mesh->ay || !mesh->az || !mesh->e1x || !mesh->e1y || !mesh->e1z || !mesh->e2x || !mesh->e2y || !mesh->e2z || !mesh->nx || !mesh->ny || !mesh->nz))
+        return fail(c, YCGE_ERR_INVALID, "a triangle array of the mesh is NULL");
     CK(c, cudaSetDevice(c->device));
     int n = mesh->n_tris;
     std::vector<float> soa((size_t)n * 12);
@@ -929,9 +1022,10 @@ YCGE_API int ycge_mesh_upload_soa(ycge_ctx *c, int32_t id, const ycge_mesh_soa *
         d[6] = mesh->e2x[i]; d[7] = mesh->e2y[i]; d[8] = mesh->e2z[i]; d[9] = mesh->nx[i]; d[10] = mesh->ny[i]; d[11] = mesh->nz[i];
     }
     return store_mesh(c, id, n, soa.data(), view_of(*mesh->bvh), mesh->material);
-}
+} YCGE_CATCH
 
-YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *c, int32_t id, int32_t n, const float *abc, const ycge_material *material) {
+YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *c, int32_t id, int32_t n, const float *abc, const ycge_material *material) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_mesh_upload_triangles(f, id, n, abc, material); });
     if (!c || !abc || !material || n < 0) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     std::vector<float> soa((size_t)n * 12);
@@ -951,11 +1045,14 @@ YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *c, int32_t id, int32_t n, cons
     FlatTree tree;
     build_reference_tree(items, 8, true, tree);
     return store_mesh(c, id, n, soa.data(), view_of(tree), *material);
-}
+} YCGE_CATCH
 
 // ---- volumes -----------------------------------------------------------------------------------------------
-YCGE_API int ycge_volume_upload(ycge_ctx *c, int32_t id, const ycge_volume *v) {
+YCGE_API int ycge_volume_upload(ycge_ctx *c, int32_t id, const ycge_volume *v) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_volume_upload(f, id, v); });
     if (!c || !v || !v->mat || !v->meta || !v->palette) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if (v->palette_n_ids < 0 || v->palette_meta_levels < 0) return fail(c, YCGE_ERR_INVALID, "negative voxel palette size");
+    if ((size_t)v->palette_n_ids * (size_t)(v->palette_meta_levels < 1 ? 1 : v->palette_meta_levels) > (size_t)1 << 24) return fail(c, YCGE_ERR_LIMIT, "voxel palette larger than 2^24 entries");
     if (v->nx <= 0 || v->ny <= 0 || v->nz <= 0) return fail(c, YCGE_ERR_UNBOUNDED, "empty VolumeGrid has no bounds");
     CK(c, cudaSetDevice(c->device));
     std::unique_ptr<VolumeStore> vs(new VolumeStore());
@@ -988,10 +1085,11 @@ YCGE_API int ycge_volume_upload(ycge_ctx *c, int32_t id, const ycge_volume *v) {
     c->volumes[id] = std::move(vs);
     c->have_scene = false;
     return 0;
-}
+} YCGE_CATCH
 
 // ---- textures ----------------------------------------------------------------------------------------------
-YCGE_API int ycge_texture_upload(ycge_ctx *c, int32_t id, int32_t w, int32_t h, const uint32_t *rgba) {
+YCGE_API int ycge_texture_upload(ycge_ctx *c, int32_t id, int32_t w, int32_t h, const uint32_t *rgba) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_texture_upload(f, id, w, h, rgba); });
     if (!c || id < 0 || w < 0 || h < 0 || ((size_t)w * h > 0 && !rgba)) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if ((size_t)w * h > (size_t)0x7fffffff) return fail(c, YCGE_ERR_LIMIT, "texture larger than 2^31 texels (the reference indexes with int)");
     CK(c, cudaSetDevice(c->device));
@@ -1006,7 +1104,7 @@ YCGE_API int ycge_texture_upload(ycge_ctx *c, int32_t id, int32_t w, int32_t h, 
     c->textures[id] = std::move(t);
     c->have_scene = false; // the texture table is rebuilt by ycge_scene_upload
     return 0;
-}
+} YCGE_CATCH
 
 // ---- scene -------------------------------------------------------------------------------------------------
 static bool object_bounds(ycge_ctx *c, const ycge_object &o, Aabb &box, float cen[3]) {
@@ -1044,9 +1142,11 @@ static bool object_bounds(ycge_ctx *c, const ycge_object &o, Aabb &box, float ce
     return true;
 }
 
-YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) {
+YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) try {
+    if (c && c->group) { int rc = group_each_front(c, [&](ycge_ctx *f) { return ycge_scene_upload(f, s); }); c->have_scene = rc == 0; return rc; }
     if (!c || !s) return fail(c, YCGE_ERR_INVALID, "ctx/scene is NULL");
     if (s->n_objects < 0 || s->n_lights < 0 || s->n_materials < 0) return fail(c, YCGE_ERR_INVALID, "negative count");
+    if ((s->n_objects > 0 && !s->objects) || (s->n_lights > 0 && !s->lights) || (s->n_materials > 0 && !s->materials)) return fail(c, YCGE_ERR_INVALID, "a count is positive but its array is NULL");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     c->have_scene = false;
@@ -1121,6 +1221,7 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) {
                 if (!vol_slot.count(o.ref_id)) { vol_slot[o.ref_id] = (int)dvols.size(); dvols.push_back(it->second->dv); }
                 d.ref = vol_slot[o.ref_id];
                 for (int mi : it->second->palette) if (mi >= s->n_materials) return fail(c, YCGE_ERR_INVALID, "voxel palette references a material outside the scene table");
+                if (it->second->def >= s->n_materials) return fail(c, YCGE_ERR_INVALID, "voxel palette default references a material outside the scene table");
                 needs_mat = false;
                 break; }
             default: break;
@@ -1176,9 +1277,10 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) {
     ds.ambient_intensity = s->ambient_intensity;
     c->have_scene = true;
     return 0;
-}
+} YCGE_CATCH
 
-YCGE_API int ycge_lights_update(ycge_ctx *c, int32_t n, const ycge_light *l) {
+YCGE_API int ycge_lights_update(ycge_ctx *c, int32_t n, const ycge_light *l) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_lights_update(f, n, l); });
     if (!c || n < 0 || (n > 0 && !l)) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     std::vector<DevLight> lights((size_t)n);
@@ -1192,32 +1294,59 @@ YCGE_API int ycge_lights_update(ycge_ctx *c, int32_t n, const ycge_light *l) {
     CK(c, cudaStreamSynchronize(c->stream));
     c->ds.lights = c->s_lights.p; c->ds.n_lights = n;
     return 0;
-}
+} YCGE_CATCH
 
-YCGE_API int ycge_globals_update(ycge_ctx *c, const float bg_top[3], const float bg_bottom[3], const float ambient_color[3], float ambient_intensity) {
+YCGE_API int ycge_globals_update(ycge_ctx *c, const float bg_top[3], const float bg_bottom[3], const float ambient_color[3], float ambient_intensity) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_globals_update(f, bg_top, bg_bottom, ambient_color, ambient_intensity); });
     if (!c || !bg_top || !bg_bottom || !ambient_color) return fail(c, YCGE_ERR_INVALID, "bad argument");
     for (int k = 0; k < 3; k++) { c->ds.bg_top[k] = bg_top[k]; c->ds.bg_bottom[k] = bg_bottom[k]; c->ds.ambient[k] = ambient_color[k]; }
     c->ds.ambient_intensity = ambient_intensity;
     return 0;
-}
+} YCGE_CATCH
 
 // ---- per frame ---------------------------------------------------------------------------------------------
-YCGE_API int ycge_set_camera(ycge_ctx *c, const float pos[3], float yaw, float pitch) {
+YCGE_API int ycge_set_camera(ycge_ctx *c, const float pos[3], float yaw, float pitch) try {
+    if (c && c->group) { if (!pos) return fail(c, YCGE_ERR_INVALID, "bad argument"); return group_each_front(c, [&](ycge_ctx *f) { return ycge_set_camera(f, pos, yaw, pitch); }); }
     if (!c || !pos) return fail(c, YCGE_ERR_INVALID, "bad argument");
     c->cam[0] = pos[0]; c->cam[1] = pos[1]; c->cam[2] = pos[2]; c->yaw = yaw; c->pitch = pitch;
     return 0;
-}
-YCGE_API int ycge_set_trace_variant(ycge_ctx *c, int32_t variant) {
+} YCGE_CATCH
+YCGE_API int ycge_set_trace_variant(ycge_ctx *c, int32_t variant) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_set_trace_variant(f, variant); });
     if (!c || variant < 0 || variant > 1) return fail(c, YCGE_ERR_INVALID, "trace variant must be 0 (thread per pixel path) or 1 (ray stream)");
     c->trace_variant = variant;
     return 0;
+} YCGE_CATCH
+YCGE_API int ycge_set_inplace_variant(ycge_ctx *c, int32_t variant) try {
+    if (c && c->group) { for (ycge_ctx *b : c->group->back) { int rc = ycge_set_inplace_variant(b, variant); if (rc) return rc; } return 0; }
+    if (!c || variant < 0 || variant > 1) return fail(c, YCGE_ERR_INVALID, "in-place variant must be 0 (one warp per chain) or 1 (systolic bands)");
+    if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_set_inplace_variant inside a frame");
+    c->use_wave = variant == 1;
+    return 0;
+} YCGE_CATCH
+YCGE_API int ycge_set_fov(ycge_ctx *c, float fov_deg) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_set_fov(f, fov_deg); });
+    c->fov = fov_deg; return 0;
 }
-YCGE_API int ycge_set_fov(ycge_ctx *c, float fov_deg) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); c->fov = fov_deg; return 0; }
-YCGE_API int ycge_reset_history(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); c->force_reset = true; return 0; }
+YCGE_API int ycge_reset_history(ycge_ctx *c) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_reset_history(f); });
+    c->force_reset = true; return 0;
+}
 
-YCGE_API int ycge_frame_begin(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); return frame_begin_impl(c); }
-YCGE_API int ycge_frame_finish(ycge_ctx *c) { if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL"); return frame_finish_impl(c); }
-YCGE_API int ycge_frame_halo(ycge_ctx *c, ycge_halo *h) {
+YCGE_API int ycge_frame_begin(ycge_ctx *c) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (c->group) return fail(c, YCGE_ERR_INVALID, "ycge_frame_begin is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
+    return frame_begin_impl(c);
+}
+YCGE_API int ycge_frame_finish(ycge_ctx *c) {
+    if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
+    if (c->group) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
+    return frame_finish_impl(c);
+}
+YCGE_API int ycge_frame_halo(ycge_ctx *c, ycge_halo *h) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_frame_halo is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || !h) return fail(c, YCGE_ERR_INVALID, "bad argument");
     memset(h, 0, sizeof *h);
     if (!c->frame_open || !c->dn.pending) return 0;
@@ -1230,8 +1359,9 @@ YCGE_API int ycge_frame_halo(ycge_ctx *c, ycge_halo *h) {
     if (a > lo) { h->recv_ptr = nw + (size_t)lo * c->W; h->recv_bytes = (size_t)(a - lo) * row; h->recv_row0 = lo; h->recv_rows = a - lo; }
     if (sa > slo) { h->send_ptr = nw + (size_t)slo * c->W; h->send_bytes = (size_t)(sa - slo) * row; h->send_row0 = slo; h->send_rows = sa - slo; }
     return 1;
-}
-YCGE_API int ycge_stash_config(ycge_ctx *c, int32_t n_slots) {
+} YCGE_CATCH
+YCGE_API int ycge_stash_config(ycge_ctx *c, int32_t n_slots) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_stash_config is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || n_slots < 0 || n_slots > 64) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -1244,8 +1374,9 @@ YCGE_API int ycge_stash_config(ycge_ctx *c, int32_t n_slots) {
         c->stash.push_back(std::move(st));
     }
     return 0;
-}
-YCGE_API int ycge_frame_stash(ycge_ctx *c, int32_t slot) {
+} YCGE_CATCH
+YCGE_API int ycge_frame_stash(ycge_ctx *c, int32_t slot) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_frame_stash is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || slot < 0 || slot >= (int)c->stash.size()) return fail(c, YCGE_ERR_INVALID, "bad stash slot");
     if (!c->frame_open || c->dn.it <= c->dn.K) return fail(c, YCGE_ERR_INVALID, "no finished frame to stash");
     ycge_ctx::Stash &st = *c->stash[slot];
@@ -1255,19 +1386,22 @@ YCGE_API int ycge_frame_stash(ycge_ctx *c, int32_t slot) {
     memcpy(c->last_cam, c->snap_cam, sizeof c->last_cam); c->last_yaw = c->snap_yaw; c->last_pitch = c->snap_pitch; // taa.CommitCamera
     c->frame_open = false;
     return 0;
-}
-YCGE_API int ycge_frame_finish_stashed(ycge_ctx *c, int32_t slot, void *cuda_stream) {
+} YCGE_CATCH
+YCGE_API int ycge_frame_finish_stashed(ycge_ctx *c, int32_t slot, void *cuda_stream) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_frame_finish_stashed is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || slot < 0 || slot >= (int)c->stash.size()) return fail(c, YCGE_ERR_INVALID, "bad stash slot");
     ycge_ctx::Stash &st = *c->stash[slot];
     const size_t row0 = (size_t)c->tile_row0 * 2 * c->ss;
     return finish_launch(c, st.logs.p, st.den.p - row0 * c->W, (cudaStream_t)cuda_stream, false); // cells_kernel indexes rows absolutely
-}
-YCGE_API int ycge_stash_logs_ptr(ycge_ctx *c, int32_t slot, void **ptr, size_t *bytes) {
+} YCGE_CATCH
+YCGE_API int ycge_stash_logs_ptr(ycge_ctx *c, int32_t slot, void **ptr, size_t *bytes) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_stash_logs_ptr is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || !ptr || !bytes || slot < 0 || slot >= (int)c->stash.size()) return fail(c, YCGE_ERR_INVALID, "bad argument");
     *ptr = c->stash[slot]->logs.p; *bytes = c->stash[slot]->logs.n * sizeof(float);
     return 0;
-}
-YCGE_API int ycge_peer_export(ycge_ctx *c, ycge_peer *out) {
+} YCGE_CATCH
+YCGE_API int ycge_peer_export(ycge_ctx *c, ycge_peer *out) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_peer_export is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     memset(out, 0, sizeof *out);
@@ -1277,8 +1411,9 @@ YCGE_API int ycge_peer_export(ycge_ctx *c, ycge_peer *out) {
     CK(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->sb_ipc, c->sb.p));
     CK(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->flags_ipc, c->flags.p));
     return 0;
-}
-YCGE_API int ycge_peer_attach(ycge_ctx *c, const ycge_peer *above, const ycge_peer *below, int32_t via_ipc) {
+} YCGE_CATCH
+YCGE_API int ycge_peer_attach(ycge_ctx *c, const ycge_peer *above, const ycge_peer *below, int32_t via_ipc) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_peer_attach is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     if (!c->sharded) return fail(c, YCGE_ERR_INVALID, "peers are for row-tile contexts");
     { // a tile forwards nothing: the rows the rank below needs must be rows this rank computes itself
@@ -1309,27 +1444,31 @@ YCGE_API int ycge_peer_attach(ycge_ctx *c, const ycge_peer *above, const ycge_pe
     }
     c->peers = true;
     return 0;
-}
-YCGE_API int ycge_frame_inplace(ycge_ctx *c) {
+} YCGE_CATCH
+YCGE_API int ycge_frame_inplace(ycge_ctx *c) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_frame_inplace is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     if (!c->frame_open || !c->dn.pending) return fail(c, YCGE_ERR_INVALID, "no in-place pass is pending");
     return denoise_run(c);
-}
+} YCGE_CATCH
 
 // ---- frame-parallel sharding: FRONT on row tiles, BACK of whole frames round-robin over the ranks ------------------
-YCGE_API int ycge_frame_front(ycge_ctx *c) {
+YCGE_API int ycge_frame_front(ycge_ctx *c) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_frame_front is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     if (c->peers) return fail(c, YCGE_ERR_INVALID, "a ctx with attached peers runs whole frames (ycge_frame_begin)");
     return frame_begin_impl(c, true);
-}
-YCGE_API int ycge_back_config(ycge_ctx *c, int32_t n_slots) {
+} YCGE_CATCH
+YCGE_API int ycge_back_config(ycge_ctx *c, int32_t n_slots) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_back_config is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || n_slots < 0 || n_slots > 16) return fail(c, YCGE_ERR_INVALID, "n_slots must be in [0,16]");
     if (c->sharded) return fail(c, YCGE_ERR_INVALID, "the BACK runs on a whole-frame ctx");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaDeviceSynchronize());
     return alloc_back_slots(c, n_slots);
-}
-YCGE_API int ycge_back_ptr(ycge_ctx *c, int32_t slot, int32_t kind, void **ptr, size_t *bytes) {
+} YCGE_CATCH
+YCGE_API int ycge_back_ptr(ycge_ctx *c, int32_t slot, int32_t kind, void **ptr, size_t *bytes) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_back_ptr is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || !ptr || !bytes || slot < 0 || slot >= (int)c->back_slots.size()) return fail(c, YCGE_ERR_INVALID, "bad argument");
     ycge_ctx::BackSlot &b = *c->back_slots[slot];
     switch (kind) {
@@ -1340,8 +1479,9 @@ YCGE_API int ycge_back_ptr(ycge_ctx *c, int32_t slot, int32_t kind, void **ptr, 
         case YCGE_PTR_GAS: *ptr = b.gas.p; *bytes = b.gas.n * sizeof(float4); return 0;
         default: return fail(c, YCGE_ERR_INVALID, "unknown pointer kind");
     }
-}
-YCGE_API int ycge_back_denoise(ycge_ctx *c, int32_t slot, void *cuda_stream) {
+} YCGE_CATCH
+YCGE_API int ycge_back_denoise(ycge_ctx *c, int32_t slot, void *cuda_stream) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_back_denoise is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || slot < 0 || slot >= (int)c->back_slots.size()) return fail(c, YCGE_ERR_INVALID, "bad back slot");
     if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "a frame is open on this ctx");
     CK(c, cudaSetDevice(c->device));
@@ -1358,16 +1498,23 @@ YCGE_API int ycge_back_denoise(ycge_ctx *c, int32_t slot, void *cuda_stream) {
     c->io = nullptr;
     b.denoised = c->denoised;
     return rc;
-}
-YCGE_API int ycge_back_finish(ycge_ctx *c, int32_t slot, void *cuda_stream) {
+} YCGE_CATCH
+YCGE_API int ycge_back_finish(ycge_ctx *c, int32_t slot, void *cuda_stream) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_back_finish is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || slot < 0 || slot >= (int)c->back_slots.size()) return fail(c, YCGE_ERR_INVALID, "bad back slot");
     ycge_ctx::BackSlot &b = *c->back_slots[slot];
     if (!b.denoised) return fail(c, YCGE_ERR_INVALID, "ycge_back_finish before ycge_back_denoise");
     CK(c, cudaSetDevice(c->device));
     return finish_launch(c, b.logs.p, b.denoised, (cudaStream_t)cuda_stream, false, b.cells.p);
-}
+} YCGE_CATCH
 
-YCGE_API int ycge_render_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
+YCGE_API int ycge_render_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) try {
+    if (c && c->group) { // the synchronous drop-in call: one frame through the same path, then wait for its cells
+        if (!out) return fail(c, YCGE_ERR_INVALID, "out is NULL");
+        int64_t id = 0;
+        int rc = group_submit(c, out, stride_cells, &id);
+        return rc ? rc : group_frame_wait(c, id);
+    }
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
     int rc = frame_begin_impl(c);
@@ -1375,15 +1522,17 @@ YCGE_API int ycge_render_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells
     rc = frame_finish_impl(c);
     if (rc) return rc;
     return read_cells_impl(c, out, stride_cells);
-}
-YCGE_API int ycge_render_frame_stats(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
+} YCGE_CATCH
+YCGE_API int ycge_render_frame_stats(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_render_frame_stats is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     c->want_stats = true;
     int rc = ycge_render_frame(c, out, stride_cells);
     c->want_stats = false;
     return rc;
-}
-YCGE_API int ycge_render_frames_async(ycge_ctx *c, int32_t n) {
+} YCGE_CATCH
+YCGE_API int ycge_render_frames_async(ycge_ctx *c, int32_t n) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_render_frames_async is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || n < 0) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
     c->pipelined = c->n_slots >= 2;
@@ -1398,8 +1547,9 @@ YCGE_API int ycge_render_frames_async(ycge_ctx *c, int32_t n) {
     // everything enqueued later on the ctx's stream (reads, synchronous frames, ycge_wait) comes after the last FINISH
     if (c->last_fin) { CK(c, cudaStreamWaitEvent(c->stream, c->last_fin, 0)); c->last_fin = nullptr; }
     return 0;
-}
-YCGE_API int ycge_pipeline_config(ycge_ctx *c, int32_t n_slots) {
+} YCGE_CATCH
+YCGE_API int ycge_pipeline_config(ycge_ctx *c, int32_t n_slots) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_pipeline_config is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || n_slots < 1 || n_slots > 64) return fail(c, YCGE_ERR_INVALID, "n_slots must be in [1,64]");
     if (c->sharded && n_slots > 1) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx pipelines over ranks (ycge_frame_stash), not over slots");
     if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "a frame is open");
@@ -1420,11 +1570,12 @@ YCGE_API int ycge_pipeline_config(ycge_ctx *c, int32_t n_slots) {
     CK(c, cudaMemcpy(gas_of(c, keep), ta.p, px * sizeof(float4), cudaMemcpyDeviceToDevice));
     c->last_gset = keep;
     return 0;
-}
+} YCGE_CATCH
 /* Streaming path: SetCamera + TryFlipAndBlit without the wait.  The frame is enqueued (pipelined over the slots) and its
  * cells are copied into `out` (caller-owned, should be pinned) as part of the frame's FINISH; ycge_frame_wait(id) blocks
  * until that copy has landed.  At most n_slots frames may be un-waited. */
-YCGE_API int ycge_submit_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells, int64_t *frame_id) {
+YCGE_API int ycge_submit_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells, int64_t *frame_id) try {
+    if (c && c->group) { if (!out) return fail(c, YCGE_ERR_INVALID, "bad argument"); return group_submit(c, out, stride_cells, frame_id); }
     if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if (c->sharded) return fail(c, YCGE_ERR_INVALID, "a row-tile ctx is driven with ycge_frame_begin / _halo / _inplace / _finish");
     if (stride_cells <= 0) stride_cells = c->fbW;
@@ -1446,28 +1597,32 @@ YCGE_API int ycge_submit_frame(ycge_ctx *c, ycge_cell *out, int32_t stride_cells
     c->in_flight.push_back(std::make_pair(c->frame_counter, sv.host_done));
     if (frame_id) *frame_id = c->frame_counter;
     return 0;
-}
-YCGE_API int ycge_frame_wait(ycge_ctx *c, int64_t frame_id) {
+} YCGE_CATCH
+YCGE_API int ycge_frame_wait(ycge_ctx *c, int64_t frame_id) try {
+    if (c && c->group) return group_frame_wait(c, frame_id);
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     for (size_t i = 0; i < c->in_flight.size(); i++) {
         if (c->in_flight[i].first != frame_id) continue;
         CK(c, cudaEventSynchronize(c->in_flight[i].second));
         c->in_flight.erase(c->in_flight.begin(), c->in_flight.begin() + i + 1); // frames finish in order
-        return 0;
+        return wave_check(c);
     }
     return fail(c, YCGE_ERR_INVALID, "frame id is not in flight");
-}
-YCGE_API int ycge_wait(ycge_ctx *c) {
+} YCGE_CATCH
+YCGE_API int ycge_wait(ycge_ctx *c) try {
+    if (c && c->group) return group_wait(c);
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     { int rc = join_pipeline(c); if (rc) return rc; }
     CK(c, cudaStreamSynchronize(c->stream));
-    return 0;
-}
-YCGE_API int ycge_read_cells(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) {
+    return wave_check(c);
+} YCGE_CATCH
+YCGE_API int ycge_read_cells(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_read_cells is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     return read_cells_impl(c, out, stride_cells);
-}
-YCGE_API int ycge_ansi_emit(ycge_ctx *c, uint8_t *out, size_t cap, size_t *n_bytes) {
+} YCGE_CATCH
+YCGE_API int ycge_ansi_emit(ycge_ctx *c, uint8_t *out, size_t cap, size_t *n_bytes) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_ansi_emit is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || !out || !n_bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if (c->frame_counter == 0) return fail(c, YCGE_ERR_INVALID, "no frame rendered yet");
     CK(c, cudaSetDevice(c->device));
@@ -1491,8 +1646,9 @@ YCGE_API int ycge_ansi_emit(ycge_ctx *c, uint8_t *out, size_t cap, size_t *n_byt
     CK(c, cudaMemcpyAsync(out, c->ansi.p, n, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
     return 0;
-}
-YCGE_API int ycge_device_ptr(ycge_ctx *c, int32_t kind, void **ptr, size_t *bytes) {
+} YCGE_CATCH
+YCGE_API int ycge_device_ptr(ycge_ctx *c, int32_t kind, void **ptr, size_t *bytes) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_device_ptr is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || !ptr || !bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if (kind == YCGE_PTR_CELLS) { *ptr = c->cells.p; *bytes = c->cells.n * sizeof(ycge_cell); return 0; }
     if (kind == YCGE_PTR_LOG_SAMPLES) { *ptr = c->logs.p; *bytes = c->logs.n * sizeof(float); return 0; }
@@ -1501,10 +1657,11 @@ YCGE_API int ycge_device_ptr(ycge_ctx *c, int32_t kind, void **ptr, size_t *byte
     if (kind == YCGE_PTR_GAS) { *ptr = gas_of(c, c->last_gset); *bytes = (size_t)c->W * c->H * sizeof(float4); return 0; }
     if (kind == YCGE_PTR_EXPOSURE) { *ptr = c->expo.p; *bytes = sizeof(ExposureState); return 0; }
     return fail(c, YCGE_ERR_INVALID, "unknown pointer kind");
-}
+} YCGE_CATCH
 
 // ---- introspection -----------------------------------------------------------------------------------------
-YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes) {
+YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_debug_read is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || !dst) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     { int rc = join_pipeline(c); if (rc) return rc; }
@@ -1534,9 +1691,31 @@ YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes)
     if (bytes < need) return fail(c, YCGE_ERR_INVALID, "destination too small");
     CK(c, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
     return 0;
-}
+} YCGE_CATCH
 
-YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
+YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) try {
+    if (c && c->group) { // what a multi-GPU context can say: frames, rays traced by all fronts (halo rows included), the exposure state
+        if (!out) return fail(c, YCGE_ERR_INVALID, "bad argument");
+        memset(out, 0, sizeof *out);
+        { int rc = group_wait(c); if (rc) return rc; }
+        YcgeGroup &G = *c->group;
+        out->frames = (uint64_t)G.frame;
+        for (int g = 0; g < G.n; g++) {
+            ycge_stats st;
+            int rc = ycge_get_stats(G.front[g], &st);
+            if (rc) return rc;
+            out->rays += st.rays; out->rays_total += st.rays_total; out->kernel_launches += st.kernel_launches;
+            if (st.ms_trace > out->ms_trace) out->ms_trace = st.ms_trace;
+            if (st.ms_taa > out->ms_taa) out->ms_taa = st.ms_taa;
+        }
+        if (G.frame > 0) {
+            ycge_stats st;
+            int rc = ycge_get_stats(G.back[(int)((G.frame - 1) % G.n)], &st);
+            if (rc) return rc;
+            out->ae_exposure = st.ae_exposure; out->log_sum = st.log_sum; out->log_cnt = st.log_cnt; out->fast_div = st.fast_div;
+        }
+        return 0;
+    }
     if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     { int rc = join_pipeline(c); if (rc) return rc; }
@@ -1572,13 +1751,14 @@ YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) {
     out->kernel_launches = c->launches_last;
     out->fast_div = c->fast_div ? 1 : 0;
     return 0;
-}
+} YCGE_CATCH
 
-YCGE_API int ycge_get_frame_counter(ycge_ctx *c, int64_t *frame) {
+YCGE_API int ycge_get_frame_counter(ycge_ctx *c, int64_t *frame) try {
+    if (c && c->group && frame) { *frame = c->group->frame; return 0; }
     if (!c || !frame) return fail(c, YCGE_ERR_INVALID, "bad argument");
     *frame = c->frame_counter;
     return 0;
-}
+} YCGE_CATCH
 
 YCGE_API int ycge_rng_kat(ycge_ctx *c, int32_t which, int32_t n, const int32_t *x, const int32_t *y, const int64_t *frame, int32_t n_draws,
                           uint32_t *out_bits, uint64_t *out_seed) {

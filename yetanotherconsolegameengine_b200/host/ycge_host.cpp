@@ -1775,13 +1775,19 @@ static std::unique_ptr<FlatScene> Flatten(std::shared_ptr<Scene> sp) {
 void CudaRaytraceRenderer::Check(int rc, const char *what) {
     if (rc != 0) throw std::runtime_error(std::string(what) + " failed with error " + std::to_string(rc) + ": " + ycge_last_error(ctx)); // cf. Win32TerminalRenderer.cs:99-104
 }
-CudaRaytraceRenderer::CudaRaytraceRenderer(Framebuffer &framebuffer, Scene &scene, float fovDeg, int pxW, int pxH, int superSample, int device, int tileRow0, int tileRows) {
+CudaRaytraceRenderer::CudaRaytraceRenderer(Framebuffer &framebuffer, Scene &scene, float fovDeg, int pxW, int pxH, int superSample, int device, int tileRow0, int tileRows,
+                                           const std::vector<int> &devices) {
     (void)pxW; (void)pxH; // the reference ignores them too: hiW/hiH come from the framebuffer (RaytraceRenderer.cs:83-87)
     ycge_config cfg;
     memset(&cfg, 0, sizeof cfg);
     ss = std::max(1, superSample);
     fbW = framebuffer.Width; fbH = framebuffer.Height;
     cfg.fb_w = fbW; cfg.fb_h = fbH; cfg.ss = ss; cfg.device = device; cfg.tile_row0 = tileRow0; cfg.tile_rows = tileRows;
+    if (devices.size() >= 2) {
+        if (devices.size() > 8) throw std::invalid_argument("at most 8 devices");
+        cfg.n_devices = (int)devices.size();
+        for (size_t k = 0; k < devices.size(); k++) cfg.devices[k] = devices[k];
+    }
     ycge_default_params(&cfg.params);
     int rc = ycge_create(&cfg, &ctx);
     if (rc != 0) throw std::runtime_error(std::string("ycge_create failed with error ") + std::to_string(rc) + ": " + ycge_last_error(nullptr));
@@ -2038,6 +2044,16 @@ YH_API void *ycgeh_renderer_create(void *scene, int fb_w, int fb_h, int ss, int 
         h->fb.reset(new Framebuffer(fb_w, fb_h));
         Scene &s = *((SceneHandle *)scene)->scene;
         h->r.reset(new CudaRaytraceRenderer(*h->fb, s, s.DefaultFovDeg, fb_w * ss, fb_h * 2 * ss, ss, device, tile_row0, tile_rows));
+        h->r->SetCamera(s.CameraPos, s.Yaw, s.Pitch);
+        return h;
+    } catch (const std::exception &e) { yh_error = e.what(); return nullptr; }
+}
+YH_API void *ycgeh_renderer_create_multi(void *scene, int fb_w, int fb_h, int ss, int n_devices, const int *devices) { // one renderer, several GPUs
+    try {
+        auto h = new RendererHandle();
+        h->fb.reset(new Framebuffer(fb_w, fb_h));
+        Scene &s = *((SceneHandle *)scene)->scene;
+        h->r.reset(new CudaRaytraceRenderer(*h->fb, s, s.DefaultFovDeg, fb_w * ss, fb_h * 2 * ss, ss, n_devices > 0 ? devices[0] : 0, 0, 0, std::vector<int>(devices, devices + n_devices)));
         h->r->SetCamera(s.CameraPos, s.Yaw, s.Pitch);
         return h;
     } catch (const std::exception &e) { yh_error = e.what(); return nullptr; }

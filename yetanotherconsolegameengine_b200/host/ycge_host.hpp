@@ -351,7 +351,8 @@ class IConsoleRenderer { // RaytraceEntity.cs:12-18
 // The drop-in: same constructor arguments as RaytraceRenderer (RaytraceRenderer.cs:74), frames from libycge.so.
 class CudaRaytraceRenderer : public IConsoleRenderer {
   public:
-    CudaRaytraceRenderer(Framebuffer &framebuffer, Scene &scene, float fovDeg, int pxW, int pxH, int superSample, int device = 0, int tileRow0 = 0, int tileRows = 0);
+    CudaRaytraceRenderer(Framebuffer &framebuffer, Scene &scene, float fovDeg, int pxW, int pxH, int superSample, int device = 0, int tileRow0 = 0, int tileRows = 0,
+                         const std::vector<int> &devices = std::vector<int>()); // two or more devices: the library renders frames in parallel over them (ycge_config.n_devices)
     ~CudaRaytraceRenderer() override;
     void SetCamera(Vec3 pos, float yaw, float pitch) override;
     void SetFov(float fovDeg) override;

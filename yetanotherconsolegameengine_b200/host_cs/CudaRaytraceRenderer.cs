@@ -91,7 +91,11 @@ namespace ConsoleGame.RayTracing
         }
 
         [StructLayout(LayoutKind.Sequential)]
-        public struct YConfig { public int FbW, FbH, Ss, Device, TileRow0, TileRows; public YParams Params; }
+        public unsafe struct YConfig
+        {
+            public int FbW, FbH, Ss, Device, TileRow0, TileRows; public YParams Params;
+            public int NDevices; public fixed int Devices[8]; // >= 2: the library drives these GPUs of the box behind this one context
+        }
 
         [StructLayout(LayoutKind.Sequential, Pack = 1)]
         public struct YCell
@@ -137,11 +141,18 @@ namespace ConsoleGame.RayTracing
         private BVH uploadedBvh; // the tree object the device copy was made from
 
         /// Same arguments as RaytraceRenderer's ctor (RaytraceRenderer.cs:74): hiW = fbW*ss, hiH = fbH*2*ss.
-        public CudaRaytraceRenderer(Framebuffer framebuffer, Scene scene, float fovDeg, int pxW, int pxH, int superSample, int device = 0)
+        /// `devices`: two or more CUDA ordinals of one box -> the library renders frames in parallel over them behind this one renderer.
+        public unsafe CudaRaytraceRenderer(Framebuffer framebuffer, Scene scene, float fovDeg, int pxW, int pxH, int superSample, int device = 0, int[] devices = null)
         {
             this.scene = scene ?? throw new ArgumentNullException(nameof(scene));
             ss = Math.Max(1, superSample); fbW = framebuffer.Width; fbH = framebuffer.Height;
             var cfg = new YConfig { FbW = fbW, FbH = fbH, Ss = ss, Device = device };
+            if (devices != null && devices.Length >= 2)
+            {
+                if (devices.Length > 8) throw new ArgumentException("at most 8 devices");
+                cfg.NDevices = devices.Length;
+                for (int k = 0; k < devices.Length; k++) cfg.Devices[k] = devices[k];
+            }
             ycge_default_params(out cfg.Params); // the reference's compile-time constants (RaytraceRenderer.cs:31-43,65)
             Check(ycge_create(ref cfg, out ctx));
             AllocCells();
