@@ -1,0 +1,94 @@
+// ref_harness.cpp — C entry points over oracle/_ref/ref_generated.hpp, i.e. over the reference's own C# text rewritten into C++
+// by oracle/ref_transpile.py (test infrastructure; see that script).  Nothing here computes: it moves planes in and out.
+#include "_ref/ref_generated.hpp"
+
+#define RH_API extern "C" __attribute__((visibility("default")))
+using namespace refcs;
+
+namespace {
+struct Handle {
+    RendererRef r;
+    Fast2D<Chexel> target;
+    std::unique_ptr<Framebuffer> fb;
+    int W = 0, H = 0;
+};
+template <class T> Fast2D<T> plane(int w, int h) { return Fast2D<T>(w, h); }
+}
+
+// ---- the tail of TryFlipAndBlit (RaytraceRenderer.cs:218-264): TAA, a-trous, exposure, cells
+RH_API void *ref_renderer_create(int fb_w, int fb_h, int ss, int proc_count) {
+    auto *h = new Handle();
+    h->r.ss = ss; h->r.fbW = fb_w; h->r.fbH = fb_h; h->r.procCount = proc_count;
+    h->W = fb_w * ss; h->H = fb_h * 2 * ss; // hiW, hiH (RaytraceRenderer.cs:86-87)
+    h->target = Fast2D<Chexel>(fb_w, fb_h);
+    h->fb.reset(new Framebuffer(fb_w, fb_h));
+    return h;
+}
+RH_API void ref_renderer_destroy(void *hh) { delete (Handle *)hh; }
+// one frame: the trace stage's planes in (row-major W x H: hdr rgb, albedo rgb, raw normal xyz, depth, sky 0/1), everything after out
+RH_API int ref_post_frame(void *hh, const float *hdr3, const float *albedo3, const float *normal3, const float *depth, const uint8_t *sky, int reset_history,
+                          float *taa3, float *den3, float *exposure2, uint16_t *glyph, uint8_t *fg16, uint8_t *bg16, uint8_t *fg_ansi, uint8_t *bg_ansi, float *fg3, float *bg3) {
+    Handle &h = *(Handle *)hh;
+    const int W = h.W, H = h.H;
+    try {
+        Fast2D<Vec3> cur(W, H);
+        h.r.gAlbedo = Fast2D<Vec3>(W, H); h.r.gNormal = Fast2D<Vec3>(W, H); h.r.gDepth = Fast2D<float>(W, H); h.r.skyMask = Fast2D<bool>(W, H);
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            const size_t p = (size_t)x + (size_t)y * W;
+            cur[x, y] = Vec3(hdr3[3 * p], hdr3[3 * p + 1], hdr3[3 * p + 2]);
+            h.r.gAlbedo[x, y] = Vec3(albedo3[3 * p], albedo3[3 * p + 1], albedo3[3 * p + 2]);
+            h.r.gNormal[x, y] = Vec3(normal3[3 * p], normal3[3 * p + 1], normal3[3 * p + 2]);
+            h.r.gDepth[x, y] = depth[p];
+            h.r.skyMask[x, y] = sky[p] != 0;
+        }
+        h.r.PostTail(cur, reset_history != 0, h.target, *h.fb);
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            const size_t p = (size_t)x + (size_t)y * W;
+            const Vec3 t = h.r.taaHistory[x, y], d = h.r.lastDenoised[x, y];
+            taa3[3 * p] = t.X; taa3[3 * p + 1] = t.Y; taa3[3 * p + 2] = t.Z;
+            den3[3 * p] = d.X; den3[3 * p + 1] = d.Y; den3[3 * p + 2] = d.Z;
+        }
+        exposure2[0] = h.r.toneMapper.aeExposure; exposure2[1] = h.r.toneMapper.effectiveExposure;
+        for (int cy = 0; cy < h.r.fbH; cy++) for (int cx = 0; cx < h.r.fbW; cx++) {
+            const size_t c = (size_t)cx + (size_t)cy * h.r.fbW;
+            const Chexel ch = h.target[cx, cy];
+            glyph[c] = (uint16_t)ch.Char;
+            fg16[c] = (uint8_t)(int)ch.ForegroundColor.color_16; bg16[c] = (uint8_t)(int)ch.BackgroundColor.color_16;
+            fg_ansi[c] = (uint8_t)AnsiRef::ChexelToAnsi256(ch.ForegroundColor); bg_ansi[c] = (uint8_t)AnsiRef::ChexelToAnsi256(ch.BackgroundColor);
+            fg3[3 * c] = ch.ForegroundColor.color_f32.X; fg3[3 * c + 1] = ch.ForegroundColor.color_f32.Y; fg3[3 * c + 2] = ch.ForegroundColor.color_f32.Z;
+            bg3[3 * c] = ch.BackgroundColor.color_f32.X; bg3[3 * c + 1] = ch.BackgroundColor.color_f32.Y; bg3[3 * c + 2] = ch.BackgroundColor.color_f32.Z;
+        }
+        return 0;
+    } catch (...) { return -1; }
+}
+
+// ---- RaytraceSampler.cs
+RH_API uint64_t ref_per_frame_seed(int x, int y, int64_t frame, int jx, int jy, uint64_t salt) { return RaytraceSampler::PerFrameSeed(x, y, frame, jx, jy, salt); }
+RH_API uint64_t ref_splitmix64(uint64_t z) { return RaytraceSampler::SplitMix64(z); }
+RH_API void ref_rng_draws(uint64_t seed, int n, float *out) { RaytraceSampler::Rng rng(seed); for (int i = 0; i < n; i++) out[i] = rng.NextUnit(); }
+RH_API float ref_blue_noise(int x, int y, int frame_idx, int channel) { return RaytraceSampler::BlueNoiseSample(x, y, frame_idx, channel); }
+RH_API void ref_cosine_sample(float nx, float ny, float nz, uint64_t seed, float *out3) {
+    RaytraceSampler::Rng rng(seed);
+    const Vec3 d = RaytraceSampler::CosineSampleHemisphere(Vec3(nx, ny, nz), rng);
+    out3[0] = d.X; out3[1] = d.Y; out3[2] = d.Z;
+}
+// ---- BSDF helpers of RaytraceRenderer.cs
+RH_API float ref_fresnel_schlick(float cos_theta, float eta_i, float eta_t) { return RendererRef::FresnelSchlick(cos_theta, eta_i, eta_t); }
+RH_API int ref_refract(const float *v3, const float *n3, float eta, float *out3) {
+    Vec3 o;
+    const bool ok = RendererRef::Refract(Vec3(v3[0], v3[1], v3[2]), Vec3(n3[0], n3[1], n3[2]), eta, o);
+    out3[0] = o.X; out3[1] = o.Y; out3[2] = o.Z;
+    return ok ? 1 : 0;
+}
+RH_API void ref_reflect(const float *v3, const float *n3, float *out3) {
+    const Vec3 o = RendererRef::Reflect(Vec3(v3[0], v3[1], v3[2]), Vec3(n3[0], n3[1], n3[2]));
+    out3[0] = o.X; out3[1] = o.Y; out3[2] = o.Z;
+}
+RH_API void ref_oren_nayar(const float *albedo3, const float *n3, const float *wo3, const float *wi3, float sigma, float *out3) {
+    const Vec3 o = RendererRef::OrenNayarBRDF(Vec3(albedo3[0], albedo3[1], albedo3[2]), Vec3(n3[0], n3[1], n3[2]), Vec3(wo3[0], wo3[1], wo3[2]), Vec3(wi3[0], wi3[1], wi3[2]), sigma);
+    out3[0] = o.X; out3[1] = o.Y; out3[2] = o.Z;
+}
+// ---- quantisers
+RH_API int ref_ansi256(float r, float g, float b) { return AnsiRef::ChexelToAnsi256(ChexelColor(Vec3(r, g, b))); }
+RH_API int ref_nearest16(float r, float g, float b) { return (int)ChexelColor(Vec3(r, g, b)).color_16; }
+RH_API int ref_linear_to_srgb8(double c) { return AnsiRef::LinearToSrgb8(c); }

@@ -1,0 +1,222 @@
+"""ref_transpile.py — rewrites the reference's own C# SOURCE TEXT into C++ mechanically (test infrastructure).
+
+    python oracle/ref_transpile.py /root/reference/ConsoleGame oracle/_ref/ref_generated.hpp
+
+The reference is C#/.NET and no .NET toolchain exists here, so "run the reference" is not available.  Its hot-path arithmetic,
+however, is plain imperative code over structs, arrays and floats, and C# and C++ share that statement syntax almost token
+for token.  This script reads the files under /root/reference at BUILD time and applies only SYNTACTIC rewrites (listed in
+`rewrite`): access modifiers dropped, `new T(...)` -> `T(...)`, `MathF.Max` -> `MathF::Max`, `1f` -> `1.0f`, `ref T x` ->
+`T &x`, lambdas, array declarations, operators -> friends, properties -> methods ...  No arithmetic expression is touched:
+every `a * b + c`, every cast, every loop bound and every comparison of the output is the reference author's text.  The
+result is compiled (-std=c++23 -ffp-contract=off) together with oracle/ref_shims.hpp (the sliver of the .NET library the
+text calls) and oracle/ref_harness.cpp (C entry points) into oracle/_ref/libycge_ref.so.  Nothing generated is committed
+(oracle/_ref/ is git-ignored): the reference's sources never enter this repository.
+
+What is transpiled (and then compared with the oracle, bit for bit, by tests/test_reference_transpiled.py):
+  RayTracing/Vec3.cs (whole), RayTracing/RaytraceSampler.cs (whole: blue noise, Rng, PerFrameSeed, SplitMix64,
+  CosineSampleHemisphere), RayTracing/ToneMapper.cs (whole), Renderer/Chexel.cs (whole), the ANSI-256 quantiser of
+  Renderer/ANSITerminalRenderer.cs, and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
+  the BSDF helpers, and -- verbatim -- the tail of TryFlipAndBlit from the TAA call to the cell loop (:218-264), i.e. the
+  reference's own buffer juggling, including the swap at :718 that makes the second a-trous iteration run in place.
+"""
+import os
+import re
+import sys
+
+
+def strip_namespace(src):
+    src = src.lstrip("﻿")
+    src = re.sub(r"^\s*using [\w.= ]+;[ \t]*$", "", src, flags=re.M)
+    m = re.search(r"namespace\s+[\w.]+\s*\{", src)
+    if not m:
+        return src
+    end = src.rindex("}")
+    return src[m.end():end]
+
+
+def block_end(s, i):
+    """index just past the brace block that starts at s[i] == '{' (char / string literals and comments skipped)"""
+    depth = 0
+    j = i
+    while j < len(s):
+        ch = s[j]
+        if s.startswith("//", j):
+            j = s.index("\n", j)
+            continue
+        if ch == "'" or ch == '"':
+            k = j + 1
+            while s[k] != ch:
+                k += 2 if s[k] == "\\" else 1
+            j = k + 1
+            continue
+        if ch == "{":
+            depth += 1
+        elif ch == "}":
+            depth -= 1
+            if depth == 0:
+                return j + 1
+        j += 1
+    raise ValueError("unbalanced braces")
+
+
+def type_body(src, name):
+    m = re.search(r"\b(?:struct|class)\s+" + re.escape(name) + r"\b[^{;]*\{", src)
+    if not m:
+        raise KeyError(name)
+    i = m.end() - 1
+    return src[i + 1:block_end(src, i) - 1]
+
+
+def members(body):
+    """split a type body into its members: (text, name).  A member ends at ';' or at the end of its brace block."""
+    out, i, n = [], 0, len(body)
+    while i < n:
+        while i < n and body[i] in " \t\r\n":
+            i += 1
+        if i >= n:
+            break
+        if body.startswith("//", i):
+            i = body.index("\n", i) if "\n" in body[i:] else n
+            continue
+        if body[i] == "[":  # attribute
+            i = body.index("]", i) + 1
+            continue
+        j = i
+        while j < n and body[j] not in "{;":
+            if body[j] == "=" and body[j + 1] == ">":  # expression-bodied member: ends at ';'
+                j = body.index(";", j)
+                break
+            j += 1
+        if j < n and body[j] == "{":
+            k = block_end(body, j)
+            # `T[] x = new T[] { ... };` : an initialiser, the member ends at the following ';'
+            if re.search(r"=\s*new\b[^;{]*$", body[i:j]) or re.search(r"=\s*$", body[i:j]):
+                k = body.index(";", k) + 1
+            text = body[i:k]
+        else:
+            text = body[i:j + 1]
+            k = j + 1
+        head = text.split("{")[0].split("=>")[0]
+        head = head.split("=")[0] if "(" not in head.split("=")[0] else head
+        m = re.search(r"(operator\s*[^\s(]+|\w+)\s*(?:\(|$|;)", head.strip().rstrip(";").strip() + ";")
+        names = re.findall(r"(operator\s*\S+?|\w+)\s*(?=\()", head)
+        if names:
+            name = names[0]
+        else:
+            toks = re.findall(r"\w+", head)
+            name = toks[-1] if toks else ""
+        out.append((text, name))
+        i = k
+    return out
+
+
+def rewrite(t, struct_name=None, statics=()):
+    """the syntactic C# -> C++ rewrites; nothing here touches an arithmetic expression"""
+    t = re.sub(r"^\s*\[[A-Za-z][^\]\n]*\]\s*$", "", t, flags=re.M)                       # attributes
+    t = re.sub(r"\b(public|private|internal|protected)\s+", "", t)                        # access modifiers
+    t = re.sub(r"\b(readonly|sealed|unsafe)\s+", "", t)
+    t = re.sub(r"\bunchecked\s*\{", "{", t)
+    t = re.sub(r"\bvar\b", "auto", t)
+    t = re.sub(r"\bnull\b", "nullptr", t)
+    t = re.sub(r"\bulong\b", "uint64_t", t)
+    t = re.sub(r"\buint\b", "uint32_t", t)
+    t = re.sub(r"\blong\b", "int64_t", t)
+    t = re.sub(r"\bchar\b", "char16_t", t)
+    t = re.sub(r"'([^\x00-\x7f])'", r"u'\1'", t)                                          # '▀' -> u'▀'
+    t = re.sub(r"(?<![\w.])(?<![eE][-+])(\d+)f\b", r"\1.0f", t)                            # 1f -> 1.0f
+    t = re.sub(r"=\s*default;", "= {};", t)
+    t = re.sub(r"\bthrow new \w+\([^;]*\);", 'throw std::runtime_error("reference exception");', t)
+    # arrays
+    t = re.sub(r"static (\w+)\[,\] (\w+) = new \1\[(\w+), (\w+)\]\s*\{", r"static constexpr \1 \2[\3][\4] = {", t)                  # byte[,] table
+    t = re.sub(r"static (\w+)\[\] (\w+) = new \1\[\]\s*\{", r"static inline const std::vector<\1> \2 = {", t)
+    t = re.sub(r"static (\w+)\[\] (\w+) = new \1\[(\w+)\];", r"static inline std::vector<\1> \2 = std::vector<\1>(\3);", t)
+    t = re.sub(r"\b(\w+)\[\] (\w+) = new \1\[[^\]]*\]\s*\{", r"std::vector<\1> \2 = {", t)                                          # float[] k = new float[5] { ... }
+    t = re.sub(r"\b(\w+)\[\] (\w+) = new \1\[([^\]]*)\];", r"std::vector<\1> \2(\3);", t)                                           # float[] a = new float[n];
+    t = re.sub(r"\bconst (\w+) (\w+)\s*=", r"static constexpr \1 \2 =", t)                                                          # C# const members are static
+    t = re.sub(r"\.Length\b", ".size()", t)
+    # new
+    t = re.sub(r"\bnew ((?:Fast2D<\w+>|\w+(?:\.\w+)?)\s*\()", r"\1", t)
+    # parameters passed by reference
+    t = re.sub(r"\b(?:ref|out) ([\w.<>]+) (\w+)(?=\s*[,)])", r"\1 &\2", t)
+    t = re.sub(r"\bout ([\w.<>]+) (\w+)\)", r"\2)", t)                                                                             # inline `out T x` at a call site (declared by the caller of rewrite)
+    t = re.sub(r"(?<=[(,\s])(?:ref|out) (?=\w+\s*[,)])", "", t)                                                                    # call sites
+    # lambdas
+    t = re.sub(r"(?<![\w)])(\w+)\s*=>\s*\{", r"[&](int \1) {", t)
+    # static members of known types
+    for s in ("MathF", "Math", "RaytraceSampler", "Vec3", "ChexelColor", "ToneMapper") + tuple(statics):
+        t = re.sub(r"\b" + s + r"\.(?=[A-Z])", s + "::", t)
+    t = re.sub(r"\bfloat\.(?=[A-Z])", "Single::", t)
+    t = re.sub(r"\bint\.(?=[A-Z])", "Int32::", t)
+    t = re.sub(r"\bVec3::Zero\b(?!\()", "Vec3::Zero()", t)
+    t = re.sub(r"\bBlueNoise8x8\[(\w+), (\w+)\]", r"BlueNoise8x8[\1][\2]", t)
+    t = re.sub(r"\bthis\.", "this->", t)
+    t = re.sub(r"\breturn this;", "return *this;", t)
+    # members
+    if struct_name:
+        # conversions: from the struct -> conversion operator; to the struct -> the converting constructor already exists
+        t = re.sub(r"static implicit operator (\w+)\(" + struct_name + r" (\w+)\)\s*\{", r"operator \1() const { const " + struct_name + r" &\2 = *this;", t)
+        t = re.sub(r"static implicit operator " + struct_name + r"\([^)]*\)\s*\{[^}]*\}", "", t)
+    t = re.sub(r"static (\w+) (\w+) => ([^;]+);", r"static \1 \2() { return \3; }", t)                                              # static T Zero => expr;
+    t = re.sub(r"\bstatic (\w+) operator\s*([^\s(]+)\s*\(", r"friend \1 operator\2(", t)
+    t = re.sub(r"\babstract\s+", "virtual ", t)
+    t = re.sub(r"\boverride\s+", "", t)
+    return t
+
+
+def emit_struct(src, name, statics=()):
+    body = rewrite(type_body(src, name), name, statics)
+    body = re.sub(r"^(\s*)((?:float|int|bool|double|Vec3|ChexelColor|ConsoleColor|char16_t|uint64_t|uint32_t) \w+);", r"\1\2 = {};", body, flags=re.M)  # C# zero-initialises fields
+    return "struct %s {\n    %s() = default;\n%s\n};\n" % (name, name, body)
+
+
+def main(ref, out_path):
+    rd = lambda p: strip_namespace(open(os.path.join(ref, p), encoding="utf-8-sig").read())
+    out = ["// GENERATED by oracle/ref_transpile.py from the reference's C# sources under " + ref + " -- do not edit, do not commit.",
+           "#pragma once", '#include "../ref_shims.hpp"', "namespace refcs {", ""]
+    out.append(emit_struct(rd("RayTracing/Vec3.cs"), "Vec3"))
+    chex = rd("Renderer/Chexel.cs")
+    out.append(emit_struct(chex, "ChexelColor"))
+    out.append(emit_struct(chex, "Chexel"))
+    out.append("struct Framebuffer { Fast2D<Chexel> cells; Framebuffer(int w, int h) : cells(w, h) {} void SetChexel(int x, int y, Chexel c) { cells[x, y] = c; } };\n")
+    samp = rd("RayTracing/RaytraceSampler.cs")
+    body = rewrite(type_body(samp, "RaytraceSampler"), None)
+    body = re.sub(r"^(\s*)(uint64_t state);", r"\1\2 = 0;", body, flags=re.M)
+    body = body.replace("struct Rng\n", "struct Rng\n").replace("};", "};")
+    body = re.sub(r"(struct Rng\s*\{)", r"\1\n            Rng() = default;", body)
+    body = re.sub(r"(struct Rng\s*\{.*?\n        \})", r"\1;", body, flags=re.S)  # nested struct needs its ';'
+    out.append("struct RaytraceSampler {\n%s\n};\n" % body)
+    tm = rd("RayTracing/ToneMapper.cs")
+    tb = rewrite(type_body(tm, "ToneMapper"), None)
+    tb = re.sub(r"float EffectiveExposure\s*\{\s*get \{ return effectiveExposure; \}\s*\}", "", tb)
+    tb = re.sub(r"(Fast2D<bool> optionalSkyMask) = nullptr", r"\1 = Fast2D<bool>()", tb)
+    tb = re.sub(r"if \(threadpool == nullptr\) \{[^}]*\}", "", tb)   # a FixedThreadFor VALUE is never null
+    tb = re.sub(r"if \(threadpool == nullptr\) return [^;]*;", "", tb)
+    tb = re.sub(r"FixedThreadFor threadpool\b", "FixedThreadFor &threadpool", tb)
+    out.append("struct ToneMapper {\n%s\n};\n" % tb)
+    ansi = rd("Renderer/ANSITerminalRenderer.cs")
+    ab = type_body(ansi, "ANSITerminalRenderer")
+    want = {"s_cubeSrgb", "s_cubeLinear", "s_graySrgb", "s_grayLinear", "ChexelToAnsi256", "ToCubeLevelSrgb", "LinearToSrgb8", "Dist2Srgb"}
+    sel = [t for t, n in members(ab) if n in want]
+    out.append("struct AnsiRef {\n%s\n};\n" % rewrite("\n".join(sel), None))
+    rr = rd("RayTracing/RaytraceRenderer.cs")
+    rb = type_body(rr, "RaytraceRenderer")
+    mem = members(rb)
+    fields = {"taaAlpha", "taaHistory", "taaHistoryValid", "prevNormal", "prevDepth", "prevSky", "spatialA", "spatialB", "gAlbedo", "gNormal", "gDepth", "skyMask",
+              "toneMapper", "threadpool", "procCount", "ss", "fbW", "fbH", "Pi", "InvPi", "DiffuseSigmaDeg", "Eps", "MirrorThreshold"}
+    funcs = {"Luma", "TemporalBlendWithClamp", "ApplyAtrousDenoise", "OrenNayarBRDF", "FresnelSchlick", "Refract", "Reflect"}
+    sel = [t for t, n in mem if n in fields] + [t for t, n in mem if n in funcs]
+    flip = [t for t, n in mem if n == "TryFlipAndBlit"][0]
+    a, b = flip.index("Fast2D<Vec3> blendedHdr = TemporalBlendWithClamp("), flip.index("taa.CommitCamera")
+    tail = flip[a:b]
+    tail = re.sub(r"(?<=[(,\s])([A-Za-z_]\w*):\s+(?=[\w\d.\-])", "", tail)  # named arguments (all in declaration order) -> positional
+    sel.append("void PostTail(Fast2D<Vec3> currentHdr, bool resetHistory, Fast2D<Chexel> target, Framebuffer &fb)\n{\n" + tail + "\n    lastDenoised = denoisedHdr;\n}\n")
+    body = rewrite("\n".join(sel), None)
+    body = re.sub(r"^(\s*)((?:int|bool) \w+);", r"\1\2 = {};", body, flags=re.M)
+    out.append("struct RendererRef {\n    Fast2D<Vec3> lastDenoised;\n%s\n};\n" % body)
+    out.append("} // namespace refcs\n")
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    open(out_path, "w", encoding="utf-8").write("\n".join(out))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/ConsoleGame", sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_generated.hpp"))

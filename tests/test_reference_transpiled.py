@@ -1,0 +1,141 @@
+"""The oracle against THE REFERENCE'S OWN SOURCE TEXT.
+
+oracle/ref_transpile.py rewrites the C# files under /root/reference into C++ syntactically (no arithmetic expression is touched)
+and oracle/Makefile compiles the result into oracle/_ref/libycge_ref.so (git-ignored; nothing generated is committed).  What
+runs here is therefore the reference author's code -- TemporalBlendWithClamp, ApplyAtrousDenoise and the verbatim tail of
+TryFlipAndBlit with its buffer juggling (RaytraceRenderer.cs:218-264, :274-398, :622-722), ToneMapper.cs, Chexel.cs, the
+ANSI-256 quantiser of ANSITerminalRenderer.cs, RaytraceSampler.cs, Vec3.cs -- with one documented substitution: MathF.Exp /
+Log / Pow / Sin / Cos forward to include/ycge_detmath.h, as they do in the oracle and the product.  The hand-written
+oracle (oracle/ycge_oracle.cpp) must agree with it bit for bit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from yetanotherconsolegameengine_b200 import api
+from oracle_binding import Oracle
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libycge_ref.so")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libycge_ref.so is not built (needs /root/reference at build time)")
+    lib = C.CDLL(REF_SO)
+    vp, f32, u64, i64 = C.c_void_p, C.c_float, C.c_uint64, C.c_int64
+    lib.ref_renderer_create.restype = vp
+    lib.ref_renderer_create.argtypes = [C.c_int] * 4
+    lib.ref_renderer_destroy.argtypes = [vp]
+    lib.ref_post_frame.argtypes = [vp] * 6 + [C.c_int] + [vp] * 10
+    lib.ref_per_frame_seed.restype = u64
+    lib.ref_per_frame_seed.argtypes = [C.c_int, C.c_int, i64, C.c_int, C.c_int, u64]
+    lib.ref_splitmix64.restype = u64
+    lib.ref_splitmix64.argtypes = [u64]
+    lib.ref_rng_draws.argtypes = [u64, C.c_int, vp]
+    lib.ref_blue_noise.restype = f32
+    lib.ref_blue_noise.argtypes = [C.c_int] * 4
+    lib.ref_cosine_sample.argtypes = [f32, f32, f32, u64, vp]
+    lib.ref_ansi256.argtypes = [f32, f32, f32]
+    lib.ref_nearest16.argtypes = [f32, f32, f32]
+    lib.ref_linear_to_srgb8.argtypes = [C.c_double]
+    return lib
+
+
+def P(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+CASES = [("cornell", 24, 10, 2, None), ("mirror_spheres", 30, 9, 2, None), ("knot:40x10", 24, 9, 3, api.BENCH_POSE), ("voxel_world:64x64", 20, 8, 2, None),
+         ("boxes", 17, 5, 1, None), ("cylinders_disks_triangles", 16, 6, 4, None)]
+
+
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss,pose", CASES, ids=[c[0] for c in CASES])
+def test_image_passes_equal_the_reference_source(ref, scene, fb_w, fb_h, ss, pose):
+    """Five frames (history reset on frame 1 and, forced, on frame 4): the oracle's trace planes go into the TRANSPILED tail of
+    TryFlipAndBlit; its TAA history, denoised image (three a-trous iterations, the second one in place -- nobody wrote that down,
+    it follows from the reference's own `dst = (tmp == scratchA) ? scratchB : scratchA`), exposure and every cell field must
+    equal the oracle's."""
+    s = api.HostScene(scene)
+    o = Oracle(s, fb_w, fb_h, ss)
+    if pose is not None:
+        o.set_camera(*pose)
+    W, H = fb_w * ss, fb_h * 2 * ss
+    h = ref.ref_renderer_create(fb_w, fb_h, ss, 3)
+    taa, den = np.empty((H, W, 3), np.float32), np.empty((H, W, 3), np.float32)
+    expo = np.empty(2, np.float32)
+    glyph = np.empty((fb_h, fb_w), np.uint16)
+    fg16, bg16, fga, bga = (np.empty((fb_h, fb_w), np.uint8) for _ in range(4))
+    fg, bg = np.empty((fb_h, fb_w, 3), np.float32), np.empty((fb_h, fb_w, 3), np.float32)
+    for frame in range(1, 6):
+        if frame == 4:
+            o.reset_history()
+        cells = o.render_frame(threads=2)
+        hdr = np.ascontiguousarray(o.debug_read(api.DBG_HDR)[..., :3])
+        asky = o.debug_read(api.DBG_ALBEDO_SKY)
+        alb, sky = np.ascontiguousarray(asky[..., :3]), np.ascontiguousarray((asky[..., 3] != 0).astype(np.uint8))
+        nrm = o.raw_normal()
+        dep = np.ascontiguousarray(o.debug_read(api.DBG_NORMAL_DEPTH)[..., 3])
+        rc = ref.ref_post_frame(h, P(hdr), P(alb), P(nrm), P(dep), P(sky), 1 if frame in (1, 4) else 0, P(taa), P(den), P(expo), P(glyph), P(fg16), P(bg16), P(fga), P(bga), P(fg), P(bg))
+        assert rc == 0
+        what = f"{scene} frame {frame}"
+        assert np.array_equal(bits(taa), bits(o.debug_read(api.DBG_TAA)[..., :3])), what + ": TAA history"
+        assert np.array_equal(bits(den), bits(o.debug_read(api.DBG_DENOISED)[..., :3])), what + ": denoised"
+        assert bits(expo[:1])[0] == bits(np.float32(o.stats()["ae_exposure"]))[()], what + ": aeExposure"
+        assert np.array_equal(glyph, cells["glyph"]) and np.array_equal(fg16, cells["fg16"]) and np.array_equal(bg16, cells["bg16"]), what + ": cells"
+        assert np.array_equal(fga, cells["fg_ansi"]) and np.array_equal(bga, cells["bg_ansi"]), what + ": ANSI-256"
+        assert np.array_equal(bits(fg), bits(cells["fg"])) and np.array_equal(bits(bg), bits(cells["bg"])), what + ": SDR colours"
+    ref.ref_renderer_destroy(h)
+    o.close()
+    s.close()
+
+
+def test_sampler_equals_the_reference_source(ref, oracle_lib):
+    rng = np.random.default_rng(5)
+    for x, y, f in zip(rng.integers(0, 4000, 300), rng.integers(0, 2200, 300), rng.integers(1, 1 << 40, 300)):
+        a = ref.ref_per_frame_seed(int(x), int(y), int(f), 0, 0, 0x9E3779B97F4A7C15)
+        assert a == oracle_lib.yo_per_frame_seed(int(x), int(y), int(f), 0, 0, 0x9E3779B97F4A7C15)
+        assert ref.ref_splitmix64(a) == oracle_lib.yo_splitmix64(a)
+        d = np.empty(16, np.float32)
+        ref.ref_rng_draws(a, 16, P(d))
+        b, m = np.empty(16, np.uint32), np.empty(16, np.uint32)
+        oracle_lib.yo_rng_draws(C.c_uint64(a), 16, P(b), P(m))
+        assert np.array_equal(d.view(np.uint32), b)
+    assert ref.ref_per_frame_seed(0, 0, 1, 0, 0, 0x9E3779B97F4A7C15) == 0x17EF7D0094EB2C76
+    assert ref.ref_per_frame_seed(1919, 1079, 64, 0, 0, 0x9E3779B97F4A7C15) == 0x5BEAD3AD13E75BBB
+    oracle_lib.yo_blue_noise.restype = C.c_float
+    for x in range(0, 40, 3):
+        for y in range(0, 17, 2):
+            for fi in (0, 1, 7, 123456):
+                for ch in (0, 1):
+                    assert np.float32(ref.ref_blue_noise(x, y, fi, ch)).view(np.uint32) == np.float32(oracle_lib.yo_blue_noise(x, y, fi, ch)).view(np.uint32)
+    oracle_lib.yo_cosine_sample.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_void_p]
+    for k in range(200):
+        n = rng.normal(size=3)
+        n = (n / np.linalg.norm(n)).astype(np.float32)
+        if k == 0:
+            n = np.array([0.0, 0.0, -1.0], np.float32)  # the wz < -0.999999 branch
+        a, b = np.empty(3, np.float32), np.empty(3, np.float32)
+        seed = int(rng.integers(1, 1 << 62))
+        ref.ref_cosine_sample(float(n[0]), float(n[1]), float(n[2]), seed, P(a))
+        oracle_lib.yo_cosine_sample(float(n[0]), float(n[1]), float(n[2]), seed, P(b))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_quantisers_equal_the_reference_source(ref, oracle_lib):
+    oracle_lib.yo_ansi256.argtypes = [C.c_float] * 3
+    oracle_lib.yo_nearest16.argtypes = [C.c_float] * 3
+    oracle_lib.yo_linear_to_srgb8.argtypes = [C.c_double]
+    rng = np.random.default_rng(11)
+    cols = np.concatenate([rng.random((4000, 3)), rng.random((500, 1)).repeat(3, 1), np.array([[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [1.5, -0.2, 0.3]])]).astype(np.float32)
+    for r, g, b in cols:
+        assert ref.ref_ansi256(float(r), float(g), float(b)) == oracle_lib.yo_ansi256(float(r), float(g), float(b))
+        assert ref.ref_nearest16(float(r), float(g), float(b)) == oracle_lib.yo_nearest16(float(r), float(g), float(b))
+    for c in np.linspace(-0.1, 1.1, 5001):
+        assert ref.ref_linear_to_srgb8(float(c)) == oracle_lib.yo_linear_to_srgb8(float(c))
