@@ -92,3 +92,55 @@ RH_API void ref_oren_nayar(const float *albedo3, const float *n3, const float *w
 RH_API int ref_ansi256(float r, float g, float b) { return AnsiRef::ChexelToAnsi256(ChexelColor(Vec3(r, g, b))); }
 RH_API int ref_nearest16(float r, float g, float b) { return (int)ChexelColor(Vec3(r, g, b)).color_16; }
 RH_API int ref_linear_to_srgb8(double c) { return AnsiRef::LinearToSrgb8(c); }
+
+// ---- the analytic primitives: objects built by the reference's own constructors from the flat scene description
+// (include/ycge.h: ycge_object.p = the public fields after the ctor ran), rays against the reference's own Hit methods.
+// Materials: 13 floats (albedo3, specular, reflectivity, emission3, transparency, ior, transmission3).
+namespace {
+Material mat_of(const float *m) {
+    return Material(Vec3(m[0], m[1], m[2]), (double)m[3], (double)m[4], Vec3(m[5], m[6], m[7]), (double)m[8], (double)m[9], Vec3(m[10], m[11], m[12]));
+}
+Hittable *make_prim(int kind, const float *p, const float *ma, const float *mb, float checker_scale, float spec, float refl) {
+    const Material A = mat_of(ma);
+    std::function<Material(Vec3, Vec3, float)> fn = [A](Vec3, Vec3, float) { return A; }; // `(pos, n, u) => m`, as the scene factories write it
+    if (checker_scale != 0.0f) fn = ScenesRef::Checker(Vec3(ma[0], ma[1], ma[2]), Vec3(mb[0], mb[1], mb[2]), checker_scale);
+    switch (kind) {
+        case 0: return new Sphere(Vec3(p[0], p[1], p[2]), p[3], A);
+        case 1: return new Plane(Vec3(p[0], p[1], p[2]), Vec3(p[3], p[4], p[5]), fn, spec, refl);
+        case 2: return new Disk(Vec3(p[0], p[1], p[2]), Vec3(p[3], p[4], p[5]), p[6], fn, spec, refl);
+        case 3: return new XYRect(p[0], p[1], p[2], p[3], p[4], fn, spec, refl);
+        case 4: return new XZRect(p[0], p[1], p[2], p[3], p[4], fn, spec, refl);
+        case 5: return new YZRect(p[0], p[1], p[2], p[3], p[4], fn, spec, refl);
+        case 6: return new Box(Vec3(p[0], p[1], p[2]), Vec3(p[3], p[4], p[5]), fn, spec, refl);
+        case 7: return new CylinderY(Vec3(p[0], p[1], p[2]), p[3], p[4], p[5], p[6] != 0.0f, A);
+        case 8: return new Triangle(Vec3(p[0], p[1], p[2]), Vec3(p[3], p[4], p[5]), Vec3(p[6], p[7], p[8]), A);
+    }
+    return nullptr;
+}
+}
+// nearest hit over the objects IN ORDER with a shrinking tMax (what a leaf of BVH.Hit does with its items, BVH.cs:160-178)
+RH_API int ref_objects_hit(int n_obj, const int *kind, const float *p12, const float *mat_a13, const float *mat_b13, const float *checker_scale, const float *spec, const float *refl,
+                           int n, const float *rays6, float t_min, float t_max, int *id_out, float *t_out, float *n_out3, float *p_out3, float *mat_out5) {
+    std::vector<Hittable *> objs;
+    for (int k = 0; k < n_obj; k++) {
+        objs.push_back(make_prim(kind[k], p12 + 12 * k, mat_a13 + 13 * k, mat_b13 + 13 * k, checker_scale[k], spec[k], refl[k]));
+        if (!objs.back()) return -1;
+    }
+    for (int i = 0; i < n; i++) {
+        const float *q = rays6 + 6 * i;
+        const Ray r(Vec3(q[0], q[1], q[2]), Vec3(q[3], q[4], q[5]));
+        HitRecord rec, tmp;
+        float closest = t_max;
+        int id = -1;
+        for (int k = 0; k < n_obj; k++)
+            if (objs[k]->Hit(r, t_min, closest, tmp, 0.0f, 0.0f)) { closest = tmp.T; rec = tmp; id = k; }
+        id_out[i] = id;
+        t_out[i] = id >= 0 ? rec.T : 0.0f;
+        n_out3[3 * i] = rec.N.X; n_out3[3 * i + 1] = rec.N.Y; n_out3[3 * i + 2] = rec.N.Z;
+        p_out3[3 * i] = rec.P.X; p_out3[3 * i + 1] = rec.P.Y; p_out3[3 * i + 2] = rec.P.Z;
+        mat_out5[5 * i] = rec.Mat.Albedo.X; mat_out5[5 * i + 1] = rec.Mat.Albedo.Y; mat_out5[5 * i + 2] = rec.Mat.Albedo.Z;
+        mat_out5[5 * i + 3] = (float)rec.Mat.Specular; mat_out5[5 * i + 4] = (float)rec.Mat.Reflectivity;
+    }
+    for (Hittable *h : objs) delete h;
+    return 0;
+}

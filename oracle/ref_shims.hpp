@@ -38,6 +38,7 @@ struct MathF {
     static float Abs(float a) { return std::fabs(a); }
     static float Sqrt(float a) { return std::sqrt(a); }
     static float Floor(float a) { return std::floor(a); }
+    static float CopySign(float a, float b) { return std::copysign(a, b); }
     static float Exp(float a) { return ycge_expf(a); }
     static float Log(float a) { return ycge_logf(a); }
     static float Pow(float a, float b) { return ycge_powf(a, b); }

@@ -135,7 +135,10 @@ def rewrite(t, struct_name=None, statics=()):
     t = re.sub(r"\bconst (\w+) (\w+)\s*=", r"static constexpr \1 \2 =", t)                                                          # C# const members are static
     t = re.sub(r"\.Length\b", ".size()", t)
     # new
-    t = re.sub(r"\bnew ((?:Fast2D<\w+>|\w+(?:\.\w+)?)\s*\()", r"\1", t)
+    t = re.sub(r"\bnew ((?:Fast2D<\w+>|Vec3|Material|Ray|HitRecord|Chexel|ChexelColor|RaytraceSampler\.Rng)\s*\()", r"\1", t)  # value types (and the Fast2D handle) are constructed in place
+    t = re.sub(r"\bHittable\[\] (\w+);", r"std::vector<Hittable *> \1;", t)
+    t = re.sub(r"\b(\w+) = new Hittable\[(\w+)\];", r"\1.assign(\2, nullptr);", t)
+    t = re.sub(r"\bfaces\[(\w+)\]\.", r"faces[\1]->", t)
     # parameters passed by reference
     t = re.sub(r"\b(?:ref|out) ([\w.<>]+) (\w+)(?=\s*[,)])", r"\1 &\2", t)
     t = re.sub(r"\bout ([\w.<>]+) (\w+)\)", r"\2)", t)                                                                             # inline `out T x` at a call site (declared by the caller of rewrite)
@@ -156,8 +159,14 @@ def rewrite(t, struct_name=None, statics=()):
         # conversions: from the struct -> conversion operator; to the struct -> the converting constructor already exists
         t = re.sub(r"static implicit operator (\w+)\(" + struct_name + r" (\w+)\)\s*\{", r"operator \1() const { const " + struct_name + r" &\2 = *this;", t)
         t = re.sub(r"static implicit operator " + struct_name + r"\([^)]*\)\s*\{[^}]*\}", "", t)
+    t = re.sub(r"^(\s*)static (?!constexpr|inline)(\w+) (\w+) = ", r"\1static inline \2 \3 = ", t, flags=re.M)
     t = re.sub(r"static (\w+) (\w+) => ([^;]+);", r"static \1 \2() { return \3; }", t)                                              # static T Zero => expr;
     t = re.sub(r"\bstatic (\w+) operator\s*([^\s(]+)\s*\(", r"friend \1 operator\2(", t)
+    t = re.sub(r"\babstract ([^;{]*\));", r"virtual \1 = 0;", t)
+    t = re.sub(r"Func<(\w+), (\w+), (\w+), (\w+)>", r"std::function<\4(\1, \2, \3)>", t)
+    t = re.sub(r"\(pos, n, u\) =>\s*\{", "[=](Vec3 pos, Vec3 n, float u) {", t)
+    t = re.sub(r"\(pos, n, u\) => ([^;]+);", r"[=](Vec3 pos, Vec3 n, float u) { return \1; };", t)
+    t = re.sub(r"\bTexture (\w+)", r"Texture *\1", t)
     t = re.sub(r"\babstract\s+", "virtual ", t)
     t = re.sub(r"\boverride\s+", "", t)
     return t
@@ -213,6 +222,31 @@ def main(ref, out_path):
     body = rewrite("\n".join(sel), None)
     body = re.sub(r"^(\s*)((?:int|bool) \w+);", r"\1\2 = {};", body, flags=re.M)
     out.append("struct RendererRef {\n    Fast2D<Vec3> lastDenoised;\n%s\n};\n" % body)
+    # ---- the analytic primitives and what their Hit needs
+    out.append("struct Texture;\n")
+    out.append(emit_struct(rd("RayTracing/Ray.cs"), "Ray"))
+    out.append(emit_struct(rd("RayTracing/Material.cs"), "Material"))
+    out.append(emit_struct(rd("RayTracing/HitRecord.cs"), "HitRecord"))
+    hb = rewrite(type_body(rd("RayTracing/Objects/Hittable.cs"), "Hittable"))
+    out.append("struct Hittable {\n    virtual ~Hittable() {}\n%s\n};\n" % hb)
+    for path, names in (("RayTracing/Objects/Surfaces.cs", ("Plane", "Disk", "XYRect", "XZRect", "YZRect")), ("RayTracing/Objects/BoundedObjects.cs", ("Sphere", "Box", "CylinderY")),
+                        ("RayTracing/Objects/Triangle.cs", ("Triangle",))):
+        src = rd(path)
+        for nm in names:
+            body = type_body(src, nm)
+            if nm == "Triangle":  # the scalar path is the specified one: drop the SSE fields and the SSE branch, mechanically
+                body = re.sub(r"^.*Vector128.*$", "", body, flags=re.M)
+                while True:
+                    m = re.search(r"if \(Sse\.IsSupported[^)]*\)", body)
+                    if not m:
+                        break
+                    b0 = body.index("{", m.end())
+                    body = body[:m.start()] + body[block_end(body, b0):]
+                body = re.sub(r"\|\s*MethodImplOptions\.AggressiveOptimization", "", body)
+            out.append("struct %s : Hittable {\n%s\n};\n" % (nm, rewrite(body)))
+    sc = rd("RayTracing/Scenes/Scenes.cs")
+    sel = [t for t, n in members(type_body(sc, "Scenes")) if n in ("Solid", "Emissive", "Checker")]
+    out.append("struct ScenesRef {\n%s\n};\n" % rewrite("\n".join(sel)))
     out.append("} // namespace refcs\n")
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     open(out_path, "w", encoding="utf-8").write("\n".join(out))
