@@ -144,3 +144,41 @@ RH_API int ref_objects_hit(int n_obj, const int *kind, const float *p12, const f
     for (Hittable *h : objs) delete h;
     return 0;
 }
+
+// ---- MeshBVH.cs: the reference's own constructor (SoA, binned-SAH BuildRecursive with its partition and Array.Sort fallback) and Hit
+RH_API void *ref_mesh_build(int n_tris, const float *abc9, const float *mat13) {
+    try {
+        const Material m = mat_of(mat13);
+        std::vector<Triangle *> tris;
+        for (int i = 0; i < n_tris; i++) {
+            const float *t = abc9 + 9 * (size_t)i;
+            tris.push_back(new Triangle(Vec3(t[0], t[1], t[2]), Vec3(t[3], t[4], t[5]), Vec3(t[6], t[7], t[8]), m));
+        }
+        MeshBVH *b = new MeshBVH(tris);
+        for (Triangle *t : tris) delete t;
+        return b;
+    } catch (...) { return nullptr; }
+}
+RH_API void ref_mesh_destroy(void *h) { delete (MeshBVH *)h; }
+RH_API void ref_mesh_info(void *h, int *n_nodes, int *root, int *n_leaf) { MeshBVH &b = *(MeshBVH *)h; *n_nodes = b.nodeCountUsed; *root = b.rootIndex; *n_leaf = (int)b.leafTriIndex.size(); }
+RH_API void ref_mesh_tree(void *h, float *boxes6, int *lrsc4, int *leaf) {
+    MeshBVH &b = *(MeshBVH *)h;
+    for (int i = 0; i < b.nodeCountUsed; i++) {
+        float *q = boxes6 + 6 * (size_t)i;
+        q[0] = b.nodeMinX[i]; q[1] = b.nodeMinY[i]; q[2] = b.nodeMinZ[i]; q[3] = b.nodeMaxX[i]; q[4] = b.nodeMaxY[i]; q[5] = b.nodeMaxZ[i];
+        int *w = lrsc4 + 4 * (size_t)i;
+        w[0] = b.nodeLeft[i]; w[1] = b.nodeRight[i]; w[2] = b.nodeStart[i]; w[3] = b.nodeCount[i];
+    }
+    for (size_t i = 0; i < b.leafTriIndex.size(); i++) leaf[i] = b.leafTriIndex[i];
+}
+RH_API void ref_mesh_hit(void *h, int n, const float *rays6, float t_min, float t_max, uint8_t *hit, float *t_out, float *n_out3) {
+    MeshBVH &b = *(MeshBVH *)h;
+    for (int i = 0; i < n; i++) {
+        const float *q = rays6 + 6 * i;
+        const Ray r(Vec3(q[0], q[1], q[2]), Vec3(q[3], q[4], q[5]));
+        HitRecord rec;
+        hit[i] = b.Hit(r, t_min, t_max, rec, 0.0f, 0.0f) ? 1 : 0;
+        t_out[i] = rec.T;
+        n_out3[3 * i] = rec.N.X; n_out3[3 * i + 1] = rec.N.Y; n_out3[3 * i + 2] = rec.N.Z;
+    }
+}

@@ -84,4 +84,89 @@ struct FixedThreadFor { // Renderer/FixedThreadFor.cs: For(from, to, body) -- ev
 
 enum ConsoleColor : int { Black = 0 };
 
+// System.Collections.Generic.List<T>: a reference type in C# -- the transpiler passes it by reference
+template <class T> struct List {
+    std::vector<T> v;
+    List() {}
+    explicit List(int capacity) { v.reserve((size_t)capacity); }
+    void Add(const T &x) { v.push_back(x); }
+    int Count() const { return (int)v.size(); }
+    std::vector<T> ToArray() const { return v; }
+    T &operator[](int i) { return v[(size_t)i]; }
+    const T &operator[](int i) const { return v[(size_t)i]; }
+};
+template <class T> using Comparison = std::function<int(const T &, const T &)>;
+inline int SingleCompareTo(float a, float b) { // System.Single.CompareTo
+    if (a < b) return -1;
+    if (a > b) return 1;
+    if (a == b) return 0;
+    if (a != a) return (b != b) ? 0 : -1;
+    return 1;
+}
+// System.Array.Sort(keys, index, length, comparer) = dotnet/runtime ArraySortHelper<T>.IntrospectiveSort (.NET 8): insertion sort up to
+// 16 elements, heap sort at depth 0, else median-of-three partition.  Unstable: the PERMUTATION it produces is part of the reference's
+// behaviour (the builders' fallback split), hence restated here as runtime library.
+struct Array {
+    template <class T, class Cmp> static void Sort(std::vector<T> &keys, int index, int length, Cmp cmp) {
+        if (length < 2) return;
+        int lg = 0;
+        for (unsigned v = (unsigned)length; v > 1; v >>= 1) lg++;
+        Intro(keys.data() + index, length, 2 * (lg + 1), cmp);
+    }
+    template <class T, class Cmp> static void SwapIfGreater(T *a, int i, int j, Cmp &cmp) { if (cmp(a[i], a[j]) > 0) std::swap(a[i], a[j]); }
+    template <class T, class Cmp> static void Insertion(T *a, int n, Cmp &cmp) {
+        for (int i = 0; i + 1 < n; i++) {
+            T t = a[i + 1];
+            int j = i;
+            for (; j >= 0 && cmp(t, a[j]) < 0; j--) a[j + 1] = a[j];
+            a[j + 1] = t;
+        }
+    }
+    template <class T, class Cmp> static void DownHeap(T *a, int i, int n, Cmp &cmp) {
+        T d = a[i - 1];
+        while (i <= n / 2) {
+            int ch = 2 * i;
+            if (ch < n && cmp(a[ch - 1], a[ch]) < 0) ch++;
+            if (!(cmp(d, a[ch - 1]) < 0)) break;
+            a[i - 1] = a[ch - 1];
+            i = ch;
+        }
+        a[i - 1] = d;
+    }
+    template <class T, class Cmp> static void Heap(T *a, int n, Cmp &cmp) {
+        for (int i = n / 2; i >= 1; i--) DownHeap(a, i, n, cmp);
+        for (int i = n; i > 1; i--) { std::swap(a[0], a[i - 1]); DownHeap(a, 1, i - 1, cmp); }
+    }
+    template <class T, class Cmp> static int Partition(T *a, int n, Cmp &cmp) {
+        int hi = n - 1, mid = hi >> 1;
+        SwapIfGreater(a, 0, mid, cmp); SwapIfGreater(a, 0, hi, cmp); SwapIfGreater(a, mid, hi, cmp);
+        T pivot = a[mid];
+        std::swap(a[mid], a[hi - 1]);
+        int l = 0, r = hi - 1;
+        while (l < r) {
+            while (cmp(a[++l], pivot) < 0) {}
+            while (cmp(pivot, a[--r]) < 0) {}
+            if (l >= r) break;
+            std::swap(a[l], a[r]);
+        }
+        if (l != hi - 1) std::swap(a[l], a[hi - 1]);
+        return l;
+    }
+    template <class T, class Cmp> static void Intro(T *a, int n, int depth, Cmp &cmp) {
+        while (n > 1) {
+            if (n <= 16) {
+                if (n == 2) { SwapIfGreater(a, 0, 1, cmp); return; }
+                if (n == 3) { SwapIfGreater(a, 0, 1, cmp); SwapIfGreater(a, 0, 2, cmp); SwapIfGreater(a, 1, 2, cmp); return; }
+                Insertion(a, n, cmp);
+                return;
+            }
+            if (depth == 0) { Heap(a, n, cmp); return; }
+            depth--;
+            int p = Partition(a, n, cmp);
+            Intro(a + p + 1, n - (p + 1), depth, cmp);
+            n = p;
+        }
+    }
+};
+
 } // namespace refcs

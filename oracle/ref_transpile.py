@@ -244,6 +244,55 @@ def main(ref, out_path):
                     body = body[:m.start()] + body[block_end(body, b0):]
                 body = re.sub(r"\|\s*MethodImplOptions\.AggressiveOptimization", "", body)
             out.append("struct %s : Hittable {\n%s\n};\n" % (nm, rewrite(body)))
+    # ---- MeshBVH.cs whole: constructor (triangle SoA, Item list), BuildRecursive (binned SAH, partition, Array.Sort fallback), Hit, TriHit, BoxHitFast
+    mb = type_body(rd("RayTracing/Objects/MeshBVH.cs"), "MeshBVH")
+    mb = re.sub(r"^.*Vector128.*$", "", mb, flags=re.M)
+    while True:
+        m = re.search(r"if \(Sse\w*\.IsSupported[^)]*\)", mb)
+        if not m:
+            break
+        b0 = mb.index("{", m.end())
+        e0 = block_end(mb, b0)
+        m2 = re.match(r"\s*else\s*\{", mb[e0:])  # `if (Sse...) {...} else {scalar}` keeps the scalar block
+        if m2:
+            b1 = e0 + m2.end() - 1
+            e1 = block_end(mb, b1)
+            mb = mb[:m.start()] + mb[b1 + 1:e1 - 1] + mb[e1:]
+        else:
+            mb = mb[:m.start()] + mb[e0:]
+    mb = re.sub(r"IEnumerable<Triangle> (\w+)", r"const std::vector<Triangle *> &\1", mb)
+    mb = re.sub(r"\bobjects\.Count\(\)", "(int)objects.size()", mb)
+    mb = re.sub(r"foreach \(Triangle (\w+) in (\w+)\)", r"for (Triangle *\1 : \2)", mb)
+    mb = re.sub(r"\bList<Triangle>", "List<Triangle *>", mb)
+    mb = re.sub(r"\bTriangle (t|tr)\b(?! :)", r"Triangle *\1", mb)
+    mb = re.sub(r"\b(t|tr)\.(?=[A-Z])", r"\1->", mb)
+    mb = re.sub(r"new (List<[\w *]+>)\(", r"\1(", mb)
+    mb = re.sub(r"([(,]\s*)(List<[\w *]+>) (\w+)(?=[,)])", r"\1\2 &\3", mb)           # List<T> parameters: reference types
+    mb = re.sub(r"([(,]\s*)(\w+)\[\] (\w+)(?=[,)])", r"\1std::vector<\2> &\3", mb)       # T[] parameters likewise
+    mb = re.sub(r"\b(nodes|leafIndices|tris|items)\.Count\b(?!\()", r"\1.Count()", mb)   # List<T>.Count is a property
+    mb = re.sub(r"\bin Ray (\w+)", r"const Ray &\1", mb)
+    mb = re.sub(r"^(\s*)(?:private |public )?(float|int|Material)\[\] ([\w, ]+);", r"\1std::vector<\2> \3;", mb, flags=re.M)   # float[] ax, ay, az;
+    mb = re.sub(r"= Array\.Empty<(\w+)>\(\)", r"= std::vector<\1>()", mb)
+    mb = re.sub(r"\bnew (float|int|Material)\[([^\]]+)\](?!\s*\{)", r"std::vector<\1>(\2)", mb)
+    mb = re.sub(r"^(\s*)(float|int)\[\] ", r"\1std::vector<\2> ", mb, flags=re.M)
+    mb = re.sub(r"(\w+)\[\] (\w+) = (\w+)\.ToArray\(\);", r"std::vector<\1> \2 = \3.ToArray();", mb)
+    mb = re.sub(r"\b(\w+) = (\w+)\.ToArray\(\);", r"\1 = \2.ToArray();", mb)
+    mb = re.sub(r"Span<int> (\w+) = stackalloc int\[(\d+)\];", r"int \1[\2];", mb)
+    mb = re.sub(r"\(a, b\) => (a\.\w+)\.CompareTo\((b\.\w+)\)", r"[](const Item &a, const Item &b) { return SingleCompareTo(\1, \2); }", mb)
+    mb = re.sub(r"Array\.Sort\((\w+), (\w+), (\w+), Comparer<Item>\.Create\((\w+)\)\);", r"Array::Sort(\1, \2, \3, \4);", mb)
+    mb = re.sub(r"\bnew (NodeTmp|Item)\(\)", r"\1()", mb)
+    mb = re.sub(r"\.Add\(default\)", ".Add({})", mb)
+    mb = re.sub(r"\bout (\w+\.\w+)", r"\1", mb)                                        # `out it.MinX` at a call site
+    mb = re.sub(r"\bref (\w+\[[^\]]+\])", r"\1", mb)                                   # `ref lminx[b]` at a call site
+    mb = re.sub(r"(struct (?:NodeTmp|Item)\s*\{[^}]*\})", r"\1;", mb)
+    mb = re.sub(r"\|\s*MethodImplOptions\.\w+", "", mb)
+    mb = rewrite(mb)
+    mb = re.sub(r"^(\s*)((?:float|int) [\w, ]+);", lambda m_: m_.group(1) + ", ".join(x.strip() + " = {}" if i else x + " = {}" for i, x in enumerate(m_.group(2).split(","))) + ";", mb, flags=re.M) if False else mb
+    # the nested structs must be declared before the methods that take them by value in default arguments: hoist them
+    nested = re.findall(r"struct (?:NodeTmp|Item)\s*\{[^}]*\};", mb)
+    for nsrc in nested:
+        mb = mb.replace(nsrc, "")
+    out.append("struct MeshBVH : Hittable {\n%s\n%s\n};\n" % ("\n".join(nested), mb))
     sc = rd("RayTracing/Scenes/Scenes.cs")
     sel = [t for t, n in members(type_body(sc, "Scenes")) if n in ("Solid", "Emissive", "Checker")]
     out.append("struct ScenesRef {\n%s\n};\n" % rewrite("\n".join(sel)))

@@ -199,3 +199,55 @@ def test_primitive_hits_equal_the_reference_source(ref, scene):
     assert np.array_equal(nn[hit].view(np.uint32), n_o[hit].view(np.uint32)), f"{scene}: normals differ"
     o.close()
     s.close()
+
+
+@pytest.mark.parametrize("scene", ["teapot", "knot:40x10", "cow", "bunny"])
+def test_mesh_tree_and_hits_equal_the_reference_source(ref, scene):
+    """MeshBVH.cs whole, transpiled: its constructor builds the tree (binned SAH, the in-place partition, the Array.Sort fallback) from
+    the triangles MeshLoader produced; node for node and leaf slot for leaf slot it must be the tree the host mirror built (the one the
+    GPU traverses), and its Hit -- BoxHitFast, TriHit, the near-child-first stack walk -- must return the oracle's t and normal."""
+    vp = C.c_void_p
+    ref.ref_mesh_build.restype = vp
+    ref.ref_mesh_build.argtypes = [C.c_int, vp, vp]
+    ref.ref_mesh_destroy.argtypes = [vp]
+    ref.ref_mesh_info.argtypes = [vp] * 4
+    ref.ref_mesh_tree.argtypes = [vp] * 4
+    ref.ref_mesh_hit.argtypes = [vp, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp]
+    s = api.HostScene(scene)
+    tris = np.ascontiguousarray(s.mesh_triangles(0), np.float32)
+    m = s.mesh(0).contents.material
+    mat = np.array(list(m.albedo) + [m.specular, m.reflectivity] + list(m.emission) + [m.transparency, m.ior] + list(m.transmission), np.float32)
+    h = ref.ref_mesh_build(len(tris), P(tris), P(mat))
+    assert h
+    nn, root, nl = C.c_int(), C.c_int(), C.c_int()
+    ref.ref_mesh_info(h, C.byref(nn), C.byref(root), C.byref(nl))
+    host = s.bvh_arrays(0)
+    assert nn.value == len(host["boxes"]) and root.value == host["root"] and nl.value == len(host["leaf"])
+    boxes, lrsc, leaf = np.empty((nn.value, 6), np.float32), np.empty((nn.value, 4), np.int32), np.empty(nl.value, np.int32)
+    ref.ref_mesh_tree(h, P(boxes), P(lrsc), P(leaf))
+    assert np.array_equal(boxes.view(np.uint32), host["boxes"].view(np.uint32)), "node boxes"
+    assert np.array_equal(lrsc, host["lrsc"]) and np.array_equal(leaf, host["leaf"]), "node links / leaf order"
+    o = Oracle(s, 16, 8, 1)
+    rng = np.random.default_rng(9)
+    n = 4000
+    lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+    org = (rng.uniform(-1.5, 1.5, (n, 3)) + (lo + hi) / 2).astype(np.float32)
+    tgt = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = tgt - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.ascontiguousarray(np.concatenate([org, d.astype(np.float32)], 1), np.float32)
+    t_o, ids_o, n_o = o.scene_hit(rays)
+    hit, t, nrm = np.empty(n, np.uint8), np.empty(n, np.float32), np.empty((n, 3), np.float32)
+    ref.ref_mesh_hit(h, n, P(rays), np.float32(0.001), np.float32(3.4028234663852886e38), P(hit), P(t), P(nrm))
+    f = s.flat.contents
+    mesh_obj = [k for k in range(f.n_objects) if f.objects[k].kind == 9][0]
+    on_mesh = ids_o[:, 0] == mesh_obj
+    assert on_mesh.sum() > 1000
+    assert hit[on_mesh].all()
+    assert np.array_equal(t[on_mesh].view(np.uint32), t_o[on_mesh].view(np.uint32)), "t"
+    assert np.array_equal(nrm[on_mesh].view(np.uint32), n_o[on_mesh].view(np.uint32)), "normal"
+    closer = (hit == 1) & ~on_mesh & (ids_o[:, 0] >= 0)
+    assert (t[closer] >= t_o[closer]).all(), "the reference's mesh walk found a hit the oracle's scene walk missed"
+    ref.ref_mesh_destroy(h)
+    o.close()
+    s.close()
