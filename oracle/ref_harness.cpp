@@ -182,3 +182,76 @@ RH_API void ref_mesh_hit(void *h, int n, const float *rays6, float t_min, float 
         n_out3[3 * i] = rec.N.X; n_out3[3 * i + 1] = rec.N.Y; n_out3[3 * i + 2] = rec.N.Z;
     }
 }
+
+// ---- the whole trace stage: the reference's Scene (transpiled Objects / Lights / BVH), its constructors, and the verbatim head of
+// TryFlipAndBlit (frame counter, jitter rotations, MakeJitteredRay, PerFrameSeed, TraceFull per pixel)
+namespace {
+struct TraceHandle {
+    SceneRef scene;
+    RendererRef r;
+    std::vector<Hittable *> owned;
+};
+}
+RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_obj, const int *kind, const float *p12, const float *mat_a13, const float *mat_b13,
+                              const float *checker_scale, const float *spec, const float *refl, const int *mesh_tris, const float *const *mesh_abc9, const float *mesh_mat13,
+                              int n_lights, const float *lights7, const float *bg_top3, const float *bg_bottom3, const float *ambient4) {
+    try {
+        auto *h = new TraceHandle();
+        int mi = 0;
+        for (int k = 0; k < n_obj; k++) {
+            Hittable *o = nullptr;
+            if (kind[k] == 9) { // Mesh: MeshLoader's triangles through the reference's Mesh / MeshBVH constructors
+                const Material m = mat_of(mesh_mat13 + 13 * mi);
+                std::vector<Triangle *> tris;
+                for (int i = 0; i < mesh_tris[mi]; i++) {
+                    const float *t = mesh_abc9[mi] + 9 * (size_t)i;
+                    tris.push_back(new Triangle(Vec3(t[0], t[1], t[2]), Vec3(t[3], t[4], t[5]), Vec3(t[6], t[7], t[8]), m));
+                }
+                o = new Mesh(tris, Vec3(0.0f, 0.0f, 0.0f), Vec3(0.0f, 0.0f, 0.0f)); // BoundsMin / BoundsMax are informational (Mesh.cs:9-10)
+                for (Triangle *t : tris) delete t;
+                mi++;
+            } else o = make_prim(kind[k], p12 + 12 * k, mat_a13 + 13 * k, mat_b13 + 13 * k, checker_scale[k], spec[k], refl[k]);
+            if (!o) { delete h; return nullptr; }
+            h->owned.push_back(o);
+            h->scene.Objects.Add(o);
+        }
+        for (int i = 0; i < n_lights; i++) {
+            const float *l = lights7 + 7 * i;
+            h->scene.Lights.Add(PointLight(Vec3(l[0], l[1], l[2]), Vec3(l[3], l[4], l[5]), l[6]));
+        }
+        h->scene.BackgroundTop = Vec3(bg_top3[0], bg_top3[1], bg_top3[2]);
+        h->scene.BackgroundBottom = Vec3(bg_bottom3[0], bg_bottom3[1], bg_bottom3[2]);
+        h->scene.Ambient = AmbientLight(Vec3(ambient4[0], ambient4[1], ambient4[2]), ambient4[3]);
+        h->scene.RebuildBVH();
+        RendererRef &r = h->r;
+        r.scene = &h->scene;
+        r.ss = ss; r.fbW = fb_w; r.fbH = fb_h; r.procCount = 3; r.fovDeg = fov_deg;
+        r.hiW = fb_w * ss; r.hiH = fb_h * 2 * ss; // RaytraceRenderer.cs:86-87
+        r.rays = Fast2D<Ray>(r.hiW, r.hiH);
+        r.gAlbedo = Fast2D<Vec3>(r.hiW, r.hiH); r.gNormal = Fast2D<Vec3>(r.hiW, r.hiH); r.gDepth = Fast2D<float>(r.hiW, r.hiH); r.skyMask = Fast2D<bool>(r.hiW, r.hiH);
+        r.frameBuffer = Fast2D<Chexel>(fb_w, fb_h);
+        return h;
+    } catch (...) { return nullptr; }
+}
+RH_API void ref_trace_destroy(void *hh) { TraceHandle *h = (TraceHandle *)hh; for (Hittable *o : h->owned) delete o; delete h; }
+// one frame of the trace stage; planes out (row-major hiW x hiH)
+RH_API int ref_trace_frame(void *hh, const float *cam3, float yaw, float pitch, float *rays6, float *hdr3, float *albedo3, float *normal3, float *depth, uint8_t *sky) {
+    TraceHandle &h = *(TraceHandle *)hh;
+    try {
+        h.r.TraceStage(Vec3(cam3[0], cam3[1], cam3[2]), yaw, pitch);
+        const int W = h.r.hiW, H = h.r.hiH;
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            const size_t p = (size_t)x + (size_t)y * W;
+            const Ray ry = h.r.rays[x, y];
+            rays6[6 * p] = ry.Origin.X; rays6[6 * p + 1] = ry.Origin.Y; rays6[6 * p + 2] = ry.Origin.Z; rays6[6 * p + 3] = ry.Dir.X; rays6[6 * p + 4] = ry.Dir.Y; rays6[6 * p + 5] = ry.Dir.Z;
+            const Vec3 c = h.r.currentHdr[x, y], a = h.r.gAlbedo[x, y], n = h.r.gNormal[x, y];
+            hdr3[3 * p] = c.X; hdr3[3 * p + 1] = c.Y; hdr3[3 * p + 2] = c.Z;
+            albedo3[3 * p] = a.X; albedo3[3 * p + 1] = a.Y; albedo3[3 * p + 2] = a.Z;
+            normal3[3 * p] = n.X; normal3[3 * p + 1] = n.Y; normal3[3 * p + 2] = n.Z;
+            depth[p] = h.r.gDepth[x, y];
+            sky[p] = h.r.skyMask[x, y] ? 1 : 0;
+        }
+        return 0;
+    } catch (...) { return -1; }
+}
+refcs::Vec3 refcs::Texture::SampleBilinear(float, float) { throw std::runtime_error("textured scenes are not run through the transpiled reference"); }

@@ -82,6 +82,9 @@ struct FixedThreadFor { // Renderer/FixedThreadFor.cs: For(from, to, body) -- ev
     void For(int from, int to, const std::function<void(int)> &body) { for (int i = from; i < to; i++) body(i); }
 };
 
+struct PixelThreadPool { // Renderer/PixelThreadPool.cs: For2D(w, h, body(px, py, threadId)) -- every pixel once; serial here (pixels are independent)
+    void For2D(int w, int h, const std::function<void(int, int, int)> &body) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) body(x, y, 0); }
+};
 enum ConsoleColor : int { Black = 0 };
 
 // System.Collections.Generic.List<T>: a reference type in C# -- the transpiler passes it by reference

@@ -125,7 +125,7 @@ def rewrite(t, struct_name=None, statics=()):
     t = re.sub(r"'([^\x00-\x7f])'", r"u'\1'", t)                                          # '▀' -> u'▀'
     t = re.sub(r"(?<![\w.])(?<![eE][-+])(\d+)f\b", r"\1.0f", t)                            # 1f -> 1.0f
     t = re.sub(r"=\s*default;", "= {};", t)
-    t = re.sub(r"\bthrow new \w+\([^;]*\);", 'throw std::runtime_error("reference exception");', t)
+    t = re.sub(r"\bthrow new \w+\(.*\);", 'throw std::runtime_error("reference exception");', t)
     # arrays
     t = re.sub(r"static (\w+)\[,\] (\w+) = new \1\[(\w+), (\w+)\]\s*\{", r"static constexpr \1 \2[\3][\4] = {", t)                  # byte[,] table
     t = re.sub(r"static (\w+)\[\] (\w+) = new \1\[\]\s*\{", r"static inline const std::vector<\1> \2 = {", t)
@@ -135,13 +135,13 @@ def rewrite(t, struct_name=None, statics=()):
     t = re.sub(r"\bconst (\w+) (\w+)\s*=", r"static constexpr \1 \2 =", t)                                                          # C# const members are static
     t = re.sub(r"\.Length\b", ".size()", t)
     # new
-    t = re.sub(r"\bnew ((?:Fast2D<\w+>|Vec3|Material|Ray|HitRecord|Chexel|ChexelColor|RaytraceSampler\.Rng)\s*\()", r"\1", t)  # value types (and the Fast2D handle) are constructed in place
+    t = re.sub(r"\bnew ((?:Fast2D<\w+>|Vec3|Material|Ray|HitRecord|Chexel|ChexelColor|RaytraceSampler\.Rng|PathWorkItem|PrimaryGBuffer)\s*\()", r"\1", t)  # value types (and the Fast2D handle) are constructed in place
     t = re.sub(r"\bHittable\[\] (\w+);", r"std::vector<Hittable *> \1;", t)
     t = re.sub(r"\b(\w+) = new Hittable\[(\w+)\];", r"\1.assign(\2, nullptr);", t)
     t = re.sub(r"\bfaces\[(\w+)\]\.", r"faces[\1]->", t)
+    t = re.sub(r"^(\s*)((?:[\w.<>]+ \w+ = |if \().*)\bout (Vec3|float|int|bool) (\w+)\)", r"\1\3 \4;\n\1\2\4)", t, flags=re.M)   # inline `out T x` at a call site: declared just before the statement
     # parameters passed by reference
     t = re.sub(r"\b(?:ref|out) ([\w.<>]+) (\w+)(?=\s*[,)])", r"\1 &\2", t)
-    t = re.sub(r"\bout ([\w.<>]+) (\w+)\)", r"\2)", t)                                                                             # inline `out T x` at a call site (declared by the caller of rewrite)
     t = re.sub(r"(?<=[(,\s])(?:ref|out) (?=\w+\s*[,)])", "", t)                                                                    # call sites
     # lambdas
     t = re.sub(r"(?<![\w)])(\w+)\s*=>\s*\{", r"[&](int \1) {", t)
@@ -178,11 +178,73 @@ def emit_struct(src, name, statics=()):
     return "struct %s {\n    %s() = default;\n%s\n};\n" % (name, name, body)
 
 
+
+def bvh_class(src, name, elem, var_names):
+    """MeshBVH.cs / BVH.cs whole: constructor (Item list), BuildRecursive (binned SAH, partition, Array.Sort fallback), Hit, BoxHitFast (+ TriHit).
+    `elem` = the element class (Triangle / Hittable: reference types -> pointers), `var_names` = the identifiers that hold one."""
+    mb = type_body(src, name)
+    mb = re.sub(r"^.*Vector128.*$", "", mb, flags=re.M)
+    while True:
+        m = re.search(r"if \(Sse\w*\.IsSupported[^)]*\)", mb)
+        if not m:
+            break
+        b0 = mb.index("{", m.end())
+        e0 = block_end(mb, b0)
+        m2 = re.match(r"\s*else\s*\{", mb[e0:])  # `if (Sse...) {...} else {scalar}` keeps the scalar block
+        if m2:
+            b1 = e0 + m2.end() - 1
+            e1 = block_end(mb, b1)
+            mb = mb[:m.start()] + mb[b1 + 1:e1 - 1] + mb[e1:]
+        else:
+            mb = mb[:m.start()] + mb[e0:]
+    E = elem
+    mb = re.sub(r"^\s*(?:private |public )?delegate [^;]*;", "", mb, flags=re.M)
+    mb = re.sub(r"\bHitFunc\[\] (\w+);", r"std::vector<std::function<bool(Ray, float, float, HitRecord &, float, float)>> \1;", mb)
+    mb = re.sub(r"= Array\.Empty<HitFunc>\(\)", "= {}", mb)
+    mb = re.sub(r"(\w+) = new HitFunc\[(\w+)\];", r"\1.resize(\2);", mb)
+    mb = re.sub(r"(\w+)\[(\w+)\] = (\w+)\[\2\]\.Hit;", r"\1[\2] = [p_ = \3[\2]](Ray r_, float a_, float b_, HitRecord &h_, float u_, float v_) { return p_->Hit(r_, a_, b_, h_, u_, v_); };", mb)  # method group -> delegate
+    mb = re.sub(r"IEnumerable<" + E + r"> (\w+)", r"const std::vector<" + E + r" *> &\1", mb)
+    mb = re.sub(r"\bobjects\.Count\(\)", "(int)objects.size()", mb)
+    mb = re.sub(r"foreach \(" + E + r" (\w+) in (\w+)\)", r"for (" + E + r" *\1 : \2)", mb)
+    mb = re.sub(r"\bList<" + E + r">", "List<" + E + " *>", mb)
+    vn = "|".join(var_names)
+    mb = re.sub(r"\b" + E + r" (" + vn + r")\b(?! :)", E + r" *\1", mb)
+    mb = re.sub(r"\b(" + vn + r")\.(?=[A-Z])", r"\1->", mb)
+    mb = re.sub(r"new (List<[\w *]+>)\(", r"\1(", mb)
+    mb = re.sub(r"([(,]\s*)(List<[\w *]+>) (\w+)(?=[,)])", r"\1\2 &\3", mb)           # List<T> parameters: reference types
+    mb = re.sub(r"([(,]\s*)(\w+)\[\] (\w+)(?=[,)])", r"\1std::vector<\2> &\3", mb)       # T[] parameters likewise
+    mb = re.sub(r"\b(nodes|leafIndices|tris|items|objs)\.Count\b(?!\()", r"\1.Count()", mb)   # List<T>.Count is a property
+    mb = re.sub(r"\bin Ray (\w+)", r"const Ray &\1", mb)
+    mb = re.sub(r"^(\s*)(?:private |public )?(float|int|Material)\[\] ([\w, ]+);", r"\1std::vector<\2> \3;", mb, flags=re.M)   # float[] ax, ay, az;
+    mb = re.sub(r"= Array\.Empty<(\w+)>\(\)", r"= std::vector<\1>()", mb)
+    mb = re.sub(r"\bnew (float|int|Material)\[([^\]]+)\](?!\s*\{)", r"std::vector<\1>(\2)", mb)
+    mb = re.sub(r"^(\s*)(float|int)\[\] ", r"\1std::vector<\2> ", mb, flags=re.M)
+    mb = re.sub(r"(\w+)\[\] (\w+) = (\w+)\.ToArray\(\);", r"std::vector<\1> \2 = \3.ToArray();", mb)
+    mb = re.sub(r"Span<int> (\w+) = stackalloc int\[(\d+)\];", r"int \1[\2];", mb)
+    mb = re.sub(r"\(a, b\) => (a\.\w+)\.CompareTo\((b\.\w+)\)", r"[](const Item &a, const Item &b) { return SingleCompareTo(\1, \2); }", mb)
+    mb = re.sub(r"Array\.Sort\((\w+), (\w+), (\w+), Comparer<Item>\.Create\((\w+)\)\);", r"Array::Sort(\1, \2, \3, \4);", mb)
+    mb = re.sub(r"\bnew (NodeTmp|Item)\(\)", r"\1()", mb)
+    mb = re.sub(r"\.Add\(default\)", ".Add({})", mb)
+    mb = re.sub(r"\bout (\w+\.\w+)", r"\1", mb)                                        # `out it.MinX` at a call site
+    mb = re.sub(r"\bref (\w+\[[^\]]+\])", r"\1", mb)                                   # `ref lminx[b]` at a call site
+    mb = re.sub(r"(struct (?:NodeTmp|Item)\s*\{[^}]*\})", r"\1;", mb)
+    mb = re.sub(r"\|\s*MethodImplOptions\.\w+", "", mb)
+    mb = rewrite(mb)
+    nested = re.findall(r"struct (?:NodeTmp|Item)\s*\{[^}]*\};", mb)  # hoisted: C++ wants them declared before the signatures that name them
+    for nsrc in nested:
+        mb = mb.replace(nsrc, "")
+    return "struct %s : Hittable {\n%s\n%s\n};\n" % (name, "\n".join(nested), mb)
+
+
 def main(ref, out_path):
     rd = lambda p: strip_namespace(open(os.path.join(ref, p), encoding="utf-8-sig").read())
     out = ["// GENERATED by oracle/ref_transpile.py from the reference's C# sources under " + ref + " -- do not edit, do not commit.",
            "#pragma once", '#include "../ref_shims.hpp"', "namespace refcs {", ""]
-    out.append(emit_struct(rd("RayTracing/Vec3.cs"), "Vec3"))
+    v3 = emit_struct(rd("RayTracing/Vec3.cs"), "Vec3")
+    # two things the C# COMPILER supplies: overload resolution picks the float constructor for int arguments (`new Vec3(1, 1, 1)`), and
+    # `a += b` is `a = a + b` for a type that defines operator +
+    v3 = v3.replace("    Vec3() = default;", "    Vec3() = default;\n    Vec3(int x, int y, int z) : Vec3((float)x, (float)y, (float)z) {}\n    Vec3 &operator+=(Vec3 b) { *this = *this + b; return *this; }")
+    out.append(v3)
     chex = rd("Renderer/Chexel.cs")
     out.append(emit_struct(chex, "ChexelColor"))
     out.append(emit_struct(chex, "Chexel"))
@@ -207,23 +269,8 @@ def main(ref, out_path):
     want = {"s_cubeSrgb", "s_cubeLinear", "s_graySrgb", "s_grayLinear", "ChexelToAnsi256", "ToCubeLevelSrgb", "LinearToSrgb8", "Dist2Srgb"}
     sel = [t for t, n in members(ab) if n in want]
     out.append("struct AnsiRef {\n%s\n};\n" % rewrite("\n".join(sel), None))
-    rr = rd("RayTracing/RaytraceRenderer.cs")
-    rb = type_body(rr, "RaytraceRenderer")
-    mem = members(rb)
-    fields = {"taaAlpha", "taaHistory", "taaHistoryValid", "prevNormal", "prevDepth", "prevSky", "spatialA", "spatialB", "gAlbedo", "gNormal", "gDepth", "skyMask",
-              "toneMapper", "threadpool", "procCount", "ss", "fbW", "fbH", "Pi", "InvPi", "DiffuseSigmaDeg", "Eps", "MirrorThreshold"}
-    funcs = {"Luma", "TemporalBlendWithClamp", "ApplyAtrousDenoise", "OrenNayarBRDF", "FresnelSchlick", "Refract", "Reflect"}
-    sel = [t for t, n in mem if n in fields] + [t for t, n in mem if n in funcs]
-    flip = [t for t, n in mem if n == "TryFlipAndBlit"][0]
-    a, b = flip.index("Fast2D<Vec3> blendedHdr = TemporalBlendWithClamp("), flip.index("taa.CommitCamera")
-    tail = flip[a:b]
-    tail = re.sub(r"(?<=[(,\s])([A-Za-z_]\w*):\s+(?=[\w\d.\-])", "", tail)  # named arguments (all in declaration order) -> positional
-    sel.append("void PostTail(Fast2D<Vec3> currentHdr, bool resetHistory, Fast2D<Chexel> target, Framebuffer &fb)\n{\n" + tail + "\n    lastDenoised = denoisedHdr;\n}\n")
-    body = rewrite("\n".join(sel), None)
-    body = re.sub(r"^(\s*)((?:int|bool) \w+);", r"\1\2 = {};", body, flags=re.M)
-    out.append("struct RendererRef {\n    Fast2D<Vec3> lastDenoised;\n%s\n};\n" % body)
     # ---- the analytic primitives and what their Hit needs
-    out.append("struct Texture;\n")
+    out.append("struct Vec3;\nstruct Texture { Vec3 SampleBilinear(float u, float v); }; // textured scenes are not run through the transpiled reference\n")
     out.append(emit_struct(rd("RayTracing/Ray.cs"), "Ray"))
     out.append(emit_struct(rd("RayTracing/Material.cs"), "Material"))
     out.append(emit_struct(rd("RayTracing/HitRecord.cs"), "HitRecord"))
@@ -244,58 +291,68 @@ def main(ref, out_path):
                     body = body[:m.start()] + body[block_end(body, b0):]
                 body = re.sub(r"\|\s*MethodImplOptions\.AggressiveOptimization", "", body)
             out.append("struct %s : Hittable {\n%s\n};\n" % (nm, rewrite(body)))
-    # ---- MeshBVH.cs whole: constructor (triangle SoA, Item list), BuildRecursive (binned SAH, partition, Array.Sort fallback), Hit, TriHit, BoxHitFast
-    mb = type_body(rd("RayTracing/Objects/MeshBVH.cs"), "MeshBVH")
-    mb = re.sub(r"^.*Vector128.*$", "", mb, flags=re.M)
-    while True:
-        m = re.search(r"if \(Sse\w*\.IsSupported[^)]*\)", mb)
-        if not m:
-            break
-        b0 = mb.index("{", m.end())
-        e0 = block_end(mb, b0)
-        m2 = re.match(r"\s*else\s*\{", mb[e0:])  # `if (Sse...) {...} else {scalar}` keeps the scalar block
-        if m2:
-            b1 = e0 + m2.end() - 1
-            e1 = block_end(mb, b1)
-            mb = mb[:m.start()] + mb[b1 + 1:e1 - 1] + mb[e1:]
-        else:
-            mb = mb[:m.start()] + mb[e0:]
-    mb = re.sub(r"IEnumerable<Triangle> (\w+)", r"const std::vector<Triangle *> &\1", mb)
-    mb = re.sub(r"\bobjects\.Count\(\)", "(int)objects.size()", mb)
-    mb = re.sub(r"foreach \(Triangle (\w+) in (\w+)\)", r"for (Triangle *\1 : \2)", mb)
-    mb = re.sub(r"\bList<Triangle>", "List<Triangle *>", mb)
-    mb = re.sub(r"\bTriangle (t|tr)\b(?! :)", r"Triangle *\1", mb)
-    mb = re.sub(r"\b(t|tr)\.(?=[A-Z])", r"\1->", mb)
-    mb = re.sub(r"new (List<[\w *]+>)\(", r"\1(", mb)
-    mb = re.sub(r"([(,]\s*)(List<[\w *]+>) (\w+)(?=[,)])", r"\1\2 &\3", mb)           # List<T> parameters: reference types
-    mb = re.sub(r"([(,]\s*)(\w+)\[\] (\w+)(?=[,)])", r"\1std::vector<\2> &\3", mb)       # T[] parameters likewise
-    mb = re.sub(r"\b(nodes|leafIndices|tris|items)\.Count\b(?!\()", r"\1.Count()", mb)   # List<T>.Count is a property
-    mb = re.sub(r"\bin Ray (\w+)", r"const Ray &\1", mb)
-    mb = re.sub(r"^(\s*)(?:private |public )?(float|int|Material)\[\] ([\w, ]+);", r"\1std::vector<\2> \3;", mb, flags=re.M)   # float[] ax, ay, az;
-    mb = re.sub(r"= Array\.Empty<(\w+)>\(\)", r"= std::vector<\1>()", mb)
-    mb = re.sub(r"\bnew (float|int|Material)\[([^\]]+)\](?!\s*\{)", r"std::vector<\1>(\2)", mb)
-    mb = re.sub(r"^(\s*)(float|int)\[\] ", r"\1std::vector<\2> ", mb, flags=re.M)
-    mb = re.sub(r"(\w+)\[\] (\w+) = (\w+)\.ToArray\(\);", r"std::vector<\1> \2 = \3.ToArray();", mb)
-    mb = re.sub(r"\b(\w+) = (\w+)\.ToArray\(\);", r"\1 = \2.ToArray();", mb)
-    mb = re.sub(r"Span<int> (\w+) = stackalloc int\[(\d+)\];", r"int \1[\2];", mb)
-    mb = re.sub(r"\(a, b\) => (a\.\w+)\.CompareTo\((b\.\w+)\)", r"[](const Item &a, const Item &b) { return SingleCompareTo(\1, \2); }", mb)
-    mb = re.sub(r"Array\.Sort\((\w+), (\w+), (\w+), Comparer<Item>\.Create\((\w+)\)\);", r"Array::Sort(\1, \2, \3, \4);", mb)
-    mb = re.sub(r"\bnew (NodeTmp|Item)\(\)", r"\1()", mb)
-    mb = re.sub(r"\.Add\(default\)", ".Add({})", mb)
-    mb = re.sub(r"\bout (\w+\.\w+)", r"\1", mb)                                        # `out it.MinX` at a call site
-    mb = re.sub(r"\bref (\w+\[[^\]]+\])", r"\1", mb)                                   # `ref lminx[b]` at a call site
-    mb = re.sub(r"(struct (?:NodeTmp|Item)\s*\{[^}]*\})", r"\1;", mb)
-    mb = re.sub(r"\|\s*MethodImplOptions\.\w+", "", mb)
-    mb = rewrite(mb)
-    mb = re.sub(r"^(\s*)((?:float|int) [\w, ]+);", lambda m_: m_.group(1) + ", ".join(x.strip() + " = {}" if i else x + " = {}" for i, x in enumerate(m_.group(2).split(","))) + ";", mb, flags=re.M) if False else mb
-    # the nested structs must be declared before the methods that take them by value in default arguments: hoist them
-    nested = re.findall(r"struct (?:NodeTmp|Item)\s*\{[^}]*\};", mb)
-    for nsrc in nested:
-        mb = mb.replace(nsrc, "")
-    out.append("struct MeshBVH : Hittable {\n%s\n%s\n};\n" % ("\n".join(nested), mb))
+    out.append(bvh_class(rd("RayTracing/Objects/MeshBVH.cs"), "MeshBVH", "Triangle", ("t", "tr")))
+    out.append(bvh_class(open(os.path.join(ref, "RayTracing/Objects/BVH.cs"), encoding="utf-8-sig").read(), "BVH", "Hittable", ("h",)))
+    msrc = type_body(rd("RayTracing/Mesh.cs"), "Mesh")
+    msel = [t for t, n in members(msrc) if n != "FromObj"]
+    mtxt = "\n".join(msel)
+    mtxt = re.sub(r"\bHittable bvh;", "Hittable *bvh = nullptr;", mtxt)
+    mtxt = re.sub(r"List<Triangle> (\w+)", r"const std::vector<Triangle *> &\1", mtxt)
+    mtxt = re.sub(r"\bbvh\.(?=[A-Z])", "bvh->", mtxt)
+    mtxt = rewrite(mtxt).replace("bvh = new MeshBVH(", "bvh = new MeshBVH(")
+    out.append("struct Mesh : Hittable {\n%s\n};\n" % mtxt)
+    out.append(emit_struct(rd("RayTracing/Objects/PointLight.cs"), "PointLight"))
+    out.append(emit_struct(rd("RayTracing/Objects/AmbientLight.cs"), "AmbientLight"))
+    ssrc = type_body(rd("RayTracing/Scenes/Scene.cs"), "Scene")
+    want = {"Objects", "Lights", "BackgroundTop", "BackgroundBottom", "Ambient", "bvh", "RebuildBVH", "Hit", "Occluded"}
+    stxt = "\n".join(t for t, n in members(ssrc) if n in want)
+    stxt = re.sub(r"List<Hittable> Objects = new List<Hittable>\(\);", "List<Hittable *> Objects;", stxt)
+    stxt = re.sub(r"List<PointLight> Lights = new List<PointLight>\(\);", "List<PointLight> Lights;", stxt)
+    stxt = re.sub(r"\bBVH bvh;", "BVH *bvh = nullptr;", stxt)
+    stxt = re.sub(r"new BVH\(Objects\)", "new BVH(Objects.v)", stxt)
+    stxt = re.sub(r"\bbvh\.(?=[A-Z])", "bvh->", stxt)
+    stxt = re.sub(r"new AmbientLight\(", "AmbientLight(", stxt)
+    out.append("struct SceneRef {\n    bool IsVolumeScene = false; // `scene is VolumeScene`\n    virtual ~SceneRef() {}\n%s\n};\n" % rewrite(stxt))
     sc = rd("RayTracing/Scenes/Scenes.cs")
     sel = [t for t, n in members(type_body(sc, "Scenes")) if n in ("Solid", "Emissive", "Checker")]
     out.append("struct ScenesRef {\n%s\n};\n" % rewrite("\n".join(sel)))
+    rr = rd("RayTracing/RaytraceRenderer.cs")
+    rb = type_body(rr, "RaytraceRenderer")
+    mem = members(rb)
+    fields = {"taaAlpha", "taaHistory", "taaHistoryValid", "prevNormal", "prevDepth", "prevSky", "spatialA", "spatialB", "gAlbedo", "gNormal", "gDepth", "skyMask",
+              "toneMapper", "threadpool", "procCount", "ss", "fbW", "fbH", "Pi", "InvPi", "DiffuseSigmaDeg", "Eps", "MirrorThreshold"}
+    fields |= {"hiW", "hiH", "fovDeg", "rays", "currentHdr", "pixelPool", "frameCounter", "frameBuffer", "scene"}
+    fields |= {"DiffuseBounces", "IndirectSamples", "MaxMirrorBounces", "MaxRefractions", "SeedSalt", "MaxLuminance", "PrimaryGBuffer", "PathWorkItem"}
+    funcs = {"Luma", "TemporalBlendWithClamp", "ApplyAtrousDenoise", "OrenNayarBRDF", "FresnelSchlick", "Refract", "Reflect", "Lerp", "SampleAlbedo", "ForwardFromYawPitch",
+             "MakeJitteredRay", "TraceFull", "ComputeTransmittanceToLight", "CosineSampleHemisphere"}
+    sel = [t for t, n in mem if n in fields] + [t for t, n in mem if n in funcs]
+    flip = [t for t, n in mem if n == "TryFlipAndBlit"][0]
+    a, b = flip.index("Fast2D<Vec3> blendedHdr = TemporalBlendWithClamp("), flip.index("taa.CommitCamera")
+    tail = flip[a:b]
+    tail = re.sub(r"(?<=[(,\s])([A-Za-z_]\w*):\s+(?=[\w\d.\-])", "", tail)  # named arguments (all in declaration order) -> positional
+    sel.append("void PostTail(Fast2D<Vec3> currentHdr, bool resetHistory, Fast2D<Chexel> target, Framebuffer &fb)\n{\n" + tail + "\n    lastDenoised = denoisedHdr;\n}\n")
+    # ... and its head, verbatim as well (:159, :175-216): frame counter, per-frame jitter rotations, ray generation, the per-pixel trace loop
+    a2, b2 = flip.index("long frame = Interlocked.Increment(ref frameCounter);"), flip.index("Fast2D<Vec3> blendedHdr = TemporalBlendWithClamp(")
+    head = re.search(r"float aspect = [^;]*;", flip).group(0) + "\n" + flip[a2:b2]
+    head = head.replace("Interlocked.Increment(ref frameCounter)", "(++frameCounter)")       # an atomic increment that returns the new value
+    head = re.sub(r"\bunchecked\(", "(", head)
+    head = re.sub(r"\(px, py, threadId\) =>\s*\{", "[&](int px, int py, int threadId) {", head)
+    head = head.replace("TraceFull(scene,", "TraceFull(*scene,")
+    sel.append("void TraceStage(Vec3 camPosSnapshot, float yawSnapshot, float pitchSnapshot)\n{\n" + head + "\n}\n")
+    body = "\n".join(sel)
+    body = re.sub(r"^\s*(?:private |public )?(?:readonly )?Scene scene;", "SceneRef *scene = nullptr;", body, flags=re.M)
+    body = re.sub(r"\bScene scene\b", "SceneRef &scene", body)
+    body = re.sub(r"\bscene is [\w.]*VolumeScene\b", "scene.IsVolumeScene", body)
+    body = re.sub(r"\bscene\.Lights\.Count\b", "scene.Lights.Count()", body)
+    body = re.sub(r"\bDiffuseTexture\.(?=[A-Z])", "DiffuseTexture->", body)
+    body = re.sub(r"new (PathWorkItem|PrimaryGBuffer) \{([^}]*)\}", lambda m_: m_.group(1) + "{" + re.sub(r"(^|,)\s*(\w+) =", r"\1 .\2 =", m_.group(2)) + "}", body)  # object initialisers -> designated initialisers
+    nested = re.findall(r"struct (?:PathWorkItem|PrimaryGBuffer)\s*\{[^}]*\}", body)  # hoisted, and kept aggregates (designated initialisers)
+    for nsrc in nested:
+        body = body.replace(nsrc, "")
+    nested = [rewrite(x) + ";" for x in nested]
+    body = rewrite(body, None)
+    body = re.sub(r"^(\s*)((?:int|bool) \w+);", r"\1\2 = {};", body, flags=re.M)
+    out.append("struct RendererRef {\n    Fast2D<Vec3> lastDenoised;\n%s\n%s\n};\n" % ("\n".join(nested), body))
     out.append("} // namespace refcs\n")
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     open(out_path, "w", encoding="utf-8").write("\n".join(out))

@@ -251,3 +251,65 @@ def test_mesh_tree_and_hits_equal_the_reference_source(ref, scene):
     ref.ref_mesh_destroy(h)
     o.close()
     s.close()
+
+
+TRACE_CASES = [("cornell", 20, 8, 2, None), ("mirror_spheres", 24, 8, 2, None), ("boxes", 20, 8, 1, None), ("cylinders_disks_triangles", 20, 8, 2, None), ("test", 24, 9, 2, None),
+               ("teapot", 20, 8, 2, api.BENCH_POSE), ("knot:40x10", 18, 7, 2, api.BENCH_POSE), ("cow", 16, 6, 2, api.BENCH_POSE)]
+
+
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss,pose", TRACE_CASES, ids=[c[0] for c in TRACE_CASES])
+def test_trace_stage_equals_the_reference_source(ref, scene, fb_w, fb_h, ss, pose):
+    """The whole trace stage as the reference wrote it: the scene's objects rebuilt by the reference's constructors (primitives, Mesh ->
+    MeshBVH), Scene.RebuildBVH -> BVH.cs, then the verbatim head of TryFlipAndBlit -- frame counter, jitter rotations, MakeJitteredRay,
+    PerFrameSeed, TraceFull with its work stack, ComputeTransmittanceToLight, OrenNayar, the cosine-weighted bounce -- for three frames.
+    Rays, radiance, albedo, raw normal, depth and the sky mask of every pixel must equal the oracle's, bit for bit."""
+    vp = C.c_void_p
+    ref.ref_trace_create.restype = vp
+    ref.ref_trace_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int] + [vp] * 10 + [C.c_int] + [vp] * 4
+    ref.ref_trace_destroy.argtypes = [vp]
+    ref.ref_trace_frame.argtypes = [vp, vp, C.c_float, C.c_float] + [vp] * 6
+    s = api.HostScene(scene)
+    f = s.flat.contents
+    n_obj = f.n_objects
+    assert all(f.objects[k].kind <= 9 for k in range(n_obj))
+    kind = np.array([f.objects[k].kind for k in range(n_obj)], np.int32)
+    p12 = np.array([list(f.objects[k].p) for k in range(n_obj)], np.float32)
+
+    def mat(m):
+        return list(m.albedo) + [m.specular, m.reflectivity] + list(m.emission) + [m.transparency, m.ior] + list(m.transmission)
+    ma = np.array([mat(f.materials[max(0, f.objects[k].mat_a)]) for k in range(n_obj)], np.float32)
+    mb = np.array([mat(f.materials[max(0, f.objects[k].mat_b)]) for k in range(n_obj)], np.float32)
+    cs = np.array([f.objects[k].checker_scale for k in range(n_obj)], np.float32)
+    sp = np.array([f.objects[k].specular for k in range(n_obj)], np.float32)
+    rf = np.array([f.objects[k].reflectivity for k in range(n_obj)], np.float32)
+    meshes = [np.ascontiguousarray(s.mesh_triangles(i), np.float32) for i in range(s.n_meshes)]
+    mesh_n = np.array([len(m) for m in meshes] + [0], np.int32)
+    mesh_ptrs = (C.c_void_p * max(1, len(meshes)))(*[m.ctypes.data for m in meshes])
+    mesh_mat = np.array([mat(s.mesh(i).contents.material) for i in range(s.n_meshes)] + [[0] * 13], np.float32)
+    lights = np.array([list(f.lights[i].pos) + list(f.lights[i].color) + [f.lights[i].intensity] for i in range(f.n_lights)] + [[0] * 7], np.float32)
+    top, bot = np.array(list(f.bg_top), np.float32), np.array(list(f.bg_bottom), np.float32)
+    amb = np.array(list(f.ambient_color) + [f.ambient_intensity], np.float32)
+    cam = pose if pose is not None else s.default_camera()[:3]
+    fov = s.default_camera()[3]
+    h = ref.ref_trace_create(fb_w, fb_h, ss, fov, n_obj, P(kind), P(p12), P(ma), P(mb), P(cs), P(sp), P(rf), P(mesh_n), mesh_ptrs, P(mesh_mat), f.n_lights, P(lights), P(top), P(bot), P(amb))
+    assert h
+    o = Oracle(s, fb_w, fb_h, ss)
+    o.set_camera(*cam)
+    o.debug_read(api.DBG_RAYS) if False else None
+    W, H = fb_w * ss, fb_h * 2 * ss
+    rays, hdr, alb, nrm = np.empty((H, W, 6), np.float32), np.empty((H, W, 3), np.float32), np.empty((H, W, 3), np.float32), np.empty((H, W, 3), np.float32)
+    dep, sky = np.empty((H, W), np.float32), np.empty((H, W), np.uint8)
+    c3 = np.array(cam[0], np.float32)
+    for frame in range(1, 4):
+        o.render_frame(threads=2)
+        assert ref.ref_trace_frame(h, P(c3), np.float32(cam[1]), np.float32(cam[2]), P(rays), P(hdr), P(alb), P(nrm), P(dep), P(sky)) == 0
+        what = f"{scene} frame {frame}"
+        asky = o.debug_read(api.DBG_ALBEDO_SKY)
+        assert np.array_equal(sky != 0, asky[..., 3] != 0), what + ": sky mask"
+        assert np.array_equal(bits(hdr), bits(o.debug_read(api.DBG_HDR)[..., :3])), what + f": radiance differs in {int((bits(hdr) != bits(o.debug_read(api.DBG_HDR)[..., :3])).any(-1).sum())} pixels"
+        assert np.array_equal(bits(alb), bits(asky[..., :3])), what + ": albedo"
+        assert np.array_equal(bits(nrm), bits(o.raw_normal())), what + ": normal"
+        assert np.array_equal(bits(dep), bits(o.debug_read(api.DBG_NORMAL_DEPTH)[..., 3])), what + ": depth"
+    ref.ref_trace_destroy(h)
+    o.close()
+    s.close()
