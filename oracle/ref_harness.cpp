@@ -1,6 +1,7 @@
 // ref_harness.cpp — C entry points over oracle/_ref/ref_generated.hpp, i.e. over the reference's own C# text rewritten into C++
 // by oracle/ref_transpile.py (test infrastructure; see that script).  Nothing here computes: it moves planes in and out.
 #include "_ref/ref_generated.hpp"
+#include "../include/ycge.h"
 
 #define RH_API extern "C" __attribute__((visibility("default")))
 using namespace refcs;
@@ -194,10 +195,12 @@ struct TraceHandle {
 }
 RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_obj, const int *kind, const float *p12, const float *mat_a13, const float *mat_b13,
                               const float *checker_scale, const float *spec, const float *refl, const int *mesh_tris, const float *const *mesh_abc9, const float *mesh_mat13,
-                              int n_lights, const float *lights7, const float *bg_top3, const float *bg_bottom3, const float *ambient4) {
+                              int n_lights, const float *lights7, const float *bg_top3, const float *bg_bottom3, const float *ambient4,
+                              int n_vols, const ycge_volume *vols, int n_mats, const float *scene_mats13, int is_volume_scene) {
     try {
         auto *h = new TraceHandle();
-        int mi = 0;
+        h->scene.IsVolumeScene = is_volume_scene != 0;
+        int mi = 0, vi = 0;
         for (int k = 0; k < n_obj; k++) {
             Hittable *o = nullptr;
             if (kind[k] == 9) { // Mesh: MeshLoader's triangles through the reference's Mesh / MeshBVH constructors
@@ -210,6 +213,27 @@ RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_o
                 o = new Mesh(tris, Vec3(0.0f, 0.0f, 0.0f), Vec3(0.0f, 0.0f, 0.0f)); // BoundsMin / BoundsMax are informational (Mesh.cs:9-10)
                 for (Triangle *t : tris) delete t;
                 mi++;
+            } else if (kind[k] == 10) { // VolumeGrid: the fields its constructor derives (VolumeGrid.cs:55-93), from the flat description
+                if (vi >= n_vols) { delete h; return nullptr; }
+                const ycge_volume &v = vols[vi++];
+                VolumeGrid *g = new VolumeGrid();
+                g->nx = v.nx; g->ny = v.ny; g->nz = v.nz;
+                g->nbx = (v.nx + 7) >> 3; g->nby = (v.ny + 7) >> 3; g->nbz = (v.nz + 7) >> 3;
+                g->brickCount = g->nbx * g->nby * g->nbz; g->capacity = g->brickCount * 512;
+                g->matPtr = const_cast<int *>(v.mat); g->metaPtr = const_cast<int *>(v.meta);
+                g->minCorner = Vec3(v.min_corner[0], v.min_corner[1], v.min_corner[2]);
+                g->voxelSize = Vec3(MathF::Max(1e-6f, v.voxel_size[0]), MathF::Max(1e-6f, v.voxel_size[1]), MathF::Max(1e-6f, v.voxel_size[2]));
+                g->wireframe = v.wireframe != 0; g->wireWidthFrac = v.wire_width_frac; g->wireMaxDistance = v.wire_max_distance;
+                std::vector<int> table(v.palette, v.palette + (size_t)v.palette_n_ids * (v.palette_meta_levels < 1 ? 1 : v.palette_meta_levels));
+                std::vector<Material> mats;
+                for (int m = 0; m < n_mats; m++) mats.push_back(mat_of(scene_mats13 + 13 * m));
+                const int n_ids = v.palette_n_ids, levels = v.palette_meta_levels < 1 ? 1 : v.palette_meta_levels, def = v.palette_default;
+                g->materialLookup = [table, mats, n_ids, levels, def](int id, int meta) { // ycge.h: the palette as data
+                    if (id >= n_ids || id < 0) return mats[(size_t)def];
+                    const int m = meta < 0 ? 0 : (meta >= levels ? levels - 1 : meta);
+                    return mats[(size_t)table[(size_t)id * levels + m]];
+                };
+                o = g;
             } else o = make_prim(kind[k], p12 + 12 * k, mat_a13 + 13 * k, mat_b13 + 13 * k, checker_scale[k], spec[k], refl[k]);
             if (!o) { delete h; return nullptr; }
             h->owned.push_back(o);

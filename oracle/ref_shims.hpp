@@ -27,6 +27,7 @@ struct Single {
     static constexpr float MaxValue = std::numeric_limits<float>::max();
     static bool IsFinite(float v) { return std::isfinite(v); }
     static bool IsNaN(float v) { return v != v; }
+    static bool IsInfinity(float v) { return std::isinf(v); }
 };
 struct Int32 { static constexpr int MaxValue = 2147483647; static constexpr int MinValue = -2147483647 - 1; };
 

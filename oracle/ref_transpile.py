@@ -164,6 +164,8 @@ def rewrite(t, struct_name=None, statics=()):
     t = re.sub(r"\bstatic (\w+) operator\s*([^\s(]+)\s*\(", r"friend \1 operator\2(", t)
     t = re.sub(r"\babstract ([^;{]*\));", r"virtual \1 = 0;", t)
     t = re.sub(r"Func<(\w+), (\w+), (\w+), (\w+)>", r"std::function<\4(\1, \2, \3)>", t)
+    t = re.sub(r"Func<(\w+), (\w+), (\w+)>", r"std::function<\3(\1, \2)>", t)
+    t = re.sub(r"\bfloat\.IsInfinity\(", "Single::IsInfinity(", t)
     t = re.sub(r"\(pos, n, u\) =>\s*\{", "[=](Vec3 pos, Vec3 n, float u) {", t)
     t = re.sub(r"\(pos, n, u\) => ([^;]+);", r"[=](Vec3 pos, Vec3 n, float u) { return \1; };", t)
     t = re.sub(r"\bTexture (\w+)", r"Texture *\1", t)
@@ -293,6 +295,14 @@ def main(ref, out_path):
             out.append("struct %s : Hittable {\n%s\n};\n" % (nm, rewrite(body)))
     out.append(bvh_class(rd("RayTracing/Objects/MeshBVH.cs"), "MeshBVH", "Triangle", ("t", "tr")))
     out.append(bvh_class(open(os.path.join(ref, "RayTracing/Objects/BVH.cs"), encoding="utf-8-sig").read(), "BVH", "Hittable", ("h",)))
+    # ---- VolumeGrid.cs: everything but the constructor (it takes a C# tuple array; the harness fills the same fields from the flat
+    # description, whose mat / meta arrays already are in the reference's bricked-Morton order), the GC handles and disposal
+    vsrc = type_body(rd("RayTracing/Objects/VolumeGrid.cs"), "VolumeGrid")
+    skip = {"VolumeGrid", "mat", "meta", "matHandle", "metaHandle", "BoundsMin", "BoundsMax", "Dispose", "disposed"}
+    vtxt = "\n".join(t for t, n in members(vsrc) if n not in skip and not t.lstrip().startswith("~"))
+    vtxt = re.sub(r"^(\s*)(?:private |public )?(?:readonly )?(int|float|bool) (\w+);", r"\1\2 \3 = {};", vtxt, flags=re.M)
+    vtxt = re.sub(r"\bint\* (\w+);", r"int *\1 = nullptr;", vtxt)
+    out.append("struct VolumeGrid : Hittable {\n%s\n};\n" % rewrite(vtxt))
     msrc = type_body(rd("RayTracing/Mesh.cs"), "Mesh")
     msel = [t for t, n in members(msrc) if n != "FromObj"]
     mtxt = "\n".join(msel)

@@ -254,7 +254,8 @@ def test_mesh_tree_and_hits_equal_the_reference_source(ref, scene):
 
 
 TRACE_CASES = [("cornell", 20, 8, 2, None), ("mirror_spheres", 24, 8, 2, None), ("boxes", 20, 8, 1, None), ("cylinders_disks_triangles", 20, 8, 2, None), ("test", 24, 9, 2, None),
-               ("teapot", 20, 8, 2, api.BENCH_POSE), ("knot:40x10", 18, 7, 2, api.BENCH_POSE), ("cow", 16, 6, 2, api.BENCH_POSE)]
+               ("teapot", 20, 8, 2, api.BENCH_POSE), ("knot:40x10", 18, 7, 2, api.BENCH_POSE), ("cow", 16, 6, 2, api.BENCH_POSE),
+               ("volume_grid_test", 24, 9, 2, None), ("voxel_world:64x64", 20, 8, 2, None), ("voxel_island:64x64", 20, 8, 2, None)]
 
 
 @pytest.mark.parametrize("scene,fb_w,fb_h,ss,pose", TRACE_CASES, ids=[c[0] for c in TRACE_CASES])
@@ -265,13 +266,15 @@ def test_trace_stage_equals_the_reference_source(ref, scene, fb_w, fb_h, ss, pos
     Rays, radiance, albedo, raw normal, depth and the sky mask of every pixel must equal the oracle's, bit for bit."""
     vp = C.c_void_p
     ref.ref_trace_create.restype = vp
-    ref.ref_trace_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int] + [vp] * 10 + [C.c_int] + [vp] * 4
+    ref.ref_trace_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int] + [vp] * 10 + [C.c_int] + [vp] * 4 + [C.c_int, vp, C.c_int, vp, C.c_int]
     ref.ref_trace_destroy.argtypes = [vp]
     ref.ref_trace_frame.argtypes = [vp, vp, C.c_float, C.c_float] + [vp] * 6
     s = api.HostScene(scene)
     f = s.flat.contents
     n_obj = f.n_objects
-    assert all(f.objects[k].kind <= 9 for k in range(n_obj))
+    assert all(f.objects[k].kind <= 10 for k in range(n_obj))
+    vols = (api.Volume * max(1, s.n_volumes))(*[s.volume(i).contents for i in range(s.n_volumes)])
+    all_mats = np.array([mat(f.materials[i]) for i in range(f.n_materials)] + [[0] * 13], np.float32) if False else None
     kind = np.array([f.objects[k].kind for k in range(n_obj)], np.int32)
     p12 = np.array([list(f.objects[k].p) for k in range(n_obj)], np.float32)
 
@@ -291,7 +294,9 @@ def test_trace_stage_equals_the_reference_source(ref, scene, fb_w, fb_h, ss, pos
     amb = np.array(list(f.ambient_color) + [f.ambient_intensity], np.float32)
     cam = pose if pose is not None else s.default_camera()[:3]
     fov = s.default_camera()[3]
-    h = ref.ref_trace_create(fb_w, fb_h, ss, fov, n_obj, P(kind), P(p12), P(ma), P(mb), P(cs), P(sp), P(rf), P(mesh_n), mesh_ptrs, P(mesh_mat), f.n_lights, P(lights), P(top), P(bot), P(amb))
+    all_mats = np.array([mat(f.materials[i]) for i in range(f.n_materials)] + [[0] * 13], np.float32)
+    h = ref.ref_trace_create(fb_w, fb_h, ss, fov, n_obj, P(kind), P(p12), P(ma), P(mb), P(cs), P(sp), P(rf), P(mesh_n), mesh_ptrs, P(mesh_mat), f.n_lights, P(lights), P(top), P(bot), P(amb),
+                             s.n_volumes, C.cast(vols, C.c_void_p), f.n_materials, P(all_mats), f.is_volume_scene)
     assert h
     o = Oracle(s, fb_w, fb_h, ss)
     o.set_camera(*cam)
