@@ -114,17 +114,51 @@ def algorithmic_bytes(st, W, H, fb_w, fb_h, ss):
 
 
 def cpu_leg(args, fb_w, fb_h, ss, seconds, steps=None, warmup=1):
-    """The reference's CPU path (oracle restatement, reference thread partitioning) on the workload itself: the same scene,
-    pose and FULL internal resolution; the sample is bounded in FRAMES (each one a complete TryFlipAndBlit), never in pixels.
-    `steps`: render exactly that many frames (the reference arm, capped by `seconds`); else as many as fit `seconds` (>= 2)."""
+    """The reference's CPU path on the workload itself: the same scene, pose and FULL internal resolution; the sample is bounded in
+    FRAMES (each one a complete TryFlipAndBlit), never in pixels.  `steps`: render exactly that many frames (the reference arm,
+    capped by `seconds`); else as many as fit `seconds` (>= 2).
+    kind "reference": oracle/_ref/libycge_ref.so -- the reference's OWN C# source text, rewritten into C++ syntactically at build time
+    (oracle/ref_transpile.py) and compiled; its thread pools run on all host cores as the reference's do (trace striped over the cores;
+    TAA, a-trous, exposure serial, RaytraceRenderer.cs:218-227).  It has no ray counter (neither has the reference): rays per frame are
+    counted by the oracle restatement on the same pose (identical frames, tests/test_reference_transpiled.py).
+    kind "port": the oracle restatement itself, when the transpiled library was not built (no reference checkout at build time)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import yetanotherconsolegameengine_b200 as pkg
     from oracle_binding import Oracle
+    import ref_binding
     cores = os.cpu_count() or 1
     scene = pkg.HostScene(args.scene)
+    pose = pkg.BENCH_POSE if uses_bench_pose(args.scene) else None
+    use_ref = ref_binding.available() and scene.n_textures == 0 and not os.environ.get("YCGE_CPU_PORT")
+    if use_ref:
+        o = Oracle(scene, fb_w, fb_h, ss)
+        if pose:
+            o.set_camera(*pose)
+        o.render_frame(threads=cores)
+        o.render_frame(threads=cores)
+        rays_per_frame = o.stats()["rays"]  # frame 2 (frames differ by a fraction of a percent: the RNG stream is per frame)
+        o.close()
+        r = ref_binding.RefRenderer(scene, fb_w, fb_h, ss, threads=cores)
+        if pose:
+            r.set_camera(*pose)
+        for _ in range(warmup):
+            r.render_frame()
+        frames, t0 = 0, time.perf_counter()
+        while True:
+            r.render_frame()
+            frames += 1
+            el = time.perf_counter() - t0
+            if (steps is not None and frames >= steps) or (frames >= 2 and el >= seconds) or frames >= 64:
+                break
+        el = time.perf_counter() - t0
+        r.close()
+        return {"value": rays_per_frame * frames / el / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                "sample": f"{frames} complete frames (after {warmup} untimed) of the workload itself at the full {fb_w}x{fb_h} cells ss={ss} ({fb_w*ss}x{fb_h*2*ss} px) through oracle/_ref: the "
+                          f"reference's own C# sources transpiled to C++ at build time; thread pools on all {cores} cores (trace), TAA / a-trous / exposure serial as in the reference",
+                "frames_per_s": frames / el, "ms_per_stage": None, "seconds": el, "frames": frames}
     o = Oracle(scene, fb_w, fb_h, ss)
-    if uses_bench_pose(args.scene):
-        o.set_camera(*pkg.BENCH_POSE)
+    if pose:
+        o.set_camera(*pose)
     for _ in range(warmup):
         o.render_frame(threads=cores)
     rays, frames, t0 = 0, 0, time.perf_counter()
@@ -165,7 +199,7 @@ def main():
         line = {"impl": "reference", "metric": "Mrays/s", "value": leg["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "steps_run": leg["frames"], "ms_per_step": 1e3 * leg["seconds"] / leg["frames"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "frames_per_s": leg["frames_per_s"], "same_config": True,
-                "config": {"workload": workload, "note": "CPU restatement of the C# reference (no .NET toolchain here), all host cores; every step is a complete frame at the workload's full resolution"},
+                "config": {"workload": workload, "note": "the reference's CPU path on all host cores (cpu_baseline.kind says which build of it: its own sources transpiled, or the restatement); every step is a complete frame at the workload's full resolution"},
                 "stage_ms": leg["ms_per_stage"],
                 "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": leg["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}

@@ -249,7 +249,7 @@ RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_o
         h->scene.RebuildBVH();
         RendererRef &r = h->r;
         r.scene = &h->scene;
-        r.ss = ss; r.fbW = fb_w; r.fbH = fb_h; r.procCount = 3; r.fovDeg = fov_deg;
+        r.ss = ss; r.fbW = fb_w; r.fbH = fb_h; r.procCount = refcs::ref_threads() > 1 ? refcs::ref_threads() : 3; r.fovDeg = fov_deg;
         r.hiW = fb_w * ss; r.hiH = fb_h * 2 * ss; // RaytraceRenderer.cs:86-87
         r.rays = Fast2D<Ray>(r.hiW, r.hiH);
         r.gAlbedo = Fast2D<Vec3>(r.hiW, r.hiH); r.gNormal = Fast2D<Vec3>(r.hiW, r.hiH); r.gDepth = Fast2D<float>(r.hiW, r.hiH); r.skyMask = Fast2D<bool>(r.hiW, r.hiH);
@@ -279,3 +279,6 @@ RH_API int ref_trace_frame(void *hh, const float *cam3, float yaw, float pitch, 
     } catch (...) { return -1; }
 }
 refcs::Vec3 refcs::Texture::SampleBilinear(float, float) { throw std::runtime_error("textured scenes are not run through the transpiled reference"); }
+
+// worker threads of FixedThreadFor / PixelThreadPool (the reference uses Environment.ProcessorCount); 1 = serial
+RH_API void ref_set_threads(int n) { refcs::ref_threads() = n < 1 ? 1 : n; }

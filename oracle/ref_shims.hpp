@@ -14,6 +14,7 @@
 #include <limits>
 #include <memory>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 #include "../include/ycge_detmath.h"
 
@@ -79,12 +80,25 @@ template <class T> struct Fast2D {
     T *Buffer() const { return p->d.get(); }
 };
 
-struct FixedThreadFor { // Renderer/FixedThreadFor.cs: For(from, to, body) -- every worker index once; serial here (the bodies write disjoint rows)
-    void For(int from, int to, const std::function<void(int)> &body) { for (int i = from; i < to; i++) body(i); }
+// Renderer/FixedThreadFor.cs: For(from, to, body) -- every worker index once, one thread each (the bodies write disjoint rows)
+inline int &ref_threads() { static int n = 1; return n; }
+struct FixedThreadFor {
+    void For(int from, int to, const std::function<void(int)> &body) {
+        if (ref_threads() <= 1 || to - from <= 1) { for (int i = from; i < to; i++) body(i); return; }
+        std::vector<std::thread> th;
+        for (int i = from; i < to; i++) th.emplace_back([&body, i] { body(i); });
+        for (auto &t : th) t.join();
+    }
 };
 
-struct PixelThreadPool { // Renderer/PixelThreadPool.cs: For2D(w, h, body(px, py, threadId)) -- every pixel once; serial here (pixels are independent)
-    void For2D(int w, int h, const std::function<void(int, int, int)> &body) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) body(x, y, 0); }
+struct PixelThreadPool { // Renderer/PixelThreadPool.cs: For2D(w, h, body(px, py, threadId)) -- every pixel once, striped over the worker threads (pixels are independent)
+    void For2D(int w, int h, const std::function<void(int, int, int)> &body) {
+        const int n = ref_threads();
+        if (n <= 1) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) body(x, y, 0); return; }
+        std::vector<std::thread> th;
+        for (int k = 0; k < n; k++) th.emplace_back([&body, k, n, w, h] { for (long long p = k; p < (long long)w * h; p += n) body((int)(p % w), (int)(p / w), k); });
+        for (auto &t : th) t.join();
+    }
 };
 enum ConsoleColor : int { Black = 0 };
 

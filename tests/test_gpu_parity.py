@@ -124,6 +124,44 @@ def test_systolic_in_place_pass_full_size_equals_the_default_form():
         a.close(); b.close(); s.close()
 
 
+# ------------------------------------------------------------------------------------------- the reference's own source, no oracle in between
+REF_CASES = [("cornell", 40, 12, 2, None), ("mirror_spheres", 48, 14, 2, None), ("cylinders_disks_triangles", 32, 10, 2, None), ("teapot", 40, 12, 2, api.BENCH_POSE),
+             ("knot:60x16", 36, 10, 3, api.BENCH_POSE), ("volume_grid_test", 40, 12, 2, None), ("voxel_world:64x64", 36, 10, 2, None)]
+
+
+@pytest.mark.parametrize("case", REF_CASES, ids=[c[0] for c in REF_CASES])
+def test_gpu_equals_the_transpiled_reference(case):
+    """The CUDA path against oracle/_ref -- the reference's OWN C# source text rewritten into C++ syntactically at build time
+    (oracle/ref_transpile.py; the built library travels to this box) -- with no hand-written oracle in between: four frames of
+    TryFlipAndBlit (trace stage + TAA + a-trous + exposure + cells), every plane and every cell field bit for bit."""
+    import ref_binding
+    if not ref_binding.available():
+        pytest.fail("oracle/_ref/libycge_ref.so did not travel to the GPU box (it is built where /root/reference exists)")
+    scene, fb_w, fb_h, ss, pose = case
+    s = api.HostScene(scene)
+    r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
+    ref = ref_binding.RefRenderer(s, fb_w, fb_h, ss)
+    if pose is not None:
+        r.SetCamera(*pose)
+        ref.set_camera(*pose)
+    for frame in range(1, 5):
+        g = r.TryFlipAndBlit()
+        c = ref.render_frame()
+        what = f"{scene} frame {frame}"
+        asky = r.debug_read(api.DBG_ALBEDO_SKY)
+        assert np.array_equal(asky[..., 3] != 0, c["sky"] != 0), what + ": sky mask"
+        assert bits_differ(r.debug_read(api.DBG_HDR)[..., :3], c["hdr"]) == 0, what + ": radiance"
+        assert bits_differ(asky[..., :3], c["albedo"]) == 0, what + ": albedo"
+        assert bits_differ(r.debug_read(api.DBG_NORMAL_DEPTH)[..., 3], c["depth"]) == 0, what + ": depth"
+        assert bits_differ(r.debug_read(api.DBG_TAA)[..., :3], c["taa"]) == 0, what + ": TAA history"
+        assert bits_differ(r.debug_read(api.DBG_DENOISED)[..., :3], c["den"]) == 0, what + ": denoised"
+        assert np.float32(r.stats()["ae_exposure"]).view(np.uint32) == c["expo"][:1].view(np.uint32)[0], what + ": aeExposure"
+        for k in ("glyph", "fg16", "bg16", "fg_ansi", "bg_ansi"):
+            assert np.array_equal(g[k], c[k]), what + ": cell field " + k
+        assert bits_differ(g["fg"], c["fg"]) == 0 and bits_differ(g["bg"], c["bg"]) == 0, what + ": SDR colours"
+    ref.close(); r.close(); s.close()
+
+
 # ------------------------------------------------------------------------------------------- live oracle, every tap
 LIVE = [  # scene, fb_w, fb_h, ss, frames, pose
     ("cornell", 60, 34, 1, 3, None),
