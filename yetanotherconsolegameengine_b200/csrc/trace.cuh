@@ -109,10 +109,14 @@ __device__ __forceinline__ Mat load_material(const DevScene &sc, const Hit &h) {
 #define YCGE_STACK 96
 struct Stack { int ref[YCGE_STACK]; float tn[YCGE_STACK]; };
 
-template <bool STATS> struct Cnt {
+template <int MODE> struct Cnt {
     unsigned int rays = 0, top_nodes = 0, mesh_nodes = 0, leaf_refs = 0, tris = 0, prims = 0, dda = 0, overflow = 0;
 };
-#define CNT_INC(c, f) do { if (STATS) (c).f++; } while (0)
+// MODE bit 0: count the reference-defined traversal events (ycge_render_frame_stats); bit 1: LEAN -- the scene holds no voxel grid, no texture
+// and no transparent material (decided at ycge_scene_upload), so the DDA, the texture sampler and the deferred-branch stack are compiled out:
+// a smaller kernel for the mesh / primitive scenes (same arithmetic for what remains, bit-identical)
+#define CNT_INC(c, f) do { if (MODE & 1) (c).f++; } while (0)
+#define YCGE_LEAN ((MODE & 2) != 0)
 
 // ------------------------------------------------------------------------------------------------ box tests
 // BVH.BoxHitFast (BVH.cs:201-236): swap-ordered slabs, NaN-propagating max/min, clamp to [tMin,tMax].
@@ -153,8 +157,8 @@ __device__ __forceinline__ bool box_mesh(float mnx, float mny, float mnz, float 
 // 1.20 ms; (3) 16..40 resident warps per SM via launch bounds: no change.  The triangle loop runs with 2-3 of 32 lanes
 // active and 21 % of the stall samples are instruction-fetch misses, but the kernel is bound by the dependent node /
 // triangle fetch latency of the longest paths in each warp, not by those.
-template <bool STATS>
-__device__ bool mesh_hit(const DevMesh &mesh, const RayD &r, float tMin, float tMax, Stack &st, int sp0, Cnt<STATS> &cnt,
+template <int MODE>
+__device__ bool mesh_hit(const DevMesh &mesh, const RayD &r, float tMin, float tMax, Stack &st, int sp0, Cnt<MODE> &cnt,
                          float &tOut, int &slotOut) {
     V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     int sx = inv.x < 0.0f ? 1 : 0, sy = inv.y < 0.0f ? 1 : 0, sz = inv.z < 0.0f ? 1 : 0;
@@ -254,8 +258,8 @@ __device__ __forceinline__ double edge_distance(double v, double v0, double v1) 
     if (b < 0.0) b = 0.0;
     return a < b ? a : b;
 }
-template <bool STATS>
-__device__ bool volume_hit(const DevVolume &g, const RayD &r, float tMin, float tMax, Cnt<STATS> &cnt, Hit &h) {
+template <int MODE>
+__device__ bool volume_hit(const DevVolume &g, const RayD &r, float tMin, float tMax, Cnt<MODE> &cnt, Hit &h) {
     float minX = g.min_corner[0], minY = g.min_corner[1], minZ = g.min_corner[2];
     float sizeX = g.voxel_size[0], sizeY = g.voxel_size[1], sizeZ = g.voxel_size[2];
     int nx = g.nx, ny = g.ny, nz = g.nz;
@@ -375,8 +379,8 @@ __device__ __forceinline__ bool rect_hit(const DevObject &o, int axis, float a0,
     return true;
 }
 
-template <bool STATS>
-__device__ bool object_hit(const DevScene &sc, int objId, const RayD &r, float tMin, float tMax, Stack &st, int sp, Cnt<STATS> &cnt, Hit &h) {
+template <int MODE>
+__device__ bool object_hit(const DevScene &sc, int objId, const RayD &r, float tMin, float tMax, Stack &st, int sp, Cnt<MODE> &cnt, Hit &h) {
     CNT_INC(cnt, prims);
     const DevObject &o = sc.objects[objId];
     const int kind = o.kind;
@@ -534,7 +538,7 @@ __device__ bool object_hit(const DevScene &sc, int objId, const RayD &r, float t
         case YCGE_MESH: { // Mesh.cs:26-29 -> MeshBVH.Hit
             const DevMesh &mesh = sc.meshes[o.ref];
             float t; int slot;
-            if (!mesh_hit<STATS>(mesh, r, tMin, tMax, st, sp, cnt, t, slot)) return false;
+            if (!mesh_hit<MODE>(mesh, r, tMin, tMax, st, sp, cnt, t, slot)) return false;
             float4 t2 = __ldg(&mesh.tris[slot].t2);
             float nx = t2.y, ny = t2.z, nz = t2.w;
             h.t = t; h.P = mk(r.o.x + t * r.d.x, r.o.y + t * r.d.y, r.o.z + t * r.d.z);
@@ -544,14 +548,14 @@ __device__ bool object_hit(const DevScene &sc, int objId, const RayD &r, float t
             h.sub = slot; // leaf slot; the MeshLoader face index (tri_id[slot]) is looked up by whoever needs it (mesh_face_id)
             return true;
         }
-        case YCGE_VOLUME: return volume_hit<STATS>(sc.volumes[o.ref], r, tMin, tMax, cnt, h);
+        case YCGE_VOLUME: if (YCGE_LEAN) return false; else return volume_hit<MODE>(sc.volumes[o.ref], r, tMin, tMax, cnt, h);
     }
     return false;
 }
 
 // ------------------------------------------------------------------------------------------------ Scene.Hit -> BVH.Hit (BVH.cs:99-198)
-template <bool STATS>
-__device__ bool scene_hit(const DevScene &sc, const RayD &r, float tMin, float tMax, Stack &st, Cnt<STATS> &cnt, Hit &best) {
+template <int MODE>
+__device__ bool scene_hit(const DevScene &sc, const RayD &r, float tMin, float tMax, Stack &st, Cnt<MODE> &cnt, Hit &best) {
     cnt.rays++;
     if (sc.root.ref == YCGE_REF_NONE) return false;
     V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
@@ -578,7 +582,7 @@ __device__ bool scene_hit(const DevScene &sc, const RayD &r, float tMin, float t
                 CNT_INC(cnt, leaf_refs);
                 int objId = __ldg(sc.leaf_obj + start + i);
                 Hit tmp;
-                if (object_hit<STATS>(sc, objId, r, tMin, closest, st, sp, cnt, tmp)) {
+                if (object_hit<MODE>(sc, objId, r, tMin, closest, st, sp, cnt, tmp)) {
                     any = true; closest = tmp.t; best = tmp; best.obj = objId;
                 }
             }
@@ -654,18 +658,18 @@ __device__ V3 cosine_sample_hemisphere(V3 w, unsigned long long &rng) { // Raytr
     return uAxis * x + vAxis * y + w * z;
 }
 
-template <bool STATS>
-__device__ V3 transmittance_to_light(const DevScene &sc, const TraceParams &tp, const RayD &shadow, float maxDist, Stack &st, Cnt<STATS> &cnt) { // :757-798
+template <int MODE>
+__device__ V3 transmittance_to_light(const DevScene &sc, const TraceParams &tp, const RayD &shadow, float maxDist, Stack &st, Cnt<MODE> &cnt) { // :757-798
     Hit block;
-    if (sc.is_volume_scene) { // Scene.Occluded: a full nearest-hit query with tMin 0.001 (Scene.cs:77-82)
-        bool blocked = scene_hit<STATS>(sc, shadow, 0.001f, maxDist, st, cnt, block);
+    if (!YCGE_LEAN && sc.is_volume_scene) { // Scene.Occluded: a full nearest-hit query with tMin 0.001 (Scene.cs:77-82)
+        bool blocked = scene_hit<MODE>(sc, shadow, 0.001f, maxDist, st, cnt, block);
         return blocked ? mk(0.0f, 0.0f, 0.0f) : mk(1.0f, 1.0f, 1.0f);
     }
     float transR = 1.0f, transG = 1.0f, transB = 1.0f;
     float tmin = 0.0f + tp.eps;
     int counter = 0;
     const float cutoff = 1e-6f;
-    while (counter < tp.max_refractions && scene_hit<STATS>(sc, shadow, tmin, maxDist, st, cnt, block)) {
+    while (counter < tp.max_refractions && scene_hit<MODE>(sc, shadow, tmin, maxDist, st, cnt, block)) {
         counter++;
         Mat bm = load_material(sc, block);
         if (bm.transparency <= 0.0f) return mk(0.0f, 0.0f, 0.0f);
@@ -777,13 +781,13 @@ struct PathItem { RayD ray; V3 beta; int mirror, diffuse; };
 #ifndef YCGE_TRACE_MIN_CTAS
 #define YCGE_TRACE_MIN_CTAS 8 // measured on B200 (dragon 1080p): 5 CTAs/SM 1.21 ms, 6: 1.22, 8: 1.19, 10: 1.21 — occupancy is not the limiter
 #endif
-template <bool STATS>
+template <int MODE>
 __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScene sc, FrameConsts fc, TraceParams tp, ImagePlanes img, int parity, TraceCounters *counters, TraceTotals *totals) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int py = fc.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < fc.W && py < fc.y1;
-    Cnt<STATS> cnt;
+    Cnt<MODE> cnt;
 
     if (active) {
         Stack st;
@@ -824,7 +828,7 @@ __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScen
         while (havePath) {
             for (;;) {
                 Hit rec;
-                if (!scene_hit<STATS>(sc, cur, 0.001f, YCGE_FLT_MAX, st, cnt, rec)) {
+                if (!scene_hit<MODE>(sc, cur, 0.001f, YCGE_FLT_MAX, st, cnt, rec)) {
                     float tbg = 0.5f * (cur.d.y + 1.0f);
                     V3 bb = mk(sc.bg_bottom[0], sc.bg_bottom[1], sc.bg_bottom[2]), bt = mk(sc.bg_top[0], sc.bg_top[1], sc.bg_top[2]);
                     V3 sky = bb * (1.0f - tbg) + bt * tbg;
@@ -833,7 +837,7 @@ __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScen
                     break;
                 }
                 Mat m = load_material(sc, rec);
-                if (sc.n_textures > 0) { // :494,:505 (both calls see the same hit)
+                if (!YCGE_LEAN && sc.n_textures > 0) { // :494,:505 (both calls see the same hit)
                     TexRefs tr = {sc.objects, sc.meshes, sc.materials, sc.textures, sc.n_textures};
                     float3 al = sample_albedo(tr, make_float3(m.albedo.x, m.albedo.y, m.albedo.z), rec.mat, rec.obj, rec.sub, make_float3(rec.P.x, rec.P.y, rec.P.z),
                                               make_float3(cur.o.x, cur.o.y, cur.o.z), make_float3(cur.d.x, cur.d.y, cur.d.z));
@@ -847,7 +851,7 @@ __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScen
                 if (m.emission.x != 0.0f || m.emission.y != 0.0f || m.emission.z != 0.0f)
                     radiance = radiance + mk(beta.x * m.emission.x, beta.y * m.emission.y, beta.z * m.emission.z);
                 V3 baseAlbedo = m.albedo;
-                if (m.transparency > 0.0f) {
+                if (!YCGE_LEAN && m.transparency > 0.0f) {
                     if (mirrorDepth >= tp.max_mirror_bounces) break;
                     V3 n = rec.N, wo = cur.d;
                     bool frontFace = dot3(n, wo) < 0.0f;
@@ -902,7 +906,7 @@ __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScen
                     float nDotL = MaxF(0.0f, dot3(rec.N, ldir));
                     if (nDotL <= 0.0f) continue;
                     RayD shadow = make_ray(rec.P + rec.N * tp.eps, ldir);
-                    V3 trans = transmittance_to_light<STATS>(sc, tp, shadow, dist - tp.eps, st, cnt);
+                    V3 trans = transmittance_to_light<MODE>(sc, tp, shadow, dist - tp.eps, st, cnt);
                     if (trans.x <= 1e-6f && trans.y <= 1e-6f && trans.z <= 1e-6f) continue;
                     float atten = L.intensity / dist2;
                     V3 fDiffuse = oren_nayar(baseAlbedo, rec.N, woView, ldir, tp.sigma_rad);
@@ -923,7 +927,7 @@ __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScen
                 }
                 break;
             }
-            if (sp > 0) {
+            if (!YCGE_LEAN && sp > 0) {
                 sp--;
                 cur = stack[sp].ray; beta = stack[sp].beta; mirrorDepth = stack[sp].mirror; diffuseDepth = stack[sp].diffuse;
                 itemPrimary = false;
@@ -945,7 +949,7 @@ __global__ void __launch_bounds__(128, YCGE_TRACE_MIN_CTAS) trace_kernel(DevScen
     for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
     if (lane == 0 && rays) { atomicAdd(&counters->rays, (unsigned long long)rays); atomicAdd(&totals->rays_total, (unsigned long long)rays); }
     if (cnt.overflow) { atomicAdd(&counters->stack_overflow, (unsigned long long)cnt.overflow); if (tp.host_err) *(volatile int *)tp.host_err = 2; }
-    if (STATS) {
+    if (MODE & 1) {
         unsigned int vals[6] = {cnt.top_nodes, cnt.mesh_nodes, cnt.leaf_refs, cnt.tris, cnt.prims, cnt.dda};
         unsigned long long *dst[6] = {&counters->top_nodes, &counters->mesh_nodes, &counters->leaf_refs, &counters->tris, &counters->prims, &counters->dda};
         for (int k = 0; k < 6; k++) {

@@ -30,7 +30,7 @@ enum { YCGE_ACT_TRACE = 0, YCGE_ACT_LIGHT_DONE = 1, YCGE_ACT_NEXT_LIGHT = 2, YCG
 #define YCGE_STREAM_MIN_CTAS 8
 #endif
 
-template <bool STATS>
+template <int MODE>
 __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel(DevScene sc, FrameConsts fc, TraceParams tp, ImagePlanes img, int parity, TraceCounters *counters,
                                                                                  TraceTotals *totals, int refill_min) {
     const unsigned int FULL = 0xffffffffu;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel
     const int tiles_x = (fc.W + 7) >> 3;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)((fc.y1 - fc.y0 + 3) >> 2);
     unsigned int *next_tile = (unsigned int *)&counters->next_tile;
-    Cnt<STATS> cnt;
+    Cnt<MODE> cnt;
     Stack st;
     PathItem stack[YCGE_PATH_STACK];
 
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel
         // ---- one Scene.Hit / Scene.Occluded for every lane that carries a ray
         Hit rec;
         bool hit = false;
-        if (phase != YCGE_PH_IDLE) hit = scene_hit<STATS>(sc, ray, tMin, tMax, st, cnt, rec);
+        if (phase != YCGE_PH_IDLE) hit = scene_hit<MODE>(sc, ray, tMin, tMax, st, cnt, rec);
         if (phase == YCGE_PH_IDLE) continue;
 
         int act = YCGE_ACT_TRACE;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel
                 act = YCGE_ACT_ITEM_DONE;
             } else {
                 Mat m = load_material(sc, rec);
-                if (sc.n_textures > 0) { // :494,:505 (both calls see the same hit)
+                if (!YCGE_LEAN && sc.n_textures > 0) { // :494,:505 (both calls see the same hit)
                     TexRefs tr = {sc.objects, sc.meshes, sc.materials, sc.textures, sc.n_textures};
                     float3 al = sample_albedo(tr, make_float3(m.albedo.x, m.albedo.y, m.albedo.z), rec.mat, rec.obj, rec.sub, make_float3(rec.P.x, rec.P.y, rec.P.z),
                                               make_float3(ray.o.x, ray.o.y, ray.o.z), make_float3(ray.d.x, ray.d.y, ray.d.z));
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel
                 if (m.emission.x != 0.0f || m.emission.y != 0.0f || m.emission.z != 0.0f)
                     radiance = radiance + mk(beta.x * m.emission.x, beta.y * m.emission.y, beta.z * m.emission.z);
                 V3 baseAlbedo = m.albedo;
-                if (m.transparency > 0.0f) {
+                if (!YCGE_LEAN && m.transparency > 0.0f) {
                     if (mirrorDepth < tp.max_mirror_bounces) {
                         V3 n = rec.N, wo = ray.d;
                         bool frontFace = dot3(n, wo) < 0.0f;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel
                 }
             }
         } else { // the shadow ray of light `li` came back: one turn of ComputeTransmittanceToLight's loop :757-798
-            if (sc.is_volume_scene) { // Scene.Occluded: a full nearest-hit query with tMin 0.001 (Scene.cs:77-82)
+            if (!YCGE_LEAN && sc.is_volume_scene) { // Scene.Occluded: a full nearest-hit query with tMin 0.001 (Scene.cs:77-82)
                 float tv = hit ? 0.0f : 1.0f;
                 transR = tv; transG = tv; transB = tv;
                 act = YCGE_ACT_LIGHT_DONE;
@@ -270,13 +270,13 @@ __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel
             transR = 1.0f; transG = 1.0f; transB = 1.0f;
             counter = 0;
             tMax = maxDist;
-            if (sc.is_volume_scene) { tMin = 0.001f; phase = YCGE_PH_SHADOW; act = YCGE_ACT_TRACE; }
+            if (!YCGE_LEAN && sc.is_volume_scene) { tMin = 0.001f; phase = YCGE_PH_SHADOW; act = YCGE_ACT_TRACE; }
             else if (counter < tp.max_refractions) { tMin = 0.0f + tp.eps; phase = YCGE_PH_SHADOW; act = YCGE_ACT_TRACE; }
             else act = YCGE_ACT_LIGHT_DONE; // max_refractions == 0: the loop :773 never runs, full transmittance
         }
 
         if (act == YCGE_ACT_ITEM_DONE) {
-            if (sp > 0) { // :463-468: next deferred item (reflection / refraction branch)
+            if (!YCGE_LEAN && sp > 0) { // :463-468: next deferred item (reflection / refraction branch)
                 sp--;
                 ray = stack[sp].ray; beta = stack[sp].beta; mirrorDepth = stack[sp].mirror; diffuseDepth = stack[sp].diffuse;
                 itemPrimary = false;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128, YCGE_STREAM_MIN_CTAS) trace_stream_kernel
     for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(FULL, rays, off);
     if (lane == 0 && rays) { atomicAdd(&counters->rays, (unsigned long long)rays); atomicAdd(&totals->rays_total, (unsigned long long)rays); }
     if (cnt.overflow) { atomicAdd(&counters->stack_overflow, (unsigned long long)cnt.overflow); if (tp.host_err) *(volatile int *)tp.host_err = 2; }
-    if (STATS) {
+    if (MODE & 1) {
         unsigned int vals[6] = {cnt.top_nodes, cnt.mesh_nodes, cnt.leaf_refs, cnt.tris, cnt.prims, cnt.dda};
         unsigned long long *dst[6] = {&counters->top_nodes, &counters->mesh_nodes, &counters->leaf_refs, &counters->tris, &counters->prims, &counters->dda};
         for (int k = 0; k < 6; k++) {

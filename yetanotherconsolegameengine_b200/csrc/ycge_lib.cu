@@ -122,6 +122,7 @@ struct ycge_ctx {
     bool debug_rays = false;
     float ansi_th[5] = {0, 0, 0, 0, 0};
     int inplace_ctas_per_launch = 0, inplace_ctas_static = 0;
+    bool trace_lean = false; // the scene holds no voxel grid, no texture and no transparent material: the smaller kernel variant (trace.cuh MODE bit 1)
     int trace_variant = 1;  // 0: one thread per pixel path (trace_kernel), 1: ray stream with lane refill (trace_stream_kernel)
     int stream_ctas = 0, stream_ctas_stats = 0;
     // resumable à-trous state of the frame in flight (a sharded tile pauses before every in-place pass so that the caller
@@ -516,19 +517,28 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
                 int occ = 0, occ_s = 0;
                 cudaDeviceProp prop;
                 CK(c, cudaGetDeviceProperties(&prop, c->device));
-                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_stream_kernel<false>, 128, 0));
-                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, trace_stream_kernel<true>, 128, 0));
+                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_stream_kernel<0>, 128, 0));
+                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, trace_stream_kernel<1>, 128, 0));
                 c->stream_ctas = std::max(1, occ * prop.multiProcessorCount);
                 c->stream_ctas_stats = std::max(1, occ_s * prop.multiProcessorCount);
             }
             const int n_tiles = div_up(W, 8) * div_up(b - a, 4);
             const int refill_min = getenv("YCGE_STREAM_REFILL") ? atoi(getenv("YCGE_STREAM_REFILL")) : 32; // development aid; see trace_stream.cuh
-            if (c->want_stats) trace_stream_kernel<true><<<std::min(c->stream_ctas_stats, div_up(n_tiles, 4)), 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min);
-            else trace_stream_kernel<false><<<std::min(c->stream_ctas, div_up(n_tiles, 4)), 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min);
+            const int gs = std::min(c->want_stats ? c->stream_ctas_stats : c->stream_ctas, div_up(n_tiles, 4));
+            switch ((c->want_stats ? 1 : 0) | (c->trace_lean ? 2 : 0)) { // MODE (trace.cuh): bit 0 event counters, bit 1 lean scene
+                case 0: trace_stream_kernel<0><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
+                case 1: trace_stream_kernel<1><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
+                case 2: trace_stream_kernel<2><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
+                default: trace_stream_kernel<3><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
+            }
         } else {
             dim3 grid(div_up(W, 16), div_up(b - a, 8));
-            if (c->want_stats) trace_kernel<true><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
-            else trace_kernel<false><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p);
+            switch ((c->want_stats ? 1 : 0) | (c->trace_lean ? 2 : 0)) {
+                case 0: trace_kernel<0><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
+                case 1: trace_kernel<1><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
+                case 2: trace_kernel<2><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
+                default: trace_kernel<3><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
+            }
         }
         launches++;
     }
@@ -1275,6 +1285,11 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) try {
     ds.n_lights = s->n_lights; ds.is_volume_scene = s->is_volume_scene;
     for (int k = 0; k < 3; k++) { ds.bg_top[k] = s->bg_top[k]; ds.bg_bottom[k] = s->bg_bottom[k]; ds.ambient[k] = s->ambient_color[k]; }
     ds.ambient_intensity = s->ambient_intensity;
+    { // lean scene: nothing that needs the DDA, the texture sampler or the deferred-branch stack (mats[4 m + 1].w = transparency)
+        bool lean = dvols.empty() && dtex.empty() && !s->is_volume_scene && !getenv("YCGE_NO_LEAN");
+        for (size_t m = 0; lean && m + 3 < mats.size(); m += 4) if (mats[m + 1].w > 0.0f) lean = false;
+        c->trace_lean = lean;
+    }
     c->have_scene = true;
     return 0;
 } YCGE_CATCH
