@@ -5,14 +5,22 @@
  * call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, as the checker and as the timed CPU baseline.
  *
- * PARITY UNPINNED: the reference (C#/.NET 8) has no tests, golden vectors or fixtures for this path
- * and cannot be compiled or run here (no dotnet/mono).  This file follows the reference source line
- * by line (citations are relative to /root/reference/ConsoleGame/).  What pins it instead:
- * known-answer vectors derived by hand from the integer-defined parts (tests/test_oracle_kat.py); a SECOND restatement of
- * every stage in another language, transcribed from the C# source into numpy binary32 scalars, that reproduces this file bit
- * for bit (trace: tests/test_oracle_trace_literal.py; TAA, exposure, cells, à-trous: tests/test_oracle_render.py; both BVH
- * builders: tests/test_bvh_builder_literal.py); scene factories, palettes, tables and constants compared with values
- * extracted mechanically from the C# text (tools/extract_scene_literals.py).
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN SOURCE TEXT (oracle/_ref).  The reference (C#/.NET 8) has no tests, golden
+ * vectors or fixtures for this path and no .NET toolchain exists here, so it cannot be run as shipped.  Instead
+ * oracle/ref_transpile.py rewrites its C# sources into C++ SYNTACTICALLY at build time (no arithmetic expression is touched;
+ * nothing generated is committed) and oracle/Makefile compiles them into oracle/_ref/libycge_ref.so: Vec3, Ray, Material,
+ * HitRecord, RaytraceSampler, every analytic primitive, Triangle (scalar path), MeshBVH and BVH (builders and traversal),
+ * Mesh, VolumeGrid, Scene.Hit / Occluded, TraceFull, ComputeTransmittanceToLight, the BSDF helpers, MakeJitteredRay, the
+ * verbatim head and tail of TryFlipAndBlit (ray generation, per-pixel trace loop; TAA, a-trous with the reference's own
+ * buffer swap, exposure, cell loop), ToneMapper, Chexel, the ANSI-256 quantiser.  This file must equal that library bit for
+ * bit -- whole frames, every plane (tests/test_reference_transpiled.py; the GPU is compared with it directly in
+ * tests/test_gpu_parity.py::test_gpu_equals_the_transpiled_reference).  One substitution is shared by all sides: MathF.Exp /
+ * Log / Pow / Sin / Cos / Tan = include/ycge_detmath.h (the platform libm behind them is not bit-reproducible).  Not covered by the
+ * transpiled library: Texture.SampleBilinear (static textures), TemporalAA.ShouldResetHistory, the scene factories and MeshLoader
+ * (host side) -- those keep the earlier pins: hand-derived known answers (tests/test_oracle_kat.py), a second
+ * restatement in numpy binary32 (tests/test_oracle_trace_literal.py, test_oracle_render.py, test_bvh_builder_literal.py), scene
+ * literals extracted by executing the C# factories' text (tools/extract_scene_literals.py).  This file follows the reference
+ * source line by line (citations are relative to /root/reference/ConsoleGame/).
  *
  * Arithmetic rules: binary32 everywhere the reference uses float, evaluated in the reference's
  * order, no FMA contraction (build with -O2 -ffp-contract=off, no -ffast-math, x86-64 SSE2).
