@@ -224,7 +224,7 @@ YDM_HD uint32_t ydm_f32_to_bits(float f) {
  * (remainder < 0.1 ulp), scaled by 2^k in two exact steps so that subnormal results are rounded once.  Within 1 ulp of
  * the true value for every input (tools/check_expf.c compares all 2^32 inputs with the binary64 evaluation above: never
  * more than 1 ulp apart, equal on 99.6 %, monotonic) -- the accuracy class of a platform expf, which is what MathF.Exp forwards to. */
-YDM_HD float ycge_expf(float x) {
+YDM_HD float ydm_expf_core(float x) {
     const float t = YDM_FMAF(x, 1.44269502f, 12582912.0f);                 /* 1.5 * 2^23 + rint(x / ln 2) */
     const float kf = YDM_ADDF(t, -12582912.0f);
     const int k = (int)(ydm_f32_to_bits(t) - 0x4B400000u);
@@ -240,9 +240,19 @@ YDM_HD float ycge_expf(float x) {
     const float p = YDM_ADDF(1.0f, q);
     const int k1 = k >> 1, k2 = k - k1;                                    /* both scale factors are normal numbers */
     const float s1 = ydm_f32_from_bits((uint32_t)(k1 + 127) << 23), s2 = ydm_f32_from_bits((uint32_t)(k2 + 127) << 23);
-    float res = YDM_MULF(YDM_MULF(p, s1), s2);
+    return YDM_MULF(YDM_MULF(p, s1), s2);
+}
+YDM_HD float ycge_expf(float x) {
+    float res = ydm_expf_core(x);
     res = (x > 88.7228317f) ? ydm_f32_from_bits(0x7F800000u) : res;        /* largest finite result: x = 0x42B17217 */
     res = (x < -104.0f) ? 0.0f : res;                                      /* e^-104 < 2^-150: rounds to 0 */
+    return (x != x) ? x : res;
+}
+/* the same function for callers that know x <= 0 or NaN (every a-trous weight is exp(-d / phi), d >= 0): one select less;
+ * tools/check_expf.c compares it with ycge_expf on all 2^31 + NaN inputs of that domain */
+YDM_HD float ycge_expf_nonpos(float x) {
+    float res = ydm_expf_core(x);
+    res = (x < -104.0f) ? 0.0f : res;
     return (x != x) ? x : res;
 }
 

@@ -5,10 +5,9 @@
 //   (1) literally: row-major, in place, taps clamped to the image (the reference's loop, RaytraceRenderer.cs:651-719);
 //   (2) the way atrous_wave_kernel does: per pixel 26 records laid out by wavefront_layout.h (old taps as finished terms,
 //       new taps as a history address), bands in ticket order, chains in lock step i = t - L r - cx, every new value
-//       read from the band's 16-entry history rings, the two rows above a band committed from "global memory" by the
-//       halo loader 3 resp. 6 pixels ahead.
-// Steps that wavefront_layout.h calls REGULAR read all filtered taps but slots 9 and 11 ONE STEP EARLY, at fixed offsets
-// (the kernel's pipelined path); the simulator does the same and checks that those offsets equal the recorded addresses.
+//       read from the band's history rings, the two rows above a band committed from "global memory" by the halo warp:
+//       the pixels of "step s" (3 resp. 6 pixels ahead of the band's first row) anywhere between AHEAD steps early and
+//       just in time -- the simulator runs both extremes (last argument: 0 = just in time, 1 = as early as allowed).
 // Every history read is checked against a tag: it must hold exactly the pixel the tap names, written in an EARLIER step,
 // and no entry may be overwritten in a step in which it is read; a halo commit must find its pixel already produced by a
 // band with a lower ticket.  The two results must be bit-identical.  Exit code 0 and "ok" on success.
@@ -29,7 +28,8 @@ static const float KW[5] = {1.f / 16.f, 1.f / 4.f, 3.f / 8.f, 1.f / 4.f, 1.f / 1
 struct Rec { float x, y, z; int32_t code; float w; }; // code >= 0: new tap, history entry; < 0: finished term (x, y, z, w)
 
 int main(int argc, char **argv) {
-    if (argc < 5) { fprintf(stderr, "usage: wf_sim W H y0 y1 [seed]\n"); return 2; }
+    if (argc < 5) { fprintf(stderr, "usage: wf_sim W H y0 y1 [seed] [early]\n"); return 2; }
+    const int early_halo = argc > 6 ? atoi(argv[6]) : 0;
     const int W = atoi(argv[1]), H = atoi(argv[2]), y0 = atoi(argv[3]), y1 = atoi(argv[4]);
     uint32_t seed = argc > 5 ? (uint32_t)atoi(argv[5]) : 1u;
     auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return (float)((seed >> 8) & 0xFFFF) / 65536.0f; };
@@ -104,42 +104,29 @@ int main(int argc, char **argv) {
         if (b >= g.nb[cy]) continue;
         const int yb0 = g.yf[cy] + 2 * YCGE_WF_ROWS * b;
         std::vector<Ent> hist(YCGE_WF_HISTORY_ENTRIES, Ent{Px{0, 0, 0, 0}, -1, -1, -1000000});
-        for (int t = -YCGE_WF_LEAD; t < g.nt; t++) {
+        int halo_next = -YCGE_WF_LEAD;
+        for (int t = -YCGE_WF_LEAD - (early_halo ? YCGE_WF_AHEAD : 0); t < g.nt; t++) {
             std::vector<int> read_set;
             struct Wr { int e; Ent v; };
             std::vector<Wr> writes;
-            // halo loader: rows h = 0, 1 (virtual rows r = -2, -1), both column parities
-            for (int h = 0; h < 2; h++) for (int cxh = 0; cxh < 2; cxh++) {
-                const int hy = wf_halo_row(yb0, h);
-                if (hy >= yb0) continue; // not a halo: the band's own row (top of the image)
-                const int ih = t + YCGE_WF_L * (2 - h) - cxh;
-                if (ih < 0 || ih >= g.ws[cxh]) continue;
-                const int x = 2 * ih + cxh;
-                if (!produced[(size_t)hy * W + x]) { if (violations++ < 10) printf("halo (%d,%d) not produced before warp %d step %d\n", x, hy, warp, t); }
-                writes.push_back(Wr{(h * 2 + cxh) * YCGE_WF_RING + (ih & (YCGE_WF_RING - 1)), Ent{out[(size_t)hy * W + x], x, hy, t}});
+            // halo warp: rows h = 0, 1 (virtual rows r = -2, -1), both column parities; the pixels of step s enter the history
+            // while the band is in step t = s (just in time) or t = s - AHEAD (as early as the kernel allows)
+            const int s_hi = early_halo ? t + YCGE_WF_AHEAD : t;
+            for (; halo_next <= s_hi && halo_next < g.nt; halo_next++) {
+                const int sc = halo_next;
+                for (int h = 0; h < 2; h++) for (int cxh = 0; cxh < 2; cxh++) {
+                    const int hy = wf_halo_row(yb0, h);
+                    if (hy >= yb0) continue; // not a halo: the band's own row (top of the image)
+                    const int ih = sc + YCGE_WF_L * (2 - h) - cxh;
+                    if (ih < 0 || ih >= g.ws[cxh]) continue;
+                    const int x = 2 * ih + cxh;
+                    if (!produced[(size_t)hy * W + x]) { if (violations++ < 10) printf("halo (%d,%d) not produced before warp %d step %d\n", x, hy, warp, t); }
+                    writes.push_back(Wr{(h * 2 + cxh) * YCGE_WF_RING + (ih & (YCGE_WF_RING - 1)), Ent{out[(size_t)hy * W + x], x, hy, t}});
+                }
             }
             for (int c = 0; c < YCGE_WF_CHAINS; c++) {
                 const int r = c >> 1, cx = c & 1, i = t - YCGE_WF_L * r - cx, y = yb0 + 2 * r, x = 2 * i + cx;
-                // the pipelined path evaluates the early slots of the NEXT step's pixel now: check their reads here
-                if (y < y1 && wf_row_regular(g, y) && wf_step_regular(g, t + 1 - YCGE_WF_L * r) && i + 1 >= 0 && i + 1 < g.ws[cx]) {
-                    WfPlace pn; pn.warp = warp; pn.step = t + 1; pn.chain = c; pn.yb0 = yb0;
-                    for (int k = 0; k < 11; k++) {
-                        if (k == 9) continue;
-                        const Rec rc = rec[wf_record_index(g, pn, k)];
-                        const int ky = k / 5 - 2, kx = k % 5 - 2;
-                        const int geo = ((r + ky + 2) * 2 + cx) * YCGE_WF_RING + ((i + 1 + kx) & (YCGE_WF_RING - 1));
-                        const int sx = x + 2 + 2 * kx, sy = y + 2 * ky;
-                        if (sx < 0 || sx >= W || sy < 0) { if (violations++ < 10) printf("regular pixel (%d,%d) has a clamped tap %d\n", x + 2, y, k); continue; }
-                        if (geo != wf_history_entry(yb0, sx, sy)) { if (violations++ < 10) printf("regular pixel (%d,%d) tap %d: fixed offset %d != recorded address %d\n", x + 2, y, k, geo, wf_history_entry(yb0, sx, sy)); }
-                        if (rc.code >= 0 && rc.code != geo) { if (violations++ < 10) printf("regular pixel (%d,%d) tap %d: record address differs\n", x + 2, y, k); }
-                        const Ent &e = hist[geo];
-                        if (e.tag_x != sx || e.tag_y != sy || e.t >= t) { if (violations++ < 10) printf("early read: pixel (%d,%d) tap %d wants (%d,%d) in step %d, history holds (%d,%d) written at %d\n", x + 2, y, k, sx, sy, t, e.tag_x, e.tag_y, e.t); }
-                        read_set.push_back(geo);
-                    }
-                    for (int k = 12; k < 25; k++) if (rec[wf_record_index(g, pn, k)].code >= 0) { if (violations++ < 10) printf("regular pixel (%d,%d): slot %d is a filtered tap\n", x + 2, y, k); }
-                }
                 if (y >= y1 || i < 0 || i >= g.ws[cx]) continue;
-                const bool pipelined = wf_row_regular(g, y) && wf_step_regular(g, t - YCGE_WF_L * r);
                 WfPlace pl; pl.warp = warp; pl.step = t; pl.chain = c; pl.yb0 = yb0;
                 const Rec cen = rec[wf_record_index(g, pl, 25)];
                 float acc[4] = {0, 0, 0, 0};
@@ -151,14 +138,11 @@ int main(int argc, char **argv) {
                         const int sy = clampi(y + 2 * ky, 0, H - 1), sx = clampi(x + 2 * kx, 0, W - 1);
                         if (rc.code >= YCGE_WF_HISTORY_ENTRIES) { printf("history address out of range\n"); return 1; }
                         const Ent &e = hist[rc.code];
-                        const bool early = pipelined && k != 9 && k != 11; // read (and checked) one step ago
-                        if (!early) {
-                            if (e.tag_x != sx || e.tag_y != sy || e.t >= t) {
-                                if (violations++ < 10) printf("pixel (%d,%d) tap %d wants (%d,%d) at step %d, history holds (%d,%d) written at %d\n", x, y, k, sx, sy, t, e.tag_x, e.tag_y, e.t);
-                            }
-                            read_set.push_back(rc.code);
+                        if (e.tag_x != sx || e.tag_y != sy || e.t >= t) {
+                            if (violations++ < 10) printf("pixel (%d,%d) tap %d wants (%d,%d) at step %d, history holds (%d,%d) written at %d\n", x, y, k, sx, sy, t, e.tag_x, e.tag_y, e.t);
                         }
-                        const Px tv = early ? ref[(size_t)sy * W + sx] : e.v; // an early read was validated against the tag when it happened
+                        read_set.push_back(rc.code);
+                        const Px tv = e.v;
                         const float w = KW[kx + 2] * KW[ky + 2] * wfun(fabsf(tv.l - cen.w)) * rc.x;
                         term[0] = tv.r * w; term[1] = tv.g * w; term[2] = tv.b * w; term[3] = w;
                     } else { term[0] = rc.x; term[1] = rc.y; term[2] = rc.z; term[3] = rc.w; }

@@ -15,7 +15,10 @@ r.SetCamera(*pkg.BENCH_POSE)
 for _ in range(3):
     r.TryFlipAndBlit()
 st = r.stats()
-t = np.fromfile(path, dtype=np.uint64).reshape(-1, 2).astype(np.int64)
+full = np.fromfile(path, dtype=np.uint64).reshape(-1, 32).astype(np.int64)
+np.save(os.path.join(ROOT, "gpurun_out", "wave_trace_full.npy"), full)
+t = full[:, :2]
+np.save(os.path.join(ROOT, "gpurun_out", "wave_trace.npy"), t)
 t = t[(t[:, 0] > 0) & (t[:, 1] > 0)]
 t0 = t[:, 0].min()
 W = fb_w * ss

@@ -7,17 +7,19 @@
 //                            yet) becomes its three guide weights plus the ADDRESS of that value in the band's history
 //                            rings.  Clamping at the image border, rows 0 / H-1 (where taps of other kernel rows fold
 //                            onto the pixel's own row) and sky are resolved here, per tap: the wavefront kernel has no
-//                            border cases.
-//   atrous_wave_kernel       one warp per band of 4 rows x 2 chains, 4 lanes per chain (lane = r, g, b, weight); all chains
-//                            of a band advance one pixel per step in lock step (i = t - 3 r - cx), so that everything a
-//                            pixel needs from its own band is in the shared-memory history by construction: no flags, no
-//                            polling, no memory round trip inside a band.  Per step a lane
-//                              1. evaluates the colour weight exp(-|dlum| / cPhi) of 3 of the 12 filtered taps and the product
-//                                 wBase*wc*wn*wz*wa in the reference's order (:699), shuffles them round the quad;
-//                              2. adds its channel's 25 terms in the reference's ky-major / kx order;
-//                              3. normalises, shuffles r, g, b round the quad for the luma, publishes (history + L2).
-//                            The records arrive by cp.async 7 steps ahead; the two rows above the band (another warp's, an
-//                            earlier launch's or a peer GPU's output) are read from L2 two steps ahead of their commit to
+//                            border cases and ONE code path.
+//   atrous_wave_kernel       ONE WARP per band of 4 rows x 2 chains, a quad of lanes per chain; all chains of a band advance
+//                            one pixel per step in lock step (i = t - 3 r - cx), so that everything a pixel needs from its
+//                            own band is in the shared-memory history by construction: no flags, no polling, no memory
+//                            round trip, no block-wide barrier inside a band (only __syncwarp).  Per step
+//                              1. lane q of a quad turns the records of slots 3q .. 3q+2 into terms: for a filtered tap the
+//                                 colour weight exp(-|dlum| / cPhi) from the history and the product wBase*wc*wn*wz*wa in the
+//                                 reference's order (:699); the term replaces the record in shared memory;
+//                              2. every lane of the quad adds the 25 terms of its chain in the reference's ky-major / kx order
+//                                 (packed FADD2), normalises (:706-714), takes the luma;
+//                              3. lane 0 of the quad publishes the pixel: history ring + L2 (+ the peer GPU's buffer).
+//                            The records arrive by cp.async DEPTH - 1 steps ahead; the two rows above the band (another warp's,
+//                            an earlier launch's or a peer GPU's output) are read from L2 two steps ahead of their commit to
 //                            the history and validated against the all-ones sentinel the output buffer is pre-filled with.
 //   Bands take tickets in dispatch order; a band only ever waits for lower tickets, i.e. for warps that are running or
 //   done, so the kernel needs no co-residency guarantee and shares the GPU with other frames' kernels.  Every poll has a
@@ -30,13 +32,9 @@ namespace ycge {
 
 __device__ __forceinline__ float wf_kw(int k) { return k == 0 ? 3.f / 8.f : ((k == 1 || k == -1) ? 1.f / 4.f : 1.f / 16.f); }
 
-// shared-memory history: every entry is stored twice, at e and e + RING, so that the five entries i - 2 .. i + 2 of a row
-// are contiguous from ((i - 2) & 15) without a wrap: the pipelined path reads all filtered taps at immediate offsets from
-// one moving pointer.  A second array of the same shape holds 1.0f: the lane that sums the WEIGHT channel reads its "colour"
-// from there (term.w = 1 * w), with the same addresses as the colour lanes.
-#define YCGE_WF_HROW_BYTES (2 * 2 * YCGE_WF_RING * 16)                          // one history row: 2 chains x 32 entries x 16 B
-#define YCGE_WF_HIST_FLOATS ((YCGE_WF_ROWS + 2) * 2 * 2 * YCGE_WF_RING * 4)
-__host__ __device__ __forceinline__ int wf_history_offset(int entry) { return ((entry >> 4) * (2 * YCGE_WF_RING) + (entry & (YCGE_WF_RING - 1))) * 16; } // logical entry -> byte offset
+// shared-memory history: (ROWS + 2) rows x 2 chains x RING entries of (r, g, b, luma); a record names an entry by its byte offset
+__host__ __device__ __forceinline__ int wf_history_offset(int entry) { return entry * 16; } // logical entry -> byte offset
+#define YCGE_WF_BLOCK (YCGE_WF_SLOTS * YCGE_WF_CHAINS) // float4 records of one (band, step)
 
 struct WavePreArgs {
     const float4 *old_, *gnd, *gas;
@@ -55,7 +53,7 @@ template <bool FAST> __global__ void __launch_bounds__(256) atrous_wave_pre_kern
     const float4 nd0 = __ldg(&a.gnd[pix]);
     const bool sky0 = as0.w != 0.0f; // sky centre: every tap contributes nothing, the wavefront then falls back to c0 (:659)
     const WfPlace pl = wf_place(a.g, x, y);
-    float4 *out = a.rec + wf_record_index(a.g, pl, 0);
+    float4 *out = a.rec + ((size_t)pl.warp * (size_t)a.g.nt + (size_t)pl.step) * YCGE_WF_BLOCK; // the (band, step) block
 #pragma unroll 1
     for (int ky = -2; ky <= 2; ky++) {
         const int sy = clampi(y + ky * 2, 0, H - 1);
@@ -86,10 +84,11 @@ template <bool FAST> __global__ void __launch_bounds__(256) atrous_wave_pre_kern
                     v = make_float4(c.x * wght, c.y * wght, c.z * wght, wght == wght ? wght : __int_as_float(0x7FC00000)); // a finished term: never negative (a NaN keeps the sign clear)
                 }
             }
-            out[(size_t)((ky + 2) * 5 + (kx + 2)) * YCGE_WF_CHAINS] = v;
+            const int slot = (ky + 2) * 5 + (kx + 2);
+            out[slot * YCGE_WF_CHAINS + wf_record_column(slot, pl.chain)] = v;
         }
     }
-    out[(size_t)25 * YCGE_WF_CHAINS] = c0;
+    out[25 * YCGE_WF_CHAINS + wf_record_column(25, pl.chain)] = c0;
 }
 
 struct WaveArgs {
@@ -100,7 +99,7 @@ struct WaveArgs {
     unsigned int *ticket;
     unsigned int ticket_base;
     int *err;          // mapped host memory: set to 1 when a poll gives up
-    unsigned long long *trace; // development aid: globaltimer at the first and the last step of every band, or NULL
+    unsigned long long *trace; // development aid: per band 32 words: globaltimer at the first step, after the last one, at every 64th step; or NULL
     // multi-GPU: rows [peer_y0, peer_y1) are ALSO stored into the output buffer of the rank below (see post.cuh)
     float4 *peer_new;
     int peer_y0, peer_y1;
@@ -108,193 +107,212 @@ struct WaveArgs {
     int frame;
 };
 
-__device__ __forceinline__ float ld_relaxed_f32(const float *p) {
-    float v;
-    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_f32(float *p, float v) { asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-__device__ __forceinline__ void st_relaxed_sys_f32(float *p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 #define YCGE_WF_POLL_LIMIT (1 << 21) // ~1 s of L2 round trips
 
-template <bool FAST, bool PEER> __global__ void __launch_bounds__(YCGE_WF_ROWS * 32) atrous_wave_kernel(WaveArgs a) {
-    __shared__ __align__(16) float4 s_rec[YCGE_WF_DEPTH][YCGE_WF_SLOTS * YCGE_WF_CHAINS];
-    __shared__ __align__(16) float s_hist[2][YCGE_WF_HIST_FLOATS]; // [0]: filtered values (r, g, b, luma); [1]: ones
-    __shared__ int s_ticket;
+
+// one record -> one term (see the header).  R = the record, hv = the history entry it names (anything for a finished term),
+// lum0 = luma of the centre, dc, rc = max(1e-6, cPhi) and its reciprocal
+template <bool FAST> __device__ __forceinline__ float4 wf_term(const float4 R, const float4 hv, const float lum0, const float wB, const float dc, const float rc) {
+    const float wc = ycge_expf_nonpos(neg_div<FAST>(fabsf(hv.w - lum0), dc, rc));
+    const float w = wB * wc * R.x * R.y * R.z; // the reference's product order wBase*wc*wn*wz*wa (:699)
+    float4 t; // opaque select (every lane runs the exp chain: a compiler-made branch around it would split the block)
+    asm("{ .reg .pred p; setp.lt.s32 p, %8, 0; selp.f32 %0, %4, %9, p; selp.f32 %1, %5, %10, p; selp.f32 %2, %6, %11, p; selp.f32 %3, %7, %12, p; }"
+        : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+        : "f"(hv.x * w), "f"(hv.y * w), "f"(hv.z * w), "f"(w), "r"(__float_as_int(R.w)), "f"(R.x), "f"(R.y), "f"(R.z), "f"(R.w));
+    return t;
+}
+#define YCGE_WF_HIST_MASK 0x1FF0 // a record names a history entry by its byte offset: sign bit | offset; a finished term reads any entry
+static_assert(YCGE_WF_HISTORY_ENTRIES * 16 <= YCGE_WF_HIST_MASK + 16, "history must cover every offset the mask lets through");
+
+template <bool V> struct WfTag { static constexpr bool value = V; };
+__device__ __forceinline__ int lds_volatile(const int *p) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory"); return v; }
+__device__ __forceinline__ void sts_volatile(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
+
+// The HALO WARP of a band (warp 1 of its CTA): brings the two rows above the band from L2 into the band's history, in the
+// order and at the addresses the schedule defines (in "step s" the four loaders -- row h above the band x column parity --
+// commit one pixel each), as early as the producer and the history rings allow, and announces in *ready the last step
+// whose pixels are complete.  The band's own warp never touches global memory for them: it only compares *ready with its
+// step counter.  Here: lane = 4 j + loader polls the pixel of step base + j with a STRONG load (a weak one, cp.async
+// included, may be served from a stale copy of the line in the near L2 partition: measured -- once a band had read a
+// line before its producer wrote it, every later request for it returned the sentinel), the longest complete prefix of
+// the eight steps is committed, the window moves on.  All registers are dead at the end of an iteration: no value in
+// flight is ever moved or examined early, so the warp only ever waits for the loads it has just issued.
+__device__ __forceinline__ void wf_halo_warp(const WaveArgs &a, const WfGeom &g, const int yb0, const int lane, float4 *s_hist, int *ready, const int *runner_t, const int nt) {
     const unsigned int FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5, cx = lane >> 4, s = lane & 15, q = s & 3, c = 2 * r + cx;
-    const int hbase = lane & 16; // first lane of this chain's half warp
-    if (tid == 0) s_ticket = (int)(atomicAdd(a.ticket, 1u) - a.ticket_base);
-    for (int k = tid; k < YCGE_WF_HIST_FLOATS; k += YCGE_WF_ROWS * 32) { s_hist[0][k] = 0.0f; s_hist[1][k] = 1.0f; }
+    const int L = lane & 3, j = lane >> 2, lh = L >> 1, lcx = L & 1;
+    const int hy = wf_halo_row(yb0, lh);
+    const bool loader = hy < yb0; // at the top of the image the rows above fold onto the band's own rows: no halo
+    const int tl0 = lcx - YCGE_WF_L * (2 - lh); // loader L commits pixel ih = s - tl0 in step s
+    const unsigned int n_halo = loader ? (unsigned int)g.ws[lcx] : 0u;
+    const float4 *halo_p = a.new_ + (size_t)hy * g.W + lcx; // + 2 ih
+    float4 *halo_hist = s_hist + (lh * 2 + lcx) * YCGE_WF_RING;
+    int base = -YCGE_WF_LEAD, idle = 0;
+    while (base < nt) {
+        // steps the history rings have room for: the band's own warp is in step rt and still reads pixels down to rt - 6
+        const int rt = lds_volatile(runner_t);
+        const int room = min(min(rt + YCGE_WF_AHEAD, nt - 1) - base + 1, 8);
+        const int ih = base + j - tl0;
+        const bool mine = (unsigned int)ih < n_halo && j < room;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (mine) v = ld_relaxed_f4(halo_p + 2 * ih);
+        const bool ok = !mine || f4_valid(v);
+        unsigned int m = __ballot_sync(FULL, ok); // bit 4 j + L
+        m &= m >> 1; m &= m >> 2;                 // bit 4 j: step base + j complete
+        const int n_ok = min(room, (__ffs((int)(~m & 0x11111111u)) - 1) >> 2); // leading complete steps (ffs(0) = 0 -> -1 >> 2 = -1 -> min(...)
+        const int n = (~m & 0x11111111u) ? n_ok : room;
+        if (mine && j < n) halo_hist[ih & (YCGE_WF_RING - 1)] = v;
+        if (n > 0) {
+            __syncwarp();
+            __threadfence_block();
+            base += n;
+            if (lane == 0) sts_volatile(ready, base - 1);
+            idle = 0;
+        } else if (room > 0 && ++idle > YCGE_WF_POLL_LIMIT) { // the producer is gone: fail the frame, let the band run out
+            if (lane == 0) { *(volatile int *)a.err = 1; sts_volatile(ready, nt); }
+            break;
+        }
+    }
+}
+
+template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wave_kernel(WaveArgs a) {
+    __shared__ __align__(128) float4 s_rec[YCGE_WF_DEPTH][YCGE_WF_BLOCK];
+    __shared__ __align__(16) float4 s_hist[(YCGE_WF_HIST_MASK + 16) / 16];
+    __shared__ int s_band, s_ready, s_runner_t;
+    const int lane = threadIdx.x & 31, c = lane >> 2, q = lane & 3, r = c >> 1, cx = c & 1;
+    if (threadIdx.x == 0) { s_band = (int)(atomicAdd(a.ticket, 1u) - a.ticket_base); s_ready = -YCGE_WF_LEAD - 1; s_runner_t = 0; }
+    for (int k = threadIdx.x; k < (YCGE_WF_HIST_MASK + 16) / 16; k += 64) s_hist[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncthreads();
-    const int band = s_ticket;
+    const int band = s_band;
     const WfGeom &g = a.g;
     const int cy = band & 1, b = band >> 1;
     if (band >= g.n_warps || b >= g.nb[cy]) return;
     const int yb0 = g.yf[cy] + 2 * YCGE_WF_ROWS * b;
+    const int nt = g.nt;
+    if (threadIdx.x >= 32) { wf_halo_warp(a, g, yb0, lane, s_hist, &s_ready, &s_runner_t, nt); return; }
     const int y = yb0 + 2 * r;
     const bool row_ok = y < g.y1;
-    const bool row_reg = wf_row_regular(g, y);
-    const int ws_c = g.ws[cx];
-    const bool writer = s < 4; // lanes 0..3 of a half warp = channels r, g, b, weight of the chain
-    // the slot whose colour weight this lane evaluates: 0..11, and on the last row 15, 16, 20, 21 (lanes 12..15)
-    const int my_slot = s < 12 ? s : (s == 12 ? 15 : (s == 13 ? 16 : (s == 14 ? 20 : 21)));
-    const int my_ky = my_slot / 5 - 2, my_kx = my_slot % 5 - 2;
-    const float my_wB = wf_kw(my_kx) * wf_kw(my_ky);
-    const int my_d = (s == 9 || s == 11 || s >= 12) ? 0 : 1; // pipelined path: slots 9 and 11 belong to this step's pixel, the others to the next one
-    const int my_rowoff = ((r + my_ky + 2) * 2 + cx) * (2 * YCGE_WF_RING) * 4 + 3; // float index of the luma of entry 0 of my slot's history row (rows above / own)
-    float *hist_f = s_hist[0];
-    const float *chan_f = (q == 3 ? s_hist[1] : s_hist[0] + q); // where this lane's channel of a history entry lives
-    const int own_row_f = ((r + 2) * 2 + cx) * (2 * YCGE_WF_RING) * 4;
-    const int geo_row_f = (r * 2 + cx) * (2 * YCGE_WF_RING) * 4;    // history row of (y - 4): the pipelined path's window origin
-    float *new_f = reinterpret_cast<float *>(a.new_);
-    float *out_row = new_f + (size_t)y * g.W * 4;
-    float *peer_row = nullptr;
+    const bool last_row_band = yb0 + 2 * (YCGE_WF_ROWS - 1) >= g.H - 1 && g.y1 == g.H; // row H-1 folds the kernel rows below onto itself: slots 15, 16, 20, 21 may be filtered taps
+    const char *hist_b = reinterpret_cast<const char *>(s_hist);
+    // my three slots 3q + j (and, in the last band, a fourth one), their kernel weights and their byte offsets in a block
+    const int s4 = q == 0 ? 15 : (q == 1 ? 16 : (q == 2 ? 20 : 21));
+    float wB[4];
+    int off[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int k = j < 3 ? 3 * q + j : s4;
+        wB[j] = wf_kw(k % 5 - 2) * wf_kw(k / 5 - 2);
+        off[j] = (k * YCGE_WF_CHAINS + wf_record_column(k, c)) * 16;
+    }
+    const int off_c0 = (25 * YCGE_WF_CHAINS + wf_record_column(25, c)) * 16;
+    int col[4]; // byte offset of my chain's column in the slots k with (k / 3) & 3 == m
+#pragma unroll
+    for (int m = 0; m < 4; m++) col[m] = ((c + 2 * m) & (YCGE_WF_CHAINS - 1)) * 16;
+    // publishing lane of the quad: pixel i = t - t0 of the chain while 0 <= i < n_pub
+    const int t0 = YCGE_WF_L * r + cx;
+    const unsigned int n_pub = (q == 0 && row_ok) ? (unsigned int)g.ws[cx] : 0u;
+    float4 *out_p = a.new_ + (size_t)y * g.W + cx; // + 2 i
+    float4 *own_hist = s_hist + ((r + 2) * 2 + cx) * YCGE_WF_RING;
+    float4 *peer_p = out_p;
     if (PEER) {
-        if (a.peer_new && row_ok && y >= a.peer_y0 && y < a.peer_y1) peer_row = reinterpret_cast<float *>(a.peer_new) + (size_t)y * g.W * 4;
-        if (a.peer_new && tid == 0) { // the rank below must have reset its buffer for this frame before anything is stored into it
+        if (a.peer_new && row_ok && y >= a.peer_y0 && y < a.peer_y1) peer_p = a.peer_new + (size_t)y * g.W + cx; // else: this row once more (no branch in the body)
+        if (a.peer_new && lane == 0) { // the rank below must have reset its buffer for this frame before anything is stored into it
             int v, n = 0;
             do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(a.ready) : "memory"); } while (v < a.frame && ++n < YCGE_WF_POLL_LIMIT);
             if (v < a.frame) *(volatile int *)a.err = 1;
         }
+        __syncwarp();
     }
-    // halo loader: warp 0, lanes 0..15 = (row h above the band, column parity, channel)
-    const int lh = (lane >> 3) & 1, lcx = (lane >> 2) & 1;
-    const int hy = wf_halo_row(yb0, lh);
-    const bool loader = r == 0 && lane < 16 && hy < yb0; // at the top of the image the rows above fold onto the band's own rows: no halo
-    const float *halo_row = new_f + (size_t)hy * g.W * 4 + q;
-    const int ws_l = g.ws[lcx];
-    auto halo_ptr = [&](int t) -> const float * { // the word this lane commits in step t, or NULL
-        const int ih = t + YCGE_WF_L * (2 - lh) - lcx;
-        return (loader && ih >= 0 && ih < ws_l) ? halo_row + (size_t)(2 * ih + lcx) * 4 : nullptr;
-    };
-    float pf[YCGE_WF_PF];
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    // record ring: the block of step ts into ring slot ts & (DEPTH - 1); one commit group per call.  Past the last step the
+    // last block is loaded once more (into a slot nobody reads): no branch in the body
+    const float4 *rec_g = a.rec + (size_t)band * (size_t)nt * YCGE_WF_BLOCK + lane;
+    unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(&s_rec[0][0]) + lane * 16; // shared-window address of my 16 bytes of ring slot 0
+    asm volatile("" : "+r"(ring_s)); // keep it in a register (the compiler would otherwise rebuild it from %cluster_ctarank every step)
+    auto fetch = [&](int ts) {
+        const float4 *src = rec_g + (size_t)min(ts, nt - 1) * YCGE_WF_BLOCK;
+        const unsigned int dst = ring_s + (unsigned int)(ts & (YCGE_WF_DEPTH - 1)) * (YCGE_WF_BLOCK * 16);
 #pragma unroll
-    for (int k = 0; k < YCGE_WF_PF; k++) { const float *p = halo_ptr(-YCGE_WF_LEAD + k); pf[k] = p ? ld_relaxed_f32(p) : 0.0f; }
-    const float4 *rec_g = a.rec + (size_t)band * (size_t)g.nt * (YCGE_WF_SLOTS * YCGE_WF_CHAINS);
-    float P = 0.0f, t10 = 0.0f; // pipelined path: ordered partial sum of slots 0..8 and the term of slot 10 of the NEXT pixel
-    bool pipe_valid = false;    // ... valid for the pixel of the coming step
-    const int RS = YCGE_WF_CHAINS * 4;          // floats between consecutive slots of a chain's records
-    const int HR = YCGE_WF_HROW_BYTES / 4;      // floats per history row
-    // normalise (:706-714), luma, publish: shared by both paths
-    auto publish = [&](float acc, const float *rec_t, int i, bool store) {
-        const float wsum = __shfl_sync(FULL, acc, hbase | 3);
-        const float inv = rcp_rn<FAST>(wsum);
-        const float resq = wsum > 1e-8f ? acc * inv : rec_t[25 * RS + q];
-        const float rr = __shfl_sync(FULL, resq, hbase), gg = __shfl_sync(FULL, resq, hbase | 1), bb = __shfl_sync(FULL, resq, hbase | 2);
-        const float outv = q == 3 ? luma3(rr, gg, bb) : resq;
-        if (store && writer) {
-            float *h = hist_f + own_row_f + (i & (YCGE_WF_RING - 1)) * 4 + q;
-            h[0] = outv; h[YCGE_WF_RING * 4] = outv;
-            const size_t xo = (size_t)(2 * i + cx) * 4 + q;
-            st_relaxed_f32(out_row + xo, outv);
-            if (PEER && peer_row) st_relaxed_sys_f32(peer_row + xo, outv);
-        }
+        for (int p = 0; p < YCGE_WF_BLOCK; p += 32)
+            if (p + 32 <= YCGE_WF_BLOCK || p + lane < YCGE_WF_BLOCK) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + p * 16), "l"(src + p) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    __syncthreads();
-
 #pragma unroll 1
-    for (int t = -YCGE_WF_LEAD; t < g.nt; t++) {
-        if (a.trace && tid == 0 && t == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[2 * band] = tm; }
-        // ---- halo commit: the word loaded PF steps ago must be valid by now (else poll), then it enters the history
-        {
-            const float *p = halo_ptr(t);
-            float v = pf[0];
+    for (int ts = 0; ts < YCGE_WF_DEPTH - 1; ts++) fetch(ts);
+    asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 2) : "memory"); // the block of step 0 has landed (mine: the warp barrier covers the other lanes')
+    __syncwarp();
+    const float dc = a.dc, rc = a.rc;
+    // the records of my slots and the centre of the coming step, loaded one step ahead (their block has landed by then)
+    float4 R[4], c0;
+    {
+        const char *blk = reinterpret_cast<const char *>(s_rec[0]);
+        c0 = *reinterpret_cast<const float4 *>(blk + off_c0);
 #pragma unroll
-            for (int k = 0; k + 1 < YCGE_WF_PF; k++) pf[k] = pf[k + 1];
-            const float *pn = halo_ptr(t + YCGE_WF_PF);
-            pf[YCGE_WF_PF - 1] = pn ? ld_relaxed_f32(pn) : 0.0f;
-            bool ok = !p || __float_as_uint(v) != YCGE_SENTINEL;
-            if (!__all_sync(FULL, ok)) {
-                int n = 0;
-                while (!ok && ++n < YCGE_WF_POLL_LIMIT) { v = ld_relaxed_f32(p); ok = __float_as_uint(v) != YCGE_SENTINEL; }
-                if (!ok) *(volatile int *)a.err = 1;
-                __syncwarp();
-            }
-            if (p) {
-                const int ih = t + YCGE_WF_L * (2 - lh) - lcx;
-                float *h = hist_f + ((lh * 2 + lcx) * (2 * YCGE_WF_RING) + (ih & (YCGE_WF_RING - 1))) * 4 + q;
-                h[0] = v; h[YCGE_WF_RING * 4] = v;
-            }
-        }
-        const int i0 = t - YCGE_WF_L * r, i = i0 - cx;
-        const bool active = row_ok && i >= 0 && i < ws_c;
-        const bool reg_next = row_reg && wf_step_regular(g, i0 + 1);
-        const bool lean = pipe_valid; // this step's pixels were prepared in the step before
-        const float *rec_t = reinterpret_cast<const float *>(s_rec[t & (YCGE_WF_DEPTH - 1)]) + c * 4;        // this step's records of my chain
-        if (lean || reg_next) {
-            // ---- pipelined path, ONE basic block so that its three dependency chains interleave:
-            // (1) one colour weight per lane.  Lanes 9 and 11: this step's pixel (values of the step before); the other lanes:
-            //     the NEXT step's pixel, whose filtered taps but 9 and 11 are in the history already;
-            // (2) this step's pixel: the partial sum prepared one step ago + slots 9, 10, 11 + the 13 unfiltered taps, publish;
-            // (3) the next step's pixel: ordered partial sum of slots 0..8, term of slot 10.
-            const float *rec_n = reinterpret_cast<const float *>(s_rec[(t + 1) & (YCGE_WF_DEPTH - 1)]) + c * 4;
-            const float *rec_m = my_d ? rec_n : rec_t;
-            const float4 R = *reinterpret_cast<const float4 *>(rec_m + my_slot * RS);
-            const float c0w = rec_m[25 * RS + 3];
-            const float lt = hist_f[my_rowoff + ((i + my_d + my_kx) & (YCGE_WF_RING - 1)) * 4];
-            const float wc = exp_nonpos(neg_div<FAST>(fabsf(lt - c0w), a.dc, a.rc));
-            const float Wm = my_wB * wc * R.x * R.y * R.z; // the reference's product order wBase*wc*wn*wz*wa (:699)
-            // the next pixel may take this path if none of its 12 filtered taps is skipped (sky edge): all their records are "filtered tap"
-            const bool clean = __float_as_int(rec_n[my_slot * RS + 3]) < 0;
-            const bool next_valid = reg_next && __all_sync(FULL, clean || s >= 12);
-            const float *win = chan_f + geo_row_f + ((i - 2) & (YCGE_WF_RING - 1)) * 4; // entry (i - 2) of the row two above; slot k at + (ky + 2) rows + (kx + 2) entries
-            const float *wnx = chan_f + geo_row_f + ((i - 1) & (YCGE_WF_RING - 1)) * 4; // the same for the next pixel
-            float acc = P;
-            acc = acc + win[HR * 1 + 4 * 4] * __shfl_sync(FULL, Wm, hbase | 9);
-            acc = acc + t10;
-            acc = acc + win[HR * 2 + 1 * 4] * __shfl_sync(FULL, Wm, hbase | 11);
-#pragma unroll
-            for (int k = 12; k < 25; k++) acc = acc + rec_t[k * RS + q];
-            publish(acc, rec_t, i, lean);
-            float p = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 9; k++) p = p + wnx[HR * (k / 5) + (k % 5) * 4] * __shfl_sync(FULL, Wm, hbase | k);
-            P = p;
-            t10 = wnx[HR * 2] * __shfl_sync(FULL, Wm, hbase | 10);
-            pipe_valid = next_valid;
-        } else pipe_valid = false;
-        if (!lean && __any_sync(FULL, active)) {
-            // ---- generic path (image border columns, rows 0..3 and H-1, sky edges): every filtered tap at the address the
-            // pre-pass recorded, everything of this step's pixel evaluated now
-            const float c0w = rec_t[25 * RS + 3];
-            const float4 R = *reinterpret_cast<const float4 *>(rec_t + my_slot * RS);
-            const int code = __float_as_int(R.w);
-            const float lt = hist_f[min(code & 0x3FF0, YCGE_WF_HIST_FLOATS * 4 - 16) / 4 + 3];
-            const float wc = exp_nonpos(neg_div<FAST>(fabsf(lt - c0w), a.dc, a.rc));
-            const float Wm = my_wB * wc * R.x * R.y * R.z;
-            float acc = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 25; k++) {
-                const int src_lane = k < 12 ? k : (k == 15 ? 12 : (k == 16 ? 13 : (k == 20 ? 14 : 15)));
-                const bool may_be_new = k < 12 || k == 15 || k == 16 || k == 20 || k == 21;
-                const float *rk = rec_t + k * RS;
-                if (may_be_new) {
-                    const float Wk = __shfl_sync(FULL, Wm, hbase | src_lane);
-                    const int ck = __float_as_int(rk[3]);
-                    const bool is_new = ck < 0;
-                    const float v = is_new ? chan_f[min(ck & 0x3FF0, YCGE_WF_HIST_FLOATS * 4 - 16) / 4] : rk[q];
-                    acc = acc + (is_new ? v * Wk : v);
-                } else acc = acc + rk[q];
-            }
-            publish(acc, rec_t, i, active);
-        }
-        // ---- records of step t + DEPTH - 1 into the ring slot step t - 1 has left; the groups of steps t + 1 and t + 2 must have landed
-        {
-            const int ts = min(max(t + YCGE_WF_DEPTH - 1, 0), g.nt - 1); // out of range: a harmless reload
-            const float4 *src = rec_g + (size_t)ts * (YCGE_WF_SLOTS * YCGE_WF_CHAINS);
-            float4 *dst = s_rec[(t + YCGE_WF_DEPTH - 1) & (YCGE_WF_DEPTH - 1)];
-#pragma unroll
-            for (int p = tid; p < YCGE_WF_SLOTS * YCGE_WF_CHAINS; p += YCGE_WF_ROWS * 32) cp_async16(dst + p, src + p);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 3) : "memory");
-        }
-        __syncthreads();
+        for (int j = 0; j < 4; j++) R[j] = *reinterpret_cast<const float4 *>(blk + off[j]);
     }
-    if (a.trace && tid == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[2 * band + 1] = tm; }
+    int rdy = lds_volatile(&s_ready); // what the halo warp had announced a step ago: enough in the steady state, re-read otherwise
+    bool traced = false;
+
+    auto run = [&](auto last_tag) { // two copies of the loop: the band that holds row H-1 evaluates a fourth slot per lane
+    constexpr bool LASTROW = decltype(last_tag)::value;
+#pragma unroll 1
+    for (int t = 0; t < nt; t++) {
+        // step t reads the halo pixels committed in the steps up to t - 1
+        if (rdy < t - 1) {
+            int n = 0;
+            do { rdy = lds_volatile(&s_ready); } while (rdy < t - 1 && ++n < (1 << 30));
+        }
+        if (a.trace && lane == 0) { // development aid
+            if (!traced) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band] = tm; traced = true; }
+            if ((t & 63) == 63 && (t >> 6) < 30) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 2 + (t >> 6)] = tm; }
+        }
+        if (lane == 0) sts_volatile(&s_runner_t, t);
+        fetch(t + YCGE_WF_DEPTH - 1); // into the ring slot step t - 1 has left
+        char *blk = reinterpret_cast<char *>(s_rec[t & (YCGE_WF_DEPTH - 1)]);
+        // ---- 1. my slots: record -> term, in place: three independent dependency chains
+        float4 hv[4];
+#pragma unroll
+        for (int j = 0; j < 3; j++) hv[j] = *reinterpret_cast<const float4 *>(hist_b + (__float_as_int(R[j].w) & YCGE_WF_HIST_MASK));
+#pragma unroll
+        for (int j = 0; j < 3; j++) R[j] = wf_term<FAST>(R[j], hv[j], c0.w, wB[j], dc, rc);
+#pragma unroll
+        for (int j = 0; j < 3; j++) *reinterpret_cast<float4 *>(blk + off[j]) = R[j];
+        if (LASTROW) {
+            hv[3] = *reinterpret_cast<const float4 *>(hist_b + (__float_as_int(R[3].w) & YCGE_WF_HIST_MASK));
+            *reinterpret_cast<float4 *>(blk + off[3]) = wf_term<FAST>(R[3], hv[3], c0.w, wB[3], dc, rc);
+        }
+        __syncwarp();
+        rdy = lds_volatile(&s_ready);
+        // ---- 2. the 25 terms in the reference's order, normalise (:706-714), luma
+        float4 acc = zero4;
+#pragma unroll
+        for (int k = 0; k < 25; k++) acc = add4_rn(acc, *reinterpret_cast<const float4 *>(blk + k * (YCGE_WF_CHAINS * 16) + col[(k / 3) & 3]));
+        const float inv = rcp_rn<FAST>(acc.w);
+        const bool okw = acc.w > 1e-8f;
+        const float rr = okw ? acc.x * inv : c0.x, gg = okw ? acc.y * inv : c0.y, bb = okw ? acc.z * inv : c0.z;
+        const float4 res = make_float4(rr, gg, bb, luma3(rr, gg, bb));
+        // ---- 3. publish
+        const int i = t - t0;
+        if ((unsigned int)i < n_pub) {
+            own_hist[i & (YCGE_WF_RING - 1)] = res;
+            st_relaxed_f4(out_p + 2 * i, res);
+            if (PEER) st_relaxed_sys_f4(peer_p + 2 * i, res);
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 2) : "memory"); // the block of step t + 1 has landed
+        __syncwarp();
+        {
+            const char *nblk = reinterpret_cast<const char *>(s_rec[(t + 1) & (YCGE_WF_DEPTH - 1)]);
+            c0 = *reinterpret_cast<const float4 *>(nblk + off_c0);
+#pragma unroll
+            for (int j = 0; j < (LASTROW ? 4 : 3); j++) R[j] = *reinterpret_cast<const float4 *>(nblk + off[j]);
+        }
+    }
+    };
+    if (last_row_band) run(WfTag<true>{}); else run(WfTag<false>{});
+    if (lane == 0) sts_volatile(&s_runner_t, nt + YCGE_WF_AHEAD); // lets the halo warp run out
+    if (a.trace && lane == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 1] = tm; }
 }
 
 } // namespace ycge

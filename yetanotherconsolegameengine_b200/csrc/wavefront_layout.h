@@ -8,7 +8,8 @@
 // y +- 2, 4 (then clamped to the image): a pixel row holds two independent CHAINS (x even / x odd), rows of equal parity
 // depend on each other, and a chain may run L = 3 pixels behind the chain above it ((x + 4, y - 2) must be done).
 //
-// One WARP owns a BAND: 4 rows of one row parity x 2 chains = 8 chains, 4 lanes per chain (lane = colour channel).  All
+// One WARP owns a BAND: 4 rows of one row parity x 2 chains = 8 chains, 4 lanes per chain (a QUAD; lane q evaluates the
+// taps 3q .. 3q+2, every lane of the quad then adds the 25 terms in the reference's order).  All
 // chains of a band advance in LOCK STEP, one pixel per step: chain (row r, column parity cx) is at pixel index
 //     i = t - L * r - cx                      (x = 2 i + cx)
 // in step t.  With that schedule every filtered value a pixel needs from its own band — the two rows above, the pixels to
@@ -27,10 +28,10 @@
 #define YCGE_WF_ROWS 4     // rows per band
 #define YCGE_WF_CHAINS 8   // chains per band
 #define YCGE_WF_SLOTS 26   // records per pixel: 25 taps + the centre
-#define YCGE_WF_RING 16    // history entries per chain (the oldest value a pixel reads is 2 L + 3 = 9 steps old)
-#define YCGE_WF_DEPTH 8    // steps of records in flight in shared memory
-#define YCGE_WF_LEAD 8     // steps the loop starts before step 0 (halo prefetch, record ring), >= DEPTH - 1 and >= 2 L + PF
-#define YCGE_WF_PF 2       // steps between the issue of a halo load and its commit to the history
+#define YCGE_WF_RING 32    // history entries per chain: a band reads values up to 2 L + 3 = 9 steps old, and the rows above it are brought in up to AHEAD steps early
+#define YCGE_WF_AHEAD 16   // steps the halo warp may run ahead of its band
+#define YCGE_WF_DEPTH 8    // steps of records in flight in shared memory (a power of two)
+#define YCGE_WF_LEAD 6     // steps the halo warp starts before step 0, >= 2 L
 
 struct WfGeom {
     int W, H, y0, y1; // the pass covers pixel rows [y0, y1) of a W x H image
@@ -70,8 +71,13 @@ YWF_HD WfPlace wf_place(const WfGeom &g, int x, int y) {
     p.yb0 = g.yf[cy] + 2 * YCGE_WF_ROWS * b;
     return p;
 }
+// The 26 x 8 records of one (band, step) are contiguous (3 328 bytes) and travel to shared memory verbatim (cp.async), so
+// the position inside the block is chosen for the shared-memory banks: the four lanes of a quad read the slots 3q + j of
+// their chain at the same time, which a plain [slot][chain] layout would put on the same banks; rotating the chain
+// index by 2 * (slot / 3) gives the eight lanes of a quarter warp eight different 16-byte columns.
+YWF_HD int wf_record_column(int slot, int chain) { return (chain + 2 * (slot / 3)) & (YCGE_WF_CHAINS - 1); }
 YWF_HD size_t wf_record_index(const WfGeom &g, const WfPlace &p, int slot) {
-    return (((size_t)p.warp * (size_t)g.nt + (size_t)p.step) * YCGE_WF_SLOTS + (size_t)slot) * YCGE_WF_CHAINS + (size_t)p.chain;
+    return (((size_t)p.warp * (size_t)g.nt + (size_t)p.step) * YCGE_WF_SLOTS + (size_t)slot) * YCGE_WF_CHAINS + (size_t)wf_record_column(slot, p.chain);
 }
 // the two rows above a band that another warp (or an earlier launch, or a peer GPU) produces; needed iff < yb0
 YWF_HD int wf_halo_row(int yb0, int h) { const int y = yb0 - 4 + 2 * h; return y < 0 ? 0 : y; }
@@ -81,12 +87,3 @@ YWF_HD int wf_history_entry(int yb0, int sx, int sy) {
     return (hrow * 2 + (sx & 1)) * YCGE_WF_RING + ((sx >> 1) & (YCGE_WF_RING - 1));
 }
 #define YCGE_WF_HISTORY_ENTRIES ((YCGE_WF_ROWS + 2) * 2 * YCGE_WF_RING)
-
-// REGULAR steps.  A row's two chains (cx = 0 at pixel i0 = t - L r, cx = 1 at i0 - 1) take the pipelined path in step t when
-// none of their taps is clamped and their rows above are the two rows above in the history: then the 12 filtered taps sit
-// at FIXED offsets from the pixel ((hrow r + ky + 2, entry i + kx), no lookup), and only slots 9 ((i + 2, row above)) and
-// 11 ((i - 1, own row)) were produced in the step before -- every other filtered tap is at least two steps old, so its
-// weight and the ordered partial sum of slots 0..8 are evaluated ONE STEP AHEAD, off the critical path.  Everything else
-// (image border columns, rows 0..3 and H-1) takes the generic path, which reads the addresses the pre-pass recorded.
-YWF_HD bool wf_row_regular(const WfGeom &g, int y) { return y >= 4 && y != g.H - 1 && y < g.y1; }
-YWF_HD bool wf_step_regular(const WfGeom &g, int i0) { return i0 >= 3 && i0 <= g.ws[0] - 3 && i0 - 1 <= g.ws[1] - 3; }

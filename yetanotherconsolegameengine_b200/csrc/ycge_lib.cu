@@ -648,7 +648,7 @@ int denoise_run(ycge_ctx *c) {
                     if (sa_ > slo) { wa.peer_new = (Y == 2) ? c->below_sb : c->below_sa; wa.peer_y0 = slo; wa.peer_y1 = sa_; }
                 }
                 if (getenv("YCGE_CHAIN_TRACE")) { // development aid: first / last step of every band, dumped by ycge_get_stats
-                    if (c->chain_trace.n < (size_t)2 * wa.g.n_warps) CK(c, c->chain_trace.alloc((size_t)2 * wa.g.n_warps));
+                    if (c->chain_trace.n < (size_t)32 * wa.g.n_warps) CK(c, c->chain_trace.alloc((size_t)32 * wa.g.n_warps));
                     CK(c, cudaMemsetAsync(c->chain_trace.p, 0, c->chain_trace.n * 8, s));
                     wa.trace = c->chain_trace.p;
                 }
@@ -656,7 +656,7 @@ int denoise_run(ycge_ctx *c) {
                 c->ticket_advance(0, ticket_slot, (unsigned int)wa.g.n_warps); // one ticket per CTA
                 CK(c, cudaEventRecord(c->ev[7], s));
                 if (wa.g.n_warps > 0) {
-                    const dim3 gr(wa.g.n_warps), th(YCGE_WF_ROWS * 32); // one CTA per band, one warp per row
+                    const dim3 gr(wa.g.n_warps), th(64); // one CTA per band: the band's warp and its halo warp
                     if (fast && wa.peer_new) atrous_wave_kernel<true, true><<<gr, th, 0, s>>>(wa);
                     else if (fast) atrous_wave_kernel<true, false><<<gr, th, 0, s>>>(wa);
                     else if (wa.peer_new) atrous_wave_kernel<false, true><<<gr, th, 0, s>>>(wa);
