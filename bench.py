@@ -558,7 +558,7 @@ def main():
     if stage_ms["ms_trace"] >= stage_ms["ms_atrous_chain"]:
         kname, kbytes, kms = "trace_kernel", b_trace * rows_here // H, stage_ms["ms_trace"]
     else:
-        kname, kbytes, kms = "atrous_chain_static_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
+        kname, kbytes, kms = "atrous_wave_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
     achieved = kbytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
     # DRAM traffic of that kernel per launch: only from an `ncu --set full` capture of THIS build of the library and this
     # command (tools/summarize_ncu.py records the sha256 of libycge.so beside dram__bytes_read.sum + dram__bytes_write.sum);

@@ -270,8 +270,9 @@ YCGE_API int ycge_reset_history(ycge_ctx *ctx);                                 
  * lane carries one ray per round through a single traversal; a warp takes its next 8x4 pixel tile when all of its lanes
  * are done -- refilling single lanes was measured slower, see csrc/trace_stream.cuh). */
 YCGE_API int ycge_set_trace_variant(ycge_ctx *ctx, int32_t variant);
-/* Two forms of the in-place a-trous iteration (RaytraceRenderer.cs:718) with bit-identical results: 0 (default) = one warp
- * per chain, rows handed over through L2 (csrc/post.cuh); 1 = systolic bands in lock step (csrc/wavefront.cuh). */
+/* Two forms of the in-place a-trous iteration (RaytraceRenderer.cs:718) with bit-identical results: 0 = one warp per chain,
+ * rows handed over through L2 (csrc/post.cuh); 1 (default) = systolic bands: one warp per 4 rows in lock step plus a halo
+ * warp that brings the rows above (csrc/wavefront.cuh). */
 YCGE_API int ycge_set_inplace_variant(ycge_ctx *ctx, int32_t variant);
 /* TryFlipAndBlit (RaytraceRenderer.cs:157-267): synchronous; writes tile_rows*fb_w cells (the ctx's tile;
  * the whole frame when unsharded) into caller-owned host memory, row stride `stride_cells` (0 => fb_w). */

@@ -91,14 +91,15 @@ def test_gpu_matches_golden(case):
 
 
 @pytest.mark.parametrize("case", make_golden.CASES, ids=[c[0] for c in make_golden.CASES])
-def test_systolic_in_place_pass_matches_golden(case):
-    """The other form of the in-place a-trous iteration (ycge_set_inplace_variant(1): bands of 4 rows in lock step, csrc/wavefront.cuh;
-    its schedule is replayed on the CPU by tests/test_wavefront_layout.py) against the same golden vectors."""
+def test_warp_per_chain_in_place_pass_matches_golden(case):
+    """The other form of the in-place a-trous iteration (ycge_set_inplace_variant(0): one warp per chain, csrc/post.cuh; the
+    default is 1: bands of 4 rows in lock step, csrc/wavefront.cuh, whose schedule is replayed on the CPU by
+    tests/test_wavefront_layout.py) against the same golden vectors."""
     name, scene, fb_w, fb_h, ss, frames, pose = case
     gold = np.load(os.path.join(GOLDEN, f"oracle_{name}.npz"))
     s = api.HostScene(scene)
     r = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
-    r.set_inplace_variant(1)
+    r.set_inplace_variant(0)
     if pose is not None:
         r.SetCamera(*pose)
     for f in range(1, frames + 1):
@@ -109,12 +110,12 @@ def test_systolic_in_place_pass_matches_golden(case):
     s.close()
 
 
-def test_systolic_in_place_pass_full_size_equals_the_default_form():
+def test_both_forms_of_the_in_place_pass_agree_at_full_size():
     """1920x1080 (dragon stand-in, bench pose) and an odd-sized frame: both forms of the in-place pass, every denoised bit."""
     for scene, fb_w, fb_h, ss, pose in (("dragon", 480, 135, 4, api.BENCH_POSE), ("bunny", 61, 23, 3, api.BENCH_POSE)):
         s = api.HostScene(scene)
         a, b = api.CudaRaytraceRenderer(s, fb_w, fb_h, ss), api.CudaRaytraceRenderer(s, fb_w, fb_h, ss)
-        b.set_inplace_variant(1)
+        a.set_inplace_variant(1); b.set_inplace_variant(0)
         for r in (a, b):
             r.SetCamera(*pose)
         for f in range(2):

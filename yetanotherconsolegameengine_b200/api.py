@@ -503,7 +503,7 @@ class CudaRaytraceRenderer:
         self._ck(self._lib.ycge_set_trace_variant(self.ctx, variant))
 
     def set_inplace_variant(self, variant: int):
-        """0 (default): one warp per chain of the in-place a-trous iteration; 1: systolic bands (wavefront.cuh).  Bit-identical."""
+        """0: one warp per chain of the in-place a-trous iteration (post.cuh); 1 (default): systolic bands (wavefront.cuh).  Bit-identical."""
         self._ck(self._lib.ycge_set_inplace_variant(self.ctx, variant))
 
     def lights_update(self, lights):

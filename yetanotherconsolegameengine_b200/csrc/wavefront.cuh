@@ -128,8 +128,10 @@ template <bool FAST> __device__ __forceinline__ float4 wf_term(const float4 R, c
 static_assert(YCGE_WF_HISTORY_ENTRIES * 16 <= YCGE_WF_HIST_MASK + 16, "history must cover every offset the mask lets through");
 
 template <bool V> struct WfTag { static constexpr bool value = V; };
-__device__ __forceinline__ int lds_volatile(const int *p) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory"); return v; }
-__device__ __forceinline__ void sts_volatile(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
+// volatile shared-memory words by shared-window address (kept in a register by the caller: see keep_reg)
+__device__ __forceinline__ int lds_volatile(unsigned int sa) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa) : "memory"); return v; }
+__device__ __forceinline__ void sts_volatile(unsigned int sa, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(sa), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int keep_reg(unsigned int v) { asm volatile("" : "+r"(v)); return v; } // the compiler would otherwise rebuild a shared-window address from %cluster_ctarank at every use
 
 // The HALO WARP of a band (warp 1 of its CTA): brings the two rows above the band from L2 into the band's history, in the
 // order and at the addresses the schedule defines (in "step s" the four loaders -- row h above the band x column parity --
@@ -138,9 +140,12 @@ __device__ __forceinline__ void sts_volatile(int *p, int v) { asm volatile("st.v
 // step counter.  Here: lane = 4 j + loader polls the pixel of step base + j with a STRONG load (a weak one, cp.async
 // included, may be served from a stale copy of the line in the near L2 partition: measured -- once a band had read a
 // line before its producer wrote it, every later request for it returned the sentinel), the longest complete prefix of
-// the eight steps is committed, the window moves on.  All registers are dead at the end of an iteration: no value in
-// flight is ever moved or examined early, so the warp only ever waits for the loads it has just issued.
-__device__ __forceinline__ void wf_halo_warp(const WaveArgs &a, const WfGeom &g, const int yb0, const int lane, float4 *s_hist, int *ready, const int *runner_t, const int nt) {
+// the eight steps is committed, the window moves on.  YCGE_WF_POLLS such windows are in flight, each in its own
+// registers (the loop is unrolled over them), re-issued as soon as they are examined: a pixel is seen a quarter of an L2
+// round trip after it became visible, on average, and no instruction ever touches a value that is still in flight except
+// the one that has waited longest.
+#define YCGE_WF_POLLS 4
+__device__ __forceinline__ void wf_halo_warp(const WaveArgs &a, const WfGeom &g, const int yb0, const int lane, float4 *s_hist, const unsigned int ready, const unsigned int runner_t, const int nt, const int trace_band) {
     const unsigned int FULL = 0xffffffffu;
     const int L = lane & 3, j = lane >> 2, lh = L >> 1, lcx = L & 1;
     const int hy = wf_halo_row(yb0, lh);
@@ -150,29 +155,52 @@ __device__ __forceinline__ void wf_halo_warp(const WaveArgs &a, const WfGeom &g,
     const float4 *halo_p = a.new_ + (size_t)hy * g.W + lcx; // + 2 ih
     float4 *halo_hist = s_hist + (lh * 2 + lcx) * YCGE_WF_RING;
     int base = -YCGE_WF_LEAD, idle = 0;
-    while (base < nt) {
-        // steps the history rings have room for: the band's own warp is in step rt and still reads pixels down to rt - 6
-        const int rt = lds_volatile(runner_t);
-        const int room = min(min(rt + YCGE_WF_AHEAD, nt - 1) - base + 1, 8);
+    float4 v[YCGE_WF_POLLS];
+    int bs[YCGE_WF_POLLS];
+    auto issue = [&](float4 &vv, int &b0) {
+        b0 = base;
         const int ih = base + j - tl0;
-        const bool mine = (unsigned int)ih < n_halo && j < room;
-        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (mine) v = ld_relaxed_f4(halo_p + 2 * ih);
-        const bool ok = !mine || f4_valid(v);
-        unsigned int m = __ballot_sync(FULL, ok); // bit 4 j + L
-        m &= m >> 1; m &= m >> 2;                 // bit 4 j: step base + j complete
-        const int n_ok = min(room, (__ffs((int)(~m & 0x11111111u)) - 1) >> 2); // leading complete steps (ffs(0) = 0 -> -1 >> 2 = -1 -> min(...)
-        const int n = (~m & 0x11111111u) ? n_ok : room;
-        if (mine && j < n) halo_hist[ih & (YCGE_WF_RING - 1)] = v;
-        if (n > 0) {
-            __syncwarp();
-            __threadfence_block();
-            base += n;
-            if (lane == 0) sts_volatile(ready, base - 1);
-            idle = 0;
-        } else if (room > 0 && ++idle > YCGE_WF_POLL_LIMIT) { // the producer is gone: fail the frame, let the band run out
-            if (lane == 0) { *(volatile int *)a.err = 1; sts_volatile(ready, nt); }
-            break;
+        vv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if ((unsigned int)ih < n_halo) vv = ld_relaxed_f4(halo_p + 2 * ih);
+    };
+#pragma unroll
+    for (int k = 0; k < YCGE_WF_POLLS; k++) issue(v[k], bs[k]);
+    for (;;) {
+#pragma unroll
+        for (int k = 0; k < YCGE_WF_POLLS; k++) {
+            // the window issued longest ago: lane (j, L) holds the pixel loader L commits in step bs + j
+            const int s = bs[k] + j, ih = s - tl0;
+            const bool mine = (unsigned int)ih < n_halo;
+            const bool ok = !mine || f4_valid(v[k]);
+            unsigned int m = __ballot_sync(FULL, ok); // bit 4 j + L
+            m &= m >> 1; m &= m >> 2;                 // bit 4 j: step bs + j complete
+            const int shift = base - bs[k];           // steps of this window that are committed already
+            // steps the history rings have room for: the band's own warp is in step rt and still reads pixels down to rt - 6
+            const int rt = lds_volatile(runner_t);
+            const int room = min(min(rt + YCGE_WF_AHEAD, nt - 1) - base + 1, 8 - shift);
+            int n = 0;
+            if (shift < 8) {
+                const unsigned int miss = (~m & 0x11111111u) >> (4 * shift); // bit 4 i: step base + i incomplete
+                n = miss ? (__ffs((int)miss) - 1) >> 2 : 8;
+                n = min(n, room);
+            }
+            if (mine && s >= base && s < base + n) halo_hist[ih & (YCGE_WF_RING - 1)] = v[k];
+            if (n > 0) {
+                __syncwarp();
+                __threadfence_block();
+#ifdef YCGE_WF_TRACE
+                if (a.trace && lane == 0 && base <= 500 && base + n > 500) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * trace_band + 21] = tm; } // development aid
+#endif
+                base += n;
+                if (lane == 0) sts_volatile(ready, base - 1);
+                idle = 0;
+                if (base >= nt) return;
+            } else if (room <= 0) __nanosleep(100); // the band's own warp has to move first
+            else if (shift < 8 && ++idle > YCGE_WF_POLL_LIMIT) { // the producer is gone: fail the frame, let the band run out
+                if (lane == 0) { *(volatile int *)a.err = 1; sts_volatile(ready, nt); }
+                return;
+            }
+            issue(v[k], bs[k]);
         }
     }
 }
@@ -191,7 +219,8 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
     if (band >= g.n_warps || b >= g.nb[cy]) return;
     const int yb0 = g.yf[cy] + 2 * YCGE_WF_ROWS * b;
     const int nt = g.nt;
-    if (threadIdx.x >= 32) { wf_halo_warp(a, g, yb0, lane, s_hist, &s_ready, &s_runner_t, nt); return; }
+    const unsigned int ready_s = keep_reg((unsigned int)__cvta_generic_to_shared(&s_ready)), runner_s = keep_reg((unsigned int)__cvta_generic_to_shared(&s_runner_t));
+    if (threadIdx.x >= 32) { wf_halo_warp(a, g, yb0, lane, s_hist, ready_s, runner_s, nt, band); return; }
     const int y = yb0 + 2 * r;
     const bool row_ok = y < g.y1;
     const bool last_row_band = yb0 + 2 * (YCGE_WF_ROWS - 1) >= g.H - 1 && g.y1 == g.H; // row H-1 folds the kernel rows below onto itself: slots 15, 16, 20, 21 may be filtered taps
@@ -229,8 +258,7 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
     // record ring: the block of step ts into ring slot ts & (DEPTH - 1); one commit group per call.  Past the last step the
     // last block is loaded once more (into a slot nobody reads): no branch in the body
     const float4 *rec_g = a.rec + (size_t)band * (size_t)nt * YCGE_WF_BLOCK + lane;
-    unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(&s_rec[0][0]) + lane * 16; // shared-window address of my 16 bytes of ring slot 0
-    asm volatile("" : "+r"(ring_s)); // keep it in a register (the compiler would otherwise rebuild it from %cluster_ctarank every step)
+    const unsigned int ring_s = keep_reg((unsigned int)__cvta_generic_to_shared(&s_rec[0][0]) + lane * 16); // shared-window address of my 16 bytes of ring slot 0
     auto fetch = [&](int ts) {
         const float4 *src = rec_g + (size_t)min(ts, nt - 1) * YCGE_WF_BLOCK;
         const unsigned int dst = ring_s + (unsigned int)(ts & (YCGE_WF_DEPTH - 1)) * (YCGE_WF_BLOCK * 16);
@@ -241,7 +269,7 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
     };
 #pragma unroll 1
     for (int ts = 0; ts < YCGE_WF_DEPTH - 1; ts++) fetch(ts);
-    asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 2) : "memory"); // the block of step 0 has landed (mine: the warp barrier covers the other lanes')
+    asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 3) : "memory"); // the blocks of steps 0 and 1 have landed (mine: the warp barrier covers the other lanes')
     __syncwarp();
     const float dc = a.dc, rc = a.rc;
     // the records of my slots and the centre of the coming step, loaded one step ahead (their block has landed by then)
@@ -252,23 +280,21 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
 #pragma unroll
         for (int j = 0; j < 4; j++) R[j] = *reinterpret_cast<const float4 *>(blk + off[j]);
     }
-    int rdy = lds_volatile(&s_ready); // what the halo warp had announced a step ago: enough in the steady state, re-read otherwise
-    bool traced = false;
+    int rdy = lds_volatile(ready_s); // what the halo warp had announced a step ago: enough in the steady state, re-read otherwise
+    if (a.trace && lane == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band] = tm; }
 
     auto run = [&](auto last_tag) { // two copies of the loop: the band that holds row H-1 evaluates a fourth slot per lane
     constexpr bool LASTROW = decltype(last_tag)::value;
 #pragma unroll 1
-    for (int t = 0; t < nt; t++) {
-        // step t reads the halo pixels committed in the steps up to t - 1
-        if (rdy < t - 1) {
-            int n = 0;
-            do { rdy = lds_volatile(&s_ready); } while (rdy < t - 1 && ++n < (1 << 30));
-        }
-        if (a.trace && lane == 0) { // development aid
-            if (!traced) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band] = tm; traced = true; }
-            if ((t & 63) == 63 && (t >> 6) < 30) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 2 + (t >> 6)] = tm; }
-        }
-        if (lane == 0) sts_volatile(&s_runner_t, t);
+    for (int t = 0; t < nt;) {
+        // step t reads the halo pixels committed in the steps up to t - 1 (the common case falls through)
+        if (rdy < t - 1) { rdy = lds_volatile(ready_s); continue; }
+#ifdef YCGE_WF_TRACE
+        if (a.trace && lane == 0 && t == 501) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 22] = tm; }
+        if (a.trace && lane == 0 && t == 513) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 20] = tm; } // step 512 (row 3 pixel 503, row 2 pixel 506) is published
+        if (a.trace && lane == 0 && (t & 63) == 63 && (t >> 6) < 18) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 2 + (t >> 6)] = tm; } // development aid
+#endif
+        if (lane == 0) sts_volatile(runner_s, t);
         fetch(t + YCGE_WF_DEPTH - 1); // into the ring slot step t - 1 has left
         char *blk = reinterpret_cast<char *>(s_rec[t & (YCGE_WF_DEPTH - 1)]);
         // ---- 1. my slots: record -> term, in place: three independent dependency chains
@@ -284,7 +310,15 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
             *reinterpret_cast<float4 *>(blk + off[3]) = wf_term<FAST>(R[3], hv[3], c0.w, wB[3], dc, rc);
         }
         __syncwarp();
-        rdy = lds_volatile(&s_ready);
+        rdy = lds_volatile(ready_s);
+        // the records of the NEXT step (its block landed a step ago): their addresses into the history are ready when this step ends
+        float4 c0n;
+        {
+            const char *nblk = reinterpret_cast<const char *>(s_rec[(t + 1) & (YCGE_WF_DEPTH - 1)]);
+            c0n = *reinterpret_cast<const float4 *>(nblk + off_c0);
+#pragma unroll
+            for (int j = 0; j < (LASTROW ? 4 : 3); j++) R[j] = *reinterpret_cast<const float4 *>(nblk + off[j]);
+        }
         // ---- 2. the 25 terms in the reference's order, normalise (:706-714), luma
         float4 acc = zero4;
 #pragma unroll
@@ -300,18 +334,14 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
             st_relaxed_f4(out_p + 2 * i, res);
             if (PEER) st_relaxed_sys_f4(peer_p + 2 * i, res);
         }
-        asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 2) : "memory"); // the block of step t + 1 has landed
+        asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 3) : "memory"); // the block of step t + 2 has landed
         __syncwarp();
-        {
-            const char *nblk = reinterpret_cast<const char *>(s_rec[(t + 1) & (YCGE_WF_DEPTH - 1)]);
-            c0 = *reinterpret_cast<const float4 *>(nblk + off_c0);
-#pragma unroll
-            for (int j = 0; j < (LASTROW ? 4 : 3); j++) R[j] = *reinterpret_cast<const float4 *>(nblk + off[j]);
-        }
+        c0 = c0n;
+        t++;
     }
     };
     if (last_row_band) run(WfTag<true>{}); else run(WfTag<false>{});
-    if (lane == 0) sts_volatile(&s_runner_t, nt + YCGE_WF_AHEAD); // lets the halo warp run out
+    if (lane == 0) sts_volatile(runner_s, nt + YCGE_WF_AHEAD); // lets the halo warp run out
     if (a.trace && lane == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 1] = tm; }
 }
 

@@ -152,7 +152,7 @@ struct ycge_ctx {
     bool fast_div = false; // the FMA division sequence was verified against IEEE division for these four divisors
     volatile int *wave_err_host = nullptr; // pinned, mapped: set by a wavefront kernel whose poll gave up (a value that never arrived)
     int *wave_err_dev = nullptr;
-    bool use_wave = false;             // stride-2 in-place pass: true = the systolic form (wavefront.cuh, bit-identical, measured SLOWER: 3.1 vs 2.2 ms at 1080p); false: one warp per chain (post.cuh)
+    bool use_wave = true;              // stride-2 in-place pass: true = systolic bands (wavefront.cuh, 1.33 ms at 1080p); false: one warp per chain (post.cuh, 2.2 ms); bit-identical
     DevBuf<unsigned int> tickets;      // [0]: plain wavefront launches, [1]: peer-storing launches (dispatch-order tickets)
     std::vector<unsigned int> ticket_bases = std::vector<unsigned int>(132, 0u); // host mirror of the counters
     unsigned int ticket_base_of(int peer, int slot) const { return ticket_bases[peer ? 1 : 2 * slot + 2]; }
