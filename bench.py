@@ -250,6 +250,13 @@ def main():
         r = pkg.CudaRaytraceRenderer(scene, fb_w, fb_h, ss, device=local_rank)
         torch.cuda.synchronize()
         scene_switch["create_and_upload_ms"] = 1e3 * (time.perf_counter() - t_sw)
+        if scene.n_meshes > 0:
+            # the mesh trees once more, by the library's host builder and ON THE DEVICE (same trees, node for node);
+            # the timed frames below are rendered from the device-built ones
+            r.rebuild_meshes_on_device()  # untimed: the first call sizes the scratch arena
+            tm = r.rebuild_meshes_on_device(also_time_host_builder=True)
+            scene_switch["mesh_trees_host_builder_ms"] = tm["host"]
+            scene_switch["mesh_trees_device_builder_ms"] = tm["device"]
         r.SetCamera(*pose)
         r.set_stream(stream.cuda_stream)
         # untimed: one frame with the reference-defined event counters (feeds the algorithmic-bytes roofline)

@@ -251,6 +251,14 @@ YCGE_API int ycge_resize(ycge_ctx *ctx, int32_t fb_w, int32_t fb_h, int32_t ss);
 YCGE_API int ycge_mesh_upload_soa(ycge_ctx *ctx, int32_t id, const ycge_mesh_soa *mesh);          /* MeshBVH.cs:18-39 */
 YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *ctx, int32_t id, int32_t n_tris, const float *abc,
                                         const ycge_material *material);                       /* new MeshBVH(tris)  MeshBVH.cs:41-130 */
+/* the same call, the tree built ON THE DEVICE (csrc/bvh_device.cuh): MeshBVH.BuildRecursive
+ * (MeshBVH.cs:371-576) node for node -- binned SAH with the reference's bin mapping, its in-place two-pointer partition in
+ * closed form, its Array.Sort fallback -- from a device-wide work queue, written straight in the device layout.  A scene
+ * switch (RaytraceEntity.cs:234-246) then costs milliseconds of GPU time instead of the host build. */
+YCGE_API int ycge_mesh_build_device(ycge_ctx *ctx, int32_t id, int32_t n_tris, const float *abc, const ycge_material *material);
+/* Development / test aid: the stored device arrays of a mesh.  what: 0 = pair nodes (64 B each), 1 = triangles in leaf
+ * order (48 B), 2 = leaf slot -> triangle index (4 B), 3 = root record (32 B).  dst == NULL: *bytes = size of the array. */
+YCGE_API int ycge_mesh_debug_read(ycge_ctx *ctx, int32_t id, int32_t what, void *dst, size_t *bytes);
 YCGE_API int ycge_volume_upload(ycge_ctx *ctx, int32_t id, const ycge_volume *vol);              /* new VolumeGrid(...)  VolumeGrid.cs:55-93 */
 /* new Texture(path) (Renderer/Texture.cs:25-49, :81-90): `rgba` = the reference's int[] pixels (byte 0 = R, row-major, row 0
  * first), read during the call.  Materials refer to it through ycge_material.tex_id; upload before ycge_scene_upload.

@@ -116,7 +116,7 @@ PTR_CELLS, PTR_LOG_SAMPLES, PTR_HIST, PTR_GND, PTR_GAS, PTR_EXPOSURE = 0, 1, 2, 
 # every symbol include/ycge.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "ycge_default_params", "ycge_create", "ycge_destroy", "ycge_last_error", "ycge_resize", "ycge_mesh_upload_soa",
-    "ycge_mesh_upload_triangles", "ycge_volume_upload", "ycge_texture_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
+    "ycge_mesh_upload_triangles", "ycge_mesh_build_device", "ycge_mesh_debug_read", "ycge_volume_upload", "ycge_texture_upload", "ycge_scene_upload", "ycge_lights_update", "ycge_globals_update",
     "ycge_set_camera", "ycge_set_fov", "ycge_set_trace_variant", "ycge_set_inplace_variant", "ycge_reset_history", "ycge_render_frame", "ycge_render_frame_stats",
     "ycge_render_frames_async", "ycge_wait", "ycge_pipeline_config", "ycge_submit_frame", "ycge_frame_wait", "ycge_read_cells", "ycge_peer_export", "ycge_peer_attach", "ycge_stash_config", "ycge_frame_stash",
     "ycge_frame_finish_stashed", "ycge_stash_logs_ptr", "ycge_frame_begin", "ycge_frame_halo", "ycge_frame_inplace",
@@ -147,6 +147,8 @@ def load_lib() -> C.CDLL:
         lib.ycge_resize.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
         lib.ycge_mesh_upload_soa.argtypes = [vp, C.c_int32, vp]
         lib.ycge_mesh_upload_triangles.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+        lib.ycge_mesh_build_device.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+        lib.ycge_mesh_debug_read.argtypes = [vp, C.c_int32, C.c_int32, vp, C.POINTER(C.c_size_t)]
         lib.ycge_volume_upload.argtypes = [vp, C.c_int32, vp]
         lib.ycge_scene_upload.argtypes = [vp, vp]
         lib.ycge_texture_upload.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
@@ -505,6 +507,29 @@ class CudaRaytraceRenderer:
     def set_inplace_variant(self, variant: int):
         """0: one warp per chain of the in-place a-trous iteration (post.cuh); 1 (default): systolic bands (wavefront.cuh).  Bit-identical."""
         self._ck(self._lib.ycge_set_inplace_variant(self.ctx, variant))
+
+    def rebuild_meshes_on_device(self, also_time_host_builder: bool = False) -> dict:
+        """builds every mesh tree of the scene again ON THE DEVICE from the raw triangles (ycge_mesh_build_device:
+        MeshBVH.BuildRecursive node for node) and re-syncs the object table; frames are bit-identical to those of the
+        host-built trees.  Returns wall times in ms: 'device' and, on request, 'host' (the library's host builder on the
+        same triangles, ycge_mesh_upload_triangles) -- what a scene switch pays for its mesh trees either way."""
+        import time
+        out = {"device": 0.0, "triangles": 0}
+        if also_time_host_builder:
+            out["host"] = 0.0
+        for i in range(self.scene.n_meshes):
+            tris = np.ascontiguousarray(self.scene.mesh_triangles(i), np.float32)
+            mat = self.scene.mesh(i).contents.material
+            out["triangles"] += len(tris)
+            if also_time_host_builder:
+                t0 = time.perf_counter()
+                self._ck(self._lib.ycge_mesh_upload_triangles(self.ctx, i, len(tris), tris.ctypes.data, C.byref(mat)))
+                out["host"] += 1e3 * (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            self._ck(self._lib.ycge_mesh_build_device(self.ctx, i, len(tris), tris.ctypes.data, C.byref(mat)))
+            out["device"] += 1e3 * (time.perf_counter() - t0)
+        self._ck(self._lib.ycge_scene_upload(self.ctx, self.scene.flat))
+        return out
 
     def lights_update(self, lights):
         """Per-frame light changes without re-uploading geometry (DayNightCycle.cs:80-83): [(pos3, color3, intensity), ...]"""

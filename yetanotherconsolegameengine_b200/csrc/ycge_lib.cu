@@ -4,8 +4,10 @@
 #include "wavefront.cuh"
 #include "trace_stream.cuh"
 #include "bvh_build.hpp"
+#include "bvh_device.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -50,7 +52,8 @@ struct MeshStore {
     DevBuf<int> tri_id;
     TreeRoot root;
     ycge_material material;
-    int n_tris = 0;
+    int n_tris = 0, n_pairs = 0;
+    unsigned int sort_fallbacks = 0;
 };
 struct TextureStore {
     DevBuf<uchar4> px;
@@ -82,6 +85,7 @@ struct ycge_ctx {
     // image planes
     DevBuf<float4> cur, gnd0, gnd1, gas0, gas1, hist, sa, sb;
     DevBuf<unsigned long long> chain_trace;
+    DevBuf<unsigned char> db_scratch; // device BVH build (ycge_mesh_build_device)
     DevBuf<unsigned char> ansi;       // device ANSI byte stream (ycge_ansi_emit)
     DevBuf<unsigned int> ansi_rows;   // [rows] lengths, [rows] offsets, [1] total
     DevBuf<float4> pre; // in-place à-trous pass: 25 planes of per-tap precomputed terms / guide weights
@@ -1011,7 +1015,7 @@ static int store_mesh(ycge_ctx *c, int id, int n, const float *soa12 /* n x (A,e
     CK(c, m->nodes.upload(pairs, c->stream));
     CK(c, m->tris.upload(tris, c->stream));
     CK(c, m->tri_id.upload(ids, c->stream));
-    m->root = root; m->material = mat; m->n_tris = n;
+    m->root = root; m->material = mat; m->n_tris = n; m->n_pairs = (int)pairs.size();
     c->meshes[id] = std::move(m);
     c->have_scene = false; // object table must be rebuilt
     return 0;
@@ -1055,6 +1059,104 @@ YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *c, int32_t id, int32_t n, cons
     FlatTree tree;
     build_reference_tree(items, 8, true, tree);
     return store_mesh(c, id, n, soa.data(), view_of(tree), *material);
+} YCGE_CATCH
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// the same tree, built on the device (bvh_device.cuh).  Everything is enqueued on the context's stream; the
+// host only waits for the 32-byte root record (the object table of ycge_scene_upload carries the root box by value).
+YCGE_API int ycge_mesh_build_device(ycge_ctx *c, int32_t id, int32_t n, const float *abc, const ycge_material *material) try {
+    if (c && c->group) return group_each_front(c, [&](ycge_ctx *f) { return ycge_mesh_build_device(f, id, n, abc, material); });
+    if (!c || !abc || !material || n < 0) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    if (n == 0) return ycge_mesh_upload_triangles(c, id, n, abc, material);
+    if (n >= YCGE_LEAF_MAX_START) return fail(c, YCGE_ERR_LIMIT, "mesh larger than 2^26 triangles");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int n_sm = 0;
+    CK(c, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+    const int grid = 2 * n_sm;
+    const size_t N = (size_t)n;
+    // scratch: one grow-only arena per context (cudaMalloc / cudaFree of a dozen buffers cost more than the build itself)
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_abc = carve(N * 9 * 4), o_box = carve(N * 9 * 4), o_soa = carve(N * 12 * 4), o_nbox = carve(N * 2 * 6 * 4);
+    const size_t o_int = carve((N * 6 + N + grid + 16) * 4), o_nint = carve(N * 2 * 3 * 4), o_nodes = carve(N * 2 * sizeof(DbNode));
+    const size_t o_cnt = carve(sizeof(DbCounters)), o_root = carve(sizeof(TreeRoot));
+    if (c->db_scratch.n < off) { CK(c, cudaStreamSynchronize(s)); CK(c, c->db_scratch.alloc(off)); }
+    unsigned char *base = c->db_scratch.p;
+    std::unique_ptr<MeshStore> m(new MeshStore());
+    CK(c, m->nodes.alloc(N)); CK(c, m->tris.alloc(N)); CK(c, m->tri_id.alloc(N));
+    float *d_abc = reinterpret_cast<float *>(base + o_abc), *d_box = reinterpret_cast<float *>(base + o_box);
+    int *d_int = reinterpret_cast<int *>(base + o_int), *d_nint = reinterpret_cast<int *>(base + o_nint);
+    TreeRoot *d_root = reinterpret_cast<TreeRoot *>(base + o_root);
+    DbCounters *d_cnt = reinterpret_cast<DbCounters *>(base + o_cnt);
+    CK(c, cudaMemcpyAsync(d_abc, abc, N * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+    DbArgs a;
+    a.n = n; a.abc = d_abc;
+    a.blo = d_box; a.bhi = d_box + 3 * N; a.cen = d_box + 6 * N; a.soa12 = reinterpret_cast<float *>(base + o_soa);
+    a.idx = d_int; a.tmp = a.idx + N; a.pre = a.tmp + N; a.rpos = a.pre + N; a.lpos = a.rpos + N; a.queue = a.lpos + N; a.ready = a.queue + N;
+    a.nodes = reinterpret_cast<DbNode *>(base + o_nodes); a.cnt = d_cnt;
+    a.nbox = reinterpret_cast<float *>(base + o_nbox); a.nsize = d_nint; a.ninner = a.nsize + 2 * N; a.nflag = a.ninner + 2 * N;
+    a.pairs = m->nodes.p; a.tris = m->tris.p; a.tri_id = m->tri_id.p; a.root = d_root;
+    CK(c, cudaMemsetAsync(a.ready, 0, (N + grid + 16) * sizeof(int), s));
+    CK(c, cudaMemsetAsync(a.nflag, 0, 2 * N * sizeof(int), s));
+    const bool timing = getenv("YCGE_DB_TIME") != nullptr; // development aid
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    const double h0 = now_ms();
+    if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, s); }
+    db_items_kernel<<<div_up(n, 256), 256, 0, s>>>(a);
+    db_init_kernel<<<1, 1, 0, s>>>(a);
+    if (timing) cudaEventRecord(e1, s);
+    db_build_kernel<<<grid, YCGE_DB_THREADS, 0, s>>>(a);
+    if (timing) cudaEventRecord(e2, s);
+    db_boxes_kernel<<<div_up(2 * n, 256), 256, 0, s>>>(a);
+    db_emit_kernel<<<div_up(2 * n, 256), 256, 0, s>>>(a);
+    db_tris_kernel<<<div_up(n, 256), 256, 0, s>>>(a);
+    CK(c, cudaGetLastError());
+    TreeRoot root;
+    DbCounters cnt;
+    CK(c, cudaMemcpyAsync(&root, d_root, sizeof root, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    if (timing) {
+        float t01 = 0, t12 = 0;
+        cudaEventElapsedTime(&t01, e0, e1); cudaEventElapsedTime(&t12, e1, e2);
+        fprintf(stderr, "ycge_mesh_build_device: %d triangles: items %.3f ms, build %.3f ms, enqueue->done %.3f ms host, nodes %u, fallbacks %u\n", n, t01, t12, now_ms() - h0, cnt.n_nodes, cnt.fallbacks);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    }
+    if (cnt.done_items != n) return fail(c, YCGE_ERR_CUDA, "device BVH build did not place every triangle");
+    m->root = root; m->material = *material; m->n_tris = n;
+    m->n_pairs = cnt.n_nodes > 1 ? (int)(cnt.n_nodes - 1) / 2 : 0; // a full binary tree: inner = (nodes - 1) / 2
+    m->sort_fallbacks = cnt.fallbacks;
+    c->meshes[id] = std::move(m);
+    c->have_scene = false; // object table must be rebuilt
+    return 0;
+} YCGE_CATCH
+
+// Development / test aid: the stored device arrays of a mesh.  what: 0 = pair nodes (64 B each), 1 = triangles in leaf order
+// (48 B), 2 = leaf slot -> triangle index (4 B), 3 = the root record (32 B).  dst == NULL: *bytes = size of that array.
+YCGE_API int ycge_mesh_debug_read(ycge_ctx *c, int32_t id, int32_t what, void *dst, size_t *bytes) try {
+    if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_mesh_debug_read is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
+    if (!c || !bytes) return fail(c, YCGE_ERR_INVALID, "bad argument");
+    auto it = c->meshes.find(id);
+    if (it == c->meshes.end()) return fail(c, YCGE_ERR_INVALID, "no such mesh");
+    MeshStore &m = *it->second;
+    const void *src = nullptr;
+    size_t need = 0;
+    switch (what) {
+        case 0: src = m.nodes.p; need = (size_t)m.n_pairs * sizeof(PairNode); break;
+        case 1: src = m.tris.p; need = (size_t)m.n_tris * sizeof(DevTri); break;
+        case 2: src = m.tri_id.p; need = (size_t)m.n_tris * sizeof(int); break;
+        case 3: need = sizeof(TreeRoot); break;
+        default: return fail(c, YCGE_ERR_INVALID, "unknown array");
+    }
+    if (!dst) { *bytes = need; return 0; }
+    if (*bytes < need) return fail(c, YCGE_ERR_INVALID, "destination too small");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (what == 3) memcpy(dst, &m.root, need);
+    else if (need) CK(c, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    *bytes = need;
+    return 0;
 } YCGE_CATCH
 
 // ---- volumes -----------------------------------------------------------------------------------------------
