@@ -128,6 +128,9 @@ template <bool FAST> __device__ __forceinline__ float4 wf_term(const float4 R, c
 static_assert(YCGE_WF_HISTORY_ENTRIES * 16 <= YCGE_WF_HIST_MASK + 16, "history must cover every offset the mask lets through");
 
 template <bool V> struct WfTag { static constexpr bool value = V; };
+#ifndef YCGE_WF_UNROLL
+#define YCGE_WF_UNROLL 1 // steps per loop iteration; 2 and 8 (= DEPTH: every ring slot a constant) were measured: no difference, the step is bound by its dependency chain
+#endif
 // volatile shared-memory words by shared-window address (kept in a register by the caller: see keep_reg)
 __device__ __forceinline__ int lds_volatile(unsigned int sa) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa) : "memory"); return v; }
 __device__ __forceinline__ void sts_volatile(unsigned int sa, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(sa), "r"(v) : "memory"); }
@@ -285,10 +288,15 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
 
     auto run = [&](auto last_tag) { // two copies of the loop: the band that holds row H-1 evaluates a fourth slot per lane
     constexpr bool LASTROW = decltype(last_tag)::value;
+    constexpr int U = LASTROW ? 1 : YCGE_WF_UNROLL; // steps per loop iteration: ring slots become constants, one back edge per U steps
 #pragma unroll 1
-    for (int t = 0; t < nt;) {
+    for (int tb = 0; tb < nt; tb += U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int t = tb + u;
+        if (U > 1 && t >= nt) break;
         // step t reads the halo pixels committed in the steps up to t - 1 (the common case falls through)
-        if (rdy < t - 1) { rdy = lds_volatile(ready_s); continue; }
+        while (rdy < t - 1) rdy = lds_volatile(ready_s);
 #ifdef YCGE_WF_TRACE
         if (a.trace && lane == 0 && t == 501) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 22] = tm; }
         if (a.trace && lane == 0 && t == 513) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 20] = tm; } // step 512 (row 3 pixel 503, row 2 pixel 506) is published
@@ -337,7 +345,7 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
         asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 3) : "memory"); // the block of step t + 2 has landed
         __syncwarp();
         c0 = c0n;
-        t++;
+    }
     }
     };
     if (last_row_band) run(WfTag<true>{}); else run(WfTag<false>{});
