@@ -115,8 +115,17 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 
 // one record -> one term (see the header).  R = the record, hv = the history entry it names (anything for a finished term),
 // lum0 = luma of the centre, dc, rc = max(1e-6, cPhi) and its reciprocal
+__device__ __forceinline__ float4 wf_term_wc(const float4 R, const float4 hv, const float wc, const float wB) {
+    const float w = wB * wc * R.x * R.y * R.z; // the reference's product order wBase*wc*wn*wz*wa (:699)
+    float4 t; // opaque select (every lane runs the exp chain: a compiler-made branch around it would split the block)
+    asm("{ .reg .pred p; setp.lt.s32 p, %8, 0; selp.f32 %0, %4, %9, p; selp.f32 %1, %5, %10, p; selp.f32 %2, %6, %11, p; selp.f32 %3, %7, %12, p; }"
+        : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+        : "f"(hv.x * w), "f"(hv.y * w), "f"(hv.z * w), "f"(w), "r"(__float_as_int(R.w)), "f"(R.x), "f"(R.y), "f"(R.z), "f"(R.w));
+    return t;
+}
+template <bool FAST> __device__ __forceinline__ float wf_wc(const float4 hv, const float lum0, const float dc, const float rc) { return ycge_expf_nonpos(neg_div<FAST>(fabsf(hv.w - lum0), dc, rc)); }
 template <bool FAST> __device__ __forceinline__ float4 wf_term(const float4 R, const float4 hv, const float lum0, const float wB, const float dc, const float rc) {
-    const float wc = ycge_expf_nonpos(neg_div<FAST>(fabsf(hv.w - lum0), dc, rc));
+    const float wc = wf_wc<FAST>(hv, lum0, dc, rc);
     const float w = wB * wc * R.x * R.y * R.z; // the reference's product order wBase*wc*wn*wz*wa (:699)
     float4 t; // opaque select (every lane runs the exp chain: a compiler-made branch around it would split the block)
     asm("{ .reg .pred p; setp.lt.s32 p, %8, 0; selp.f32 %0, %4, %9, p; selp.f32 %1, %5, %10, p; selp.f32 %2, %6, %11, p; selp.f32 %3, %7, %12, p; }"
@@ -228,16 +237,23 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
     const bool row_ok = y < g.y1;
     const bool last_row_band = yb0 + 2 * (YCGE_WF_ROWS - 1) >= g.H - 1 && g.y1 == g.H; // row H-1 folds the kernel rows below onto itself: slots 15, 16, 20, 21 may be filtered taps
     const char *hist_b = reinterpret_cast<const char *>(s_hist);
-    // my three slots 3q + j (and, in the last band, a fourth one), their kernel weights and their byte offsets in a block
-    const int s4 = q == 0 ? 15 : (q == 1 ? 16 : (q == 2 ? 20 : 21));
-    float wB[4];
-    int off[4];
+    // my three slots 3q + j, their kernel weights and their byte offsets in a block
+    float wB[3];
+    int off[3];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int k = j < 3 ? 3 * q + j : s4;
+    for (int j = 0; j < 3; j++) {
+        const int k = 3 * q + j;
         wB[j] = wf_kw(k % 5 - 2) * wf_kw(k / 5 - 2);
         off[j] = (k * YCGE_WF_CHAINS + wf_record_column(k, c)) * 16;
     }
+    // Row H-1 folds the kernel rows below onto itself: its slots 15, 20 (resp. 16, 21) are filtered taps with the SOURCE PIXEL
+    // of slot 10 (resp. 11) -- same centre, hence the same colour weight, guide weights and history entry, only the kernel
+    // weight differs.  Lane 3 of that chain's quad (it owns slots 10 and 11) writes those four terms as well.
+    const bool fold_lane = last_row_band && q == 3 && y == g.H - 1;
+    int off_fold[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int sl = k == 0 ? 15 : (k == 1 ? 20 : (k == 2 ? 16 : 21)); off_fold[k] = (sl * YCGE_WF_CHAINS + wf_record_column(sl, c)) * 16; }
+    const float wB_fold[4] = {wf_kw(-2) * wf_kw(1), wf_kw(-2) * wf_kw(2), wf_kw(-1) * wf_kw(1), wf_kw(-1) * wf_kw(2)}; // slots 15, 20, 16, 21
     const int off_c0 = (25 * YCGE_WF_CHAINS + wf_record_column(25, c)) * 16;
     int col[4]; // byte offset of my chain's column in the slots k with (k / 3) & 3 == m
 #pragma unroll
@@ -276,17 +292,17 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
     __syncwarp();
     const float dc = a.dc, rc = a.rc;
     // the records of my slots and the centre of the coming step, loaded one step ahead (their block has landed by then)
-    float4 R[4], c0;
+    float4 R[3], c0;
     {
         const char *blk = reinterpret_cast<const char *>(s_rec[0]);
         c0 = *reinterpret_cast<const float4 *>(blk + off_c0);
 #pragma unroll
-        for (int j = 0; j < 4; j++) R[j] = *reinterpret_cast<const float4 *>(blk + off[j]);
+        for (int j = 0; j < 3; j++) R[j] = *reinterpret_cast<const float4 *>(blk + off[j]);
     }
     int rdy = lds_volatile(ready_s); // what the halo warp had announced a step ago: enough in the steady state, re-read otherwise
     if (a.trace && lane == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band] = tm; }
 
-    auto run = [&](auto last_tag) { // two copies of the loop: the band that holds row H-1 evaluates a fourth slot per lane
+    auto run = [&](auto last_tag) { // two copies of the loop: the band that holds row H-1 also writes that row's folded slots
     constexpr bool LASTROW = decltype(last_tag)::value;
     constexpr int U = LASTROW ? 1 : YCGE_WF_UNROLL; // steps per loop iteration: ring slots become constants, one back edge per U steps
 #pragma unroll 1
@@ -306,17 +322,27 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
         fetch(t + YCGE_WF_DEPTH - 1); // into the ring slot step t - 1 has left
         char *blk = reinterpret_cast<char *>(s_rec[t & (YCGE_WF_DEPTH - 1)]);
         // ---- 1. my slots: record -> term, in place: three independent dependency chains
-        float4 hv[4];
+        float4 hv[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) hv[j] = *reinterpret_cast<const float4 *>(hist_b + (__float_as_int(R[j].w) & YCGE_WF_HIST_MASK));
+        if (LASTROW) {
+            float wc[3];
 #pragma unroll
-        for (int j = 0; j < 3; j++) R[j] = wf_term<FAST>(R[j], hv[j], c0.w, wB[j], dc, rc);
+            for (int j = 0; j < 3; j++) wc[j] = wf_wc<FAST>(hv[j], c0.w, dc, rc);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { // the folded slots of row H-1, from slot 10 (k < 2) or 11
+                const int j = 1 + (k >> 1);
+                const float4 tf = wf_term_wc(R[j], hv[j], wc[j], wB_fold[k]);
+                if (fold_lane && __float_as_int(R[j].w) < 0) *reinterpret_cast<float4 *>(blk + off_fold[k]) = tf;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) R[j] = wf_term_wc(R[j], hv[j], wc[j], wB[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; j++) R[j] = wf_term<FAST>(R[j], hv[j], c0.w, wB[j], dc, rc);
+        }
 #pragma unroll
         for (int j = 0; j < 3; j++) *reinterpret_cast<float4 *>(blk + off[j]) = R[j];
-        if (LASTROW) {
-            hv[3] = *reinterpret_cast<const float4 *>(hist_b + (__float_as_int(R[3].w) & YCGE_WF_HIST_MASK));
-            *reinterpret_cast<float4 *>(blk + off[3]) = wf_term<FAST>(R[3], hv[3], c0.w, wB[3], dc, rc);
-        }
         __syncwarp();
         rdy = lds_volatile(ready_s);
         // the records of the NEXT step (its block landed a step ago): their addresses into the history are ready when this step ends
@@ -325,7 +351,7 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
             const char *nblk = reinterpret_cast<const char *>(s_rec[(t + 1) & (YCGE_WF_DEPTH - 1)]);
             c0n = *reinterpret_cast<const float4 *>(nblk + off_c0);
 #pragma unroll
-            for (int j = 0; j < (LASTROW ? 4 : 3); j++) R[j] = *reinterpret_cast<const float4 *>(nblk + off[j]);
+            for (int j = 0; j < 3; j++) R[j] = *reinterpret_cast<const float4 *>(nblk + off[j]);
         }
         // ---- 2. the 25 terms in the reference's order, normalise (:706-714), luma
         float4 acc = zero4;
