@@ -137,6 +137,26 @@ template <bool FAST> __device__ __forceinline__ float4 wf_term(const float4 R, c
 static_assert(YCGE_WF_HISTORY_ENTRIES * 16 <= YCGE_WF_HIST_MASK + 16, "history must cover every offset the mask lets through");
 
 template <bool V> struct WfTag { static constexpr bool value = V; };
+// ---- thread-block clusters: consecutive bands of one row parity sit in one cluster and hand their last two rows over
+// through distributed shared memory instead of an L2 round trip: the band stores each pixel of its rows 2 and 3, tagged with
+// its index, into a staging ring of the band below, whose halo warp polls that ring in its OWN shared memory.  No fence
+// anywhere (a release / acquire pair at cluster scope compiles to MEMBAR.ALL.GPU resp. CCTL.IVALL per step: measured 2x
+// slower than no clusters): a staging entry is the all-ones sentinel until all four words of the pixel have landed and
+// carries the pixel index instead of the luma (recomputed on arrival), so it validates itself.
+// MEASURED (B200, 1080p, bit-identical, tests green): the hand-off inside a cluster takes 0.4 us instead of 1.8 us, but every
+// step of every band gets slower (0.39 -> 0.45 us: the remote stores go through the generic path, and a cluster is packed
+// onto few SMs of one GPC, so two ACTIVE bands share an SM's shared-memory pipeline where the plain launch pairs bands
+// that are 148 tickets apart and never active together): 1.34 ms with clusters of 8, 1.36 of 4, 1.41 of 2 against 1.27 ms
+// without.  The form is kept opt-in (YCGE_WAVE_CLUSTER=8) and off by default.
+__device__ __forceinline__ unsigned int cluster_rank() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned int map_to_rank(unsigned int sa, unsigned int rank) { unsigned int ra; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(sa), "r"(rank)); return ra; }
+__device__ __forceinline__ int ld_remote_s32(unsigned int ra) { int v; asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory"); return v; }
+__device__ __forceinline__ void st_remote_f4(unsigned int ra, float4 v) { asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
+__device__ __forceinline__ void st_remote_s32(unsigned int ra, int v) { asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory"); }
+__device__ __forceinline__ float4 lds_volatile_f4(unsigned int sa) { float4 v; asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa) : "memory"); return v; }
+#define YCGE_WF_SPIN_LIMIT (1u << 27) // shared-memory polls of a band's warp, all waits together (seconds)
+#define YCGE_WF_PUSH_AHEAD 24 // steps a band may run ahead of the band below it in its cluster (whose 32-entry rings it writes)
 #ifndef YCGE_WF_UNROLL
 #define YCGE_WF_UNROLL 1 // steps per loop iteration; 2 and 8 (= DEPTH: every ring slot a constant) were measured: no difference, the step is bound by its dependency chain
 #endif
@@ -217,22 +237,78 @@ __device__ __forceinline__ void wf_halo_warp(const WaveArgs &a, const WfGeom &g,
     }
 }
 
-template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wave_kernel(WaveArgs a) {
+// The halo warp of a band whose rows above come through the staging ring (the band above sits in the same cluster): the same
+// window of eight steps, polled in the band's own shared memory.  An entry is valid when none of its words is the sentinel
+// and its tag is the pixel index expected at that place; it is committed with its luma recomputed (:269-272, the same
+// three products and two sums as the producer's) and set back to the sentinel for the pixel 32 places on.
+__device__ __forceinline__ void wf_halo_warp_staged(const WaveArgs &a, const WfGeom &g, const int lane, float4 *s_hist, float4 *s_stage, const unsigned int ready, const unsigned int runner_t, const int nt) {
+    const unsigned int FULL = 0xffffffffu;
+    const int L = lane & 3, j = lane >> 2, lh = L >> 1, lcx = L & 1;
+    const int tl0 = lcx - YCGE_WF_L * (2 - lh);
+    const unsigned int n_halo = (unsigned int)g.ws[lcx];
+    float4 *halo_hist = s_hist + (lh * 2 + lcx) * YCGE_WF_RING;
+    float4 *stage = s_stage + L * YCGE_WF_RING;
+    const unsigned int stage_sa = (unsigned int)__cvta_generic_to_shared(stage);
+    const float sv = __uint_as_float(YCGE_SENTINEL);
+    int base = -YCGE_WF_LEAD, idle = 0;
+    while (base < nt) {
+        const int rt = lds_volatile(runner_t);
+        const int room = min(min(rt + YCGE_WF_AHEAD, nt - 1) - base + 1, 8);
+        const int ih = base + j - tl0;
+        const bool mine = (unsigned int)ih < n_halo && j < room;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (mine) v = lds_volatile_f4(stage_sa + (unsigned int)(ih & (YCGE_WF_RING - 1)) * 16u);
+        const bool ok = !mine || (f4_valid(v) && __float_as_int(v.w) == ih);
+        unsigned int m = __ballot_sync(FULL, ok);
+        m &= m >> 1; m &= m >> 2;
+        const unsigned int miss = ~m & 0x11111111u;
+        const int n = min(room, miss ? (__ffs((int)miss) - 1) >> 2 : 8);
+        if (mine && j < n) {
+            halo_hist[ih & (YCGE_WF_RING - 1)] = make_float4(v.x, v.y, v.z, luma3(v.x, v.y, v.z));
+            stage[ih & (YCGE_WF_RING - 1)] = make_float4(sv, sv, sv, sv);
+        }
+        if (n > 0) {
+            __syncwarp();
+            __threadfence_block();
+            base += n;
+            if (lane == 0) sts_volatile(ready, base - 1);
+            idle = 0;
+        } else if (room <= 0) __nanosleep(100);
+        else if (++idle > (1 << 26)) { // the band above is gone: fail the frame, let the band run out
+            if (lane == 0) { *(volatile int *)a.err = 1; sts_volatile(ready, nt); }
+            return;
+        } else __nanosleep(20);
+    }
+}
+
+// CL = CTAs per cluster (1: no cluster).  A cluster takes ONE ticket: ticket k = row parity k & 1, bands (k >> 1) * CL + rank.
+template <bool FAST, bool PEER, int CL> __global__ void __launch_bounds__(64) atrous_wave_kernel(WaveArgs a) {
     __shared__ __align__(128) float4 s_rec[YCGE_WF_DEPTH][YCGE_WF_BLOCK];
     __shared__ __align__(16) float4 s_hist[(YCGE_WF_HIST_MASK + 16) / 16];
-    __shared__ int s_band, s_ready, s_runner_t;
+    __shared__ __align__(16) float4 s_stage[4 * YCGE_WF_RING]; // [row h above x column parity][pixel & 31]: (r, g, b, pixel index) from the band above, or the sentinel
+    __shared__ int s_band, s_ready, s_runner_t, s_below_t;
     const int lane = threadIdx.x & 31, c = lane >> 2, q = lane & 3, r = c >> 1, cx = c & 1;
-    if (threadIdx.x == 0) { s_band = (int)(atomicAdd(a.ticket, 1u) - a.ticket_base); s_ready = -YCGE_WF_LEAD - 1; s_runner_t = 0; }
+    const unsigned int rank = CL > 1 ? cluster_rank() : 0u;
+    if (threadIdx.x == 0) { if (rank == 0) s_band = (int)(atomicAdd(a.ticket, 1u) - a.ticket_base); s_ready = -YCGE_WF_LEAD - 1; s_runner_t = 0; s_below_t = 0; }
     for (int k = threadIdx.x; k < (YCGE_WF_HIST_MASK + 16) / 16; k += 64) s_hist[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (CL > 1) for (int k = threadIdx.x; k < 4 * YCGE_WF_RING; k += 64) { const float sv = __uint_as_float(YCGE_SENTINEL); s_stage[k] = make_float4(sv, sv, sv, sv); }
     __syncthreads();
-    const int band = s_band;
+    int ticket = s_band;
+    if (CL > 1) { cluster_sync_all(); ticket = ld_remote_s32(map_to_rank((unsigned int)__cvta_generic_to_shared(&s_band), 0u)); }
     const WfGeom &g = a.g;
-    const int cy = band & 1, b = band >> 1;
-    if (band >= g.n_warps || b >= g.nb[cy]) return;
+    const int cy = ticket & 1, b = (ticket >> 1) * CL + (int)rank, band = 2 * b + cy;
+    const bool valid = band < g.n_warps && b < g.nb[cy];
     const int yb0 = g.yf[cy] + 2 * YCGE_WF_ROWS * b;
     const int nt = g.nt;
     const unsigned int ready_s = keep_reg((unsigned int)__cvta_generic_to_shared(&s_ready)), runner_s = keep_reg((unsigned int)__cvta_generic_to_shared(&s_runner_t));
-    if (threadIdx.x >= 32) { wf_halo_warp(a, g, yb0, lane, s_hist, ready_s, runner_s, nt, band); return; }
+    const bool pushed = CL > 1 && rank > 0 && valid;                                 // the band above (same cluster) stores my two halo rows into my history
+    const bool pushes = CL > 1 && rank + 1 < CL && valid && b + 1 < g.nb[cy];        // ... and I do that for the band below
+    if (!valid || threadIdx.x >= 32) {
+        if (valid && !pushed) wf_halo_warp(a, g, yb0, lane, s_hist, ready_s, runner_s, nt, band);
+        if (valid && pushed) wf_halo_warp_staged(a, g, lane, s_hist, s_stage, ready_s, runner_s, nt);
+        if (CL > 1) cluster_sync_all(); // nobody leaves while a neighbour may still store into its shared memory
+        return;
+    }
     const int y = yb0 + 2 * r;
     const bool row_ok = y < g.y1;
     const bool last_row_band = yb0 + 2 * (YCGE_WF_ROWS - 1) >= g.H - 1 && g.y1 == g.H; // row H-1 folds the kernel rows below onto itself: slots 15, 16, 20, 21 may be filtered taps
@@ -263,6 +339,16 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
     const unsigned int n_pub = (q == 0 && row_ok) ? (unsigned int)g.ws[cx] : 0u;
     float4 *out_p = a.new_ + (size_t)y * g.W + cx; // + 2 i
     float4 *own_hist = s_hist + ((r + 2) * 2 + cx) * YCGE_WF_RING;
+    // cluster hand-off: rows 2 and 3 of this band are the rows h = 0, 1 above the next one
+    const unsigned int below_s = keep_reg((unsigned int)__cvta_generic_to_shared(&s_below_t));
+    unsigned int rem_hist = 0, rem_above_t = 0;
+    if (CL > 1) {
+        if (pushes) {
+            rem_hist = map_to_rank((unsigned int)__cvta_generic_to_shared(s_stage + ((r >= 2 ? r - 2 : 0) * 2 + cx) * YCGE_WF_RING), rank + 1);
+        }
+        if (pushed) rem_above_t = map_to_rank(below_s, rank - 1);
+    }
+    const bool push_lane = pushes && r >= 2;
     float4 *peer_p = out_p;
     if (PEER) {
         if (a.peer_new && row_ok && y >= a.peer_y0 && y < a.peer_y1) peer_p = a.peer_new + (size_t)y * g.W + cx; // else: this row once more (no branch in the body)
@@ -300,7 +386,12 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
         for (int j = 0; j < 3; j++) R[j] = *reinterpret_cast<const float4 *>(blk + off[j]);
     }
     int rdy = lds_volatile(ready_s); // what the halo warp had announced a step ago: enough in the steady state, re-read otherwise
-    if (a.trace && lane == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band] = tm; }
+    int below = 0;                   // the step the band below (same cluster) has reached
+    unsigned int spins = 0;          // every wait of this warp counts: past the limit nothing waits any more and the frame fails
+    if (a.trace && lane == 0) {
+        unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band] = tm;
+        unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[32 * band + 23] = smid; // development aid: where the band runs
+    }
 
     auto run = [&](auto last_tag) { // two copies of the loop: the band that holds row H-1 also writes that row's folded slots
     constexpr bool LASTROW = decltype(last_tag)::value;
@@ -312,7 +403,11 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
         const int t = tb + u;
         if (U > 1 && t >= nt) break;
         // step t reads the halo pixels committed in the steps up to t - 1 (the common case falls through)
-        while (rdy < t - 1) rdy = lds_volatile(ready_s);
+        while (rdy < t - 1 && spins < YCGE_WF_SPIN_LIMIT) { rdy = lds_volatile(ready_s); spins++; }
+        if (CL > 1) {
+            while (pushes && t - below > YCGE_WF_PUSH_AHEAD && spins < YCGE_WF_SPIN_LIMIT) { below = lds_volatile(below_s); spins++; } // the band below still reads what I would overwrite
+            if (pushed && lane == 0) st_remote_s32(rem_above_t, t);
+        }
 #ifdef YCGE_WF_TRACE
         if (a.trace && lane == 0 && t == 501) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 22] = tm; }
         if (a.trace && lane == 0 && t == 513) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 20] = tm; } // step 512 (row 3 pixel 503, row 2 pixel 506) is published
@@ -345,6 +440,7 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
         for (int j = 0; j < 3; j++) *reinterpret_cast<float4 *>(blk + off[j]) = R[j];
         __syncwarp();
         rdy = lds_volatile(ready_s);
+        if (CL > 1) below = lds_volatile(below_s);
         // the records of the NEXT step (its block landed a step ago): their addresses into the history are ready when this step ends
         float4 c0n;
         {
@@ -367,6 +463,7 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
             own_hist[i & (YCGE_WF_RING - 1)] = res;
             st_relaxed_f4(out_p + 2 * i, res);
             if (PEER) st_relaxed_sys_f4(peer_p + 2 * i, res);
+            if (CL > 1 && push_lane) st_remote_f4(rem_hist + (unsigned int)(i & (YCGE_WF_RING - 1)) * 16u, make_float4(res.x, res.y, res.z, __int_as_float(i)));
         }
         asm volatile("cp.async.wait_group %0;" ::"n"(YCGE_WF_DEPTH - 3) : "memory"); // the block of step t + 2 has landed
         __syncwarp();
@@ -375,8 +472,13 @@ template <bool FAST, bool PEER> __global__ void __launch_bounds__(64) atrous_wav
     }
     };
     if (last_row_band) run(WfTag<true>{}); else run(WfTag<false>{});
+    if (spins >= YCGE_WF_SPIN_LIMIT && lane == 0) *(volatile int *)a.err = 1;
     if (lane == 0) sts_volatile(runner_s, nt + YCGE_WF_AHEAD); // lets the halo warp run out
+    if (CL > 1 && lane == 0) {
+        if (pushed) st_remote_s32(rem_above_t, nt + 2 * YCGE_WF_PUSH_AHEAD);
+    }
     if (a.trace && lane == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); a.trace[32 * band + 1] = tm; }
+    if (CL > 1) cluster_sync_all();
 }
 
 } // namespace ycge

@@ -31,6 +31,7 @@
 #define YCGE_WF_RING 32    // history entries per chain: a band reads values up to 2 L + 3 = 9 steps old, and the rows above it are brought in up to AHEAD steps early
 #define YCGE_WF_AHEAD 16   // steps the halo warp may run ahead of its band
 #define YCGE_WF_DEPTH 8    // steps of records in flight in shared memory (a power of two)
+#define YCGE_WF_CLUSTER 8  // bands per thread-block cluster of the OPT-IN cluster form (hand-off through distributed shared memory; measured slower, see wavefront.cuh)
 #define YCGE_WF_LEAD 6     // steps the halo warp starts before step 0, >= 2 L
 
 struct WfGeom {

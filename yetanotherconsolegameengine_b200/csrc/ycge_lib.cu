@@ -156,6 +156,8 @@ struct ycge_ctx {
     bool fast_div = false; // the FMA division sequence was verified against IEEE division for these four divisors
     volatile int *wave_err_host = nullptr; // pinned, mapped: set by a wavefront kernel whose poll gave up (a value that never arrived)
     int *wave_err_dev = nullptr;
+    int wave_pad_smem = 72 * 1024;      // see the launch of atrous_wave_kernel
+    int wave_cluster = 1; // bands per thread-block cluster of the systolic form: 1 = no clusters (default); YCGE_WAVE_CLUSTER=8 in the environment opts in
     bool use_wave = true;              // stride-2 in-place pass: true = systolic bands (wavefront.cuh, 1.33 ms at 1080p); false: one warp per chain (post.cuh, 2.2 ms); bit-identical
     DevBuf<unsigned int> tickets;      // [0]: plain wavefront launches, [1]: peer-storing launches (dispatch-order tickets)
     std::vector<unsigned int> ticket_bases = std::vector<unsigned int>(132, 0u); // host mirror of the counters
@@ -656,15 +658,36 @@ int denoise_run(ycge_ctx *c) {
                     CK(c, cudaMemsetAsync(c->chain_trace.p, 0, c->chain_trace.n * 8, s));
                     wa.trace = c->chain_trace.p;
                 }
+                // one CTA per band (the band's warp and its halo warp); clusters of YCGE_WF_CLUSTER consecutive bands of one row
+                // parity take one ticket and hand rows over through distributed shared memory
+                const int CLS = c->wave_cluster;
+                const int n_tickets = CLS > 1 ? 2 * div_up(wa.g.n_warps / 2, CLS) : wa.g.n_warps;
                 wa.ticket = c->tickets.p + 16 * (2 * ticket_slot + 2); wa.ticket_base = c->ticket_base_of(0, ticket_slot);
-                c->ticket_advance(0, ticket_slot, (unsigned int)wa.g.n_warps); // one ticket per CTA
+                c->ticket_advance(0, ticket_slot, (unsigned int)n_tickets);
                 CK(c, cudaEventRecord(c->ev[7], s));
                 if (wa.g.n_warps > 0) {
-                    const dim3 gr(wa.g.n_warps), th(64); // one CTA per band: the band's warp and its halo warp
-                    if (fast && wa.peer_new) atrous_wave_kernel<true, true><<<gr, th, 0, s>>>(wa);
-                    else if (fast) atrous_wave_kernel<true, false><<<gr, th, 0, s>>>(wa);
-                    else if (wa.peer_new) atrous_wave_kernel<false, true><<<gr, th, 0, s>>>(wa);
-                    else atrous_wave_kernel<false, false><<<gr, th, 0, s>>>(wa);
+                    cudaLaunchConfig_t lc = {};
+                    lc.gridDim = dim3(CLS > 1 ? n_tickets * CLS : wa.g.n_warps); lc.blockDim = dim3(64); lc.stream = s;
+                    // a cluster is placed inside one GPC and the block scheduler packs it onto few SMs: without a limit three bands
+                    // can share an SM (and two of them a sub-partition) while other SMs idle.  Dynamic shared memory that nobody
+                    // uses caps the residency at two CTAs per SM.
+                    lc.dynamicSmemBytes = CLS > 1 ? (size_t)c->wave_pad_smem : 0;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = CLS > 1 ? CLS : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    lc.attrs = at; lc.numAttrs = 1;
+                    const bool peer = wa.peer_new != nullptr;
+                    if (CLS > 1) {
+                        if (fast && peer) CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<true, true, YCGE_WF_CLUSTER>, wa));
+                        else if (fast) CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<true, false, YCGE_WF_CLUSTER>, wa));
+                        else if (peer) CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<false, true, YCGE_WF_CLUSTER>, wa));
+                        else CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<false, false, YCGE_WF_CLUSTER>, wa));
+                    } else {
+                        if (fast && peer) CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<true, true, 1>, wa));
+                        else if (fast) CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<true, false, 1>, wa));
+                        else if (peer) CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<false, true, 1>, wa));
+                        else CK(c, cudaLaunchKernelEx(&lc, atrous_wave_kernel<false, false, 1>, wa));
+                    }
                     launches++;
                 }
                 CK(c, cudaEventRecord(c->ev[8], s));
@@ -920,6 +943,15 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) try {
         CK(nullptr, cudaHostGetDevicePointer((void **)&c->wave_err_dev, h, 0));
     }
     if (const char *e = getenv("YCGE_WAVE")) c->use_wave = atoi(e) != 0; // 1 = the systolic wavefront kernels (wavefront.cuh)
+    if (const char *e = getenv("YCGE_WAVE_CLUSTER")) c->wave_cluster = atoi(e) > 1 ? YCGE_WF_CLUSTER : 1; // opt-in: thread-block clusters of 8 bands
+    if (const char *e = getenv("YCGE_WAVE_PAD_SMEM")) c->wave_pad_smem = atoi(e);                          // development aid
+    if (c->wave_cluster > 1) {
+        const int pad = c->wave_pad_smem;
+        CK(nullptr, cudaFuncSetAttribute(atrous_wave_kernel<true, true, YCGE_WF_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+        CK(nullptr, cudaFuncSetAttribute(atrous_wave_kernel<true, false, YCGE_WF_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+        CK(nullptr, cudaFuncSetAttribute(atrous_wave_kernel<false, true, YCGE_WF_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+        CK(nullptr, cudaFuncSetAttribute(atrous_wave_kernel<false, false, YCGE_WF_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+    }
     CK(nullptr, c->totals.alloc(1));
     CK(nullptr, cudaMemsetAsync(c->totals.p, 0, sizeof(TraceTotals), c->stream));
     { // edge-stopping divisors; verify the fast division over every non-negative binary32 numerator (a few ms, once)
