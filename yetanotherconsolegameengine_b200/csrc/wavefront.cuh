@@ -110,7 +110,12 @@ struct WaveArgs {
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
-#define YCGE_WF_POLL_LIMIT (1 << 21) // ~1 s of L2 round trips
+#define YCGE_WF_POLL_LIMIT (1 << 21) // polls of the peer's `ready` word (system-scope loads over NVLink: seconds)
+// A band that waits for rows another kernel or another GPU has yet to produce gives up after this many nanoseconds WITHOUT
+// ANY PROGRESS (globaltimer): ranks driven by separate host processes may start their kernels far apart -- a count of polls
+// (an earlier form: 2^21 polls of 0.15 us) expired during such a gap on 4 GPUs and the frame was silently wrong.
+#define YCGE_WF_WAIT_NS 20000000000ull
+__device__ __forceinline__ unsigned long long wf_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 
 // one record -> one term (see the header).  R = the record, hv = the history entry it names (anything for a finished term),
@@ -155,7 +160,7 @@ __device__ __forceinline__ int ld_remote_s32(unsigned int ra) { int v; asm volat
 __device__ __forceinline__ void st_remote_f4(unsigned int ra, float4 v) { asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
 __device__ __forceinline__ void st_remote_s32(unsigned int ra, int v) { asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory"); }
 __device__ __forceinline__ float4 lds_volatile_f4(unsigned int sa) { float4 v; asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa) : "memory"); return v; }
-#define YCGE_WF_SPIN_LIMIT (1u << 27) // shared-memory polls of a band's warp, all waits together (seconds)
+#define YCGE_WF_SPIN_LIMIT (1u << 31) // shared-memory polls of a band's warp, all waits together (a minute): its halo warp gives up long before
 #define YCGE_WF_PUSH_AHEAD 24 // steps a band may run ahead of the band below it in its cluster (whose 32-entry rings it writes)
 #ifndef YCGE_WF_UNROLL
 #define YCGE_WF_UNROLL 1 // steps per loop iteration; 2 and 8 (= DEPTH: every ring slot a constant) were measured: no difference, the step is bound by its dependency chain
@@ -187,6 +192,7 @@ __device__ __forceinline__ void wf_halo_warp(const WaveArgs &a, const WfGeom &g,
     const float4 *halo_p = a.new_ + (size_t)hy * g.W + lcx; // + 2 ih
     float4 *halo_hist = s_hist + (lh * 2 + lcx) * YCGE_WF_RING;
     int base = -YCGE_WF_LEAD, idle = 0;
+    unsigned long long t_progress = wf_now_ns();
     float4 v[YCGE_WF_POLLS];
     int bs[YCGE_WF_POLLS];
     auto issue = [&](float4 &vv, int &b0) {
@@ -227,8 +233,8 @@ __device__ __forceinline__ void wf_halo_warp(const WaveArgs &a, const WfGeom &g,
                 if (lane == 0) sts_volatile(ready, base - 1);
                 idle = 0;
                 if (base >= nt) return;
-            } else if (room <= 0) __nanosleep(100); // the band's own warp has to move first
-            else if (shift < 8 && ++idle > YCGE_WF_POLL_LIMIT) { // the producer is gone: fail the frame, let the band run out
+            } else if (room <= 0) { __nanosleep(100); idle = 0; } // the band's own warp has to move first
+            else if (shift < 8 && (++idle & 1023) == 0 && (idle == 1024 ? (t_progress = wf_now_ns(), false) : wf_now_ns() - t_progress > YCGE_WF_WAIT_NS)) { // the producer is gone: fail the frame, let the band run out
                 if (lane == 0) { *(volatile int *)a.err = 1; sts_volatile(ready, nt); }
                 return;
             }
@@ -251,6 +257,7 @@ __device__ __forceinline__ void wf_halo_warp_staged(const WaveArgs &a, const WfG
     const unsigned int stage_sa = (unsigned int)__cvta_generic_to_shared(stage);
     const float sv = __uint_as_float(YCGE_SENTINEL);
     int base = -YCGE_WF_LEAD, idle = 0;
+    unsigned long long t_progress = 0;
     while (base < nt) {
         const int rt = lds_volatile(runner_t);
         const int room = min(min(rt + YCGE_WF_AHEAD, nt - 1) - base + 1, 8);
@@ -274,7 +281,7 @@ __device__ __forceinline__ void wf_halo_warp_staged(const WaveArgs &a, const WfG
             if (lane == 0) sts_volatile(ready, base - 1);
             idle = 0;
         } else if (room <= 0) __nanosleep(100);
-        else if (++idle > (1 << 26)) { // the band above is gone: fail the frame, let the band run out
+        else if ((++idle & 1023) == 0 && (idle == 1024 ? (t_progress = wf_now_ns(), false) : wf_now_ns() - t_progress > YCGE_WF_WAIT_NS)) { // the band above is gone: fail the frame, let the band run out
             if (lane == 0) { *(volatile int *)a.err = 1; sts_volatile(ready, nt); }
             return;
         } else __nanosleep(20);
