@@ -153,7 +153,9 @@ __device__ __forceinline__ bool box_mesh(float mnx, float mny, float mnz, float 
 // Measured and dropped (B200, dragon 1080p, trace 1.18 ms): (1) parking a leaf while the lane keeps walking inner nodes
 // until its next entry is a leaf too ("postponed leaves": same leaf order, same hits — every entry is re-tested against
 // the current `closest` when popped — verified bit-exact), with and without warp votes to enter the triangle loop
-// together: 1.30 / 1.33 ms; (2) scene_hit as one __noinline__ copy instead of three inlined ones (halves the code):
+// together: 1.30 / 1.33 ms; (1b, round 2) the "while-while" shape -- every lane descends through inner nodes until it holds a leaf, the nearer
+// child kept in a register instead of pushed and popped, then the lanes of a warp intersect their leaves together -- bit-identical incl. the
+// event counters, 1.13 against 1.12 ms (dragon stand-in), 1.00 against 1.02 (bunny): no gain, not kept; (2) scene_hit as one __noinline__ copy instead of three inlined ones (halves the code):
 // 1.20 ms; (3) 16..40 resident warps per SM via launch bounds: no change.  The triangle loop runs with 2-3 of 32 lanes
 // active and 21 % of the stall samples are instruction-fetch misses, but the kernel is bound by the dependent node /
 // triangle fetch latency of the longest paths in each warp, not by those.

@@ -54,6 +54,10 @@ struct MeshStore {
     ycge_material material;
     int n_tris = 0, n_pairs = 0;
     unsigned int sort_fallbacks = 0;
+    // a device build in flight (ycge_mesh_build_device): root record and counters arrive in pinned memory behind `pending`
+    struct Pending { TreeRoot root; DbCounters cnt; } *pending_host = nullptr;
+    cudaEvent_t pending = nullptr;
+    ~MeshStore() { if (pending) cudaEventDestroy(pending); if (pending_host) cudaFreeHost(pending_host); }
 };
 struct TextureStore {
     DevBuf<uchar4> px;
@@ -445,6 +449,7 @@ void halo_rows(const ycge_ctx *c, int &lo, int &a, int &slo, int &sa);
 int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
     if (!c->have_scene) return fail(c, YCGE_ERR_NO_SCENE, "Scene BVH not built; call ycge_scene_upload() after populating the scene");
     if (c->frame_open) return fail(c, YCGE_ERR_INVALID, "ycge_frame_begin called twice without ycge_frame_finish");
+    { int rc = wave_check(c); if (rc) return rc; } // a wavefront kernel of an EARLIER frame gave up waiting (the phase API has no wait of its own: the flag is mapped host memory, reading it is free)
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const int W = c->W, H = c->H, ss = c->ss;
@@ -701,7 +706,7 @@ int denoise_run(ycge_ctx *c) {
             }
             AtrousChainArgs ia;
             ia.old_ = d.phys[X]; ia.new_ = d.phys[Y]; ia.pre = pre.p; ia.plane = (size_t)W * H;
-            ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc; ia.trace = nullptr;
+            ia.W = W; ia.H = H; ia.step = step; ia.shift = it; ia.dc = ed.dc; ia.rc = ed.rc; ia.trace = nullptr; ia.err = c->wave_err_dev;
             ia.peer_new = nullptr; ia.peer_y0 = ia.peer_y1 = 0; ia.ready = c->flags.p; ia.frame = (int)c->frame_counter;
             if (c->peers && c->has_below) {
                 int lo, aa, slo, sa_; halo_rows(c, lo, aa, slo, sa_);
@@ -1093,6 +1098,19 @@ YCGE_API int ycge_mesh_upload_triangles(ycge_ctx *c, int32_t id, int32_t n, cons
     return store_mesh(c, id, n, soa.data(), view_of(tree), *material);
 } YCGE_CATCH
 
+// completes a device build in flight: waits for its root record, checks that every triangle was placed
+static int resolve_mesh(ycge_ctx *c, MeshStore &m) {
+    if (!m.pending) return 0;
+    CK(c, cudaEventSynchronize(m.pending));
+    const DbCounters cnt = m.pending_host->cnt;
+    m.root = m.pending_host->root;
+    cudaEventDestroy(m.pending); m.pending = nullptr;
+    cudaFreeHost(m.pending_host); m.pending_host = nullptr;
+    if (cnt.done_items != m.n_tris) return fail(c, YCGE_ERR_CUDA, "device BVH build did not place every triangle");
+    m.n_pairs = cnt.n_nodes > 1 ? (int)(cnt.n_nodes - 1) / 2 : 0; // a full binary tree: inner = (nodes - 1) / 2
+    m.sort_fallbacks = cnt.fallbacks;
+    return 0;
+}
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 // the same tree, built on the device (bvh_device.cuh).  Everything is enqueued on the context's stream; the
 // host only waits for the 32-byte root record (the object table of ycge_scene_upload carries the root box by value).
@@ -1144,21 +1162,22 @@ YCGE_API int ycge_mesh_build_device(ycge_ctx *c, int32_t id, int32_t n, const fl
     db_emit_kernel<<<div_up(2 * n, 256), 256, 0, s>>>(a);
     db_tris_kernel<<<div_up(n, 256), 256, 0, s>>>(a);
     CK(c, cudaGetLastError());
-    TreeRoot root;
-    DbCounters cnt;
-    CK(c, cudaMemcpyAsync(&root, d_root, sizeof root, cudaMemcpyDeviceToHost, s));
-    CK(c, cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, s));
-    CK(c, cudaStreamSynchronize(s));
+    // root record and counters: to pinned memory behind an event; whoever needs them first waits (ycge_scene_upload,
+    // ycge_mesh_debug_read): the call returns with the build still running
+    CK(c, cudaHostAlloc((void **)&m->pending_host, sizeof(MeshStore::Pending), cudaHostAllocDefault));
+    CK(c, cudaEventCreateWithFlags(&m->pending, cudaEventDisableTiming));
+    CK(c, cudaMemcpyAsync(&m->pending_host->root, d_root, sizeof(TreeRoot), cudaMemcpyDeviceToHost, s));
+    CK(c, cudaMemcpyAsync(&m->pending_host->cnt, d_cnt, sizeof(DbCounters), cudaMemcpyDeviceToHost, s));
+    CK(c, cudaEventRecord(m->pending, s));
+    m->material = *material; m->n_tris = n;
     if (timing) {
+        CK(c, cudaStreamSynchronize(s));
+        const DbCounters &cnt = m->pending_host->cnt;
         float t01 = 0, t12 = 0;
         cudaEventElapsedTime(&t01, e0, e1); cudaEventElapsedTime(&t12, e1, e2);
         fprintf(stderr, "ycge_mesh_build_device: %d triangles: items %.3f ms, build %.3f ms, enqueue->done %.3f ms host, nodes %u, fallbacks %u\n", n, t01, t12, now_ms() - h0, cnt.n_nodes, cnt.fallbacks);
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     }
-    if (cnt.done_items != n) return fail(c, YCGE_ERR_CUDA, "device BVH build did not place every triangle");
-    m->root = root; m->material = *material; m->n_tris = n;
-    m->n_pairs = cnt.n_nodes > 1 ? (int)(cnt.n_nodes - 1) / 2 : 0; // a full binary tree: inner = (nodes - 1) / 2
-    m->sort_fallbacks = cnt.fallbacks;
     c->meshes[id] = std::move(m);
     c->have_scene = false; // object table must be rebuilt
     return 0;
@@ -1172,6 +1191,7 @@ YCGE_API int ycge_mesh_debug_read(ycge_ctx *c, int32_t id, int32_t what, void *d
     auto it = c->meshes.find(id);
     if (it == c->meshes.end()) return fail(c, YCGE_ERR_INVALID, "no such mesh");
     MeshStore &m = *it->second;
+    { int rc = resolve_mesh(c, m); if (rc) return rc; }
     const void *src = nullptr;
     size_t need = 0;
     switch (what) {
@@ -1294,6 +1314,7 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) try {
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     c->have_scene = false;
+    for (auto &kv : c->meshes) { int rc = resolve_mesh(c, *kv.second); if (rc) return rc; } // device builds in flight: their root boxes are needed now
     // materials: the scene's table, then one entry per uploaded mesh
     std::vector<float4> mats;
     std::vector<DevTexture> dtex;

@@ -112,6 +112,9 @@ namespace ConsoleGame.RayTracing
         [DllImport(Lib)] private static extern IntPtr ycge_last_error(IntPtr ctx);
         [DllImport(Lib)] private static extern int ycge_resize(IntPtr ctx, int fbW, int fbH, int ss);
         [DllImport(Lib)] private static extern int ycge_mesh_upload_soa(IntPtr ctx, int id, ref YMeshSoa mesh);
+        // optional (SURVEY 8f-2): the same MeshBVH, node for node, built on the GPU from the raw triangle list (n x 9 floats: A, B, C);
+        // a loader that knows this renderer is active may skip `new MeshBVH(tris)` and call this instead of ycge_mesh_upload_soa
+        [DllImport(Lib)] private static extern int ycge_mesh_build_device(IntPtr ctx, int id, int nTris, [In] float[] abc, ref YMaterial material);
         [DllImport(Lib)] private static extern int ycge_volume_upload(IntPtr ctx, int id, ref YVolume vol);
         [DllImport(Lib)] private static extern int ycge_scene_upload(IntPtr ctx, ref YScene scene);
         [DllImport(Lib)] private static extern int ycge_lights_update(IntPtr ctx, int n, [In] YLight[] lights);
