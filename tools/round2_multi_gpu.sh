@@ -17,5 +17,6 @@ except Exception as e:
     print(tag, "FAILED", e)
 PY
 }
-run dragon
+if [ "${ONLY:-}" != "second" ]; then run dragon; fi
+if [ "${ONLY:-}" = "first" ]; then exit 0; fi
 if [ "$N" = "8" ]; then run c5_dragon_4k --scene dragon --fb 480x135 --ss 8; else run c4_voxel_world --scene voxel_world --fb 320x90 --ss 8; fi

@@ -90,6 +90,15 @@ struct ycge_ctx {
     DevBuf<float4> cur, gnd0, gnd1, gas0, gas1, hist, sa, sb;
     DevBuf<unsigned long long> chain_trace;
     DevBuf<unsigned char> db_scratch; // device BVH build (ycge_mesh_build_device)
+    // FRONT-only frames (ycge_frame_front): the trace of a frame depends on nothing of the frame before it -- only its TAA does
+    // -- so it runs on its own stream (one per frame parity) into its own radiance plane, guide set (three of them) and
+    // counters, ordered by events: trace(f) waits for TAA(f-2), TAA(f) for trace(f) and, by stream order, TAA(f-1)
+    bool front_ahead = true, front_ahead_ready = false;
+    cudaStream_t trace_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_trace_done[2] = {nullptr, nullptr}, ev_taa_done[2] = {nullptr, nullptr};
+    DevBuf<float4> cur_b, gnd2, gas2;
+    DevBuf<TraceCounters> counters_b;
+    TraceCounters *counters_last = nullptr; // the counters of the frame traced last
     DevBuf<unsigned char> ansi;       // device ANSI byte stream (ycge_ansi_emit)
     DevBuf<unsigned int> ansi_rows;   // [rows] lengths, [rows] offsets, [1] total
     DevBuf<float4> pre; // in-place à-trous pass: 25 planes of per-tap precomputed terms / guide weights
@@ -249,9 +258,15 @@ SlotView slot_view(ycge_ctx *c, int k) {
     ycge_ctx::Slot &s = *c->slots[k - 1];
     return SlotView{s.sa.p, s.sb.p, &s.pre, s.logs.p, s.logs.n, s.st, s.front_done, s.fin_done, s.host_done};
 }
-int n_gsets(const ycge_ctx *c) { return std::max(2, c->n_slots); }
-float4 *gnd_of(ycge_ctx *c, int g) { return g == 0 ? c->gnd0.p : (g == 1 ? c->gnd1.p : c->slots[g - 1]->gnd.p); }
-float4 *gas_of(ycge_ctx *c, int g) { return g == 0 ? c->gas0.p : (g == 1 ? c->gas1.p : c->slots[g - 1]->gas.p); }
+int n_gsets(const ycge_ctx *c) { return c->front_ahead_ready ? 3 : std::max(2, c->n_slots); }
+float4 *gnd_of(ycge_ctx *c, int g) { return g == 0 ? c->gnd0.p : (g == 1 ? c->gnd1.p : (c->front_ahead_ready ? c->gnd2.p : c->slots[g - 1]->gnd.p)); }
+float4 *gas_of(ycge_ctx *c, int g) { return g == 0 ? c->gas0.p : (g == 1 ? c->gas1.p : (c->front_ahead_ready ? c->gas2.p : c->slots[g - 1]->gas.p)); }
+// every wait for "the context's stream" also covers the trace streams of FRONT-only frames
+cudaError_t sync_ctx_streams(ycge_ctx *c) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) if (c->trace_stream[k]) e = cudaStreamSynchronize(c->trace_stream[k]);
+    return e;
+}
 
 // ---- reference SoA tree -> pair nodes (device_types.h) ------------------------------------------------------
 struct TreeView {
@@ -362,7 +377,7 @@ int alloc_slots(ycge_ctx *c, int n) {
     }
     c->n_slots = std::max(1, n);
     c->last_fin = nullptr;
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     return 0;
 }
 
@@ -417,7 +432,13 @@ int set_geometry(ycge_ctx *c, int fb_w, int fb_h, int ss, int tile_row0, int til
     if (tile_row0 + tile_rows > fb_h) return fail(c, YCGE_ERR_INVALID, "tile exceeds framebuffer");
     c->tile_row0 = tile_row0; c->tile_rows = tile_rows;
     c->sharded = !(tile_row0 == 0 && tile_rows == fb_h);
-    return alloc_planes(c);
+    int rc = alloc_planes(c);
+    if (rc == 0 && c->front_ahead_ready) { // the extra planes of FRONT-only frames follow the geometry (the caller has synchronised the device)
+        const size_t px = (size_t)c->W * c->H;
+        CK(c, c->cur_b.alloc(px)); CK(c, c->gnd2.alloc(px)); CK(c, c->gas2.alloc(px));
+        CK(c, cudaMemset(c->gnd2.p, 0, px * sizeof(float4))); CK(c, cudaMemset(c->gas2.p, 0, px * sizeof(float4)));
+    }
+    return rc;
 }
 
 void normalize3(float v[3]) { // Vec3.Normalized
@@ -484,6 +505,27 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
     if (!front_only) for (int k = K - 1; k >= 0; k--) halo_after[k] = halo_after[k + 1] + 2 * (1 << k); // FRONT only: the passes run elsewhere
     auto range = [&](int halo, int &a, int &b) { a = std::max(0, ty0 - halo); b = std::min(H, ty1 + halo); };
 
+    // FRONT-only frames: the trace on its own stream (see the members)
+    const bool ahead = front_only && c->front_ahead && !c->want_stats && !c->debug_rays && c->n_slots <= 1;
+    if (ahead && !c->front_ahead_ready) {
+        CK(c, cudaDeviceSynchronize());
+        int lo = 0, hi = 0;
+        CK(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int k = 0; k < 2; k++) {
+            CK(c, cudaStreamCreateWithPriority(&c->trace_stream[k], cudaStreamNonBlocking, hi));
+            CK(c, cudaEventCreateWithFlags(&c->ev_trace_done[k], cudaEventDisableTiming));
+            CK(c, cudaEventCreateWithFlags(&c->ev_taa_done[k], cudaEventDisableTiming));
+        }
+        const size_t px = (size_t)W * H;
+        CK(c, c->cur_b.alloc(px)); CK(c, c->gnd2.alloc(px)); CK(c, c->gas2.alloc(px)); CK(c, c->counters_b.alloc(1));
+        CK(c, cudaMemset(c->gnd2.p, 0, px * sizeof(float4))); CK(c, cudaMemset(c->gas2.p, 0, px * sizeof(float4)));
+        c->front_ahead_ready = true;
+    }
+    const int fp = (int)(frame & 1);
+    cudaStream_t ts = ahead ? c->trace_stream[fp] : s;
+    float4 *cur_plane = (ahead && fp) ? c->cur_b.p : c->cur.p;
+    TraceCounters *cnt_dev = (ahead && fp) ? c->counters_b.p : c->counters.p;
+    c->counters_last = cnt_dev;
     // slot and guide set of this frame; `parity` selects the guide set the trace kernel writes (img.gnd/gas[parity])
     const int slot = (int)(frame % c->n_slots), gset = (int)(frame % n_gsets(c)), gprev = c->last_gset == gset ? (gset + 1) % n_gsets(c) : c->last_gset;
     c->cur_slot = slot; c->cur_gset = gset;
@@ -493,11 +535,12 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
     else if (c->last_fin) { CK(c, cudaStreamWaitEvent(s, c->last_fin, 0)); c->last_fin = nullptr; } // a synchronous frame after pipelined ones
     const int parity = 0;
     ImagePlanes img;
-    img.cur = c->cur.p; img.gnd[0] = gnd_of(c, gset); img.gnd[1] = gnd_of(c, gprev); img.gas[0] = gas_of(c, gset); img.gas[1] = gas_of(c, gprev);
+    img.cur = cur_plane; img.gnd[0] = gnd_of(c, gset); img.gnd[1] = gnd_of(c, gprev); img.gas[0] = gas_of(c, gset); img.gas[1] = gas_of(c, gprev);
     img.hist = c->hist.p; img.sa = sv.sa; img.sb = sv.sb; img.prim = c->prim.p; img.rays = c->debug_rays ? c->rays_dbg.p : nullptr;
 
     int launches = 0;
-    CK(c, cudaEventRecord(c->ev[0], s));
+    if (ahead) CK(c, cudaStreamWaitEvent(ts, c->ev_taa_done[fp], 0)); // TAA of frame f-2 (and, by its stream's order, the copies of frame f-3) has left this radiance plane / guide set
+    CK(c, cudaEventRecord(c->ev[0], ts));
     c->dn.early_reset = false;
     if (c->sharded && c->peers && K >= 2) {
         // Peer hand-off: the output buffer of the first in-place iteration (it = 1: OLD = scratchA, NEW = scratchB) is free
@@ -510,7 +553,7 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
         if (c->has_above) { peer_signal_kernel<<<1, 1, 0, s>>>(c->above_flags, (int)frame); launches++; }
         c->dn.early_reset = true;
     }
-    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(TraceCounters), s));
+    CK(c, cudaMemsetAsync(cnt_dev, 0, sizeof(TraceCounters), ts));
     { // K1
         int a, b; range(halo_after[0] + 1, a, b);
         fc.y0 = a; fc.y1 = b;
@@ -537,27 +580,28 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
             const int refill_min = getenv("YCGE_STREAM_REFILL") ? atoi(getenv("YCGE_STREAM_REFILL")) : 32; // development aid; see trace_stream.cuh
             const int gs = std::min(c->want_stats ? c->stream_ctas_stats : c->stream_ctas, div_up(n_tiles, 4));
             switch ((c->want_stats ? 1 : 0) | (c->trace_lean ? 2 : 0)) { // MODE (trace.cuh): bit 0 event counters, bit 1 lean scene
-                case 0: trace_stream_kernel<0><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
-                case 1: trace_stream_kernel<1><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
-                case 2: trace_stream_kernel<2><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
-                default: trace_stream_kernel<3><<<gs, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p, refill_min); break;
+                case 0: trace_stream_kernel<0><<<gs, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p, refill_min); break;
+                case 1: trace_stream_kernel<1><<<gs, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p, refill_min); break;
+                case 2: trace_stream_kernel<2><<<gs, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p, refill_min); break;
+                default: trace_stream_kernel<3><<<gs, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p, refill_min); break;
             }
         } else {
             dim3 grid(div_up(W, 16), div_up(b - a, 8));
             switch ((c->want_stats ? 1 : 0) | (c->trace_lean ? 2 : 0)) {
-                case 0: trace_kernel<0><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
-                case 1: trace_kernel<1><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
-                case 2: trace_kernel<2><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
-                default: trace_kernel<3><<<grid, 128, 0, s>>>(c->ds, fc, tp, img, parity, c->counters.p, c->totals.p); break;
+                case 0: trace_kernel<0><<<grid, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p); break;
+                case 1: trace_kernel<1><<<grid, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p); break;
+                case 2: trace_kernel<2><<<grid, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p); break;
+                default: trace_kernel<3><<<grid, 128, 0, ts>>>(c->ds, fc, tp, img, parity, cnt_dev, c->totals.p); break;
             }
         }
         launches++;
     }
-    CK(c, cudaEventRecord(c->ev[1], s));
+    CK(c, cudaEventRecord(c->ev[1], ts));
+    if (ahead) { CK(c, cudaEventRecord(c->ev_trace_done[fp], ts)); CK(c, cudaStreamWaitEvent(s, c->ev_trace_done[fp], 0)); }
     { // K2
         int a, b; range(halo_after[0], a, b);
         TaaArgs t;
-        t.cur = c->cur.p; t.gnd_now = img.gnd[parity]; t.gnd_prev = img.gnd[parity ^ 1]; t.gas_now = img.gas[parity]; t.gas_prev = img.gas[parity ^ 1];
+        t.cur = cur_plane; t.gnd_now = img.gnd[parity]; t.gnd_prev = img.gnd[parity ^ 1]; t.gas_now = img.gas[parity]; t.gas_prev = img.gas[parity ^ 1];
         t.hist = c->hist.p; t.W = W; t.H = H; t.y0 = a; t.y1 = b; t.reset = reset ? 1 : 0;
         float al = c->P.taa_alpha; al = al < 0.0f ? 0.0f : (al > 1.0f ? 1.0f : al); // :305
         t.alpha = al; t.pad = c->P.luminance_pad;
@@ -566,6 +610,7 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
         c->taa_valid = true;
     }
     CK(c, cudaEventRecord(c->ev[2], s));
+    if (ahead) CK(c, cudaEventRecord(c->ev_taa_done[fp], s));
     if (front_only) { // the frame's à-trous passes, exposure and cells run on another rank (ycge_back_*); taa.CommitCamera :266
         c->launches_last = launches;
         c->last_gset = gset;
@@ -876,7 +921,7 @@ int read_cells_impl(ycge_ctx *c, ycge_cell *out, int stride) {
     if (stride < c->fbW) return fail(c, YCGE_ERR_INVALID, "stride smaller than fb_w");
     CK(c, cudaMemcpy2DAsync(out, (size_t)stride * sizeof(ycge_cell), c->cells.p, (size_t)c->fbW * sizeof(ycge_cell), (size_t)c->fbW * sizeof(ycge_cell),
                             (size_t)c->tile_rows, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     return wave_check(c);
 }
 
@@ -947,6 +992,7 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) try {
         c->wave_err_host = h;
         CK(nullptr, cudaHostGetDevicePointer((void **)&c->wave_err_dev, h, 0));
     }
+    if (const char *e = getenv("YCGE_FRONT_AHEAD")) c->front_ahead = atoi(e) != 0; // 0: the trace of a FRONT-only frame stays on the context's stream
     if (const char *e = getenv("YCGE_WAVE")) c->use_wave = atoi(e) != 0; // 1 = the systolic wavefront kernels (wavefront.cuh)
     if (const char *e = getenv("YCGE_WAVE_CLUSTER")) c->wave_cluster = atoi(e) > 1 ? YCGE_WF_CLUSTER : 1; // opt-in: thread-block clusters of 8 bands
     if (const char *e = getenv("YCGE_WAVE_PAD_SMEM")) c->wave_pad_smem = atoi(e);                          // development aid
@@ -969,7 +1015,7 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) try {
         div_selftest_kernel<<<(0x7F800000u >> 8) + 1, 256, 0, c->stream>>>(e, mm.p);
         unsigned int h[8] = {1, 1, 1, 1, 1, 1, 1, 1};
         CK(nullptr, cudaMemcpyAsync(h, mm.p, 32, cudaMemcpyDeviceToHost, c->stream));
-        CK(nullptr, cudaStreamSynchronize(c->stream));
+        CK(nullptr, sync_ctx_streams(c.get()));
         c->fast_div = (h[0] | h[1] | h[2] | h[3] | h[4]) == 0;
         if (!(e.dc < 1e30f && e.dn < 1e30f && e.dz < 1e30f && e.da < 1e30f)) c->fast_div = false;
     }
@@ -977,7 +1023,7 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) try {
     for (int k = 0; k < 5; k++) c->ansi_th[k] = ansi_threshold(bounds[k]);
     int rc = set_geometry(c.get(), cfg->fb_w, cfg->fb_h, cfg->ss, cfg->tile_row0, cfg->tile_rows);
     if (rc != 0) { tl_error = c->err; return rc; }
-    CK(nullptr, cudaStreamSynchronize(c->stream));
+    CK(nullptr, sync_ctx_streams(c.get()));
     memset(&c->ds, 0, sizeof c->ds);
     *out = c.release();
     return 0;
@@ -996,6 +1042,11 @@ YCGE_API void ycge_destroy(ycge_ctx *ctx) {
     if (ctx->host_done0) cudaEventDestroy(ctx->host_done0);
     for (auto &p : ctx->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->trace_stream[k]) { cudaStreamSynchronize(ctx->trace_stream[k]); cudaStreamDestroy(ctx->trace_stream[k]); }
+        if (ctx->ev_trace_done[k]) cudaEventDestroy(ctx->ev_trace_done[k]);
+        if (ctx->ev_taa_done[k]) cudaEventDestroy(ctx->ev_taa_done[k]);
+    }
     if (ctx->e_fork) cudaEventDestroy(ctx->e_fork);
     if (ctx->e_join) cudaEventDestroy(ctx->e_join);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1025,7 +1076,7 @@ YCGE_API int ycge_set_stream(ycge_ctx *c, void *cuda_stream) try {
     if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_set_stream is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     { int rc = join_pipeline(c); if (rc) return rc; }
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)cuda_stream;
     return 0;
@@ -1204,7 +1255,7 @@ YCGE_API int ycge_mesh_debug_read(ycge_ctx *c, int32_t id, int32_t what, void *d
     if (!dst) { *bytes = need; return 0; }
     if (*bytes < need) return fail(c, YCGE_ERR_INVALID, "destination too small");
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     if (what == 3) memcpy(dst, &m.root, need);
     else if (need) CK(c, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
     *bytes = need;
@@ -1242,7 +1293,7 @@ YCGE_API int ycge_volume_upload(ycge_ctx *c, int32_t id, const ycge_volume *v) t
     CK(c, pal.upload(vs->palette, c->stream));
     voxel_pack_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(vs->raw_mat.p, vs->raw_meta.p, vs->vox.p, cap, pal.p, vs->n_ids, vs->levels, vs->def);
     CK(c, cudaGetLastError());
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     vs->raw_mat.release(); vs->raw_meta.release();
     vs->packed = true;
     d.vox = vs->vox.p;
@@ -1257,13 +1308,13 @@ YCGE_API int ycge_texture_upload(ycge_ctx *c, int32_t id, int32_t w, int32_t h, 
     if (!c || id < 0 || w < 0 || h < 0 || ((size_t)w * h > 0 && !rgba)) return fail(c, YCGE_ERR_INVALID, "bad argument");
     if ((size_t)w * h > (size_t)0x7fffffff) return fail(c, YCGE_ERR_LIMIT, "texture larger than 2^31 texels (the reference indexes with int)");
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     std::unique_ptr<TextureStore> t(new TextureStore());
     t->w = w; t->h = h;
     if ((size_t)w * h > 0) {
         CK(c, t->px.alloc((size_t)w * h));
         CK(c, cudaMemcpyAsync(t->px.p, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, sync_ctx_streams(c));
     }
     c->textures[id] = std::move(t);
     c->have_scene = false; // the texture table is rebuilt by ycge_scene_upload
@@ -1312,7 +1363,7 @@ YCGE_API int ycge_scene_upload(ycge_ctx *c, const ycge_scene *s) try {
     if (s->n_objects < 0 || s->n_lights < 0 || s->n_materials < 0) return fail(c, YCGE_ERR_INVALID, "negative count");
     if ((s->n_objects > 0 && !s->objects) || (s->n_lights > 0 && !s->lights) || (s->n_materials > 0 && !s->materials)) return fail(c, YCGE_ERR_INVALID, "a count is positive but its array is NULL");
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     c->have_scene = false;
     for (auto &kv : c->meshes) { int rc = resolve_mesh(c, *kv.second); if (rc) return rc; } // device builds in flight: their root boxes are needed now
     // materials: the scene's table, then one entry per uploaded mesh
@@ -1458,10 +1509,10 @@ YCGE_API int ycge_lights_update(ycge_ctx *c, int32_t n, const ycge_light *l) try
         for (int k = 0; k < 3; k++) { lights[i].pos[k] = l[i].pos[k]; lights[i].color[k] = l[i].color[k]; }
         lights[i].intensity = l[i].intensity; lights[i].pad = 0.0f;
     }
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     if ((size_t)n > c->s_lights.n) CK(c, c->s_lights.alloc((size_t)n));
     if (n) CK(c, cudaMemcpyAsync(c->s_lights.p, lights.data(), (size_t)n * sizeof(DevLight), cudaMemcpyHostToDevice, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     c->ds.lights = c->s_lights.p; c->ds.n_lights = n;
     return 0;
 } YCGE_CATCH
@@ -1534,7 +1585,7 @@ YCGE_API int ycge_stash_config(ycge_ctx *c, int32_t n_slots) try {
     if (c && c->group) return fail(c, YCGE_ERR_INVALID, "ycge_stash_config is not available on a multi-GPU context (ycge_config.n_devices >= 2)");
     if (!c || n_slots < 0 || n_slots > 64) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     c->stash.clear();
     const size_t rows = (size_t)c->tile_rows * 2 * c->ss;
     for (int k = 0; k < n_slots; k++) {
@@ -1593,7 +1644,7 @@ YCGE_API int ycge_peer_attach(ycge_ctx *c, const ycge_peer *above, const ycge_pe
             return fail(c, YCGE_ERR_INVALID, "tile too small for the peer hand-off (fewer pixel rows than the in-place pass reaches); use the send/recv hand-off of ycge_frame_halo");
     }
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     for (auto &p : c->ipc_opened) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
     c->has_above = above != nullptr; c->has_below = below != nullptr;
     c->above_flags = nullptr; c->below_sa = c->below_sb = nullptr;
@@ -1783,7 +1834,7 @@ YCGE_API int ycge_wait(ycge_ctx *c) try {
     if (c && c->group) return group_wait(c);
     if (!c) return fail(nullptr, YCGE_ERR_INVALID, "ctx is NULL");
     { int rc = join_pipeline(c); if (rc) return rc; }
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     return wave_check(c);
 } YCGE_CATCH
 YCGE_API int ycge_read_cells(ycge_ctx *c, ycge_cell *out, int32_t stride_cells) try {
@@ -1835,7 +1886,7 @@ YCGE_API int ycge_debug_read(ycge_ctx *c, int32_t kind, void *dst, size_t bytes)
     if (!c || !dst) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     { int rc = join_pipeline(c); if (rc) return rc; }
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     size_t n = (size_t)c->W * c->H;
     const void *src = nullptr;
     size_t need = 0;
@@ -1889,10 +1940,10 @@ YCGE_API int ycge_get_stats(ycge_ctx *c, ycge_stats *out) try {
     if (!c || !out) return fail(c, YCGE_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
     { int rc = join_pipeline(c); if (rc) return rc; }
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     memset(out, 0, sizeof *out);
     TraceCounters tc;
-    CK(c, cudaMemcpy(&tc, c->counters.p, sizeof tc, cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(&tc, c->counters_last ? c->counters_last : c->counters.p, sizeof tc, cudaMemcpyDeviceToHost));
     ExposureState es;
     CK(c, cudaMemcpy(&es, c->expo.p, sizeof es, cudaMemcpyDeviceToHost));
     TraceTotals tt;
@@ -1944,7 +1995,7 @@ YCGE_API int ycge_rng_kat(ycge_ctx *c, int32_t which, int32_t n, const int32_t *
     CK(c, cudaMemcpy(df.p, frame, n * sizeof(long long), cudaMemcpyHostToDevice));
     rng_kat_kernel<<<div_up(n, 128), 128, 0, c->stream>>>(which, n, dx.p, dy.p, df.p, n_draws, db.p, dsd.p, c->P.seed_salt);
     CK(c, cudaGetLastError());
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sync_ctx_streams(c));
     CK(c, cudaMemcpy(out_bits, db.p, (size_t)n * n_draws * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     CK(c, cudaMemcpy(out_seed, dsd.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
