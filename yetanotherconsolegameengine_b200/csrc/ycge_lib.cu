@@ -93,7 +93,7 @@ struct ycge_ctx {
     // FRONT-only frames (ycge_frame_front): the trace of a frame depends on nothing of the frame before it -- only its TAA does
     // -- so it runs on its own stream (one per frame parity) into its own radiance plane, guide set (three of them) and
     // counters, ordered by events: trace(f) waits for TAA(f-2), TAA(f) for trace(f) and, by stream order, TAA(f-1)
-    bool front_ahead = true, front_ahead_ready = false;
+    bool front_ahead = true, front_ahead_force = false, front_ahead_ready = false;
     cudaStream_t trace_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_trace_done[2] = {nullptr, nullptr}, ev_taa_done[2] = {nullptr, nullptr};
     DevBuf<float4> cur_b, gnd2, gas2;
@@ -506,7 +506,10 @@ int frame_begin_impl(ycge_ctx *c, bool front_only = false) {
     auto range = [&](int halo, int &a, int &b) { a = std::max(0, ty0 - halo); b = std::min(H, ty1 + halo); };
 
     // FRONT-only frames: the trace on its own stream (see the members)
-    const bool ahead = front_only && c->front_ahead && !c->want_stats && !c->debug_rays && c->n_slots <= 1;
+    // Worth it where the tile's trace leaves the GPU idle (a third of the frame or less: 4 and 8 GPUs, +22 % / +50 % at 8); on
+    // half-frame tiles the traces fill the GPU and overlapping them only adds contention (2 GPUs: 645 -> 571 frames/s)
+    const bool ahead = front_only && c->front_ahead && !c->want_stats && !c->debug_rays && c->n_slots <= 1 &&
+                       (c->front_ahead_force || c->front_ahead_ready || c->tile_rows * 3 <= c->fbH);
     if (ahead && !c->front_ahead_ready) {
         CK(c, cudaDeviceSynchronize());
         int lo = 0, hi = 0;
@@ -992,7 +995,7 @@ YCGE_API int ycge_create(const ycge_config *cfg, ycge_ctx **out) try {
         c->wave_err_host = h;
         CK(nullptr, cudaHostGetDevicePointer((void **)&c->wave_err_dev, h, 0));
     }
-    if (const char *e = getenv("YCGE_FRONT_AHEAD")) c->front_ahead = atoi(e) != 0; // 0: the trace of a FRONT-only frame stays on the context's stream
+    if (const char *e = getenv("YCGE_FRONT_AHEAD")) { c->front_ahead = atoi(e) != 0; c->front_ahead_force = atoi(e) > 1; } // 0: the trace of a FRONT-only frame stays on the context's stream; 2: own streams whatever the tile size
     if (const char *e = getenv("YCGE_WAVE")) c->use_wave = atoi(e) != 0; // 1 = the systolic wavefront kernels (wavefront.cuh)
     if (const char *e = getenv("YCGE_WAVE_CLUSTER")) c->wave_cluster = atoi(e) > 1 ? YCGE_WF_CLUSTER : 1; // opt-in: thread-block clusters of 8 bands
     if (const char *e = getenv("YCGE_WAVE_PAD_SMEM")) c->wave_pad_smem = atoi(e);                          // development aid
