@@ -568,17 +568,18 @@ def main():
         kname, kbytes, kms = "atrous_wave_kernel (wavefront of the in-place a-trous iteration)", W * rows_here * 53, stage_ms["ms_atrous_chain"]
     achieved = kbytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
     # DRAM traffic of that kernel per launch: only from an `ncu --set full` capture of THIS build of the library and this
-    # command (tools/summarize_ncu.py records the sha256 of libycge.so beside dram__bytes_read.sum + dram__bytes_write.sum);
+    # command (tools/summarize_ncu.py records the sha256 of the library's SOURCES -- nvcc's output is not byte-reproducible -- beside
+    # dram__bytes_read.sum + dram__bytes_write.sum);
     # a capture of any other build is not this run's traffic -> null
     traffic, traffic_src = None, None
     try:
         import hashlib
         cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        sha = hashlib.sha256(open(api.LIB_PATH, "rb").read()).hexdigest()
-        if n == 1 and cap.get("lib_sha256") == sha and cap.get("workload") == f"{args.scene} {fb_w}x{fb_h} ss={ss}":
+        sha = api.library_source_digest()
+        if n == 1 and cap.get("source_sha256") == sha and cap.get("workload") == f"{args.scene} {fb_w}x{fb_h} ss={ss}":
             key = next(k for k in cap["kernels"] if k.startswith("trace_" if kname == "trace_kernel" else kname.split(" ")[0]))
             traffic = float(cap["kernels"][key]["dram_bytes"])
-            traffic_src = "profiles/ncu_traffic.json (%s; dram__bytes_read.sum + dram__bytes_write.sum of %s, same libycge.so sha256)" % (cap.get("captured", "?"), key)
+            traffic_src = "profiles/ncu_traffic.json (%s; dram__bytes_read.sum + dram__bytes_write.sum of %s, same library sources, sha256 %s)" % (cap.get("captured", "?"), key, sha[:12])
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -65,3 +65,20 @@ def test_random_patterns():
         check([i >= n // 3 for i in range(n)])
         check([i < n // 3 for i in range(n)])
         check([bool(i & 1) for i in range(n)])
+
+
+def test_device_introsort_equals_the_host_introsort(tmp_path):
+    """The Array.Sort fallback of the device builder (DbIntroSort, one thread) against the host builder's NetIntroSort --
+    itself pinned against a Python transcription of .NET's introsort in tests/test_bvh_builder_literal.py -- on the CPU:
+    the same permutation, ties and NaNs included (tests/db_introsort_check.cu, host code compiled by nvcc)."""
+    import os
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "db_introsort_check")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, os.path.join(here, "db_introsort_check.cu")], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "same permutation -> ok" in r.stdout, r.stdout[-1000:]

@@ -65,7 +65,9 @@ if os.path.exists(rep):
     import hashlib
     to_b = lambda v: float(v.split()[0]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[v.split()[1]]
     lib = os.path.join(ROOT, "yetanotherconsolegameengine_b200", "libycge.so")
-    traffic = {"lib_sha256": hashlib.sha256(open(lib, "rb").read()).hexdigest(), "workload": "dragon 480x135 ss=4", "captured": f"profiles/{tag}_ncu_full.json, ncu --set full --clock-control none of `python bench.py --steps 2 --warmup 3`",
+    sys.path.insert(0, ROOT)
+    from yetanotherconsolegameengine_b200 import api as _api
+    traffic = {"lib_sha256": hashlib.sha256(open(lib, "rb").read()).hexdigest(), "source_sha256": _api.library_source_digest(), "workload": "dragon 480x135 ss=4", "captured": f"profiles/{tag}_ncu_full.json, ncu --set full --clock-control none of `python bench.py --steps 2 --warmup 3`",
                "kernels": {k: {"dram_bytes": to_b(c[-1]["dram__bytes_read.sum"]) + to_b(c[-1]["dram__bytes_write.sum"])} for k, c in js.items() if "dram__bytes_read.sum" in c[-1]}}
     json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
 for f in (f"bench_{tag}.json", f"clocks_{tag}.csv"):

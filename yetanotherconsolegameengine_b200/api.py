@@ -128,6 +128,22 @@ _lib = None
 _host = None
 
 
+def library_source_digest() -> str:
+    """sha256 over the sources libycge.so is built from (csrc/, include/, the Makefile), in a fixed order.  Identifies a BUILD
+    of the library for profiles/ncu_traffic.json: nvcc's output is not byte-reproducible (internal-linkage symbols carry a
+    per-compilation id), the sources are."""
+    import hashlib
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    files = sorted([os.path.join(here, "csrc", f) for f in os.listdir(os.path.join(here, "csrc"))] +
+                   [os.path.join(root, "include", f) for f in os.listdir(os.path.join(root, "include"))] + [os.path.join(here, "Makefile")])
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def load_lib() -> C.CDLL:
     """Load libycge.so.  Raises (never falls back) if the extension was not built."""
     global _lib

@@ -103,10 +103,11 @@ __global__ void db_init_kernel(DbArgs a) {
 }
 
 // System.Array.Sort on a range of the index array keyed by one centroid axis: dotnet/runtime's introsort as restated in
-// bvh_build.hpp (NetIntroSort), item swaps become index swaps.  One thread.
+// bvh_build.hpp (NetIntroSort), item swaps become index swaps.  One thread.  (__host__ as well: tests/test_bvh_device_partition.py
+// runs it on the CPU against NetIntroSort, permutation for permutation.)
 struct DbIntroSort {
     int *a_; const float *key_;
-    __device__ int cmp(int p, int q) const {
+    __host__ __device__ int cmp(int p, int q) const {
         const float x = key_[p], y = key_[q];
         if (x < y) return -1;
         if (x > y) return 1;
@@ -114,9 +115,9 @@ struct DbIntroSort {
         if (x != x) return (y != y) ? 0 : -1;
         return 1;
     }
-    __device__ void swp(int i, int j) { const int t = a_[i]; a_[i] = a_[j]; a_[j] = t; }
-    __device__ void order2(int i, int j) { if (cmp(a_[i], a_[j]) > 0) swp(i, j); }
-    __device__ void insertion(int lo, int n) {
+    __host__ __device__ void swp(int i, int j) { const int t = a_[i]; a_[i] = a_[j]; a_[j] = t; }
+    __host__ __device__ void order2(int i, int j) { if (cmp(a_[i], a_[j]) > 0) swp(i, j); }
+    __host__ __device__ void insertion(int lo, int n) {
         for (int i = 0; i + 1 < n; i++) {
             const int t = a_[lo + i + 1];
             int j = i;
@@ -124,7 +125,7 @@ struct DbIntroSort {
             a_[lo + j + 1] = t;
         }
     }
-    __device__ void sift(int lo, int i, int n) {
+    __host__ __device__ void sift(int lo, int i, int n) {
         const int d = a_[lo + i - 1];
         while (i <= n / 2) {
             int ch = 2 * i;
@@ -135,11 +136,11 @@ struct DbIntroSort {
         }
         a_[lo + i - 1] = d;
     }
-    __device__ void heap(int lo, int n) {
+    __host__ __device__ void heap(int lo, int n) {
         for (int i = n / 2; i >= 1; i--) sift(lo, i, n);
         for (int i = n; i > 1; i--) { swp(lo, lo + i - 1); sift(lo, 1, i - 1); }
     }
-    __device__ int partition(int lo, int n) {
+    __host__ __device__ int partition(int lo, int n) {
         const int hi = n - 1, mid = hi >> 1;
         order2(lo, lo + mid);
         order2(lo, lo + hi);
@@ -157,7 +158,7 @@ struct DbIntroSort {
         return l;
     }
     // the recursion of IntroSort on the right part, the loop on the left one; an explicit stack keeps it off the call stack
-    __device__ void run(int start, int count) {
+    __host__ __device__ void run(int start, int count) {
         if (count < 2) return;
         int lg = 0;
         for (unsigned v = (unsigned)count; v > 1; v >>= 1) lg++;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(YCGE_DB_THREADS) db_build_kernel(DbArgs a) {
     __shared__ float s_cmin[3], s_cmax[3];
     __shared__ int s_bcnt[3][YCGE_DB_BINS];
     __shared__ float s_blo[3][YCGE_DB_BINS][3], s_bhi[3][YCGE_DB_BINS][3];
-    __shared__ int s_split, s_axis, s_warp_sum[YCGE_DB_THREADS / 32], s_run, s_K, s_mid;
+    __shared__ int s_split, s_axis, s_warp_sum[YCGE_DB_THREADS / 32], s_run, s_K;
     __shared__ float s_origin, s_inv;
     const float INF = __int_as_float(0x7F800000);
     for (;;) {
