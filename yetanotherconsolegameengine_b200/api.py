@@ -129,18 +129,19 @@ _host = None
 
 
 def library_source_digest() -> str:
-    """sha256 over the sources libycge.so is built from (csrc/, include/, the Makefile), in a fixed order.  Identifies a BUILD
-    of the library for profiles/ncu_traffic.json: nvcc's output is not byte-reproducible (internal-linkage symbols carry a
-    per-compilation id), the sources are."""
+    """sha256 over the sources libycge.so is built from -- the prerequisites of `libycge.so` in the Makefile, in the order listed,
+    and the compiler flags (NVFLAGS).  Identifies a BUILD of the library for profiles/ncu_traffic.json: nvcc's output is not
+    byte-reproducible (internal-linkage symbols carry a per-compilation id), the sources are."""
     import hashlib
     here = os.path.dirname(os.path.abspath(__file__))
-    root = os.path.dirname(here)
-    files = sorted([os.path.join(here, "csrc", f) for f in os.listdir(os.path.join(here, "csrc"))] +
-                   [os.path.join(root, "include", f) for f in os.listdir(os.path.join(root, "include"))] + [os.path.join(here, "Makefile")])
+    mk = open(os.path.join(here, "Makefile")).read().replace("\\\n", " ")
+    deps = next(l for l in mk.splitlines() if l.startswith("libycge.so:")).split(":", 1)[1].split()
+    flags = next(l for l in mk.splitlines() if l.startswith("NVFLAGS"))
     h = hashlib.sha256()
-    for f in files:
+    h.update(flags.encode() + b"\0")
+    for f in deps:
         h.update(os.path.basename(f).encode() + b"\0")
-        h.update(open(f, "rb").read())
+        h.update(open(os.path.join(here, f), "rb").read())
     return h.hexdigest()
 
 
@@ -489,8 +490,10 @@ class CudaRaytraceRenderer:
     def Resize(self, fb_w: int, fb_h: int, super_sample: int):
         if self._h.ycgeh_renderer_resize(self.handle, fb_w, fb_h, super_sample) != 0:
             raise YcgeError(-1, self._h.ycgeh_last_error().decode())
+        whole = self.tile_row0 == 0 and self.tile_rows == self.fb_h
         self.fb_w, self.fb_h, self.ss = fb_w, fb_h, max(1, super_sample)
-        self.tile_row0, self.tile_rows = 0, fb_h
+        if whole:  # ycge_resize keeps the row tile of a sharded context (and refuses one that no longer fits)
+            self.tile_row0, self.tile_rows = 0, fb_h
 
     def TryFlipAndBlit(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Synchronous frame: returns the (tile_rows, fb_w) cell array (the Framebuffer's Chexels)."""

@@ -75,8 +75,8 @@ class ParallelSah {
         top_fallbacks_ += cut.fallbacks;
         if (depth < par_depth_) { // the two halves are disjoint: cut the left one on another thread
             std::thread other([&] { p->left = plan(arr, start, mid - start, depth + 1); });
+            struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } guard{other}; // joined also when the sibling call throws
             p->right = plan(arr, mid, start + count - mid, depth + 1);
-            other.join();
         } else {
             p->left = plan(arr, start, mid - start, depth + 1);
             p->right = plan(arr, mid, start + count - mid, depth + 1);
