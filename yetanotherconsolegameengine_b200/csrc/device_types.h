@@ -42,6 +42,7 @@ struct DevMesh {
 // 0 = empty (matId <= 0), else 1 + material index, i.e. materialLookup(mat, meta) resolved at upload.
 struct DevVolume {
     const uint8_t *vox;
+    const uint8_t *occ; // one byte per 8^3 brick: bit o = octant o (4^3 voxels, x>>2 | y>>2 << 1 | z>>2 << 2) holds a solid voxel
     int nx, ny, nz, nbx, nby, nbz;
     float min_corner[3];
     float voxel_size[3];

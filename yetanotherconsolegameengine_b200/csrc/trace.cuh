@@ -298,12 +298,18 @@ __device__ bool volume_hit(const DevVolume &g, const RayD &r, float tMin, float 
     float wireMax2 = g.wire_max_distance <= 0.0f ? -1.0f : g.wire_max_distance * g.wire_max_distance;
     float dirLen2 = dx * dx + dy * dy + dz * dz;
 
+    // The voxel itself is fetched only in octants (4^3 blocks) the occupancy byte of the brick marks solid: a ray through air
+    // takes the same steps and counts the same cells with one cached byte per brick instead of a fetch per cell.
+    int curBrick = -1;
+    unsigned occ = 0u;
     while (t <= tExit && t <= tMax) {
         if ((unsigned)ix < (unsigned)nx && (unsigned)iy < (unsigned)ny && (unsigned)iz < (unsigned)nz) {
             CNT_INC(cnt, dda);
             int brick = (((iz >> 3) * g.nby) + (iy >> 3)) * g.nbx + (ix >> 3);
-            int idx = brick * 512 + morton3(ix & 7, iy & 7, iz & 7);
-            int code = __ldg(g.vox + idx);
+            if (brick != curBrick) { curBrick = brick; occ = __ldg(g.occ + brick); }
+            int code = 0;
+            if ((occ >> ((((iz >> 2) & 1) << 2) | (((iy >> 2) & 1) << 1) | ((ix >> 2) & 1))) & 1u)
+                code = __ldg(g.vox + brick * 512 + morton3(ix & 7, iy & 7, iz & 7));
             if (code > 0) {
                 int normalAxis = lastAxis; // never < 0 here (lastAxis is resolved above), VolumeGrid.cs:161-166 is dead
                 float hitT = MaxF(t, tMin);

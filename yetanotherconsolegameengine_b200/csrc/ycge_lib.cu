@@ -65,6 +65,7 @@ struct TextureStore {
 };
 struct VolumeStore {
     DevBuf<uint8_t> vox;
+    DevBuf<uint8_t> occ; // occupancy byte per brick (voxel_occupancy_kernel)
     DevBuf<int> raw_mat, raw_meta; // kept until the scene (and so the material indices) is known
     std::vector<int> palette;
     int n_ids = 0, levels = 1, def = 0;
@@ -1296,10 +1297,14 @@ YCGE_API int ycge_volume_upload(ycge_ctx *c, int32_t id, const ycge_volume *v) t
     CK(c, pal.upload(vs->palette, c->stream));
     voxel_pack_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(vs->raw_mat.p, vs->raw_meta.p, vs->vox.p, cap, pal.p, vs->n_ids, vs->levels, vs->def);
     CK(c, cudaGetLastError());
+    CK(c, vs->occ.alloc(cap / 512));
+    voxel_occupancy_kernel<<<(unsigned)((cap / 64 + 255) / 256), 256, 0, c->stream>>>(vs->vox.p, vs->occ.p, cap / 64);
+    CK(c, cudaGetLastError());
     CK(c, sync_ctx_streams(c));
     vs->raw_mat.release(); vs->raw_meta.release();
     vs->packed = true;
     d.vox = vs->vox.p;
+    d.occ = vs->occ.p;
     c->volumes[id] = std::move(vs);
     c->have_scene = false;
     return 0;
