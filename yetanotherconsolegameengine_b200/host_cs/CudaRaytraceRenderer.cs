@@ -217,31 +217,51 @@ namespace ConsoleGame.RayTracing
             Check(ycge_globals_update(ctx, V(scene.BackgroundTop), V(scene.BackgroundBottom), V(scene.Ambient.Color), scene.Ambient.Intensity));
         }
 
-        /// Scene.RebuildBVH happened (geometry changed / scene switch): flatten again.  (RaytraceEntity.cs:234-246)
+        // What survives a re-sync of the objects (the C++ mirror's SceneExport does the same, host/ycge_host.cpp): the material table
+        // is append-only and de-duplicated by value -- a VolumeGrid's palette (37 materials, VoxelMaterialPalette.cs:48-98) and the
+        // one or two materials of every object would otherwise pass the library's limit of 255 voxel materials, and an index, once
+        // handed to ycge_volume_upload as part of a palette, must keep its meaning --; meshes, voxel grids and textures are uploaded
+        // once per object and found again by reference.
+        private readonly List<YMaterial> materials = new List<YMaterial>();
+        private readonly Dictionary<(float, float, float, float, float, float, float, float, float, float, float, float, float, int, float, float), int> materialIndex
+            = new Dictionary<(float, float, float, float, float, float, float, float, float, float, float, float, float, int, float, float), int>();
+        private readonly Dictionary<ConsoleGame.Renderer.Texture, int> texIds = new Dictionary<ConsoleGame.Renderer.Texture, int>();
+        private readonly Dictionary<Mesh, int> meshIds = new Dictionary<Mesh, int>();
+        private readonly Dictionary<VolumeGrid, int> volIds = new Dictionary<VolumeGrid, int>();
+
+        // new Texture(path) (Renderer/Texture.cs:25-49): the int[] pixels (RGBA bytes, row 0 first, :81-90) go to the device once per
+        // distinct Texture object; Material.DiffuseTexture becomes its id.  Needs one internal accessor, Texture.Pixels.
+        private int TexId(Material m)
+        {
+            if (m.DiffuseTexture == null) return -1;
+            if (!texIds.TryGetValue(m.DiffuseTexture, out int id))
+            {
+                id = texIds.Count;
+                Check(ycge_texture_upload(ctx, id, m.DiffuseTexture.width, m.DiffuseTexture.height, m.DiffuseTexture.Pixels));
+                texIds[m.DiffuseTexture] = id;
+            }
+            return id;
+        }
+        private YMaterial ToMaterialWithTexture(Material m) { var ym = ToMaterial(m); ym.TexId = TexId(m); return ym; }
+        private int AddMat(Material m)
+        {
+            YMaterial ym = ToMaterialWithTexture(m);
+            var key = (ym.AlbedoX, ym.AlbedoY, ym.AlbedoZ, ym.Reflectivity, ym.EmissionX, ym.EmissionY, ym.EmissionZ, ym.Transparency,
+                       ym.TransmissionX, ym.TransmissionY, ym.TransmissionZ, ym.Ior, ym.Specular, ym.TexId, ym.TexWeight, ym.UvScale);
+            if (!materialIndex.TryGetValue(key, out int idx)) { idx = materials.Count; materials.Add(ym); materialIndex[key] = idx; }
+            return idx;
+        }
+
+        /// Scene.RebuildBVH happened (geometry changed / scene switch, RaytraceEntity.cs:234-246; or an entity moved an object,
+        /// Scene.cs:121-127): the object records and the top-level tree are flattened again -- the cheap part.  A mesh, a voxel grid
+        /// or a texture the renderer has seen before is NOT uploaded again (a bobbing sphere rebuilds the tree every frame).
         public unsafe void UploadScene()
         {
-            var materials = new List<YMaterial>();
             var objects = new List<YObject>();
             var pins = new List<GCHandle>();
             IntPtr Pin(Array a) { var h = GCHandle.Alloc(a, GCHandleType.Pinned); pins.Add(h); return h.AddrOfPinnedObject(); }
-            // new Texture(path) (Renderer/Texture.cs:25-49): the int[] pixels (RGBA bytes, row 0 first, :81-90) go to the device once per
-            // distinct Texture object; Material.DiffuseTexture becomes its id.  Needs one internal accessor, Texture.Pixels.
-            var texIds = new Dictionary<ConsoleGame.Renderer.Texture, int>();
-            int TexId(Material m)
-            {
-                if (m.DiffuseTexture == null) return -1;
-                if (!texIds.TryGetValue(m.DiffuseTexture, out int id))
-                {
-                    id = texIds.Count;
-                    Check(ycge_texture_upload(ctx, id, m.DiffuseTexture.width, m.DiffuseTexture.height, m.DiffuseTexture.Pixels));
-                    texIds[m.DiffuseTexture] = id;
-                }
-                return id;
-            }
-            int AddMat(Material m) { var ym = ToMaterial(m); ym.TexId = TexId(m); materials.Add(ym); return materials.Count - 1; }
             try
             {
-                int meshId = 0, volId = 0;
                 foreach (Hittable h in scene.Objects) // enumeration order = primary-hit objId = BVH item index (BVH.cs:34-50)
                 {
                     var o = new YObject { MatA = 0, MatB = 0, RefId = -1 };
@@ -256,23 +276,28 @@ namespace ConsoleGame.RayTracing
                         case Box b: o.Kind = (int)Kind.Box; Set(o.P, b.Min.X, b.Min.Y, b.Min.Z, b.Max.X, b.Max.Y, b.Max.Z); MatFunc(ref o, b.MaterialFunc, b.Specular, b.Reflectivity, AddMat); break;
                         case CylinderY c: o.Kind = (int)Kind.CylinderY; Set(o.P, c.Center.X, c.Center.Y, c.Center.Z, c.Radius, c.YMin, c.YMax, c.Capped ? 1f : 0f); o.MatA = o.MatB = AddMat(c.Mat); break;
                         case Triangle t: o.Kind = (int)Kind.Triangle; Set(o.P, t.A.X, t.A.Y, t.A.Z, t.B.X, t.B.Y, t.B.Z, t.C.X, t.C.Y, t.C.Z); o.MatA = o.MatB = AddMat(t.Mat); break;
+                        case Mesh m when meshIds.TryGetValue(m, out int knownMesh): o.Kind = (int)Kind.Mesh; o.RefId = knownMesh; break;
                         case Mesh m:
                         {   // MeshBVH's private SoA + tree through the `internal` accessor MeshBVH.ExportFlat (INTEGRATION.md)
                             MeshBVH.Flat f = m.Bvh.ExportFlat();
+                            int meshId = meshIds.Count;
                             var tree = new YBvh { NNodes = f.NodeCount, Root = f.Root, NLeafRefs = f.LeafTriIndex.Length,
                                 MinX = Pin(f.NodeMinX), MinY = Pin(f.NodeMinY), MinZ = Pin(f.NodeMinZ), MaxX = Pin(f.NodeMaxX), MaxY = Pin(f.NodeMaxY), MaxZ = Pin(f.NodeMaxZ),
                                 Left = Pin(f.NodeLeft), Right = Pin(f.NodeRight), Start = Pin(f.NodeStart), Count = Pin(f.NodeCount_), LeafIndex = Pin(f.LeafTriIndex) };
                             var treeBox = new[] { tree };
                             var soa = new YMeshSoa { NTris = f.Ax.Length, Ax = Pin(f.Ax), Ay = Pin(f.Ay), Az = Pin(f.Az), E1x = Pin(f.E1x), E1y = Pin(f.E1y), E1z = Pin(f.E1z),
                                 E2x = Pin(f.E2x), E2y = Pin(f.E2y), E2z = Pin(f.E2z), Nx = Pin(f.Nx), Ny = Pin(f.Ny), Nz = Pin(f.Nz),
-                                Material = ToMaterial(f.TriMat[0]), Bvh = Pin(treeBox) }; // MeshLoader gives every triangle the same material (MeshLoader.cs:58-97)
+                                Material = ToMaterialWithTexture(f.TriMat[0]), Bvh = Pin(treeBox) }; // MeshLoader gives every triangle the same material (MeshLoader.cs:58-97)
                             Check(ycge_mesh_upload_soa(ctx, meshId, ref soa));
-                            o.Kind = (int)Kind.Mesh; o.RefId = meshId++;
+                            meshIds[m] = meshId;
+                            o.Kind = (int)Kind.Mesh; o.RefId = meshId;
                             break;
                         }
+                        case VolumeGrid g when volIds.TryGetValue(g, out int knownVol): o.Kind = (int)Kind.Volume; o.RefId = knownVol; break;
                         case VolumeGrid g:
                         {   // the grid's pinned bricked-Morton arrays go over unchanged (VolumeGrid.cs:70-73, 235-252)
                             VolumeGrid.Flat f = g.ExportFlat();
+                            int volId = volIds.Count;
                             var palette = new List<int>(); // materialLookup(id, meta) tabulated: a closed table (VoxelMaterialPalette.cs:48-98)
                             for (int id = 0; id < f.PaletteIds; id++) for (int meta = 0; meta < f.PaletteMetaLevels; meta++) palette.Add(AddMat(f.MaterialLookup(id, meta)));
                             int def = AddMat(f.MaterialLookup(int.MaxValue, 0));
@@ -280,9 +305,10 @@ namespace ConsoleGame.RayTracing
                                 SizeX = f.VoxelSize.X, SizeY = f.VoxelSize.Y, SizeZ = f.VoxelSize.Z, Mat = f.MatPtr, Meta = f.MetaPtr,
                                 Wireframe = f.Wireframe ? 1 : 0, WireWidthFrac = f.WireWidthFraction, WireMaxDistance = f.WireMaxDistance,
                                 PaletteNIds = f.PaletteIds, PaletteMetaLevels = f.PaletteMetaLevels, Palette = Pin(palette.ToArray()), PaletteDefault = def };
-                            // NOTE: upload after the material table is final — palette indices refer to YScene.Materials
+                            // palette entries are indices into the append-only material table: they stay valid over later re-syncs
                             Check(ycge_volume_upload(ctx, volId, ref vol));
-                            o.Kind = (int)Kind.Volume; o.RefId = volId++;
+                            volIds[g] = volId;
+                            o.Kind = (int)Kind.Volume; o.RefId = volId;
                             break;
                         }
                         default: throw new InvalidOperationException("Unbounded Hittable"); // BVH.cs:39
