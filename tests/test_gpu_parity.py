@@ -205,6 +205,46 @@ def test_gpu_matches_oracle_every_tap(case):
     s.close()
 
 
+def morton_index(nbx, nby, x, y, z):
+    """VolumeGrid.IndexOf (VolumeGrid.cs:235-252): brick ((bz * nby) + by) * nbx + bx, inside it the bits x0 y0 z0 x1 y1 z1 x2 y2 z2."""
+    lx, ly, lz = x & 7, y & 7, z & 7
+    m = (lx & 1) | ((ly & 1) << 1) | ((lz & 1) << 2) | ((lx & 2) << 2) | ((ly & 2) << 3) | ((lz & 2) << 4) | ((lx & 4) << 4) | ((ly & 4) << 5) | ((lz & 4) << 6)
+    return ((((z >> 3) * nby) + (y >> 3)) * nbx + (x >> 3)) * 512 + m
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,fill", [(1, 0.02), (2, 0.10), (3, 0.45), (4, 0.0)])
+def test_sparse_random_voxels_match_the_oracle(seed, fill):
+    """The DDA fetches a voxel only in octants (4^3 blocks) its occupancy byte marks solid (trace.cuh volume_hit, post.cuh
+    voxel_occupancy_kernel): the small voxel test grid refilled at random -- nearly empty, sparse, half full, empty -- puts every
+    mix of empty and solid octants on the rays' way.  Planes, cells and the DDA cell count equal the oracle's."""
+    s = api.HostScene("volume_grid_test")
+    v = s.volume(0).contents
+    nbx, nby, nbz = (v.nx + 7) >> 3, (v.ny + 7) >> 3, (v.nz + 7) >> 3
+    mat = np.ctypeslib.as_array(v.mat, shape=(nbx * nby * nbz * 512,))
+    rng = np.random.default_rng(seed)
+    mat[:] = 0
+    for z in range(v.nz):
+        for y in range(v.ny):
+            for x in range(v.nx):
+                if rng.random() < fill:
+                    mat[morton_index(nbx, nby, x, y, z)] = int(rng.integers(1, v.palette_n_ids))
+    r = api.CudaRaytraceRenderer(s, 44, 12, 2)
+    o = Oracle(s, 44, 12, 2)
+    pose = ((0.4, 5.5, 5.0), 0.05, -0.46)  # outside the grid (x -4..4, y 0..4, z -6..2), looking down and across it
+    r.SetCamera(*pose)
+    o.set_camera(*pose)
+    for f in range(2):
+        g = r.render_frame_stats()
+        c = o.render_frame(threads=os.cpu_count() or 1, fast_post=True)
+        assert_cells_equal(g, c, f"seed {seed} frame {f + 1}")
+        assert_frame_parity(r, o, f"seed {seed} frame {f + 1}")
+        assert r.stats()["dda_cells"] == o.stats()["dda_cells"] and (fill == 0.0 or r.stats()["dda_cells"] > 0)
+    r.close()
+    o.close()
+    s.close()
+
+
 @pytest.mark.parametrize("scene,fb_w,fb_h,ss,pose", [("mirror_spheres", 57, 19, 3, None), ("knot:60x16", 48, 27, 4, api.BENCH_POSE),
                                                      ("voxel_world:64x64", 50, 13, 2, None), ("texture_gallery", 41, 11, 2, None)])
 def test_trace_kernel_forms_are_bit_identical(scene, fb_w, fb_h, ss, pose):
