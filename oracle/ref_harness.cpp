@@ -93,6 +93,28 @@ RH_API void ref_oren_nayar(const float *albedo3, const float *n3, const float *w
 RH_API int ref_ansi256(float r, float g, float b) { return AnsiRef::ChexelToAnsi256(ChexelColor(Vec3(r, g, b))); }
 RH_API int ref_nearest16(float r, float g, float b) { return (int)ChexelColor(Vec3(r, g, b)).color_16; }
 RH_API int ref_linear_to_srgb8(double c) { return AnsiRef::LinearToSrgb8(c); }
+// ANSITerminalRenderer.Render (:86-153) over one Framebuffer of fb_w x fb_h cells (row-major glyph / fg rgb / bg rgb) placed at (vx, vy) on a
+// console of console_w x console_h cells; the renderer believes the console to be known_w x known_h (differs -> the resize prologue).
+// Returns the number of bytes the reference would write (or -needed when `cap` is too small).
+RH_API int ref_ansi_render(int fb_w, int fb_h, const uint16_t *glyph, const float *fg3, const float *bg3, int vx, int vy, int console_w, int console_h, int known_w, int known_h,
+                           uint8_t *out, int cap) {
+    try {
+        Framebuffer fb(fb_w, fb_h);
+        fb.ViewportX = vx; fb.ViewportY = vy;
+        for (int y = 0; y < fb_h; y++) for (int x = 0; x < fb_w; x++) {
+            const size_t c = (size_t)x + (size_t)y * fb_w;
+            fb.SetChexel(x, y, Chexel((char16_t)glyph[c], Vec3(fg3[3 * c], fg3[3 * c + 1], fg3[3 * c + 2]), Vec3(bg3[3 * c], bg3[3 * c + 1], bg3[3 * c + 2])));
+        }
+        AnsiRenderRef r;
+        r.frameBuffers.Add(&fb);
+        Console::WindowWidth = console_w; Console::WindowHeight = console_h + 1; // consoleHeight = Console.WindowHeight - 1 (:32, :89)
+        r.consoleWidth = known_w; r.consoleHeight = known_h;
+        r.Render();
+        if ((int)r.flushed.size() > cap) return -(int)r.flushed.size();
+        std::memcpy(out, r.flushed.data(), r.flushed.size());
+        return (int)r.flushed.size();
+    } catch (...) { return -1; }
+}
 
 // ---- the analytic primitives: objects built by the reference's own constructors from the flat scene description
 // (include/ycge.h: ycge_object.p = the public fields after the ctor ran), rays against the reference's own Hit methods.

@@ -14,6 +14,7 @@
 #include <limits>
 #include <memory>
 #include <stdexcept>
+#include <string>
 #include <thread>
 #include <vector>
 #include "../include/ycge_detmath.h"
@@ -101,6 +102,11 @@ struct PixelThreadPool { // Renderer/PixelThreadPool.cs: For2D(w, h, body(px, py
     }
 };
 enum ConsoleColor : int { Black = 0 };
+// System.Console: the window size ANSITerminalRenderer.Render compares its own with (set by the harness)
+struct Console { static inline int WindowWidth = 0, WindowHeight = 0; };
+struct Buffer { // System.Buffer.BlockCopy on byte arrays
+    static void BlockCopy(const std::vector<byte> &src, int src_offset, std::vector<byte> &dst, int dst_offset, int count) { std::memcpy(dst.data() + dst_offset, src.data() + src_offset, (size_t)count); }
+};
 
 // System.Collections.Generic.List<T>: a reference type in C# -- the transpiler passes it by reference
 template <class T> struct List {
@@ -125,6 +131,7 @@ inline int SingleCompareTo(float a, float b) { // System.Single.CompareTo
 // 16 elements, heap sort at depth 0, else median-of-three partition.  Unstable: the PERMUTATION it produces is part of the reference's
 // behaviour (the builders' fallback split), hence restated here as runtime library.
 struct Array {
+    template <class T> static void Resize(std::vector<T> &a, int n) { a.resize((size_t)n); } // Array.Resize(ref a, n): contents kept, zero-filled tail
     template <class T, class Cmp> static void Sort(std::vector<T> &keys, int index, int length, Cmp cmp) {
         if (length < 2) return;
         int lg = 0;

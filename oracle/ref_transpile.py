@@ -15,7 +15,7 @@ text calls) and oracle/ref_harness.cpp (C entry points) into oracle/_ref/libycge
 What is transpiled (and then compared with the oracle, bit for bit, by tests/test_reference_transpiled.py):
   RayTracing/Vec3.cs (whole), RayTracing/RaytraceSampler.cs (whole: blue noise, Rng, PerFrameSeed, SplitMix64,
   CosineSampleHemisphere), RayTracing/ToneMapper.cs (whole), Renderer/Chexel.cs (whole), the ANSI-256 quantiser of
-  Renderer/ANSITerminalRenderer.cs, and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
+  Renderer/ANSITerminalRenderer.cs and its Render with the Append* helpers (the byte stream), and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
   the BSDF helpers, and -- verbatim -- the tail of TryFlipAndBlit from the TAA call to the cell loop (:218-264), i.e. the
   reference's own buffer juggling, including the swap at :718 that makes the second a-trous iteration run in place.
 """
@@ -250,7 +250,8 @@ def main(ref, out_path):
     chex = rd("Renderer/Chexel.cs")
     out.append(emit_struct(chex, "ChexelColor"))
     out.append(emit_struct(chex, "Chexel"))
-    out.append("struct Framebuffer { Fast2D<Chexel> cells; Framebuffer(int w, int h) : cells(w, h) {} void SetChexel(int x, int y, Chexel c) { cells[x, y] = c; } };\n")
+    out.append("struct Framebuffer { Fast2D<Chexel> cells; int Width, Height, ViewportX = 0, ViewportY = 0; Framebuffer(int w, int h) : cells(w, h), Width(w), Height(h) {} "
+               "void SetChexel(int x, int y, Chexel c) { cells[x, y] = c; } Chexel GetChexel(int x, int y) { return cells[x, y]; } };\n")
     samp = rd("RayTracing/RaytraceSampler.cs")
     body = rewrite(type_body(samp, "RaytraceSampler"), None)
     body = re.sub(r"^(\s*)(uint64_t state);", r"\1\2 = 0;", body, flags=re.M)
@@ -271,6 +272,23 @@ def main(ref, out_path):
     want = {"s_cubeSrgb", "s_cubeLinear", "s_graySrgb", "s_grayLinear", "ChexelToAnsi256", "ToCubeLevelSrgb", "LinearToSrgb8", "Dist2Srgb"}
     sel = [t for t, n in members(ab) if n in want]
     out.append("struct AnsiRef {\n%s\n};\n" % rewrite("\n".join(sel), None))
+    # ---- ANSITerminalRenderer.Render (:86-153) with everything it calls (GetChexelForPoint, Append*, EnsureCapacity): the byte stream the
+    # terminal receives.  Not taken: the constructor (console mode, cursor), Flush (WriteFile / stdout: the harness keeps the bytes instead).
+    want = {"frameBuffers", "consoleWidth", "consoleHeight", "defaultFg", "defaultBg", "onResize", "zeroSeq", "outBuf", "outLen", "GetChexelForPoint", "Render",
+            "EnsureCapacity", "AppendAscii", "AppendBytes", "AppendInt", "AppendCharUtf8"}
+    rt = "\n".join(t for t, n in members(ab) if n in want and "ITerminalRenderer." not in t)          # not the explicit interface properties
+    rt = re.sub(r"\(byte\[\] (\w+)\)", r"(std::vector<byte> &\1)", rt)                                   # an array parameter: a reference
+    rt = re.sub(r"List<Framebuffer> frameBuffers;", "List<Framebuffer *> frameBuffers;", rt)             # Framebuffer is a class: a list of references
+    rt = re.sub(r"Framebuffer fb = frameBuffers\[i\];", "Framebuffer &fb = *frameBuffers[i];", rt)
+    rt = re.sub(r"\bframeBuffers\.Count\b(?!\()", "frameBuffers.Count()", rt)                           # List<T>.Count is a property
+    rt = re.sub(r"Action<int, int> onResize;", "std::function<void(int, int)> onResize;", rt)
+    rt = re.sub(r"onResize\?\.Invoke\(([^;]*)\);", r"if (onResize) onResize(\1);", rt)                  # null-conditional call
+    rt = re.sub(r"Array\.Resize\(ref (\w+), (\w+)\);", r"Array::Resize(\1, \2);", rt)
+    rt = re.sub(r"\bstring (\w+)\)", r"const std::string &\1)", rt)
+    rt = rewrite(rt, None, statics=("Console", "Buffer"))
+    rt = re.sub(r"std::vector<byte> outBuf\(([^;]*)\);", r"std::vector<byte> outBuf = std::vector<byte>(\1);", rt)  # a member initialiser
+    rt = re.sub(r"^(\s*)((?:int|ConsoleColor) \w+);", r"\1\2 = {};", rt, flags=re.M)                    # C# zero-initialises fields
+    out.append("struct AnsiRenderRef : AnsiRef {\n    std::vector<byte> flushed;\n    void Flush() { flushed.insert(flushed.end(), outBuf.begin(), outBuf.begin() + outLen); }\n%s\n};\n" % rt)
     # ---- the analytic primitives and what their Hit needs
     out.append("struct Vec3;\nstruct Texture { Vec3 SampleBilinear(float u, float v); }; // textured scenes are not run through the transpiled reference\n")
     out.append(emit_struct(rd("RayTracing/Ray.cs"), "Ray"))

@@ -4,7 +4,7 @@ oracle/ref_transpile.py rewrites the C# files under /root/reference into C++ syn
 and oracle/Makefile compiles the result into oracle/_ref/libycge_ref.so (git-ignored; nothing generated is committed).  What
 runs here is therefore the reference author's code -- TemporalBlendWithClamp, ApplyAtrousDenoise and the verbatim tail of
 TryFlipAndBlit with its buffer juggling (RaytraceRenderer.cs:218-264, :274-398, :622-722), ToneMapper.cs, Chexel.cs, the
-ANSI-256 quantiser of ANSITerminalRenderer.cs, RaytraceSampler.cs, Vec3.cs -- with one documented substitution: MathF.Exp /
+ANSI-256 quantiser and the byte-stream Render of ANSITerminalRenderer.cs, RaytraceSampler.cs, Vec3.cs -- with one documented substitution: MathF.Exp /
 Log / Pow / Sin / Cos forward to include/ycge_detmath.h, as they do in the oracle and the product.  The hand-written
 oracle (oracle/ycge_oracle.cpp) must agree with it bit for bit."""
 import ctypes as C
@@ -41,6 +41,7 @@ def ref():
     lib.ref_ansi256.argtypes = [f32, f32, f32]
     lib.ref_nearest16.argtypes = [f32, f32, f32]
     lib.ref_linear_to_srgb8.argtypes = [C.c_double]
+    lib.ref_ansi_render.argtypes = [C.c_int, C.c_int, vp, vp, vp] + [C.c_int] * 6 + [vp, C.c_int]
     return lib
 
 
@@ -139,6 +140,65 @@ def test_quantisers_equal_the_reference_source(ref, oracle_lib):
         assert ref.ref_nearest16(float(r), float(g), float(b)) == oracle_lib.yo_nearest16(float(r), float(g), float(b))
     for c in np.linspace(-0.1, 1.1, 5001):
         assert ref.ref_linear_to_srgb8(float(c)) == oracle_lib.yo_linear_to_srgb8(float(c))
+
+
+def ref_ansi_stream(ref, cells, vx=0, vy=0, console=None, known=None):
+    """ANSITerminalRenderer.Render of the transpiled reference over one Framebuffer holding `cells` (glyph + float colours)."""
+    fb_h, fb_w = cells.shape
+    console = console or (fb_w, fb_h)
+    known = known or console
+    glyph = np.ascontiguousarray(cells["glyph"], np.uint16)
+    fg = np.ascontiguousarray(cells["fg"], np.float32)
+    bg = np.ascontiguousarray(cells["bg"], np.float32)
+    cap = 64 + console[0] * console[1] * 32
+    buf = np.empty(cap, np.uint8)
+    n = ref.ref_ansi_render(fb_w, fb_h, P(glyph), P(fg), P(bg), vx, vy, console[0], console[1], known[0], known[1], P(buf), cap)
+    assert n >= 0
+    return buf[:n].tobytes()
+
+
+def test_ansi_byte_stream_equals_the_reference_source(ref):
+    """the bytes the terminal receives.  ANSITerminalRenderer.Render (:86-153) with GetChexelForPoint, AppendInt,
+    AppendCharUtf8 ... runs as the reference's own text; the host mirror's Render (what the device's ycge_ansi_emit is compared
+    with on the GPU) must produce the same stream from the same cells: cursor addressing per row, colour runs (both / fg only /
+    bg only -- the first `if` needs BOTH to differ, :120), 1-, 2- and 3-byte glyphs, the final reset; a console whose size
+    changed gets the clear-screen prologue in front."""
+    rng = np.random.default_rng(5)
+    for fb_w, fb_h in [(31, 9), (1, 1), (120, 33)]:
+        cells = np.zeros((fb_h, fb_w), api.CELL_DTYPE)
+        cells["glyph"] = 0x2580
+        cells["fg"] = rng.random((fb_h, fb_w, 3)).astype(np.float32)
+        cells["bg"] = rng.random((fb_h, fb_w, 3)).astype(np.float32)
+        if fb_h > 2:
+            cells["fg"][2, :] = (0.1, 0.7, 0.3)   # runs: no escape while nothing changes, then bg-only changes
+            cells["bg"][2, 5:] = (0.9, 0.2, 0.2)
+            cells["bg"][3, :] = (0.2, 0.2, 0.9)   # fg-only changes
+            cells["glyph"][0, 0] = ord("A")
+            cells["glyph"][0, 1] = 0x00E9
+        for y in range(fb_h):
+            for x in range(fb_w):
+                cells["fg_ansi"][y, x] = ref.ref_ansi256(*map(float, cells["fg"][y, x]))
+                cells["bg_ansi"][y, x] = ref.ref_ansi256(*map(float, cells["bg"][y, x]))
+        want = ref_ansi_stream(ref, cells)
+        assert want.startswith(b"\x1b[1;1H") and want.endswith(b"\x1b[0m")
+        assert api.ansi_from_cells(cells) == want, (fb_w, fb_h)
+        # the renderer remembers another console size: onResize, then ESC[2J ESC[H in front of the same stream (:88-103)
+        assert ref_ansi_stream(ref, cells, known=(fb_w + 1, fb_h)) == b"\x1b[2J\x1b[H" + want
+    # a framebuffer smaller than the console, placed at (2, 1): what it does not cover is a space in the default colours
+    # (ConsoleColor.Black on Black here), and so is a cell whose glyph is a space (GetChexelForPoint :67-84)
+    cells = np.zeros((2, 3), api.CELL_DTYPE)
+    cells["glyph"] = 0x2580
+    cells["glyph"][1, 1] = ord(" ")
+    cells["fg"][:] = (1.0, 1.0, 1.0)
+    cells["bg"][:] = (1.0, 0.0, 0.0)
+    k = ref.ref_ansi256(0.0, 0.0, 0.0)
+    f, b = ref.ref_ansi256(1.0, 1.0, 1.0), ref.ref_ansi256(1.0, 0.0, 0.0)
+    got = ref_ansi_stream(ref, cells, vx=2, vy=1, console=(6, 4))
+    blk = "\u2580".encode()
+    want = (b"\x1b[1;1H\x1b[38;5;%d;48;5;%dm      " % (k, k) + b"\x1b[2;1H  \x1b[38;5;%d;48;5;%dm" % (f, b) + blk * 3 + b"\x1b[38;5;%d;48;5;%dm " % (k, k)
+            + b"\x1b[3;1H  \x1b[38;5;%d;48;5;%dm" % (f, b) + blk + b"\x1b[38;5;%d;48;5;%dm " % (k, k) + b"\x1b[38;5;%d;48;5;%dm" % (f, b) + blk
+            + b"\x1b[38;5;%d;48;5;%dm " % (k, k) + b"\x1b[4;1H      \x1b[0m")
+    assert got == want
 
 
 PRIM_SCENES = ["cornell", "mirror_spheres", "boxes", "cylinders_disks_triangles", "test", "texture_gallery"]

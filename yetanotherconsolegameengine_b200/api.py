@@ -546,6 +546,10 @@ class CudaRaytraceRenderer:
                 out["host"] += 1e3 * (time.perf_counter() - t0)
             t0 = time.perf_counter()
             self._ck(self._lib.ycge_mesh_build_device(self.ctx, i, len(tris), tris.ctypes.data, C.byref(mat)))
+            # the call returns with the build in flight; asking for the root record waits for it, so that 'device' is the whole
+            # build like 'host' (not available on a multi-GPU context: there the time is the enqueue only)
+            n = C.c_size_t(0)
+            self._lib.ycge_mesh_debug_read(self.ctx, i, 3, None, C.byref(n))
             out["device"] += 1e3 * (time.perf_counter() - t0)
         self._ck(self._lib.ycge_scene_upload(self.ctx, self.scene.flat))
         return out
