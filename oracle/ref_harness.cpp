@@ -11,6 +11,7 @@ struct Handle {
     RendererRef r;
     Fast2D<Chexel> target;
     std::unique_ptr<Framebuffer> fb;
+    std::unique_ptr<TemporalAA> taa; // RaytraceRenderer.taa (:56, :96): asked for the reset decision (:171), told the camera (:266)
     int W = 0, H = 0;
 };
 template <class T> Fast2D<T> plane(int w, int h) { return Fast2D<T>(w, h); }
@@ -23,9 +24,14 @@ RH_API void *ref_renderer_create(int fb_w, int fb_h, int ss, int proc_count) {
     h->W = fb_w * ss; h->H = fb_h * 2 * ss; // hiW, hiH (RaytraceRenderer.cs:86-87)
     h->target = Fast2D<Chexel>(fb_w, fb_h);
     h->fb.reset(new Framebuffer(fb_w, fb_h));
+    h->taa.reset(new TemporalAA(h->W, h->H, h->r.taaAlpha, RendererRef::MotionTransReset, RendererRef::MotionRotReset)); // :96
     return h;
 }
 RH_API void ref_renderer_destroy(void *hh) { delete (Handle *)hh; }
+// TryFlipAndBlit :171 (without `|| scene.HasDynamicTextures`) and :266; Resize :128
+RH_API int ref_taa_should_reset(void *hh, const float *cam3, float yaw, float pitch) { return ((Handle *)hh)->taa->ShouldResetHistory(Vec3(cam3[0], cam3[1], cam3[2]), yaw, pitch) ? 1 : 0; }
+RH_API void ref_taa_commit_camera(void *hh, const float *cam3, float yaw, float pitch) { ((Handle *)hh)->taa->CommitCamera(Vec3(cam3[0], cam3[1], cam3[2]), yaw, pitch); }
+RH_API void ref_taa_resize(void *hh) { Handle &h = *(Handle *)hh; h.taa->Resize(h.W, h.H); }
 // one frame: the trace stage's planes in (row-major W x H: hdr rgb, albedo rgb, raw normal xyz, depth, sky 0/1), everything after out
 RH_API int ref_post_frame(void *hh, const float *hdr3, const float *albedo3, const float *normal3, const float *depth, const uint8_t *sky, int reset_history,
                           float *taa3, float *den3, float *exposure2, uint16_t *glyph, uint8_t *fg16, uint8_t *bg16, uint8_t *fg_ansi, uint8_t *bg_ansi, float *fg3, float *bg3) {
@@ -93,6 +99,7 @@ RH_API void ref_oren_nayar(const float *albedo3, const float *n3, const float *w
 RH_API int ref_ansi256(float r, float g, float b) { return AnsiRef::ChexelToAnsi256(ChexelColor(Vec3(r, g, b))); }
 RH_API int ref_nearest16(float r, float g, float b) { return (int)ChexelColor(Vec3(r, g, b)).color_16; }
 RH_API int ref_linear_to_srgb8(double c) { return AnsiRef::LinearToSrgb8(c); }
+RH_API int ref_map_attributes(int fg16, int bg16) { return (int)Win32Ref::MapAttributes((ConsoleColor)fg16, (ConsoleColor)bg16); } // Win32TerminalRenderer.cs:109-112
 // ANSITerminalRenderer.Render (:86-153) over one Framebuffer of fb_w x fb_h cells (row-major glyph / fg rgb / bg rgb) placed at (vx, vy) on a
 // console of console_w x console_h cells; the renderer believes the console to be known_w x known_h (differs -> the resize prologue).
 // Returns the number of bytes the reference would write (or -needed when `cap` is too small).

@@ -22,11 +22,13 @@
 namespace refcs {
 
 using byte = uint8_t;
+using ushort = uint16_t;
 
 struct Single {
     static constexpr float PositiveInfinity = std::numeric_limits<float>::infinity();
     static constexpr float NegativeInfinity = -std::numeric_limits<float>::infinity();
     static constexpr float MaxValue = std::numeric_limits<float>::max();
+    static constexpr float NaN = std::numeric_limits<float>::quiet_NaN();
     static bool IsFinite(float v) { return std::isfinite(v); }
     static bool IsNaN(float v) { return v != v; }
     static bool IsInfinity(float v) { return std::isinf(v); }

@@ -15,7 +15,8 @@ text calls) and oracle/ref_harness.cpp (C entry points) into oracle/_ref/libycge
 What is transpiled (and then compared with the oracle, bit for bit, by tests/test_reference_transpiled.py):
   RayTracing/Vec3.cs (whole), RayTracing/RaytraceSampler.cs (whole: blue noise, Rng, PerFrameSeed, SplitMix64,
   CosineSampleHemisphere), RayTracing/ToneMapper.cs (whole), Renderer/Chexel.cs (whole), the ANSI-256 quantiser of
-  Renderer/ANSITerminalRenderer.cs and its Render with the Append* helpers (the byte stream), and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
+  Renderer/ANSITerminalRenderer.cs and its Render with the Append* helpers (the byte stream), RayTracing/TemporalAA.cs (constructor,
+  ShouldResetHistory, CommitCamera, Resize), and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
   the BSDF helpers, and -- verbatim -- the tail of TryFlipAndBlit from the TAA call to the cell loop (:218-264), i.e. the
   reference's own buffer juggling, including the swap at :718 that makes the second a-trous iteration run in place.
 """
@@ -267,6 +268,15 @@ def main(ref, out_path):
     tb = re.sub(r"if \(threadpool == nullptr\) return [^;]*;", "", tb)
     tb = re.sub(r"FixedThreadFor threadpool\b", "FixedThreadFor &threadpool", tb)
     out.append("struct ToneMapper {\n%s\n};\n" % tb)
+    # ---- Win32TerminalRenderer.MapAttributes (:109-112): the console attribute word of a cell (fg | bg << 4)
+    w32 = [t for t, n in members(type_body(rd("Renderer/Win32TerminalRenderer.cs"), "Win32TerminalRenderer")) if n == "MapAttributes"]
+    out.append("struct Win32Ref {\n%s\n};\n" % rewrite("\n".join(w32), None))
+    # ---- TemporalAA.cs: what TryFlipAndBlit asks it (:171 ShouldResetHistory, :266 CommitCamera, :128 Resize) and its constructor; the
+    # blend itself lives in RaytraceRenderer.TemporalBlendWithClamp (BlendIntoHistory is not on the path)
+    taa_members = [t for t, n in members(type_body(rd("RayTracing/TemporalAA.cs"), "TemporalAA")) if n not in ("BlendIntoHistory", "GetHistory", "History", "HistoryValid")]
+    taa = rewrite("\n".join(taa_members), None)
+    taa = re.sub(r"^(\s*)((?:int|bool|float) \w+);", r"\1\2 = {};", taa, flags=re.M)
+    out.append("struct TemporalAA {\n%s\n};\n" % taa)
     ansi = rd("Renderer/ANSITerminalRenderer.cs")
     ab = type_body(ansi, "ANSITerminalRenderer")
     want = {"s_cubeSrgb", "s_cubeLinear", "s_graySrgb", "s_grayLinear", "ChexelToAnsi256", "ToCubeLevelSrgb", "LinearToSrgb8", "Dist2Srgb"}
@@ -350,6 +360,7 @@ def main(ref, out_path):
     fields = {"taaAlpha", "taaHistory", "taaHistoryValid", "prevNormal", "prevDepth", "prevSky", "spatialA", "spatialB", "gAlbedo", "gNormal", "gDepth", "skyMask",
               "toneMapper", "threadpool", "procCount", "ss", "fbW", "fbH", "Pi", "InvPi", "DiffuseSigmaDeg", "Eps", "MirrorThreshold"}
     fields |= {"hiW", "hiH", "fovDeg", "rays", "currentHdr", "pixelPool", "frameCounter", "frameBuffer", "scene"}
+    fields |= {"MotionTransReset", "MotionRotReset"}
     fields |= {"DiffuseBounces", "IndirectSamples", "MaxMirrorBounces", "MaxRefractions", "SeedSalt", "MaxLuminance", "PrimaryGBuffer", "PathWorkItem"}
     funcs = {"Luma", "TemporalBlendWithClamp", "ApplyAtrousDenoise", "OrenNayarBRDF", "FresnelSchlick", "Refract", "Reflect", "Lerp", "SampleAlbedo", "ForwardFromYawPitch",
              "MakeJitteredRay", "TraceFull", "ComputeTransmittanceToLight", "CosineSampleHemisphere"}

@@ -28,6 +28,9 @@ def load():
     lib.ref_trace_destroy.argtypes = [vp]
     lib.ref_trace_frame.argtypes = [vp, vp, C.c_float, C.c_float] + [vp] * 6
     lib.ref_set_threads.argtypes = [C.c_int]
+    lib.ref_taa_should_reset.argtypes = [vp, vp, C.c_float, C.c_float]
+    lib.ref_taa_commit_camera.argtypes = [vp, vp, C.c_float, C.c_float]
+    lib.ref_taa_resize.argtypes = [vp]
     return lib
 
 
@@ -79,8 +82,9 @@ class RefRenderer:
         self.cam = (pos, yaw, pitch)
 
     def render_frame(self, reset_history=None):
-        """-> dict of planes (rays, hdr, albedo, normal, depth, sky, taa, den), ae_exposure and the cell fields.  `reset_history`: the
-        decision of TemporalAA.ShouldResetHistory (not transpiled: camera motion thresholds); default: only on the first frame."""
+        """-> dict of planes (rays, hdr, albedo, normal, depth, sky, taa, den), ae_exposure and the cell fields.  `reset_history`: None =
+        the reference's own decision, taa.ShouldResetHistory(camera) of the transpiled TemporalAA.cs (TryFlipAndBlit :171; the camera is
+        committed after the frame, :266); True / False overrides it (`|| scene.HasDynamicTextures`)."""
         W, H, fb_w, fb_h = self.fb_w * self.ss, self.fb_h * 2 * self.ss, self.fb_w, self.fb_h
         o = dict(rays=np.empty((H, W, 6), np.float32), hdr=np.empty((H, W, 3), np.float32), albedo=np.empty((H, W, 3), np.float32), normal=np.empty((H, W, 3), np.float32),
                  depth=np.empty((H, W), np.float32), sky=np.empty((H, W), np.uint8), taa=np.empty((H, W, 3), np.float32), den=np.empty((H, W, 3), np.float32),
@@ -90,10 +94,12 @@ class RefRenderer:
         rc = self.lib.ref_trace_frame(self.trace, P(c3), np.float32(self.cam[1]), np.float32(self.cam[2]), P(o["rays"]), P(o["hdr"]), P(o["albedo"]), P(o["normal"]), P(o["depth"]), P(o["sky"]))
         assert rc == 0
         self.frame += 1
-        reset = (self.frame == 1) if reset_history is None else reset_history
+        reset = bool(self.lib.ref_taa_should_reset(self.post, P(c3), np.float32(self.cam[1]), np.float32(self.cam[2]))) if reset_history is None else reset_history
+        self.last_reset = reset
         rc = self.lib.ref_post_frame(self.post, P(o["hdr"]), P(o["albedo"]), P(o["normal"]), P(o["depth"]), P(o["sky"]), 1 if reset else 0, P(o["taa"]), P(o["den"]), P(o["expo"]),
                                      P(o["glyph"]), P(o["fg16"]), P(o["bg16"]), P(o["fg_ansi"]), P(o["bg_ansi"]), P(o["fg"]), P(o["bg"]))
         assert rc == 0
+        self.lib.ref_taa_commit_camera(self.post, P(c3), np.float32(self.cam[1]), np.float32(self.cam[2]))
         return o
 
     def close(self):

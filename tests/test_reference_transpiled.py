@@ -91,6 +91,8 @@ def test_image_passes_equal_the_reference_source(ref, scene, fb_w, fb_h, ss, pos
         assert bits(expo[:1])[0] == bits(np.float32(o.stats()["ae_exposure"]))[()], what + ": aeExposure"
         assert np.array_equal(glyph, cells["glyph"]) and np.array_equal(fg16, cells["fg16"]) and np.array_equal(bg16, cells["bg16"]), what + ": cells"
         assert np.array_equal(fga, cells["fg_ansi"]) and np.array_equal(bga, cells["bg_ansi"]), what + ": ANSI-256"
+        attr = np.array([[ref.ref_map_attributes(int(a), int(b)) for a, b in zip(ra, rb)] for ra, rb in zip(fg16, bg16)], np.uint16)
+        assert np.array_equal(attr, cells["attr"]), what + ": Win32 attribute word (Win32TerminalRenderer.MapAttributes)"
         assert np.array_equal(bits(fg), bits(cells["fg"])) and np.array_equal(bits(bg), bits(cells["bg"])), what + ": SDR colours"
     ref.ref_renderer_destroy(h)
     o.close()
@@ -199,6 +201,40 @@ def test_ansi_byte_stream_equals_the_reference_source(ref):
             + b"\x1b[3;1H  \x1b[38;5;%d;48;5;%dm" % (f, b) + blk + b"\x1b[38;5;%d;48;5;%dm " % (k, k) + b"\x1b[38;5;%d;48;5;%dm" % (f, b) + blk
             + b"\x1b[38;5;%d;48;5;%dm " % (k, k) + b"\x1b[4;1H      \x1b[0m")
     assert got == want
+
+
+def test_history_reset_follows_the_reference_camera_thresholds(ref):
+    """TryFlipAndBlit :171 / :266 with the reference's own TemporalAA.cs (ShouldResetHistory :58-67, CommitCamera): whole frames of the
+    transpiled reference along a camera path that stays, creeps below the 0.0025 thresholds, jumps above them, turns by just less and
+    just more than 0.0025 rad in yaw and in pitch.  The oracle (its own restatement of the rule) must take the same decision every
+    frame: the TAA history -- a 1 % blend against a plain copy -- and everything after it are compared bit for bit."""
+    import ref_binding
+    s = api.HostScene("cornell")
+    fb_w, fb_h, ss = 16, 6, 2
+    rr = ref_binding.RefRenderer(s, fb_w, fb_h, ss)
+    o = Oracle(s, fb_w, fb_h, ss)
+    (x, y, z), yaw, pitch = s.default_camera()[:3]
+    f32 = lambda v: float(np.float32(v))
+    path = [((x, y, z), yaw, pitch, False), ((x, y, z), yaw, pitch, False),
+            ((f32(x + 0.001), y, z), yaw, pitch, False),                          # 0.001 < 0.0025: history kept
+            ((f32(x + 0.001), f32(y + 0.002), z), yaw, pitch, False),             # 0.002 from the LAST pose: kept (no drift accumulates)
+            ((f32(x + 0.001), f32(y + 0.002), f32(z + 0.01)), yaw, pitch, True),  # 0.01: reset
+            ((f32(x + 0.001), f32(y + 0.002), f32(z + 0.01)), f32(yaw + 0.002), pitch, False),
+            ((f32(x + 0.001), f32(y + 0.002), f32(z + 0.01)), f32(yaw + 0.002 + 0.003), pitch, True),
+            ((f32(x + 0.001), f32(y + 0.002), f32(z + 0.01)), f32(yaw + 0.005), f32(pitch - 0.002), False),
+            ((f32(x + 0.001), f32(y + 0.002), f32(z + 0.01)), f32(yaw + 0.005), f32(pitch - 0.002 - 0.0026), True)]
+    for k, (pos, yw, pt, expect_reset) in enumerate(path):
+        rr.set_camera(pos, yw, pt)
+        o.set_camera(pos, yw, pt)
+        a = rr.render_frame()
+        c = o.render_frame(threads=1, fast_post=False)
+        assert rr.last_reset == expect_reset, f"frame {k + 1}: the reference's own decision"
+        assert np.array_equal(bits(a["taa"]), bits(o.debug_read(api.DBG_TAA)[..., :3])), f"frame {k + 1}: TAA history"
+        assert np.array_equal(bits(a["den"]), bits(o.debug_read(api.DBG_DENOISED)[..., :3])), f"frame {k + 1}: denoised"
+        assert np.array_equal(a["fg_ansi"], c["fg_ansi"]) and np.array_equal(a["bg_ansi"], c["bg_ansi"]), f"frame {k + 1}: cells"
+    rr.close()
+    o.close()
+    s.close()
 
 
 PRIM_SCENES = ["cornell", "mirror_spheres", "boxes", "cylinders_disks_triangles", "test", "texture_gallery"]
