@@ -73,6 +73,7 @@ RH_API int ref_post_frame(void *hh, const float *hdr3, const float *albedo3, con
 RH_API uint64_t ref_per_frame_seed(int x, int y, int64_t frame, int jx, int jy, uint64_t salt) { return RaytraceSampler::PerFrameSeed(x, y, frame, jx, jy, salt); }
 RH_API uint64_t ref_splitmix64(uint64_t z) { return RaytraceSampler::SplitMix64(z); }
 RH_API void ref_rng_draws(uint64_t seed, int n, float *out) { RaytraceSampler::Rng rng(seed); for (int i = 0; i < n; i++) out[i] = rng.NextUnit(); }
+RH_API void ref_rng_cs_draws(uint64_t seed, int n, uint32_t *bits_out) { rngcs::Rng g(seed); for (int i = 0; i < n; i++) { float f = g.NextUnit(); std::memcpy(&bits_out[i], &f, 4); } } // Rng.cs
 RH_API float ref_blue_noise(int x, int y, int frame_idx, int channel) { return RaytraceSampler::BlueNoiseSample(x, y, frame_idx, channel); }
 RH_API void ref_cosine_sample(float nx, float ny, float nz, uint64_t seed, float *out3) {
     RaytraceSampler::Rng rng(seed);

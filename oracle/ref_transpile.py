@@ -268,6 +268,8 @@ def main(ref, out_path):
     tb = re.sub(r"if \(threadpool == nullptr\) return [^;]*;", "", tb)
     tb = re.sub(r"FixedThreadFor threadpool\b", "FixedThreadFor &threadpool", tb)
     out.append("struct ToneMapper {\n%s\n};\n" % tb)
+    # ---- Rng.cs (ConsoleRayTracing.Rng: dead code in the engine, named by the north star): whole, in a namespace of its own (RaytraceSampler has a Rng too)
+    out.append("namespace rngcs {\n%s}\n" % emit_struct(rd("Rng.cs"), "Rng"))
     # ---- Win32TerminalRenderer.MapAttributes (:109-112): the console attribute word of a cell (fg | bg << 4)
     w32 = [t for t, n in members(type_body(rd("Renderer/Win32TerminalRenderer.cs"), "Win32TerminalRenderer")) if n == "MapAttributes"]
     out.append("struct Win32Ref {\n%s\n};\n" % rewrite("\n".join(w32), None))

@@ -112,6 +112,13 @@ def test_sampler_equals_the_reference_source(ref, oracle_lib):
         assert np.array_equal(d.view(np.uint32), b)
     assert ref.ref_per_frame_seed(0, 0, 1, 0, 0, 0x9E3779B97F4A7C15) == 0x17EF7D0094EB2C76
     assert ref.ref_per_frame_seed(1919, 1079, 64, 0, 0, 0x9E3779B97F4A7C15) == 0x5BEAD3AD13E75BBB
+    # Rng.cs (ConsoleRayTracing.Rng; SURVEY 8 a3'): the reference's text against the oracle's RngCs (what the device's rng_kat_kernel equals)
+    ref.ref_rng_cs_draws.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
+    for seed in (0, 1, 12345, 0xDEADBEEFCAFEBABE, 0xFFFFFFFFFFFFFFFF):
+        a, b = np.zeros(64, np.uint32), np.zeros(64, np.uint32)
+        ref.ref_rng_cs_draws(seed, 64, P(a))
+        oracle_lib.yo_rng_cs_draws(seed, 64, P(b))
+        assert np.array_equal(a, b), seed
     oracle_lib.yo_blue_noise.restype = C.c_float
     for x in range(0, 40, 3):
         for y in range(0, 17, 2):
