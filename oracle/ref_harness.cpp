@@ -191,6 +191,24 @@ RH_API void *ref_mesh_build(int n_tris, const float *abc9, const float *mat13) {
     } catch (...) { return nullptr; }
 }
 RH_API void ref_mesh_destroy(void *h) { delete (MeshBVH *)h; }
+// MeshScenes.AddMeshAutoGround (:173-184) as the reference wrote it: TryReadObjBoundsNormalized(path) -> the ground translate, then
+// MeshLoader.FromObj(path, mat, scale, translate, normalize: true, targetSize: 1) -> the triangles A, B, C (9 floats each) the scene gets.
+// Returns the triangle count (out_abc9 may be NULL to ask for it), -1 on a reference exception.
+RH_API int ref_mesh_from_obj(const char *path, float scale, const float *target3, float *out_abc9, int cap_tris, float *translate3) {
+    try {
+        const Vec3 tr = MeshScenesRef::AutoGroundTranslate(String(path), scale, Vec3(target3[0], target3[1], target3[2]));
+        if (translate3) { translate3[0] = tr.X; translate3[1] = tr.Y; translate3[2] = tr.Z; }
+        List<Triangle *> tris = MeshLoaderRef::FromObj(String(path), Material(), scale, tr, true, 1.0f);
+        const int n = tris.Count();
+        if (out_abc9) for (int i = 0; i < n && i < cap_tris; i++) {
+            const Triangle &t = *tris[i];
+            const float v[9] = {t.A.X, t.A.Y, t.A.Z, t.B.X, t.B.Y, t.B.Z, t.C.X, t.C.Y, t.C.Z};
+            std::memcpy(out_abc9 + 9 * (size_t)i, v, sizeof v);
+        }
+        for (int i = 0; i < n; i++) delete tris[i];
+        return n;
+    } catch (...) { return -1; }
+}
 RH_API void ref_mesh_info(void *h, int *n_nodes, int *root, int *n_leaf) { MeshBVH &b = *(MeshBVH *)h; *n_nodes = b.nodeCountUsed; *root = b.rootIndex; *n_leaf = (int)b.leafTriIndex.size(); }
 RH_API void ref_mesh_tree(void *h, float *boxes6, int *lrsc4, int *leaf) {
     MeshBVH &b = *(MeshBVH *)h;

@@ -16,6 +16,10 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <cstdio>
+#include <cstdlib>
+#include <optional>
+#include <unordered_map>
 #include <vector>
 #include "../include/ycge_detmath.h"
 
@@ -121,6 +125,95 @@ template <class T> struct List {
     T &operator[](int i) { return v[(size_t)i]; }
     const T &operator[](int i) const { return v[(size_t)i]; }
 };
+// ---- what MeshLoader.FromObj / MeshScenes.TryReadObjBoundsNormalized call: strings, a line reader, number parsing, and the
+// collections whose enumeration order the text relies on (HashSet<int> / Dictionary<K, V> without removals enumerate in insertion order)
+struct String {
+    std::string s;
+    bool null = true;
+    String() {}
+    String(const char *c) : s(c), null(false) {}
+    String(std::string v) : s(std::move(v)), null(false) {}
+    size_t size() const { return s.size(); }                       // .Length
+    char operator[](int i) const { return s[(size_t)i]; }
+    bool operator==(const char *c) const { return !null && s == c; }
+    bool operator!=(std::nullptr_t) const { return !null; }
+    bool operator==(std::nullptr_t) const { return null; }
+    static bool IsWhite(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+    static bool IsNullOrEmpty(const String &v) { return v.null || v.s.empty(); }
+    static bool IsNullOrWhiteSpace(const String &v) { if (v.null) return true; for (char c : v.s) if (!IsWhite(c)) return false; return true; }
+    std::vector<String> SplitWhitespace() const {                   // Split((char[])null, StringSplitOptions.RemoveEmptyEntries)
+        std::vector<String> out;
+        size_t i = 0;
+        while (i < s.size()) {
+            while (i < s.size() && IsWhite(s[i])) i++;
+            size_t j = i;
+            while (j < s.size() && !IsWhite(s[j])) j++;
+            if (j > i) out.push_back(String(s.substr(i, j - i)));
+            i = j;
+        }
+        return out;
+    }
+    std::vector<String> Split(char sep) const {                      // Split('/'): empty entries kept
+        std::vector<String> out;
+        size_t i = 0;
+        for (;;) {
+            size_t j = s.find(sep, i);
+            out.push_back(String(s.substr(i, j == std::string::npos ? std::string::npos : j - i)));
+            if (j == std::string::npos) break;
+            i = j + 1;
+        }
+        return out;
+    }
+};
+struct NumberFormatInfo {};
+struct CultureInfo { NumberFormatInfo NumberFormat; static const CultureInfo InvariantCulture; };
+inline const CultureInfo CultureInfo::InvariantCulture{};
+struct File { static bool Exists(const String &p) { FILE *f = std::fopen(p.s.c_str(), "rb"); if (!f) return false; std::fclose(f); return true; } };
+struct StreamReader {
+    FILE *f;
+    explicit StreamReader(const String &p) : f(std::fopen(p.s.c_str(), "rb")) {}
+    ~StreamReader() { if (f) std::fclose(f); }
+    String ReadLine() {                                              // a line without its terminator (\n, \r\n), null at the end of the file
+        if (!f) return String();
+        std::string line;
+        int c = std::fgetc(f);
+        if (c == EOF) return String();
+        while (c != EOF && c != '\n') { line.push_back((char)c); c = std::fgetc(f); }
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return String(line);
+    }
+};
+template <class Fmt> float SingleParse(const String &t, const Fmt &) { return std::strtof(t.s.c_str(), nullptr); }   // float.Parse(s, invariant): correctly rounded (.NET Core 3.0+), as strtof
+template <class Fmt> int Int32Parse(const String &t, const Fmt &) { return (int)std::strtol(t.s.c_str(), nullptr, 10); }
+template <class T> struct HashSet {
+    std::vector<T> order;
+    std::unordered_map<T, int> index;
+    bool Add(const T &x) { if (index.count(x)) return false; index[x] = (int)order.size(); order.push_back(x); return true; }
+    int Count() const { return (int)order.size(); }
+    typename std::vector<T>::const_iterator begin() const { return order.begin(); }
+    typename std::vector<T>::const_iterator end() const { return order.end(); }
+};
+template <class K, class V> struct KeyValuePair { K Key; V Value; };
+template <class K, class V> struct Dictionary {
+    std::vector<KeyValuePair<K, V>> items;
+    std::unordered_map<K, int> index;
+    Dictionary() {}
+    explicit Dictionary(int) {}
+    bool TryGetValue(const K &k, V &out) const { auto it = index.find(k); if (it == index.end()) return false; out = items[(size_t)it->second].Value; return true; }
+    V &operator[](const K &k) { auto it = index.find(k); if (it != index.end()) return items[(size_t)it->second].Value; index[k] = (int)items.size(); items.push_back({k, V()}); return items.back().Value; }
+    typename std::vector<KeyValuePair<K, V>>::iterator begin() { return items.begin(); }
+    typename std::vector<KeyValuePair<K, V>>::iterator end() { return items.end(); }
+};
+// a List<T> held by several names at once (a C# class instance): copies alias
+template <class T> struct RList {
+    std::shared_ptr<std::vector<T>> p;
+    RList() {}
+    explicit RList(int capacity) : p(new std::vector<T>()) { p->reserve((size_t)capacity); }
+    void Add(const T &x) { p->push_back(x); }
+    int Count() const { return (int)p->size(); }
+    T &operator[](int i) const { return (*p)[(size_t)i]; }
+};
+struct Face3 { int a, b, c; }; // the value tuple (int a, int b, int c)
 template <class T> using Comparison = std::function<int(const T &, const T &)>;
 inline int SingleCompareTo(float a, float b) { // System.Single.CompareTo
     if (a < b) return -1;

@@ -16,7 +16,8 @@ What is transpiled (and then compared with the oracle, bit for bit, by tests/tes
   RayTracing/Vec3.cs (whole), RayTracing/RaytraceSampler.cs (whole: blue noise, Rng, PerFrameSeed, SplitMix64,
   CosineSampleHemisphere), RayTracing/ToneMapper.cs (whole), Renderer/Chexel.cs (whole), the ANSI-256 quantiser of
   Renderer/ANSITerminalRenderer.cs and its Render with the Append* helpers (the byte stream), RayTracing/TemporalAA.cs (constructor,
-  ShouldResetHistory, CommitCamera, Resize), and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
+  ShouldResetHistory, CommitCamera, Resize), RayTracing/MeshLoader.cs (whole) with MeshScenes.TryReadObjBoundsNormalized and the
+  ground placement of AddMeshAutoGround, and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
   the BSDF helpers, and -- verbatim -- the tail of TryFlipAndBlit from the TAA call to the cell loop (:218-264), i.e. the
   reference's own buffer juggling, including the swap at :718 that makes the second a-trous iteration run in place.
 """
@@ -341,6 +342,45 @@ def main(ref, out_path):
     mtxt = re.sub(r"\bbvh\.(?=[A-Z])", "bvh->", mtxt)
     mtxt = rewrite(mtxt).replace("bvh = new MeshBVH(", "bvh = new MeshBVH(")
     out.append("struct Mesh : Hittable {\n%s\n};\n" % mtxt)
+    # ---- MeshLoader.cs (FromObj with its OBJ reader, ParseIndex, NormalizeAllUsedVertices) and, of Scenes/MeshScenes.cs, TryReadObjBoundsNormalized
+    # (:186-331) with the three lines of AddMeshAutoGround that place the mesh on the ground (:175-182): what decides the triangles a mesh scene uploads
+    def mesh_text(t):
+        t = re.sub(r"using \(var sr = new StreamReader\(path\)\)", "if (StreamReader sr(path); true)", t)                     # using (...) { } : a scope
+        t = re.sub(r"(\w+)\.Split\(\(char\[\]\)null, StringSplitOptions\.RemoveEmptyEntries\)", r"\1.SplitWhitespace()", t)
+        t = re.sub(r"\bstring\[\] (\w+) =", r"std::vector<String> \1 =", t)
+        t = re.sub(r"\bfloat\.Parse\(", "SingleParse(", t)
+        t = re.sub(r"\bint\.Parse\(", "Int32Parse(", t)
+        t = re.sub(r"\bstring\.(?=[A-Z])", "String::", t)
+        t = re.sub(r"\bstring\b", "String", t)
+        t = re.sub(r"List<\(int a, int b, int c\)>|List<\(int, int, int\)>", "List<Face3>", t)                               # the value tuple -> a struct with the same field names
+        t = re.sub(r"\.Add\(\((vIdx\[0\], vIdx\[i - 1\], vIdx\[i\])\)\);", r".Add(Face3{\1});", t)
+        t = re.sub(r"= \((remap\[f\.a\], remap\[f\.b\], remap\[f\.c\])\);", r"= Face3{\1};", t)
+        t = re.sub(r"\bvar \((\w+), (\w+), (\w+)\) =", r"auto [\1, \2, \3] =", t)                                           # deconstruction -> structured binding
+        t = re.sub(r"Vec3\? translate = null", "std::optional<Vec3> translate = std::nullopt", t)
+        t = re.sub(r"translate \?\? (new Vec3\([^)]*\))", r"translate.value_or(\1)", t)
+        t = re.sub(r"\bref Vec3\[\] (\w+)", r"std::vector<Vec3> &\1", t)
+        t = re.sub(r"\bVec3\[\] (\w+) = (\w+)\.ToArray\(\);", r"std::vector<Vec3> \1 = \2.ToArray();", t)
+        t = re.sub(r"Dictionary<int, List<int>>", "Dictionary<int, RList<int>>", t)                                          # List<int> instances shared between the dictionary and a local
+        t = re.sub(r"if \(!compToFaces\.TryGetValue\(r, out var list\)\) \{ list = new List<int>\(64\);", "RList<int> list;\n                if (!compToFaces.TryGetValue(r, list)) { list = RList<int>(64);", t)
+        t = re.sub(r"new ((?:List|HashSet|Dictionary|RList)<[^()]*>)\(", r"\1(", t)                                          # collections are constructed in place
+        t = re.sub(r"List<Triangle> (\w+) = List<Triangle>\(", r"List<Triangle *> \1 = List<Triangle *>(", t)
+        t = re.sub(r"\b(positions|faces|fi|keptFaces|usedVerts)\.Count\b(?!\()", r"\1.Count()", t)                          # Count is a property
+        t = re.sub(r"\bkv\.Value\.Count\b", "kv.Value.Count()", t)
+        t = re.sub(r"foreach \((?:int|var) (\w+) in (\w+)\)", r"for (auto &\1 : \2)", t)
+        t = re.sub(r"^(\s*)int Find\(int x\) \{(.*)\}\s*$", r"\1auto Find = [&](int x) -> int {\2};", t, flags=re.M)                # local functions -> lambdas
+        t = re.sub(r"^(\s*)void Union\(int x, int y\) \{(.*)\}\s*$", r"\1auto Union = [&](int x, int y) -> void {\2};", t, flags=re.M)
+        t = re.sub(r"\bstatic Mesh FromObj\(", "static List<Triangle *> FromObj(", t)                                        # the triangle list itself: Mesh (-> MeshBVH) is built from it elsewhere
+        t = re.sub(r"return new Mesh\(tris, mn, mx\);", "return tris;", t)
+        t = rewrite(t, None, statics=("CultureInfo", "File"))
+        return re.sub(r"\bfaces\[(\w+)\]->", r"faces[\1].", t)   # `faces` is a list of value tuples here (rewrite() knows the name from Box: a list of references)
+    ml = mesh_text(type_body(rd("RayTracing/MeshLoader.cs"), "MeshLoader"))
+    out.append("struct MeshLoaderRef {\n%s\n};\n" % ml)
+    msb = type_body(rd("RayTracing/Scenes/MeshScenes.cs"), "MeshScenes")
+    msel = [t for t, n in members(msb) if n in ("TryReadObjBoundsNormalized", "ParseIndex")]
+    ag = [t for t, n in members(msb) if n == "AddMeshAutoGround"][0]
+    a3, b3 = ag.index("Vec3 mnN, mxN;"), ag.index("s.Objects.Add(")
+    msel.append("static Vec3 AutoGroundTranslate(string objPath, float scale, Vec3 targetPos)\n{\n" + ag[a3:b3] + "\n    return translate;\n}\n")
+    out.append("struct MeshScenesRef {\n%s\n};\n" % mesh_text("\n".join(msel)))
     out.append(emit_struct(rd("RayTracing/Objects/PointLight.cs"), "PointLight"))
     out.append(emit_struct(rd("RayTracing/Objects/AmbientLight.cs"), "AmbientLight"))
     ssrc = type_body(rd("RayTracing/Scenes/Scene.cs"), "Scene")

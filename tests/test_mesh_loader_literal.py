@@ -121,3 +121,44 @@ def test_mesh_loader_and_auto_ground_match_a_literal_transcription(scene, asset)
     assert got.shape == tris.shape
     assert np.array_equal(got.view(np.uint32), tris.view(np.uint32)), f"{scene}: {int((got != tris).any(1).sum())} triangles differ"
     s.close()
+
+
+REF_SO = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "libycge_ref.so")
+
+
+@pytest.mark.parametrize("scene,asset", [("teapot", "teapot"), ("cow", "cow"), ("bunny", "stanford-bunny")])
+def test_mesh_loader_equals_the_reference_source(scene, asset, tmp_path):
+    """The same triangles from THE REFERENCE'S OWN TEXT: MeshLoader.cs (FromObj with its OBJ reader, ParseIndex,
+    NormalizeAllUsedVertices) and MeshScenes.TryReadObjBoundsNormalized + the ground placement of AddMeshAutoGround, rewritten
+    into C++ syntactically at build time (oracle/ref_transpile.py -> oracle/_ref), read an OBJ file and return the triangles a mesh
+    scene gets; the host mirror's -- the ones uploaded to the GPU -- must equal them bit for bit.  The OBJ text is written here
+    from the committed binary twin of the asset (9 significant digits: every binary32 survives the round trip), or is the
+    reference's own file where the checkout is present."""
+    import ctypes as C
+    so = os.path.normpath(REF_SO)
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libycge_ref.so is not built (needs /root/reference at build time)")
+    ref = C.CDLL(so)
+    ref.ref_mesh_from_obj.argtypes = [C.c_char_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    xyz, faces = read_ymesh(os.path.join(GOLDEN, "meshes", asset + ".ymesh"))
+    path = str(tmp_path / (asset + ".obj"))
+    with open(path, "w") as f:
+        f.write("# written from the binary twin\n")
+        for v in xyz:
+            f.write("v %.9g %.9g %.9g\n" % (float(v[0]), float(v[1]), float(v[2])))
+        for a, b, c in faces.tolist():
+            f.write("f %d/%d %d//%d %d\n" % (a + 1, a + 1, b + 1, b + 1, c + 1))     # v/vt, v//vn and plain v: ParseIndex takes what precedes the first '/'
+    paths = [path]
+    if os.path.exists(os.path.join(ASSETS, asset + ".obj")):
+        paths.append(os.path.join(ASSETS, asset + ".obj"))                           # the reference's own file (quads fan-triangulated by FromObj itself)
+    s = api.HostScene(scene)
+    want = s.mesh_triangles(0)
+    target = np.array([0.0, 0.5, 1.0], F)                                            # targetPos of the mesh scenes (MeshScenes.cs:108-133), scale 1
+    for pth in paths:
+        n = ref.ref_mesh_from_obj(pth.encode(), 1.0, target.ctypes.data, None, 0, None)
+        assert n == len(want), (pth, n, len(want))
+        got, tr = np.empty((n, 9), F), np.empty(3, F)
+        assert ref.ref_mesh_from_obj(pth.encode(), 1.0, target.ctypes.data, got.ctypes.data, n, tr.ctypes.data) == n
+        assert tr[0] == 0.0 and tr[2] == 1.0 and 0.0 < tr[1] < 2.0
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{scene} ({pth}): {int((got != want).any(1).sum())} triangles differ"
+    s.close()
