@@ -25,7 +25,20 @@ RH_API void *ref_renderer_create(int fb_w, int fb_h, int ss, int proc_count) {
     h->target = Fast2D<Chexel>(fb_w, fb_h);
     h->fb.reset(new Framebuffer(fb_w, fb_h));
     h->taa.reset(new TemporalAA(h->W, h->H, h->r.taaAlpha, RendererRef::MotionTransReset, RendererRef::MotionRotReset)); // :96
+    h->r.taa = h->taa.get();
     return h;
+}
+// RaytraceRenderer.Resize (:110-138) as the reference wrote it: planes and history reallocated, taa.Resize, taaHistoryValid = false;
+// the tone mapper (aeExposure) and the frame counter stay.  The trace half of the harness is resized by ref_trace_resize.
+RH_API int ref_renderer_resize(void *hh, int fb_w, int fb_h, int ss) {
+    Handle &h = *(Handle *)hh;
+    try {
+        h.fb.reset(new Framebuffer(fb_w, fb_h));
+        h.r.Resize(h.fb.get(), ss);
+        h.W = h.r.hiW; h.H = h.r.hiH;
+        h.target = h.r.frameBuffer; // `var target = frameBuffer;` (:181)
+        return 0;
+    } catch (...) { return -1; }
 }
 RH_API void ref_renderer_destroy(void *hh) { delete (Handle *)hh; }
 // TryFlipAndBlit :171 (without `|| scene.HasDynamicTextures`) and :266; Resize :128
@@ -239,6 +252,7 @@ struct TraceHandle {
     SceneRef scene;
     RendererRef r;
     std::vector<Hittable *> owned;
+    std::unique_ptr<TemporalAA> taa; // only so that the reference's Resize finds its `taa` (the decisions are taken on the post handle's)
 };
 }
 RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_obj, const int *kind, const float *p12, const float *mat_a13, const float *mat_b13,
@@ -306,6 +320,15 @@ RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_o
     } catch (...) { return nullptr; }
 }
 RH_API void ref_trace_destroy(void *hh) { TraceHandle *h = (TraceHandle *)hh; for (Hittable *o : h->owned) delete o; delete h; }
+RH_API int ref_trace_resize(void *hh, int fb_w, int fb_h, int ss) { // the same Resize on the trace half: rays and G-buffer planes at the new size, frame counter kept
+    TraceHandle &h = *(TraceHandle *)hh;
+    try {
+        if (!h.taa) { h.taa.reset(new TemporalAA(h.r.hiW, h.r.hiH, h.r.taaAlpha, RendererRef::MotionTransReset, RendererRef::MotionRotReset)); h.r.taa = h.taa.get(); }
+        Framebuffer fb(fb_w, fb_h);
+        h.r.Resize(&fb, ss);
+        return 0;
+    } catch (...) { return -1; }
+}
 // one frame of the trace stage; planes out (row-major hiW x hiH)
 RH_API int ref_trace_frame(void *hh, const float *cam3, float yaw, float pitch, float *rays6, float *hdr3, float *albedo3, float *normal3, float *depth, uint8_t *sky) {
     TraceHandle &h = *(TraceHandle *)hh;

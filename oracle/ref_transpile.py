@@ -402,9 +402,9 @@ def main(ref, out_path):
     fields = {"taaAlpha", "taaHistory", "taaHistoryValid", "prevNormal", "prevDepth", "prevSky", "spatialA", "spatialB", "gAlbedo", "gNormal", "gDepth", "skyMask",
               "toneMapper", "threadpool", "procCount", "ss", "fbW", "fbH", "Pi", "InvPi", "DiffuseSigmaDeg", "Eps", "MirrorThreshold"}
     fields |= {"hiW", "hiH", "fovDeg", "rays", "currentHdr", "pixelPool", "frameCounter", "frameBuffer", "scene"}
-    fields |= {"MotionTransReset", "MotionRotReset"}
+    fields |= {"MotionTransReset", "MotionRotReset", "taa"}
     fields |= {"DiffuseBounces", "IndirectSamples", "MaxMirrorBounces", "MaxRefractions", "SeedSalt", "MaxLuminance", "PrimaryGBuffer", "PathWorkItem"}
-    funcs = {"Luma", "TemporalBlendWithClamp", "ApplyAtrousDenoise", "OrenNayarBRDF", "FresnelSchlick", "Refract", "Reflect", "Lerp", "SampleAlbedo", "ForwardFromYawPitch",
+    funcs = {"Resize", "Luma", "TemporalBlendWithClamp", "ApplyAtrousDenoise", "OrenNayarBRDF", "FresnelSchlick", "Refract", "Reflect", "Lerp", "SampleAlbedo", "ForwardFromYawPitch",
              "MakeJitteredRay", "TraceFull", "ComputeTransmittanceToLight", "CosineSampleHemisphere"}
     sel = [t for t, n in mem if n in fields] + [t for t, n in mem if n in funcs]
     flip = [t for t, n in mem if n == "TryFlipAndBlit"][0]
@@ -422,6 +422,11 @@ def main(ref, out_path):
     sel.append("void TraceStage(Vec3 camPosSnapshot, float yawSnapshot, float pitchSnapshot)\n{\n" + head + "\n}\n")
     body = "\n".join(sel)
     body = re.sub(r"^\s*(?:private |public )?(?:readonly )?Scene scene;", "SceneRef *scene = nullptr;", body, flags=re.M)
+    # Resize (:110-138): TemporalAA and Framebuffer are classes -> references
+    body = re.sub(r"^\s*(?:private |public )?TemporalAA taa;", "TemporalAA *taa = nullptr;", body, flags=re.M)
+    body = re.sub(r"\btaa\.(?=[A-Z])", "taa->", body)
+    body = re.sub(r"void Resize\(Framebuffer framebuffer,", "void Resize(Framebuffer *framebuffer,", body)
+    body = re.sub(r"\bframebuffer\.(?=[A-Z])", "framebuffer->", body)
     body = re.sub(r"\bScene scene\b", "SceneRef &scene", body)
     body = re.sub(r"\bscene is [\w.]*VolumeScene\b", "scene.IsVolumeScene", body)
     body = re.sub(r"\bscene\.Lights\.Count\b", "scene.Lights.Count()", body)

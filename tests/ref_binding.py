@@ -31,6 +31,8 @@ def load():
     lib.ref_taa_should_reset.argtypes = [vp, vp, C.c_float, C.c_float]
     lib.ref_taa_commit_camera.argtypes = [vp, vp, C.c_float, C.c_float]
     lib.ref_taa_resize.argtypes = [vp]
+    lib.ref_renderer_resize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.ref_trace_resize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     return lib
 
 
@@ -101,6 +103,12 @@ class RefRenderer:
         assert rc == 0
         self.lib.ref_taa_commit_camera(self.post, P(c3), np.float32(self.cam[1]), np.float32(self.cam[2]))
         return o
+
+    def resize(self, fb_w, fb_h, ss):
+        """RaytraceRenderer.Resize (:110-138), the reference's own text, on both halves of the harness."""
+        assert self.lib.ref_trace_resize(self.trace, fb_w, fb_h, ss) == 0
+        assert self.lib.ref_renderer_resize(self.post, fb_w, fb_h, ss) == 0
+        self.fb_w, self.fb_h, self.ss = fb_w, fb_h, ss
 
     def close(self):
         if self.trace:

@@ -244,6 +244,37 @@ def test_history_reset_follows_the_reference_camera_thresholds(ref):
     s.close()
 
 
+def test_resize_follows_the_reference_source(ref):
+    """RaytraceRenderer.Resize (:110-138) as the reference wrote it, in the middle of a run: two frames at 16x6 cells ss = 2, Resize to
+    20x5 cells ss = 3, two more frames, Resize back.  What the text implies -- history invalid (the first frame after it is a plain
+    copy although the camera did not move), camera memory forgotten (taa.Resize), auto-exposure state and frame counter (hence the
+    RNG seeds and jitter) carried over -- must come out of the oracle's resize the same way: rays, TAA history, denoised image,
+    exposure and cells bit for bit on every frame."""
+    import ref_binding
+    s = api.HostScene("cornell")
+    rr = ref_binding.RefRenderer(s, 16, 6, 2)
+    o = Oracle(s, 16, 6, 2)
+    frame = 0
+    for fb_w, fb_h, ss in [(16, 6, 2), (20, 5, 3), (16, 6, 2)]:
+        if frame:
+            rr.resize(fb_w, fb_h, ss)
+            o.resize(fb_w, fb_h, ss)
+        for _ in range(2):
+            frame += 1
+            a = rr.render_frame()
+            c = o.render_frame(threads=1, fast_post=False)
+            what = f"frame {frame} at {fb_w}x{fb_h} ss={ss}"
+            assert not rr.last_reset, what + ": the camera never moves"
+            assert np.array_equal(bits(a["rays"]), bits(o.debug_read(api.DBG_RAYS))), what + ": rays (frame counter carried over)"
+            assert np.array_equal(bits(a["taa"]), bits(o.debug_read(api.DBG_TAA)[..., :3])), what + ": TAA history"
+            assert np.array_equal(bits(a["den"]), bits(o.debug_read(api.DBG_DENOISED)[..., :3])), what + ": denoised"
+            assert bits(a["expo"][:1])[0] == bits(np.float32(o.stats()["ae_exposure"]))[()], what + ": aeExposure (carried over)"
+            assert np.array_equal(a["fg_ansi"], c["fg_ansi"]) and np.array_equal(a["bg_ansi"], c["bg_ansi"]) and np.array_equal(a["fg16"], c["fg16"]), what + ": cells"
+    rr.close()
+    o.close()
+    s.close()
+
+
 PRIM_SCENES = ["cornell", "mirror_spheres", "boxes", "cylinders_disks_triangles", "test", "texture_gallery"]
 
 
