@@ -113,6 +113,18 @@ RH_API void ref_oren_nayar(const float *albedo3, const float *n3, const float *w
 RH_API int ref_ansi256(float r, float g, float b) { return AnsiRef::ChexelToAnsi256(ChexelColor(Vec3(r, g, b))); }
 RH_API int ref_nearest16(float r, float g, float b) { return (int)ChexelColor(Vec3(r, g, b)).color_16; }
 RH_API int ref_linear_to_srgb8(double c) { return AnsiRef::LinearToSrgb8(c); }
+// Texture.SampleBilinear (Texture.cs:108-163, static image) and RaytraceRenderer.SampleAlbedo (:724-735) over a w x h image of RGBA words, row 0 first
+RH_API void ref_texture_sample(int w, int hh, const uint32_t *rgba, float u, float v, float *out3) {
+    Texture t; t.width = w; t.height = hh; t.pixels.assign((const int *)rgba, (const int *)rgba + (size_t)w * hh);
+    const Vec3 c = t.SampleBilinear(u, v);
+    out3[0] = c.X; out3[1] = c.Y; out3[2] = c.Z;
+}
+RH_API void ref_sample_albedo(const float *albedo3, double texture_weight, double uv_scale, int w, int hh, const uint32_t *rgba, float u, float v, float *out3) {
+    Texture t; t.width = w; t.height = hh; t.pixels.assign((const int *)rgba, (const int *)rgba + (size_t)w * hh);
+    Material m; m.Albedo = Vec3(albedo3[0], albedo3[1], albedo3[2]); m.DiffuseTexture = rgba ? &t : nullptr; m.TextureWeight = texture_weight; m.UVScale = uv_scale;
+    const Vec3 c = RendererRef::SampleAlbedo(m, Vec3(0.0f, 0.0f, 0.0f), Vec3(0.0f, 1.0f, 0.0f), u, v);
+    out3[0] = c.X; out3[1] = c.Y; out3[2] = c.Z;
+}
 RH_API int ref_map_attributes(int fg16, int bg16) { return (int)Win32Ref::MapAttributes((ConsoleColor)fg16, (ConsoleColor)bg16); } // Win32TerminalRenderer.cs:109-112
 // ANSITerminalRenderer.Render (:86-153) over one Framebuffer of fb_w x fb_h cells (row-major glyph / fg rgb / bg rgb) placed at (vx, vy) on a
 // console of console_w x console_h cells; the renderer believes the console to be known_w x known_h (differs -> the resize prologue).
@@ -139,10 +151,16 @@ RH_API int ref_ansi_render(int fb_w, int fb_h, const uint16_t *glyph, const floa
 
 // ---- the analytic primitives: objects built by the reference's own constructors from the flat scene description
 // (include/ycge.h: ycge_object.p = the public fields after the ctor ran), rays against the reference's own Hit methods.
-// Materials: 13 floats (albedo3, specular, reflectivity, emission3, transparency, ior, transmission3).
+// Materials: MS = 16 floats (albedo3, specular, reflectivity, emission3, transparency, ior, transmission3, texture id or -1, texture weight,
+// uv scale); a texture id names an image handed over before by ref_set_textures (static images: `new Texture(path)`, Texture.cs:25-49).
 namespace {
+constexpr int MS = 16;
+std::vector<std::unique_ptr<Texture>> g_textures;
 Material mat_of(const float *m) {
-    return Material(Vec3(m[0], m[1], m[2]), (double)m[3], (double)m[4], Vec3(m[5], m[6], m[7]), (double)m[8], (double)m[9], Vec3(m[10], m[11], m[12]));
+    Material r(Vec3(m[0], m[1], m[2]), (double)m[3], (double)m[4], Vec3(m[5], m[6], m[7]), (double)m[8], (double)m[9], Vec3(m[10], m[11], m[12]));
+    const int tex = (int)m[13];
+    if (tex >= 0 && tex < (int)g_textures.size()) { r.DiffuseTexture = g_textures[(size_t)tex].get(); r.TextureWeight = (double)m[14]; r.UVScale = (double)m[15]; }
+    return r;
 }
 Hittable *make_prim(int kind, const float *p, const float *ma, const float *mb, float checker_scale, float spec, float refl) {
     const Material A = mat_of(ma);
@@ -162,12 +180,22 @@ Hittable *make_prim(int kind, const float *p, const float *ma, const float *mb, 
     return nullptr;
 }
 }
+// the scene's static images for the materials of the objects created AFTER this call (kept until the next call): w x h RGBA words, row 0 first
+RH_API void ref_set_textures(int n, const int *w, const int *hh, const uint32_t *const *rgba) {
+    g_textures.clear();
+    for (int i = 0; i < n; i++) {
+        std::unique_ptr<Texture> t(new Texture());
+        t->width = w[i]; t->height = hh[i];
+        t->pixels.assign((const int *)rgba[i], (const int *)rgba[i] + (size_t)w[i] * hh[i]);
+        g_textures.push_back(std::move(t));
+    }
+}
 // nearest hit over the objects IN ORDER with a shrinking tMax (what a leaf of BVH.Hit does with its items, BVH.cs:160-178)
 RH_API int ref_objects_hit(int n_obj, const int *kind, const float *p12, const float *mat_a13, const float *mat_b13, const float *checker_scale, const float *spec, const float *refl,
                            int n, const float *rays6, float t_min, float t_max, int *id_out, float *t_out, float *n_out3, float *p_out3, float *mat_out5) {
     std::vector<Hittable *> objs;
     for (int k = 0; k < n_obj; k++) {
-        objs.push_back(make_prim(kind[k], p12 + 12 * k, mat_a13 + 13 * k, mat_b13 + 13 * k, checker_scale[k], spec[k], refl[k]));
+        objs.push_back(make_prim(kind[k], p12 + 12 * k, mat_a13 + MS * k, mat_b13 + MS * k, checker_scale[k], spec[k], refl[k]));
         if (!objs.back()) return -1;
     }
     for (int i = 0; i < n; i++) {
@@ -266,7 +294,7 @@ RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_o
         for (int k = 0; k < n_obj; k++) {
             Hittable *o = nullptr;
             if (kind[k] == 9) { // Mesh: MeshLoader's triangles through the reference's Mesh / MeshBVH constructors
-                const Material m = mat_of(mesh_mat13 + 13 * mi);
+                const Material m = mat_of(mesh_mat13 + MS * mi);
                 std::vector<Triangle *> tris;
                 for (int i = 0; i < mesh_tris[mi]; i++) {
                     const float *t = mesh_abc9[mi] + 9 * (size_t)i;
@@ -288,7 +316,7 @@ RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_o
                 g->wireframe = v.wireframe != 0; g->wireWidthFrac = v.wire_width_frac; g->wireMaxDistance = v.wire_max_distance;
                 std::vector<int> table(v.palette, v.palette + (size_t)v.palette_n_ids * (v.palette_meta_levels < 1 ? 1 : v.palette_meta_levels));
                 std::vector<Material> mats;
-                for (int m = 0; m < n_mats; m++) mats.push_back(mat_of(scene_mats13 + 13 * m));
+                for (int m = 0; m < n_mats; m++) mats.push_back(mat_of(scene_mats13 + MS * m));
                 const int n_ids = v.palette_n_ids, levels = v.palette_meta_levels < 1 ? 1 : v.palette_meta_levels, def = v.palette_default;
                 g->materialLookup = [table, mats, n_ids, levels, def](int id, int meta) { // ycge.h: the palette as data
                     if (id >= n_ids || id < 0) return mats[(size_t)def];
@@ -296,7 +324,7 @@ RH_API void *ref_trace_create(int fb_w, int fb_h, int ss, float fov_deg, int n_o
                     return mats[(size_t)table[(size_t)id * levels + m]];
                 };
                 o = g;
-            } else o = make_prim(kind[k], p12 + 12 * k, mat_a13 + 13 * k, mat_b13 + 13 * k, checker_scale[k], spec[k], refl[k]);
+            } else o = make_prim(kind[k], p12 + 12 * k, mat_a13 + MS * k, mat_b13 + MS * k, checker_scale[k], spec[k], refl[k]);
             if (!o) { delete h; return nullptr; }
             h->owned.push_back(o);
             h->scene.Objects.Add(o);
@@ -349,7 +377,6 @@ RH_API int ref_trace_frame(void *hh, const float *cam3, float yaw, float pitch, 
         return 0;
     } catch (...) { return -1; }
 }
-refcs::Vec3 refcs::Texture::SampleBilinear(float, float) { throw std::runtime_error("textured scenes are not run through the transpiled reference"); }
 
 // worker threads of FixedThreadFor / PixelThreadPool (the reference uses Environment.ProcessorCount); 1 = serial
 RH_API void ref_set_threads(int n) { refcs::ref_threads() = n < 1 ? 1 : n; }

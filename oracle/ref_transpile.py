@@ -137,7 +137,7 @@ def rewrite(t, struct_name=None, statics=()):
     t = re.sub(r"\bconst (\w+) (\w+)\s*=", r"static constexpr \1 \2 =", t)                                                          # C# const members are static
     t = re.sub(r"\.Length\b", ".size()", t)
     # new
-    t = re.sub(r"\bnew ((?:Fast2D<\w+>|Vec3|Material|Ray|HitRecord|Chexel|ChexelColor|RaytraceSampler\.Rng|PathWorkItem|PrimaryGBuffer)\s*\()", r"\1", t)  # value types (and the Fast2D handle) are constructed in place
+    t = re.sub(r"\bnew ((?:Fast2D<\w+>|Vec3|Material|Ray|HitRecord|Chexel|ChexelColor|RGBA32|RaytraceSampler\.Rng|PathWorkItem|PrimaryGBuffer)\s*\()", r"\1", t)  # value types (and the Fast2D handle) are constructed in place
     t = re.sub(r"\bHittable\[\] (\w+);", r"std::vector<Hittable *> \1;", t)
     t = re.sub(r"\b(\w+) = new Hittable\[(\w+)\];", r"\1.assign(\2, nullptr);", t)
     t = re.sub(r"\bfaces\[(\w+)\]\.", r"faces[\1]->", t)
@@ -303,7 +303,22 @@ def main(ref, out_path):
     rt = re.sub(r"^(\s*)((?:int|ConsoleColor) \w+);", r"\1\2 = {};", rt, flags=re.M)                    # C# zero-initialises fields
     out.append("struct AnsiRenderRef : AnsiRef {\n    std::vector<byte> flushed;\n    void Flush() { flushed.insert(flushed.end(), outBuf.begin(), outBuf.begin() + outLen); }\n%s\n};\n" % rt)
     # ---- the analytic primitives and what their Hit needs
-    out.append("struct Vec3;\nstruct Texture { Vec3 SampleBilinear(float u, float v); }; // textured scenes are not run through the transpiled reference\n")
+    # ---- Renderer/RGBA32.cs (the packed pixel: the int constructor and toVec3) and Renderer/Texture.cs: the static-image half of SampleBilinear
+    # (:108-163 without the live-frame branch, removed mechanically), Lerp, Frac; pixels / width / height are filled by the harness
+    rg = type_body(rd("Renderer/RGBA32.cs"), "RGBA32")
+    rsel = [t for t, n in members(rg) if n in ("a", "g", "b", "r", "toVec3") or (n == "RGBA32" and "(int value)" in t)]
+    out.append("struct RGBA32 {\n%s\n};\n" % rewrite("\n".join(rsel), None))
+    tx = type_body(rd("Renderer/Texture.cs"), "Texture")
+    tsel = "\n".join(t for t, n in members(tx) if n in ("pixels", "width", "height", "SampleBilinear", "Lerp", "Frac"))
+    m_dyn = re.search(r"if \(isDynamic && dynamicReader != null\)", tsel)
+    b0 = tsel.index("{", m_dyn.end())
+    tsel = tsel[:m_dyn.start()] + tsel[block_end(tsel, b0):]
+    tsel = re.sub(r"\bint\[\] pixels;", "std::vector<int> pixels;", tsel)
+    tsel = re.sub(r"if \(pixels == null\)", "if (pixels.empty())", tsel)
+    tsel = re.sub(r"static float Frac\(float x\) => ([^;]+);", r"static float Frac(float x) { return \1; }", tsel)
+    tsel = rewrite(tsel, None)
+    tsel = re.sub(r"^(\s*)(int \w+);", r"\1\2 = {};", tsel, flags=re.M)
+    out.append("struct Texture {\n%s\n};\n" % tsel)
     out.append(emit_struct(rd("RayTracing/Ray.cs"), "Ray"))
     out.append(emit_struct(rd("RayTracing/Material.cs"), "Material"))
     out.append(emit_struct(rd("RayTracing/HitRecord.cs"), "HitRecord"))

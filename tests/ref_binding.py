@@ -41,7 +41,22 @@ def P(a):
 
 
 def mat13(m):
-    return list(m.albedo) + [m.specular, m.reflectivity] + list(m.emission) + [m.transparency, m.ior] + list(m.transmission)
+    """one material row of the harness: 16 floats (ref_harness.cpp MS): the 13 scalars of Material + texture id (-1: none), weight, uv scale"""
+    return list(m.albedo) + [m.specular, m.reflectivity] + list(m.emission) + [m.transparency, m.ior] + list(m.transmission) + [float(m.tex_id), m.tex_weight, m.uv_scale]
+
+
+MAT_PAD = [[0.0] * 13 + [-1.0, 0.0, 0.0]]
+
+
+def set_textures(lib, scene):
+    """hands the scene's static images (Texture.cs:81-90 layout) to the harness; the arrays must stay alive while objects are created"""
+    tex = [np.ascontiguousarray(scene.texture(i), np.uint32) for i in range(scene.n_textures)]
+    w = np.array([t.shape[1] for t in tex] + [0], np.int32)
+    h = np.array([t.shape[0] for t in tex] + [0], np.int32)
+    ptrs = (C.c_void_p * max(1, len(tex)))(*[t.ctypes.data for t in tex])
+    lib.ref_set_textures.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ref_set_textures(len(tex), P(w), P(h), ptrs)
+    return tex
 
 
 class RefRenderer:
@@ -65,13 +80,14 @@ class RefRenderer:
         meshes = [np.ascontiguousarray(scene.mesh_triangles(i), np.float32) for i in range(scene.n_meshes)]
         mesh_n = np.array([len(m) for m in meshes] + [0], np.int32)
         mesh_ptrs = (C.c_void_p * max(1, len(meshes)))(*[m.ctypes.data for m in meshes])
-        mesh_mat = np.array([mat13(scene.mesh(i).contents.material) for i in range(scene.n_meshes)] + [[0] * 13], np.float32)
+        mesh_mat = np.array([mat13(scene.mesh(i).contents.material) for i in range(scene.n_meshes)] + MAT_PAD, np.float32)
         lights = np.array([list(f.lights[i].pos) + list(f.lights[i].color) + [f.lights[i].intensity] for i in range(f.n_lights)] + [[0] * 7], np.float32)
         top, bot = np.array(list(f.bg_top), np.float32), np.array(list(f.bg_bottom), np.float32)
         amb = np.array(list(f.ambient_color) + [f.ambient_intensity], np.float32)
         vols = (api.Volume * max(1, scene.n_volumes))(*[scene.volume(i).contents for i in range(scene.n_volumes)])
-        all_mats = np.array([mat13(f.materials[i]) for i in range(f.n_materials)] + [[0] * 13], np.float32)
+        all_mats = np.array([mat13(f.materials[i]) for i in range(f.n_materials)] + MAT_PAD, np.float32)
         self.keep += [meshes, vols]
+        set_textures(self.lib, scene)  # copied by the harness; materials with a texture id point at them
         fov = scene.default_camera()[3]
         self.trace = self.lib.ref_trace_create(fb_w, fb_h, ss, fov, n, P(kind), P(p12), P(ma), P(mb), P(cs), P(sp), P(rf), P(mesh_n), mesh_ptrs, P(mesh_mat), f.n_lights, P(lights),
                                                P(top), P(bot), P(amb), scene.n_volumes, C.cast(vols, C.c_void_p), f.n_materials, P(all_mats), f.is_volume_scene)

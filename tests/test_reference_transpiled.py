@@ -210,6 +210,43 @@ def test_ansi_byte_stream_equals_the_reference_source(ref):
     assert got == want
 
 
+@pytest.mark.parametrize("scene,pose", [("cornell", None), ("texture_gallery", None), ("volume_grid_test", None), ("teapot", api.BENCH_POSE)])
+def test_whole_frames_of_the_reference_source_equal_the_oracle(ref, scene, pose):
+    """RefRenderer -- the harness the GPU tests, smoke() and `bench.py --impl reference` drive: the verbatim head and tail of
+    TryFlipAndBlit with the reference's own TemporalAA decision -- against the oracle, three frames, every cell field."""
+    import ref_binding
+    s = api.HostScene(scene)
+    rr = ref_binding.RefRenderer(s, 40, 12, 2)
+    o = Oracle(s, 40, 12, 2)
+    if pose is not None:
+        rr.set_camera(*pose)
+        o.set_camera(*pose)
+    for f in range(3):
+        a, c = rr.render_frame(), o.render_frame(threads=2)
+        for k in ("glyph", "fg16", "bg16", "fg_ansi", "bg_ansi"):
+            assert np.array_equal(a[k], c[k]), f"{scene} frame {f + 1}: {k}"
+        assert np.array_equal(bits(a["fg"]), bits(c["fg"])) and np.array_equal(bits(a["bg"]), bits(c["bg"])), f"{scene} frame {f + 1}: SDR colours"
+    rr.close()
+    o.close()
+    s.close()
+
+
+def test_texture_sampler_equals_the_reference_source(ref, oracle_lib):
+    """Texture.SampleBilinear (static image: wrap by frac, (w - 1) scaling, the % wrap of the +1 texel, RGBA32.toVec3, two Lerps, Saturate)
+    and RGBA32's int constructor as the reference wrote them, against the oracle's sampler (which the device's equals on the GPU)."""
+    ref.ref_texture_sample.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    oracle_lib.yo_texture_sample.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    rng = np.random.default_rng(21)
+    for w, h in [(12, 6), (1, 1), (2, 5), (64, 64)]:
+        px = rng.integers(0, 1 << 32, size=(h, w), dtype=np.uint64).astype(np.uint32)
+        uv = [(0.0, 0.0), (1.0, 1.0), (0.5, 0.5), (-0.25, 2.75), (0.99999994, 0.99999994), (1e-8, -1e-8)] + [tuple(x) for x in rng.uniform(-3.0, 3.0, size=(300, 2))]
+        a, b = np.empty(3, np.float32), np.empty(3, np.float32)
+        for u, v in uv:
+            ref.ref_texture_sample(w, h, P(px), u, v, P(a))
+            oracle_lib.yo_texture_sample(w, h, P(px), u, v, P(b))
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (w, h, u, v)
+
+
 def test_history_reset_follows_the_reference_camera_thresholds(ref):
     """TryFlipAndBlit :171 / :266 with the reference's own TemporalAA.cs (ShouldResetHistory :58-67, CommitCamera): whole frames of the
     transpiled reference along a camera path that stays, creeps below the 0.0025 thresholds, jumps above them, turns by just less and
@@ -294,9 +331,11 @@ def test_primitive_hits_equal_the_reference_source(ref, scene):
     kind = np.array([f.objects[k].kind for k in range(n_obj)], np.int32)
     p12 = np.array([list(f.objects[k].p) for k in range(n_obj)], np.float32)
 
+    import ref_binding
+    textures = ref_binding.set_textures(ref, s)  # noqa: F841  (textured materials point at the harness's copies)
+
     def mat(i):
-        m = f.materials[i]
-        return list(m.albedo) + [m.specular, m.reflectivity] + list(m.emission) + [m.transparency, m.ior] + list(m.transmission)
+        return ref_binding.mat13(f.materials[i])
     ma = np.array([mat(f.objects[k].mat_a) for k in range(n_obj)], np.float32)
     mb = np.array([mat(f.objects[k].mat_b) for k in range(n_obj)], np.float32)
     cs = np.array([f.objects[k].checker_scale for k in range(n_obj)], np.float32)
@@ -389,10 +428,12 @@ def test_mesh_tree_and_hits_equal_the_reference_source(ref, scene):
 
 TRACE_CASES = [("cornell", 20, 8, 2, None), ("mirror_spheres", 24, 8, 2, None), ("boxes", 20, 8, 1, None), ("cylinders_disks_triangles", 20, 8, 2, None), ("test", 24, 9, 2, None),
                ("teapot", 20, 8, 2, api.BENCH_POSE), ("knot:40x10", 18, 7, 2, api.BENCH_POSE), ("cow", 16, 6, 2, api.BENCH_POSE),
-               ("volume_grid_test", 24, 9, 2, None), ("voxel_world:64x64", 20, 8, 2, None), ("voxel_island:64x64", 20, 8, 2, None)]
+               ("volume_grid_test", 24, 9, 2, None), ("voxel_world:64x64", 20, 8, 2, None), ("voxel_island:64x64", 20, 8, 2, None),
+               # textured materials: SampleAlbedo (:724-735) -> Texture.SampleBilinear (Texture.cs:108-163) of the reference's text, with the U, V its Hit methods report
+               ("texture_gallery", 32, 9, 2, None), ("texture_gallery", 24, 8, 2, ((1.2, 1.4, -0.6), 0.5, -0.3)), ("texture_test", 20, 8, 2, ((0.6, 0.4, 0.0), 0.25, -0.2))]
 
 
-@pytest.mark.parametrize("scene,fb_w,fb_h,ss,pose", TRACE_CASES, ids=[c[0] for c in TRACE_CASES])
+@pytest.mark.parametrize("scene,fb_w,fb_h,ss,pose", TRACE_CASES, ids=[f"{c[0]}-{k}" for k, c in enumerate(TRACE_CASES)])
 def test_trace_stage_equals_the_reference_source(ref, scene, fb_w, fb_h, ss, pose):
     """The whole trace stage as the reference wrote it: the scene's objects rebuilt by the reference's constructors (primitives, Mesh ->
     MeshBVH), Scene.RebuildBVH -> BVH.cs, then the verbatim head of TryFlipAndBlit -- frame counter, jitter rotations, MakeJitteredRay,
@@ -408,12 +449,12 @@ def test_trace_stage_equals_the_reference_source(ref, scene, fb_w, fb_h, ss, pos
     n_obj = f.n_objects
     assert all(f.objects[k].kind <= 10 for k in range(n_obj))
     vols = (api.Volume * max(1, s.n_volumes))(*[s.volume(i).contents for i in range(s.n_volumes)])
-    all_mats = np.array([mat(f.materials[i]) for i in range(f.n_materials)] + [[0] * 13], np.float32) if False else None
     kind = np.array([f.objects[k].kind for k in range(n_obj)], np.int32)
     p12 = np.array([list(f.objects[k].p) for k in range(n_obj)], np.float32)
 
-    def mat(m):
-        return list(m.albedo) + [m.specular, m.reflectivity] + list(m.emission) + [m.transparency, m.ior] + list(m.transmission)
+    import ref_binding
+    ref_binding.set_textures(ref, s)
+    mat = ref_binding.mat13
     ma = np.array([mat(f.materials[max(0, f.objects[k].mat_a)]) for k in range(n_obj)], np.float32)
     mb = np.array([mat(f.materials[max(0, f.objects[k].mat_b)]) for k in range(n_obj)], np.float32)
     cs = np.array([f.objects[k].checker_scale for k in range(n_obj)], np.float32)
@@ -422,13 +463,13 @@ def test_trace_stage_equals_the_reference_source(ref, scene, fb_w, fb_h, ss, pos
     meshes = [np.ascontiguousarray(s.mesh_triangles(i), np.float32) for i in range(s.n_meshes)]
     mesh_n = np.array([len(m) for m in meshes] + [0], np.int32)
     mesh_ptrs = (C.c_void_p * max(1, len(meshes)))(*[m.ctypes.data for m in meshes])
-    mesh_mat = np.array([mat(s.mesh(i).contents.material) for i in range(s.n_meshes)] + [[0] * 13], np.float32)
+    mesh_mat = np.array([mat(s.mesh(i).contents.material) for i in range(s.n_meshes)] + ref_binding.MAT_PAD, np.float32)
     lights = np.array([list(f.lights[i].pos) + list(f.lights[i].color) + [f.lights[i].intensity] for i in range(f.n_lights)] + [[0] * 7], np.float32)
     top, bot = np.array(list(f.bg_top), np.float32), np.array(list(f.bg_bottom), np.float32)
     amb = np.array(list(f.ambient_color) + [f.ambient_intensity], np.float32)
     cam = pose if pose is not None else s.default_camera()[:3]
     fov = s.default_camera()[3]
-    all_mats = np.array([mat(f.materials[i]) for i in range(f.n_materials)] + [[0] * 13], np.float32)
+    all_mats = np.array([mat(f.materials[i]) for i in range(f.n_materials)] + ref_binding.MAT_PAD, np.float32)
     h = ref.ref_trace_create(fb_w, fb_h, ss, fov, n_obj, P(kind), P(p12), P(ma), P(mb), P(cs), P(sp), P(rf), P(mesh_n), mesh_ptrs, P(mesh_mat), f.n_lights, P(lights), P(top), P(bot), P(amb),
                              s.n_volumes, C.cast(vols, C.c_void_p), f.n_materials, P(all_mats), f.is_volume_scene)
     assert h
