@@ -17,7 +17,8 @@ What is transpiled (and then compared with the oracle, bit for bit, by tests/tes
   CosineSampleHemisphere), RayTracing/ToneMapper.cs (whole), Renderer/Chexel.cs (whole), the ANSI-256 quantiser of
   Renderer/ANSITerminalRenderer.cs and its Render with the Append* helpers (the byte stream), RayTracing/TemporalAA.cs (constructor,
   ShouldResetHistory, CommitCamera, Resize), RayTracing/MeshLoader.cs (whole) with MeshScenes.TryReadObjBoundsNormalized and the
-  ground placement of AddMeshAutoGround, and of RayTracing/RaytraceRenderer.cs: Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
+  ground placement of AddMeshAutoGround, Renderer/Texture.cs (SampleBilinear on static images) with Renderer/RGBA32.cs, Rng.cs,
+  Win32TerminalRenderer.MapAttributes, and of RayTracing/RaytraceRenderer.cs: Resize, Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
   the BSDF helpers, and -- verbatim -- the tail of TryFlipAndBlit from the TAA call to the cell loop (:218-264), i.e. the
   reference's own buffer juggling, including the swap at :718 that makes the second a-trous iteration run in place.
 """
