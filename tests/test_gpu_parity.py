@@ -127,7 +127,8 @@ def test_both_forms_of_the_in_place_pass_agree_at_full_size():
 
 # ------------------------------------------------------------------------------------------- the reference's own source, no oracle in between
 REF_CASES = [("cornell", 40, 12, 2, None), ("mirror_spheres", 48, 14, 2, None), ("cylinders_disks_triangles", 32, 10, 2, None), ("teapot", 40, 12, 2, api.BENCH_POSE),
-             ("knot:60x16", 36, 10, 3, api.BENCH_POSE), ("volume_grid_test", 40, 12, 2, None), ("voxel_world:64x64", 36, 10, 2, None)]
+             ("knot:60x16", 36, 10, 3, api.BENCH_POSE), ("volume_grid_test", 40, 12, 2, None), ("voxel_world:64x64", 36, 10, 2, None),
+             ("texture_gallery", 48, 14, 2, None)]  # SampleAlbedo -> Texture.SampleBilinear of the reference's text on rects, box faces, a triangle, a mesh, glass
 
 
 @pytest.mark.parametrize("case", REF_CASES, ids=[c[0] for c in REF_CASES])
