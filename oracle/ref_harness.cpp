@@ -125,6 +125,19 @@ RH_API void ref_sample_albedo(const float *albedo3, double texture_weight, doubl
     const Vec3 c = RendererRef::SampleAlbedo(m, Vec3(0.0f, 0.0f, 0.0f), Vec3(0.0f, 1.0f, 0.0f), u, v);
     out3[0] = c.X; out3[1] = c.Y; out3[2] = c.Z;
 }
+// The island generator as the reference wrote it: BuildMinecraftLike's WorldConfig (VolumeScenes.cs:579-591: chunks of 32, worldMin (-size/2, 0, -size/2),
+// unit voxels, seed 0) for a world of size x height x size, then the three passes of WorldManager.GenerateAndSaveWorld (heights + rivers, voxel fill,
+// flora).  ids / metas: [x][y][z], size * height * size ints each.
+RH_API int ref_generate_island(int world_size, int world_height, int *ids, int *metas) {
+    try {
+        const int chunk = 32;
+        WorldConfig cfg(chunk, world_size / chunk, world_height / chunk, world_size / chunk, 8, Vec3(-world_size / 2, 0, -world_size / 2), Vec3(1, 1, 1), 0);
+        Array3<Cell2> cells = WorldGenRef::GenerateCells(cfg);
+        const size_t n = (size_t)cells.n0 * cells.n1 * cells.n2;
+        for (size_t i = 0; i < n; i++) { ids[i] = (*cells.p)[i].Item1; metas[i] = (*cells.p)[i].Item2; }
+        return 0;
+    } catch (...) { return -1; }
+}
 RH_API int ref_map_attributes(int fg16, int bg16) { return (int)Win32Ref::MapAttributes((ConsoleColor)fg16, (ConsoleColor)bg16); } // Win32TerminalRenderer.cs:109-112
 // ANSITerminalRenderer.Render (:86-153) over one Framebuffer of fb_w x fb_h cells (row-major glyph / fg rgb / bg rgb) placed at (vx, vy) on a
 // console of console_w x console_h cells; the renderer believes the console to be known_w x known_h (differs -> the resize prologue).

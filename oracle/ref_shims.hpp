@@ -47,6 +47,8 @@ struct MathF {
     static float Abs(float a) { return std::fabs(a); }
     static float Sqrt(float a) { return std::sqrt(a); }
     static float Floor(float a) { return std::floor(a); }
+    static float Ceiling(float a) { return std::ceil(a); }
+    static float Round(float a) { return std::nearbyintf(a); } // MidpointRounding.ToEven under the default rounding mode
     static float CopySign(float a, float b) { return std::copysign(a, b); }
     static float Exp(float a) { return ycge_expf(a); }
     static float Log(float a) { return ycge_logf(a); }
@@ -61,6 +63,8 @@ struct Math {
     static int Min(int a, int b) { return a < b ? a : b; }
     static double Max(double a, double b) { if (a != b) return (a != a) ? a : (b < a ? a : b); return std::signbit(b) ? a : b; }
     static double Min(double a, double b) { if (a != b) return (a != a) ? a : (a < b ? a : b); return std::signbit(a) ? a : b; }
+    static float Max(float a, float b) { if (a != b) return (a != a) ? a : (b < a ? a : b); return std::signbit(b) ? a : b; }   // Math.Max(float, float): C# keeps binary32
+    static float Min(float a, float b) { if (a != b) return (a != a) ? a : (a < b ? a : b); return std::signbit(a) ? a : b; }
     static int Abs(int a) { return a < 0 ? -a : a; }
     static double Abs(double a) { return std::fabs(a); }
     static double Round(double a) { return std::nearbyint(a); } // MidpointRounding.ToEven, the default rounding mode
@@ -214,6 +218,26 @@ template <class T> struct RList {
     T &operator[](int i) const { return (*p)[(size_t)i]; }
 };
 struct Face3 { int a, b, c; }; // the value tuple (int a, int b, int c)
+// ---- WorldGeneration: rectangular arrays (C# arrays are references: copies alias; zero-initialised), the (int, int) block tuple, sbyte
+using sbyte = int8_t;
+struct Cell2 { int Item1 = 0, Item2 = 0; };
+struct OrderItem { int x, z, h; };
+inline int Int32CompareTo(int a, int b) { return a < b ? -1 : (a > b ? 1 : 0); }
+template <class T> struct Array2 {
+    std::shared_ptr<std::vector<T>> p;
+    int n0 = 0, n1 = 0;
+    Array2() {}
+    Array2(int a, int b) : p(new std::vector<T>((size_t)a * b)), n0(a), n1(b) {}
+    T &operator[](int i, int j) const { return (*p)[(size_t)i * n1 + j]; }
+    int GetLength(int d) const { return d == 0 ? n0 : n1; }
+};
+template <class T> struct Array3 {
+    std::shared_ptr<std::vector<T>> p;
+    int n0 = 0, n1 = 0, n2 = 0;
+    Array3() {}
+    Array3(int a, int b, int c) : p(new std::vector<T>((size_t)a * b * c)), n0(a), n1(b), n2(c) {}
+    T &operator[](int i, int j, int k) const { return (*p)[((size_t)i * n1 + j) * n2 + k]; }
+};
 template <class T> using Comparison = std::function<int(const T &, const T &)>;
 inline int SingleCompareTo(float a, float b) { // System.Single.CompareTo
     if (a < b) return -1;
@@ -226,6 +250,7 @@ inline int SingleCompareTo(float a, float b) { // System.Single.CompareTo
 // 16 elements, heap sort at depth 0, else median-of-three partition.  Unstable: the PERMUTATION it produces is part of the reference's
 // behaviour (the builders' fallback split), hence restated here as runtime library.
 struct Array {
+    template <class T, class Cmp> static void Sort(std::vector<T> &keys, Cmp cmp) { Sort(keys, 0, (int)keys.size(), cmp); }                     // Array.Sort(array, comparison): the same introsort
     template <class T> static void Resize(std::vector<T> &a, int n) { a.resize((size_t)n); } // Array.Resize(ref a, n): contents kept, zero-filled tail
     template <class T, class Cmp> static void Sort(std::vector<T> &keys, int index, int length, Cmp cmp) {
         if (length < 2) return;

@@ -18,7 +18,8 @@ What is transpiled (and then compared with the oracle, bit for bit, by tests/tes
   Renderer/ANSITerminalRenderer.cs and its Render with the Append* helpers (the byte stream), RayTracing/TemporalAA.cs (constructor,
   ShouldResetHistory, CommitCamera, Resize), RayTracing/MeshLoader.cs (whole) with MeshScenes.TryReadObjBoundsNormalized and the
   ground placement of AddMeshAutoGround, Renderer/Texture.cs (SampleBilinear on static images) with Renderer/RGBA32.cs, Rng.cs,
-  Win32TerminalRenderer.MapAttributes, and of RayTracing/RaytraceRenderer.cs: Resize, Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
+  Win32TerminalRenderer.MapAttributes, Scenes/WorldGeneration (the island generator: GenMath, TerrainNoise, RiverNetworkGlobal, BiomeMap,
+  Layering, StrataMap, FloraPlacer, settings, WorldConfig, the passes of WorldManager.GenerateAndSaveWorld), and of RayTracing/RaytraceRenderer.cs: Resize, Luma, TemporalBlendWithClamp, ApplyAtrousDenoise,
   the BSDF helpers, and -- verbatim -- the tail of TryFlipAndBlit from the TAA call to the cell loop (:218-264), i.e. the
   reference's own buffer juggling, including the swap at :718 that makes the second a-trous iteration run in place.
 """
@@ -397,6 +398,56 @@ def main(ref, out_path):
     a3, b3 = ag.index("Vec3 mnN, mxN;"), ag.index("s.Objects.Add(")
     msel.append("static Vec3 AutoGroundTranslate(string objPath, float scale, Vec3 targetPos)\n{\n" + ag[a3:b3] + "\n    return translate;\n}\n")
     out.append("struct MeshScenesRef {\n%s\n};\n" % mesh_text("\n".join(msel)))
+    # ---- Scenes/WorldGeneration: the island generator behind BuildMinecraftLike (VolumeScenes.cs:569) -- GenMath, TerrainNoise, BiomeMap, Layering,
+    # StrataMap, RiverNetworkGlobal, FloraPlacer, the settings, WorldConfig, and the three passes of WorldManager.GenerateAndSaveWorld (:510-606,
+    # up to the file writer): every (block id, meta) of the world
+    wg = "RayTracing/Scenes/WorldGeneration/"
+    def nested_static_classes(t):
+        while True:
+            m_ = re.search(r"(?:public |internal )?static class (\w+)\s*\{", t)
+            if not m_:
+                return t
+            b0_ = m_.end() - 1
+            e0_ = block_end(t, b0_)
+            t = t[:m_.start()] + "struct " + m_.group(1) + " {" + t[b0_ + 1:e0_] + ";" + t[e0_:]
+    def gen_text(t):
+        t = re.sub(r"Console\.WriteLine\([^;]*\);", "(void)0;", t)                                                                  # progress messages
+        t = re.sub(r"\(int x, int z, int h\)\[\]|var order = new \(int x, int z, int h\)\[([^\]]*)\];", lambda m_: "std::vector<OrderItem> order(%s);" % m_.group(1) if m_.group(1) else "std::vector<OrderItem>", t)
+        t = re.sub(r"order\[k\+\+\] = \((x, z, ground\[x, z\])\);", r"order[k++] = OrderItem{\1};", t)
+        t = re.sub(r"Array\.Sort\(order, \(a, b\) => a\.h\.CompareTo\(b\.h\)\);", "Array::Sort(order, [](const OrderItem &a, const OrderItem &b) { return Int32CompareTo(a.h, b.h); });", t)
+        t = re.sub(r"new \(int, int\)\[(\w+), (\w+), (\w+)\]", r"Array3<Cell2>(\1, \2, \3)", t)
+        t = re.sub(r"\(int, int\)\[,,\] (\w+)", r"Array3<Cell2> \1", t)
+        t = re.sub(r"\(int, int\) (\w+);", r"Cell2 \1;", t)
+        t = re.sub(r"\((WorldGenSettings\.Blocks\.\w+|top|sub), (0|1|meta)\)", r"Cell2{\1, \2}", t)                                    # (id, meta) tuple literals
+        t = re.sub(r"new (\w+)\[(\w+), (\w+)\]", r"Array2<\1>(\2, \3)", t)
+        t = re.sub(r"\bout (\w+)\[,\] (\w+)", r"Array2<\1> &\2", t)
+        t = re.sub(r"\b(\w+)\[,\] (\w+)", r"Array2<\1> \2", t)
+        t = re.sub(r"RiverNetworkGlobal\.Compute\(nx, nz, config, ground, out var carveDepth, out var riverWater\);",
+                   "Array2<float> carveDepth; Array2<int> riverWater;\n            RiverNetworkGlobal::Compute(nx, nz, config, ground, carveDepth, riverWater);", t)
+        t = re.sub(r"static float\[\] (\w+)\(", r"static std::vector<float> \1(", t)
+        t = re.sub(r"return new float\[\] \{", "return std::vector<float>{", t)
+        t = re.sub(r"\(float\[\] g,", "(const std::vector<float> &g,", t)
+        t = re.sub(r"static (\w+) (\w+)\(([^)]*)\) => ([^;]+);", r"static \1 \2(\3) { return \4; }", t)                                   # expression-bodied methods
+        t = re.sub(r"(?:internal|public) enum (\w+)", r"enum \1", t)
+        t = re.sub(r"\bWorldGenSettings\.(\w+)\.(\w+)", r"WorldGenSettings::\1::\2", t)
+        t = rewrite(t, None, statics=("GenMath", "IslandSettings", "TerrainNoise", "BiomeMap", "Layering", "StrataMap", "RiverNetworkGlobal", "FloraPlacer", "Biome"))
+        return t
+    def static_class(path, name):
+        body = nested_static_classes(type_body(rd(path), name))
+        return "struct %s {\n%s\n};\n" % (name, gen_text(body))
+    out.append(static_class(wg + "WorldGenSettings.cs", "WorldGenSettings"))
+    out.append(static_class(wg + "IslandSettings.cs", "IslandSettings"))
+    bsrc = rd(wg + "Biome.cs")
+    out.append(gen_text(bsrc[bsrc.index("internal enum"):bsrc.rindex("}") + 1]) + ";\n")
+    wc = gen_text(type_body(rd(wg + "WorldConfig.cs"), "WorldConfig"))
+    wc = re.sub(r"^(\s*)((?:int|Vec3) \w+);", r"\1\2 = {};", wc, flags=re.M)
+    out.append("struct WorldConfig {\n%s\n};\n" % wc)
+    for fn, nm in (("GenMath.cs", "GenMath"), ("StrataMap.cs", "StrataMap"), ("BiomeMap.cs", "BiomeMap"), ("Layering.cs", "Layering"), ("TerrainNoise.cs", "TerrainNoise"),
+                   ("RiverNetworkGlobal.cs", "RiverNetworkGlobal"), ("FloraPlacer.cs", "FloraPlacer")):
+        out.append(static_class(wg + fn, nm))
+    gsw = [t for t, n in members(type_body(rd(wg + "WorldManager.cs"), "WorldManager")) if n == "GenerateAndSaveWorld"][0]
+    a4, b4 = gsw.index("int nx = config.ChunksX"), gsw.index("// --- Write file ---")
+    out.append("struct WorldGenRef {\nstatic Array3<Cell2> GenerateCells(WorldConfig config)\n{\n" + gen_text(gsw[a4:b4]) + "\n    return worldCells;\n}\n};\n")
     out.append(emit_struct(rd("RayTracing/Objects/PointLight.cs"), "PointLight"))
     out.append(emit_struct(rd("RayTracing/Objects/AmbientLight.cs"), "AmbientLight"))
     ssrc = type_body(rd("RayTracing/Scenes/Scene.cs"), "Scene")

@@ -231,6 +231,33 @@ def test_whole_frames_of_the_reference_source_equal_the_oracle(ref, scene, pose)
     s.close()
 
 
+ISLAND_SIZES = [(64, 128), (96, 128), (256, 256)] + ([(1024, 256)] if os.environ.get("YCGE_FULL_ISLAND") else [])
+
+
+@pytest.mark.parametrize("size,height", ISLAND_SIZES, ids=[f"{a}x{b}" for a, b in ISLAND_SIZES])
+def test_island_generator_equals_the_reference_source(ref, size, height, tmp_path):
+    """BASELINE config 4's world.  The reference's island generator as its authors wrote it -- GenMath (gradient noise, FBM, ridged FBM, the
+    FNV hash), TerrainNoise (domain warp, island mask, heights, inland water), RiverNetworkGlobal (D8 descent, Array.Sort by height,
+    accumulation, carving), BiomeMap, Layering, StrataMap, FloraPlacer (trees, desert props) and the three passes of
+    WorldManager.GenerateAndSaveWorld, with BuildMinecraftLike's WorldConfig -- against the host mirror's generator (the one whose
+    chunk grids are uploaded to the GPU): every (block id, meta) of the world, through the mirror's own VG01 writer.
+    256 x 256 x 256 holds every block kind the full world has (sand, wood, leaves, the three rock metas).  The full 1024 x 256 x 1024
+    world (268 M cells, a minute of CPU and 9 GB) was compared once, equal cell for cell; YCGE_FULL_ISLAND=1 runs it again."""
+    ref.ref_generate_island.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = size * height * size
+    ids, metas = np.empty(n, np.int32), np.empty(n, np.int32)
+    assert ref.ref_generate_island(size, height, P(ids), P(metas)) == 0
+    path = str(tmp_path / "island.vg")
+    assert api.load_host().ycgeh_write_island_world(path.encode(), size, height) == 0
+    assert open(path, "rb").read(4) == b"VG01" and tuple(np.fromfile(path, np.int32, 3, offset=4)) == (size, height, size)   # WorldManager.cs:612-616
+    cells = np.fromfile(path, np.int32, offset=16).reshape(-1, 2)                                                           # x, y, z order, (id, meta) pairs (:617-629)
+    assert len(cells) == n
+    assert np.array_equal(cells[:, 0], ids), f"{int((cells[:, 0] != ids).sum())} block ids differ"
+    assert np.array_equal(cells[:, 1], metas), f"{int((cells[:, 1] != metas).sum())} metas differ"
+    if size >= 256:
+        assert set(np.unique(ids)) >= {0, 1, 2, 3, 4, 5, 6, 7} and set(np.unique(metas)) == {0, 1, 2}
+
+
 def test_texture_sampler_equals_the_reference_source(ref, oracle_lib):
     """Texture.SampleBilinear (static image: wrap by frac, (w - 1) scaling, the % wrap of the +1 texel, RGBA32.toVec3, two Lerps, Saturate)
     and RGBA32's int constructor as the reference wrote them, against the oracle's sampler (which the device's equals on the GPU)."""
