@@ -128,13 +128,14 @@ RH_API void ref_sample_albedo(const float *albedo3, double texture_weight, doubl
 // The island generator as the reference wrote it: BuildMinecraftLike's WorldConfig (VolumeScenes.cs:579-591: chunks of 32, worldMin (-size/2, 0, -size/2),
 // unit voxels, seed 0) for a world of size x height x size, then the three passes of WorldManager.GenerateAndSaveWorld (heights + rivers, voxel fill,
 // flora).  ids / metas: [x][y][z], size * height * size ints each.
-RH_API int ref_generate_island(int world_size, int world_height, int *ids, int *metas) {
+// path != NULL: the reference's own VG01 writer (WorldManager.cs:607-631) writes the world there as well; ids / metas may be NULL then.
+RH_API int ref_generate_island(int world_size, int world_height, int *ids, int *metas, const char *path) {
     try {
         const int chunk = 32;
         WorldConfig cfg(chunk, world_size / chunk, world_height / chunk, world_size / chunk, 8, Vec3(-world_size / 2, 0, -world_size / 2), Vec3(1, 1, 1), 0);
-        Array3<Cell2> cells = WorldGenRef::GenerateCells(cfg);
+        Array3<Cell2> cells = WorldGenRef::GenerateCells(cfg, path ? String(path) : String());
         const size_t n = (size_t)cells.n0 * cells.n1 * cells.n2;
-        for (size_t i = 0; i < n; i++) { ids[i] = (*cells.p)[i].Item1; metas[i] = (*cells.p)[i].Item2; }
+        if (ids && metas) for (size_t i = 0; i < n; i++) { ids[i] = (*cells.p)[i].Item1; metas[i] = (*cells.p)[i].Item2; }
         return 0;
     } catch (...) { return -1; }
 }

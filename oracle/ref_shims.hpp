@@ -187,6 +187,13 @@ struct StreamReader {
         return String(line);
     }
 };
+struct BinaryWriter { // System.IO.BinaryWriter over a new file: Write(char) = the character's UTF-8 bytes, Write(int) = 4 bytes little endian
+    FILE *f;
+    explicit BinaryWriter(const String &p) : f(std::fopen(p.s.c_str(), "wb")) { if (!f) throw std::runtime_error("cannot create file"); }
+    ~BinaryWriter() { if (f) std::fclose(f); }
+    void Write(char c) { std::fputc((unsigned char)c, f); }   // ASCII only here ('V', 'G', '0', '1')
+    void Write(int v) { unsigned char b[4] = {(unsigned char)(v & 255), (unsigned char)((v >> 8) & 255), (unsigned char)((v >> 16) & 255), (unsigned char)((v >> 24) & 255)}; std::fwrite(b, 1, 4, f); }
+};
 template <class Fmt> float SingleParse(const String &t, const Fmt &) { return std::strtof(t.s.c_str(), nullptr); }   // float.Parse(s, invariant): correctly rounded (.NET Core 3.0+), as strtof
 template <class Fmt> int Int32Parse(const String &t, const Fmt &) { return (int)std::strtol(t.s.c_str(), nullptr, 10); }
 template <class T> struct HashSet {

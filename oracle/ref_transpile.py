@@ -447,7 +447,13 @@ def main(ref, out_path):
         out.append(static_class(wg + fn, nm))
     gsw = [t for t, n in members(type_body(rd(wg + "WorldManager.cs"), "WorldManager")) if n == "GenerateAndSaveWorld"][0]
     a4, b4 = gsw.index("int nx = config.ChunksX"), gsw.index("// --- Write file ---")
-    out.append("struct WorldGenRef {\nstatic Array3<Cell2> GenerateCells(WorldConfig config)\n{\n" + gen_text(gsw[a4:b4]) + "\n    return worldCells;\n}\n};\n")
+    # ... and the VG01 writer that follows them (:607-631), verbatim but for the directory creation and the stream constructor
+    wtxt = gsw[b4:gsw.rindex("}")]
+    wtxt = re.sub(r"string dir = Path\.GetDirectoryName\(filename\);", "", wtxt)
+    wtxt = re.sub(r"if \(!string\.IsNullOrEmpty\(dir\) && !Directory\.Exists\(dir\)\) Directory\.CreateDirectory\(dir\);", "", wtxt)
+    wtxt = re.sub(r"using \(var bw = new BinaryWriter\(File\.Open\(filename, FileMode\.Create, FileAccess\.Write, FileShare\.None\)\)\)", "if (BinaryWriter bw(filename); true)", wtxt)
+    out.append("struct WorldGenRef {\nstatic Array3<Cell2> GenerateCells(WorldConfig config, const String &filename = String())\n{\n" + gen_text(gsw[a4:b4])
+               + "\n    if (filename != nullptr) {\n" + gen_text(wtxt) + "\n    }\n    return worldCells;\n}\n};\n")
     out.append(emit_struct(rd("RayTracing/Objects/PointLight.cs"), "PointLight"))
     out.append(emit_struct(rd("RayTracing/Objects/AmbientLight.cs"), "AmbientLight"))
     ssrc = type_body(rd("RayTracing/Scenes/Scene.cs"), "Scene")

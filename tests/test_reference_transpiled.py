@@ -243,10 +243,11 @@ def test_island_generator_equals_the_reference_source(ref, size, height, tmp_pat
     chunk grids are uploaded to the GPU): every (block id, meta) of the world, through the mirror's own VG01 writer.
     256 x 256 x 256 holds every block kind the full world has (sand, wood, leaves, the three rock metas).  The full 1024 x 256 x 1024
     world (268 M cells, a minute of CPU and 9 GB) was compared once, equal cell for cell; YCGE_FULL_ISLAND=1 runs it again."""
-    ref.ref_generate_island.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    ref.ref_generate_island.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p]
     n = size * height * size
     ids, metas = np.empty(n, np.int32), np.empty(n, np.int32)
-    assert ref.ref_generate_island(size, height, P(ids), P(metas)) == 0
+    ref_path = str(tmp_path / "island_ref.vg") if size <= 256 else None   # ... and the reference's own VG01 writer (:607-631): the same file, byte for byte
+    assert ref.ref_generate_island(size, height, P(ids), P(metas), ref_path.encode() if ref_path else None) == 0
     path = str(tmp_path / "island.vg")
     assert api.load_host().ycgeh_write_island_world(path.encode(), size, height) == 0
     assert open(path, "rb").read(4) == b"VG01" and tuple(np.fromfile(path, np.int32, 3, offset=4)) == (size, height, size)   # WorldManager.cs:612-616
@@ -256,6 +257,8 @@ def test_island_generator_equals_the_reference_source(ref, size, height, tmp_pat
     assert np.array_equal(cells[:, 1], metas), f"{int((cells[:, 1] != metas).sum())} metas differ"
     if size >= 256:
         assert set(np.unique(ids)) >= {0, 1, 2, 3, 4, 5, 6, 7} and set(np.unique(metas)) == {0, 1, 2}
+    if ref_path:
+        assert open(ref_path, "rb").read() == open(path, "rb").read(), "VG01 file of the mirror's writer differs from the reference writer's"
 
 
 def test_texture_sampler_equals_the_reference_source(ref, oracle_lib):
